@@ -1,0 +1,72 @@
+"""ctypes binding of libcocodr_b200.so (the C ABI in include/cocodr_b200.h).
+
+Fails loudly: a missing library or a missing symbol raises -- there is no fallback path.
+"""
+import ctypes as C
+import os
+import re
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcocodr_b200.so")
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "cocodr_b200.h")
+
+_lib = None
+
+# epilogue enum (keep in sync with include/cocodr_b200.h)
+EPI_STORE_F16, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_DGELU, EPI_F32_ATOMIC, EPI_F32_STORE, EPI_SCAN_FILTER = range(7)
+CDR_EOVERFLOW = -5
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [("a", C.c_void_p), ("b", C.c_void_p), ("out", C.c_void_p), ("out2", C.c_void_p),
+                ("bias", C.c_void_p), ("aux", C.c_void_p),
+                ("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64),
+                ("lda", C.c_int64), ("ldb", C.c_int64), ("ldo", C.c_int64), ("ldaux", C.c_int64),
+                ("a_major", C.c_int32), ("b_major", C.c_int32), ("epilogue", C.c_int32), ("split_k", C.c_int32),
+                ("alpha", C.c_float), ("dbg_lbo", C.c_int32), ("dbg_sbo", C.c_int32)]
+
+
+def declared_symbols():
+    """Every function the public header declares (used by the CPU export test)."""
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(cdr_[a-z0-9_]+)\s*\(", txt)))
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python __graft_entry__.py` (nvcc, sm_100a). "
+            "cocodr_b200 has no CPU / PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    missing = [s for s in declared_symbols() if not hasattr(lib, s)]
+    if missing:
+        raise RuntimeError(f"libcocodr_b200.so does not export: {missing}")
+    lib.cdr_last_error.restype = C.c_char_p
+    lib.cdr_version.restype = C.c_int
+    for name in declared_symbols():
+        fn = getattr(lib, name)
+        if name.endswith("_bytes"):
+            fn.restype = C.c_size_t
+        elif name != "cdr_last_error":
+            fn.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().cdr_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"cocodr_b200 {what} failed (code {rc}): {msg}")
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())

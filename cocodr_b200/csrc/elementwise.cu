@@ -1,0 +1,410 @@
+// Memory-bound kernels of the encoder: embedding gather + LayerNorm (K1), LayerNorm fwd/bwd over
+// fp16 activations (the LN halves of K4/K6), column sums for bias gradients, fp32->fp16 casts.
+// One warp per row, 16-byte vector accesses, fp32 statistics.  hidden % 8 == 0, hidden <= 1024 * 2.
+#include "cdr_common.cuh"
+
+namespace cdr {
+
+constexpr int LN_WARPS = 4;
+constexpr int MAX_VPL = 8;  // vectors (of 8 elements) per lane -> hidden <= 2048
+
+__device__ __forceinline__ void load8_h(const __half* p, float (&v)[8]) {
+  const uint4 q = *reinterpret_cast<const uint4*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float2 f = __half22float2(h[t]);
+    v[2 * t] = f.x;
+    v[2 * t + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void store8_h(__half* p, const float (&v)[8]) {
+  uint4 q;
+  __half2* h = reinterpret_cast<__half2*>(&q);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) h[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
+  *reinterpret_cast<uint4*>(p) = q;
+}
+__device__ __forceinline__ void load8_f(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p + 4));
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void store8_f(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void atomic_add8(float* p, const float (&v)[8]) {
+  atomicAdd(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+  atomicAdd(reinterpret_cast<float4*>(p + 4), make_float4(v[4], v[5], v[6], v[7]));
+}
+
+// Row statistics from register-resident values (two-pass: mean, then centred variance).
+template <int VPL>
+__device__ __forceinline__ void row_stats(const float (&x)[VPL][8], int nvec, int lane, int hidden, float eps,
+                                          float& mean, float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+    if (lane + 32 * i < nvec)
+#pragma unroll
+      for (int t = 0; t < 8; ++t) s += x[i][t];
+  mean = warp_sum(s) / hidden;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+    if (lane + 32 * i < nvec)
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const float d = x[i][t] - mean;
+        q += d * d;
+      }
+  rstd = rsqrtf(warp_sum(q) / hidden + eps);
+}
+
+// ------------------------------------------------------------------------------------------ fwd
+// MODE 0: x = fp16 activations.  MODE 1: x = word[id] + pos[l] + type0 (fp32 tables).
+template <int VPL, int MODE>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+ln_fwd_kernel(const __half* __restrict__ x, const int64_t* __restrict__ ids, const float* __restrict__ word,
+              const float* __restrict__ pos, const float* __restrict__ type0, const float* __restrict__ gamma,
+              const float* __restrict__ beta, __half* __restrict__ y, float* __restrict__ mean_out,
+              float* __restrict__ rstd_out, float* __restrict__ cls_out, int rows, int hidden, int seq_len,
+              int vocab, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = hidden >> 3;
+  float v[VPL][8];
+  if constexpr (MODE == 0) {
+#pragma unroll
+    for (int i = 0; i < VPL; ++i)
+      if (lane + 32 * i < nvec) load8_h(x + static_cast<long long>(row) * hidden + 8 * (lane + 32 * i), v[i]);
+  } else {
+    long long id = ids[row];
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    const int l = row % seq_len;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i)
+      if (lane + 32 * i < nvec) {
+        const int c = 8 * (lane + 32 * i);
+        float a[8], b[8], t[8];
+        load8_f(word + id * hidden + c, a);
+        load8_f(pos + static_cast<long long>(l) * hidden + c, b);
+        load8_f(type0 + c, t);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[i][k] = (a[k] + t[k]) + b[k];  // HF order: (word + type) + pos
+      }
+  }
+  float mean, rstd;
+  row_stats<VPL>(v, nvec, lane, hidden, eps, mean, rstd);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+  const bool is_cls = cls_out != nullptr && (row % seq_len) == 0;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+    if (lane + 32 * i < nvec) {
+      const int c = 8 * (lane + 32 * i);
+      float g[8], b[8], o[8];
+      load8_f(gamma + c, g);
+      load8_f(beta + c, b);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = (v[i][k] - mean) * rstd * g[k] + b[k];
+      store8_h(y + static_cast<long long>(row) * hidden + c, o);
+      if (is_cls) store8_f(cls_out + static_cast<long long>(row / seq_len) * hidden + c, o);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ bwd
+// Block (l, split): position l, sequences split, split+gridDim.y, ...  (rows = seq*seq_len + l), so
+// that the position-embedding gradient of MODE 1 reduces inside the block.  For MODE 0 the same
+// mapping is used (any row partition works for the column sums).
+// Column sums (dgamma, dbeta, dcol = sum of dx) are reduced warp-registers -> smem -> atomics.
+template <int VPL, int MODE>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+ln_bwd_kernel(const __half* __restrict__ dy, const __half* __restrict__ x, const int64_t* __restrict__ ids,
+              const float* __restrict__ word, const float* __restrict__ pos, const float* __restrict__ type0,
+              const float* __restrict__ gamma, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+              const float* __restrict__ dy_cls, __half* __restrict__ dx, float* __restrict__ dgamma,
+              float* __restrict__ dbeta, float* __restrict__ dcol, float* __restrict__ dword, float* __restrict__ dpos,
+              int n_seq, int hidden, int seq_len, int vocab, int pad_id, float in_scale, float out_scale) {
+  extern __shared__ float red[];  // [3][hidden]
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int l = blockIdx.x;
+  const int nvec = hidden >> 3;
+  float a_dg[VPL][8], a_db[VPL][8], a_dc[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a_dg[i][k] = a_db[i][k] = a_dc[i][k] = 0.f;
+  float g[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+    if (lane + 32 * i < nvec) load8_f(gamma + 8 * (lane + 32 * i), g[i]);
+
+  for (int seq = blockIdx.y * LN_WARPS + warp; seq < n_seq; seq += gridDim.y * LN_WARPS) {
+    const long long row = static_cast<long long>(seq) * seq_len + l;
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float xh[VPL][8], gy[VPL][8];
+    long long id = 0;
+    if constexpr (MODE == 1) {
+      id = ids[row];
+      id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    }
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i)
+      if (lane + 32 * i < nvec) {
+        const int c = 8 * (lane + 32 * i);
+        float xv[8], d[8];
+        if constexpr (MODE == 0) {
+          load8_h(x + row * hidden + c, xv);
+        } else {
+          float a[8], b[8], t[8];
+          load8_f(word + id * hidden + c, a);
+          load8_f(pos + static_cast<long long>(l) * hidden + c, b);
+          load8_f(type0 + c, t);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) xv[k] = (a[k] + t[k]) + b[k];
+        }
+        if (dy != nullptr) {
+          load8_h(dy + row * hidden + c, d);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) d[k] *= in_scale;
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) d[k] = 0.f;
+        }
+        if (dy_cls != nullptr && l == 0) {  // fp32 gradient of the CLS embedding output
+          float e[8];
+          load8_f(dy_cls + static_cast<long long>(seq) * hidden + c, e);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) d[k] += e[k] * in_scale;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          xh[i][k] = (xv[k] - mean) * rstd;
+          gy[i][k] = d[k] * g[i][k];
+          s1 += gy[i][k];
+          s2 += gy[i][k] * xh[i][k];
+          a_dg[i][k] += d[k] * xh[i][k];
+          a_db[i][k] += d[k];
+        }
+      }
+    const float c1 = warp_sum(s1) / hidden;
+    const float c2 = warp_sum(s2) / hidden;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i)
+      if (lane + 32 * i < nvec) {
+        const int c = 8 * (lane + 32 * i);
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          o[k] = rstd * (gy[i][k] - c1 - xh[i][k] * c2);
+          a_dc[i][k] += o[k];
+        }
+        if constexpr (MODE == 0) {
+          store8_h(dx + row * hidden + c, o);
+        } else {
+          if (id != pad_id) {
+            float w[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) w[k] = o[k] * out_scale;
+            atomic_add8(dword + id * hidden + c, w);
+          }
+        }
+      }
+  }
+  // block reduction of the three column accumulators, one at a time through smem
+  auto reduce_to = [&](float (&acc)[VPL][8], float* dst, long long dst_off) {
+    if (dst == nullptr) return;
+    __syncthreads();
+    for (int i = threadIdx.x; i < hidden; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < VPL; ++i)
+      if (lane + 32 * i < nvec)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) atomicAdd(&red[8 * (lane + 32 * i) + k], acc[i][k]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < hidden; i += blockDim.x) atomicAdd(dst + dst_off + i, red[i] * out_scale);
+  };
+  reduce_to(a_dg, dgamma, 0);
+  reduce_to(a_db, dbeta, 0);
+  if constexpr (MODE == 0) {
+    reduce_to(a_dc, dcol, 0);
+  } else {
+    reduce_to(a_dc, dcol, 0);                                       // token_type_embeddings row 0
+    reduce_to(a_dc, dpos, static_cast<long long>(l) * hidden);      // position row l
+  }
+}
+
+// out[c] += scale * sum_r x[r, c]      (fp16 in, fp32 accumulate; bias gradients)
+__global__ void __launch_bounds__(256)
+colsum_kernel(const __half* __restrict__ x, float* __restrict__ out, int rows, int cols, long long ld, float scale,
+              int rows_per_block) {
+  // thread handles 8 columns; blockDim.x threads cover cols in strides; blockIdx.y picks the row slab
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (c >= cols) return;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(r0 + rows_per_block, rows);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int r = r0; r < r1; ++r) {
+    float v[8];
+    load8_h(x + static_cast<long long>(r) * ld + c, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] += v[k];
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] *= scale;
+  atomic_add8(out + c, acc);
+}
+
+__global__ void cast_f32_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long n) {
+  long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    float v[8];
+    load8_f(src + i, v);
+    store8_h(dst + i, v);
+  } else {
+    for (; i < n; ++i) dst[i] = __float2half_rn(src[i]);
+  }
+}
+
+template <int MODE>
+static int launch_ln_fwd(const __half* x, const int64_t* ids, const float* word, const float* pos, const float* type0,
+                         const float* gamma, const float* beta, __half* y, float* mean, float* rstd, float* cls_out,
+                         int rows, int hidden, int seq_len, int vocab, float eps, cudaStream_t st) {
+  const int nvec = hidden / 8;
+  const int vpl = (nvec + 31) / 32;
+  const dim3 grid((rows + LN_WARPS - 1) / LN_WARPS), block(LN_WARPS * 32);
+#define LN_FWD(V)                                                                                             \
+  ln_fwd_kernel<V, MODE><<<grid, block, 0, st>>>(x, ids, word, pos, type0, gamma, beta, y, mean, rstd, cls_out, \
+                                                 rows, hidden, seq_len, vocab, eps)
+  if (vpl <= 1) LN_FWD(1);
+  else if (vpl <= 2) LN_FWD(2);
+  else if (vpl <= 3) LN_FWD(3);
+  else if (vpl <= 4) LN_FWD(4);
+  else LN_FWD(8);
+#undef LN_FWD
+  CDR_LAUNCH_CHECK();
+  return CDR_OK;
+}
+
+template <int MODE>
+static int launch_ln_bwd(const __half* dy, const __half* x, const int64_t* ids, const float* word, const float* pos,
+                         const float* type0, const float* gamma, const float* mean, const float* rstd,
+                         const float* dy_cls, __half* dx, float* dgamma, float* dbeta, float* dcol, float* dword,
+                         float* dpos, int n_seq, int hidden, int seq_len, int vocab, int pad_id, float in_scale,
+                         float out_scale, cudaStream_t st) {
+  const int nvec = hidden / 8;
+  const int vpl = (nvec + 31) / 32;
+  // aim for ~4 waves of blocks: grid.x = seq_len positions, grid.y = sequence splits
+  int ysplit = (4 * sm_count() + seq_len - 1) / seq_len;
+  const int max_split = (n_seq + LN_WARPS - 1) / LN_WARPS;
+  if (ysplit > max_split) ysplit = max_split;
+  if (ysplit < 1) ysplit = 1;
+  const dim3 grid(seq_len, ysplit), block(LN_WARPS * 32);
+  const size_t smem = sizeof(float) * hidden;
+#define LN_BWD(V)                                                                                                 \
+  ln_bwd_kernel<V, MODE><<<grid, block, smem, st>>>(dy, x, ids, word, pos, type0, gamma, mean, rstd, dy_cls, dx,    \
+                                                    dgamma, dbeta, dcol, dword, dpos, n_seq, hidden, seq_len, vocab, \
+                                                    pad_id, in_scale, out_scale)
+  if (vpl <= 1) LN_BWD(1);
+  else if (vpl <= 2) LN_BWD(2);
+  else if (vpl <= 3) LN_BWD(3);
+  else if (vpl <= 4) LN_BWD(4);
+  else LN_BWD(8);
+#undef LN_BWD
+  CDR_LAUNCH_CHECK();
+  return CDR_OK;
+}
+
+static int check_hidden(int hidden) {
+  CDR_REQUIRE(hidden > 0 && hidden % 8 == 0 && hidden <= 32 * 8 * MAX_VPL, "hidden must be a multiple of 8 and <= %d (got %d)",
+              32 * 8 * MAX_VPL, hidden);
+  return CDR_OK;
+}
+
+}  // namespace cdr
+
+using namespace cdr;
+
+extern "C" {
+
+int cdr_embed_ln_fwd(const int64_t* ids, const float* word, const float* pos, const float* type0, const float* gamma,
+                     const float* beta, void* out, float* mean, float* rstd, int32_t n_seq, int32_t seq_len,
+                     int32_t hidden, int32_t vocab, float eps, void* stream) {
+  if (int rc = check_hidden(hidden)) return rc;
+  CDR_REQUIRE(ids && word && pos && type0 && gamma && beta && out, "cdr_embed_ln_fwd: null pointer");
+  if (n_seq <= 0 || seq_len <= 0) return CDR_OK;
+  return launch_ln_fwd<1>(nullptr, ids, word, pos, type0, gamma, beta, static_cast<__half*>(out), mean, rstd, nullptr,
+                          n_seq * seq_len, hidden, seq_len, vocab, eps, static_cast<cudaStream_t>(stream));
+}
+
+int cdr_embed_ln_bwd(const void* dy, const int64_t* ids, const float* word, const float* pos, const float* type0,
+                     const float* gamma, const float* mean, const float* rstd, float* dword, float* dpos, float* dtype0,
+                     float* dgamma, float* dbeta, int32_t n_seq, int32_t seq_len, int32_t hidden, int32_t vocab,
+                     int32_t pad_id, float in_scale, float out_scale, void* stream) {
+  if (int rc = check_hidden(hidden)) return rc;
+  CDR_REQUIRE(dy && ids && word && pos && type0 && gamma && mean && rstd && dword && dpos && dtype0 && dgamma && dbeta,
+              "cdr_embed_ln_bwd: null pointer");
+  if (n_seq <= 0 || seq_len <= 0) return CDR_OK;
+  return launch_ln_bwd<1>(static_cast<const __half*>(dy), nullptr, ids, word, pos, type0, gamma, mean, rstd, nullptr,
+                          nullptr, dgamma, dbeta, dtype0, dword, dpos, n_seq, hidden, seq_len, vocab, pad_id, in_scale,
+                          out_scale, static_cast<cudaStream_t>(stream));
+}
+
+int cdr_ln_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, float* cls_out,
+               int32_t n_seq, int32_t seq_len, int32_t hidden, float eps, void* stream) {
+  if (int rc = check_hidden(hidden)) return rc;
+  CDR_REQUIRE(x && gamma && beta && y, "cdr_ln_fwd: null pointer");
+  if (n_seq <= 0 || seq_len <= 0) return CDR_OK;
+  return launch_ln_fwd<0>(static_cast<const __half*>(x), nullptr, nullptr, nullptr, nullptr, gamma, beta,
+                          static_cast<__half*>(y), mean, rstd, cls_out, n_seq * seq_len, hidden, seq_len, 0, eps,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int cdr_ln_bwd(const void* dy, const float* dy_cls, const void* x, const float* gamma, const float* mean,
+               const float* rstd, void* dx, float* dgamma, float* dbeta, float* dbias, int32_t n_seq, int32_t seq_len,
+               int32_t hidden, float in_scale, float out_scale, void* stream) {
+  if (int rc = check_hidden(hidden)) return rc;
+  CDR_REQUIRE((dy || dy_cls) && x && gamma && mean && rstd && dx, "cdr_ln_bwd: null pointer");
+  if (n_seq <= 0 || seq_len <= 0) return CDR_OK;
+  return launch_ln_bwd<0>(static_cast<const __half*>(dy), static_cast<const __half*>(x), nullptr, nullptr, nullptr,
+                          nullptr, gamma, mean, rstd, dy_cls, static_cast<__half*>(dx), dgamma, dbeta, dbias, nullptr,
+                          nullptr, n_seq, hidden, seq_len, 0, -1, in_scale, out_scale,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int cdr_colsum_f16(const void* x, float* out, int64_t rows, int64_t cols, int64_t ld, float scale, void* stream) {
+  CDR_REQUIRE(x && out, "cdr_colsum_f16: null pointer");
+  CDR_REQUIRE(cols % 8 == 0 && ld % 8 == 0, "cdr_colsum_f16: cols and ld must be multiples of 8");
+  if (rows <= 0 || cols <= 0) return CDR_OK;
+  const int threads = 128;
+  const int gx = static_cast<int>((cols / 8 + threads - 1) / threads);
+  int rpb = static_cast<int>((rows + 4 * sm_count() - 1) / (4 * sm_count()));
+  if (rpb < 32) rpb = 32;
+  const int gy = static_cast<int>((rows + rpb - 1) / rpb);
+  colsum_kernel<<<dim3(gx, gy), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), out, static_cast<int>(rows), static_cast<int>(cols), ld, scale, rpb);
+  CDR_LAUNCH_CHECK();
+  return CDR_OK;
+}
+
+int cdr_cast_f32_f16(const float* src, void* dst, int64_t n, void* stream) {
+  CDR_REQUIRE(src && dst, "cdr_cast_f32_f16: null pointer");
+  CDR_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+              "cdr_cast_f32_f16: pointers must be 16-byte aligned");
+  if (n <= 0) return CDR_OK;
+  const long long threads = (n + 7) / 8;
+  cast_f32_f16_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<__half*>(dst), n);
+  CDR_LAUNCH_CHECK();
+  return CDR_OK;
+}
+
+}  // extern "C"

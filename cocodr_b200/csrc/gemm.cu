@@ -1,0 +1,123 @@
+// cdr_gemm: host-side validation, TMA map construction and kernel dispatch for the tcgen05 GEMM.
+#include "gemm_sm100.cuh"
+#include "tma_host.h"
+
+namespace cdr {
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI>;
+  constexpr int smem = GemmSmem<BN>::TOTAL;
+  static bool configured = false;  // per-instantiation; attribute is sticky per device context
+  if (!configured) {
+    CDR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int items = p.m_tiles * p.n_tiles * p.split_k;
+  const int grid = items < sm_count() ? items : sm_count();
+  kern<<<grid, GEMM_THREADS, smem, st>>>(ta, tb, p);
+  CDR_LAUNCH_CHECK();
+  return CDR_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  switch (epi) {
+    case CDR_EPI_STORE_F16: return launch_gemm<BN, A_MN, B_MN, CDR_EPI_STORE_F16>(ta, tb, p, st);
+    case CDR_EPI_BIAS_RESIDUAL: return launch_gemm<BN, A_MN, B_MN, CDR_EPI_BIAS_RESIDUAL>(ta, tb, p, st);
+    case CDR_EPI_F32_STORE: return launch_gemm<BN, A_MN, B_MN, CDR_EPI_F32_STORE>(ta, tb, p, st);
+    default: break;
+  }
+  if constexpr (!A_MN && !B_MN) {
+    if (epi == CDR_EPI_BIAS_GELU) return launch_gemm<BN, false, false, CDR_EPI_BIAS_GELU>(ta, tb, p, st);
+    if (epi == CDR_EPI_SCAN_FILTER) return launch_gemm<BN, false, false, CDR_EPI_SCAN_FILTER>(ta, tb, p, st);
+  }
+  if constexpr (!A_MN && B_MN) {
+    if (epi == CDR_EPI_DGELU) return launch_gemm<BN, false, true, CDR_EPI_DGELU>(ta, tb, p, st);
+  }
+  if constexpr (A_MN && B_MN) {
+    if (epi == CDR_EPI_F32_ATOMIC) return launch_gemm<BN, true, true, CDR_EPI_F32_ATOMIC>(ta, tb, p, st);
+  }
+  set_error("cdr_gemm: epilogue %d not instantiated for layout a_major=%d b_major=%d", epi, (int)A_MN, (int)B_MN);
+  return CDR_EINVAL;
+}
+
+template <int BN>
+static int dispatch_layout(int a_mn, int b_mn, int epi, const CUtensorMap& ta, const CUtensorMap& tb,
+                           const GemmParams& p, cudaStream_t st) {
+  if (!a_mn && !b_mn) return dispatch_epi<BN, false, false>(epi, ta, tb, p, st);
+  if (!a_mn && b_mn) return dispatch_epi<BN, false, true>(epi, ta, tb, p, st);
+  if (a_mn && b_mn) return dispatch_epi<BN, true, true>(epi, ta, tb, p, st);
+  set_error("cdr_gemm: layout a_major=1,b_major=0 not instantiated");
+  return CDR_EINVAL;
+}
+
+int gemm_run(const cdr_gemm_args& g, GemmParams p, cudaStream_t st) {
+  CDR_REQUIRE(g.a && g.b, "cdr_gemm: null operand");
+  CDR_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "cdr_gemm: empty problem M=%lld N=%lld K=%lld", (long long)g.M,
+              (long long)g.N, (long long)g.K);
+  CDR_REQUIRE(g.N % 8 == 0 && g.K % 8 == 0, "cdr_gemm: N and K must be multiples of 8 (N=%lld K=%lld)",
+              (long long)g.N, (long long)g.K);
+  CDR_REQUIRE(g.M < (1ll << 31) && g.N < (1ll << 31) && g.K < (1ll << 31), "cdr_gemm: dimension overflow");
+  const int a_mn = g.a_major, b_mn = g.b_major;
+  if (a_mn) CDR_REQUIRE(g.M % 64 == 0, "cdr_gemm: MN-major A needs M %% 64 == 0 (M=%lld)", (long long)g.M);
+  if (b_mn) CDR_REQUIRE(g.N % 64 == 0, "cdr_gemm: MN-major B needs N %% 64 == 0 (N=%lld)", (long long)g.N);
+  const int BN = (g.N > 128) ? 256 : 128;
+  p.M = (int)g.M; p.N = (int)g.N; p.K = (int)g.K;
+  p.m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
+  p.n_tiles = (p.N + BN - 1) / BN;
+  const int total_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+  int split = g.split_k;
+  if (split <= 0) {
+    // auto: enough work items to fill the machine, at least 4 k-blocks per split
+    const int tiles = p.m_tiles * p.n_tiles;
+    split = (2 * sm_count() + tiles - 1) / tiles;
+    if (split > total_kb / 4) split = total_kb / 4;
+    if (split < 1) split = 1;
+  }
+  if (split > total_kb) split = total_kb;
+  p.kb_per_split = (total_kb + split - 1) / split;
+  p.split_k = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
+  CDR_REQUIRE(p.split_k == 1 || g.epilogue == CDR_EPI_F32_ATOMIC, "cdr_gemm: split_k > 1 needs CDR_EPI_F32_ATOMIC");
+  p.alpha = g.alpha;
+  p.dbg_lbo = g.dbg_lbo; p.dbg_sbo = g.dbg_sbo;
+
+  CUtensorMap ta, tb;
+  int rc;
+  if (a_mn) rc = make_tma_2d_f16(&ta, g.a, g.M, g.K, g.lda, 64, GEMM_BK);
+  else rc = make_tma_2d_f16(&ta, g.a, g.K, g.M, g.lda, GEMM_BK, GEMM_BM);
+  if (rc != CDR_OK) return rc;
+  if (b_mn) rc = make_tma_2d_f16(&tb, g.b, g.N, g.K, g.ldb, 64, GEMM_BK);
+  else rc = make_tma_2d_f16(&tb, g.b, g.K, g.N, g.ldb, GEMM_BK, BN);
+  if (rc != CDR_OK) return rc;
+
+  if (BN == 256) return dispatch_layout<256>(a_mn, b_mn, g.epilogue, ta, tb, p, st);
+  return dispatch_layout<128>(a_mn, b_mn, g.epilogue, ta, tb, p, st);
+}
+
+}  // namespace cdr
+
+extern "C" int cdr_gemm(const cdr_gemm_args* g, void* stream) {
+  if (g == nullptr) {
+    cdr::set_error("cdr_gemm: null args");
+    return CDR_EINVAL;
+  }
+  CDR_REQUIRE(g->epilogue != CDR_EPI_SCAN_FILTER, "cdr_gemm: CDR_EPI_SCAN_FILTER is internal to cdr_scan_topk");
+  CDR_REQUIRE(g->out != nullptr, "cdr_gemm: null output");
+  const bool f32 = g->epilogue == CDR_EPI_F32_ATOMIC || g->epilogue == CDR_EPI_F32_STORE;
+  CDR_REQUIRE(g->ldo % (f32 ? 4 : 8) == 0, "cdr_gemm: ldo must keep rows 16-byte aligned (ldo=%lld)", (long long)g->ldo);
+  CDR_REQUIRE((reinterpret_cast<uintptr_t>(g->out) & 15) == 0, "cdr_gemm: out must be 16-byte aligned");
+  if (g->epilogue == CDR_EPI_BIAS_RESIDUAL || g->epilogue == CDR_EPI_DGELU) {
+    CDR_REQUIRE(g->aux != nullptr && g->ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(g->aux) & 15) == 0,
+                "cdr_gemm: epilogue %d needs a 16-byte aligned aux operand", g->epilogue);
+  }
+  if (g->bias) CDR_REQUIRE((reinterpret_cast<uintptr_t>(g->bias) & 15) == 0, "cdr_gemm: bias must be 16-byte aligned");
+  cdr::GemmParams p{};
+  p.out = g->out;
+  p.out2 = g->out2;
+  p.bias = g->bias;
+  p.aux = static_cast<const __half*>(g->aux);
+  p.ldo = g->ldo;
+  p.ldaux = g->ldaux;
+  return cdr::gemm_run(*g, p, static_cast<cudaStream_t>(stream));
+}

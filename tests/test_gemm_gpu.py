@@ -1,0 +1,82 @@
+"""GPU: tcgen05 GEMM (all operand layouts / epilogues) vs a torch fp32 reference of the same op."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).half().cuda()
+
+
+def _check(got, ref, tol=2e-2, what=""):
+    got, ref = got.float(), ref.float()
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-6
+    assert err <= tol * scale, f"{what}: max err {err} vs scale {scale}"
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 128), (384, 768, 768), (200, 384, 136), (1024, 2304, 768),
+                                   (8192, 768, 3072)])
+def test_nt_store(M, N, K):
+    from cocodr_b200 import kernels as k
+    a, b = _rand((M, K), 1), _rand((N, K), 2, 0.1)
+    bias = torch.randn(N, device="cuda")
+    out = torch.empty(M, N, dtype=torch.float16, device="cuda")
+    k.gemm(a, b, out, M=M, N=N, K=K, bias=bias)
+    _check(out, a.float() @ b.float().t() + bias, what=f"NT {M}x{N}x{K}")
+
+
+def test_nt_gelu_residual():
+    from cocodr_b200 import kernels as k
+    M, N, K = 512, 1024, 256
+    a, b = _rand((M, K), 3), _rand((N, K), 4, 0.1)
+    bias = torch.randn(N, device="cuda") * 0.1
+    res = _rand((M, N), 5)
+    out = torch.empty(M, N, dtype=torch.float16, device="cuda")
+    z = torch.empty_like(out)
+    k.gemm(a, b, out, M=M, N=N, K=K, bias=bias, epilogue=k.EPI_BIAS_GELU, out2=z)
+    zr = a.float() @ b.float().t() + bias
+    _check(z, zr, what="pre-activation")
+    _check(out, torch.nn.functional.gelu(z.float()), tol=2e-3, what="gelu(z16)")
+    k.gemm(a, b, out, M=M, N=N, K=K, bias=bias, epilogue=k.EPI_BIAS_RESIDUAL, aux=res)
+    _check(out, zr + res.float(), what="bias+residual")
+    o32 = torch.empty(M, N, dtype=torch.float32, device="cuda")
+    k.gemm(a, b, o32, M=M, N=N, K=K, epilogue=k.EPI_F32_STORE, alpha=0.5)
+    _check(o32, 0.5 * (a.float() @ b.float().t()), tol=1e-3, what="f32 store")
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 128), (512, 768, 3072), (1000, 3072, 768)])
+def test_dgrad_b_mn_major(M, N, K):
+    """dx[M,N] = dy[M,K] @ W[K,N]   (B stored [K, N] row-major = MN-major)."""
+    from cocodr_b200 import kernels as k
+    dy, w = _rand((M, K), 6), _rand((K, N), 7, 0.1)
+    out = torch.empty(M, N, dtype=torch.float16, device="cuda")
+    k.gemm(dy, w, out, M=M, N=N, K=K, b_major=1)
+    _check(out, dy.float() @ w.float(), what="dgrad")
+    zpre = _rand((M, N), 8)
+    k.gemm(dy, w, out, M=M, N=N, K=K, b_major=1, epilogue=k.EPI_DGELU, aux=zpre)
+    zf = zpre.float().requires_grad_(True)
+    torch.nn.functional.gelu(zf).sum().backward()
+    _check(out, (dy.float() @ w.float()) * zf.grad, what="dgrad*gelu'")
+
+
+@pytest.mark.parametrize("M,N,K,split", [(128, 128, 256, 1), (768, 768, 4096, 0), (3072, 768, 2048, 0), (128, 512, 1000, 3)])
+def test_wgrad_both_mn_major(M, N, K, split):
+    """dW[M,N] += dy[K,M]^T @ x[K,N]   (both operands MN-major, split-K with fp32 atomics)."""
+    from cocodr_b200 import kernels as k
+    dy, x = _rand((K, M), 9), _rand((K, N), 10)
+    out = torch.ones(M, N, dtype=torch.float32, device="cuda")
+    k.gemm(dy, x, out, M=M, N=N, K=K, a_major=1, b_major=1, epilogue=k.EPI_F32_ATOMIC, split_k=split, alpha=0.25)
+    _check(out, 1.0 + 0.25 * (dy.float().t() @ x.float()), tol=2e-3, what="wgrad")
+
+
+def test_errors_are_loud():
+    from cocodr_b200 import kernels as k
+    a, b = _rand((128, 60), 1), _rand((128, 60), 2)
+    out = torch.empty(128, 128, dtype=torch.float16, device="cuda")
+    with pytest.raises(RuntimeError):
+        k.gemm(a, b, out, M=128, N=128, K=60)
