@@ -17,6 +17,28 @@ EPI_STORE_F16, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_DGELU, EPI_F32_ATOMIC, EPI_
 CDR_EOVERFLOW = -5
 
 
+class AttnArgs(C.Structure):
+    _fields_ = [("qkv", C.c_void_p), ("key_bias", C.c_void_p), ("out", C.c_void_p), ("lse", C.c_void_p),
+                ("d_out", C.c_void_p), ("dqkv", C.c_void_p),
+                ("n_seq", C.c_int32), ("seq_len", C.c_int32), ("heads", C.c_int32), ("head_dim", C.c_int32),
+                ("scale", C.c_float)]
+
+
+class SimmatArgs(C.Structure):
+    _fields_ = [("q", C.c_void_p), ("k", C.c_void_p), ("scores", C.c_void_p), ("gmat", C.c_void_p),
+                ("loss", C.c_void_p), ("lse", C.c_void_p), ("dloss", C.c_void_p), ("dq", C.c_void_p),
+                ("dk", C.c_void_p),
+                ("n_rows", C.c_int32), ("n_keys", C.c_int32), ("dim", C.c_int32), ("mode", C.c_int32),
+                ("row_offset", C.c_int32), ("loss_scale", C.c_float)]
+
+
+class ScanArgs(C.Structure):
+    _fields_ = [("docs", C.c_void_p), ("queries", C.c_void_p), ("out_scores", C.c_void_p), ("out_ids", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("status", C.c_void_p),
+                ("n_docs", C.c_int64), ("ld_docs", C.c_int64), ("doc_base", C.c_int64),
+                ("n_q", C.c_int32), ("dim", C.c_int32), ("k", C.c_int32), ("reserved", C.c_int32)]
+
+
 class GemmArgs(C.Structure):
     _fields_ = [("a", C.c_void_p), ("b", C.c_void_p), ("out", C.c_void_p), ("out2", C.c_void_p),
                 ("bias", C.c_void_p), ("aux", C.c_void_p),
@@ -51,6 +73,8 @@ def load():
         fn = getattr(lib, name)
         if name.endswith("_bytes"):
             fn.restype = C.c_size_t
+        elif name == "cdr_scan_exhaustive_docs":
+            fn.restype = C.c_int64
         elif name != "cdr_last_error":
             fn.restype = C.c_int
     _lib = lib

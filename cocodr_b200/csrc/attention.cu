@@ -1,0 +1,434 @@
+// Fused multi-head attention (K3) for BERT, head_dim 64, seq_len <= 128, forward and backward, on the
+// sm_100a tensor cores (tcgen05.mma, accumulators in TMEM, operands staged by TMA).
+//
+// One CTA per (sequence, head).  Q/K/V come straight out of the packed QKV projection [T, 3H]
+// (columns [0,H) = Q, [H,2H) = K, [2H,3H) = V; head h owns 64 contiguous columns), so a single 2-D
+// TMA box {64, 128} per operand lands a 128B-swizzled [128 rows][64 halfs] tile that is at the same
+// time
+//   * a K-major  operand over the head dimension  (S = Q K^T,  dP = dO V^T)
+//   * an MN-major operand over the row dimension   (O = P V,  dV = P^T dO,  dK = dS^T Q,  dQ = dS K)
+// -- no transposes are ever materialised.  P / dS are written by the softmax threads into shared
+// memory in the same swizzled layout as two [128][64] chunks, which again serves both as a K-major A
+// operand (P V, dS K) and as an MN-major A operand (P^T dO, dS^T Q).
+//
+// Rows beyond seq_len inside the 128-row box belong to the next sequence (or are TMA zero fill);
+// they are neutralised by the key bias (-inf) on columns and by explicit zeroing of P/dS rows.
+//
+// Replaces HF eager_attention_forward / SDPA reached through self.bert(...) in
+// ANCE/model/models.py:226 and COCO/modeling.py:199-204 (dropout p = 0 / eval-mode semantics).
+#include "cdr_common.cuh"
+#include "tma_host.h"
+
+namespace cdr {
+
+constexpr int ATT_T = 128;  // query rows per tile == max keys
+constexpr int ATT_D = 64;   // head dim
+constexpr int ATT_TILE_BYTES = ATT_T * ATT_D * 2;  // 16 KB
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct AttParams {
+  int n_seq, seq_len, heads, hidden;
+  const float* key_bias;  // [n_seq, seq_len] additive (0 / -large) or null
+  float scale;            // 1/sqrt(64)
+  // forward
+  __half* out;            // ctx [T, hidden]
+  float* lse;             // [n_seq, heads, seq_len]
+  // backward
+  const __half* o;        // ctx [T, hidden]
+  const __half* d_o;      // dctx [T, hidden]
+  __half* dqkv;           // [T, 3*hidden]
+};
+
+// byte offset of element (r, c), c in [0,128), inside two 128B-swizzled [128][64-half] chunks
+__device__ __forceinline__ uint32_t swz_off(int r, int c) {
+  return static_cast<uint32_t>(((c >> 6) * ATT_TILE_BYTES) + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) +
+                               ((c & 7) << 1));
+}
+
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  uint4 q;
+  __half2* h = reinterpret_cast<__half2*>(&q);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) h[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
+  return q;
+}
+
+__device__ __forceinline__ float dot8(const uint4& a, const uint4& b) {
+  const __half2* x = reinterpret_cast<const __half2*>(&a);
+  const __half2* y = reinterpret_cast<const __half2*>(&b);
+  float s = 0.f;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float2 f = __half22float2(x[t]), g = __half22float2(y[t]);
+    s += f.x * g.x + f.y * g.y;
+  }
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------ forward
+constexpr int ATT_FWD_SMEM = 3 * ATT_TILE_BYTES + 512 + 64 + 1024;
+
+__global__ void __launch_bounds__(128, 4)
+fmha_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + ATT_TILE_BYTES;
+  uint8_t* sV = smem + 2 * ATT_TILE_BYTES;
+  uint8_t* sP = smem;  // overlays Q and K once S = Q K^T has retired
+  float* sBias = reinterpret_cast<float*>(smem + 3 * ATT_TILE_BYTES);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 3 * ATT_TILE_BYTES + 512);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int seq = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
+  const int L = p.seq_len;
+  const int row0 = seq * L;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tma_qkv);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) mbar_init(&bar[i], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_ptr, 128);
+    tmem_relinquish();
+  }
+  {
+    float b = -INFINITY;
+    if (tid < L) b = p.key_bias ? p.key_bias[static_cast<long long>(seq) * L + tid] * LOG2E : 0.f;
+    sBias[tid] = b;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+
+  if (tid == 0) {
+    mbar_expect_tx(&bar[0], 2 * ATT_TILE_BYTES);
+    tma_load_2d(sQ, &tma_qkv, &bar[0], h * ATT_D, row0);
+    tma_load_2d(sK, &tma_qkv, &bar[0], p.hidden + h * ATT_D, row0);
+    mbar_expect_tx(&bar[1], ATT_TILE_BYTES);
+    tma_load_2d(sV, &tma_qkv, &bar[1], 2 * p.hidden + h * ATT_D, row0);
+    mbar_wait(&bar[0], 0);
+    tc_fence_after();
+    constexpr uint32_t idesc = make_idesc_f16(ATT_T, ATT_T, 0, 0);
+    const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK);
+#pragma unroll
+    for (int k = 0; k < ATT_D / 16; ++k)
+      tc_mma_f16(tmem, make_smem_desc(qa + k * 32, 16, 1024), make_smem_desc(ka + k * 32, 16, 1024), idesc, k > 0);
+    tc_commit(&bar[2]);
+  }
+  __syncwarp();
+  mbar_wait(&bar[2], 0);
+  tc_fence_after();
+  __syncwarp();
+
+  const int r = tid;  // TMEM lane == query row
+  const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const float sl2 = p.scale * LOG2E;
+  float mx = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t v[32];
+    tmem_ld_32x32(trow + c * 32, v);
+    tc_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaf(__uint_as_float(v[j]), sl2, sBias[c * 32 + j]));
+  }
+  if (mx == -INFINITY) mx = 0.f;  // fully masked row: P = 0, output 0
+  float sum = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t v[32];
+    tmem_ld_32x32(trow + c * 32, v);
+    tc_wait_ld();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float e[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        e[j] = exp2f(fmaf(__uint_as_float(v[g * 8 + j]), sl2, sBias[c * 32 + g * 8 + j]) - mx);
+        sum += e[j];
+      }
+      *reinterpret_cast<uint4*>(sP + swz_off(r, c * 32 + g * 8)) = pack8(e);
+    }
+  }
+  if (r < L && p.lse) p.lse[(static_cast<long long>(seq) * p.heads + h) * L + r] = (mx + log2f(sum)) / LOG2E;
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+
+  if (tid == 0) {
+    tc_fence_after();
+    mbar_wait(&bar[1], 0);
+    tc_fence_after();
+    constexpr uint32_t idesc = make_idesc_f16(ATT_T, ATT_D, 0, 1);
+    const uint32_t pa = smem_u32(sP), va = smem_u32(sV);
+#pragma unroll
+    for (int k = 0; k < ATT_T / 16; ++k)
+      tc_mma_f16(tmem, make_smem_desc(pa + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 16, 1024),
+                 make_smem_desc(va + k * 2048, 8192, 1024), idesc, k > 0);
+    tc_commit(&bar[3]);
+  }
+  __syncwarp();
+  mbar_wait(&bar[3], 0);
+  tc_fence_after();
+  __syncwarp();
+
+  const float inv = sum > 0.f ? 1.f / sum : 0.f;
+  __half* orow = p.out + static_cast<long long>(row0 + r) * p.hidden + h * ATT_D;
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c) {
+    uint32_t v[32];
+    tmem_ld_32x32(trow + c * 32, v);
+    tc_wait_ld();
+    if (r < L) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float e[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) e[j] = __uint_as_float(v[g * 8 + j]) * inv;
+        *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = pack8(e);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 128);
+  }
+}
+
+// ----------------------------------------------------------------------------------------- backward
+// smem: Q K V dO (4 x 16 KB) | P (32 KB) | dS (32 KB) | bias | barriers
+constexpr int ATT_BWD_SMEM = 8 * ATT_TILE_BYTES + 512 + 64 + 1024;
+
+__global__ void __launch_bounds__(256, 1)
+fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do,
+                const AttParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + ATT_TILE_BYTES;
+  uint8_t* sV = smem + 2 * ATT_TILE_BYTES;
+  uint8_t* sdO = smem + 3 * ATT_TILE_BYTES;
+  uint8_t* sP = smem + 4 * ATT_TILE_BYTES;
+  uint8_t* sdS = smem + 6 * ATT_TILE_BYTES;
+  float* sBias = reinterpret_cast<float*>(smem + 8 * ATT_TILE_BYTES);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 8 * ATT_TILE_BYTES + 512);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int seq = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
+  const int L = p.seq_len;
+  const int row0 = seq * L;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tma_qkv);
+    tma_prefetch_desc(&tma_do);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) mbar_init(&bar[i], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_ptr, 256);
+    tmem_relinquish();
+  }
+  if (tid < ATT_T) {
+    float b = -INFINITY;
+    if (tid < L) b = p.key_bias ? p.key_bias[static_cast<long long>(seq) * L + tid] * LOG2E : 0.f;
+    sBias[tid] = b;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+
+  if (tid == 0) {
+    mbar_expect_tx(&bar[0], 2 * ATT_TILE_BYTES);
+    tma_load_2d(sQ, &tma_qkv, &bar[0], h * ATT_D, row0);
+    tma_load_2d(sK, &tma_qkv, &bar[0], p.hidden + h * ATT_D, row0);
+    mbar_expect_tx(&bar[1], 2 * ATT_TILE_BYTES);
+    tma_load_2d(sV, &tma_qkv, &bar[1], 2 * p.hidden + h * ATT_D, row0);
+    tma_load_2d(sdO, &tma_do, &bar[1], h * ATT_D, row0);
+    constexpr uint32_t idesc = make_idesc_f16(ATT_T, ATT_T, 0, 0);
+    mbar_wait(&bar[0], 0);
+    tc_fence_after();
+    const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK), va = smem_u32(sV), da = smem_u32(sdO);
+#pragma unroll
+    for (int k = 0; k < ATT_D / 16; ++k)  // S = Q K^T -> cols [0,128)
+      tc_mma_f16(tmem, make_smem_desc(qa + k * 32, 16, 1024), make_smem_desc(ka + k * 32, 16, 1024), idesc, k > 0);
+    mbar_wait(&bar[1], 0);
+    tc_fence_after();
+#pragma unroll
+    for (int k = 0; k < ATT_D / 16; ++k)  // dP = dO V^T -> cols [128,256)
+      tc_mma_f16(tmem + 128, make_smem_desc(da + k * 32, 16, 1024), make_smem_desc(va + k * 32, 16, 1024), idesc,
+                 k > 0);
+    tc_commit(&bar[2]);
+  }
+
+  // delta_r = sum_d dO[r,d] * O[r,d]  (both halves of the row's threads compute it redundantly)
+  const int r = (warp & 3) * 32 + lane;  // TMEM lane == query row
+  const int half = warp >> 2;            // which 64 key columns this thread handles
+  float delta = 0.f, lse2 = 0.f;
+  if (r < L) {
+    const long long off = static_cast<long long>(row0 + r) * p.hidden + h * ATT_D;
+    const uint4* po = reinterpret_cast<const uint4*>(p.o + off);
+    const uint4* pd = reinterpret_cast<const uint4*>(p.d_o + off);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) delta += dot8(__ldg(po + i), __ldg(pd + i));
+    lse2 = p.lse[(static_cast<long long>(seq) * p.heads + h) * L + r] * LOG2E;
+  }
+  __syncwarp();
+  mbar_wait(&bar[2], 0);
+  tc_fence_after();
+  __syncwarp();
+
+  const uint32_t trow = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+  const float sl2 = p.scale * LOG2E;
+#pragma unroll 1
+  for (int cc = 0; cc < 2; ++cc) {
+    const int c0 = half * 64 + cc * 32;
+    uint32_t s[32], d[32];
+    tmem_ld_32x32(trow + c0, s);
+    tmem_ld_32x32(trow + 128 + c0, d);
+    tc_wait_ld();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float pv[8], ds[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = c0 + g * 8 + j;
+        const bool ok = (r < L) && (c < L);
+        const float pe = ok ? exp2f(fmaf(__uint_as_float(s[g * 8 + j]), sl2, sBias[c]) - lse2) : 0.f;
+        pv[j] = pe;
+        ds[j] = ok ? pe * (__uint_as_float(d[g * 8 + j]) - delta) * p.scale : 0.f;
+      }
+      const uint32_t o = swz_off(r, c0 + g * 8);
+      *reinterpret_cast<uint4*>(sP + o) = pack8(pv);
+      *reinterpret_cast<uint4*>(sdS + o) = pack8(ds);
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+
+  if (tid == 0) {
+    tc_fence_after();
+    const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK), da = smem_u32(sdO), pa = smem_u32(sP), sa = smem_u32(sdS);
+    constexpr uint32_t idesc_tt = make_idesc_f16(ATT_T, ATT_D, 1, 1);
+    constexpr uint32_t idesc_nt = make_idesc_f16(ATT_T, ATT_D, 0, 1);
+#pragma unroll
+    for (int k = 0; k < ATT_T / 16; ++k)  // dV[kv,d] = sum_q P[q,kv] dO[q,d] -> cols [0,64)
+      tc_mma_f16(tmem, make_smem_desc(pa + k * 2048, ATT_TILE_BYTES, 1024),
+                 make_smem_desc(da + k * 2048, 8192, 1024), idesc_tt, k > 0);
+#pragma unroll
+    for (int k = 0; k < ATT_T / 16; ++k)  // dK[kv,d] = sum_q dS[q,kv] Q[q,d] -> cols [64,128)
+      tc_mma_f16(tmem + 64, make_smem_desc(sa + k * 2048, ATT_TILE_BYTES, 1024),
+                 make_smem_desc(qa + k * 2048, 8192, 1024), idesc_tt, k > 0);
+#pragma unroll
+    for (int k = 0; k < ATT_T / 16; ++k)  // dQ[q,d] = sum_kv dS[q,kv] K[kv,d] -> cols [128,192)
+      tc_mma_f16(tmem + 128, make_smem_desc(sa + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 16, 1024),
+                 make_smem_desc(ka + k * 2048, 8192, 1024), idesc_nt, k > 0);
+    tc_commit(&bar[3]);
+  }
+  __syncwarp();
+  mbar_wait(&bar[3], 0);
+  tc_fence_after();
+  __syncwarp();
+
+  // rows of dV / dK are key rows, rows of dQ are query rows -- all indexed by the TMEM lane r
+  __half* grow = p.dqkv + static_cast<long long>(row0 + r) * (3 * p.hidden) + h * ATT_D + half * 32;
+#pragma unroll 1
+  for (int t = 0; t < 3; ++t) {  // t: 0 = dV, 1 = dK, 2 = dQ
+    uint32_t v[32];
+    tmem_ld_32x32(trow + t * 64 + half * 32, v);
+    tc_wait_ld();
+    if (r < L) {
+      __half* dst = grow + (2 - t) * p.hidden;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float e[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) e[j] = __uint_as_float(v[g * 8 + j]);
+        *reinterpret_cast<uint4*>(dst + g * 8) = pack8(e);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+static int att_check(const cdr_attn_args* a) {
+  CDR_REQUIRE(a != nullptr, "cdr_attn: null args");
+  CDR_REQUIRE(a->qkv != nullptr, "cdr_attn: null qkv");
+  CDR_REQUIRE(a->n_seq > 0 && a->seq_len > 0 && a->heads > 0, "cdr_attn: empty problem");
+  CDR_REQUIRE(a->seq_len <= ATT_T, "cdr_attn: seq_len %d > %d not supported by this build", a->seq_len, ATT_T);
+  CDR_REQUIRE(a->head_dim == ATT_D, "cdr_attn: head_dim must be 64 (got %d)", a->head_dim);
+  return CDR_OK;
+}
+
+}  // namespace cdr
+
+using namespace cdr;
+
+extern "C" {
+
+int cdr_attn_fwd(const cdr_attn_args* a, void* stream) {
+  if (int rc = att_check(a)) return rc;
+  CDR_REQUIRE(a->out != nullptr && a->lse != nullptr, "cdr_attn_fwd: null output");
+  const int hidden = a->heads * ATT_D;
+  const long long T = static_cast<long long>(a->n_seq) * a->seq_len;
+  CUtensorMap tq;
+  if (int rc = make_tma_2d_f16(&tq, a->qkv, 3 * hidden, T, 3 * hidden, ATT_D, ATT_T)) return rc;
+  AttParams p{};
+  p.n_seq = a->n_seq; p.seq_len = a->seq_len; p.heads = a->heads; p.hidden = hidden;
+  p.key_bias = a->key_bias;
+  p.scale = a->scale;
+  p.out = static_cast<__half*>(a->out);
+  p.lse = a->lse;
+  static bool configured = false;
+  if (!configured) {
+    CDR_CUDA(cudaFuncSetAttribute(fmha_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWD_SMEM));
+    configured = true;
+  }
+  fmha_fwd_kernel<<<a->n_seq * a->heads, 128, ATT_FWD_SMEM, static_cast<cudaStream_t>(stream)>>>(tq, p);
+  CDR_LAUNCH_CHECK();
+  return CDR_OK;
+}
+
+int cdr_attn_bwd(const cdr_attn_args* a, void* stream) {
+  if (int rc = att_check(a)) return rc;
+  CDR_REQUIRE(a->out != nullptr && a->lse != nullptr && a->d_out != nullptr && a->dqkv != nullptr,
+              "cdr_attn_bwd: null pointer");
+  const int hidden = a->heads * ATT_D;
+  const long long T = static_cast<long long>(a->n_seq) * a->seq_len;
+  CUtensorMap tq, td;
+  if (int rc = make_tma_2d_f16(&tq, a->qkv, 3 * hidden, T, 3 * hidden, ATT_D, ATT_T)) return rc;
+  if (int rc = make_tma_2d_f16(&td, a->d_out, hidden, T, hidden, ATT_D, ATT_T)) return rc;
+  AttParams p{};
+  p.n_seq = a->n_seq; p.seq_len = a->seq_len; p.heads = a->heads; p.hidden = hidden;
+  p.key_bias = a->key_bias;
+  p.scale = a->scale;
+  p.lse = a->lse;
+  p.o = static_cast<const __half*>(a->out);
+  p.d_o = static_cast<const __half*>(a->d_out);
+  p.dqkv = static_cast<__half*>(a->dqkv);
+  static bool configured = false;
+  if (!configured) {
+    CDR_CUDA(cudaFuncSetAttribute(fmha_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWD_SMEM));
+    configured = true;
+  }
+  fmha_bwd_kernel<<<a->n_seq * a->heads, 256, ATT_BWD_SMEM, static_cast<cudaStream_t>(stream)>>>(tq, td, p);
+  CDR_LAUNCH_CHECK();
+  return CDR_OK;
+}
+
+}  // extern "C"

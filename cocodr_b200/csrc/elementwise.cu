@@ -172,8 +172,10 @@ ln_bwd_kernel(const __half* __restrict__ dy, const __half* __restrict__ x, const
         }
         if (dy != nullptr) {
           load8_h(dy + row * hidden + c, d);
+          if constexpr (MODE == 1) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) d[k] *= in_scale;
+            for (int k = 0; k < 8; ++k) d[k] *= in_scale;
+          }
         } else {
 #pragma unroll
           for (int k = 0; k < 8; ++k) d[k] = 0.f;

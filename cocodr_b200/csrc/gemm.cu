@@ -56,8 +56,8 @@ int gemm_run(const cdr_gemm_args& g, GemmParams p, cudaStream_t st) {
   CDR_REQUIRE(g.a && g.b, "cdr_gemm: null operand");
   CDR_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "cdr_gemm: empty problem M=%lld N=%lld K=%lld", (long long)g.M,
               (long long)g.N, (long long)g.K);
-  CDR_REQUIRE(g.N % 8 == 0 && g.K % 8 == 0, "cdr_gemm: N and K must be multiples of 8 (N=%lld K=%lld)",
-              (long long)g.N, (long long)g.K);
+  CDR_REQUIRE(g.N % 8 == 0 || g.epilogue == CDR_EPI_SCAN_FILTER, "cdr_gemm: N must be a multiple of 8 (N=%lld)",
+              (long long)g.N);
   CDR_REQUIRE(g.M < (1ll << 31) && g.N < (1ll << 31) && g.K < (1ll << 31), "cdr_gemm: dimension overflow");
   const int a_mn = g.a_major, b_mn = g.b_major;
   if (a_mn) CDR_REQUIRE(g.M % 64 == 0, "cdr_gemm: MN-major A needs M %% 64 == 0 (M=%lld)", (long long)g.M);

@@ -52,6 +52,9 @@ struct GemmParams {
   int dbg_lbo, dbg_sbo;
 };
 
+// host-side entry shared by cdr_gemm and the scan (gemm.cu)
+int gemm_run(const cdr_gemm_args& g, GemmParams p, cudaStream_t st);
+
 template <int BN>
 struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;

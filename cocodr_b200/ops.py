@@ -1,0 +1,318 @@
+"""torch.autograd.Function wrappers that chain the C-ABI kernels into the operators of the hot path.
+
+One Function per BERT *layer* (not per encoder) so that ``output_hidden_states``, the Condenser
+``skip_from`` tap and iDRO's re-entrant partial backward (ANCE/model/dro_loss.py:192-204 calls
+``torch.autograd.grad(..., retain_graph=True)`` once per group) keep working unmodified.
+
+Numerics: fp16 activations / fp16 weight shadows, fp32 accumulation, fp32 LayerNorm statistics, fp32
+parameters, biases and parameter gradients; the CLS embedding leaves the last LayerNorm in fp32
+(SURVEY.md H4).  Activation gradients travel between layers as fp16 tensors multiplied by a static
+power-of-two ``grad_scale`` (they would underflow otherwise); every parameter gradient is divided by it
+again inside the producing kernel (GEMM alpha / LN out_scale), so callers only ever see true gradients.
+"""
+import torch
+
+from . import kernels as K
+
+_GRAD_SCALE = 1024.0
+
+
+def set_grad_scale(s: float):
+    """Static scale of the internal fp16 activation-gradient domain (power of two)."""
+    global _GRAD_SCALE
+    _GRAD_SCALE = float(s)
+
+
+def get_grad_scale() -> float:
+    return _GRAD_SCALE
+
+
+def _f16(*shape, dev):
+    return torch.empty(*shape, dtype=torch.float16, device=dev)
+
+
+def _f32(*shape, dev):
+    return torch.empty(*shape, dtype=torch.float32, device=dev)
+
+
+def _z32(*shape, dev):
+    return torch.zeros(*shape, dtype=torch.float32, device=dev)
+
+
+class LayerShadow:
+    """fp16 operand copies of one BertLayer's matrices (QKV packed [3H, H]) + packed fp32 QKV bias.
+
+    The HF-named fp32 ``nn.Parameter``s stay the source of truth (state-dict contract);
+    the shadow is rebuilt whenever a parameter's storage or version counter changes."""
+
+    __slots__ = ("key", "wqkv", "bqkv", "wo", "wi", "wo2")
+
+    def __init__(self):
+        self.key = None
+
+    def refresh(self, wq, bq, wk, bk, wv, bv, wo, wi, wo2):
+        srcs = (wq, bq, wk, bk, wv, bv, wo, wi, wo2)
+        key = tuple((t.data_ptr(), t._version) for t in srcs)
+        if key == self.key:
+            return self
+        dev = wq.device
+        H, I = wq.shape[0], wi.shape[0]
+        if self.key is None or self.wqkv.device != dev or self.wqkv.shape != (3 * H, H):
+            self.wqkv, self.bqkv = _f16(3 * H, H, dev=dev), _f32(3 * H, dev=dev)
+            self.wo, self.wi, self.wo2 = _f16(H, H, dev=dev), _f16(I, H, dev=dev), _f16(H, I, dev=dev)
+        with torch.no_grad():
+            for i, (w, b) in enumerate(((wq, bq), (wk, bk), (wv, bv))):
+                K.cast_f32_f16(w.detach().contiguous(), self.wqkv[i * H:(i + 1) * H])
+                self.bqkv[i * H:(i + 1) * H].copy_(b.detach())
+            K.cast_f32_f16(wo.detach().contiguous(), self.wo)
+            K.cast_f32_f16(wi.detach().contiguous(), self.wi)
+            K.cast_f32_f16(wo2.detach().contiguous(), self.wo2)
+        self.key = key
+        return self
+
+
+class EmbedLN(torch.autograd.Function):
+    """K1: LayerNorm(word[ids] + pos[0:L] + type[0]) -> fp16 [n_seq*L, H]  (HF BertEmbeddings)."""
+
+    @staticmethod
+    def forward(ctx, ids, word, pos, typ, gamma, beta, eps):
+        n_seq, L = ids.shape
+        H = word.shape[1]
+        dev = word.device
+        ids = ids.contiguous()
+        out = _f16(n_seq * L, H, dev=dev)
+        mean, rstd = _f32(n_seq * L, dev=dev), _f32(n_seq * L, dev=dev)
+        K.embed_ln_fwd(ids, word, pos, typ, gamma, beta, out, mean, rstd, n_seq=n_seq, seq_len=L, hidden=H,
+                       vocab=word.shape[0], eps=eps)
+        ctx.save_for_backward(ids, word, pos, typ, gamma, mean, rstd)
+        ctx.eps = eps
+        ctx.scale = _GRAD_SCALE
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        ids, word, pos, typ, gamma, mean, rstd = ctx.saved_tensors
+        n_seq, L = ids.shape
+        H = word.shape[1]
+        dev = word.device
+        dword, dpos, dtyp = torch.zeros_like(word), torch.zeros_like(pos), torch.zeros_like(typ)
+        dgamma, dbeta = _z32(H, dev=dev), _z32(H, dev=dev)
+        K.embed_ln_bwd(dy.contiguous(), ids, word, pos, typ, gamma, mean, rstd, dword, dpos, dtyp, dgamma, dbeta,
+                       n_seq=n_seq, seq_len=L, hidden=H, vocab=word.shape[0], pad_id=0, in_scale=1.0,
+                       out_scale=1.0 / ctx.scale)
+        return None, dword, dpos, dtyp, dgamma, dbeta, None
+
+
+class BertLayerFn(torch.autograd.Function):
+    """K2-K7: one post-LN transformer layer on fp16 [T, H] activations.
+
+    forward(x, key_bias, <16 HF parameters>, shadow, n_seq, seq_len, heads, eps, emit_cls)
+      -> y fp16 [T, H]  (and cls fp32 [n_seq, H] = row 0 of every sequence when emit_cls)
+    """
+
+    @staticmethod
+    def forward(ctx, x, key_bias, wq, bq, wk, bk, wv, bv, wo, bo, g1, be1, wi, bi, wo2, bo2, g2, be2, shadow, n_seq,
+                L, heads, eps, emit_cls):
+        T, H = x.shape
+        I = wi.shape[0]
+        dev = x.device
+        sh = shadow.refresh(wq, bq, wk, bk, wv, bv, wo, wi, wo2)
+        x = x.contiguous()
+        qkv = _f16(T, 3 * H, dev=dev)
+        K.gemm(x, sh.wqkv, qkv, M=T, N=3 * H, K=H, bias=sh.bqkv)
+        att = _f16(T, H, dev=dev)
+        lse = _f32(n_seq, heads, L, dev=dev)
+        K.attn_fwd(qkv, key_bias, att, lse, n_seq=n_seq, seq_len=L, heads=heads)
+        y1 = _f16(T, H, dev=dev)  # x + attn_out, pre-LayerNorm
+        K.gemm(att, sh.wo, y1, M=T, N=H, K=H, bias=bo, epilogue=K.EPI_BIAS_RESIDUAL, aux=x)
+        x1 = _f16(T, H, dev=dev)
+        mean1, rstd1 = _f32(T, dev=dev), _f32(T, dev=dev)
+        K.ln_fwd(y1, g1, be1, x1, mean1, rstd1, None, n_seq=n_seq, seq_len=L, hidden=H, eps=eps)
+        z, gl = _f16(T, I, dev=dev), _f16(T, I, dev=dev)
+        K.gemm(x1, sh.wi, gl, M=T, N=I, K=H, bias=bi, epilogue=K.EPI_BIAS_GELU, out2=z)
+        y2 = _f16(T, H, dev=dev)
+        K.gemm(gl, sh.wo2, y2, M=T, N=H, K=I, bias=bo2, epilogue=K.EPI_BIAS_RESIDUAL, aux=x1)
+        y = _f16(T, H, dev=dev)
+        mean2, rstd2 = _f32(T, dev=dev), _f32(T, dev=dev)
+        cls = _f32(n_seq, H, dev=dev) if emit_cls else None
+        K.ln_fwd(y2, g2, be2, y, mean2, rstd2, cls, n_seq=n_seq, seq_len=L, hidden=H, eps=eps)
+        ctx.save_for_backward(x, key_bias, qkv, att, lse, y1, x1, mean1, rstd1, z, gl, y2, mean2, rstd2, g1, g2)
+        ctx.shadow_w = (sh.wqkv, sh.wo, sh.wi, sh.wo2)
+        ctx.meta = (n_seq, L, heads, I, emit_cls, _GRAD_SCALE)
+        ctx.set_materialize_grads(False)
+        if emit_cls:
+            return y, cls
+        return y
+
+    @staticmethod
+    def backward(ctx, dy, dcls=None):
+        x, key_bias, qkv, att, lse, y1, x1, mean1, rstd1, z, gl, y2, mean2, rstd2, g1, g2 = ctx.saved_tensors
+        wqkv, wo, wi, wo2 = ctx.shadow_w
+        n_seq, L, heads, I, emit_cls, S = ctx.meta
+        T, H = x.shape
+        dev = x.device
+        inv = 1.0 / S
+        if dy is not None:
+            dy = dy.contiguous()
+        if dcls is not None:
+            dcls = dcls.contiguous().float()
+        # ---- output LayerNorm; column sums of its dx are the FFN-down bias gradient
+        dy2 = _f16(T, H, dev=dev)
+        dg2, dbe2, dbo2 = _z32(H, dev=dev), _z32(H, dev=dev), _z32(H, dev=dev)
+        K.ln_bwd(dy, dcls, y2, g2, mean2, rstd2, dy2, dg2, dbe2, dbo2, n_seq=n_seq, seq_len=L, hidden=H, in_scale=S,
+                 out_scale=inv)
+        # ---- FFN down: dG = dy2 W2 (fused gelu'), dW2 = dy2^T G
+        dz = _f16(T, I, dev=dev)
+        K.gemm(dy2, wo2, dz, M=T, N=I, K=H, b_major=1, epilogue=K.EPI_DGELU, aux=z)
+        dwo2 = _z32(H, I, dev=dev)
+        K.gemm(dy2, gl, dwo2, M=H, N=I, K=T, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0, alpha=inv)
+        # ---- FFN up: dx1 = dZ W1 + dy2 (residual), dW1 = dZ^T x1, db1 = colsum(dZ)
+        dbi = _z32(I, dev=dev)
+        K.colsum(dz, dbi, rows=T, cols=I, scale=inv)
+        dx1 = _f16(T, H, dev=dev)
+        K.gemm(dz, wi, dx1, M=T, N=H, K=I, b_major=1, epilogue=K.EPI_BIAS_RESIDUAL, aux=dy2)
+        dwi = _z32(I, H, dev=dev)
+        K.gemm(dz, x1, dwi, M=I, N=H, K=T, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0, alpha=inv)
+        # ---- attention-output LayerNorm
+        dy1 = _f16(T, H, dev=dev)
+        dg1, dbe1, dbo = _z32(H, dev=dev), _z32(H, dev=dev), _z32(H, dev=dev)
+        K.ln_bwd(dx1, None, y1, g1, mean1, rstd1, dy1, dg1, dbe1, dbo, n_seq=n_seq, seq_len=L, hidden=H, in_scale=S,
+                 out_scale=inv)
+        # ---- attention output projection
+        datt = _f16(T, H, dev=dev)
+        K.gemm(dy1, wo, datt, M=T, N=H, K=H, b_major=1)
+        dwo = _z32(H, H, dev=dev)
+        K.gemm(dy1, att, dwo, M=H, N=H, K=T, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0, alpha=inv)
+        # ---- attention core
+        dqkv = _f16(T, 3 * H, dev=dev)
+        K.attn_bwd(qkv, key_bias, att, lse, datt, dqkv, n_seq=n_seq, seq_len=L, heads=heads)
+        # ---- QKV projection: dx = dQKV Wqkv + dy1 (residual)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = _f16(T, H, dev=dev)
+            K.gemm(dqkv, wqkv, dx, M=T, N=H, K=3 * H, b_major=1, epilogue=K.EPI_BIAS_RESIDUAL, aux=dy1)
+        dwqkv = _z32(3 * H, H, dev=dev)
+        K.gemm(dqkv, x, dwqkv, M=3 * H, N=H, K=T, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0,
+               alpha=inv)
+        dbqkv = _z32(3 * H, dev=dev)
+        K.colsum(dqkv, dbqkv, rows=T, cols=3 * H, scale=inv)
+        return (dx, None, dwqkv[0:H], dbqkv[0:H], dwqkv[H:2 * H], dbqkv[H:2 * H], dwqkv[2 * H:], dbqkv[2 * H:], dwo,
+                dbo, dg1, dbe1, dwi, dbi, dwo2, dbo2, dg2, dbe2, None, None, None, None, None, None)
+
+
+class HiddenToFloat(torch.autograd.Function):
+    """Boundary between the internal fp16 hidden states (scaled-gradient domain) and caller-visible fp32
+    tensors: forward casts, backward multiplies the caller's true gradient by grad_scale."""
+
+    @staticmethod
+    def forward(ctx, h, n_seq, L):
+        ctx.scale = _GRAD_SCALE
+        return h.float().view(n_seq, L, -1)
+
+    @staticmethod
+    def backward(ctx, g):
+        return (g.reshape(-1, g.shape[-1]) * ctx.scale).to(torch.float16), None, None
+
+
+class FloatToHidden(torch.autograd.Function):
+    """Inverse boundary: caller fp32 [n_seq, L, H] -> internal fp16 [T, H]."""
+
+    @staticmethod
+    def forward(ctx, h):
+        ctx.scale = _GRAD_SCALE
+        ctx.shape = h.shape
+        return h.reshape(-1, h.shape[-1]).to(torch.float16)
+
+    @staticmethod
+    def backward(ctx, g):
+        return (g.float() / ctx.scale).view(ctx.shape)
+
+
+class PairNLL(torch.autograd.Function):
+    """K8 (ANCE/model/models.py:101-108): (loss[B], accs[B] int64, logits[B,2])."""
+
+    @staticmethod
+    def forward(ctx, q, a, b):
+        q, a, b = q.contiguous().float(), a.contiguous().float(), b.contiguous().float()
+        n = q.shape[0]
+        dev = q.device
+        loss, logits = _f32(n, dev=dev), _f32(n, 2, dev=dev)
+        accs = torch.empty(n, dtype=torch.int64, device=dev)
+        K.pair_nll_fwd(q, a, b, loss, accs, logits)
+        ctx.save_for_backward(q, a, b, logits)
+        ctx.mark_non_differentiable(accs, logits)
+        return loss, accs, logits
+
+    @staticmethod
+    def backward(ctx, dloss, _dacc, _dlogits):
+        q, a, b, logits = ctx.saved_tensors
+        dq, da, db = torch.empty_like(q), torch.empty_like(a), torch.empty_like(b)
+        K.pair_nll_bwd(q, a, b, logits, dloss.contiguous().float(), dq, da, db)
+        return dq, da, db
+
+
+class SimmatCE(torch.autograd.Function):
+    """K9 / K9': per-row softmax cross-entropy over the similarity matrix q k^T (fp32)."""
+
+    @staticmethod
+    def forward(ctx, q, k, mode, row_offset, loss_scale):
+        q, k = q.contiguous().float(), k.contiguous().float()
+        n, m = q.shape[0], k.shape[0]
+        dev = q.device
+        scores, loss, lse = _f32(n, m, dev=dev), _f32(n, dev=dev), _f32(n, dev=dev)
+        K.simmat_ce_fwd(q, k, scores, loss, lse, mode=mode, row_offset=row_offset, loss_scale=loss_scale)
+        ctx.save_for_backward(q, k, scores, lse)
+        ctx.cfg = (mode, row_offset, loss_scale)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        q, k, scores, lse = ctx.saved_tensors
+        mode, row_offset, loss_scale = ctx.cfg
+        gmat = torch.empty_like(scores)
+        dq = torch.empty_like(q) if ctx.needs_input_grad[0] else None
+        dk = torch.empty_like(k) if ctx.needs_input_grad[1] else None
+        K.simmat_ce_bwd(q, k, scores, lse, dloss.contiguous().float(), gmat, dq, dk, mode=mode, row_offset=row_offset,
+                        loss_scale=loss_scale)
+        return dq, dk, None, None, None
+
+
+class GroupStats(torch.autograd.Function):
+    """K10 (ANCE/model/dro_loss.py:217-224): scatter-add of per-sample losses / ones by group id."""
+
+    @staticmethod
+    def forward(ctx, loss, g, n_groups):
+        loss, g = loss.contiguous().float(), g.contiguous().long()
+        dev = loss.device
+        sums, cnts = _f32(n_groups, dev=dev), _f32(n_groups, dev=dev)
+        K.group_reduce_fwd(loss, g, sums, cnts, n_groups=n_groups)
+        ctx.save_for_backward(g)
+        ctx.n_groups = n_groups
+        ctx.mark_non_differentiable(cnts)
+        return sums, cnts
+
+    @staticmethod
+    def backward(ctx, dsums, _dc):
+        (g,) = ctx.saved_tensors
+        dloss = _f32(g.numel(), dev=g.device)
+        K.group_reduce_bwd(dsums.contiguous().float(), g, dloss, n_groups=ctx.n_groups)
+        return dloss, None, None
+
+
+def pair_nll(q, a, b):
+    return PairNLL.apply(q, a, b)
+
+
+def coco_contrastive(E, row_offset=0, n_rows=None, loss_scale=1.0):
+    """loss_i = loss_scale * CE(S[i,:], i^1), S = E_rows E^T with the diagonal masked (COCO/modeling.py:244-248)."""
+    q = E if n_rows is None else E[row_offset:row_offset + n_rows]
+    return SimmatCE.apply(q, E, K.SIM_COCO, row_offset, float(loss_scale))
+
+
+def qp_infonce(Q, P_all, row_offset=0):
+    """In-batch q x p InfoNCE over (all-gathered) passages: loss_i = CE(Q_i P_all^T, row_offset + i)."""
+    return SimmatCE.apply(Q, P_all, K.SIM_QP, row_offset, 1.0)
+
+
+def group_stats(loss, g, n_groups):
+    return GroupStats.apply(loss, g, n_groups)

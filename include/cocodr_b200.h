@@ -70,6 +70,123 @@ typedef struct cdr_gemm_args {
 
 int cdr_gemm(const cdr_gemm_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Memory-bound encoder kernels (K1, LN halves of K4/K6, bias gradients, casts).
+ * Replace HF BertEmbeddings / nn.LayerNorm (+ their autograd) reached through self.bert(...)
+ * (ANCE/model/models.py:226, COCO/modeling.py:199-204).  fp16 activations, fp32 parameters/statistics.
+ * in_scale multiplies the incoming activation gradient, out_scale the emitted parameter gradients
+ * (loss-scaling plumbing).  Parameter gradients are ACCUMULATED (+=) into the given buffers.
+ * ---------------------------------------------------------------------------------------------- */
+int cdr_embed_ln_fwd(const int64_t* ids, const float* word, const float* pos, const float* type0, const float* gamma,
+                     const float* beta, void* out, float* mean, float* rstd, int32_t n_seq, int32_t seq_len,
+                     int32_t hidden, int32_t vocab, float eps, void* stream);
+int cdr_embed_ln_bwd(const void* dy, const int64_t* ids, const float* word, const float* pos, const float* type0,
+                     const float* gamma, const float* mean, const float* rstd, float* dword, float* dpos, float* dtype0,
+                     float* dgamma, float* dbeta, int32_t n_seq, int32_t seq_len, int32_t hidden, int32_t vocab,
+                     int32_t pad_id, float in_scale, float out_scale, void* stream);
+/* y = LN(x); optional cls_out[n_seq, hidden] fp32 = row 0 of every sequence (K7, CLS pooling:
+ * ANCE/model/models.py:228, COCO/modeling.py:206) */
+int cdr_ln_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, float* cls_out,
+               int32_t n_seq, int32_t seq_len, int32_t hidden, float eps, void* stream);
+/* dx = LN'(dy [+ in_scale * dy_cls on row 0 of every sequence]); dbias (optional) += column sums of dx.
+ * dy (fp16) is already in the scaled-gradient domain; dy_cls (fp32) enters it through in_scale. */
+int cdr_ln_bwd(const void* dy, const float* dy_cls, const void* x, const float* gamma, const float* mean,
+               const float* rstd, void* dx, float* dgamma, float* dbeta, float* dbias, int32_t n_seq, int32_t seq_len,
+               int32_t hidden, float in_scale, float out_scale, void* stream);
+int cdr_colsum_f16(const void* x, float* out, int64_t rows, int64_t cols, int64_t ld, float scale, void* stream);
+int cdr_cast_f32_f16(const float* src, void* dst, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused multi-head attention (K3): softmax(Q K^T * scale + key_bias) V on tcgen05, head_dim 64,
+ * seq_len <= 128, straight from / to the packed QKV projection.  Replaces HF
+ * eager_attention_forward / SDPA inside BertSelfAttention (reached through ANCE/model/models.py:226,
+ * COCO/modeling.py:199-204); dropout p = 0.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct cdr_attn_args {
+  const void* qkv;       /* fp16 [n_seq*seq_len, 3*heads*64]  (Q | K | V) */
+  const float* key_bias; /* fp32 [n_seq, seq_len] additive key mask (0 / -large), or NULL */
+  void* out;             /* fp16 ctx [n_seq*seq_len, heads*64]   fwd: written, bwd: read */
+  float* lse;            /* fp32 [n_seq, heads, seq_len]         fwd: written, bwd: read */
+  const void* d_out;     /* bwd: fp16 [n_seq*seq_len, heads*64] */
+  void* dqkv;            /* bwd: fp16 [n_seq*seq_len, 3*heads*64] written */
+  int32_t n_seq, seq_len, heads, head_dim;
+  float scale;
+} cdr_attn_args;
+int cdr_attn_fwd(const cdr_attn_args* args, void* stream);
+int cdr_attn_bwd(const cdr_attn_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Contrastive heads (fp32 throughout: trained CLS dot products are ~217 with gaps ~0.3).
+ * ---------------------------------------------------------------------------------------------- */
+/* K8  ANCE pairwise NLL (ANCE/model/models.py:101-108): logits = [<q,a>, <q,b>],
+ * loss = -log_softmax(logits)[0], accs = argmax(logits) (int64). */
+int cdr_pair_nll_fwd(const float* q, const float* a, const float* b, int32_t n, int32_t dim, float* loss,
+                     int64_t* accs, float* logits, void* stream);
+int cdr_pair_nll_bwd(const float* q, const float* a, const float* b, const float* logits, const float* dloss,
+                     int32_t n, int32_t dim, float* dq, float* da, float* db, void* stream);
+
+/* K9 / K9'  similarity matrix + softmax cross-entropy.
+ *   CDR_SIM_COCO (COCO/modeling.py:244-248): S = q k^T, S[i, row_offset+i] = -inf,
+ *                target_i = (row_offset+i) ^ 1, loss_i = loss_scale * CE(S[i,:], target_i)
+ *   CDR_SIM_QP   (in-batch q x p InfoNCE over all-gathered passages): target_i = row_offset + i.
+ * bwd: dq (optional) = dS k, dk (optional) = dS^T q with dS = loss_scale*dloss_i*(softmax - onehot). */
+enum { CDR_SIM_QP = 0, CDR_SIM_COCO = 1 };
+typedef struct cdr_simmat_args {
+  const float* q;     /* [n_rows, dim] */
+  const float* k;     /* [n_keys, dim] */
+  float* scores;      /* [n_rows, n_keys] workspace: fwd writes, bwd reads */
+  float* gmat;        /* [n_rows, n_keys] workspace: bwd scratch */
+  float* loss;        /* [n_rows] fwd out */
+  float* lse;         /* [n_rows] fwd out, bwd in */
+  const float* dloss; /* [n_rows] bwd in */
+  float* dq;          /* [n_rows, dim] bwd out or NULL */
+  float* dk;          /* [n_keys, dim] bwd out or NULL */
+  int32_t n_rows, n_keys, dim, mode, row_offset;
+  float loss_scale;
+} cdr_simmat_args;
+int cdr_simmat_ce_fwd(const cdr_simmat_args* args, void* stream);
+int cdr_simmat_ce_bwd(const cdr_simmat_args* args, void* stream);
+
+/* K10 group statistics (ANCE/model/dro_loss.py:217-224): sums[g] = sum of loss_i with g_i == g,
+ * counts[g] = #{i: g_i == g} (both overwritten); bwd: dloss_i = dsums[g_i]. */
+int cdr_group_reduce_fwd(const float* loss, const int64_t* g, int32_t n, int32_t n_groups, float* sums, float* counts,
+                         void* stream);
+int cdr_group_reduce_bwd(const float* dsums, const int64_t* g, int32_t n, int32_t n_groups, float* dloss, void* stream);
+
+/* K12 Gram matrix of the per-group gradient rows (ANCE/model/dro_loss.py:235-237 computes
+ * normalise + G G^T; the row norms are the diagonal): gram[g,g] += x[g, 0:p] x[g, 0:p]^T, fp32. */
+int cdr_gram_f32(const float* x, int32_t g, int64_t p, int64_t ldx, float* gram, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K15 corpus scan: exact inner products of fp16 queries against HBM-resident fp16 doc embeddings
+ * (fp32 accumulate on tcgen05) with a fused threshold filter and a per-query sort; output ordered by
+ * (score desc, doc index asc).  Replaces faiss IndexFlatIP.add/search
+ * (evaluate/evaluation/evaluate_beir.py:220-224, ANCE/drivers/run_ann_data_gen.py:310-317,390).
+ * Admission thresholds come from a strided sample of the corpus; status[0] (device int32) counts the
+ * queries whose candidate set came out smaller than k or larger than the buffer.  Results are only
+ * valid when it is 0; otherwise the caller re-scans in chunks of <= cdr_scan_exhaustive_docs(k)
+ * documents (every document admitted: cannot fail) and folds them with cdr_topk_merge.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct cdr_scan_args {
+  const void* docs;    /* fp16 [n_docs, dim], row stride ld_docs */
+  const void* queries; /* fp16 [n_q, dim] contiguous */
+  float* out_scores;   /* [n_q, k] */
+  int64_t* out_ids;    /* [n_q, k] doc row index + doc_base */
+  void* workspace;
+  size_t workspace_bytes;
+  int32_t* status;     /* device int32[1] */
+  int64_t n_docs, ld_docs, doc_base;
+  int32_t n_q, dim, k;
+  int32_t reserved;
+} cdr_scan_args;
+size_t cdr_scan_workspace_bytes(int64_t n_docs, int32_t n_q, int32_t k);
+/* largest n_docs for which the scan admits every document (no sampling; cannot under/overflow) */
+int64_t cdr_scan_exhaustive_docs(int32_t k);
+int cdr_scan_topk(const cdr_scan_args* args, void* stream);
+/* merge n_in candidates per query (any order; e.g. all-gathered per-shard top-k lists) into the top k */
+int cdr_topk_merge(const float* scores, const int64_t* ids, int32_t n_q, int32_t n_in, int32_t k, float* out_scores,
+                   int64_t* out_ids, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,63 @@
+"""GPU: corpus scan (cocodr_b200.scan.search -> cdr_scan_topk) vs the CPU oracle (oracle/scan_ref.py) and the
+committed fixture tests/golden/scan_small.npz.  Bit-exact ranks on the exact-arithmetic corpus."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_scan_small_golden(golden_dir):
+    from cocodr_b200 import scan
+    from oracle import scan_ref
+    g = np.load(os.path.join(golden_dir, "scan_small.npz"))
+    for kind in ("exact", "gauss"):
+        Q, P = scan_ref.synth_corpus(6000, 37, 768, seed=7, kind=kind)
+        D, I = scan.search(Q.cuda(), P.cuda(), 100)
+        D, I = D.cpu().numpy(), I.cpu().numpy()
+        if kind == "exact":
+            assert (I == g["exact_I"]).all()
+            np.testing.assert_array_equal(D, g["exact_D"])
+        else:
+            np.testing.assert_allclose(D, g["gauss_D"], rtol=1e-5, atol=1e-4)
+            assert (I == g["gauss_I"]).mean() > 0.999
+
+
+@pytest.mark.parametrize("n_docs,n_q,k", [(200_000, 64, 100), (120_000, 200, 1000), (9000, 8, 10)])
+def test_scan_sampled_path_exact_ranks(n_docs, n_q, k):
+    """Large enough that the thresholds come from the corpus sample; exact corpus => bit-exact ranks."""
+    from cocodr_b200 import scan
+    from oracle import scan_ref
+    Q, P = scan_ref.synth_corpus(n_docs, n_q, 768, seed=11, kind="exact")
+    D, I = scan.search(Q.cuda(), P.cuda(), k)
+    Dr, Ir = scan_ref.search(Q, P, k)
+    assert (I.cpu().numpy() == Ir).all()
+    np.testing.assert_array_equal(D.cpu().numpy(), Dr)
+
+
+def test_scan_forced_chunked_fallback_and_sharded_merge():
+    from cocodr_b200 import scan
+    from oracle import scan_ref
+    Q, P = scan_ref.synth_corpus(30_000, 16, 256, seed=3, kind="exact")
+    Dr, Ir = scan_ref.search(Q, P, 50)
+    D, I = scan.search(Q.cuda(), P.cuda(), 50, force_exhaustive=True)
+    assert (I.cpu().numpy() == Ir).all()
+    # two document shards with global ids, merged like the multi-GPU path
+    Pc = P.cuda()
+    parts = [scan.search(Q.cuda(), Pc[lo:hi], 50, doc_base=lo) for lo, hi in ((0, 17_000), (17_000, 30_000))]
+    Dm, Im = scan.merge_topk(torch.cat([p[0] for p in parts], 1), torch.cat([p[1] for p in parts], 1), 50)
+    assert (Im.cpu().numpy() == Ir).all()
+    np.testing.assert_array_equal(Dm.cpu().numpy(), Dr)
+
+
+def test_scan_edge_cases():
+    from cocodr_b200 import scan
+    from oracle import scan_ref
+    Q, P = scan_ref.synth_corpus(40, 3, 64, seed=1, kind="exact")
+    D, I = scan.search(Q.cuda(), P.cuda(), 100)  # k > n_docs -> clamped like the oracle
+    Dr, Ir = scan_ref.search(Q, P, 100)
+    assert I.shape == (3, 40) and (I.cpu().numpy() == Ir).all()
+    with pytest.raises(RuntimeError):
+        scan.search(Q, P, 10)  # CPU tensors: no fallback
