@@ -1,0 +1,132 @@
+"""Drop-in ``BertModel`` whose forward/backward run on the sm_100a kernels.
+
+The reference never implements the encoder: it calls HuggingFace ``BertModel`` through ``self.bert(...)``
+(ANCE/model/models.py:225-229) / ``AutoModelForMaskedLM`` (COCO/modeling.py:199-204).  This class *is* a
+``transformers.BertModel`` as far as construction, ``from_pretrained`` / ``save_pretrained``, parameter names
+and ``state_dict`` go (the HF-named fp32 parameters stay the source of truth) -- only ``forward`` is replaced:
+embeddings+LN (K1), packed-QKV GEMM (K2), fused attention (K3), output / FFN GEMMs with fused
+bias / GELU / residual epilogues + LayerNorm (K4-K6) and fp32 CLS pooling (K7), all through the C ABI.
+"""
+import warnings
+
+import torch
+from transformers import BertModel as _HFBertModel
+from transformers.modeling_outputs import BaseModelOutputWithPoolingAndCrossAttentions
+
+from . import ops
+
+_warned_dropout = False
+
+
+def key_bias_from_mask(attention_mask):
+    """HF get_extended_attention_mask semantics on the key axis: (1 - mask) * finfo(float32).min, [B, L] fp32."""
+    if attention_mask is None:
+        return None
+    return (1.0 - attention_mask.to(torch.float32)) * torch.finfo(torch.float32).min
+
+
+def layer_params(layer):
+    """The 16 HF parameters of one BertLayer in the order ops.BertLayerFn expects."""
+    a, o = layer.attention, layer.output
+    return (a.self.query.weight, a.self.query.bias, a.self.key.weight, a.self.key.bias, a.self.value.weight,
+            a.self.value.bias, a.output.dense.weight, a.output.dense.bias, a.output.LayerNorm.weight,
+            a.output.LayerNorm.bias, layer.intermediate.dense.weight, layer.intermediate.dense.bias, o.dense.weight,
+            o.dense.bias, o.LayerNorm.weight, o.LayerNorm.bias)
+
+
+def check_config(config):
+    if config.hidden_size % config.num_attention_heads or config.hidden_size // config.num_attention_heads != 64:
+        raise RuntimeError("cocodr_b200 BERT kernels need head_dim == 64")
+    if getattr(config, "hidden_act", "gelu") != "gelu":
+        raise RuntimeError("cocodr_b200 BERT kernels implement exact-erf GELU only (hidden_act='gelu')")
+    if getattr(config, "position_embedding_type", "absolute") not in (None, "absolute"):
+        raise RuntimeError("cocodr_b200 BERT kernels implement absolute position embeddings only")
+
+
+def run_layer(layer, shadow, x, key_bias, n_seq, L, config, emit_cls=False):
+    """One BertLayer (HF module used as the parameter container) on internal fp16 [T, H] activations."""
+    return ops.BertLayerFn.apply(x, key_bias, *layer_params(layer), shadow, n_seq, L, config.num_attention_heads,
+                                 float(config.layer_norm_eps), emit_cls)
+
+
+class BertModel(_HFBertModel):
+    """``transformers.BertModel`` with the compute path replaced (see module docstring)."""
+
+    def __init__(self, config, add_pooling_layer=True):
+        super().__init__(config, add_pooling_layer=add_pooling_layer)
+        check_config(config)
+        self._cdr_init()
+
+    def _cdr_init(self):
+        object.__setattr__(self, "_shadows", [ops.LayerShadow() for _ in self.encoder.layer])
+
+    @classmethod
+    def adopt(cls, hf_bert):
+        """Turn an already-constructed HF BertModel into this class in place (keeps its parameters)."""
+        check_config(hf_bert.config)
+        hf_bert.__class__ = cls
+        hf_bert._cdr_init()
+        return hf_bert
+
+    # ------------------------------------------------------------------------------------------
+    def _check_inputs(self, input_ids, token_type_ids, position_ids, inputs_embeds):
+        global _warned_dropout
+        if inputs_embeds is not None or input_ids is None:
+            raise NotImplementedError("cocodr_b200.BertModel takes input_ids (inputs_embeds is not supported)")
+        if not input_ids.is_cuda:
+            raise RuntimeError("cocodr_b200.BertModel needs CUDA inputs: there is no CPU / eager fallback")
+        if position_ids is not None:
+            raise NotImplementedError("custom position_ids are not supported (positions are 0..L-1)")
+        if token_type_ids is not None and bool(token_type_ids.any()):
+            raise NotImplementedError("non-zero token_type_ids are not supported (the reference never passes them)")
+        if input_ids.shape[1] > self.config.max_position_embeddings:
+            raise RuntimeError("sequence longer than max_position_embeddings")
+        p = max(self.config.hidden_dropout_prob, self.config.attention_probs_dropout_prob)
+        if self.training and p > 0 and not _warned_dropout:
+            warnings.warn("cocodr_b200: dropout is not implemented in the sm_100a kernels yet; training runs with p=0 "
+                          f"(config asks for {p}).")
+            _warned_dropout = True
+
+    def encode(self, input_ids, attention_mask=None, token_type_ids=None, position_ids=None, inputs_embeds=None,
+               want_hidden=False, last_layer=None):
+        """Internal entry: returns (cls fp32 [B,H], last hidden fp16 [T,H], [hidden fp16] * (layers+1) or None)."""
+        self._check_inputs(input_ids, token_type_ids, position_ids, inputs_embeds)
+        if len(self._shadows) != len(self.encoder.layer):
+            self._cdr_init()
+        n_seq, L = input_ids.shape
+        e = self.embeddings
+        x = ops.EmbedLN.apply(input_ids.long(), e.word_embeddings.weight, e.position_embeddings.weight,
+                              e.token_type_embeddings.weight, e.LayerNorm.weight, e.LayerNorm.bias,
+                              float(self.config.layer_norm_eps))
+        kb = key_bias_from_mask(attention_mask)
+        hidden = [x] if want_hidden else None
+        cls = None
+        n_layers = len(self.encoder.layer)
+        for i, layer in enumerate(self.encoder.layer):
+            if i == n_layers - 1:
+                x, cls = run_layer(layer, self._shadows[i], x, kb, n_seq, L, self.config, emit_cls=True)
+            else:
+                x = run_layer(layer, self._shadows[i], x, kb, n_seq, L, self.config)
+            if want_hidden:
+                hidden.append(x)
+        return cls, x, hidden
+
+    def encode_cls(self, input_ids, attention_mask=None):
+        """``self(input_ids, attention_mask)[0][:, 0]`` without materialising the fp32 hidden states."""
+        return self.encode(input_ids, attention_mask)[0]
+
+    def forward(self, input_ids=None, attention_mask=None, token_type_ids=None, position_ids=None, inputs_embeds=None,
+                output_hidden_states=None, return_dict=None, **kwargs):
+        n_seq, L = input_ids.shape
+        want_hidden = bool(output_hidden_states) or bool(getattr(self.config, "output_hidden_states", False))
+        cls, last, hidden = self.encode(input_ids, attention_mask, token_type_ids, position_ids, inputs_embeds,
+                                        want_hidden=want_hidden)
+        seq_out = ops.HiddenToFloat.apply(last, n_seq, L)
+        # row 0 of the caller-visible tensor is the fp32 CLS straight from the last LayerNorm
+        seq_out = torch.cat([cls.unsqueeze(1), seq_out[:, 1:]], dim=1)
+        hs = tuple(ops.HiddenToFloat.apply(h, n_seq, L) for h in hidden) if want_hidden else None
+        out = BaseModelOutputWithPoolingAndCrossAttentions(last_hidden_state=seq_out, pooler_output=None,
+                                                           hidden_states=hs)
+        if return_dict is False:
+            return out.to_tuple()
+        return out

@@ -1,0 +1,223 @@
+"""Group-DRO losses of the ANCE stage, same surface as the reference's ``ANCE/model/dro_loss.py``
+(``DROGreedyLoss`` :11-135, ``AverageMeter`` :138-158, ``iDROLoss`` :160-254): constructor arguments,
+registered buffers (``h_fun``, ``sum_losses``, ``count_cat`` -- they ride along in the state dict),
+``forward`` signatures and return tuples are identical.
+
+Group statistics (K10) and the Gram matrix of per-group gradients (K12) run through the C ABI.  In a
+multi-GPU run the reference all-reduces the full [G, P_last] gradient matrix (dro_loss.py:232, 4.25 GB at
+G=50 / BERT-base); here every rank reduce-scatters it along P_last, takes the Gram of its column shard
+and all-reduces the [G, G] result -- the same numbers with half the bytes on NVLink and no full-matrix
+re-read.
+"""
+from collections import defaultdict
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import kernels as K
+from . import ops
+
+
+def _world():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+class AverageMeter(object):
+    """Running average (ANCE/model/dro_loss.py:138-158)."""
+
+    def __init__(self):
+        self.reset()
+
+    def reset(self):
+        self.val = 0
+        self.avg = 0
+        self.sum = 0
+        self.count = 0
+
+    def update(self, val, n=1):
+        self.val = val
+        self.sum += val * n
+        self.count += n
+        self.avg = self.sum / self.count if self.count > 0 else 0.
+
+
+class DROGreedyLoss(nn.Module):
+    def __init__(self, args, n_groups, alpha, eps, ema=0.1, weight_ema=False, weight_cutoff=True, fraction=None):
+        super().__init__()
+        self.args = args
+        self.alpha = alpha
+        self.ema = ema
+        self.eps = eps
+        self.weight_cutoff = weight_cutoff
+        self.weight_ema = weight_ema
+        self.n_groups = n_groups
+        self.id2group = {str(x): f"group{x}" for x in range(n_groups)}
+        self.n_splits = n_groups
+        self.register_buffer('h_fun', torch.ones(self.n_splits))
+        self.register_buffer('sum_losses', torch.zeros(self.n_splits))
+        if fraction is not None:
+            self.register_buffer('fraction', torch.as_tensor(fraction).float())
+            self.register_buffer('count_cat', None)
+        else:
+            self.register_buffer('count_cat', torch.ones(self.n_splits))
+        self.idx_dict = defaultdict(lambda: len(self.idx_dict))
+        for i in range(self.n_groups):
+            _ = self.idx_dict['[' + str(i) + ']']
+
+    def reset(self):
+        self.h_fun.fill_(1.)
+        self.sum_losses.fill_(0.)
+        if self.count_cat is not None:
+            self.count_cat.fill_(1.)
+
+    def reset_loss(self):
+        self.h_fun.fill_(1.)
+        self.sum_losses.fill_(0.)
+
+    def forward(self, losses, g, w=None):
+        """dro_loss.py:49-86 -> (robust_loss, group_losses[G], group_counts[G])."""
+        if w is not None:
+            losses = losses * w
+        batch_size = losses.size(0)
+        gdro_losses, gdro_counts = ops.group_stats(losses, g, self.n_groups)
+        robust_loss = (gdro_losses * self.h_fun).sum() / batch_size
+        with torch.no_grad():
+            if self.training:
+                if _world() > 1:
+                    # one fused exchange instead of the reference's two all_gathers (:64-65)
+                    packed = torch.stack([gdro_losses.detach(), gdro_counts])
+                    dist.all_reduce(packed)
+                    losses_agg, counts_agg = packed[0], packed[1]
+                else:
+                    losses_agg, counts_agg = gdro_losses.detach(), gdro_counts
+                group_losses_agg = losses_agg / (counts_agg + (counts_agg == 0).float())
+                valid = counts_agg > 0
+                self.sum_losses = torch.where(valid, self.sum_losses * (1 - self.ema) + group_losses_agg * self.ema,
+                                              self.sum_losses)
+                if self.count_cat is not None:
+                    self.count_cat = self.count_cat * (1 - self.ema) + counts_agg * self.ema
+                self.update_mw()
+            group_losses = gdro_losses.detach() / (gdro_counts + (gdro_counts == 0).float())
+        return robust_loss, group_losses, gdro_counts
+
+    def update_mw(self):
+        """dro_loss.py:88-120: greedy re-weighting of the worst groups (alpha-fraction cut-off)."""
+        past_losses = self.sum_losses
+        if self.count_cat is not None:
+            past_frac = self.count_cat / self.count_cat.sum()
+        else:
+            past_frac = self.fraction
+        sorted_losses, sort_id = torch.sort(past_losses, descending=True)
+        sorted_frac = past_frac[sort_id]
+        cutoff_count = torch.sum(torch.cumsum(sorted_frac, 0) < self.alpha)
+        cutoff_count = torch.clamp(cutoff_count, max=sorted_frac.numel() - 1)
+        idx = torch.arange(sorted_frac.numel(), device=sorted_frac.device)
+        top = idx < cutoff_count
+        tmp_sorted = torch.where(top, torch.full_like(sorted_frac, 1.0 / self.alpha),
+                                 torch.full_like(sorted_frac, self.eps))
+        leftover_mass = 1.0 - (sorted_frac * top.float()).sum() / self.alpha
+        tiebreak = torch.clamp(leftover_mass / sorted_frac[cutoff_count], min=self.eps)
+        tmp_sorted = torch.where(idx == cutoff_count, tiebreak.expand_as(tmp_sorted), tmp_sorted)
+        tmp = torch.empty_like(tmp_sorted)
+        tmp[sort_id] = tmp_sorted
+        if self.weight_ema:
+            tmp = torch.clamp(tmp, min=self.eps)
+            self.h_fun = self.h_fun * (1 - self.ema) + tmp * self.ema
+        else:
+            self.h_fun = tmp
+
+
+class iDROLoss(DROGreedyLoss):
+    def __init__(self, args, n_groups, alpha, eps, ema, rho, reg=0, weight_ema=False, weight_cutoff=True,
+                 fraction=None):
+        super().__init__(args, n_groups, alpha, eps, ema, weight_ema, weight_cutoff, fraction)
+        self.rho = rho
+        self.reg = reg
+        self.tol = 1e-5
+        self.max_iter = 1200
+        self.para_name = {}
+
+    def _params(self, model):
+        """dro_loss.py:174-190: parameters of the last 3 (base) / 2 (large) encoder layers."""
+        if self.args.model_size == 'large':
+            select = ['layer.23', 'layer.22']
+        else:
+            select = ['layer.10', 'layer.11', 'layer.9']
+        if len(self.para_name) == 0:
+            params = []
+            for name, param in model.named_parameters():
+                if any(name.find(s) >= 0 for s in select):
+                    params.append(param)
+                    self.para_name[name] = 1
+        else:
+            params = [param for (name, param) in model.named_parameters() if name in self.para_name]
+        return params
+
+    def _get_grad(self, params, gdro_losses_agg, gdro_counts_agg):
+        """[G, P_last] fp32 matrix of per-group gradients of the local group means (rows of absent groups = 0).
+
+        Same contract as dro_loss.py:192-204 (one ``autograd.grad(..., retain_graph=True)`` per present
+        group through the per-layer autograd Functions), written row-by-row into one preallocated matrix
+        instead of cat-ing G vectors."""
+        dim = sum(p.numel() for p in params)
+        mat = torch.zeros(self.n_groups, dim, dtype=torch.float32, device=gdro_losses_agg.device)
+        present = torch.nonzero(gdro_counts_agg > 0).flatten().tolist()
+        for li in present:
+            grads = torch.autograd.grad(gdro_losses_agg[li], params, retain_graph=True, allow_unused=True)
+            off = 0
+            for p, gr in zip(params, grads):
+                n = p.numel()
+                if gr is not None:
+                    mat[li, off:off + n].copy_(gr.reshape(-1))
+                off += n
+        return mat
+
+    def _gram(self, all_grads):
+        """Gram matrix of the rank-summed gradient rows (what :232-237 compute through a full all-reduce)."""
+        G, P = all_grads.shape
+        gram = torch.zeros(G, G, dtype=torch.float32, device=all_grads.device)
+        W = _world()
+        if W == 1:
+            K.gram_f32(all_grads, gram)
+            return gram
+        shard = (P + W - 1) // W
+        shard = (shard + 3) // 4 * 4
+        padded = torch.zeros(W, G, shard, dtype=torch.float32, device=all_grads.device)
+        for r in range(W):  # column shard r of every row, laid out [W, G, shard] for reduce_scatter
+            lo, hi = r * shard, min(P, (r + 1) * shard)
+            if hi > lo:
+                padded[r, :, :hi - lo].copy_(all_grads[:, lo:hi])
+        mine = torch.empty(G, shard, dtype=torch.float32, device=all_grads.device)
+        dist.reduce_scatter_tensor(mine, padded.view(W * G, shard))
+        K.gram_f32(mine, gram)
+        dist.all_reduce(gram)
+        return gram
+
+    def forward(self, model, losses, g):
+        """dro_loss.py:216-254 -> (robust_loss, group mean losses[G] detached, group counts[G])."""
+        if not self.training:
+            raise RuntimeError("iDROLoss.forward is only defined in training mode (as in the reference, where "
+                               "gdro_counts_agg is undefined otherwise: dro_loss.py:222-226)")
+        sums, counts = ops.group_stats(losses, g, self.n_groups)
+        means = sums / (counts + (counts == 0).float())
+        robust_loss = (means * self.h_fun).sum()
+
+        mask = (counts > 0).float()
+        params = self._params(model)
+        all_grads = self._get_grad(params, means, counts)
+        gram = self._gram(all_grads)
+        with torch.no_grad():
+            norm = torch.sqrt(torch.diagonal(gram).clamp_min(0)).unsqueeze(-1)  # ||G_g||
+            denom = 1e-12 + norm
+            RTG = gram / (denom * denom.t())
+            _gl = torch.pow(means.detach().unsqueeze(-1), self.alpha)
+            RTG = torch.mm(_gl, _gl.t()) * RTG
+            _exp = self.rho * torch.mean(RTG, dim=0)
+            _exp = _exp * mask
+            _exp = _exp - _exp.max()
+            weight = torch.exp(_exp)
+            h = torch.pow(self.h_fun, self.ema) * weight * (counts != 0).float()
+            h = h / h.sum()
+            self.h_fun = torch.clamp(h, min=self.eps)
+        return robust_loss, means.detach(), counts.detach()

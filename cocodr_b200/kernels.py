@@ -12,6 +12,16 @@ from ._lib import (EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_DGELU, EPI_F32_ATOMIC, 
                    EPI_STORE_F16, check, ptr, stream_ptr)
 
 
+# ---- instrumentation used by bench.py: kernel-launch counter and optional per-GEMM CUDA-event timing
+launches = 0          # number of CUDA kernels launched by this library so far (our own kernels only)
+gemm_events = None    # when a list: gemm() appends (flops, start_event, end_event)
+
+
+def _count(n):
+    global launches
+    launches += n
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -37,7 +47,15 @@ def gemm(a, b, out, *, M, N, K, a_major=0, b_major=0, epilogue=EPI_STORE_F16, bi
     g.dbg_lbo, g.dbg_sbo = dbg_lbo, dbg_sbo
     if bias is not None:
         assert bias.dtype == torch.float32
-    check(_lib.load().cdr_gemm(C.byref(g), stream_ptr()), "cdr_gemm")
+    if gemm_events is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(_lib.load().cdr_gemm(C.byref(g), stream_ptr()), "cdr_gemm")
+        e1.record()
+        gemm_events.append((2.0 * M * N * K, e0, e1))
+    else:
+        check(_lib.load().cdr_gemm(C.byref(g), stream_ptr()), "cdr_gemm")
+    _count(1)
     return out
 
 
@@ -61,6 +79,7 @@ def embed_ln_fwd(ids, word, pos, type0, gamma, beta, out, mean, rstd, *, n_seq, 
     check(_lib_().cdr_embed_ln_fwd(_p(ids), _p(word), _p(pos), _p(type0), _p(gamma), _p(beta), _p(out), _p(mean),
                                    _p(rstd), _i32(n_seq), _i32(seq_len), _i32(hidden), _i32(vocab), _f32(eps),
                                    stream_ptr()), "cdr_embed_ln_fwd")
+    _count(1)
 
 
 def embed_ln_bwd(dy, ids, word, pos, type0, gamma, mean, rstd, dword, dpos, dtype0, dgamma, dbeta, *, n_seq, seq_len,
@@ -70,6 +89,7 @@ def embed_ln_bwd(dy, ids, word, pos, type0, gamma, mean, rstd, dword, dpos, dtyp
                                    _p(dword), _p(dpos), _p(dtype0), _p(dgamma), _p(dbeta), _i32(n_seq), _i32(seq_len),
                                    _i32(hidden), _i32(vocab), _i32(pad_id), _f32(in_scale), _f32(out_scale),
                                    stream_ptr()), "cdr_embed_ln_bwd")
+    _count(1)
 
 
 def ln_fwd(x, gamma, beta, y, mean, rstd, cls_out, *, n_seq, seq_len, hidden, eps):
@@ -77,6 +97,7 @@ def ln_fwd(x, gamma, beta, y, mean, rstd, cls_out, *, n_seq, seq_len, hidden, ep
     assert x.dtype == torch.float16 and y.dtype == torch.float16
     check(_lib_().cdr_ln_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), _p(cls_out), _i32(n_seq),
                              _i32(seq_len), _i32(hidden), _f32(eps), stream_ptr()), "cdr_ln_fwd")
+    _count(1)
 
 
 def ln_bwd(dy, dy_cls, x, gamma, mean, rstd, dx, dgamma, dbeta, dbias, *, n_seq, seq_len, hidden, in_scale=1.0,
@@ -85,6 +106,7 @@ def ln_bwd(dy, dy_cls, x, gamma, mean, rstd, dx, dgamma, dbeta, dbias, *, n_seq,
     check(_lib_().cdr_ln_bwd(_p(dy), _p(dy_cls), _p(x), _p(gamma), _p(mean), _p(rstd), _p(dx), _p(dgamma), _p(dbeta),
                              _p(dbias), _i32(n_seq), _i32(seq_len), _i32(hidden), _f32(in_scale), _f32(out_scale),
                              stream_ptr()), "cdr_ln_bwd")
+    _count(1)
 
 
 def colsum(x, out, *, rows, cols, ld=None, scale=1.0):
@@ -92,6 +114,7 @@ def colsum(x, out, *, rows, cols, ld=None, scale=1.0):
     assert x.dtype == torch.float16 and out.dtype == torch.float32
     check(_lib_().cdr_colsum_f16(_p(x), _p(out), _i64(rows), _i64(cols), _i64(ld if ld is not None else x.stride(0)),
                                  _f32(scale), stream_ptr()), "cdr_colsum_f16")
+    _count(1)
 
 
 def cast_f32_f16(src, dst):
@@ -99,6 +122,7 @@ def cast_f32_f16(src, dst):
     assert src.dtype == torch.float32 and dst.dtype == torch.float16 and src.numel() == dst.numel()
     assert src.is_contiguous() and dst.is_contiguous()
     check(_lib_().cdr_cast_f32_f16(_p(src), _p(dst), _i64(src.numel()), stream_ptr()), "cdr_cast_f32_f16")
+    _count(1)
 
 
 def _attn_args(qkv, key_bias, out, lse, n_seq, seq_len, heads, scale, d_out=None, dqkv=None):
@@ -117,6 +141,7 @@ def attn_fwd(qkv, key_bias, out, lse, *, n_seq, seq_len, heads, scale=0.125):
     assert qkv.is_contiguous() and out.is_contiguous()
     a = _attn_args(qkv, key_bias, out, lse, n_seq, seq_len, heads, scale)
     check(_lib_().cdr_attn_fwd(C.byref(a), stream_ptr()), "cdr_attn_fwd")
+    _count(1)
 
 
 def attn_bwd(qkv, key_bias, out, lse, d_out, dqkv, *, n_seq, seq_len, heads, scale=0.125):
@@ -124,6 +149,7 @@ def attn_bwd(qkv, key_bias, out, lse, d_out, dqkv, *, n_seq, seq_len, heads, sca
     assert d_out.dtype == torch.float16 and dqkv.dtype == torch.float16 and d_out.is_contiguous()
     a = _attn_args(qkv, key_bias, out, lse, n_seq, seq_len, heads, scale, d_out, dqkv)
     check(_lib_().cdr_attn_bwd(C.byref(a), stream_ptr()), "cdr_attn_bwd")
+    _count(1)
 
 
 def pair_nll_fwd(q, a, b, loss, accs, logits):
@@ -131,12 +157,14 @@ def pair_nll_fwd(q, a, b, loss, accs, logits):
     n, dim = q.shape
     check(_lib_().cdr_pair_nll_fwd(_p(q), _p(a), _p(b), _i32(n), _i32(dim), _p(loss), _p(accs), _p(logits),
                                    stream_ptr()), "cdr_pair_nll_fwd")
+    _count(1)
 
 
 def pair_nll_bwd(q, a, b, logits, dloss, dq, da, db):
     n, dim = q.shape
     check(_lib_().cdr_pair_nll_bwd(_p(q), _p(a), _p(b), _p(logits), _p(dloss), _i32(n), _i32(dim), _p(dq), _p(da),
                                    _p(db), stream_ptr()), "cdr_pair_nll_bwd")
+    _count(1)
 
 
 SIM_QP, SIM_COCO = 0, 1
@@ -156,6 +184,7 @@ def simmat_ce_fwd(q, k, scores, loss, lse, *, mode, row_offset=0, loss_scale=1.0
     a = _simmat_args(q, k, scores, lse, mode, row_offset, loss_scale)
     a.loss = loss.data_ptr()
     check(_lib_().cdr_simmat_ce_fwd(C.byref(a), stream_ptr()), "cdr_simmat_ce_fwd")
+    _count(2)
 
 
 def simmat_ce_bwd(q, k, scores, lse, dloss, gmat, dq, dk, *, mode, row_offset=0, loss_scale=1.0):
@@ -165,6 +194,7 @@ def simmat_ce_bwd(q, k, scores, lse, dloss, gmat, dq, dk, *, mode, row_offset=0,
     a.dq = dq.data_ptr() if dq is not None else 0
     a.dk = dk.data_ptr() if dk is not None else 0
     check(_lib_().cdr_simmat_ce_bwd(C.byref(a), stream_ptr()), "cdr_simmat_ce_bwd")
+    _count(3)
 
 
 def group_reduce_fwd(loss, g, sums, counts, *, n_groups):
@@ -172,11 +202,13 @@ def group_reduce_fwd(loss, g, sums, counts, *, n_groups):
     assert g.dtype == torch.int64 and loss.dtype == torch.float32
     check(_lib_().cdr_group_reduce_fwd(_p(loss), _p(g), _i32(loss.numel()), _i32(n_groups), _p(sums), _p(counts),
                                        stream_ptr()), "cdr_group_reduce_fwd")
+    _count(1)
 
 
 def group_reduce_bwd(dsums, g, dloss, *, n_groups):
     check(_lib_().cdr_group_reduce_bwd(_p(dsums), _p(g), _i32(g.numel()), _i32(n_groups), _p(dloss), stream_ptr()),
           "cdr_group_reduce_bwd")
+    _count(1)
 
 
 def gram_f32(x, gram):
@@ -185,6 +217,7 @@ def gram_f32(x, gram):
     assert x.dtype == torch.float32 and gram.dtype == torch.float32 and x.stride(1) == 1
     check(_lib_().cdr_gram_f32(_p(x), _i32(x.shape[0]), _i64(x.shape[1]), _i64(x.stride(0)), _p(gram), stream_ptr()),
           "cdr_gram_f32")
+    _count(1)
 
 
 def scan_workspace_bytes(n_docs, n_q, k):
@@ -205,6 +238,7 @@ def scan_topk(docs, queries, out_scores, out_ids, workspace, status, *, k, doc_b
     a.n_docs, a.ld_docs, a.doc_base = docs.shape[0], docs.stride(0), doc_base
     a.n_q, a.dim, a.k = queries.shape[0], queries.shape[1], k
     check(_lib_().cdr_scan_topk(C.byref(a), stream_ptr()), "cdr_scan_topk")
+    _count(3 if docs.shape[0] <= scan_exhaustive_docs(k) else 5)
 
 
 def topk_merge(scores, ids, out_scores, out_ids, *, k):
@@ -213,3 +247,4 @@ def topk_merge(scores, ids, out_scores, out_ids, *, k):
     n_q, n_in = scores.shape
     check(_lib_().cdr_topk_merge(_p(scores), _p(ids), _i32(n_q), _i32(n_in), _i32(k), _p(out_scores), _p(out_ids),
                                  stream_ptr()), "cdr_topk_merge")
+    _count(1)

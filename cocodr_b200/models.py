@@ -1,0 +1,249 @@
+"""ANCE-stage bi-encoder, same surface as the reference's ``ANCE/model/models.py``:
+``EmbeddingMixin`` (:41-77), ``NLL.forward_model`` (:80-115), ``BertDot_NLL_LN`` (:194-290) and the
+``MSMarcoConfigDict`` registry (:418-445, key ``rdot_nll_condenser``) -- constructor, attributes
+(``bert``, ``classifier``, ``embeddingHead``, ``norm``, ``total``, ``correct``, ``dro_type``, ``n_groups``,
+``accum_loss``, ``accum_group_loss``), methods (``query_emb``, ``body_emb``, ``forward``, ``add_group_loss``,
+``output_state``, ``gather_tensors``) and state-dict keys are the reference's, so
+``MSMarcoConfigDict[name].model_class.from_pretrained(path, config=...)`` (run_ann.py:896-901) yields a
+drop-in whose encoder and losses run on the sm_100a kernels.
+
+Differences that are deliberate and documented:
+  * q / p+ / p- towers of equal length run as ONE encoder launch (the reference runs three sequential
+    passes over the same weights, models.py:97-99);
+  * the per-forward ``all_reduce(train_size)`` + ``.item()`` bookkeeping (:256-258) becomes arithmetic
+    (batch * world size) and the (2 + 2G) ``.item()`` syncs of the meters (:269-271) become one transfer;
+  * ``BertDot_InBatch_NLL_LN`` adds the q x p in-batch InfoNCE over all-gathered passages that
+    BASELINE.json's configs describe (K9'); the reference defines the gather helper (:282-290) but
+    never calls it.
+"""
+import logging
+
+import torch
+import torch.distributed as dist
+from torch import nn
+from transformers import BertConfig, BertForSequenceClassification, BertTokenizer
+
+from . import ops
+from .bert import BertModel
+from .dro_loss import AverageMeter, DROGreedyLoss, iDROLoss
+
+logger = logging.getLogger(__name__)
+
+
+def _world():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def _rank():
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
+class AllGatherWithGrad(torch.autograd.Function):
+    """all_gather whose backward returns every rank's gradient for the local slice (reduce-scatter), so the
+    multi-GPU loss equals the single-process loss on the concatenated batch once DDP averages over ranks."""
+
+    @staticmethod
+    def forward(ctx, t):
+        W = _world()
+        out = torch.empty(W * t.shape[0], *t.shape[1:], dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t.contiguous())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        W = _world()
+        out = torch.empty(g.shape[0] // W, *g.shape[1:], dtype=g.dtype, device=g.device)
+        dist.reduce_scatter_tensor(out, g.contiguous())
+        return out
+
+
+def gather_with_grad(t):
+    return AllGatherWithGrad.apply(t) if _world() > 1 else t
+
+
+class EmbeddingMixin:
+    """models.py:41-77."""
+
+    def __init__(self, model_argobj):
+        self.use_mean = False if model_argobj is None else model_argobj.use_mean
+
+    def _init_weights(self, module):
+        if isinstance(module, (nn.Linear, nn.Embedding, nn.Conv1d)):
+            module.weight.data.normal_(mean=0.0, std=0.02)
+
+    def masked_mean(self, t, mask):
+        s = torch.sum(t * mask.unsqueeze(-1).float(), axis=1)
+        d = mask.sum(axis=1, keepdim=True).float()
+        return s / d
+
+    def masked_mean_or_first(self, emb_all, mask):
+        assert isinstance(emb_all, tuple)
+        if self.use_mean:
+            return self.masked_mean(emb_all[0], mask)
+        return emb_all[0][:, 0]
+
+    def query_emb(self, input_ids, attention_mask):
+        raise NotImplementedError("Please Implement this method")
+
+    def body_emb(self, input_ids, attention_mask):
+        raise NotImplementedError("Please Implement this method")
+
+
+class NLL(EmbeddingMixin):
+    def _towers(self, q_ids, q_mask, a_ids, a_mask, b_ids=None, b_mask=None):
+        """CLS embeddings of 2 or 3 towers; one fused encoder launch when the towers share a length."""
+        ids, masks = [q_ids, a_ids], [q_mask, a_mask]
+        if b_ids is not None:
+            ids.append(b_ids)
+            masks.append(b_mask)
+        if all(t.shape == ids[0].shape for t in ids):
+            emb = self.query_emb(torch.cat(ids, 0), torch.cat(masks, 0))
+            return emb.chunk(len(ids), 0)
+        embs = [self.query_emb(q_ids, q_mask)] + [self.body_emb(i, m) for i, m in zip(ids[1:], masks[1:])]
+        return tuple(embs)
+
+    def forward_model(self, query_ids, attention_mask_q, input_ids_a=None, attention_mask_a=None, input_ids_b=None,
+                      attention_mask_b=None, is_query=True, group_ids=None):
+        """models.py:80-115: embeddings only, or (loss[B], accs[B], logits[B,2]) of the triplet NLL."""
+        if input_ids_b is None and is_query:
+            return self.query_emb(query_ids, attention_mask_q)
+        elif input_ids_b is None:
+            return self.body_emb(query_ids, attention_mask_q)
+        q_embs, a_embs, b_embs = self._towers(query_ids, attention_mask_q, input_ids_a, attention_mask_a, input_ids_b,
+                                              attention_mask_b)
+        loss, accs, logit_matrix = ops.pair_nll(q_embs, a_embs, b_embs)
+        return loss, accs, logit_matrix
+
+
+class BertDot_NLL_LN(NLL, BertForSequenceClassification):
+    """models.py:194-290 with ``self.bert`` running on the B200 kernels."""
+
+    def __init__(self, config, model_argobj=None):
+        NLL.__init__(self, model_argobj)
+        BertForSequenceClassification.__init__(self, config)
+        BertModel.adopt(self.bert)
+        self.embeddingHead = nn.Linear(config.hidden_size, 768)
+        self.norm = nn.LayerNorm(768)
+        self.use_moco = False
+        self.apply(self._init_weights)
+        self.total = 0
+        self.correct = 0
+        self.prob_diff = []
+        self.dro_type = 'erm'
+
+    def add_group_loss(self, args, n_groups, dro_type, alpha, eps, ema=0.1, rho=0.1, weight_ema=True):
+        if dro_type == 'dro-greedy':
+            self.dro_type = dro_type
+            self.loss = DROGreedyLoss(args, n_groups, alpha, eps, ema, weight_ema)
+        elif dro_type == 'idro':
+            self.dro_type = dro_type
+            self.loss = iDROLoss(args, n_groups, alpha, eps, ema, rho)
+        else:
+            logger.info("Warning! No training strategy selected")
+        if hasattr(self, "loss"):
+            self.loss.to(self.bert.embeddings.word_embeddings.weight.device)
+        self.n_groups = n_groups
+        self.accum_loss = AverageMeter()
+        self.accum_group_loss = [AverageMeter() for _ in range(n_groups)]
+
+    def query_emb(self, input_ids, attention_mask):
+        """``self.bert(input_ids, attention_mask)[0][:, 0]`` (models.py:225-229), fp32 [B, H]."""
+        if not isinstance(self.bert, BertModel):
+            BertModel.adopt(self.bert)
+        return self.bert.encode_cls(input_ids, attention_mask)
+
+    def body_emb(self, input_ids, attention_mask):
+        return self.query_emb(input_ids, attention_mask)
+
+    def _route_loss(self, loss, train_acc, logits, group_ids, weights):
+        """models.py:256-273: bookkeeping, ERM mean or DRO loss, meters."""
+        self.total += int(train_acc.shape[0]) * _world()
+        if group_ids is None:
+            if weights is not None:
+                loss = loss * weights
+            return loss.mean(), train_acc, logits
+        if self.dro_type == 'idro':
+            robust_loss, group_losses, group_counts = self.loss(self.bert, loss, group_ids)
+        else:
+            robust_loss, group_losses, group_counts = self.loss(loss, group_ids, weights)
+        host = torch.cat([robust_loss.detach().reshape(1), group_losses, group_counts]).tolist()  # one sync
+        self.accum_loss.update(host[0], loss.size(0))
+        G = self.n_groups
+        for i in range(G):
+            self.accum_group_loss[i].update(host[1 + i], host[1 + G + i])
+        return robust_loss, train_acc, group_losses, group_counts
+
+    def forward(self, query_ids, attention_mask_q, input_ids_a=None, attention_mask_a=None, input_ids_b=None,
+                attention_mask_b=None, is_query=True, group_ids=None, weights=None):
+        out = self.forward_model(query_ids, attention_mask_q, input_ids_a, attention_mask_a, input_ids_b,
+                                 attention_mask_b, is_query, group_ids)
+        if not isinstance(out, tuple):
+            return out
+        loss, train_acc, logits = out
+        return self._route_loss(loss, train_acc, logits, group_ids, weights)
+
+    def output_state(self):
+        h = self.loss.h_fun.detach().cpu().numpy()
+        h_fun = {self.loss.id2group[str(i)]: h[i] for i in range(self.n_groups)}
+        sum_loss = {self.loss.id2group[str(i)]: self.accum_group_loss[i].avg for i in range(self.n_groups)}
+        return h_fun, sum_loss
+
+    def _gather_tensor(self, t):
+        all_tensors = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+        dist.all_gather(all_tensors, t)
+        all_tensors[_rank()] = t
+        return all_tensors
+
+    def gather_tensors(self, *tt):
+        return [torch.cat(self._gather_tensor(t)) for t in tt]
+
+
+class BertDot_InBatch_NLL_LN(BertDot_NLL_LN):
+    """q x p in-batch InfoNCE with cross-GPU all-gathered passages (K9').
+
+    ``loss_i = CE(q_i . P_all^T, rank*B + i)`` over the passages of every rank (hard negatives
+    ``input_ids_b``, when given, are appended to the key set).  ERM / iDRO / DRO-greedy routing of the
+    per-sample losses is inherited unchanged."""
+
+    def forward_model(self, query_ids, attention_mask_q, input_ids_a=None, attention_mask_a=None, input_ids_b=None,
+                      attention_mask_b=None, is_query=True, group_ids=None):
+        if input_ids_a is None:
+            return super().forward_model(query_ids, attention_mask_q, is_query=is_query)
+        embs = self._towers(query_ids, attention_mask_q, input_ids_a, attention_mask_a, input_ids_b, attention_mask_b)
+        q_embs = embs[0]
+        B = q_embs.shape[0]
+        keys = gather_with_grad(embs[1])
+        offset = _rank() * B
+        if len(embs) == 3:
+            keys = torch.cat([keys, gather_with_grad(embs[2])], 0)
+        loss = ops.qp_infonce(q_embs, keys, row_offset=offset)
+        with torch.no_grad():
+            pos = (q_embs * embs[1]).sum(-1)
+            neg = (q_embs * embs[2]).sum(-1) if len(embs) == 3 else pos
+            logits = torch.stack([pos, neg], 1)
+            accs = torch.argmax(logits, dim=1)
+        return loss, accs, logits
+
+
+default_process_fn = None  # tokenisation lives outside the hot path
+
+
+class MSMarcoConfig:
+    def __init__(self, name, model, process_fn=default_process_fn, use_mean=True, tokenizer_class=BertTokenizer,
+                 config_class=BertConfig):
+        self.name = name
+        self.process_fn = process_fn
+        self.model_class = model
+        self.use_mean = use_mean
+        self.tokenizer_class = tokenizer_class
+        self.config_class = config_class
+
+
+configs = [
+    MSMarcoConfig(name="rdot_nll_condenser", model=BertDot_NLL_LN, tokenizer_class=BertTokenizer,
+                  config_class=BertConfig, use_mean=False),
+    MSMarcoConfig(name="rdot_nll_condenser_inbatch", model=BertDot_InBatch_NLL_LN, tokenizer_class=BertTokenizer,
+                  config_class=BertConfig, use_mean=False),
+]
+
+MSMarcoConfigDict = {cfg.name: cfg for cfg in configs}

@@ -1,0 +1,61 @@
+"""CPU: the C-ABI shared library loads, exports every symbol include/cocodr_b200.h declares, its argument
+structs have the layout the ctypes binding assumes, and host-only entry points answer without a GPU."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+    ge.build()
+    from cocodr_b200 import _lib
+    return _lib.load()
+
+
+def test_every_declared_symbol_is_exported(lib):
+    from cocodr_b200 import _lib
+    names = _lib.declared_symbols()
+    assert len(names) >= 20 and "cdr_gemm" in names and "cdr_attn_bwd" in names and "cdr_scan_topk" in names
+    for n in names:
+        assert hasattr(lib, n), n
+    assert lib.cdr_version() >= 100
+
+
+def test_struct_layouts_match_the_header(lib, tmp_path):
+    from cocodr_b200 import _lib
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "cocodr_b200.h"\nint main(){printf("%zu %zu %zu %zu\\n",'
+                   'sizeof(cdr_gemm_args),sizeof(cdr_attn_args),sizeof(cdr_simmat_args),sizeof(cdr_scan_args));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    sizes = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert sizes == [C.sizeof(_lib.GemmArgs), C.sizeof(_lib.AttnArgs), C.sizeof(_lib.SimmatArgs), C.sizeof(_lib.ScanArgs)]
+
+
+def test_host_only_entry_points(lib):
+    from cocodr_b200 import kernels as K
+    assert K.scan_exhaustive_docs(100) == 8192 and K.scan_exhaustive_docs(1000) == 8192
+    assert K.scan_exhaustive_docs(2000) == 16384
+    small = K.scan_workspace_bytes(6000, 37, 100)
+    big = K.scan_workspace_bytes(1_000_000, 1000, 1000)
+    assert 0 < small < big
+    assert big >= 1000 * 8192 * 8 + 1000 * 8192 * 4
+    assert K.scan_workspace_bytes(0, 10, 10) == 0
+
+
+def test_bad_arguments_fail_loudly_without_a_gpu(lib):
+    from cocodr_b200 import _lib
+    rc = lib.cdr_gemm(None, None)
+    assert rc == -1 and b"null" in lib.cdr_last_error()
+    a = _lib.AttnArgs()
+    a.qkv, a.n_seq, a.seq_len, a.heads, a.head_dim = 16, 1, 300, 1, 64
+    assert lib.cdr_attn_fwd(C.byref(a), None) == -1 and b"seq_len" in lib.cdr_last_error()
+    with pytest.raises(RuntimeError):
+        _lib.check(rc, "cdr_gemm")

@@ -1,0 +1,105 @@
+"""CPU: host-side mirror of the reference surface -- class / attribute / state-dict contract, registry, loud
+failure without CUDA, and the pure-host parts of the DRO losses against the oracle."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+TINY = dict(hidden=128, layers=12, heads=2, inter=512, vocab=2000, max_pos=64, type_vocab=2)
+
+
+def hf_config(cfg, **kw):
+    from transformers import BertConfig
+    return BertConfig(vocab_size=cfg["vocab"], hidden_size=cfg["hidden"], num_hidden_layers=cfg["layers"],
+                      num_attention_heads=cfg["heads"], intermediate_size=cfg["inter"],
+                      max_position_embeddings=cfg["max_pos"], type_vocab_size=cfg["type_vocab"],
+                      hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, **kw)
+
+
+def test_ance_surface_and_state_dict_contract():
+    from transformers import BertForSequenceClassification
+
+    from cocodr_b200 import models
+    from cocodr_b200.bert import BertModel
+    from oracle import bert_ref
+    cfgd = models.MSMarcoConfigDict["rdot_nll_condenser"]
+    m = cfgd.model_class(hf_config(TINY, num_labels=2))
+    assert isinstance(m.bert, BertModel) and isinstance(m, BertForSequenceClassification)
+    ref_keys = set(BertForSequenceClassification(hf_config(TINY, num_labels=2)).state_dict())
+    ref_keys |= {"embeddingHead.weight", "embeddingHead.bias", "norm.weight", "norm.bias"}  # models.py:202-203
+    assert set(m.state_dict()) == ref_keys
+    for k, shp in bert_ref.param_shapes(TINY).items():
+        assert tuple(m.state_dict()["bert." + k].shape) == shp
+    for attr in ("total", "correct", "dro_type", "use_mean", "query_emb", "body_emb", "forward_model", "add_group_loss",
+                 "output_state", "gather_tensors"):
+        assert hasattr(m, attr), attr
+    assert m.dro_type == "erm" and m.total == 0
+    m.add_group_loss(types.SimpleNamespace(model_size="base", local_rank=0), 5, "idro", 0.25, 0.01, 0.1, 0.05, True)
+    assert m.dro_type == "idro" and m.n_groups == 5 and len(m.accum_group_loss) == 5
+    assert {"loss.h_fun", "loss.sum_losses", "loss.count_cat"} <= set(m.state_dict())  # DRO state rides along
+    names = [n for n, _ in m.bert.named_parameters()]
+    from oracle import heads_ref
+    picked = m.loss._params(m.bert)
+    assert len(picked) == len(heads_ref.idro_param_names(names, "base")) == 48
+
+
+def test_no_cpu_fallback_anywhere():
+    from cocodr_b200 import models, ops, scan
+    m = models.BertDot_NLL_LN(hf_config(TINY, num_labels=2))
+    ids, mask = torch.ones(2, 8, dtype=torch.long), torch.ones(2, 8, dtype=torch.long)
+    with pytest.raises(RuntimeError):
+        m(ids, mask, ids, mask, ids, mask, weights=torch.ones(2))
+    with pytest.raises(RuntimeError):
+        ops.pair_nll(torch.randn(2, 8), torch.randn(2, 8), torch.randn(2, 8))
+    with pytest.raises(RuntimeError):
+        ops.coco_contrastive(torch.randn(4, 8))
+    with pytest.raises(RuntimeError):
+        scan.search(torch.randn(2, 8).half(), torch.randn(9, 8).half(), 3)
+    with pytest.raises(RuntimeError):
+        scan.IndexFlatIP(8).search(np.zeros((1, 8), np.float32), 1)
+
+
+def test_unsupported_configs_are_rejected():
+    from cocodr_b200.bert import BertModel
+    with pytest.raises(RuntimeError):
+        BertModel(hf_config(dict(TINY, heads=4)))  # head_dim 32
+    from transformers import BertConfig
+    with pytest.raises(RuntimeError):
+        BertModel(BertConfig(hidden_size=128, num_attention_heads=2, num_hidden_layers=1, intermediate_size=256,
+                             hidden_act="relu"))
+
+
+def test_dro_greedy_update_mw_matches_oracle():
+    """update_mw (dro_loss.py:88-120) is host/device-agnostic torch code: drive it on CPU against the oracle."""
+    from cocodr_b200.dro_loss import DROGreedyLoss
+    from oracle import heads_ref
+    G, alpha, eps, ema = 7, 0.25, 0.01, 0.1
+    torch.manual_seed(3)
+    for weight_ema in (True, False):
+        mod = DROGreedyLoss(types.SimpleNamespace(local_rank=0), G, alpha, eps, ema, weight_ema)
+        h, sl, cc = torch.ones(G), torch.zeros(G), torch.ones(G)
+        for step in range(4):
+            losses, g = torch.rand(16) * 3, torch.randint(0, G, (16,))
+            _, _, _, h, sl, cc = heads_ref.dro_greedy_forward(losses, g, h, sl, cc, G, alpha, eps, ema, weight_ema)
+            # same EMA inputs, then the module's own greedy re-weighting
+            mod.sum_losses, mod.count_cat = sl.clone(), cc.clone()
+            mod.update_mw()
+            np.testing.assert_allclose(mod.h_fun.numpy(), h.numpy(), rtol=1e-6, atol=1e-7)
+
+
+def test_bench_reference_arm_contract():
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RANK="1")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference"], env=env,
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.strip() == ""  # ranks > 0 exit without work
+    sys.path.insert(0, root)
+    import bench
+    assert abs(bench.fwd_flops_per_seq() / 1e9 - 22.347) < 0.01  # SURVEY.md §8d / BASELINE.md §3
+    p = bench.measured_peaks()
+    assert p["tensor"] > 1000 and p["hbm"] > 5000

@@ -1,0 +1,196 @@
+"""GPU: drop-in BertDot_NLL_LN (+ iDRO / DRO-greedy / in-batch head) vs the fixtures written by the UNMODIFIED
+reference classes (tests/golden/ance_*.npz, idro_tiny.npz, dro_greedy_tiny.npz) and vs the CPU oracle.
+
+Tolerances: the CUDA path computes in fp16 with fp32 accumulation, the fixtures are fp32; the north-star
+bar is 1e-2 relative on logits / losses."""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TINY = dict(hidden=128, layers=12, heads=2, inter=512, vocab=2000, max_pos=64, type_vocab=2)
+
+
+def hf_config(cfg, **kw):
+    from transformers import BertConfig
+    return BertConfig(vocab_size=cfg["vocab"], hidden_size=cfg["hidden"], num_hidden_layers=cfg["layers"],
+                      num_attention_heads=cfg["heads"], intermediate_size=cfg["inter"],
+                      max_position_embeddings=cfg["max_pos"], type_vocab_size=cfg["type_vocab"],
+                      hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, **kw)
+
+
+def build(cfg, cls_name="BertDot_NLL_LN"):
+    from cocodr_b200 import models
+    from oracle import bert_ref
+    m = getattr(models, cls_name)(hf_config(cfg, num_labels=2))
+    missing = m.bert.load_state_dict(bert_ref.synth_state(cfg, 0), strict=False)
+    assert all("pooler" in k or "position_ids" in k for k in missing.missing_keys), missing
+    assert not missing.unexpected_keys
+    return m.cuda()
+
+
+def triplet(cfg, B, L, seed, full=False):
+    from oracle import bert_ref
+    out = []
+    for k in range(3):
+        out += [t.cuda() for t in bert_ref.synth_batch(B, L, cfg["vocab"], seed + k, full)]
+    return out
+
+
+def rel(got, ref):
+    got, ref = np.asarray(got, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    return np.abs(got - ref).max() / (np.abs(ref).max() + 1e-12)
+
+
+def test_ance_tiny_forward_backward_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "ance_tiny.npz"))
+    m = build(TINY)
+    m.train()
+    q, mq, a, ma, b, mb = triplet(TINY, int(g["B"]), int(g["L"]), int(g["seed"]))
+    w = torch.from_numpy(g["weights"]).cuda()
+    loss, acc, logits = m(q, mq, a, ma, b, mb, weights=w)
+    assert rel(logits.detach().cpu().numpy(), g["logits"]) < 1e-2
+    assert abs(loss.item() - float(g["erm_loss"])) < 1e-2 * abs(float(g["erm_loss"]))
+    assert (acc.cpu().numpy() == g["accs"]).all()
+    with torch.no_grad():
+        assert rel(m.query_emb(q, mq).cpu().numpy(), g["q_emb"]) < 1e-2
+        assert rel(m.body_emb(b, mb).cpu().numpy(), g["b_emb"]) < 1e-2
+        per = m.forward_model(q, mq, a, ma, b, mb)[0]
+        np.testing.assert_allclose(per.cpu().numpy(), g["loss"], rtol=1e-2, atol=2e-3)
+    m.zero_grad()
+    loss.backward()
+    named = dict(m.bert.named_parameters())
+    worst = 0.0
+    for key in g.files:
+        if not key.startswith("grad."):
+            continue
+        name = key[5:]
+        if name.endswith(".rownorm"):
+            got = named[name[:-8]].grad.norm(dim=1).cpu().numpy()
+        elif name.endswith(".norm"):
+            got = named[name[:-5]].grad.norm().item()
+        else:
+            got = named[name].grad.cpu().numpy()
+        r = rel(got, g[key])
+        worst = max(worst, r)
+        # The triplet-loss gradient is sigma * (b - a): a difference of two nearly identical CLS vectors for a
+        # random-init encoder, so the fp16 forward error (<1e-2, asserted above) is amplified several-fold
+        # here.  The well-conditioned check of the backward kernels is
+        # test_encoder_backward_fixed_upstream_grad below; this one bounds the end-to-end drift.
+        cos = float((np.ravel(got) * np.ravel(g[key])).sum() /
+                    (np.linalg.norm(np.ravel(got)) * np.linalg.norm(np.ravel(g[key])) + 1e-30))
+        assert r < 1e-1 and cos > 0.995, f"{key}: rel err {r}, cos {cos}"
+    print("worst grad rel err", worst)
+
+
+def test_encoder_backward_fixed_upstream_grad():
+    """Backward of the whole encoder for a FIXED upstream gradient d(cls) -- isolates the backward kernels from
+    the conditioning of the loss.  Oracle: fp32 autograd through oracle/bert_ref.py with the same d(cls)."""
+    from oracle import bert_ref
+    m = build(TINY)
+    m.train()
+    ids, mask = (t.cuda() for t in bert_ref.synth_batch(6, 32, TINY["vocab"], 77))
+    g = torch.Generator().manual_seed(5)
+    dcls = torch.randn(6, TINY["hidden"], generator=g) * 0.05
+    cls = m.query_emb(ids, mask)
+    (cls * dcls.cuda()).sum().backward()
+    leaf = {k: v.clone().requires_grad_(True) for k, v in bert_ref.synth_state(TINY, 0).items()}
+    ref_cls = bert_ref.cls_embedding(leaf, ids.cpu(), mask.cpu(), TINY)
+    (ref_cls * dcls).sum().backward()
+    assert rel(cls.detach().cpu().numpy(), ref_cls.detach().numpy()) < 1e-2
+    named = dict(m.bert.named_parameters())
+    worst = ("", 0.0)
+    for name, ref in leaf.items():
+        got = named[name].grad.cpu().numpy()
+        r = rel(got, ref.grad.numpy())
+        if r > worst[1]:
+            worst = (name, r)
+        assert r < 2.5e-2, f"{name}: rel err {r}"
+    print("worst", worst)
+
+
+def test_ance_cfg1_base_matches_reference(golden_dir):
+    """BASELINE.json configs[0]: BERT-base, B=8, L=128 -- reference fp32 CPU outputs vs the CUDA drop-in."""
+    from oracle import bert_ref
+    from cocodr_b200 import ops
+    g = np.load(os.path.join(golden_dir, "ance_cfg1_base.npz"))
+    cfg = bert_ref.make_config()
+    m = build(cfg)
+    m.eval()
+    q, mq, a, ma, b, mb = triplet(cfg, int(g["B"]), int(g["L"]), int(g["seed"]), full=True)
+    w = torch.from_numpy(g["weights"]).cuda()
+    with torch.no_grad():
+        loss, acc, logits = m(q, mq, a, ma, b, mb, weights=w)
+        qe, ae = m.query_emb(q, mq), m.body_emb(a, ma)
+        qp = ops.qp_infonce(qe, ae)
+    assert rel(qe.cpu().numpy(), g["q_emb"]) < 1e-2
+    assert rel(logits.cpu().numpy(), g["logits"]) < 1e-2
+    np.testing.assert_allclose(qp.cpu().numpy(), g["qp_infonce"], rtol=1e-2, atol=5e-3)
+    assert abs(loss.item() - float(g["erm_loss"])) < 1e-2 * abs(float(g["erm_loss"]))
+
+
+def _run_dro(golden_dir, fname, dro_type):
+    g = np.load(os.path.join(golden_dir, fname))
+    m = build(TINY)
+    B, L, seed, G = int(g["B"]), int(g["L"]), int(g["seed"]), int(g["n_groups"])
+    args = types.SimpleNamespace(model_size="base", local_rank=0)
+    m.add_group_loss(args, G, dro_type, float(g["alpha"]), float(g["eps"]), float(g["ema"]), float(g["rho"]), True)
+    m.train()
+    for s in range(int(g["steps"])):
+        q, mq, a, ma, b, mb = triplet(TINY, B, L, seed + 10 * s)
+        gid = torch.from_numpy(g[f"group_ids_{s}"]).cuda()
+        m.zero_grad()
+        robust, acc, gl, gc = m(q, mq, a, ma, b, mb, group_ids=gid, weights=torch.ones(B, device="cuda"))
+        robust.backward()
+        assert abs(robust.item() - float(g[f"robust_{s}"])) < 1e-2 * abs(float(g[f"robust_{s}"]))
+        np.testing.assert_allclose(gl.cpu().numpy(), g[f"group_losses_{s}"], rtol=1e-2, atol=2e-3)
+        np.testing.assert_array_equal(gc.cpu().numpy(), g[f"group_counts_{s}"])
+        np.testing.assert_allclose(m.loss.h_fun.cpu().numpy(), g[f"h_fun_{s}"], rtol=1e-2, atol=1e-4)
+        got = dict(m.bert.named_parameters())["encoder.layer.11.attention.self.query.weight"].grad.cpu().numpy()
+        assert rel(got, g[f"grad_q11_{s}"]) < 1e-1  # ill-conditioned (see the ERM test); kernels checked above
+        if dro_type == "dro-greedy":
+            np.testing.assert_allclose(m.loss.sum_losses.cpu().numpy(), g[f"sum_losses_{s}"], rtol=1e-2, atol=1e-3)
+            np.testing.assert_allclose(m.loss.count_cat.cpu().numpy(), g[f"count_cat_{s}"], rtol=1e-5)
+    h_fun, sum_loss = m.output_state()
+    assert set(h_fun) == {f"group{i}" for i in range(G)} and set(sum_loss) == set(h_fun)
+
+
+def test_idro_trajectory_matches_reference(golden_dir):
+    _run_dro(golden_dir, "idro_tiny.npz", "idro")
+
+
+def test_dro_greedy_trajectory_matches_reference(golden_dir):
+    _run_dro(golden_dir, "dro_greedy_tiny.npz", "dro-greedy")
+
+
+def test_inbatch_head_and_hf_surface(golden_dir, tmp_path):
+    """K9' per-sample losses vs the fixture's qp_infonce; save_pretrained / from_pretrained round trip; the
+    HF-style ``self.bert(...)`` call returns fp32 hidden states whose row 0 is the CLS embedding."""
+    from cocodr_b200 import models
+    g = np.load(os.path.join(golden_dir, "ance_tiny.npz"))
+    m = build(TINY, "BertDot_InBatch_NLL_LN")
+    m.eval()
+    q, mq, a, ma, b, mb = triplet(TINY, int(g["B"]), int(g["L"]), int(g["seed"]))
+    with torch.no_grad():
+        per, accs, logits = m.forward_model(q, mq, a, ma)
+    np.testing.assert_allclose(per.cpu().numpy(), g["qp_infonce"], rtol=1e-2, atol=3e-3)
+    m.save_pretrained(tmp_path)
+    cfgd = models.MSMarcoConfigDict["rdot_nll_condenser_inbatch"]
+    m2 = cfgd.model_class.from_pretrained(tmp_path, config=cfgd.config_class.from_pretrained(tmp_path)).cuda().eval()
+    assert set(m2.state_dict()) == set(m.state_dict())
+    with torch.no_grad():
+        e1, e2 = m.query_emb(q, mq), m2.query_emb(q, mq)
+        out = m.bert(input_ids=q, attention_mask=mq)
+    assert torch.equal(e1, e2)
+    assert out[0].dtype == torch.float32 and out[0].shape == (q.shape[0], q.shape[1], TINY["hidden"])
+    assert torch.equal(out[0][:, 0], e1)
+
+
+def test_no_cpu_fallback():
+    m = build(TINY)
+    with pytest.raises(RuntimeError):
+        m.query_emb(torch.zeros(2, 8, dtype=torch.long), torch.ones(2, 8, dtype=torch.long))
