@@ -55,40 +55,59 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe):
+    one streaming ``nvidia-smi -lms`` process; only samples that fall between mark_start() and mark_end()
+    are summarised."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
+    def __init__(self, index, period_ms=20):
+        self.index, self.period_ms = index, period_ms
+        self.samples, self.proc, self._t = [], None, None
+        self.t0 = self.t1 = None
 
     def _loop(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+        for line in self.proc.stdout:
+            parts = [x.strip() for x in line.strip().split(",")]
+            if len(parts) >= 6:
+                self.samples.append((time.perf_counter(), parts))
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._loop, daemon=True)
-        self._t.start()
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", str(self.period_ms)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+            time.sleep(0.3)  # let the first samples arrive before the timed region starts
+        except Exception:
+            self.proc = None
         return self
 
+    def mark_start(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
+
     def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=6)
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            self._t.join(timeout=5)
 
     def summary(self):
-        sm = [int(s[0]) for s in self.samples if s and s[0].isdigit()]
-        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
+        inside = [p for t, p in self.samples if self.t0 is not None and self.t0 <= t <= (self.t1 or t)]
+        use = inside if inside else [p for _, p in self.samples[-3:]]
+        sm = [int(s[0]) for s in use if s[0].isdigit()]
+        mx = [int(s[1]) for s in use if s[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        reasons = sorted({n for s in use for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "samples_in_timed_region": len(inside)}
 
 
 # ------------------------------------------------------------------------------------------------ CPU port
@@ -195,14 +214,18 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, sampler=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sampler is not None:
+            sampler.mark_start()
         e0.record()
         for i in range(steps):
             fn(i)
         e1.record()
         barrier()
+        if sampler is not None:
+            sampler.mark_end()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -223,7 +246,7 @@ def run_ours(args):
         resident_step(i)
     l0 = kernels.launches
     with ClockSampler(local) as clocks:
-        ms = timed(resident_step, args.steps)
+        ms = timed(resident_step, args.steps, clocks)
     launches = kernels.launches - l0
     for i in range(2):
         e2e_step(i)

@@ -34,6 +34,12 @@ def layer_params(layer):
             o.dense.bias, o.LayerNorm.weight, o.LayerNorm.bias)
 
 
+def shadow_sources(layer):
+    """(wq, bq, wk, bk, wv, bv, wo, wi, wo2): the parameters that have fp16 / packed shadows."""
+    p = layer_params(layer)
+    return (p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[10], p[12])
+
+
 def check_config(config):
     if config.hidden_size % config.num_attention_heads or config.hidden_size // config.num_attention_heads != 64:
         raise RuntimeError("cocodr_b200 BERT kernels need head_dim == 64")
@@ -58,7 +64,8 @@ class BertModel(_HFBertModel):
         self._cdr_init()
 
     def _cdr_init(self):
-        object.__setattr__(self, "_shadows", [ops.LayerShadow() for _ in self.encoder.layer])
+        object.__setattr__(self, "_shadow_set", ops.ShadowSet(len(self.encoder.layer)))
+        object.__setattr__(self, "_shadows", self._shadow_set.layers)
 
     @classmethod
     def adopt(cls, hf_bert):
@@ -95,6 +102,7 @@ class BertModel(_HFBertModel):
             self._cdr_init()
         n_seq, L = input_ids.shape
         e = self.embeddings
+        self._shadow_set.refresh([shadow_sources(layer) for layer in self.encoder.layer])
         x = ops.EmbedLN.apply(input_ids.long(), e.word_embeddings.weight, e.position_embeddings.weight,
                               e.token_type_embeddings.weight, e.LayerNorm.weight, e.LayerNorm.bias,
                               float(self.config.layer_norm_eps))

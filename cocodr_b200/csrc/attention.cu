@@ -203,10 +203,11 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttParams p) 
 }
 
 // ----------------------------------------------------------------------------------------- backward
-// smem: Q K V dO (4 x 16 KB) | P (32 KB) | dS (32 KB) | bias | barriers
-constexpr int ATT_BWD_SMEM = 8 * ATT_TILE_BYTES + 512 + 64 + 1024;
+// smem: Q K V dO (4 x 16 KB) | P, then dS (ONE 32 KB buffer) | bias | barriers   -> 2 CTAs per SM.
+// P is consumed by the dV MMA first; dS waits in registers (packed fp16) and then overwrites P.
+constexpr int ATT_BWD_SMEM = 6 * ATT_TILE_BYTES + 512 + 64 + 1024;
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, 2)
 fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do,
                 const AttParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -215,11 +216,10 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
   uint8_t* sK = smem + ATT_TILE_BYTES;
   uint8_t* sV = smem + 2 * ATT_TILE_BYTES;
   uint8_t* sdO = smem + 3 * ATT_TILE_BYTES;
-  uint8_t* sP = smem + 4 * ATT_TILE_BYTES;
-  uint8_t* sdS = smem + 6 * ATT_TILE_BYTES;
-  float* sBias = reinterpret_cast<float*>(smem + 8 * ATT_TILE_BYTES);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 8 * ATT_TILE_BYTES + 512);
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 4);
+  uint8_t* sP = smem + 4 * ATT_TILE_BYTES;  // P, later dS
+  float* sBias = reinterpret_cast<float*>(smem + 6 * ATT_TILE_BYTES);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 6 * ATT_TILE_BYTES + 512);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 5);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int seq = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
@@ -230,7 +230,7 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
     tma_prefetch_desc(&tma_qkv);
     tma_prefetch_desc(&tma_do);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) mbar_init(&bar[i], 1);
+    for (int i = 0; i < 5; ++i) mbar_init(&bar[i], 1);
     fence_mbar_init();
   }
   if (warp == 0) {
@@ -246,6 +246,7 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
+  const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK), va = smem_u32(sV), da = smem_u32(sdO), pa = smem_u32(sP);
 
   if (tid == 0) {
     mbar_expect_tx(&bar[0], 2 * ATT_TILE_BYTES);
@@ -257,7 +258,6 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
     constexpr uint32_t idesc = make_idesc_f16(ATT_T, ATT_T, 0, 0);
     mbar_wait(&bar[0], 0);
     tc_fence_after();
-    const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK), va = smem_u32(sV), da = smem_u32(sdO);
 #pragma unroll
     for (int k = 0; k < ATT_D / 16; ++k)  // S = Q K^T -> cols [0,128)
       tc_mma_f16(tmem, make_smem_desc(qa + k * 32, 16, 1024), make_smem_desc(ka + k * 32, 16, 1024), idesc, k > 0);
@@ -289,7 +289,8 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
 
   const uint32_t trow = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
   const float sl2 = p.scale * LOG2E;
-#pragma unroll 1
+  uint4 ds_keep[8];  // this thread's 64 dS values, packed fp16, parked until P has been consumed
+#pragma unroll
   for (int cc = 0; cc < 2; ++cc) {
     const int c0 = half * 64 + cc * 32;
     uint32_t s[32], d[32];
@@ -307,31 +308,46 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
         pv[j] = pe;
         ds[j] = ok ? pe * (__uint_as_float(d[g * 8 + j]) - delta) * p.scale : 0.f;
       }
-      const uint32_t o = swz_off(r, c0 + g * 8);
-      *reinterpret_cast<uint4*>(sP + o) = pack8(pv);
-      *reinterpret_cast<uint4*>(sdS + o) = pack8(ds);
+      *reinterpret_cast<uint4*>(sP + swz_off(r, c0 + g * 8)) = pack8(pv);
+      ds_keep[cc * 4 + g] = pack8(ds);
     }
   }
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
 
+  constexpr uint32_t idesc_tt = make_idesc_f16(ATT_T, ATT_D, 1, 1);
+  constexpr uint32_t idesc_nt = make_idesc_f16(ATT_T, ATT_D, 0, 1);
   if (tid == 0) {
     tc_fence_after();
-    const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK), da = smem_u32(sdO), pa = smem_u32(sP), sa = smem_u32(sdS);
-    constexpr uint32_t idesc_tt = make_idesc_f16(ATT_T, ATT_D, 1, 1);
-    constexpr uint32_t idesc_nt = make_idesc_f16(ATT_T, ATT_D, 0, 1);
 #pragma unroll
     for (int k = 0; k < ATT_T / 16; ++k)  // dV[kv,d] = sum_q P[q,kv] dO[q,d] -> cols [0,64)
-      tc_mma_f16(tmem, make_smem_desc(pa + k * 2048, ATT_TILE_BYTES, 1024),
-                 make_smem_desc(da + k * 2048, 8192, 1024), idesc_tt, k > 0);
+      tc_mma_f16(tmem, make_smem_desc(pa + k * 2048, ATT_TILE_BYTES, 1024), make_smem_desc(da + k * 2048, 8192, 1024),
+                 idesc_tt, k > 0);
+    tc_commit(&bar[4]);
+  }
+  __syncwarp();
+  mbar_wait(&bar[4], 0);  // P has been read by the tensor core: its buffer may now take dS
+  tc_fence_after();
+  __syncwarp();
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      *reinterpret_cast<uint4*>(sP + swz_off(r, half * 64 + cc * 32 + g * 8)) = ds_keep[cc * 4 + g];
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+
+  if (tid == 0) {
+    tc_fence_after();
 #pragma unroll
     for (int k = 0; k < ATT_T / 16; ++k)  // dK[kv,d] = sum_q dS[q,kv] Q[q,d] -> cols [64,128)
-      tc_mma_f16(tmem + 64, make_smem_desc(sa + k * 2048, ATT_TILE_BYTES, 1024),
+      tc_mma_f16(tmem + 64, make_smem_desc(pa + k * 2048, ATT_TILE_BYTES, 1024),
                  make_smem_desc(qa + k * 2048, 8192, 1024), idesc_tt, k > 0);
 #pragma unroll
     for (int k = 0; k < ATT_T / 16; ++k)  // dQ[q,d] = sum_kv dS[q,kv] K[kv,d] -> cols [128,192)
-      tc_mma_f16(tmem + 128, make_smem_desc(sa + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 16, 1024),
+      tc_mma_f16(tmem + 128, make_smem_desc(pa + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 16, 1024),
                  make_smem_desc(ka + k * 2048, 8192, 1024), idesc_nt, k > 0);
     tc_commit(&bar[3]);
   }

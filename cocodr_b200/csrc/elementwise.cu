@@ -244,6 +244,97 @@ ln_bwd_kernel(const __half* __restrict__ dy, const __half* __restrict__ x, const
   }
 }
 
+// ------------------------------------------------------------------------------------------ bwd, split
+// The fused kernel above keeps 3 x H/32 column accumulators per lane, which caps occupancy and
+// serialises rows.  For the common case (fp16 dy only) the work is split in two bandwidth-shaped passes:
+//   ln_bwd_dx_kernel   : warp per row, dx only (+ the two per-row means c1, c2)          read 4 B, write 2 B / elem
+//   ln_bwd_cols_kernel : thread per 8 columns over a slab of rows -> dgamma, dbeta, dcol  read 4 B / elem
+// using  sum_r dx[r,c] = g[c] * sum_r rstd_r dy[r,c] - sum_r rstd_r c1_r - sum_r rstd_r c2_r xhat[r,c].
+template <int VPL>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+ln_bwd_dx_kernel(const __half* __restrict__ dy, const __half* __restrict__ x, const float* __restrict__ gamma,
+                 const float* __restrict__ mean_in, const float* __restrict__ rstd_in, __half* __restrict__ dx,
+                 float2* __restrict__ rowc, int rows, int hidden) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = hidden >> 3;
+  const float mean = mean_in[row], rstd = rstd_in[row];
+  float xh[VPL][8], gy[VPL][8];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+    if (lane + 32 * i < nvec) {
+      const int c = 8 * (lane + 32 * i);
+      float xv[8], d[8], g[8];
+      load8_h(x + static_cast<long long>(row) * hidden + c, xv);
+      load8_h(dy + static_cast<long long>(row) * hidden + c, d);
+      load8_f(gamma + c, g);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        xh[i][k] = (xv[k] - mean) * rstd;
+        gy[i][k] = d[k] * g[k];
+        s1 += gy[i][k];
+        s2 += gy[i][k] * xh[i][k];
+      }
+    }
+  const float c1 = warp_sum(s1) / hidden;
+  const float c2 = warp_sum(s2) / hidden;
+  if (lane == 0) rowc[row] = make_float2(c1, c2);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+    if (lane + 32 * i < nvec) {
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = rstd * (gy[i][k] - c1 - xh[i][k] * c2);
+      store8_h(dx + static_cast<long long>(row) * hidden + 8 * (lane + 32 * i), o);
+    }
+}
+
+__global__ void __launch_bounds__(128)
+ln_bwd_cols_kernel(const __half* __restrict__ dy, const __half* __restrict__ x, const float* __restrict__ gamma,
+                   const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                   const float2* __restrict__ rowc, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                   float* __restrict__ dcol, int rows, int hidden, int rows_per_block, float out_scale) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (c >= hidden) return;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(r0 + rows_per_block, rows);
+  float dg[8], db[8], s3[8], s4[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) dg[k] = db[k] = s3[k] = s4[k] = 0.f;
+  float csum = 0.f;
+#pragma unroll 4
+  for (int r = r0; r < r1; ++r) {
+    float d[8], xv[8];
+    load8_h(dy + static_cast<long long>(r) * hidden + c, d);
+    load8_h(x + static_cast<long long>(r) * hidden + c, xv);
+    const float m = mean_in[r], rs = rstd_in[r];
+    const float2 cc = rowc[r];
+    const float rc2 = rs * cc.y;
+    csum = fmaf(rs, cc.x, csum);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float xh = (xv[k] - m) * rs;
+      dg[k] = fmaf(d[k], xh, dg[k]);
+      db[k] += d[k];
+      s3[k] = fmaf(rs, d[k], s3[k]);
+      s4[k] = fmaf(rc2, xh, s4[k]);
+    }
+  }
+  float g[8];
+  load8_f(gamma + c, g);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    s3[k] = (g[k] * s3[k] - csum - s4[k]) * out_scale;
+    dg[k] *= out_scale;
+    db[k] *= out_scale;
+  }
+  if (dgamma) atomic_add8(dgamma + c, dg);
+  if (dbeta) atomic_add8(dbeta + c, db);
+  if (dcol) atomic_add8(dcol + c, s3);
+}
+
 // out[c] += scale * sum_r x[r, c]      (fp16 in, fp32 accumulate; bias gradients)
 __global__ void __launch_bounds__(256)
 colsum_kernel(const __half* __restrict__ x, float* __restrict__ out, int rows, int cols, long long ld, float scale,
@@ -273,6 +364,27 @@ __global__ void cast_f32_f16_kernel(const float* __restrict__ src, __half* __res
     store8_h(dst + i, v);
   } else {
     for (; i < n; ++i) dst[i] = __float2half_rn(src[i]);
+  }
+}
+
+// One launch for a whole table of fp32 -> fp16 casts (and fp32 -> fp32 copies): the per-step refresh of
+// every fp16 weight shadow of the encoder.  blockIdx.y = table entry, blockIdx.x strides its elements.
+__global__ void __launch_bounds__(256)
+cast_multi_kernel(const cdr_cast_item* __restrict__ items) {
+  const cdr_cast_item it = items[blockIdx.y];
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 8;
+  for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8; i < it.n; i += stride) {
+    if (i + 8 <= it.n) {
+      float v[8];
+      load8_f(it.src + i, v);
+      if (it.dst_f32) store8_f(static_cast<float*>(it.dst) + i, v);
+      else store8_h(static_cast<__half*>(it.dst) + i, v);
+    } else {
+      for (long long j = i; j < it.n; ++j) {
+        if (it.dst_f32) static_cast<float*>(it.dst)[j] = it.src[j];
+        else static_cast<__half*>(it.dst)[j] = __float2half_rn(it.src[j]);
+      }
+    }
   }
 }
 
@@ -371,11 +483,41 @@ int cdr_ln_fwd(const void* x, const float* gamma, const float* beta, void* y, fl
 }
 
 int cdr_ln_bwd(const void* dy, const float* dy_cls, const void* x, const float* gamma, const float* mean,
-               const float* rstd, void* dx, float* dgamma, float* dbeta, float* dbias, int32_t n_seq, int32_t seq_len,
-               int32_t hidden, float in_scale, float out_scale, void* stream) {
+               const float* rstd, void* dx, float* dgamma, float* dbeta, float* dbias, float* row_ws, int32_t n_seq,
+               int32_t seq_len, int32_t hidden, float in_scale, float out_scale, void* stream) {
   if (int rc = check_hidden(hidden)) return rc;
   CDR_REQUIRE((dy || dy_cls) && x && gamma && mean && rstd && dx, "cdr_ln_bwd: null pointer");
   if (n_seq <= 0 || seq_len <= 0) return CDR_OK;
+  if (row_ws != nullptr && dy != nullptr && dy_cls == nullptr) {
+    // split path: dx pass + column-sum pass
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int rows = n_seq * seq_len;
+    const int nvec = hidden / 8, vpl = (nvec + 31) / 32;
+    const __half* dyh = static_cast<const __half*>(dy);
+    const __half* xh = static_cast<const __half*>(x);
+    float2* rowc = reinterpret_cast<float2*>(row_ws);
+    const dim3 grid((rows + LN_WARPS - 1) / LN_WARPS), block(LN_WARPS * 32);
+#define LN_DX(V) ln_bwd_dx_kernel<V><<<grid, block, 0, st>>>(dyh, xh, gamma, mean, rstd, static_cast<__half*>(dx), rowc, rows, hidden)
+    if (vpl <= 1) LN_DX(1);
+    else if (vpl <= 2) LN_DX(2);
+    else if (vpl <= 3) LN_DX(3);
+    else if (vpl <= 4) LN_DX(4);
+    else LN_DX(8);
+#undef LN_DX
+    CDR_LAUNCH_CHECK();
+    if (dgamma || dbeta || dbias) {
+      int threads = nvec < 128 ? ((nvec + 31) / 32) * 32 : 128;
+      if (nvec % 32 != 0 && nvec < 128) threads = nvec <= 32 ? 32 : (nvec <= 64 ? 64 : (nvec <= 96 ? 96 : 128));
+      const int gx = (nvec + threads - 1) / threads;
+      int rpb = (rows + 4 * sm_count() - 1) / (4 * sm_count());
+      if (rpb < 16) rpb = 16;
+      const int gy = (rows + rpb - 1) / rpb;
+      ln_bwd_cols_kernel<<<dim3(gx, gy), threads, 0, st>>>(dyh, xh, gamma, mean, rstd, rowc, dgamma, dbeta, dbias, rows,
+                                                          hidden, rpb, out_scale);
+      CDR_LAUNCH_CHECK();
+    }
+    return CDR_OK;
+  }
   return launch_ln_bwd<0>(static_cast<const __half*>(dy), static_cast<const __half*>(x), nullptr, nullptr, nullptr,
                           nullptr, gamma, mean, rstd, dy_cls, static_cast<__half*>(dx), dgamma, dbeta, dbias, nullptr,
                           nullptr, n_seq, hidden, seq_len, 0, -1, in_scale, out_scale,
@@ -393,6 +535,17 @@ int cdr_colsum_f16(const void* x, float* out, int64_t rows, int64_t cols, int64_
   const int gy = static_cast<int>((rows + rpb - 1) / rpb);
   colsum_kernel<<<dim3(gx, gy), threads, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __half*>(x), out, static_cast<int>(rows), static_cast<int>(cols), ld, scale, rpb);
+  CDR_LAUNCH_CHECK();
+  return CDR_OK;
+}
+
+int cdr_cast_multi(const cdr_cast_item* items_device, int32_t count, int64_t max_n, void* stream) {
+  CDR_REQUIRE(items_device != nullptr && count > 0 && max_n > 0, "cdr_cast_multi: bad arguments");
+  long long gx = (max_n + 256 * 8 * 4 - 1) / (256 * 8 * 4);  // ~4 vectors per thread for the largest entry
+  if (gx < 1) gx = 1;
+  if (gx > 1024) gx = 1024;
+  cast_multi_kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(count)), 256, 0,
+                      static_cast<cudaStream_t>(stream)>>>(items_device);
   CDR_LAUNCH_CHECK();
   return CDR_OK;
 }

@@ -1,23 +1,56 @@
 // cdr_gemm: host-side validation, TMA map construction and kernel dispatch for the tcgen05 GEMM.
+#include <stdlib.h>
+
 #include "gemm_sm100.cuh"
 #include "tma_host.h"
 
 namespace cdr {
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI>;
-  constexpr int smem = GemmSmem<BN>::TOTAL;
+// CTA-pair (cta_group::2) tiles are used whenever the problem has a 256-wide N tile and more than one
+// 128-row M tile; CDR_GEMM_2CTA=0 in the environment forces the single-CTA kernel (A/B comparisons).
+static bool use_2cta_default() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CDR_GEMM_2CTA");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI, int CG>
+static int launch_gemm_cg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI, CG>;
+  constexpr int smem = GemmSmem<BN, CG>::TOTAL;
   static bool configured = false;  // per-instantiation; attribute is sticky per device context
   if (!configured) {
     CDR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   const int items = p.m_tiles * p.n_tiles * p.split_k;
-  const int grid = items < sm_count() ? items : sm_count();
-  kern<<<grid, GEMM_THREADS, smem, st>>>(ta, tb, p);
-  CDR_LAUNCH_CHECK();
+  const int workers = sm_count() / CG;
+  const int grid = (items < workers ? items : workers) * CG;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CDR_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
   return CDR_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  if constexpr (BN == 256) {
+    if (p.cta_group == 2) return launch_gemm_cg<BN, A_MN, B_MN, EPI, 2>(ta, tb, p, st);
+  }
+  return launch_gemm_cg<BN, A_MN, B_MN, EPI, 1>(ta, tb, p, st);
 }
 
 template <int BN, bool A_MN, bool B_MN>
@@ -64,14 +97,15 @@ int gemm_run(const cdr_gemm_args& g, GemmParams p, cudaStream_t st) {
   if (b_mn) CDR_REQUIRE(g.N % 64 == 0, "cdr_gemm: MN-major B needs N %% 64 == 0 (N=%lld)", (long long)g.N);
   const int BN = (g.N > 128) ? 256 : 128;
   p.M = (int)g.M; p.N = (int)g.N; p.K = (int)g.K;
-  p.m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
+  p.cta_group = (BN == 256 && g.M > GEMM_BM && use_2cta_default()) ? 2 : 1;
+  p.m_tiles = (p.M + GEMM_BM * p.cta_group - 1) / (GEMM_BM * p.cta_group);
   p.n_tiles = (p.N + BN - 1) / BN;
   const int total_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
   int split = g.split_k;
   if (split <= 0) {
     // auto: enough work items to fill the machine, at least 4 k-blocks per split
     const int tiles = p.m_tiles * p.n_tiles;
-    split = (2 * sm_count() + tiles - 1) / tiles;
+    split = (2 * (sm_count() / p.cta_group) + tiles - 1) / tiles;
     if (split > total_kb / 4) split = total_kb / 4;
     if (split < 1) split = 1;
   }
@@ -88,7 +122,7 @@ int gemm_run(const cdr_gemm_args& g, GemmParams p, cudaStream_t st) {
   else rc = make_tma_2d_f16(&ta, g.a, g.K, g.M, g.lda, GEMM_BK, GEMM_BM);
   if (rc != CDR_OK) return rc;
   if (b_mn) rc = make_tma_2d_f16(&tb, g.b, g.N, g.K, g.ldb, 64, GEMM_BK);
-  else rc = make_tma_2d_f16(&tb, g.b, g.K, g.N, g.ldb, GEMM_BK, BN);
+  else rc = make_tma_2d_f16(&tb, g.b, g.K, g.N, g.ldb, GEMM_BK, BN / p.cta_group);
   if (rc != CDR_OK) return rc;
 
   if (BN == 256) return dispatch_layout<256>(a_mn, b_mn, g.epilogue, ta, tb, p, st);

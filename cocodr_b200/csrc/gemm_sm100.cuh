@@ -35,6 +35,7 @@ struct GemmParams {
   int split_k;          // >= 1
   int kb_per_split;     // k-blocks (of 64) per split
   int m_tiles, n_tiles;
+  int cta_group;        // 1 or 2 (CTA pair, 256-row tiles)
   // epilogue
   void* out;            // fp16 or fp32 [M, ldo]
   void* out2;           // optional second output (pre-activation), fp16
@@ -55,14 +56,20 @@ struct GemmParams {
 // host-side entry shared by cdr_gemm and the scan (gemm.cu)
 int gemm_run(const cdr_gemm_args& g, GemmParams p, cudaStream_t st);
 
-template <int BN>
+// CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cta_group::2) per 256 x BN tile -- each CTA stages
+// its own 128 rows of A and HALF of the B tile (BN/2 rows); the pair's UMMA reads both halves, so the
+// operand bytes pulled through L2 per MMA cycle drop by a third and the ring gets deeper.
+template <int BN, int CG = 1>
 struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int B_ROWS = BN / CG;
+  static constexpr int B_BYTES = B_ROWS * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = (STAGE_BYTES >= 49152) ? 4 : (STAGE_BYTES >= 32768 ? 6 : 8);
   static constexpr int BAR_BYTES = 256;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
+  static constexpr int STG_BYTES = GEMM_EPI_WARPS * 32 * 32 * 4;  // epilogue staging tiles
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + STG_BYTES + 1024;  // +1024 alignment slack
+  static_assert(TOTAL <= 232448, "shared memory budget");
 };
 
 // Order-preserving packing of (score desc, doc asc) into one u64 so that a plain descending sort of
@@ -73,107 +80,151 @@ __device__ __forceinline__ unsigned long long pack_score_doc(float s, unsigned i
   return (static_cast<unsigned long long>(u) << 32) | static_cast<unsigned long long>(~doc);
 }
 
-// Epilogue for one thread: 32 consecutive columns [n0, n0+32) of row m.
+// ------------------------------------------------------------------------------------------------
+// Epilogue.  tcgen05.ld hands every thread one accumulator ROW (TMEM lane) -- the wrong shape for global
+// memory: 32 threads would touch 32 different rows per instruction.  Each epilogue warp therefore
+// transposes its 32 x 32 fp32 chunk through a private, XOR-swizzled 4 KB staging tile in shared memory and
+// re-reads it so that 4 neighbouring threads own 8 consecutive columns each of ONE row: residual /
+// pre-activation loads and output stores become 64-128 B contiguous per row (full 32 B sectors), and the
+// per-column bias / thresholds live in registers for the whole chunk.
+// ------------------------------------------------------------------------------------------------
+constexpr int GEMM_STG_BYTES = 32 * 32 * 4;  // per epilogue warp
+
+// row r, 16-byte piece j (0..7) of a [32][32] fp32 tile, conflict-free for both access shapes
+__device__ __forceinline__ float4* stg_piece(float* stg, int r, int j) {
+  return reinterpret_cast<float4*>(stg + r * 32 + ((j ^ (r & 7)) << 2));
+}
+
+// 8 consecutive columns [n, n+8) of row m; v = raw accumulators
 template <int EPI>
-__device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const uint32_t (&acc)[32], int m, int n0) {
-  if (m >= p.M) return;
+__device__ __forceinline__ void gemm_epilogue_apply(const GemmParams& p, float (&v)[8], int m, int n,
+                                                    const float (&bias)[8], const uint4& auxq) {
   if constexpr (EPI == CDR_EPI_SCAN_FILTER) {
-    // rows = documents, columns = queries.  Admit (score >= thresh[q]) into the per-query buffers.
-#pragma unroll 4
-    for (int j = 0; j < 32; ++j) {
-      const int q = n0 + j;
-      if (q >= p.N) break;
-      const float s = __uint_as_float(acc[j]);
-      if (s >= __ldg(p.thresh + q)) {
+    // rows = documents, columns = queries; bias[] holds the admission thresholds of the 8 queries
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int q = n + j;
+      if (q < p.N && v[j] >= bias[j]) {
         const int pos = atomicAdd(p.cand_count + q, 1);
         if (pos < p.cand_cap)
           p.cand[static_cast<long long>(q) * p.cand_cap + pos] =
-              pack_score_doc(s, static_cast<unsigned int>(p.row_base + m));
+              pack_score_doc(v[j], static_cast<unsigned int>(p.row_base + m));
       }
     }
-    return;
   } else if constexpr (EPI == CDR_EPI_F32_ATOMIC || EPI == CDR_EPI_F32_STORE) {
-    float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(m) * p.ldo + n0;
+    float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(m) * p.ldo + n;
+    const float4 lo = make_float4(v[0] * p.alpha, v[1] * p.alpha, v[2] * p.alpha, v[3] * p.alpha);
+    const float4 hi = make_float4(v[4] * p.alpha, v[5] * p.alpha, v[6] * p.alpha, v[7] * p.alpha);
+    if constexpr (EPI == CDR_EPI_F32_ATOMIC) {
+      atomicAdd(reinterpret_cast<float4*>(o), lo);
+      atomicAdd(reinterpret_cast<float4*>(o + 4), hi);
+    } else {
+      *reinterpret_cast<float4*>(o) = lo;
+      *reinterpret_cast<float4*>(o + 4) = hi;
+    }
+  } else {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      if (n0 + j >= p.N) break;
-      float4 v = make_float4(__uint_as_float(acc[j]) * p.alpha, __uint_as_float(acc[j + 1]) * p.alpha,
-                             __uint_as_float(acc[j + 2]) * p.alpha, __uint_as_float(acc[j + 3]) * p.alpha);
-      if constexpr (EPI == CDR_EPI_F32_ATOMIC) {
-        atomicAdd(reinterpret_cast<float4*>(o + j), v);
-      } else {
-        *reinterpret_cast<float4*>(o + j) = v;
+    for (int t = 0; t < 8; ++t) v[t] = fmaf(v[t], p.alpha, bias[t]);
+    if constexpr (EPI == CDR_EPI_BIAS_RESIDUAL) {
+      const __half2* rh = reinterpret_cast<const __half2*>(&auxq);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = __half22float2(rh[t]);
+        v[2 * t] += f.x;
+        v[2 * t + 1] += f.y;
       }
     }
-    return;
-  } else {
-    __half* o = reinterpret_cast<__half*>(p.out) + static_cast<long long>(m) * p.ldo + n0;
+    if constexpr (EPI == CDR_EPI_DGELU) {
+      const __half2* zh = reinterpret_cast<const __half2*>(&auxq);
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      if (n0 + j >= p.N) break;
-      float v[8];
-#pragma unroll
-      for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(acc[j + t]) * p.alpha;
-      if (p.bias != nullptr) {
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j + 4));
-        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = __half22float2(zh[t]);
+        v[2 * t] *= gelu_erf_grad(f.x);
+        v[2 * t + 1] *= gelu_erf_grad(f.y);
       }
-      if constexpr (EPI == CDR_EPI_BIAS_RESIDUAL) {
-        const uint4 r = *reinterpret_cast<const uint4*>(p.aux + static_cast<long long>(m) * p.ldaux + n0 + j);
-        const __half2* rh = reinterpret_cast<const __half2*>(&r);
+    }
+    if constexpr (EPI == CDR_EPI_BIAS_GELU) {
+      if (p.out2 != nullptr) {
+        uint4 zq;
+        __half2* zh = reinterpret_cast<__half2*>(&zq);
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const float2 f = __half22float2(rh[t]);
-          v[2 * t] += f.x;
-          v[2 * t + 1] += f.y;
-        }
-      }
-      if constexpr (EPI == CDR_EPI_DGELU) {
-        const uint4 z = *reinterpret_cast<const uint4*>(p.aux + static_cast<long long>(m) * p.ldaux + n0 + j);
-        const __half2* zh = reinterpret_cast<const __half2*>(&z);
+        for (int t = 0; t < 4; ++t) zh[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
+        *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out2) + static_cast<long long>(m) * p.ldo + n) = zq;
+        // GELU is applied to the fp16-rounded pre-activation so that backward (which only has Z)
+        // differentiates exactly the function forward evaluated.
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const float2 f = __half22float2(zh[t]);
-          v[2 * t] *= gelu_erf_grad(f.x);
-          v[2 * t + 1] *= gelu_erf_grad(f.y);
+          v[2 * t] = f.x;
+          v[2 * t + 1] = f.y;
         }
       }
-      if constexpr (EPI == CDR_EPI_BIAS_GELU) {
-        if (p.out2 != nullptr) {
-          uint4 zq;
-          __half2* zh = reinterpret_cast<__half2*>(&zq);
 #pragma unroll
-          for (int t = 0; t < 4; ++t) zh[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
-          *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out2) + static_cast<long long>(m) * p.ldo + n0 + j) = zq;
-          // GELU is applied to the fp16-rounded pre-activation so that backward (which only has Z)
-          // differentiates exactly the function forward evaluated.
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const float2 f = __half22float2(zh[t]);
-            v[2 * t] = f.x;
-            v[2 * t + 1] = f.y;
-          }
-        }
-#pragma unroll
-        for (int t = 0; t < 8; ++t) v[t] = gelu_erf(v[t]);
-      }
-      uint4 q;
-      __half2* qh = reinterpret_cast<__half2*>(&q);
-#pragma unroll
-      for (int t = 0; t < 4; ++t) qh[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
-      *reinterpret_cast<uint4*>(o + j) = q;
+      for (int t = 0; t < 8; ++t) v[t] = gelu_erf(v[t]);
     }
+    uint4 q;
+    __half2* qh = reinterpret_cast<__half2*>(&q);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) qh[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + static_cast<long long>(m) * p.ldo + n) = q;
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+// One warp, one 32 x 32 chunk: rows [m_base, m_base+32), columns [n0, n0+32).  acc = this thread's row.
+template <int EPI>
+__device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const uint32_t (&acc)[32], float* stg,
+                                                    int lane, int m_base, int n0) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *stg_piece(stg, lane, j) = make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]),
+                                           __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
+  __syncwarp();
+  const int seg = lane & 3;
+  const int n = n0 + seg * 8;
+  const bool col_ok = n < p.N;
+  float bias[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) bias[t] = 0.f;
+  if constexpr (EPI == CDR_EPI_SCAN_FILTER) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) bias[t] = (n + t < p.N) ? __ldg(p.thresh + n + t) : INFINITY;
+  } else if constexpr (EPI != CDR_EPI_F32_ATOMIC && EPI != CDR_EPI_F32_STORE) {
+    if (col_ok && p.bias != nullptr) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+      bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w;
+      bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
+    }
+  }
+  constexpr bool HAS_AUX = (EPI == CDR_EPI_BIAS_RESIDUAL || EPI == CDR_EPI_DGELU);
+  uint4 auxq[4];
+  if constexpr (HAS_AUX) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {  // all four rows' loads in flight before any math
+      const int m = m_base + (lane >> 2) + 8 * i;
+      auxq[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (col_ok && m < p.M) auxq[i] = *reinterpret_cast<const uint4*>(p.aux + static_cast<long long>(m) * p.ldaux + n);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = (lane >> 2) + 8 * i;
+    const int m = m_base + r;
+    const float4 lo = *stg_piece(stg, r, 2 * seg);
+    const float4 hi = *stg_piece(stg, r, 2 * seg + 1);
+    float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    if (col_ok && m < p.M) gemm_epilogue_apply<EPI>(p, v, m, n, bias, HAS_AUX ? auxq[i] : auxq[0]);
+  }
+  __syncwarp();  // staging tile is rewritten by the next chunk
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                     const GemmParams p) {
-  using S = GemmSmem<BN>;
+  using S = GemmSmem<BN, CG>;
   constexpr int STAGES = S::STAGES;
+  constexpr int BNL = S::B_ROWS;  // B rows staged by this CTA
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -183,9 +234,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* stg_all = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + S::BAR_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const int worker = blockIdx.x / CG;        // CTA (pair) index
+  const int n_workers = gridDim.x / CG;
   const int total_items = p.m_tiles * p.n_tiles * p.split_k;
   const int total_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
 
@@ -198,60 +253,83 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], GEMM_EPI_WARPS);
+      mbar_init(&tmem_empty[i], GEMM_EPI_WARPS * CG);
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr, 2 * BN);
-    tmem_relinquish();
+    if constexpr (CG == 2) {
+      tmem_alloc_cg2(tmem_ptr, 2 * BN);
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc(tmem_ptr, 2 * BN);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (every CTA stages its own A rows and its share of B) =====
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      for (int item = worker; item < total_items; item += n_workers) {
         const int tile = item / p.split_k;
         const int ks = item - tile * p.split_k;
-        const int m0 = (tile / p.n_tiles) * GEMM_BM;
-        const int n0 = (tile % p.n_tiles) * BN;
+        const int m0 = (tile / p.n_tiles) * (GEMM_BM * CG) + static_cast<int>(cta_rank) * GEMM_BM;
+        const int n0 = (tile % p.n_tiles) * BN + static_cast<int>(cta_rank) * BNL;
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, total_kb);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
-          void* da = smem_a + stage * S::A_BYTES;
-          void* db = smem_b + stage * S::B_BYTES;
-          if constexpr (A_MN) {
+          uint8_t* da = smem_a + stage * S::A_BYTES;
+          uint8_t* db = smem_b + stage * S::B_BYTES;
+          if constexpr (CG == 2) {
+            // completion bytes of BOTH CTAs are posted on the leader's barrier
+            const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);
+            if constexpr (A_MN) {
 #pragma unroll
-            for (int c = 0; c < GEMM_BM / 64; ++c)
-              tma_load_2d(static_cast<uint8_t*>(da) + c * (GEMM_BK * 128), &tma_a, &full_bar[stage], m0 + c * 64,
-                          kb * GEMM_BK);
-          } else {
-            tma_load_2d(da, &tma_a, &full_bar[stage], kb * GEMM_BK, m0);
-          }
-          if constexpr (B_MN) {
+              for (int c = 0; c < GEMM_BM / 64; ++c)
+                tma_load_2d_cg2(da + c * (GEMM_BK * 128), &tma_a, bar, m0 + c * 64, kb * GEMM_BK);
+            } else {
+              tma_load_2d_cg2(da, &tma_a, bar, kb * GEMM_BK, m0);
+            }
+            if constexpr (B_MN) {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c)
-              tma_load_2d(static_cast<uint8_t*>(db) + c * (GEMM_BK * 128), &tma_b, &full_bar[stage], n0 + c * 64,
-                          kb * GEMM_BK);
+              for (int c = 0; c < BNL / 64; ++c)
+                tma_load_2d_cg2(db + c * (GEMM_BK * 128), &tma_b, bar, n0 + c * 64, kb * GEMM_BK);
+            } else {
+              tma_load_2d_cg2(db, &tma_b, bar, kb * GEMM_BK, n0);
+            }
           } else {
-            tma_load_2d(db, &tma_b, &full_bar[stage], kb * GEMM_BK, n0);
+            mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+            if constexpr (A_MN) {
+#pragma unroll
+              for (int c = 0; c < GEMM_BM / 64; ++c)
+                tma_load_2d(da + c * (GEMM_BK * 128), &tma_a, &full_bar[stage], m0 + c * 64, kb * GEMM_BK);
+            } else {
+              tma_load_2d(da, &tma_a, &full_bar[stage], kb * GEMM_BK, m0);
+            }
+            if constexpr (B_MN) {
+#pragma unroll
+              for (int c = 0; c < BNL / 64; ++c)
+                tma_load_2d(db + c * (GEMM_BK * 128), &tma_b, &full_bar[stage], n0 + c * 64, kb * GEMM_BK);
+            } else {
+              tma_load_2d(db, &tma_b, &full_bar[stage], kb * GEMM_BK, n0);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(GEMM_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    // ===================== MMA issuer (pair leader only) =====================
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(GEMM_BM * CG, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       // descriptor geometry
       const uint32_t a_lbo = A_MN ? (p.dbg_lbo ? p.dbg_lbo : GEMM_BK * 128) : 16;
       const uint32_t b_lbo = B_MN ? (p.dbg_lbo ? p.dbg_lbo : GEMM_BK * 128) : 16;
@@ -262,7 +340,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      for (int item = worker; item < total_items; item += n_workers) {
         const int ks = item % p.split_k;
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, total_kb);
@@ -278,12 +356,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             const uint64_t ad = make_smem_desc(sa + k * a_kstep, a_lbo, sbo);
             const uint64_t bd = make_smem_desc(sb + k * b_kstep, b_lbo, sbo);
-            tc_mma_f16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (CG == 2) tc_mma_f16_cg2(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else tc_mma_f16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          tc_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) once these MMAs retire
+          if constexpr (CG == 2) tc_commit_cg2(&empty_bar[stage], 3); else tc_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&tmem_full[acc]);
+        if constexpr (CG == 2) tc_commit_cg2(&tmem_full[acc], 3); else tc_commit(&tmem_full[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -292,15 +372,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     const int ew = warp - 2;             // 0..7
     const int quad = warp & 3;           // TMEM lane quadrant this warp may access
     const int half = ew >> 2;            // which half of the column chunks this warp handles
+    float* stg = stg_all + ew * (32 * 32);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+    const uint32_t empty_remote = (CG == 2) ? mapa_shared(smem_u32(&tmem_empty[0]), 0) : 0u;
+    for (int item = worker; item < total_items; item += n_workers) {
       const int tile = item / p.split_k;
-      const int m0 = (tile / p.n_tiles) * GEMM_BM;
+      const int m0 = (tile / p.n_tiles) * (GEMM_BM * CG) + static_cast<int>(cta_rank) * GEMM_BM;
       const int n0 = (tile % p.n_tiles) * BN;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int m = m0 + quad * 32 + lane;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
       constexpr int CHUNKS = BN / 32;
 #pragma unroll 1
@@ -309,20 +390,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         uint32_t r[32];
         tmem_ld_32x32(t_row + c * 32, r);
         tc_wait_ld();
-        gemm_epilogue_chunk<EPI>(p, r, m, n0 + c * 32);
+        gemm_epilogue_chunk<EPI>(p, r, stg, lane, m0 + quad * 32, n0 + c * 32);
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(empty_remote + acc * 8);
+        else mbar_arrive(&tmem_empty[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
+    __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
+    if constexpr (CG == 2) tmem_dealloc_cg2(tmem_base, 2 * BN); else tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 

@@ -101,12 +101,14 @@ def ln_fwd(x, gamma, beta, y, mean, rstd, cls_out, *, n_seq, seq_len, hidden, ep
 
 
 def ln_bwd(dy, dy_cls, x, gamma, mean, rstd, dx, dgamma, dbeta, dbias, *, n_seq, seq_len, hidden, in_scale=1.0,
-           out_scale=1.0):
+           out_scale=1.0, row_ws=None):
     _need_cuda(x, dx)
+    if row_ws is not None:
+        assert row_ws.dtype == torch.float32 and row_ws.numel() >= 2 * n_seq * seq_len
     check(_lib_().cdr_ln_bwd(_p(dy), _p(dy_cls), _p(x), _p(gamma), _p(mean), _p(rstd), _p(dx), _p(dgamma), _p(dbeta),
-                             _p(dbias), _i32(n_seq), _i32(seq_len), _i32(hidden), _f32(in_scale), _f32(out_scale),
-                             stream_ptr()), "cdr_ln_bwd")
-    _count(1)
+                             _p(dbias), _p(row_ws), _i32(n_seq), _i32(seq_len), _i32(hidden), _f32(in_scale),
+                             _f32(out_scale), stream_ptr()), "cdr_ln_bwd")
+    _count(2 if (row_ws is not None and dy is not None and dy_cls is None) else 1)
 
 
 def colsum(x, out, *, rows, cols, ld=None, scale=1.0):
@@ -122,6 +124,23 @@ def cast_f32_f16(src, dst):
     assert src.dtype == torch.float32 and dst.dtype == torch.float16 and src.numel() == dst.numel()
     assert src.is_contiguous() and dst.is_contiguous()
     check(_lib_().cdr_cast_f32_f16(_p(src), _p(dst), _i64(src.numel()), stream_ptr()), "cdr_cast_f32_f16")
+    _count(1)
+
+
+def cast_table(entries, device):
+    """Device-resident cdr_cast_item table for cast_multi: entries = [(src fp32, dst fp16|fp32), ...]."""
+    rows = []
+    for src, dst in entries:
+        assert src.dtype == torch.float32 and src.is_contiguous() and dst.is_contiguous()
+        assert src.numel() == dst.numel() and src.data_ptr() % 16 == 0 and dst.data_ptr() % 16 == 0
+        rows.append([src.data_ptr(), dst.data_ptr(), src.numel(), 1 if dst.dtype == torch.float32 else 0])
+    # struct cdr_cast_item {ptr, ptr, int64, int32, int32}: 4 little-endian int64 words per entry
+    table = torch.tensor(rows, dtype=torch.int64).to(device)
+    return table, max(r[2] for r in rows)
+
+
+def cast_multi(table, max_n):
+    check(_lib_().cdr_cast_multi(_p(table), _i32(table.shape[0]), _i64(max_n), stream_ptr()), "cdr_cast_multi")
     _count(1)
 
 

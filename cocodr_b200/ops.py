@@ -43,32 +43,74 @@ class LayerShadow:
     """fp16 operand copies of one BertLayer's matrices (QKV packed [3H, H]) + packed fp32 QKV bias.
 
     The HF-named fp32 ``nn.Parameter``s stay the source of truth (state-dict contract, SURVEY §5.4);
-    the shadow is rebuilt whenever a parameter's storage or version counter changes."""
+    the shadow is rebuilt whenever a parameter's storage or version counter changes -- by its owner
+    (``ShadowSet.refresh``: one launch for all layers) or, standalone, by ``refresh``."""
 
-    __slots__ = ("key", "wqkv", "bqkv", "wo", "wi", "wo2")
+    __slots__ = ("key", "wqkv", "bqkv", "wo", "wi", "wo2", "managed")
 
     def __init__(self):
         self.key = None
+        self.managed = False
 
-    def refresh(self, wq, bq, wk, bk, wv, bv, wo, wi, wo2):
-        srcs = (wq, bq, wk, bk, wv, bv, wo, wi, wo2)
-        key = tuple((t.data_ptr(), t._version) for t in srcs)
-        if key == self.key:
-            return self
+    def _alloc(self, wq, wi):
         dev = wq.device
         H, I = wq.shape[0], wi.shape[0]
         if self.key is None or self.wqkv.device != dev or self.wqkv.shape != (3 * H, H):
             self.wqkv, self.bqkv = _f16(3 * H, H, dev=dev), _f32(3 * H, dev=dev)
             self.wo, self.wi, self.wo2 = _f16(H, H, dev=dev), _f16(I, H, dev=dev), _f16(H, I, dev=dev)
+            return True
+        return False
+
+    def pairs(self, wq, bq, wk, bk, wv, bv, wo, wi, wo2):
+        H = wq.shape[0]
+        out = []
+        for i, (w, b) in enumerate(((wq, bq), (wk, bk), (wv, bv))):
+            out.append((w.detach(), self.wqkv[i * H:(i + 1) * H]))
+            out.append((b.detach(), self.bqkv[i * H:(i + 1) * H]))
+        out += [(wo.detach(), self.wo), (wi.detach(), self.wi), (wo2.detach(), self.wo2)]
+        return out
+
+    def refresh(self, wq, bq, wk, bk, wv, bv, wo, wi, wo2):
+        if self.managed:
+            return self
+        srcs = (wq, bq, wk, bk, wv, bv, wo, wi, wo2)
+        key = tuple((t.data_ptr(), t._version) for t in srcs)
+        if key == self.key:
+            return self
+        self._alloc(wq, wi)
         with torch.no_grad():
-            for i, (w, b) in enumerate(((wq, bq), (wk, bk), (wv, bv))):
-                K.cast_f32_f16(w.detach().contiguous(), self.wqkv[i * H:(i + 1) * H])
-                self.bqkv[i * H:(i + 1) * H].copy_(b.detach())
-            K.cast_f32_f16(wo.detach().contiguous(), self.wo)
-            K.cast_f32_f16(wi.detach().contiguous(), self.wi)
-            K.cast_f32_f16(wo2.detach().contiguous(), self.wo2)
+            table, max_n = K.cast_table(self.pairs(*srcs), wq.device)
+            K.cast_multi(table, max_n)
         self.key = key
         return self
+
+
+class ShadowSet:
+    """All LayerShadows of an encoder, refreshed by ONE cast launch per optimizer step."""
+
+    def __init__(self, n_layers):
+        self.layers = [LayerShadow() for _ in range(n_layers)]
+        for sh in self.layers:
+            sh.managed = True
+        self.ptr_key = self.ver_key = self.table = None
+        self.max_n = 0
+
+    def refresh(self, per_layer_srcs):
+        """per_layer_srcs[i] = (wq, bq, wk, bk, wv, bv, wo, wi, wo2) of layer i."""
+        ptr_key = tuple(t.data_ptr() for srcs in per_layer_srcs for t in srcs)
+        ver_key = tuple(t._version for srcs in per_layer_srcs for t in srcs)
+        if ptr_key == self.ptr_key and ver_key == self.ver_key:
+            return
+        with torch.no_grad():
+            realloc = False
+            for sh, srcs in zip(self.layers, per_layer_srcs):
+                realloc |= sh._alloc(srcs[0], srcs[7])
+                sh.key = True
+            if realloc or ptr_key != self.ptr_key or self.table is None:
+                entries = [e for sh, srcs in zip(self.layers, per_layer_srcs) for e in sh.pairs(*srcs)]
+                self.table, self.max_n = K.cast_table(entries, per_layer_srcs[0][0].device)
+            K.cast_multi(self.table, self.max_n)
+        self.ptr_key, self.ver_key = ptr_key, ver_key
 
 
 class EmbedLN(torch.autograd.Function):
@@ -156,32 +198,36 @@ class BertLayerFn(torch.autograd.Function):
             dy = dy.contiguous()
         if dcls is not None:
             dcls = dcls.contiguous().float()
+        # ---- one zero-fill for every parameter-gradient accumulator of the layer (views below)
+        sizes = (H, H, H, H * I, I, I * H, H, H, H, H * H, 3 * H * H, 3 * H)
+        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        views, off = [], 0
+        for n in sizes:
+            views.append(flat[off:off + n])
+            off += n
+        dg2, dbe2, dbo2, dwo2, dbi, dwi, dg1, dbe1, dbo, dwo, dwqkv, dbqkv = views
+        dwo2, dwi, dwo, dwqkv = dwo2.view(H, I), dwi.view(I, H), dwo.view(H, H), dwqkv.view(3 * H, H)
+        row_ws = _f32(2 * T, dev=dev)
         # ---- output LayerNorm; column sums of its dx are the FFN-down bias gradient
         dy2 = _f16(T, H, dev=dev)
-        dg2, dbe2, dbo2 = _z32(H, dev=dev), _z32(H, dev=dev), _z32(H, dev=dev)
         K.ln_bwd(dy, dcls, y2, g2, mean2, rstd2, dy2, dg2, dbe2, dbo2, n_seq=n_seq, seq_len=L, hidden=H, in_scale=S,
-                 out_scale=inv)
+                 out_scale=inv, row_ws=row_ws)
         # ---- FFN down: dG = dy2 W2 (fused gelu'), dW2 = dy2^T G
         dz = _f16(T, I, dev=dev)
         K.gemm(dy2, wo2, dz, M=T, N=I, K=H, b_major=1, epilogue=K.EPI_DGELU, aux=z)
-        dwo2 = _z32(H, I, dev=dev)
         K.gemm(dy2, gl, dwo2, M=H, N=I, K=T, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0, alpha=inv)
         # ---- FFN up: dx1 = dZ W1 + dy2 (residual), dW1 = dZ^T x1, db1 = colsum(dZ)
-        dbi = _z32(I, dev=dev)
         K.colsum(dz, dbi, rows=T, cols=I, scale=inv)
         dx1 = _f16(T, H, dev=dev)
         K.gemm(dz, wi, dx1, M=T, N=H, K=I, b_major=1, epilogue=K.EPI_BIAS_RESIDUAL, aux=dy2)
-        dwi = _z32(I, H, dev=dev)
         K.gemm(dz, x1, dwi, M=I, N=H, K=T, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0, alpha=inv)
         # ---- attention-output LayerNorm
         dy1 = _f16(T, H, dev=dev)
-        dg1, dbe1, dbo = _z32(H, dev=dev), _z32(H, dev=dev), _z32(H, dev=dev)
         K.ln_bwd(dx1, None, y1, g1, mean1, rstd1, dy1, dg1, dbe1, dbo, n_seq=n_seq, seq_len=L, hidden=H, in_scale=S,
-                 out_scale=inv)
+                 out_scale=inv, row_ws=row_ws)
         # ---- attention output projection
         datt = _f16(T, H, dev=dev)
         K.gemm(dy1, wo, datt, M=T, N=H, K=H, b_major=1)
-        dwo = _z32(H, H, dev=dev)
         K.gemm(dy1, att, dwo, M=H, N=H, K=T, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0, alpha=inv)
         # ---- attention core
         dqkv = _f16(T, 3 * H, dev=dev)
@@ -191,10 +237,8 @@ class BertLayerFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = _f16(T, H, dev=dev)
             K.gemm(dqkv, wqkv, dx, M=T, N=H, K=3 * H, b_major=1, epilogue=K.EPI_BIAS_RESIDUAL, aux=dy1)
-        dwqkv = _z32(3 * H, H, dev=dev)
         K.gemm(dqkv, x, dwqkv, M=3 * H, N=H, K=T, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0,
                alpha=inv)
-        dbqkv = _z32(3 * H, dev=dev)
         K.colsum(dqkv, dbqkv, rows=T, cols=3 * H, scale=inv)
         return (dx, None, dwqkv[0:H], dbqkv[0:H], dwqkv[H:2 * H], dbqkv[H:2 * H], dwqkv[2 * H:], dbqkv[2 * H:], dwo,
                 dbo, dg1, dbe1, dwi, dbi, dwo2, dbo2, dg2, dbe2, None, None, None, None, None, None)

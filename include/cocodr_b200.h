@@ -90,11 +90,23 @@ int cdr_ln_fwd(const void* x, const float* gamma, const float* beta, void* y, fl
                int32_t n_seq, int32_t seq_len, int32_t hidden, float eps, void* stream);
 /* dx = LN'(dy [+ in_scale * dy_cls on row 0 of every sequence]); dbias (optional) += column sums of dx.
  * dy (fp16) is already in the scaled-gradient domain; dy_cls (fp32) enters it through in_scale. */
+/* row_ws: optional scratch of 2*n_seq*seq_len floats; when given (and dy_cls is NULL) the backward runs as two
+ * bandwidth-shaped passes (dx, then column sums) instead of one fused kernel. */
 int cdr_ln_bwd(const void* dy, const float* dy_cls, const void* x, const float* gamma, const float* mean,
-               const float* rstd, void* dx, float* dgamma, float* dbeta, float* dbias, int32_t n_seq, int32_t seq_len,
-               int32_t hidden, float in_scale, float out_scale, void* stream);
+               const float* rstd, void* dx, float* dgamma, float* dbeta, float* dbias, float* row_ws, int32_t n_seq,
+               int32_t seq_len, int32_t hidden, float in_scale, float out_scale, void* stream);
 int cdr_colsum_f16(const void* x, float* out, int64_t rows, int64_t cols, int64_t ld, float scale, void* stream);
 int cdr_cast_f32_f16(const float* src, void* dst, int64_t n, void* stream);
+/* A whole table of casts in one launch (per-step refresh of all fp16 weight shadows).  The table lives in
+ * DEVICE memory; every src/dst must be 16-byte aligned.  dst_f32 != 0 copies fp32 -> fp32 instead. */
+typedef struct cdr_cast_item {
+  const float* src;
+  void* dst;
+  int64_t n;
+  int32_t dst_f32;
+  int32_t reserved;
+} cdr_cast_item;
+int cdr_cast_multi(const cdr_cast_item* items_device, int32_t count, int64_t max_n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused multi-head attention (K3): softmax(Q K^T * scale + key_bias) V on tcgen05, head_dim 64,

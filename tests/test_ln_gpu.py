@@ -41,6 +41,33 @@ def test_ln_fwd_bwd(n_seq, L, H):
     assert (dbias - ref).abs().max().item() < 5e-3 * ref.abs().max().item() + 2e-2
 
 
+@pytest.mark.parametrize("n_seq,L,H", [(3, 32, 128), (16, 128, 768), (2, 64, 1024), (5, 8, 64)])
+def test_ln_bwd_split_path(n_seq, L, H):
+    """row_ws given and no fp32 CLS gradient -> two-pass backward (dx pass + column-sum pass)."""
+    from cocodr_b200 import kernels as k
+    g = torch.Generator().manual_seed(H + L + 1)
+    T = n_seq * L
+    x = torch.randn(T, H, generator=g).half().cuda()
+    gamma = (1 + 0.1 * torch.randn(H, generator=g)).cuda()
+    beta = (0.1 * torch.randn(H, generator=g)).cuda()
+    y = torch.empty_like(x)
+    mean, rstd = torch.empty(T, device="cuda"), torch.empty(T, device="cuda")
+    k.ln_fwd(x, gamma, beta, y, mean, rstd, None, n_seq=n_seq, seq_len=L, hidden=H, eps=1e-12)
+    dy = torch.randn(T, H, generator=g).half().cuda()
+    dx = torch.empty_like(x)
+    dgamma, dbeta, dbias = (torch.ones(H, device="cuda") for _ in range(3))  # accumulate semantics
+    ws = torch.empty(2 * T, device="cuda")
+    k.ln_bwd(dy, None, x, gamma, mean, rstd, dx, dgamma, dbeta, dbias, n_seq=n_seq, seq_len=L, hidden=H,
+             out_scale=0.25, row_ws=ws)
+    xf = x.float().requires_grad_(True)
+    gf, bf = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    (F.layer_norm(xf, (H,), gf, bf, 1e-12) * dy.float()).sum().backward()
+    assert (dx.float() - xf.grad).abs().max().item() < 4e-3 * xf.grad.abs().max().item() + 1e-3
+    for got, ref in ((dgamma, gf.grad), (dbeta, bf.grad), (dbias, xf.grad.sum(0))):
+        ref = 1.0 + 0.25 * ref
+        assert (got - ref).abs().max().item() < 3e-3 * ref.abs().max().item() + 5e-3
+
+
 def test_embed_ln_fwd_bwd():
     from cocodr_b200 import kernels as k
     from oracle import bert_ref
