@@ -291,48 +291,73 @@ ln_bwd_dx_kernel(const __half* __restrict__ dy, const __half* __restrict__ x, co
     }
 }
 
-__global__ void __launch_bounds__(128)
+constexpr int LNC_Y = 8;  // row lanes per block: cross-lane reduction in smem before the global atomics
+__global__ void __launch_bounds__(128 * LNC_Y)
 ln_bwd_cols_kernel(const __half* __restrict__ dy, const __half* __restrict__ x, const float* __restrict__ gamma,
                    const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                    const float2* __restrict__ rowc, float* __restrict__ dgamma, float* __restrict__ dbeta,
                    float* __restrict__ dcol, int rows, int hidden, int rows_per_block, float out_scale) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
-  if (c >= hidden) return;
+  __shared__ float red[LNC_Y][128 * 8];
+  __shared__ float red_c[LNC_Y];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c = (blockIdx.x * blockDim.x + tx) * 8;
+  const bool active = c < hidden;
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(r0 + rows_per_block, rows);
   float dg[8], db[8], s3[8], s4[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) dg[k] = db[k] = s3[k] = s4[k] = 0.f;
   float csum = 0.f;
+  if (active) {
 #pragma unroll 4
-  for (int r = r0; r < r1; ++r) {
-    float d[8], xv[8];
-    load8_h(dy + static_cast<long long>(r) * hidden + c, d);
-    load8_h(x + static_cast<long long>(r) * hidden + c, xv);
-    const float m = mean_in[r], rs = rstd_in[r];
-    const float2 cc = rowc[r];
-    const float rc2 = rs * cc.y;
-    csum = fmaf(rs, cc.x, csum);
+    for (int r = r0 + ty; r < r1; r += LNC_Y) {
+      float d[8], xv[8];
+      load8_h(dy + static_cast<long long>(r) * hidden + c, d);
+      load8_h(x + static_cast<long long>(r) * hidden + c, xv);
+      const float m = mean_in[r], rs = rstd_in[r];
+      const float2 cc = rowc[r];
+      const float rc2 = rs * cc.y;
+      csum = fmaf(rs, cc.x, csum);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float xh = (xv[k] - m) * rs;
-      dg[k] = fmaf(d[k], xh, dg[k]);
-      db[k] += d[k];
-      s3[k] = fmaf(rs, d[k], s3[k]);
-      s4[k] = fmaf(rc2, xh, s4[k]);
+      for (int k = 0; k < 8; ++k) {
+        const float xh = (xv[k] - m) * rs;
+        dg[k] = fmaf(d[k], xh, dg[k]);
+        db[k] += d[k];
+        s3[k] = fmaf(rs, d[k], s3[k]);
+        s4[k] = fmaf(rc2, xh, s4[k]);
+      }
     }
   }
+  if (tx == 0) red_c[ty] = csum;
   float g[8];
-  load8_f(gamma + c, g);
+  if (active) load8_f(gamma + c, g);
+  // dcol needs the block-wide sum of csum first
+  __syncthreads();
+  float ctot = 0.f;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    s3[k] = (g[k] * s3[k] - csum - s4[k]) * out_scale;
-    dg[k] *= out_scale;
-    db[k] *= out_scale;
-  }
-  if (dgamma) atomic_add8(dgamma + c, dg);
-  if (dbeta) atomic_add8(dbeta + c, db);
-  if (dcol) atomic_add8(dcol + c, s3);
+  for (int y = 0; y < LNC_Y; ++y) ctot += red_c[y];
+  auto reduce_emit = [&](float (&acc)[8], float* dst, bool is_dcol) {
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[ty][tx * 8 + k] = acc[k];
+    __syncthreads();
+    if (ty == 0 && active && dst != nullptr) {
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float t = 0.f;
+#pragma unroll
+        for (int y = 0; y < LNC_Y; ++y) t += red[y][tx * 8 + k];
+        o[k] = (is_dcol ? (t - ctot) : t) * out_scale;
+      }
+      atomic_add8(dst + c, o);
+    }
+  };
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s3[k] = active ? g[k] * s3[k] - s4[k] : 0.f;  // dcol before the -C term
+  reduce_emit(dg, dgamma, false);
+  reduce_emit(db, dbeta, false);
+  reduce_emit(s3, dcol, true);
 }
 
 // out[c] += scale * sum_r x[r, c]      (fp16 in, fp32 accumulate; bias gradients)
@@ -506,14 +531,14 @@ int cdr_ln_bwd(const void* dy, const float* dy_cls, const void* x, const float* 
 #undef LN_DX
     CDR_LAUNCH_CHECK();
     if (dgamma || dbeta || dbias) {
-      int threads = nvec < 128 ? ((nvec + 31) / 32) * 32 : 128;
-      if (nvec % 32 != 0 && nvec < 128) threads = nvec <= 32 ? 32 : (nvec <= 64 ? 64 : (nvec <= 96 ? 96 : 128));
+      const int threads = nvec < 128 ? ((nvec + 31) / 32) * 32 : 128;
       const int gx = (nvec + threads - 1) / threads;
-      int rpb = (rows + 4 * sm_count() - 1) / (4 * sm_count());
-      if (rpb < 16) rpb = 16;
+      int rpb = (rows * gx + sm_count() - 1) / sm_count();  // ~one block per SM
+      rpb = ((rpb + LNC_Y - 1) / LNC_Y) * LNC_Y;
+      if (rpb < 4 * LNC_Y) rpb = 4 * LNC_Y;
       const int gy = (rows + rpb - 1) / rpb;
-      ln_bwd_cols_kernel<<<dim3(gx, gy), threads, 0, st>>>(dyh, xh, gamma, mean, rstd, rowc, dgamma, dbeta, dbias, rows,
-                                                          hidden, rpb, out_scale);
+      ln_bwd_cols_kernel<<<dim3(gx, gy), dim3(threads, LNC_Y), 0, st>>>(dyh, xh, gamma, mean, rstd, rowc, dgamma, dbeta,
+                                                                      dbias, rows, hidden, rpb, out_scale);
       CDR_LAUNCH_CHECK();
     }
     return CDR_OK;

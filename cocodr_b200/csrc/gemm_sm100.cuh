@@ -5,7 +5,7 @@
 // * one CTA per SM, static round-robin over (m_tile, n_tile, k_split) work items
 // * warp 0  : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx-count)
 // * warp 1  : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, cta_group::1)
-// * warps 2-9: epilogue (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
+// * warps 2-17: epilogue (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
 // * two TMEM accumulator stages (2 x BN columns) so the epilogue of tile i overlaps the MMAs of
 //   tile i+1
 // * operands may be K-major ([rows, K] row-major, the "NT" case) or MN-major ([K, rows] row-major)
@@ -27,7 +27,7 @@ namespace cdr {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_EPI_WARPS = 16;  // 4 per TMEM lane quadrant / SM sub-partition: the epilogue math is latency-bound
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;  // 320
 
 struct GemmParams {
@@ -65,9 +65,10 @@ struct GemmSmem {
   static constexpr int B_ROWS = BN / CG;
   static constexpr int B_BYTES = B_ROWS * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (STAGE_BYTES >= 49152) ? 4 : (STAGE_BYTES >= 32768 ? 6 : 8);
   static constexpr int BAR_BYTES = 256;
   static constexpr int STG_BYTES = GEMM_EPI_WARPS * 32 * 32 * 4;  // epilogue staging tiles
+  static constexpr int BUDGET = 232448 - 1024 - BAR_BYTES - STG_BYTES;  // 227 KB per CTA
+  static constexpr int STAGES = (BUDGET / STAGE_BYTES) > 8 ? 8 : (BUDGET / STAGE_BYTES);
   static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + STG_BYTES + 1024;  // +1024 alignment slack
   static_assert(TOTAL <= 232448, "shared memory budget");
 };
@@ -369,9 +370,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
   } else {
     // ===================== epilogue =====================
-    const int ew = warp - 2;             // 0..7
+    const int ew = warp - 2;             // 0..GEMM_EPI_WARPS-1
     const int quad = warp & 3;           // TMEM lane quadrant this warp may access
-    const int half = ew >> 2;            // which half of the column chunks this warp handles
+    const int half = ew >> 2;            // which share of the column chunks this warp handles
     float* stg = stg_all + ew * (32 * 32);
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -385,7 +386,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
       constexpr int CHUNKS = BN / 32;
 #pragma unroll 1
-      for (int c = half; c < CHUNKS; c += 2) {
+      for (int c = half; c < CHUNKS; c += GEMM_EPI_WARPS / 4) {
         if (n0 + c * 32 >= p.N) break;
         uint32_t r[32];
         tmem_ld_32x32(t_row + c * 32, r);

@@ -56,16 +56,43 @@ __host__ __device__ __forceinline__ int next_pow2(int v) {
   return n;
 }
 
-// thresh[q] = m-th largest of sample[q, 0:S]
-__global__ void __launch_bounds__(1024)
+__device__ __forceinline__ unsigned int flip_score(float s) {
+  const unsigned int u = __float_as_uint(s);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// thresh[q] = m-th largest of sample[q, 0:S]: MSB-first radix select (4 passes of 8 bits) on the
+// order-preserving integer image of the scores -- no sort, the row is re-read from L2 each pass.
+__global__ void __launch_bounds__(256)
 scan_threshold_kernel(const float* __restrict__ sample, int S, int m, float* __restrict__ thresh) {
-  extern __shared__ unsigned long long keys[];
-  const int q = blockIdx.x;
-  const int n = next_pow2(S);
-  for (int i = threadIdx.x; i < n; i += blockDim.x)
-    keys[i] = i < S ? pack_score_doc(sample[static_cast<long long>(q) * S + i], 0u) : 0ull;
-  bitonic_sort_desc(keys, n);
-  if (threadIdx.x == 0) thresh[q] = unflip_score(static_cast<unsigned int>(keys[m - 1] >> 32));
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned int sel_prefix, sel_rank;
+  const float* row = sample + static_cast<long long>(blockIdx.x) * S;
+  unsigned int prefix = 0, mask = 0, rank = static_cast<unsigned int>(m);
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < S; i += blockDim.x) {
+      const unsigned int u = flip_score(row[i]);
+      if ((u & mask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned int r = rank;
+      int bin = 255;
+      for (; bin > 0; --bin) {
+        if (hist[bin] >= r) break;
+        r -= hist[bin];
+      }
+      sel_prefix = prefix | (static_cast<unsigned int>(bin) << shift);
+      sel_rank = r;
+    }
+    __syncthreads();
+    prefix = sel_prefix;
+    rank = sel_rank;
+    mask |= 0xFFu << shift;
+  }
+  if (threadIdx.x == 0) thresh[blockIdx.x] = unflip_score(prefix);
 }
 
 __global__ void scan_init_kernel(float* thresh, int* count, int n_q, int fill_thresh) {
@@ -217,13 +244,7 @@ int cdr_scan_topk(const cdr_scan_args* a, void* stream) {
     GemmParams p{};
     p.out = sample; p.ldo = pl.S;
     if (int rc = gemm_run(g, p, st)) return rc;
-    const int smem = next_pow2(pl.S) * 8;
-    static bool cfg_t = false;
-    if (!cfg_t) {
-      if (int rc = set_smem(scan_threshold_kernel, SCAN_SORT_MAX * 8)) return rc;
-      cfg_t = true;
-    }
-    scan_threshold_kernel<<<a->n_q, 1024, smem, st>>>(sample, pl.S, pl.m, thresh);
+    scan_threshold_kernel<<<a->n_q, 256, 0, st>>>(sample, pl.S, pl.m, thresh);
     CDR_LAUNCH_CHECK();
   }
   {

@@ -15,6 +15,7 @@ import torch
 from . import kernels as K
 
 _GRAD_SCALE = 1024.0
+FORCE_SHADOW_REFRESH = False  # set while a CUDA graph is being captured (graph.py)
 
 
 def set_grad_scale(s: float):
@@ -99,7 +100,7 @@ class ShadowSet:
         """per_layer_srcs[i] = (wq, bq, wk, bk, wv, bv, wo, wi, wo2) of layer i."""
         ptr_key = tuple(t.data_ptr() for srcs in per_layer_srcs for t in srcs)
         ver_key = tuple(t._version for srcs in per_layer_srcs for t in srcs)
-        if ptr_key == self.ptr_key and ver_key == self.ver_key:
+        if ptr_key == self.ptr_key and ver_key == self.ver_key and not FORCE_SHADOW_REFRESH:
             return
         with torch.no_grad():
             realloc = False
