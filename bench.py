@@ -289,6 +289,20 @@ def run_ours(args):
     e1.record()
     torch.cuda.synchronize()
     ev, kernels.gemm_events = kernels.gemm_events, None
+    # per-operator device time of one more eager step (every cdr_* call bracketed by events)
+    kernels.op_events = []
+    if graphed is not None:
+        graphed._eager_step()
+    else:
+        resident_step(1)
+    torch.cuda.synchronize()
+    opev, kernels.op_events = kernels.op_events, None
+    op_ms = {}
+    for name, a, b in opev:
+        t = op_ms.setdefault(name, [0, 0.0])
+        t[0] += 1
+        t[1] += a.elapsed_time(b)
+    op_breakdown = {k: {"calls": v[0], "ms": round(v[1], 3)} for k, v in sorted(op_ms.items(), key=lambda kv: -kv[1][1])}
     gemm_ms = sum(a.elapsed_time(b) for _, a, b in ev)
     gemm_flops = sum(f for f, _, _ in ev)
     step_ms_instr = e0.elapsed_time(e1)
@@ -364,6 +378,7 @@ def run_ours(args):
                 "gpu_launches": launches,
                 "roofline": roofline,
                 "model_flops_frac_of_peak": model_frac,
+                "op_breakdown_ms_per_step": op_breakdown,
                 "cpu_baseline": cpu_baseline,
                 "scan": scan_res}
         print(json.dumps(line), flush=True)

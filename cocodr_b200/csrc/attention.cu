@@ -1,4 +1,4 @@
-// Fused multi-head attention (K3) for BERT, head_dim 64, seq_len <= 128, forward and backward, on the
+// Fused multi-head attention (K3) for BERT, head_dim 64, seq_len <= 512, forward and backward, on the
 // sm_100a tensor cores (tcgen05.mma, accumulators in TMEM, operands staged by TMA).
 //
 // One CTA per (sequence, head).  Q/K/V come straight out of the packed QKV projection [T, 3H]
@@ -382,11 +382,396 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
   }
 }
 
+// ===================================================================================== seq_len > 128
+// Longer sequences (BERT-large at L = 256 for COCO pre-training, up to the 512-position table) are tiled
+// 128 x 128.  Forward: one CTA per (sequence, head, query tile), two passes over the key tiles -- pass 1
+// takes the exact row maxima (S = Q K_j^T only), pass 2 recomputes S_j, exponentiates against the final
+// maximum and accumulates O += P_j V_j in TMEM, so no running rescale of O is needed.  Backward: one CTA
+// per (sequence, head, key tile) loops over the query tiles; dV_j / dK_j accumulate in TMEM across the
+// loop, dQ_i contributions of the different key tiles meet in an fp32 workspace (red.add) that
+// dq_convert_kernel folds into the packed fp16 dQKV afterwards.
+constexpr int ATT_FWDM_SMEM = 5 * ATT_TILE_BYTES + 512 + 128 + 1024;  // Q K V | P (2 tiles)
+
+__global__ void __launch_bounds__(128, 2)
+fmha_fwd_multi_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttParams p, const int q_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + ATT_TILE_BYTES;
+  uint8_t* sV = smem + 2 * ATT_TILE_BYTES;
+  uint8_t* sP = smem + 3 * ATT_TILE_BYTES;
+  float* sBias = reinterpret_cast<float*>(smem + 5 * ATT_TILE_BYTES);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 5 * ATT_TILE_BYTES + 512);  // 0: Q, 1: K(/V), 2: S, 3: O
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int qt = blockIdx.x % q_tiles;
+  const int sh = blockIdx.x / q_tiles;
+  const int seq = sh / p.heads, h = sh % p.heads;
+  const int L = p.seq_len;
+  const int row0 = seq * L;
+  const int q0 = qt * ATT_T;
+  const int n_kv = (L + ATT_T - 1) / ATT_T;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tma_qkv);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) mbar_init(&bar[i], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_ptr, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  const uint32_t tmem_o = tmem + 128;
+  const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK), va = smem_u32(sV), pa = smem_u32(sP);
+  constexpr uint32_t idesc_s = make_idesc_f16(ATT_T, ATT_T, 0, 0);
+  constexpr uint32_t idesc_o = make_idesc_f16(ATT_T, ATT_D, 0, 1);
+  const int r = tid;
+  const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const float sl2 = p.scale * LOG2E;
+  uint32_t ph_k = 0, ph_s = 0, ph_o = 0;
+
+  if (tid == 0) {
+    mbar_expect_tx(&bar[0], ATT_TILE_BYTES);
+    tma_load_2d(sQ, &tma_qkv, &bar[0], h * ATT_D, row0 + q0);
+  }
+  float mx = -INFINITY, sum = 0.f;
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll 1
+    for (int j = 0; j < n_kv; ++j) {
+      const int k0 = j * ATT_T;
+      // all threads are past their reads of the previous tile's bias / S / P here (loop-end barrier)
+      {
+        const int c = k0 + tid;
+        float b = -INFINITY;
+        if (c < L) b = p.key_bias ? p.key_bias[static_cast<long long>(seq) * L + c] * LOG2E : 0.f;
+        sBias[tid] = b;
+      }
+      if (tid == 0) {
+        mbar_expect_tx(&bar[1], (pass == 1 ? 2 : 1) * ATT_TILE_BYTES);
+        tma_load_2d(sK, &tma_qkv, &bar[1], p.hidden + h * ATT_D, row0 + k0);
+        if (pass == 1) tma_load_2d(sV, &tma_qkv, &bar[1], 2 * p.hidden + h * ATT_D, row0 + k0);
+        if (pass == 0 && j == 0) mbar_wait(&bar[0], 0);
+        mbar_wait(&bar[1], ph_k);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; ++k)
+          tc_mma_f16(tmem, make_smem_desc(qa + k * 32, 16, 1024), make_smem_desc(ka + k * 32, 16, 1024), idesc_s,
+                     k > 0);
+        tc_commit(&bar[2]);
+      }
+      ph_k ^= 1;
+      __syncthreads();  // sBias visible
+      mbar_wait(&bar[2], ph_s);
+      ph_s ^= 1;
+      tc_fence_after();
+      __syncwarp();
+      if (pass == 0) {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(trow + c * 32, v);
+          tc_wait_ld();
+#pragma unroll
+          for (int t = 0; t < 32; ++t) mx = fmaxf(mx, fmaf(__uint_as_float(v[t]), sl2, sBias[c * 32 + t]));
+        }
+      } else {
+        const float m_use = (mx == -INFINITY) ? 0.f : mx;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(trow + c * 32, v);
+          tc_wait_ld();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float e[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              e[t] = exp2f(fmaf(__uint_as_float(v[g * 8 + t]), sl2, sBias[c * 32 + g * 8 + t]) - m_use);
+              sum += e[t];
+            }
+            *reinterpret_cast<uint4*>(sP + swz_off(r, c * 32 + g * 8)) = pack8(e);
+          }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < ATT_T / 16; ++k)
+            tc_mma_f16(tmem_o, make_smem_desc(pa + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 16, 1024),
+                       make_smem_desc(va + k * 2048, 8192, 1024), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+          tc_commit(&bar[3]);
+        }
+        __syncwarp();
+        mbar_wait(&bar[3], ph_o);  // P, K, V consumed: buffers reusable; O advanced
+        ph_o ^= 1;
+        tc_fence_after();
+      }
+      tc_fence_before();
+      __syncthreads();  // everyone done with S / sBias of this tile before the next one is produced
+      tc_fence_after();
+    }
+  }
+  const int qrow = q0 + r;
+  if (qrow < L && p.lse) {
+    const float m_use = (mx == -INFINITY) ? 0.f : mx;
+    p.lse[(static_cast<long long>(seq) * p.heads + h) * L + qrow] = (m_use + log2f(sum)) / LOG2E;
+  }
+  const float inv = sum > 0.f ? 1.f / sum : 0.f;
+  __half* orow = p.out + static_cast<long long>(row0 + qrow) * p.hidden + h * ATT_D;
+  const uint32_t trow_o = tmem_o + (static_cast<uint32_t>(warp * 32) << 16);
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c) {
+    uint32_t v[32];
+    tmem_ld_32x32(trow_o + c * 32, v);
+    tc_wait_ld();
+    if (qrow < L) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float e[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) e[t] = __uint_as_float(v[g * 8 + t]) * inv;
+        *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = pack8(e);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+// smem: K V (fixed) | Q dO (per query tile) | P then dS (32 KB)
+constexpr int ATT_BWDM_SMEM = 6 * ATT_TILE_BYTES + 1024 + 128 + 1024;
+
+__global__ void __launch_bounds__(256, 1)
+fmha_bwd_multi_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do,
+                      const AttParams p, float* __restrict__ dq_ws, const int kv_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + ATT_TILE_BYTES;
+  uint8_t* sQ = smem + 2 * ATT_TILE_BYTES;
+  uint8_t* sdO = smem + 3 * ATT_TILE_BYTES;
+  uint8_t* sP = smem + 4 * ATT_TILE_BYTES;
+  float* sBias = reinterpret_cast<float*>(smem + 6 * ATT_TILE_BYTES);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 6 * ATT_TILE_BYTES + 1024);  // 0: KV, 1: Q dO, 2: S dP, 3: dV, 4: dK dQ
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 5);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int jt = blockIdx.x % kv_tiles;
+  const int sh = blockIdx.x / kv_tiles;
+  const int seq = sh / p.heads, h = sh % p.heads;
+  const int L = p.seq_len;
+  const int row0 = seq * L;
+  const int k0 = jt * ATT_T;
+  const int q_tiles = kv_tiles;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tma_qkv);
+    tma_prefetch_desc(&tma_do);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) mbar_init(&bar[i], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  if (tid < ATT_T) {
+    const int c = k0 + tid;
+    float b = -INFINITY;
+    if (c < L) b = p.key_bias ? p.key_bias[static_cast<long long>(seq) * L + c] * LOG2E : 0.f;
+    sBias[tid] = b;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  // TMEM columns: S [0,128) dP [128,256) dV [256,320) dK [320,384) dQ [384,448)
+  const uint32_t t_s = tmem, t_dp = tmem + 128, t_dv = tmem + 256, t_dk = tmem + 320, t_dq = tmem + 384;
+  const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK), va = smem_u32(sV), da = smem_u32(sdO), pa = smem_u32(sP);
+  constexpr uint32_t idesc_s = make_idesc_f16(ATT_T, ATT_T, 0, 0);
+  constexpr uint32_t idesc_tt = make_idesc_f16(ATT_T, ATT_D, 1, 1);
+  constexpr uint32_t idesc_nt = make_idesc_f16(ATT_T, ATT_D, 0, 1);
+  const int rl = (warp & 3) * 32 + lane;  // TMEM lane
+  const int half = warp >> 2;
+  const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  const float sl2 = p.scale * LOG2E;
+
+  if (tid == 0) {
+    mbar_expect_tx(&bar[0], 2 * ATT_TILE_BYTES);
+    tma_load_2d(sK, &tma_qkv, &bar[0], p.hidden + h * ATT_D, row0 + k0);
+    tma_load_2d(sV, &tma_qkv, &bar[0], 2 * p.hidden + h * ATT_D, row0 + k0);
+  }
+  uint32_t ph = 0;
+#pragma unroll 1
+  for (int it = 0; it < q_tiles; ++it) {
+    const int q0 = it * ATT_T;
+    if (tid == 0) {
+      mbar_expect_tx(&bar[1], 2 * ATT_TILE_BYTES);
+      tma_load_2d(sQ, &tma_qkv, &bar[1], h * ATT_D, row0 + q0);
+      tma_load_2d(sdO, &tma_do, &bar[1], h * ATT_D, row0 + q0);
+      if (it == 0) mbar_wait(&bar[0], 0);
+      mbar_wait(&bar[1], ph);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < ATT_D / 16; ++k)
+        tc_mma_f16(t_s, make_smem_desc(qa + k * 32, 16, 1024), make_smem_desc(ka + k * 32, 16, 1024), idesc_s, k > 0);
+#pragma unroll
+      for (int k = 0; k < ATT_D / 16; ++k)
+        tc_mma_f16(t_dp, make_smem_desc(da + k * 32, 16, 1024), make_smem_desc(va + k * 32, 16, 1024), idesc_s, k > 0);
+      tc_commit(&bar[2]);
+    }
+    const int qrow = q0 + rl;
+    float delta = 0.f, lse2 = 0.f;
+    if (qrow < L) {
+      const long long off = static_cast<long long>(row0 + qrow) * p.hidden + h * ATT_D;
+      const uint4* po = reinterpret_cast<const uint4*>(p.o + off);
+      const uint4* pd = reinterpret_cast<const uint4*>(p.d_o + off);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) delta += dot8(__ldg(po + i), __ldg(pd + i));
+      lse2 = p.lse[(static_cast<long long>(seq) * p.heads + h) * L + qrow] * LOG2E;
+    }
+    __syncwarp();
+    mbar_wait(&bar[2], ph);
+    tc_fence_after();
+    __syncwarp();
+
+    uint4 ds_keep[8];
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      const int c0 = half * 64 + cc * 32;
+      uint32_t s[32], d[32];
+      tmem_ld_32x32(t_s + lane_off + c0, s);
+      tmem_ld_32x32(t_dp + lane_off + c0, d);
+      tc_wait_ld();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float pv[8], ds[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const int c = c0 + g * 8 + t;
+          const bool ok = (qrow < L) && (k0 + c < L);
+          const float pe = ok ? exp2f(fmaf(__uint_as_float(s[g * 8 + t]), sl2, sBias[c]) - lse2) : 0.f;
+          pv[t] = pe;
+          ds[t] = ok ? pe * (__uint_as_float(d[g * 8 + t]) - delta) * p.scale : 0.f;
+        }
+        *reinterpret_cast<uint4*>(sP + swz_off(rl, c0 + g * 8)) = pack8(pv);
+        ds_keep[cc * 4 + g] = pack8(ds);
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < ATT_T / 16; ++k)  // dV_j += P^T dO_i
+        tc_mma_f16(t_dv, make_smem_desc(pa + k * 2048, ATT_TILE_BYTES, 1024), make_smem_desc(da + k * 2048, 8192, 1024),
+                   idesc_tt, (it > 0 || k > 0) ? 1u : 0u);
+      tc_commit(&bar[3]);
+    }
+    __syncwarp();
+    mbar_wait(&bar[3], ph);
+    tc_fence_after();
+    __syncwarp();
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        *reinterpret_cast<uint4*>(sP + swz_off(rl, half * 64 + cc * 32 + g * 8)) = ds_keep[cc * 4 + g];
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < ATT_T / 16; ++k)  // dK_j += dS^T Q_i
+        tc_mma_f16(t_dk, make_smem_desc(pa + k * 2048, ATT_TILE_BYTES, 1024), make_smem_desc(qa + k * 2048, 8192, 1024),
+                   idesc_tt, (it > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+      for (int k = 0; k < ATT_T / 16; ++k)  // dQ_i (this key tile's share) = dS K_j
+        tc_mma_f16(t_dq, make_smem_desc(pa + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 16, 1024),
+                   make_smem_desc(ka + k * 2048, 8192, 1024), idesc_nt, k > 0);
+      tc_commit(&bar[4]);
+    }
+    __syncwarp();
+    mbar_wait(&bar[4], ph);
+    tc_fence_after();
+    __syncwarp();
+    {  // dQ share -> fp32 workspace
+      uint32_t v[32];
+      tmem_ld_32x32(t_dq + lane_off + half * 32, v);
+      tc_wait_ld();
+      if (qrow < L) {
+        float* dst = dq_ws + static_cast<long long>(row0 + qrow) * p.hidden + h * ATT_D + half * 32;
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          atomicAdd(reinterpret_cast<float4*>(dst + g * 4),
+                    make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
+                                __uint_as_float(v[4 * g + 3])));
+      }
+    }
+    ph ^= 1;
+    tc_fence_before();
+    __syncthreads();  // Q / dO / dS buffers and the S / dP / dQ columns are free for the next query tile
+    tc_fence_after();
+  }
+  // dV_j, dK_j rows = key rows k0 + rl
+  const int krow = k0 + rl;
+  __half* grow = p.dqkv + static_cast<long long>(row0 + krow) * (3 * p.hidden) + h * ATT_D + half * 32;
+#pragma unroll 1
+  for (int t = 0; t < 2; ++t) {  // 0 = dV, 1 = dK
+    uint32_t v[32];
+    tmem_ld_32x32((t == 0 ? t_dv : t_dk) + lane_off + half * 32, v);
+    tc_wait_ld();
+    if (krow < L) {
+      __half* dst = grow + (2 - t) * p.hidden;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float e[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) e[u] = __uint_as_float(v[g * 8 + u]);
+        *reinterpret_cast<uint4*>(dst + g * 8) = pack8(e);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// dqkv[:, 0:hidden] = fp16(dq_ws)
+__global__ void dq_convert_kernel(const float* __restrict__ ws, __half* __restrict__ dqkv, long long rows, int hidden) {
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  if (i >= rows * hidden) return;
+  const long long r = i / hidden;
+  const int c = static_cast<int>(i - r * hidden);
+  const float4 a = *reinterpret_cast<const float4*>(ws + i);
+  const float4 b = *reinterpret_cast<const float4*>(ws + i + 4);
+  const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  *reinterpret_cast<uint4*>(dqkv + r * 3 * hidden + c) = pack8(v);
+}
+
 static int att_check(const cdr_attn_args* a) {
   CDR_REQUIRE(a != nullptr, "cdr_attn: null args");
   CDR_REQUIRE(a->qkv != nullptr, "cdr_attn: null qkv");
   CDR_REQUIRE(a->n_seq > 0 && a->seq_len > 0 && a->heads > 0, "cdr_attn: empty problem");
-  CDR_REQUIRE(a->seq_len <= ATT_T, "cdr_attn: seq_len %d > %d not supported by this build", a->seq_len, ATT_T);
+  CDR_REQUIRE(a->seq_len <= 512, "cdr_attn: seq_len %d > 512 not supported", a->seq_len);
   CDR_REQUIRE(a->head_dim == ATT_D, "cdr_attn: head_dim must be 64 (got %d)", a->head_dim);
   return CDR_OK;
 }
@@ -413,7 +798,15 @@ int cdr_attn_fwd(const cdr_attn_args* a, void* stream) {
   static bool configured = false;
   if (!configured) {
     CDR_CUDA(cudaFuncSetAttribute(fmha_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWD_SMEM));
+    CDR_CUDA(cudaFuncSetAttribute(fmha_fwd_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWDM_SMEM));
     configured = true;
+  }
+  if (a->seq_len > ATT_T) {
+    const int q_tiles = (a->seq_len + ATT_T - 1) / ATT_T;
+    fmha_fwd_multi_kernel<<<a->n_seq * a->heads * q_tiles, 128, ATT_FWDM_SMEM, static_cast<cudaStream_t>(stream)>>>(
+        tq, p, q_tiles);
+    CDR_LAUNCH_CHECK();
+    return CDR_OK;
   }
   fmha_fwd_kernel<<<a->n_seq * a->heads, 128, ATT_FWD_SMEM, static_cast<cudaStream_t>(stream)>>>(tq, p);
   CDR_LAUNCH_CHECK();
@@ -440,7 +833,21 @@ int cdr_attn_bwd(const cdr_attn_args* a, void* stream) {
   static bool configured = false;
   if (!configured) {
     CDR_CUDA(cudaFuncSetAttribute(fmha_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWD_SMEM));
+    CDR_CUDA(cudaFuncSetAttribute(fmha_bwd_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWDM_SMEM));
     configured = true;
+  }
+  if (a->seq_len > ATT_T) {
+    CDR_REQUIRE(a->dq_workspace != nullptr, "cdr_attn_bwd: seq_len > %d needs dq_workspace (fp32 [T, hidden])", ATT_T);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int kv_tiles = (a->seq_len + ATT_T - 1) / ATT_T;
+    CDR_CUDA(cudaMemsetAsync(a->dq_workspace, 0, sizeof(float) * static_cast<size_t>(T) * hidden, st));
+    fmha_bwd_multi_kernel<<<a->n_seq * a->heads * kv_tiles, 256, ATT_BWDM_SMEM, st>>>(tq, td, p, a->dq_workspace,
+                                                                                    kv_tiles);
+    CDR_LAUNCH_CHECK();
+    const long long n8 = (static_cast<long long>(T) * hidden + 7) / 8;
+    dq_convert_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, st>>>(a->dq_workspace, p.dqkv, T, hidden);
+    CDR_LAUNCH_CHECK();
+    return CDR_OK;
   }
   fmha_bwd_kernel<<<a->n_seq * a->heads, 256, ATT_BWD_SMEM, static_cast<cudaStream_t>(stream)>>>(tq, td, p);
   CDR_LAUNCH_CHECK();

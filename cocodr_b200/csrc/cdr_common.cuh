@@ -226,33 +226,44 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn, in
          (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
-// Exact-erf GELU pieces with ONE exp and ONE reciprocal per element (the tensor-core epilogues are
-// issue-bound on this math).  erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, i.e. exact at fp16
-// output precision); erf(|x|/sqrt2) and the Gaussian pdf share exp(-x^2/2), and the lower tail uses
-// 0.5*poly*e directly (no 1 - erf cancellation).
-//   cdf = Phi(x),  pdf = phi(x);   gelu(x) = x*cdf,   gelu'(x) = cdf + x*pdf
-__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& pdf) {
-  const float ax = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
-  const float e = __expf(-ax * ax);
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(t, poly, 1.421413741f);
-  poly = fmaf(t, poly, -0.284496736f);
-  poly = fmaf(t, poly, 0.254829592f);
-  const float tail = 0.5f * poly * t * e;  // Phi(-|x|)
-  cdf = x > 0.f ? 1.0f - tail : tail;
-  pdf = 0.3989422804014327f * e;
+// Exact-erf GELU with one ex2 and one rcp per element, flush-to-zero MUFU forms (the tensor-core epilogues
+// are instruction-issue bound on this math: every FSETP / FMUL of the denormal-safe library sequences
+// counts).  erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, i.e. exact at fp16 output precision);
+// erf(|x|/sqrt2) and the Gaussian pdf share exp(-x^2/2); the lower tail Phi(-|x|) = poly(t)*exp(-x^2/2)
+// is used directly (no 1 - erf cancellation).
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// tail = Phi(-|x|), e = exp(-x^2/2)
+__device__ __forceinline__ void gelu_tail(float x, float& tail, float& e) {
+  const float ax = fabsf(x);
+  const float a2 = ax * 0.84932180028801904f;             // |x| * sqrt(log2(e) / 2)
+  e = fast_ex2(-a2 * a2);                                 // exp(-x^2 / 2)
+  const float t = fast_rcp(fmaf(ax, 0.23164189f, 1.0f));  // 1 / (1 + 0.3275911 |x| / sqrt2)
+  float poly = fmaf(t, 0.5307027145f, -0.7265760135f);    // 0.5 * A-S coefficients
+  poly = fmaf(t, poly, 0.7107068705f);
+  poly = fmaf(t, poly, -0.142248368f);
+  poly = fmaf(t, poly, 0.127414796f);
+  tail = poly * t * e;
 }
 __device__ __forceinline__ float gelu_erf(float x) {
-  float cdf, pdf;
-  gelu_parts(x, cdf, pdf);
-  return x * cdf;
+  float tail, e;
+  gelu_tail(x, tail, e);
+  return fmaf(-fabsf(x), tail, fmaxf(x, 0.f));  // x > 0: x - x*tail ; x < 0: x*tail
 }
 // d/dx gelu_erf(x) = Phi(x) + x * phi(x)
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  float cdf, pdf;
-  gelu_parts(x, cdf, pdf);
-  return fmaf(x, pdf, cdf);
+  float tail, e;
+  gelu_tail(x, tail, e);
+  const float cdf = x > 0.f ? 1.0f - tail : tail;
+  return fmaf(x * 0.3989422804014327f, e, cdf);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

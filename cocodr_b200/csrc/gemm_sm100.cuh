@@ -151,14 +151,6 @@ __device__ __forceinline__ void gemm_epilogue_apply(const GemmParams& p, float (
 #pragma unroll
         for (int t = 0; t < 4; ++t) zh[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
         *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out2) + static_cast<long long>(m) * p.ldo + n) = zq;
-        // GELU is applied to the fp16-rounded pre-activation so that backward (which only has Z)
-        // differentiates exactly the function forward evaluated.
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const float2 f = __half22float2(zh[t]);
-          v[2 * t] = f.x;
-          v[2 * t + 1] = f.y;
-        }
       }
 #pragma unroll
       for (int t = 0; t < 8; ++t) v[t] = gelu_erf(v[t]);

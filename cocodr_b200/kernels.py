@@ -17,9 +17,25 @@ launches = 0          # number of CUDA kernels launched by this library so far (
 gemm_events = None    # when a list: gemm() appends (flops, start_event, end_event)
 
 
+op_events = None      # when a list: every cdr_* call appends (name, start_event, end_event)
+
+
 def _count(n):
     global launches
     launches += n
+
+
+def _run(name, call):
+    """Issue one C-ABI call (optionally bracketed by CUDA events on the launching stream) and raise on error."""
+    if op_events is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = call()
+        e1.record()
+        op_events.append((name, e0, e1))
+    else:
+        rc = call()
+    check(rc, name)
 
 
 def _need_cuda(*ts):
@@ -54,7 +70,7 @@ def gemm(a, b, out, *, M, N, K, a_major=0, b_major=0, epilogue=EPI_STORE_F16, bi
         e1.record()
         gemm_events.append((2.0 * M * N * K, e0, e1))
     else:
-        check(_lib.load().cdr_gemm(C.byref(g), stream_ptr()), "cdr_gemm")
+        _run("cdr_gemm[epi%d]" % epilogue, lambda: _lib.load().cdr_gemm(C.byref(g), stream_ptr()))
     _count(1)
     return out
 
@@ -76,27 +92,27 @@ def _lib_():
 def embed_ln_fwd(ids, word, pos, type0, gamma, beta, out, mean, rstd, *, n_seq, seq_len, hidden, vocab, eps):
     _need_cuda(ids, word, out)
     assert ids.dtype == torch.int64 and word.dtype == torch.float32 and out.dtype == torch.float16
-    check(_lib_().cdr_embed_ln_fwd(_p(ids), _p(word), _p(pos), _p(type0), _p(gamma), _p(beta), _p(out), _p(mean),
+    _run("cdr_embed_ln_fwd", lambda: _lib_().cdr_embed_ln_fwd(_p(ids), _p(word), _p(pos), _p(type0), _p(gamma), _p(beta), _p(out), _p(mean),
                                    _p(rstd), _i32(n_seq), _i32(seq_len), _i32(hidden), _i32(vocab), _f32(eps),
-                                   stream_ptr()), "cdr_embed_ln_fwd")
+                                   stream_ptr()))
     _count(1)
 
 
 def embed_ln_bwd(dy, ids, word, pos, type0, gamma, mean, rstd, dword, dpos, dtype0, dgamma, dbeta, *, n_seq, seq_len,
                  hidden, vocab, pad_id, in_scale, out_scale):
     _need_cuda(dy, ids, dword)
-    check(_lib_().cdr_embed_ln_bwd(_p(dy), _p(ids), _p(word), _p(pos), _p(type0), _p(gamma), _p(mean), _p(rstd),
+    _run("cdr_embed_ln_bwd", lambda: _lib_().cdr_embed_ln_bwd(_p(dy), _p(ids), _p(word), _p(pos), _p(type0), _p(gamma), _p(mean), _p(rstd),
                                    _p(dword), _p(dpos), _p(dtype0), _p(dgamma), _p(dbeta), _i32(n_seq), _i32(seq_len),
                                    _i32(hidden), _i32(vocab), _i32(pad_id), _f32(in_scale), _f32(out_scale),
-                                   stream_ptr()), "cdr_embed_ln_bwd")
+                                   stream_ptr()))
     _count(1)
 
 
 def ln_fwd(x, gamma, beta, y, mean, rstd, cls_out, *, n_seq, seq_len, hidden, eps):
     _need_cuda(x, y)
     assert x.dtype == torch.float16 and y.dtype == torch.float16
-    check(_lib_().cdr_ln_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), _p(cls_out), _i32(n_seq),
-                             _i32(seq_len), _i32(hidden), _f32(eps), stream_ptr()), "cdr_ln_fwd")
+    _run("cdr_ln_fwd", lambda: _lib_().cdr_ln_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), _p(cls_out), _i32(n_seq),
+                             _i32(seq_len), _i32(hidden), _f32(eps), stream_ptr()))
     _count(1)
 
 
@@ -105,17 +121,17 @@ def ln_bwd(dy, dy_cls, x, gamma, mean, rstd, dx, dgamma, dbeta, dbias, *, n_seq,
     _need_cuda(x, dx)
     if row_ws is not None:
         assert row_ws.dtype == torch.float32 and row_ws.numel() >= 2 * n_seq * seq_len
-    check(_lib_().cdr_ln_bwd(_p(dy), _p(dy_cls), _p(x), _p(gamma), _p(mean), _p(rstd), _p(dx), _p(dgamma), _p(dbeta),
+    _run("cdr_ln_bwd", lambda: _lib_().cdr_ln_bwd(_p(dy), _p(dy_cls), _p(x), _p(gamma), _p(mean), _p(rstd), _p(dx), _p(dgamma), _p(dbeta),
                              _p(dbias), _p(row_ws), _i32(n_seq), _i32(seq_len), _i32(hidden), _f32(in_scale),
-                             _f32(out_scale), stream_ptr()), "cdr_ln_bwd")
+                             _f32(out_scale), stream_ptr()))
     _count(2 if (row_ws is not None and dy is not None and dy_cls is None) else 1)
 
 
 def colsum(x, out, *, rows, cols, ld=None, scale=1.0):
     _need_cuda(x, out)
     assert x.dtype == torch.float16 and out.dtype == torch.float32
-    check(_lib_().cdr_colsum_f16(_p(x), _p(out), _i64(rows), _i64(cols), _i64(ld if ld is not None else x.stride(0)),
-                                 _f32(scale), stream_ptr()), "cdr_colsum_f16")
+    _run("cdr_colsum_f16", lambda: _lib_().cdr_colsum_f16(_p(x), _p(out), _i64(rows), _i64(cols), _i64(ld if ld is not None else x.stride(0)),
+                                 _f32(scale), stream_ptr()))
     _count(1)
 
 
@@ -123,7 +139,7 @@ def cast_f32_f16(src, dst):
     _need_cuda(src, dst)
     assert src.dtype == torch.float32 and dst.dtype == torch.float16 and src.numel() == dst.numel()
     assert src.is_contiguous() and dst.is_contiguous()
-    check(_lib_().cdr_cast_f32_f16(_p(src), _p(dst), _i64(src.numel()), stream_ptr()), "cdr_cast_f32_f16")
+    _run("cdr_cast_f32_f16", lambda: _lib_().cdr_cast_f32_f16(_p(src), _p(dst), _i64(src.numel()), stream_ptr()))
     _count(1)
 
 
@@ -140,12 +156,13 @@ def cast_table(entries, device):
 
 
 def cast_multi(table, max_n):
-    check(_lib_().cdr_cast_multi(_p(table), _i32(table.shape[0]), _i64(max_n), stream_ptr()), "cdr_cast_multi")
+    _run("cdr_cast_multi", lambda: _lib_().cdr_cast_multi(_p(table), _i32(table.shape[0]), _i64(max_n), stream_ptr()))
     _count(1)
 
 
-def _attn_args(qkv, key_bias, out, lse, n_seq, seq_len, heads, scale, d_out=None, dqkv=None):
+def _attn_args(qkv, key_bias, out, lse, n_seq, seq_len, heads, scale, d_out=None, dqkv=None, dq_ws=None):
     a = _lib.AttnArgs()
+    a.dq_workspace = dq_ws.data_ptr() if dq_ws is not None else 0
     a.qkv, a.out, a.lse = qkv.data_ptr(), out.data_ptr(), lse.data_ptr()
     a.key_bias = key_bias.data_ptr() if key_bias is not None else 0
     a.d_out = d_out.data_ptr() if d_out is not None else 0
@@ -159,30 +176,33 @@ def attn_fwd(qkv, key_bias, out, lse, *, n_seq, seq_len, heads, scale=0.125):
     assert qkv.dtype == torch.float16 and out.dtype == torch.float16 and lse.dtype == torch.float32
     assert qkv.is_contiguous() and out.is_contiguous()
     a = _attn_args(qkv, key_bias, out, lse, n_seq, seq_len, heads, scale)
-    check(_lib_().cdr_attn_fwd(C.byref(a), stream_ptr()), "cdr_attn_fwd")
+    _run("cdr_attn_fwd", lambda: _lib_().cdr_attn_fwd(C.byref(a), stream_ptr()))
     _count(1)
 
 
 def attn_bwd(qkv, key_bias, out, lse, d_out, dqkv, *, n_seq, seq_len, heads, scale=0.125):
     _need_cuda(qkv, out, lse, d_out, dqkv)
     assert d_out.dtype == torch.float16 and dqkv.dtype == torch.float16 and d_out.is_contiguous()
-    a = _attn_args(qkv, key_bias, out, lse, n_seq, seq_len, heads, scale, d_out, dqkv)
-    check(_lib_().cdr_attn_bwd(C.byref(a), stream_ptr()), "cdr_attn_bwd")
-    _count(1)
+    dq_ws = None
+    if seq_len > 128:  # tiled backward: key tiles add their dQ shares in an fp32 scratch
+        dq_ws = torch.empty(n_seq * seq_len, heads * 64, dtype=torch.float32, device=qkv.device)
+    a = _attn_args(qkv, key_bias, out, lse, n_seq, seq_len, heads, scale, d_out, dqkv, dq_ws)
+    _run("cdr_attn_bwd", lambda: _lib_().cdr_attn_bwd(C.byref(a), stream_ptr()))
+    _count(1 if seq_len <= 128 else 2)
 
 
 def pair_nll_fwd(q, a, b, loss, accs, logits):
     _need_cuda(q, a, b)
     n, dim = q.shape
-    check(_lib_().cdr_pair_nll_fwd(_p(q), _p(a), _p(b), _i32(n), _i32(dim), _p(loss), _p(accs), _p(logits),
-                                   stream_ptr()), "cdr_pair_nll_fwd")
+    _run("cdr_pair_nll_fwd", lambda: _lib_().cdr_pair_nll_fwd(_p(q), _p(a), _p(b), _i32(n), _i32(dim), _p(loss), _p(accs), _p(logits),
+                                   stream_ptr()))
     _count(1)
 
 
 def pair_nll_bwd(q, a, b, logits, dloss, dq, da, db):
     n, dim = q.shape
-    check(_lib_().cdr_pair_nll_bwd(_p(q), _p(a), _p(b), _p(logits), _p(dloss), _i32(n), _i32(dim), _p(dq), _p(da),
-                                   _p(db), stream_ptr()), "cdr_pair_nll_bwd")
+    _run("cdr_pair_nll_bwd", lambda: _lib_().cdr_pair_nll_bwd(_p(q), _p(a), _p(b), _p(logits), _p(dloss), _i32(n), _i32(dim), _p(dq), _p(da),
+                                   _p(db), stream_ptr()))
     _count(1)
 
 
@@ -202,7 +222,7 @@ def simmat_ce_fwd(q, k, scores, loss, lse, *, mode, row_offset=0, loss_scale=1.0
     assert q.dtype == torch.float32 and k.dtype == torch.float32 and q.is_contiguous() and k.is_contiguous()
     a = _simmat_args(q, k, scores, lse, mode, row_offset, loss_scale)
     a.loss = loss.data_ptr()
-    check(_lib_().cdr_simmat_ce_fwd(C.byref(a), stream_ptr()), "cdr_simmat_ce_fwd")
+    _run("cdr_simmat_ce_fwd", lambda: _lib_().cdr_simmat_ce_fwd(C.byref(a), stream_ptr()))
     _count(2)
 
 
@@ -212,21 +232,20 @@ def simmat_ce_bwd(q, k, scores, lse, dloss, gmat, dq, dk, *, mode, row_offset=0,
     a.dloss, a.gmat = dloss.data_ptr(), gmat.data_ptr()
     a.dq = dq.data_ptr() if dq is not None else 0
     a.dk = dk.data_ptr() if dk is not None else 0
-    check(_lib_().cdr_simmat_ce_bwd(C.byref(a), stream_ptr()), "cdr_simmat_ce_bwd")
+    _run("cdr_simmat_ce_bwd", lambda: _lib_().cdr_simmat_ce_bwd(C.byref(a), stream_ptr()))
     _count(3)
 
 
 def group_reduce_fwd(loss, g, sums, counts, *, n_groups):
     _need_cuda(loss, g, sums, counts)
     assert g.dtype == torch.int64 and loss.dtype == torch.float32
-    check(_lib_().cdr_group_reduce_fwd(_p(loss), _p(g), _i32(loss.numel()), _i32(n_groups), _p(sums), _p(counts),
-                                       stream_ptr()), "cdr_group_reduce_fwd")
+    _run("cdr_group_reduce_fwd", lambda: _lib_().cdr_group_reduce_fwd(_p(loss), _p(g), _i32(loss.numel()), _i32(n_groups), _p(sums), _p(counts),
+                                       stream_ptr()))
     _count(1)
 
 
 def group_reduce_bwd(dsums, g, dloss, *, n_groups):
-    check(_lib_().cdr_group_reduce_bwd(_p(dsums), _p(g), _i32(g.numel()), _i32(n_groups), _p(dloss), stream_ptr()),
-          "cdr_group_reduce_bwd")
+    _run("cdr_group_reduce_bwd", lambda: _lib_().cdr_group_reduce_bwd(_p(dsums), _p(g), _i32(g.numel()), _i32(n_groups), _p(dloss), stream_ptr()))
     _count(1)
 
 
@@ -234,8 +253,7 @@ def gram_f32(x, gram):
     """gram[G,G] += x x^T for a row-major fp32 [G, P] matrix (row stride x.stride(0))."""
     _need_cuda(x, gram)
     assert x.dtype == torch.float32 and gram.dtype == torch.float32 and x.stride(1) == 1
-    check(_lib_().cdr_gram_f32(_p(x), _i32(x.shape[0]), _i64(x.shape[1]), _i64(x.stride(0)), _p(gram), stream_ptr()),
-          "cdr_gram_f32")
+    _run("cdr_gram_f32", lambda: _lib_().cdr_gram_f32(_p(x), _i32(x.shape[0]), _i64(x.shape[1]), _i64(x.stride(0)), _p(gram), stream_ptr()))
     _count(1)
 
 
@@ -256,7 +274,7 @@ def scan_topk(docs, queries, out_scores, out_ids, workspace, status, *, k, doc_b
     a.workspace, a.workspace_bytes, a.status = workspace.data_ptr(), workspace.numel() * workspace.element_size(), status.data_ptr()
     a.n_docs, a.ld_docs, a.doc_base = docs.shape[0], docs.stride(0), doc_base
     a.n_q, a.dim, a.k = queries.shape[0], queries.shape[1], k
-    check(_lib_().cdr_scan_topk(C.byref(a), stream_ptr()), "cdr_scan_topk")
+    _run("cdr_scan_topk", lambda: _lib_().cdr_scan_topk(C.byref(a), stream_ptr()))
     _count(3 if docs.shape[0] <= scan_exhaustive_docs(k) else 5)
 
 
@@ -264,6 +282,6 @@ def topk_merge(scores, ids, out_scores, out_ids, *, k):
     _need_cuda(scores, ids, out_scores, out_ids)
     assert scores.is_contiguous() and ids.is_contiguous() and ids.dtype == torch.int64
     n_q, n_in = scores.shape
-    check(_lib_().cdr_topk_merge(_p(scores), _p(ids), _i32(n_q), _i32(n_in), _i32(k), _p(out_scores), _p(out_ids),
-                                 stream_ptr()), "cdr_topk_merge")
+    _run("cdr_topk_merge", lambda: _lib_().cdr_topk_merge(_p(scores), _p(ids), _i32(n_q), _i32(n_in), _i32(k), _p(out_scores), _p(out_ids),
+                                 stream_ptr()))
     _count(1)

@@ -110,7 +110,7 @@ int cdr_cast_multi(const cdr_cast_item* items_device, int32_t count, int64_t max
 
 /* ------------------------------------------------------------------------------------------------
  * Fused multi-head attention (K3): softmax(Q K^T * scale + key_bias) V on tcgen05, head_dim 64,
- * seq_len <= 128, straight from / to the packed QKV projection.  Replaces HF
+ * seq_len <= 512 (one 128 x 128 tile up to 128, tiled above), straight from / to the packed QKV projection.  Replaces HF
  * eager_attention_forward / SDPA inside BertSelfAttention (reached through ANCE/model/models.py:226,
  * COCO/modeling.py:199-204); dropout p = 0.
  * ---------------------------------------------------------------------------------------------- */
@@ -121,6 +121,7 @@ typedef struct cdr_attn_args {
   float* lse;            /* fp32 [n_seq, heads, seq_len]         fwd: written, bwd: read */
   const void* d_out;     /* bwd: fp16 [n_seq*seq_len, heads*64] */
   void* dqkv;            /* bwd: fp16 [n_seq*seq_len, 3*heads*64] written */
+  float* dq_workspace;   /* bwd, seq_len > 128 only: fp32 [n_seq*seq_len, heads*64] scratch */
   int32_t n_seq, seq_len, heads, head_dim;
   float scale;
 } cdr_attn_args;

@@ -55,7 +55,7 @@ def test_bad_arguments_fail_loudly_without_a_gpu(lib):
     rc = lib.cdr_gemm(None, None)
     assert rc == -1 and b"null" in lib.cdr_last_error()
     a = _lib.AttnArgs()
-    a.qkv, a.n_seq, a.seq_len, a.heads, a.head_dim = 16, 1, 300, 1, 64
+    a.qkv, a.n_seq, a.seq_len, a.heads, a.head_dim = 16, 1, 600, 1, 64
     assert lib.cdr_attn_fwd(C.byref(a), None) == -1 and b"seq_len" in lib.cdr_last_error()
     with pytest.raises(RuntimeError):
         _lib.check(rc, "cdr_gemm")

@@ -19,7 +19,9 @@ def _ref(qkv, bias, n_seq, L, heads):
 
 
 @pytest.mark.parametrize("n_seq,L,heads,masked", [(2, 128, 2, False), (3, 64, 2, True), (5, 32, 2, True),
-                                                  (4, 128, 12, True), (2, 100, 3, True), (64, 128, 12, False)])
+                                                  (4, 128, 12, True), (2, 100, 3, True), (64, 128, 12, False),
+                                                  (3, 256, 2, True), (2, 200, 3, True), (2, 384, 2, False),
+                                                  (2, 512, 1, True), (8, 256, 16, True)])
 def test_attention_fwd_bwd(n_seq, L, heads, masked):
     from cocodr_b200 import kernels as k
     g = torch.Generator().manual_seed(n_seq * 1000 + L)
@@ -57,8 +59,8 @@ def test_attention_fwd_bwd(n_seq, L, heads, masked):
 
 def test_attention_rejects_long_sequences():
     from cocodr_b200 import kernels as k
-    qkv = torch.zeros(256, 192, dtype=torch.float16, device="cuda")
-    out = torch.zeros(256, 64, dtype=torch.float16, device="cuda")
-    lse = torch.zeros(1, 1, 256, device="cuda")
+    qkv = torch.zeros(640, 192, dtype=torch.float16, device="cuda")
+    out = torch.zeros(640, 64, dtype=torch.float16, device="cuda")
+    lse = torch.zeros(1, 1, 640, device="cuda")
     with pytest.raises(RuntimeError):
-        k.attn_fwd(qkv, None, out, lse, n_seq=1, seq_len=256, heads=1)
+        k.attn_fwd(qkv, None, out, lse, n_seq=1, seq_len=640, heads=1)
