@@ -115,6 +115,73 @@ simmat_ce_grad_kernel(const float* __restrict__ S, const float* __restrict__ lse
   for (int j = threadIdx.x; j < n_keys; j += blockDim.x) out[j] = g * (expf(row[j] - l) - (j == t ? 1.f : 0.f));
 }
 
+// ------------------------------------------------------------------------------ vocabulary CE (K14)
+// MLM head loss (HF BertForMaskedLM: CE(logits.view(-1, V), labels.view(-1)), COCO/modeling.py:87-93) on
+// the gathered masked rows only: logits[M, ld] fp32 straight from the decoder GEMM, bias[n_cols] fp32
+// added here (padding columns carry -inf).  One block per row.
+__global__ void __launch_bounds__(256)
+vocab_ce_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ bias,
+                    const long long* __restrict__ labels, float* __restrict__ loss, float* __restrict__ lse,
+                    int n_cols, long long ld) {
+  __shared__ float red[8];
+  const int i = blockIdx.x;
+  const float* row = logits + static_cast<long long>(i) * ld;
+  float mx = -INFINITY;
+  for (int j = threadIdx.x; j < n_cols; j += blockDim.x) mx = fmaxf(mx, row[j] + bias[j]);
+  mx = block_reduce(mx, red, true);
+  float s = 0.f;
+  for (int j = threadIdx.x; j < n_cols; j += blockDim.x) s += __expf(row[j] + bias[j] - mx);
+  s = block_reduce(s, red, false);
+  if (threadIdx.x == 0) {
+    const float l = mx + logf(s);
+    const long long t = labels[i];
+    lse[i] = l;
+    loss[i] = (t >= 0 && t < n_cols) ? l - (row[t] + bias[t]) : 0.f;
+  }
+}
+
+// dlogits[i, j] = fp16( scale * dloss[i] * (softmax_ij - [j == label_i]) )
+__global__ void __launch_bounds__(256)
+vocab_ce_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ bias,
+                    const long long* __restrict__ labels, const float* __restrict__ lse,
+                    const float* __restrict__ dloss, __half* __restrict__ dlogits, int n_cols, long long ld,
+                    float scale) {
+  const int i = blockIdx.x;
+  const float* row = logits + static_cast<long long>(i) * ld;
+  __half* out = dlogits + static_cast<long long>(i) * ld;
+  const float l = lse[i], g = dloss[i] * scale;
+  const long long t = labels[i];
+  const bool valid = t >= 0 && t < n_cols;
+  for (int j = threadIdx.x * 2; j < n_cols; j += blockDim.x * 2) {  // n_cols is even (padded to 64)
+    const float2 v = *reinterpret_cast<const float2*>(row + j);
+    const float2 b = *reinterpret_cast<const float2*>(bias + j);
+    float p0 = valid ? __expf(v.x + b.x - l) : 0.f, p1 = valid ? __expf(v.y + b.y - l) : 0.f;
+    if (j == t) p0 -= 1.f;
+    if (j + 1 == t) p1 -= 1.f;
+    *reinterpret_cast<__half2*>(out + j) = __floats2half2_rn(g * p0, g * p1);
+  }
+}
+
+// dz = dt * gelu'(z)  (the MLM transform's GELU sits between a GEMM and a LayerNorm, so its backward is
+// not a GEMM epilogue)
+__global__ void __launch_bounds__(256)
+dgelu_kernel(const __half* __restrict__ dt, const __half* __restrict__ z, __half* __restrict__ dz, long long n) {
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  if (i >= n) return;
+  const uint4 a = *reinterpret_cast<const uint4*>(dt + i);
+  const uint4 b = *reinterpret_cast<const uint4*>(z + i);
+  const __half2* ah = reinterpret_cast<const __half2*>(&a);
+  const __half2* bh = reinterpret_cast<const __half2*>(&b);
+  uint4 o;
+  __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float2 x = __half22float2(ah[t]), y = __half22float2(bh[t]);
+    oh[t] = __floats2half2_rn(x.x * gelu_erf_grad(y.x), x.y * gelu_erf_grad(y.y));
+  }
+  *reinterpret_cast<uint4*>(dz + i) = o;
+}
+
 // ------------------------------------------------------------------------------ pairwise NLL (K8)
 __global__ void __launch_bounds__(128)
 pair_nll_fwd_kernel(const float* __restrict__ q, const float* __restrict__ a, const float* __restrict__ b, int n,
@@ -299,6 +366,41 @@ int cdr_simmat_ce_bwd(const cdr_simmat_args* a, void* stream) {
   if (a->dk)  // dk[j,d] = sum_i G[i,j] q[i,d]
     if (int rc = sgemm(a->gmat, a->q, a->dk, a->n_keys, a->dim, a->n_rows, 1, a->n_keys, a->dim, 1, a->dim, 1.f, st))
       return rc;
+  return CDR_OK;
+}
+
+int cdr_vocab_ce_fwd(const float* logits, const float* bias, const int64_t* labels, float* loss, float* lse,
+                     int32_t n_rows, int32_t n_cols, int64_t ld, void* stream) {
+  CDR_REQUIRE(logits && bias && labels && loss && lse, "cdr_vocab_ce_fwd: null pointer");
+  CDR_REQUIRE(n_rows >= 0 && n_cols > 0 && ld >= n_cols, "cdr_vocab_ce_fwd: bad shape");
+  if (n_rows == 0) return CDR_OK;
+  vocab_ce_fwd_kernel<<<n_rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      logits, bias, reinterpret_cast<const long long*>(labels), loss, lse, n_cols, ld);
+  CDR_LAUNCH_CHECK();
+  return CDR_OK;
+}
+
+int cdr_vocab_ce_bwd(const float* logits, const float* bias, const int64_t* labels, const float* lse,
+                     const float* dloss, void* dlogits, int32_t n_rows, int32_t n_cols, int64_t ld, float scale,
+                     void* stream) {
+  CDR_REQUIRE(logits && bias && labels && lse && dloss && dlogits, "cdr_vocab_ce_bwd: null pointer");
+  CDR_REQUIRE(n_rows >= 0 && n_cols > 0 && n_cols % 2 == 0 && ld >= n_cols && ld % 2 == 0,
+              "cdr_vocab_ce_bwd: bad shape (n_cols and ld must be even)");
+  if (n_rows == 0) return CDR_OK;
+  vocab_ce_bwd_kernel<<<n_rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      logits, bias, reinterpret_cast<const long long*>(labels), lse, dloss, static_cast<__half*>(dlogits), n_cols, ld,
+      scale);
+  CDR_LAUNCH_CHECK();
+  return CDR_OK;
+}
+
+int cdr_dgelu_f16(const void* dt, const void* z, void* dz, int64_t n, void* stream) {
+  CDR_REQUIRE(dt && z && dz, "cdr_dgelu_f16: null pointer");
+  CDR_REQUIRE(n >= 0 && n % 8 == 0, "cdr_dgelu_f16: n must be a multiple of 8");
+  if (n == 0) return CDR_OK;
+  dgelu_kernel<<<static_cast<unsigned>((n / 8 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(dt), static_cast<const __half*>(z), static_cast<__half*>(dz), n);
+  CDR_LAUNCH_CHECK();
   return CDR_OK;
 }
 

@@ -236,6 +236,29 @@ def simmat_ce_bwd(q, k, scores, lse, dloss, gmat, dq, dk, *, mode, row_offset=0,
     _count(3)
 
 
+def vocab_ce_fwd(logits, bias, labels, loss, lse, *, n_cols):
+    _need_cuda(logits, bias, labels)
+    assert logits.dtype == torch.float32 and labels.dtype == torch.int64 and logits.stride(1) == 1
+    _run("cdr_vocab_ce_fwd", lambda: _lib_().cdr_vocab_ce_fwd(_p(logits), _p(bias), _p(labels), _p(loss), _p(lse),
+                                                             _i32(logits.shape[0]), _i32(n_cols), _i64(logits.stride(0)),
+                                                             stream_ptr()))
+    _count(1)
+
+
+def vocab_ce_bwd(logits, bias, labels, lse, dloss, dlogits, *, n_cols, scale):
+    assert dlogits.dtype == torch.float16 and dlogits.stride(0) == logits.stride(0)
+    _run("cdr_vocab_ce_bwd", lambda: _lib_().cdr_vocab_ce_bwd(_p(logits), _p(bias), _p(labels), _p(lse), _p(dloss),
+                                                             _p(dlogits), _i32(logits.shape[0]), _i32(n_cols),
+                                                             _i64(logits.stride(0)), _f32(scale), stream_ptr()))
+    _count(1)
+
+
+def dgelu(dt, z, dz):
+    assert dt.dtype == torch.float16 and z.dtype == torch.float16 and dt.is_contiguous() and z.is_contiguous()
+    _run("cdr_dgelu_f16", lambda: _lib_().cdr_dgelu_f16(_p(dt), _p(z), _p(dz), _i64(dt.numel()), stream_ptr()))
+    _count(1)
+
+
 def group_reduce_fwd(loss, g, sums, counts, *, n_groups):
     _need_cuda(loss, g, sums, counts)
     assert g.dtype == torch.int64 and loss.dtype == torch.float32

@@ -361,3 +361,110 @@ def qp_infonce(Q, P_all, row_offset=0):
 
 def group_stats(loss, g, n_groups):
     return GroupStats.apply(loss, g, n_groups)
+
+
+class MLMShadow:
+    """fp16 operands of the MLM head: transform weight [H,H]; decoder (= word embedding) matrix zero-padded to a
+    multiple of 64 rows [Vp,H]; fp32 decoder bias padded with -inf so padding columns vanish in the softmax."""
+
+    def __init__(self):
+        self.key = None
+
+    def refresh(self, wt, emb, bv):
+        key = tuple((t.data_ptr(), t._version) for t in (wt, emb, bv))
+        if key == self.key and not FORCE_SHADOW_REFRESH:
+            return self
+        dev = wt.device
+        V, H = emb.shape
+        vp = (V + 63) // 64 * 64
+        if self.key is None or self.emb.shape != (vp, H) or self.emb.device != dev:
+            self.vp = vp
+            self.wt = _f16(H, H, dev=dev)
+            self.emb = torch.zeros(vp, H, dtype=torch.float16, device=dev)
+            self.bias = torch.full((vp,), float("-inf"), dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            table, max_n = K.cast_table([(wt.detach(), self.wt), (emb.detach(), self.emb[:V]),
+                                         (bv.detach(), self.bias[:V])], dev)
+            K.cast_multi(table, max_n)
+        self.key = key
+        return self
+
+
+class MLMHead(torch.autograd.Function):
+    """K14: per-row MLM cross-entropy of HF BertOnlyMLMHead on GATHERED masked rows.
+
+    loss_i = CE(LN(gelu(x_i Wt^T + bt)) E^T + b_v, label_i);  x fp16 [M, H] (internal hidden rows), labels [M]."""
+
+    @staticmethod
+    def forward(ctx, x, labels, wt, bt, gamma, beta, emb, bv, shadow, eps):
+        M, H = x.shape
+        V = emb.shape[0]
+        dev = x.device
+        sh = shadow.refresh(wt, emb, bv)
+        x = x.contiguous()
+        labels = labels.contiguous()
+        z, t = _f16(M, H, dev=dev), _f16(M, H, dev=dev)
+        K.gemm(x, sh.wt, t, M=M, N=H, K=H, bias=bt, epilogue=K.EPI_BIAS_GELU, out2=z)
+        u = _f16(M, H, dev=dev)
+        mean, rstd = _f32(M, dev=dev), _f32(M, dev=dev)
+        K.ln_fwd(t, gamma, beta, u, mean, rstd, None, n_seq=M, seq_len=1, hidden=H, eps=eps)
+        logits = _f32(M, sh.vp, dev=dev)
+        K.gemm(u, sh.emb, logits, M=M, N=sh.vp, K=H, epilogue=K.EPI_F32_STORE)
+        loss, lse = _f32(M, dev=dev), _f32(M, dev=dev)
+        K.vocab_ce_fwd(logits, sh.bias, labels, loss, lse, n_cols=sh.vp)
+        ctx.save_for_backward(x, labels, z, t, u, mean, rstd, logits, lse, gamma)
+        ctx.sh = (sh.wt, sh.emb, sh.bias, sh.vp, V)
+        ctx.scale = _GRAD_SCALE
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        x, labels, z, t, u, mean, rstd, logits, lse, gamma = ctx.saved_tensors
+        wt16, emb16, bias, vp, V = ctx.sh
+        M, H = x.shape
+        dev = x.device
+        S = ctx.scale
+        inv = 1.0 / S
+        dlog = _f16(M, vp, dev=dev)
+        K.vocab_ce_bwd(logits, bias, labels, lse, dloss.contiguous().float(), dlog, n_cols=vp, scale=S)
+        sizes = (vp * H, vp, H, H, H * H, H)
+        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        views, off = [], 0
+        for n in sizes:
+            views.append(flat[off:off + n])
+            off += n
+        dE, dbv, dgamma, dbeta, dwt, dbt = views
+        dE, dwt = dE.view(vp, H), dwt.view(H, H)
+        du = _f16(M, H, dev=dev)
+        K.gemm(dlog, emb16, du, M=M, N=H, K=vp, b_major=1)
+        K.gemm(dlog, u, dE, M=vp, N=H, K=M, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0, alpha=inv)
+        K.colsum(dlog, dbv, rows=M, cols=vp, scale=inv)
+        dt = _f16(M, H, dev=dev)
+        K.ln_bwd(du, None, t, gamma, mean, rstd, dt, dgamma, dbeta, None, n_seq=M, seq_len=1, hidden=H, out_scale=inv,
+                 row_ws=_f32(2 * M, dev=dev))
+        dz = _f16(M, H, dev=dev)
+        K.dgelu(dt, z, dz)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = _f16(M, H, dev=dev)
+            K.gemm(dz, wt16, dx, M=M, N=H, K=H, b_major=1)
+        K.gemm(dz, x, dwt, M=H, N=H, K=M, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0, alpha=inv)
+        K.colsum(dz, dbt, rows=M, cols=H, scale=inv)
+        return dx, None, dwt, dbt, dgamma, dbeta, dE[:V], dbv[:V], None, None
+
+
+class GatherRows(torch.autograd.Function):
+    """rows idx of an internal fp16 [T, H] tensor (the ~15 % masked positions the MLM loss looks at)."""
+
+    @staticmethod
+    def forward(ctx, h, idx):
+        ctx.save_for_backward(idx)
+        ctx.rows = h.shape[0]
+        return h.index_select(0, idx)
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        out = torch.zeros(ctx.rows, g.shape[1], dtype=g.dtype, device=g.device)
+        out.index_copy_(0, idx, g)
+        return out, None

@@ -160,6 +160,17 @@ typedef struct cdr_simmat_args {
 int cdr_simmat_ce_fwd(const cdr_simmat_args* args, void* stream);
 int cdr_simmat_ce_bwd(const cdr_simmat_args* args, void* stream);
 
+/* K14 MLM head loss on gathered masked rows (HF BertForMaskedLM cross-entropy reached through
+ * COCO/modeling.py:87-93, 199-204): logits fp32 [n_rows, ld] from the decoder GEMM, bias fp32 [n_cols] added
+ * here (padding columns hold -inf), labels in [0, n_cols).  bwd writes fp16 dlogits = scale * dloss_i *
+ * (softmax - onehot).  cdr_dgelu_f16: dz = dt * gelu_erf'(z) for the MLM transform (GELU between GEMM and LN). */
+int cdr_vocab_ce_fwd(const float* logits, const float* bias, const int64_t* labels, float* loss, float* lse,
+                     int32_t n_rows, int32_t n_cols, int64_t ld, void* stream);
+int cdr_vocab_ce_bwd(const float* logits, const float* bias, const int64_t* labels, const float* lse,
+                     const float* dloss, void* dlogits, int32_t n_rows, int32_t n_cols, int64_t ld, float scale,
+                     void* stream);
+int cdr_dgelu_f16(const void* dt, const void* z, void* dz, int64_t n, void* stream);
+
 /* K10 group statistics (ANCE/model/dro_loss.py:217-224): sums[g] = sum of loss_i with g_i == g,
  * counts[g] = #{i: g_i == g} (both overwritten); bwd: dloss_i = dsums[g_i]. */
 int cdr_group_reduce_fwd(const float* loss, const int64_t* g, int32_t n, int32_t n_groups, float* sums, float* counts,
