@@ -1,0 +1,89 @@
+"""torchrun worker for the multi-GPU parity checks (launched by tests/test_multigpu_gpu.py).
+
+Every rank checks, against a single-process computation on the concatenated inputs:
+  1. sharded corpus scan (documents split over ranks, all-gather of [nq,k] lists, merge) -> bit-exact ranks
+  2. in-batch InfoNCE over all-gathered passage CLS embeddings: loss and (DDP-averaged) embedding gradients
+  3. iDRO Gram through reduce-scatter + local cdr_gram_f32 + all-reduce
+  4. COCO contrastive loss with the reference's gather convention (own slot keeps the graph, loss * world)
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    from cocodr_b200 import dro_loss, models, ops, scan
+    from oracle import heads_ref, scan_ref
+
+    # 1. sharded scan
+    Q, P = scan_ref.synth_corpus(40_000, 32, 256, seed=21, kind="exact")
+    per = P.shape[0] // world
+    lo, hi = rank * per, (P.shape[0] if rank == world - 1 else (rank + 1) * per)
+    D, I = scan.search_sharded(Q.to(dev), P[lo:hi].to(dev), 100, doc_base=lo)
+    Dr, Ir = scan_ref.search(Q, P, 100)
+    assert (I.cpu().numpy() == Ir).all() and (D.cpu().numpy() == Dr).all(), "sharded scan mismatch"
+
+    # 2. in-batch InfoNCE with gathered passages
+    torch.manual_seed(0)
+    B, H = 8, 64
+    Qa, Pa = torch.randn(world * B, H) * 0.3, torch.randn(world * B, H) * 0.3
+    q = Qa[rank * B:(rank + 1) * B].to(dev).requires_grad_(True)
+    p = Pa[rank * B:(rank + 1) * B].to(dev).requires_grad_(True)
+    keys = models.gather_with_grad(p)
+    loss = ops.qp_infonce(q, keys, row_offset=rank * B).mean()
+    loss.backward()
+    Qf, Pf = Qa.clone().requires_grad_(True), Pa.clone().requires_grad_(True)
+    ref = heads_ref.qp_infonce(Qf, Pf).mean()
+    ref.backward()
+    np.testing.assert_allclose((q.grad / world).cpu().numpy(), Qf.grad[rank * B:(rank + 1) * B].numpy(), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose((p.grad / world).cpu().numpy(), Pf.grad[rank * B:(rank + 1) * B].numpy(), rtol=1e-4, atol=1e-6)
+    lall = torch.zeros(world, device=dev)
+    lall[rank] = loss.detach()
+    dist.all_reduce(lall)
+    assert abs(lall.mean().item() - ref.item()) < 1e-5
+
+    # 3. iDRO Gram: reduce-scatter shards + local Gram + all-reduce == Gram of the all-reduced matrix
+    G, Pn = 7, 100_003
+    g = torch.Generator().manual_seed(rank)
+    local_m = torch.randn(G, Pn, generator=g).to(dev)
+    mod = dro_loss.iDROLoss(types.SimpleNamespace(model_size="base", local_rank=local), G, 0.25, 0.01, 0.1, 0.05)
+    got = mod._gram(local_m)
+    summed = local_m.clone()
+    dist.all_reduce(summed)
+    refg = (summed.double() @ summed.double().t()).float()
+    np.testing.assert_allclose(got.cpu().numpy(), refg.cpu().numpy(), rtol=3e-4, atol=5e-2)
+
+    # 4. COCO contrastive, reference gather convention
+    n_loc = 6
+    E = torch.randn(world * n_loc, H) * 0.4
+    e = E[rank * n_loc:(rank + 1) * n_loc].to(dev).requires_grad_(True)
+    parts = [torch.empty_like(e) for _ in range(world)]
+    dist.all_gather(parts, e.detach())
+    parts[rank] = e
+    co = ops.coco_contrastive(torch.cat(parts), loss_scale=float(world))
+    co.mean().backward()
+    Ef = E.clone().requires_grad_(True)
+    refc = heads_ref.coco_contrastive(Ef)
+    refc.mean().backward()
+    np.testing.assert_allclose(co.detach().cpu().numpy(), world * refc.detach().numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose((e.grad / world).cpu().numpy(), Ef.grad[rank * n_loc:(rank + 1) * n_loc].numpy(),
+                               rtol=1e-3, atol=1e-6)
+    dist.barrier()
+    if rank == 0:
+        print(f"MULTIGPU_OK world={world}")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
