@@ -16,6 +16,7 @@ from . import kernels as K
 
 _GRAD_SCALE = 1024.0
 FORCE_SHADOW_REFRESH = False  # set while a CUDA graph is being captured (graph.py)
+GRAD_SYNC = None              # an active gradsync.GradSync collects the flat gradient buffers of each backward
 
 
 def set_grad_scale(s: float):
@@ -138,11 +139,19 @@ class EmbedLN(torch.autograd.Function):
         n_seq, L = ids.shape
         H = word.shape[1]
         dev = word.device
-        dword, dpos, dtyp = torch.zeros_like(word), torch.zeros_like(pos), torch.zeros_like(typ)
-        dgamma, dbeta = _z32(H, dev=dev), _z32(H, dev=dev)
+        sizes = (word.numel(), pos.numel(), typ.numel(), H, H)
+        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        views, off = [], 0
+        for n in sizes:
+            views.append(flat[off:off + n])
+            off += n
+        dword, dpos, dtyp = views[0].view_as(word), views[1].view_as(pos), views[2].view_as(typ)
+        dgamma, dbeta = views[3], views[4]
         K.embed_ln_bwd(dy.contiguous(), ids, word, pos, typ, gamma, mean, rstd, dword, dpos, dtyp, dgamma, dbeta,
                        n_seq=n_seq, seq_len=L, hidden=H, vocab=word.shape[0], pad_id=0, in_scale=1.0,
                        out_scale=1.0 / ctx.scale)
+        if GRAD_SYNC is not None:
+            GRAD_SYNC.submit(flat)
         return None, dword, dpos, dtyp, dgamma, dbeta, None
 
 
@@ -241,6 +250,8 @@ class BertLayerFn(torch.autograd.Function):
         K.gemm(dqkv, x, dwqkv, M=3 * H, N=H, K=T, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0,
                alpha=inv)
         K.colsum(dqkv, dbqkv, rows=T, cols=3 * H, scale=inv)
+        if GRAD_SYNC is not None:
+            GRAD_SYNC.submit(flat)
         return (dx, None, dwqkv[0:H], dbqkv[0:H], dwqkv[H:2 * H], dbqkv[H:2 * H], dwqkv[2 * H:], dbqkv[2 * H:], dwo,
                 dbo, dg1, dbe1, dwi, dbi, dwo2, dbo2, dg2, dbe2, None, None, None, None, None, None)
 

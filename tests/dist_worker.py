@@ -79,6 +79,38 @@ def main():
     np.testing.assert_allclose(co.detach().cpu().numpy(), world * refc.detach().numpy(), rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose((e.grad / world).cpu().numpy(), Ef.grad[rank * n_loc:(rank + 1) * n_loc].numpy(),
                                rtol=1e-3, atol=1e-6)
+    # 5. GradSync: per-layer flat-buffer all-reduce during backward == mean over ranks of the local gradients
+    from transformers import BertConfig
+
+    from cocodr_b200.gradsync import GradSync
+    from oracle import bert_ref
+    tiny = dict(hidden=128, layers=3, heads=2, inter=512, vocab=2000, max_pos=64, type_vocab=2)
+    hf = BertConfig(vocab_size=2000, hidden_size=128, num_hidden_layers=3, num_attention_heads=2, intermediate_size=512,
+                    max_position_embeddings=64, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, num_labels=2)
+    model = models.BertDot_InBatch_NLL_LN(hf)
+    model.bert.load_state_dict(bert_ref.synth_state(tiny, 0), strict=False)
+    model = model.to(dev).train()
+    qi, qm = (t.to(dev) for t in bert_ref.synth_batch(4, 32, 2000, 100 + rank))
+    pi, pm = (t.to(dev) for t in bert_ref.synth_batch(4, 32, 2000, 200 + rank))
+    w = torch.ones(4, device=dev)
+    model(qi, qm, pi, pm, weights=w)[0].backward()
+    local_g = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+    for t in local_g.values():
+        dist.all_reduce(t)
+        t /= world
+    model.zero_grad(set_to_none=True)
+    sync = GradSync(model)
+    loss = model(qi, qm, pi, pm, weights=w)[0]
+    with sync:
+        loss.backward()
+    torch.cuda.synchronize()
+    assert len(local_g) > 50
+    for n, p in model.named_parameters():
+        if n in local_g:
+            ref_g = local_g[n]
+            err = (p.grad - ref_g).abs().max().item()
+            assert err <= 1e-5 + 1e-3 * ref_g.abs().max().item(), (n, err)
+
     dist.barrier()
     if rank == 0:
         print(f"MULTIGPU_OK world={world}")
