@@ -7,7 +7,8 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcocodr_b200.so")
+# COCODR_B200_LIB: development override used to A/B differently-compiled builds of the same library
+LIB_PATH = os.environ.get("COCODR_B200_LIB") or os.path.join(_HERE, "libcocodr_b200.so")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "cocodr_b200.h")
 
 _lib = None
@@ -45,7 +46,8 @@ class GemmArgs(C.Structure):
                 ("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64),
                 ("lda", C.c_int64), ("ldb", C.c_int64), ("ldo", C.c_int64), ("ldaux", C.c_int64),
                 ("a_major", C.c_int32), ("b_major", C.c_int32), ("epilogue", C.c_int32), ("split_k", C.c_int32),
-                ("alpha", C.c_float), ("dbg_lbo", C.c_int32), ("dbg_sbo", C.c_int32)]
+                ("alpha", C.c_float), ("dbg_lbo", C.c_int32), ("dbg_sbo", C.c_int32),
+                ("colsum", C.c_void_p), ("colsum_scale", C.c_float), ("reserved", C.c_int32)]
 
 
 def declared_symbols():

@@ -150,6 +150,11 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Relaxed variant for signals that order nothing but tcgen05.ld (already fenced): no release fence, so the
+// arriving warp does not wait for its outstanding global stores to drain.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // 2-SM TMA load: data lands in THIS CTA's shared memory, completion bytes are posted on the barrier at
 // shared::cluster address `bar_cluster_addr` (the pair leader's)
 __device__ __forceinline__ void tma_load_2d_cg2(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0,
@@ -264,6 +269,16 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   gelu_tail(x, tail, e);
   const float cdf = x > 0.f ? 1.0f - tail : tail;
   return fmaf(x * 0.3989422804014327f, e, cdf);
+}
+
+// value and derivative from one shared tail / pdf evaluation (the forward GELU epilogue stores both)
+__device__ __forceinline__ void gelu_erf_both(float x, float& y, float& dy) {
+  float tail, e;
+  gelu_tail(x, tail, e);
+  const float ax = fabsf(x);
+  y = fmaf(-ax, tail, fmaxf(x, 0.f));
+  const float cdf = x > 0.f ? 1.0f - tail : tail;
+  dy = fmaf(x * 0.3989422804014327f, e, cdf);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

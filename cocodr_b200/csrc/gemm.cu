@@ -103,18 +103,40 @@ int gemm_run(const cdr_gemm_args& g, GemmParams p, cudaStream_t st) {
   const int total_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
   int split = g.split_k;
   if (split <= 0) {
-    // auto: enough work items to fill the machine, at least 4 k-blocks per split
+    // auto: minimise rounds x (k-blocks per item + a fixed per-item cost for pipeline ramp and the exposed
+    // part of the epilogue), i.e. prefer splits whose item count fills whole waves of the persistent grid
     const int tiles = p.m_tiles * p.n_tiles;
-    split = (2 * (sm_count() / p.cta_group) + tiles - 1) / tiles;
-    if (split > total_kb / 4) split = total_kb / 4;
-    if (split < 1) split = 1;
+    const int workers = sm_count() / p.cta_group;
+    long best_cost = -1;
+    split = 1;
+    for (int s = 1; s <= 64 && s * 8 <= total_kb; ++s) {
+      const int kbps = (total_kb + s - 1) / s;
+      const int s_eff = (total_kb + kbps - 1) / kbps;
+      if (s_eff != s) continue;
+      const long rounds = (static_cast<long>(tiles) * s + workers - 1) / workers;
+      const long cost = rounds * (kbps + 4);
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        split = s;
+      }
+    }
   }
   if (split > total_kb) split = total_kb;
   p.kb_per_split = (total_kb + split - 1) / split;
   p.split_k = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
   CDR_REQUIRE(p.split_k == 1 || g.epilogue == CDR_EPI_F32_ATOMIC, "cdr_gemm: split_k > 1 needs CDR_EPI_F32_ATOMIC");
   p.alpha = g.alpha;
+  p.colsum = g.colsum;
+  p.colsum_scale = g.colsum_scale;
   p.dbg_lbo = g.dbg_lbo; p.dbg_sbo = g.dbg_sbo;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("CDR_GEMM_DBG");
+      dbg = e ? atoi(e) : 0;
+    }
+    p.dbg_flags = dbg;
+  }
 
   CUtensorMap ta, tb;
   int rc;
@@ -145,6 +167,8 @@ extern "C" int cdr_gemm(const cdr_gemm_args* g, void* stream) {
     CDR_REQUIRE(g->aux != nullptr && g->ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(g->aux) & 15) == 0,
                 "cdr_gemm: epilogue %d needs a 16-byte aligned aux operand", g->epilogue);
   }
+  if (g->colsum != nullptr)
+    CDR_REQUIRE(g->epilogue == CDR_EPI_DGELU, "cdr_gemm: the fused column sum is only available with CDR_EPI_DGELU");
   if (g->bias) CDR_REQUIRE((reinterpret_cast<uintptr_t>(g->bias) & 15) == 0, "cdr_gemm: bias must be 16-byte aligned");
   cdr::GemmParams p{};
   p.out = g->out;

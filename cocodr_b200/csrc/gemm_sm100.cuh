@@ -27,7 +27,10 @@ namespace cdr {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_EPI_WARPS = 16;  // 4 per TMEM lane quadrant / SM sub-partition: the epilogue math is latency-bound
+#ifndef CDR_GEMM_EPI_WARPS
+#define CDR_GEMM_EPI_WARPS 8
+#endif
+constexpr int GEMM_EPI_WARPS = CDR_GEMM_EPI_WARPS;  // 2 per TMEM lane quadrant: with the accumulators released early and the aux operand prefetched, 8 warps beat 16 (32 KB less staging smem = one more TMA stage)
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;  // 320
 
 struct GemmParams {
@@ -43,6 +46,8 @@ struct GemmParams {
   const __half* aux;    // residual R or pre-activation Z, [M, ldaux] fp16
   long long ldo, ldaux;
   float alpha;
+  float* colsum;        // optional fp32 [N]: += colsum_scale * column sums of the (fp32, pre-rounding) output
+  float colsum_scale;
   // scan filter epilogue
   const float* thresh;          // [N] per-query admission threshold
   unsigned long long* cand;     // [N, cand_cap] packed (score, doc) keys
@@ -51,6 +56,7 @@ struct GemmParams {
   long long row_base;           // global doc index of row 0
   // debug overrides for descriptor probing (0 = default)
   int dbg_lbo, dbg_sbo;
+  int dbg_flags;  // CDR_GEMM_DBG (environment): bit 0 = skip the epilogue math and stores (timing experiments only)
 };
 
 // host-side entry shared by cdr_gemm and the scan (gemm.cu)
@@ -117,9 +123,11 @@ __device__ __forceinline__ void gemm_epilogue_apply(const GemmParams& p, float (
     const float4 lo = make_float4(v[0] * p.alpha, v[1] * p.alpha, v[2] * p.alpha, v[3] * p.alpha);
     const float4 hi = make_float4(v[4] * p.alpha, v[5] * p.alpha, v[6] * p.alpha, v[7] * p.alpha);
     if constexpr (EPI == CDR_EPI_F32_ATOMIC) {
+      if (p.dbg_flags & 2) return;
       atomicAdd(reinterpret_cast<float4*>(o), lo);
       atomicAdd(reinterpret_cast<float4*>(o + 4), hi);
     } else {
+      if (p.dbg_flags & 2) return;
       *reinterpret_cast<float4*>(o) = lo;
       *reinterpret_cast<float4*>(o + 4) = hi;
     }
@@ -136,37 +144,62 @@ __device__ __forceinline__ void gemm_epilogue_apply(const GemmParams& p, float (
       }
     }
     if constexpr (EPI == CDR_EPI_DGELU) {
-      const __half2* zh = reinterpret_cast<const __half2*>(&auxq);
+      const __half2* gh = reinterpret_cast<const __half2*>(&auxq);  // gelu'(z) saved by the forward epilogue
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        const float2 f = __half22float2(zh[t]);
-        v[2 * t] *= gelu_erf_grad(f.x);
-        v[2 * t + 1] *= gelu_erf_grad(f.y);
+        const float2 f = __half22float2(gh[t]);
+        v[2 * t] *= f.x;
+        v[2 * t + 1] *= f.y;
       }
     }
     if constexpr (EPI == CDR_EPI_BIAS_GELU) {
-      if (p.out2 != nullptr) {
-        uint4 zq;
-        __half2* zh = reinterpret_cast<__half2*>(&zq);
+      float d[8];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) zh[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
-        *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out2) + static_cast<long long>(m) * p.ldo + n) = zq;
+      for (int t = 0; t < 8; ++t) gelu_erf_both(v[t], v[t], d[t]);
+      if (p.out2 != nullptr && !(p.dbg_flags & 2)) {
+        uint4 dq;
+        __half2* dh = reinterpret_cast<__half2*>(&dq);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) dh[t] = __floats2half2_rn(d[2 * t], d[2 * t + 1]);
+        *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out2) + static_cast<long long>(m) * p.ldo + n) = dq;
       }
-#pragma unroll
-      for (int t = 0; t < 8; ++t) v[t] = gelu_erf(v[t]);
     }
     uint4 q;
     __half2* qh = reinterpret_cast<__half2*>(&q);
 #pragma unroll
     for (int t = 0; t < 4; ++t) qh[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
+    if (p.dbg_flags & 2) {
+      if (q.x == 0x12345678u && q.y == 0x9abcdef0u) reinterpret_cast<uint4*>(p.out)[0] = q;  // keep the math alive
+      return;
+    }
     *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + static_cast<long long>(m) * p.ldo + n) = q;
+  }
+}
+
+template <int EPI>
+constexpr bool GEMM_EPI_HAS_AUX = (EPI == CDR_EPI_BIAS_RESIDUAL || EPI == CDR_EPI_DGELU);
+
+// The residual / saved-derivative operand of one 32 x 32 chunk, in the post-transpose thread mapping
+// (thread -> 8 columns of rows (lane>>2) + 8i).  Issued BEFORE the accumulator is waited for, so the global
+// latency overlaps the tile's MMAs.
+template <int EPI>
+__device__ __forceinline__ void gemm_epilogue_load_aux(const GemmParams& p, uint4 (&auxq)[4], int lane, int m_base,
+                                                       int n0) {
+  if constexpr (GEMM_EPI_HAS_AUX<EPI>) {
+    const int n = n0 + (lane & 3) * 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m_base + (lane >> 2) + 8 * i;
+      auxq[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (n < p.N && m < p.M && !(p.dbg_flags & 4)) auxq[i] = *reinterpret_cast<const uint4*>(p.aux + static_cast<long long>(m) * p.ldaux + n);
+    }
   }
 }
 
 // One warp, one 32 x 32 chunk: rows [m_base, m_base+32), columns [n0, n0+32).  acc = this thread's row.
 template <int EPI>
 __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const uint32_t (&acc)[32], float* stg,
-                                                    int lane, int m_base, int n0) {
+                                                    int lane, int m_base, int n0, const uint4 (&auxq)[4]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j)
     *stg_piece(stg, lane, j) = make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]),
@@ -189,16 +222,9 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const u
       bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
     }
   }
-  constexpr bool HAS_AUX = (EPI == CDR_EPI_BIAS_RESIDUAL || EPI == CDR_EPI_DGELU);
-  uint4 auxq[4];
-  if constexpr (HAS_AUX) {
+  float csum[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {  // all four rows' loads in flight before any math
-      const int m = m_base + (lane >> 2) + 8 * i;
-      auxq[i] = make_uint4(0u, 0u, 0u, 0u);
-      if (col_ok && m < p.M) auxq[i] = *reinterpret_cast<const uint4*>(p.aux + static_cast<long long>(m) * p.ldaux + n);
-    }
-  }
+  for (int t = 0; t < 8; ++t) csum[t] = 0.f;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int r = (lane >> 2) + 8 * i;
@@ -206,7 +232,44 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const u
     const float4 lo = *stg_piece(stg, r, 2 * seg);
     const float4 hi = *stg_piece(stg, r, 2 * seg + 1);
     float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-    if (col_ok && m < p.M) gemm_epilogue_apply<EPI>(p, v, m, n, bias, HAS_AUX ? auxq[i] : auxq[0]);
+    if (col_ok && m < p.M) {
+      gemm_epilogue_apply<EPI>(p, v, m, n, bias, auxq[i]);
+      if constexpr (EPI == CDR_EPI_DGELU) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) csum[t] += v[t];
+      }
+    }
+  }
+  if constexpr (EPI == CDR_EPI_DGELU) {
+    // fused bias gradient: column sums of this chunk.  The 8 lanes that share `seg` hold the same 8 columns
+    // for different rows; a halving butterfly over lane bits 4,3,2 leaves every lane with ONE column total.
+    if (p.colsum != nullptr) {
+      float a4[4], a2[2];
+      {
+        const bool up = (lane & 16) != 0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float keep = up ? csum[t + 4] : csum[t];
+          const float send = up ? csum[t] : csum[t + 4];
+          a4[t] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+      }
+      {
+        const bool up = (lane & 8) != 0;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const float keep = up ? a4[t + 2] : a4[t];
+          const float send = up ? a4[t] : a4[t + 2];
+          a2[t] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+      }
+      const bool up = (lane & 4) != 0;
+      const float keep = up ? a2[1] : a2[0];
+      const float send = up ? a2[0] : a2[1];
+      const float tot = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      const int col = n + ((lane & 16) ? 4 : 0) + ((lane & 8) ? 2 : 0) + ((lane & 4) ? 1 : 0);
+      if (col < p.N) atomicAdd(p.colsum + col, tot * p.colsum_scale);
+    }
   }
   __syncwarp();  // staging tile is rewritten by the next chunk
 }
@@ -234,7 +297,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
   const int worker = blockIdx.x / CG;        // CTA (pair) index
   const int n_workers = gridDim.x / CG;
-  const int total_items = p.m_tiles * p.n_tiles * p.split_k;
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int total_items = tiles * p.split_k;
   const int total_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
 
   if (threadIdx.x == 0) {
@@ -270,8 +334,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       for (int item = worker; item < total_items; item += n_workers) {
-        const int tile = item / p.split_k;
-        const int ks = item - tile * p.split_k;
+        // k-split major: the tiles that run concurrently walk the SAME k-range, so every A / B panel of a
+        // split-K wgrad is pulled from HBM once and shared through L2
+        const int ks = item / tiles;
+        const int tile = item - ks * tiles;
         const int m0 = (tile / p.n_tiles) * (GEMM_BM * CG) + static_cast<int>(cta_rank) * GEMM_BM;
         const int n0 = (tile % p.n_tiles) * BN + static_cast<int>(cta_rank) * BNL;
         const int kb0 = ks * p.kb_per_split;
@@ -334,7 +400,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int item = worker; item < total_items; item += n_workers) {
-        const int ks = item % p.split_k;
+        const int ks = item / tiles;
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, total_kb);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -370,26 +436,44 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     uint32_t acc_phase = 0;
     const uint32_t empty_remote = (CG == 2) ? mapa_shared(smem_u32(&tmem_empty[0]), 0) : 0u;
     for (int item = worker; item < total_items; item += n_workers) {
-      const int tile = item / p.split_k;
+      const int tile = item % tiles;
       const int m0 = (tile / p.n_tiles) * (GEMM_BM * CG) + static_cast<int>(cta_rank) * GEMM_BM;
       const int n0 = (tile % p.n_tiles) * BN;
+      // this warp's chunks: columns (half + NH*j) * 32 of TMEM lane quadrant `quad`, handled two at a time
+      constexpr int NH = GEMM_EPI_WARPS / 4;          // warps per lane quadrant
+      constexpr int CPW = (BN / 32) / NH;             // chunks per warp per tile
+      static_assert(CPW == 1 || CPW % 2 == 0, "chunks per epilogue warp");
+      const int mb = m0 + quad * 32;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
+      uint4 aux[CPW][4];
+#pragma unroll
+      for (int j = 0; j < CPW; ++j)  // all in flight while the MMAs of this tile finish
+        gemm_epilogue_load_aux<EPI>(p, aux[j], lane, mb, n0 + (half + NH * j) * 32);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
-      constexpr int CHUNKS = BN / 32;
-#pragma unroll 1
-      for (int c = half; c < CHUNKS; c += GEMM_EPI_WARPS / 4) {
-        if (n0 + c * 32 >= p.N) break;
-        uint32_t r[32];
-        tmem_ld_32x32(t_row + c * 32, r);
+#pragma unroll
+      for (int b = 0; b < CPW; b += 2) {
+        const int c0 = half + NH * b, c1 = half + NH * (b + 1);
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32(t_row + c0 * 32, r0);
+        if constexpr (CPW >= 2) tmem_ld_32x32(t_row + c1 * 32, r1);
         tc_wait_ld();
-        gemm_epilogue_chunk<EPI>(p, r, stg, lane, m0 + quad * 32, n0 + c * 32);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (CG == 2) mbar_arrive_cluster(empty_remote + acc * 8);
-        else mbar_arrive(&tmem_empty[acc]);
+        if (b + 2 >= CPW) {
+          // the accumulator stage is free as soon as it sits in registers: release it BEFORE the epilogue
+          // math and the global stores, so the MMAs of the tile after next never wait for this warp's stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (CG == 2) mbar_arrive_cluster_relaxed(empty_remote + acc * 8);
+            else mbar_arrive(&tmem_empty[acc]);
+          }
+        }
+        if (n0 + c0 * 32 < p.N && !(p.dbg_flags & 1)) {
+          gemm_epilogue_chunk<EPI>(p, r0, stg, lane, mb, n0 + c0 * 32, aux[b]);
+          if constexpr (CPW >= 2) {
+            if (n0 + c1 * 32 < p.N) gemm_epilogue_chunk<EPI>(p, r1, stg, lane, mb, n0 + c1 * 32, aux[b + 1 < CPW ? b + 1 : b]);
+          }
+        }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }

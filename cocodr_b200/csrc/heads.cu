@@ -162,8 +162,8 @@ vocab_ce_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ 
   }
 }
 
-// dz = dt * gelu'(z)  (the MLM transform's GELU sits between a GEMM and a LayerNorm, so its backward is
-// not a GEMM epilogue)
+// dz = dt * gelu'(z), z given as the derivative tensor saved by the forward GELU epilogue (the MLM transform's
+// GELU sits between a GEMM and a LayerNorm, so its backward is not a GEMM epilogue)
 __global__ void __launch_bounds__(256)
 dgelu_kernel(const __half* __restrict__ dt, const __half* __restrict__ z, __half* __restrict__ dz, long long n) {
   const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
@@ -177,7 +177,7 @@ dgelu_kernel(const __half* __restrict__ dt, const __half* __restrict__ z, __half
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
     const float2 x = __half22float2(ah[t]), y = __half22float2(bh[t]);
-    oh[t] = __floats2half2_rn(x.x * gelu_erf_grad(y.x), x.y * gelu_erf_grad(y.y));
+    oh[t] = __floats2half2_rn(x.x * y.x, x.y * y.y);
   }
   *reinterpret_cast<uint4*>(dz + i) = o;
 }

@@ -45,7 +45,8 @@ def _need_cuda(*ts):
 
 
 def gemm(a, b, out, *, M, N, K, a_major=0, b_major=0, epilogue=EPI_STORE_F16, bias=None, aux=None, out2=None,
-         alpha=1.0, split_k=1, lda=None, ldb=None, ldo=None, ldaux=None, dbg_lbo=0, dbg_sbo=0):
+         alpha=1.0, split_k=1, lda=None, ldb=None, ldo=None, ldaux=None, dbg_lbo=0, dbg_sbo=0, colsum=None,
+         colsum_scale=1.0):
     """out[M,N] = alpha * A[M,K] @ B[N,K]^T with a fused epilogue (see include/cocodr_b200.h)."""
     _need_cuda(a, b, out)
     assert a.dtype == torch.float16 and b.dtype == torch.float16
@@ -61,6 +62,8 @@ def gemm(a, b, out, *, M, N, K, a_major=0, b_major=0, epilogue=EPI_STORE_F16, bi
     g.a_major, g.b_major, g.epilogue, g.split_k = a_major, b_major, epilogue, split_k
     g.alpha = alpha
     g.dbg_lbo, g.dbg_sbo = dbg_lbo, dbg_sbo
+    g.colsum = colsum.data_ptr() if colsum is not None else 0
+    g.colsum_scale = colsum_scale
     if bias is not None:
         assert bias.dtype == torch.float32
     if gemm_events is not None:

@@ -180,15 +180,15 @@ class BertLayerFn(torch.autograd.Function):
         x1 = _f16(T, H, dev=dev)
         mean1, rstd1 = _f32(T, dev=dev), _f32(T, dev=dev)
         K.ln_fwd(y1, g1, be1, x1, mean1, rstd1, None, n_seq=n_seq, seq_len=L, hidden=H, eps=eps)
-        z, gl = _f16(T, I, dev=dev), _f16(T, I, dev=dev)
-        K.gemm(x1, sh.wi, gl, M=T, N=I, K=H, bias=bi, epilogue=K.EPI_BIAS_GELU, out2=z)
+        gp, gl = _f16(T, I, dev=dev), _f16(T, I, dev=dev)  # gelu'(z) (saved for the backward), gelu(z)
+        K.gemm(x1, sh.wi, gl, M=T, N=I, K=H, bias=bi, epilogue=K.EPI_BIAS_GELU, out2=gp)
         y2 = _f16(T, H, dev=dev)
         K.gemm(gl, sh.wo2, y2, M=T, N=H, K=I, bias=bo2, epilogue=K.EPI_BIAS_RESIDUAL, aux=x1)
         y = _f16(T, H, dev=dev)
         mean2, rstd2 = _f32(T, dev=dev), _f32(T, dev=dev)
         cls = _f32(n_seq, H, dev=dev) if emit_cls else None
         K.ln_fwd(y2, g2, be2, y, mean2, rstd2, cls, n_seq=n_seq, seq_len=L, hidden=H, eps=eps)
-        ctx.save_for_backward(x, key_bias, qkv, att, lse, y1, x1, mean1, rstd1, z, gl, y2, mean2, rstd2, g1, g2)
+        ctx.save_for_backward(x, key_bias, qkv, att, lse, y1, x1, mean1, rstd1, gp, gl, y2, mean2, rstd2, g1, g2)
         ctx.shadow_w = (sh.wqkv, sh.wo, sh.wi, sh.wo2)
         ctx.meta = (n_seq, L, heads, I, emit_cls, _GRAD_SCALE)
         ctx.set_materialize_grads(False)
@@ -198,7 +198,7 @@ class BertLayerFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy, dcls=None):
-        x, key_bias, qkv, att, lse, y1, x1, mean1, rstd1, z, gl, y2, mean2, rstd2, g1, g2 = ctx.saved_tensors
+        x, key_bias, qkv, att, lse, y1, x1, mean1, rstd1, gp, gl, y2, mean2, rstd2, g1, g2 = ctx.saved_tensors
         wqkv, wo, wi, wo2 = ctx.shadow_w
         n_seq, L, heads, I, emit_cls, S = ctx.meta
         T, H = x.shape
@@ -222,12 +222,11 @@ class BertLayerFn(torch.autograd.Function):
         dy2 = _f16(T, H, dev=dev)
         K.ln_bwd(dy, dcls, y2, g2, mean2, rstd2, dy2, dg2, dbe2, dbo2, n_seq=n_seq, seq_len=L, hidden=H, in_scale=S,
                  out_scale=inv, row_ws=row_ws)
-        # ---- FFN down: dG = dy2 W2 (fused gelu'), dW2 = dy2^T G
+        # ---- FFN down: dZ = (dy2 W2) * gelu'(z) with db1 = colsum(dZ) fused into the epilogue, dW2 = dy2^T G
         dz = _f16(T, I, dev=dev)
-        K.gemm(dy2, wo2, dz, M=T, N=I, K=H, b_major=1, epilogue=K.EPI_DGELU, aux=z)
+        K.gemm(dy2, wo2, dz, M=T, N=I, K=H, b_major=1, epilogue=K.EPI_DGELU, aux=gp, colsum=dbi, colsum_scale=inv)
         K.gemm(dy2, gl, dwo2, M=H, N=I, K=T, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0, alpha=inv)
-        # ---- FFN up: dx1 = dZ W1 + dy2 (residual), dW1 = dZ^T x1, db1 = colsum(dZ)
-        K.colsum(dz, dbi, rows=T, cols=I, scale=inv)
+        # ---- FFN up: dx1 = dZ W1 + dy2 (residual), dW1 = dZ^T x1
         dx1 = _f16(T, H, dev=dev)
         K.gemm(dz, wi, dx1, M=T, N=H, K=I, b_major=1, epilogue=K.EPI_BIAS_RESIDUAL, aux=dy2)
         K.gemm(dz, x1, dwi, M=I, N=H, K=T, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0, alpha=inv)
@@ -414,8 +413,8 @@ class MLMHead(torch.autograd.Function):
         sh = shadow.refresh(wt, emb, bv)
         x = x.contiguous()
         labels = labels.contiguous()
-        z, t = _f16(M, H, dev=dev), _f16(M, H, dev=dev)
-        K.gemm(x, sh.wt, t, M=M, N=H, K=H, bias=bt, epilogue=K.EPI_BIAS_GELU, out2=z)
+        gp, t = _f16(M, H, dev=dev), _f16(M, H, dev=dev)  # gelu'(z), gelu(z)
+        K.gemm(x, sh.wt, t, M=M, N=H, K=H, bias=bt, epilogue=K.EPI_BIAS_GELU, out2=gp)
         u = _f16(M, H, dev=dev)
         mean, rstd = _f32(M, dev=dev), _f32(M, dev=dev)
         K.ln_fwd(t, gamma, beta, u, mean, rstd, None, n_seq=M, seq_len=1, hidden=H, eps=eps)
@@ -423,14 +422,14 @@ class MLMHead(torch.autograd.Function):
         K.gemm(u, sh.emb, logits, M=M, N=sh.vp, K=H, epilogue=K.EPI_F32_STORE)
         loss, lse = _f32(M, dev=dev), _f32(M, dev=dev)
         K.vocab_ce_fwd(logits, sh.bias, labels, loss, lse, n_cols=sh.vp)
-        ctx.save_for_backward(x, labels, z, t, u, mean, rstd, logits, lse, gamma)
+        ctx.save_for_backward(x, labels, gp, t, u, mean, rstd, logits, lse, gamma)
         ctx.sh = (sh.wt, sh.emb, sh.bias, sh.vp, V)
         ctx.scale = _GRAD_SCALE
         return loss
 
     @staticmethod
     def backward(ctx, dloss):
-        x, labels, z, t, u, mean, rstd, logits, lse, gamma = ctx.saved_tensors
+        x, labels, gp, t, u, mean, rstd, logits, lse, gamma = ctx.saved_tensors
         wt16, emb16, bias, vp, V = ctx.sh
         M, H = x.shape
         dev = x.device
@@ -454,7 +453,7 @@ class MLMHead(torch.autograd.Function):
         K.ln_bwd(du, None, t, gamma, mean, rstd, dt, dgamma, dbeta, None, n_seq=M, seq_len=1, hidden=H, out_scale=inv,
                  row_ws=_f32(2 * M, dev=dev))
         dz = _f16(M, H, dev=dev)
-        K.dgelu(dt, z, dz)
+        K.dgelu(dt, gp, dz)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = _f16(M, H, dev=dev)

@@ -44,9 +44,10 @@ int cdr_device_check(void);
  * ---------------------------------------------------------------------------------------------- */
 enum {
   CDR_EPI_STORE_F16 = 0,     /* out16 = alpha*acc + bias                                          */
-  CDR_EPI_BIAS_GELU = 1,     /* out2 (optional) = z = alpha*acc + bias ; out16 = gelu_erf(z)      */
+  CDR_EPI_BIAS_GELU = 1,     /* z = alpha*acc + bias ; out16 = gelu_erf(z) ; out2 (optional) = gelu_erf'(z) */
   CDR_EPI_BIAS_RESIDUAL = 2, /* out16 = alpha*acc + bias + aux[m,n]                               */
-  CDR_EPI_DGELU = 3,         /* out16 = alpha*acc * gelu_erf'(aux[m,n])                           */
+  CDR_EPI_DGELU = 3,         /* out16 = alpha*acc * aux[m,n], aux = the gelu_erf'(z) saved by BIAS_GELU;
+                                optional colsum[n] += colsum_scale * sum_m out[m,n] (the bias gradient) */
   CDR_EPI_F32_ATOMIC = 4,    /* out32 += alpha*acc  (red.add, for split-K wgrad)                  */
   CDR_EPI_F32_STORE = 5,     /* out32 = alpha*acc                                                 */
   CDR_EPI_SCAN_FILTER = 6    /* internal: threshold-filter scores into candidate buffers          */
@@ -56,9 +57,9 @@ typedef struct cdr_gemm_args {
   const void* a; /* fp16 */
   const void* b; /* fp16 */
   void* out;        /* fp16 or fp32 [M, ldo] */
-  void* out2;       /* optional fp16 [M, ldo] (CDR_EPI_BIAS_GELU pre-activation) */
+  void* out2;       /* optional fp16 [M, ldo] (CDR_EPI_BIAS_GELU: derivative gelu_erf'(z) for the backward) */
   const float* bias; /* [N] fp32 or NULL */
-  const void* aux;   /* fp16 [M, ldaux] residual / pre-activation, or NULL */
+  const void* aux;   /* fp16 [M, ldaux] residual / saved GELU derivative, or NULL */
   int64_t M, N, K;
   int64_t lda, ldb, ldo, ldaux; /* in elements */
   int32_t a_major, b_major;
@@ -66,6 +67,9 @@ typedef struct cdr_gemm_args {
   int32_t split_k; /* 0 = auto (wgrad), 1 = none */
   float alpha;
   int32_t dbg_lbo, dbg_sbo; /* 0; test-only descriptor overrides */
+  float* colsum;      /* optional fp32 [N], CDR_EPI_DGELU only: accumulates the column sums of the output */
+  float colsum_scale;
+  int32_t reserved;
 } cdr_gemm_args;
 
 int cdr_gemm(const cdr_gemm_args* args, void* stream);
@@ -163,13 +167,14 @@ int cdr_simmat_ce_bwd(const cdr_simmat_args* args, void* stream);
 /* K14 MLM head loss on gathered masked rows (HF BertForMaskedLM cross-entropy reached through
  * COCO/modeling.py:87-93, 199-204): logits fp32 [n_rows, ld] from the decoder GEMM, bias fp32 [n_cols] added
  * here (padding columns hold -inf), labels in [0, n_cols).  bwd writes fp16 dlogits = scale * dloss_i *
- * (softmax - onehot).  cdr_dgelu_f16: dz = dt * gelu_erf'(z) for the MLM transform (GELU between GEMM and LN). */
+ * (softmax - onehot).  cdr_dgelu_f16: dz = dt * gprime for the MLM transform (GELU between GEMM and LN), gprime =
+ * the gelu_erf'(z) tensor saved by the CDR_EPI_BIAS_GELU epilogue. */
 int cdr_vocab_ce_fwd(const float* logits, const float* bias, const int64_t* labels, float* loss, float* lse,
                      int32_t n_rows, int32_t n_cols, int64_t ld, void* stream);
 int cdr_vocab_ce_bwd(const float* logits, const float* bias, const int64_t* labels, const float* lse,
                      const float* dloss, void* dlogits, int32_t n_rows, int32_t n_cols, int64_t ld, float scale,
                      void* stream);
-int cdr_dgelu_f16(const void* dt, const void* z, void* dz, int64_t n, void* stream);
+int cdr_dgelu_f16(const void* dt, const void* gprime, void* dz, int64_t n, void* stream);
 
 /* K10 group statistics (ANCE/model/dro_loss.py:217-224): sums[g] = sum of loss_i with g_i == g,
  * counts[g] = #{i: g_i == g} (both overwritten); bwd: dloss_i = dsums[g_i]. */

@@ -37,11 +37,14 @@ def test_nt_gelu_residual():
     bias = torch.randn(N, device="cuda") * 0.1
     res = _rand((M, N), 5)
     out = torch.empty(M, N, dtype=torch.float16, device="cuda")
-    z = torch.empty_like(out)
-    k.gemm(a, b, out, M=M, N=N, K=K, bias=bias, epilogue=k.EPI_BIAS_GELU, out2=z)
-    zr = a.float() @ b.float().t() + bias
-    _check(z, zr, what="pre-activation")
-    _check(out, torch.nn.functional.gelu(z.float()), tol=2e-3, what="gelu(z16)")
+    gp = torch.empty_like(out)
+    k.gemm(a, b, out, M=M, N=N, K=K, bias=bias, epilogue=k.EPI_BIAS_GELU, out2=gp)
+    zr = (a.float() @ b.float().t() + bias).requires_grad_(True)
+    ref = torch.nn.functional.gelu(zr)
+    ref.sum().backward()
+    _check(out, ref.detach(), tol=2e-3, what="gelu(z)")
+    _check(gp, zr.grad, tol=2e-3, what="gelu'(z) saved for the backward")
+    zr = zr.detach()
     k.gemm(a, b, out, M=M, N=N, K=K, bias=bias, epilogue=k.EPI_BIAS_RESIDUAL, aux=res)
     _check(out, zr + res.float(), what="bias+residual")
     o32 = torch.empty(M, N, dtype=torch.float32, device="cuda")
@@ -57,11 +60,12 @@ def test_dgrad_b_mn_major(M, N, K):
     out = torch.empty(M, N, dtype=torch.float16, device="cuda")
     k.gemm(dy, w, out, M=M, N=N, K=K, b_major=1)
     _check(out, dy.float() @ w.float(), what="dgrad")
-    zpre = _rand((M, N), 8)
-    k.gemm(dy, w, out, M=M, N=N, K=K, b_major=1, epilogue=k.EPI_DGELU, aux=zpre)
-    zf = zpre.float().requires_grad_(True)
-    torch.nn.functional.gelu(zf).sum().backward()
-    _check(out, (dy.float() @ w.float()) * zf.grad, what="dgrad*gelu'")
+    gp = _rand((M, N), 8, 0.5)  # the derivative tensor the forward GELU epilogue saves
+    csum = torch.ones(N, dtype=torch.float32, device="cuda")
+    k.gemm(dy, w, out, M=M, N=N, K=K, b_major=1, epilogue=k.EPI_DGELU, aux=gp, colsum=csum, colsum_scale=0.5)
+    ref = (dy.float() @ w.float()) * gp.float()
+    _check(out, ref, what="dgrad*gelu'")
+    _check(csum, 1.0 + 0.5 * ref.sum(0), tol=2e-3, what="fused bias gradient (column sums)")
 
 
 @pytest.mark.parametrize("M,N,K,split", [(128, 128, 256, 1), (768, 768, 4096, 0), (3072, 768, 2048, 0), (128, 512, 1000, 3)])
