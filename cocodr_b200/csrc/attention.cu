@@ -37,6 +37,8 @@ struct AttParams {
   const __half* o;        // ctx [T, hidden]
   const __half* d_o;      // dctx [T, hidden]
   __half* dqkv;           // [T, 3*hidden]
+  float* dbias;           // optional fp32 [3*hidden]: += dbias_scale * column sums of dqkv
+  float dbias_scale;
 };
 
 // byte offset of element (r, c), c in [0,128), inside two 128B-swizzled [128][64-half] chunks
@@ -203,182 +205,283 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttParams p) 
 }
 
 // ----------------------------------------------------------------------------------------- backward
-// smem: Q K V dO (4 x 16 KB) | P, then dS (ONE 32 KB buffer) | bias | barriers   -> 2 CTAs per SM.
-// P is consumed by the dV MMA first; dS waits in registers (packed fp16) and then overwrites P.
-constexpr int ATT_BWD_SMEM = 6 * ATT_TILE_BYTES + 512 + 64 + 1024;
+// Persistent, warp-specialised: one CTA per SM walks (sequence, head) items.
+//   warp 0      : TMA producer -- Q K V dO of item i+1 land in the other smem stage while item i computes
+//   warp 1      : tcgen05.mma issuer (one thread) + TMEM owner
+//   warps 2..9  : 256 compute threads; thread = (TMEM lane r = query/key row, half h of the 128 key columns)
+// Per item:  S = Q K^T, dP = dO V^T  ->  P = exp2(S - lse), delta_r = sum_j P dP (exact for a whole row in
+// one tile), dS = P (dP - delta) scale  ->  dV = P^T dO, dK = dS^T Q, dQ = dS K  ->  fp16 dQKV rows + the
+// QKV bias gradient (column sums, fp32, straight from the accumulators).
+// The S/dP MMAs of item i+1 are queued behind dV/dK/dQ of item i, so the tensor pipe, the TMA and the
+// softmax threads overlap; nothing but the mbarriers below synchronises them.
+// TMEM columns: S [0,128) dP [128,256) dV [256,320) dK [320,384) dQ [384,448).
+// smem: 2 stages x (Q K V dO) = 128 KB | P 32 KB | dS 32 KB | key bias x2 | delta halves | barriers.
+constexpr int ATT_BWD_THREADS = 320;
+constexpr int ATT_BWD_SMEM = 12 * ATT_TILE_BYTES + 2 * 512 + 2 * 512 + 256 + 1024;
 
-__global__ void __launch_bounds__(256, 2)
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// Column totals of a per-lane row vector: on return lane j holds sum over the 32 lanes of v[j].
+__device__ __forceinline__ float warp_colsum32(const float (&v)[32], int lane) {
+  float a16[16], a8[8], a4[4], a2[2];
+  {
+    const bool up = (lane & 16) != 0;
+#pragma unroll
+    for (int t = 0; t < 16; ++t)
+      a16[t] = (up ? v[t + 16] : v[t]) + __shfl_xor_sync(0xffffffffu, up ? v[t] : v[t + 16], 16);
+  }
+  {
+    const bool up = (lane & 8) != 0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+      a8[t] = (up ? a16[t + 8] : a16[t]) + __shfl_xor_sync(0xffffffffu, up ? a16[t] : a16[t + 8], 8);
+  }
+  {
+    const bool up = (lane & 4) != 0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      a4[t] = (up ? a8[t + 4] : a8[t]) + __shfl_xor_sync(0xffffffffu, up ? a8[t] : a8[t + 4], 4);
+  }
+  {
+    const bool up = (lane & 2) != 0;
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+      a2[t] = (up ? a4[t + 2] : a4[t]) + __shfl_xor_sync(0xffffffffu, up ? a4[t] : a4[t + 2], 2);
+  }
+  const bool up = (lane & 1) != 0;
+  return (up ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, up ? a2[0] : a2[1], 1);
+}
+
+__global__ void __launch_bounds__(ATT_BWD_THREADS, 1)
 fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do,
-                const AttParams p) {
+                const AttParams p, const int n_items) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = smem + ATT_TILE_BYTES;
-  uint8_t* sV = smem + 2 * ATT_TILE_BYTES;
-  uint8_t* sdO = smem + 3 * ATT_TILE_BYTES;
-  uint8_t* sP = smem + 4 * ATT_TILE_BYTES;  // P, later dS
-  float* sBias = reinterpret_cast<float*>(smem + 6 * ATT_TILE_BYTES);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 6 * ATT_TILE_BYTES + 512);
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 5);
+  uint8_t* sStage = smem;                         // [2][Q K V dO]
+  uint8_t* sP = smem + 8 * ATT_TILE_BYTES;        // two [128][64] chunks
+  uint8_t* sdS = smem + 10 * ATT_TILE_BYTES;
+  float* sBias = reinterpret_cast<float*>(smem + 12 * ATT_TILE_BYTES);            // [2][128]
+  float* sDelta = reinterpret_cast<float*>(smem + 12 * ATT_TILE_BYTES + 1024);    // [2][128]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 12 * ATT_TILE_BYTES + 2048);
+  uint64_t* full_qk = bar;          // [2] TMA -> MMA
+  uint64_t* full_vdo = bar + 2;     // [2]
+  uint64_t* stage_empty = bar + 4;  // [2] MMA -> TMA
+  uint64_t* sdp_full = bar + 6;     // MMA -> compute
+  uint64_t* sdp_empty = bar + 7;    // compute -> MMA (8 warps)
+  uint64_t* pds_full = bar + 8;     // compute -> MMA (8 warps): P and dS are in smem
+  uint64_t* out_full = bar + 9;     // MMA -> compute
+  uint64_t* out_empty = bar + 10;   // compute -> MMA (8 warps)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 12);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int seq = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
   const int L = p.seq_len;
-  const int row0 = seq * L;
 
   if (tid == 0) {
     tma_prefetch_desc(&tma_qkv);
     tma_prefetch_desc(&tma_do);
 #pragma unroll
-    for (int i = 0; i < 5; ++i) mbar_init(&bar[i], 1);
+    for (int i = 0; i < 6; ++i) mbar_init(&bar[i], 1);
+    mbar_init(sdp_full, 1);
+    mbar_init(sdp_empty, 8);
+    mbar_init(pds_full, 8);
+    mbar_init(out_full, 1);
+    mbar_init(out_empty, 8);
     fence_mbar_init();
   }
-  if (warp == 0) {
-    tmem_alloc(tmem_ptr, 256);
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 512);
     tmem_relinquish();
-  }
-  if (tid < ATT_T) {
-    float b = -INFINITY;
-    if (tid < L) b = p.key_bias ? p.key_bias[static_cast<long long>(seq) * L + tid] * LOG2E : 0.f;
-    sBias[tid] = b;
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
-  const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK), va = smem_u32(sV), da = smem_u32(sdO), pa = smem_u32(sP);
 
-  if (tid == 0) {
-    mbar_expect_tx(&bar[0], 2 * ATT_TILE_BYTES);
-    tma_load_2d(sQ, &tma_qkv, &bar[0], h * ATT_D, row0);
-    tma_load_2d(sK, &tma_qkv, &bar[0], p.hidden + h * ATT_D, row0);
-    mbar_expect_tx(&bar[1], 2 * ATT_TILE_BYTES);
-    tma_load_2d(sV, &tma_qkv, &bar[1], 2 * p.hidden + h * ATT_D, row0);
-    tma_load_2d(sdO, &tma_do, &bar[1], h * ATT_D, row0);
-    constexpr uint32_t idesc = make_idesc_f16(ATT_T, ATT_T, 0, 0);
-    mbar_wait(&bar[0], 0);
-    tc_fence_after();
-#pragma unroll
-    for (int k = 0; k < ATT_D / 16; ++k)  // S = Q K^T -> cols [0,128)
-      tc_mma_f16(tmem, make_smem_desc(qa + k * 32, 16, 1024), make_smem_desc(ka + k * 32, 16, 1024), idesc, k > 0);
-    mbar_wait(&bar[1], 0);
-    tc_fence_after();
-#pragma unroll
-    for (int k = 0; k < ATT_D / 16; ++k)  // dP = dO V^T -> cols [128,256)
-      tc_mma_f16(tmem + 128, make_smem_desc(da + k * 32, 16, 1024), make_smem_desc(va + k * 32, 16, 1024), idesc,
-                 k > 0);
-    tc_commit(&bar[2]);
-  }
-
-  // delta_r = sum_d dO[r,d] * O[r,d]  (both halves of the row's threads compute it redundantly)
-  const int r = (warp & 3) * 32 + lane;  // TMEM lane == query row
-  const int half = warp >> 2;            // which 64 key columns this thread handles
-  float delta = 0.f, lse2 = 0.f;
-  if (r < L) {
-    const long long off = static_cast<long long>(row0 + r) * p.hidden + h * ATT_D;
-    const uint4* po = reinterpret_cast<const uint4*>(p.o + off);
-    const uint4* pd = reinterpret_cast<const uint4*>(p.d_o + off);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) delta += dot8(__ldg(po + i), __ldg(pd + i));
-    lse2 = p.lse[(static_cast<long long>(seq) * p.heads + h) * L + r] * LOG2E;
-  }
-  __syncwarp();
-  mbar_wait(&bar[2], 0);
-  tc_fence_after();
-  __syncwarp();
-
-  const uint32_t trow = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-  const float sl2 = p.scale * LOG2E;
-  uint4 ds_keep[8];  // this thread's 64 dS values, packed fp16, parked until P has been consumed
-#pragma unroll
-  for (int cc = 0; cc < 2; ++cc) {
-    const int c0 = half * 64 + cc * 32;
-    uint32_t s[32], d[32];
-    tmem_ld_32x32(trow + c0, s);
-    tmem_ld_32x32(trow + 128 + c0, d);
-    tc_wait_ld();
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      float pv[8], ds[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = c0 + g * 8 + j;
-        const bool ok = (r < L) && (c < L);
-        const float pe = ok ? exp2f(fmaf(__uint_as_float(s[g * 8 + j]), sl2, sBias[c]) - lse2) : 0.f;
-        pv[j] = pe;
-        ds[j] = ok ? pe * (__uint_as_float(d[g * 8 + j]) - delta) * p.scale : 0.f;
-      }
-      *reinterpret_cast<uint4*>(sP + swz_off(r, c0 + g * 8)) = pack8(pv);
-      ds_keep[cc * 4 + g] = pack8(ds);
-    }
-  }
-  fence_proxy_async();
-  tc_fence_before();
-  __syncthreads();
-
-  constexpr uint32_t idesc_tt = make_idesc_f16(ATT_T, ATT_D, 1, 1);
-  constexpr uint32_t idesc_nt = make_idesc_f16(ATT_T, ATT_D, 0, 1);
-  if (tid == 0) {
-    tc_fence_after();
-#pragma unroll
-    for (int k = 0; k < ATT_T / 16; ++k)  // dV[kv,d] = sum_q P[q,kv] dO[q,d] -> cols [0,64)
-      tc_mma_f16(tmem, make_smem_desc(pa + k * 2048, ATT_TILE_BYTES, 1024), make_smem_desc(da + k * 2048, 8192, 1024),
-                 idesc_tt, k > 0);
-    tc_commit(&bar[4]);
-  }
-  __syncwarp();
-  mbar_wait(&bar[4], 0);  // P has been read by the tensor core: its buffer may now take dS
-  tc_fence_after();
-  __syncwarp();
-#pragma unroll
-  for (int cc = 0; cc < 2; ++cc)
-#pragma unroll
-    for (int g = 0; g < 4; ++g)
-      *reinterpret_cast<uint4*>(sP + swz_off(r, half * 64 + cc * 32 + g * 8)) = ds_keep[cc * 4 + g];
-  fence_proxy_async();
-  tc_fence_before();
-  __syncthreads();
-
-  if (tid == 0) {
-    tc_fence_after();
-#pragma unroll
-    for (int k = 0; k < ATT_T / 16; ++k)  // dK[kv,d] = sum_q dS[q,kv] Q[q,d] -> cols [64,128)
-      tc_mma_f16(tmem + 64, make_smem_desc(pa + k * 2048, ATT_TILE_BYTES, 1024),
-                 make_smem_desc(qa + k * 2048, 8192, 1024), idesc_tt, k > 0);
-#pragma unroll
-    for (int k = 0; k < ATT_T / 16; ++k)  // dQ[q,d] = sum_kv dS[q,kv] K[kv,d] -> cols [128,192)
-      tc_mma_f16(tmem + 128, make_smem_desc(pa + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 16, 1024),
-                 make_smem_desc(ka + k * 2048, 8192, 1024), idesc_nt, k > 0);
-    tc_commit(&bar[3]);
-  }
-  __syncwarp();
-  mbar_wait(&bar[3], 0);
-  tc_fence_after();
-  __syncwarp();
-
-  // rows of dV / dK are key rows, rows of dQ are query rows -- all indexed by the TMEM lane r
-  __half* grow = p.dqkv + static_cast<long long>(row0 + r) * (3 * p.hidden) + h * ATT_D + half * 32;
-#pragma unroll 1
-  for (int t = 0; t < 3; ++t) {  // t: 0 = dV, 1 = dK, 2 = dQ
-    uint32_t v[32];
-    tmem_ld_32x32(trow + t * 64 + half * 32, v);
-    tc_wait_ld();
-    if (r < L) {
-      __half* dst = grow + (2 - t) * p.hidden;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        float e[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) e[j] = __uint_as_float(v[g * 8 + j]);
-        *reinterpret_cast<uint4*>(dst + g * 8) = pack8(e);
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
   if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int s = it & 1;
+        const int seq = item / p.heads, h = item % p.heads;
+        const int row0 = seq * L;
+        uint8_t* st = sStage + s * 4 * ATT_TILE_BYTES;
+        mbar_wait(&stage_empty[s], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&full_qk[s], 2 * ATT_TILE_BYTES);
+        tma_load_2d(st, &tma_qkv, &full_qk[s], h * ATT_D, row0);
+        tma_load_2d(st + ATT_TILE_BYTES, &tma_qkv, &full_qk[s], p.hidden + h * ATT_D, row0);
+        mbar_expect_tx(&full_vdo[s], 2 * ATT_TILE_BYTES);
+        tma_load_2d(st + 2 * ATT_TILE_BYTES, &tma_qkv, &full_vdo[s], 2 * p.hidden + h * ATT_D, row0);
+        tma_load_2d(st + 3 * ATT_TILE_BYTES, &tma_do, &full_vdo[s], h * ATT_D, row0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_f16(ATT_T, ATT_T, 0, 0);
+      constexpr uint32_t idesc_tt = make_idesc_f16(ATT_T, ATT_D, 1, 1);
+      constexpr uint32_t idesc_nt = make_idesc_f16(ATT_T, ATT_D, 0, 1);
+      const uint32_t pa = smem_u32(sP), dsa = smem_u32(sdS);
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int s = it & 1;
+        const uint32_t ph = it & 1, phs = (it >> 1) & 1;
+        const uint32_t qa = smem_u32(sStage + s * 4 * ATT_TILE_BYTES), ka = qa + ATT_TILE_BYTES,
+                       va = qa + 2 * ATT_TILE_BYTES, da = qa + 3 * ATT_TILE_BYTES;
+        mbar_wait(&full_qk[s], phs);
+        mbar_wait(sdp_empty, ph ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; ++k)  // S = Q K^T
+          tc_mma_f16(tmem, make_smem_desc(qa + k * 32, 16, 1024), make_smem_desc(ka + k * 32, 16, 1024), idesc_s, k > 0);
+        mbar_wait(&full_vdo[s], phs);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; ++k)  // dP = dO V^T
+          tc_mma_f16(tmem + 128, make_smem_desc(da + k * 32, 16, 1024), make_smem_desc(va + k * 32, 16, 1024), idesc_s,
+                     k > 0);
+        tc_commit(sdp_full);
+        mbar_wait(pds_full, ph);
+        mbar_wait(out_empty, ph ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < ATT_T / 16; ++k)  // dV[kv,d] = sum_q P[q,kv] dO[q,d]
+          tc_mma_f16(tmem + 256, make_smem_desc(pa + k * 2048, ATT_TILE_BYTES, 1024),
+                     make_smem_desc(da + k * 2048, 8192, 1024), idesc_tt, k > 0);
+#pragma unroll
+        for (int k = 0; k < ATT_T / 16; ++k)  // dK[kv,d] = sum_q dS[q,kv] Q[q,d]
+          tc_mma_f16(tmem + 320, make_smem_desc(dsa + k * 2048, ATT_TILE_BYTES, 1024),
+                     make_smem_desc(qa + k * 2048, 8192, 1024), idesc_tt, k > 0);
+#pragma unroll
+        for (int k = 0; k < ATT_T / 16; ++k)  // dQ[q,d] = sum_kv dS[q,kv] K[kv,d]
+          tc_mma_f16(tmem + 384, make_smem_desc(dsa + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 16, 1024),
+                     make_smem_desc(ka + k * 2048, 8192, 1024), idesc_nt, k > 0);
+        tc_commit(out_full);
+        tc_commit(&stage_empty[s]);  // Q K V dO of this stage (and P / dS) are consumed
+      }
+    }
+  } else {
+    // ===================== softmax / dS / epilogue threads =====================
+    const int cw = warp - 2;
+    const int quad = warp & 3;      // TMEM lane quadrant this warp may touch
+    const int half = cw >> 2;       // which 64 key columns (softmax) / 32 head-dim columns (epilogue)
+    const int r = quad * 32 + lane; // TMEM lane == query row (S, dP, dQ) == key row (dV, dK)
+    const int ctid = tid - 64;      // 0..255
+    const uint32_t trow = tmem + (static_cast<uint32_t>(quad * 32) << 16);
+    const float sl2 = p.scale * LOG2E;
+    auto load_bias = [&](int item, int buf) {
+      if (ctid < ATT_T) {
+        const int seq = item / p.heads;
+        float b = -INFINITY;
+        if (ctid < L) b = p.key_bias ? p.key_bias[static_cast<long long>(seq) * L + ctid] * LOG2E : 0.f;
+        sBias[buf * ATT_T + ctid] = b;
+      }
+    };
+    if (blockIdx.x < n_items) load_bias(blockIdx.x, 0);
+    named_bar_sync(1, 256);
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const uint32_t ph = it & 1;
+      const int seq = item / p.heads, h = item % p.heads;
+      const int row0 = seq * L;
+      const float* bias = sBias + (it & 1) * ATT_T;
+      float lse2 = 0.f;
+      if (r < L) lse2 = p.lse[(static_cast<long long>(seq) * p.heads + h) * L + r] * LOG2E;
+      if (item + static_cast<int>(gridDim.x) < n_items) load_bias(item + gridDim.x, (it + 1) & 1);
+      mbar_wait(sdp_full, ph);
+      tc_fence_after();
+      // ---- phase 1: P (fp32 in registers, fp16 to smem) and this half's share of delta
+      float pf[64];
+      float dpart = 0.f;
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c0 = half * 64 + cc * 32;
+        uint32_t sv[32], dv[32];
+        tmem_ld_32x32(trow + c0, sv);
+        tmem_ld_32x32(trow + 128 + c0, dv);
+        tc_wait_ld();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float pv[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int c = c0 + g * 8 + j;
+            const bool ok = (r < L) && (c < L);
+            const float pe = ok ? fast_ex2(fmaf(__uint_as_float(sv[g * 8 + j]), sl2, bias[c]) - lse2) : 0.f;
+            pv[j] = pe;
+            pf[cc * 32 + g * 8 + j] = pe;
+            dpart = fmaf(pe, __uint_as_float(dv[g * 8 + j]), dpart);
+          }
+          *reinterpret_cast<uint4*>(sP + swz_off(r, c0 + g * 8)) = pack8(pv);
+        }
+      }
+      sDelta[half * ATT_T + r] = dpart;
+      named_bar_sync(1, 256);
+      const float delta = sDelta[r] + sDelta[ATT_T + r];
+      // ---- phase 2: dS = P (dP - delta) scale
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c0 = half * 64 + cc * 32;
+        uint32_t dv[32];
+        tmem_ld_32x32(trow + 128 + c0, dv);
+        tc_wait_ld();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float ds[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            ds[j] = pf[cc * 32 + g * 8 + j] * (__uint_as_float(dv[g * 8 + j]) - delta) * p.scale;
+          *reinterpret_cast<uint4*>(sdS + swz_off(r, c0 + g * 8)) = pack8(ds);
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(sdp_empty);  // S / dP columns may take item i+1
+        mbar_arrive(pds_full);   // P / dS are in shared memory
+      }
+      // ---- epilogue: dV, dK, dQ rows -> packed fp16 dQKV, column sums -> QKV bias gradient
+      mbar_wait(out_full, ph);
+      tc_fence_after();
+      __half* grow = p.dqkv + static_cast<long long>(row0 + r) * (3 * p.hidden) + h * ATT_D + half * 32;
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {  // t: 0 = dV, 1 = dK, 2 = dQ
+        uint32_t v[32];
+        tmem_ld_32x32(trow + 256 + t * 64 + half * 32, v);
+        tc_wait_ld();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (r < L) {
+          __half* dst = grow + (2 - t) * p.hidden;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float e[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) e[j] = f[g * 8 + j];
+            *reinterpret_cast<uint4*>(dst + g * 8) = pack8(e);
+          }
+        }
+        if (p.dbias != nullptr) {
+          // rows beyond seq_len are exact zeros (their P / dS rows and columns were zeroed)
+          const float tot = warp_colsum32(f, lane);
+          atomicAdd(p.dbias + (2 - t) * p.hidden + h * ATT_D + half * 32 + lane, tot * p.dbias_scale);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(out_empty);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem, 256);
+    tmem_dealloc(tmem, 512);
   }
 }
 
@@ -838,6 +941,7 @@ int cdr_attn_bwd(const cdr_attn_args* a, void* stream) {
   }
   if (a->seq_len > ATT_T) {
     CDR_REQUIRE(a->dq_workspace != nullptr, "cdr_attn_bwd: seq_len > %d needs dq_workspace (fp32 [T, hidden])", ATT_T);
+    CDR_REQUIRE(a->dbias_qkv == nullptr, "cdr_attn_bwd: the fused QKV bias gradient needs seq_len <= %d", ATT_T);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int kv_tiles = (a->seq_len + ATT_T - 1) / ATT_T;
     CDR_CUDA(cudaMemsetAsync(a->dq_workspace, 0, sizeof(float) * static_cast<size_t>(T) * hidden, st));
@@ -849,7 +953,11 @@ int cdr_attn_bwd(const cdr_attn_args* a, void* stream) {
     CDR_LAUNCH_CHECK();
     return CDR_OK;
   }
-  fmha_bwd_kernel<<<a->n_seq * a->heads, 256, ATT_BWD_SMEM, static_cast<cudaStream_t>(stream)>>>(tq, td, p);
+  p.dbias = a->dbias_qkv;
+  p.dbias_scale = a->dbias_scale;
+  const int n_items = a->n_seq * a->heads;
+  const int grid = n_items < sm_count() ? n_items : sm_count();
+  fmha_bwd_kernel<<<grid, ATT_BWD_THREADS, ATT_BWD_SMEM, static_cast<cudaStream_t>(stream)>>>(tq, td, p, n_items);
   CDR_LAUNCH_CHECK();
   return CDR_OK;
 }

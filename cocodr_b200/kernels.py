@@ -183,13 +183,17 @@ def attn_fwd(qkv, key_bias, out, lse, *, n_seq, seq_len, heads, scale=0.125):
     _count(1)
 
 
-def attn_bwd(qkv, key_bias, out, lse, d_out, dqkv, *, n_seq, seq_len, heads, scale=0.125):
+def attn_bwd(qkv, key_bias, out, lse, d_out, dqkv, *, n_seq, seq_len, heads, scale=0.125, dbias=None, dbias_scale=1.0):
+    """dbias (optional fp32 [3*heads*64], seq_len <= 128): += dbias_scale * column sums of dqkv, fused."""
     _need_cuda(qkv, out, lse, d_out, dqkv)
     assert d_out.dtype == torch.float16 and dqkv.dtype == torch.float16 and d_out.is_contiguous()
     dq_ws = None
     if seq_len > 128:  # tiled backward: key tiles add their dQ shares in an fp32 scratch
         dq_ws = torch.empty(n_seq * seq_len, heads * 64, dtype=torch.float32, device=qkv.device)
     a = _attn_args(qkv, key_bias, out, lse, n_seq, seq_len, heads, scale, d_out, dqkv, dq_ws)
+    if dbias is not None:
+        assert dbias.dtype == torch.float32 and dbias.numel() == 3 * heads * 64
+        a.dbias_qkv, a.dbias_scale = dbias.data_ptr(), dbias_scale
     _run("cdr_attn_bwd", lambda: _lib_().cdr_attn_bwd(C.byref(a), stream_ptr()))
     _count(1 if seq_len <= 128 else 2)
 

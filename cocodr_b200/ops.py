@@ -240,7 +240,9 @@ class BertLayerFn(torch.autograd.Function):
         K.gemm(dy1, att, dwo, M=H, N=H, K=T, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0, alpha=inv)
         # ---- attention core
         dqkv = _f16(T, 3 * H, dev=dev)
-        K.attn_bwd(qkv, key_bias, att, lse, datt, dqkv, n_seq=n_seq, seq_len=L, heads=heads)
+        fused_db = L <= 128  # the one-tile backward also emits the QKV bias gradient (column sums of dQKV)
+        K.attn_bwd(qkv, key_bias, att, lse, datt, dqkv, n_seq=n_seq, seq_len=L, heads=heads,
+                   dbias=dbqkv if fused_db else None, dbias_scale=inv)
         # ---- QKV projection: dx = dQKV Wqkv + dy1 (residual)
         dx = None
         if ctx.needs_input_grad[0]:
@@ -248,7 +250,8 @@ class BertLayerFn(torch.autograd.Function):
             K.gemm(dqkv, wqkv, dx, M=T, N=H, K=3 * H, b_major=1, epilogue=K.EPI_BIAS_RESIDUAL, aux=dy1)
         K.gemm(dqkv, x, dwqkv, M=3 * H, N=H, K=T, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0,
                alpha=inv)
-        K.colsum(dqkv, dbqkv, rows=T, cols=3 * H, scale=inv)
+        if not fused_db:
+            K.colsum(dqkv, dbqkv, rows=T, cols=3 * H, scale=inv)
         if GRAD_SYNC is not None:
             GRAD_SYNC.submit(flat)
         return (dx, None, dwqkv[0:H], dbqkv[0:H], dwqkv[H:2 * H], dbqkv[H:2 * H], dwqkv[2 * H:], dbqkv[2 * H:], dwo,

@@ -128,6 +128,8 @@ typedef struct cdr_attn_args {
   float* dq_workspace;   /* bwd, seq_len > 128 only: fp32 [n_seq*seq_len, heads*64] scratch */
   int32_t n_seq, seq_len, heads, head_dim;
   float scale;
+  float dbias_scale;     /* bwd, seq_len <= 128: multiplies the column sums below */
+  float* dbias_qkv;      /* bwd, optional fp32 [3*heads*64]: += dbias_scale * column sums of dqkv (QKV bias gradient) */
 } cdr_attn_args;
 int cdr_attn_fwd(const cdr_attn_args* args, void* stream);
 int cdr_attn_bwd(const cdr_attn_args* args, void* stream);

@@ -46,10 +46,16 @@ def test_attention_fwd_bwd(n_seq, L, heads, masked):
 
     d_out = (torch.randn(T, H, generator=g)).half().cuda()
     dqkv = torch.zeros(T, 3 * H, dtype=torch.float16, device="cuda")
-    k.attn_bwd(qkv, bias, out, lse, d_out, dqkv, n_seq=n_seq, seq_len=L, heads=heads)
+    fused_db = L <= 128  # the one-tile backward can emit the QKV bias gradient (column sums of dQKV) as well
+    dbias = torch.ones(3 * H, dtype=torch.float32, device="cuda") if fused_db else None
+    k.attn_bwd(qkv, bias, out, lse, d_out, dqkv, n_seq=n_seq, seq_len=L, heads=heads, dbias=dbias, dbias_scale=0.5)
     torch.cuda.synchronize()
     (o_ref * d_out.float()).sum().backward()
     ref = qf.grad
+    if fused_db:
+        cs = 1.0 + 0.5 * ref.sum(0)
+        e = (dbias - cs).abs().max().item()
+        assert e <= 5e-3 * max(1.0, (0.5 * ref).abs().sum(0).max().item()), f"fused bias gradient err {e}"
     err = (dqkv.float() - ref).abs().max().item()
     assert err <= 1e-2 * ref.abs().max().item(), f"bwd max err {err} vs scale {ref.abs().max().item()}"
     for nm, sl in (("dq", slice(0, H)), ("dk", slice(H, 2 * H)), ("dv", slice(2 * H, 3 * H))):
