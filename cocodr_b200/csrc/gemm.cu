@@ -20,7 +20,7 @@ static bool use_2cta_default() {
 template <int BN, bool A_MN, bool B_MN, int EPI, int CG>
 static int launch_gemm_cg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
   auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI, CG>;
-  constexpr int smem = GemmSmem<BN, CG>::TOTAL;
+  constexpr int smem = GemmSmem<BN, CG, GEMM_EW<EPI>>::TOTAL;
   static bool configured = false;  // per-instantiation; attribute is sticky per device context
   if (!configured) {
     CDR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -31,7 +31,7 @@ static int launch_gemm_cg(const CUtensorMap& ta, const CUtensorMap& tb, const Ge
   const int grid = (items < workers ? items : workers) * CG;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.blockDim = dim3(GEMM_THREADS<EPI>);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -144,7 +144,7 @@ int gemm_run(const cdr_gemm_args& g, GemmParams p, cudaStream_t st) {
   else rc = make_tma_2d_f16(&ta, g.a, g.K, g.M, g.lda, GEMM_BK, GEMM_BM);
   if (rc != CDR_OK) return rc;
   if (b_mn) rc = make_tma_2d_f16(&tb, g.b, g.N, g.K, g.ldb, 64, GEMM_BK);
-  else rc = make_tma_2d_f16(&tb, g.b, g.K, g.N, g.ldb, GEMM_BK, BN / p.cta_group);
+  else rc = make_tma_2d_f16(&tb, g.b, g.K, p.b_rows_alloc > g.N ? p.b_rows_alloc : g.N, g.ldb, GEMM_BK, BN / p.cta_group);
   if (rc != CDR_OK) return rc;
 
   if (BN == 256) return dispatch_layout<256>(a_mn, b_mn, g.epilogue, ta, tb, p, st);

@@ -27,11 +27,16 @@ namespace cdr {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
+// Epilogue warps (a multiple of 4: one group per TMEM lane quadrant).  With the accumulators released early and
+// the aux operand prefetched, 8 warps beat 16 for the dense epilogues (32 KB less staging smem = one more TMA
+// stage); the scan filter is bound by the round trip of its slot-reserving atomics and wants 16.
 #ifndef CDR_GEMM_EPI_WARPS
 #define CDR_GEMM_EPI_WARPS 8
 #endif
-constexpr int GEMM_EPI_WARPS = CDR_GEMM_EPI_WARPS;  // 2 per TMEM lane quadrant: with the accumulators released early and the aux operand prefetched, 8 warps beat 16 (32 KB less staging smem = one more TMA stage)
-constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;  // 320
+template <int EPI>
+constexpr int GEMM_EW = (EPI == CDR_EPI_SCAN_FILTER) ? 16 : CDR_GEMM_EPI_WARPS;
+template <int EPI>
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EW<EPI>;
 
 struct GemmParams {
   int M, N, K;          // problem size (K = reduction length)
@@ -56,6 +61,7 @@ struct GemmParams {
   long long row_base;           // global doc index of row 0
   // debug overrides for descriptor probing (0 = default)
   int dbg_lbo, dbg_sbo;
+  long long b_rows_alloc;  // rows of B that physically exist (>= N; 0 = N): lets TMA boxes read zero padding instead of going out of bounds
   int dbg_flags;  // CDR_GEMM_DBG (environment): bit 0 = skip the epilogue math and stores (timing experiments only)
 };
 
@@ -65,14 +71,14 @@ int gemm_run(const cdr_gemm_args& g, GemmParams p, cudaStream_t st);
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cta_group::2) per 256 x BN tile -- each CTA stages
 // its own 128 rows of A and HALF of the B tile (BN/2 rows); the pair's UMMA reads both halves, so the
 // operand bytes pulled through L2 per MMA cycle drop by a third and the ring gets deeper.
-template <int BN, int CG = 1>
+template <int BN, int CG, int EW>
 struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_ROWS = BN / CG;
   static constexpr int B_BYTES = B_ROWS * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int STG_BYTES = GEMM_EPI_WARPS * 32 * 32 * 4;  // epilogue staging tiles
+  static constexpr int STG_BYTES = EW * 32 * 32 * 4;  // epilogue staging tiles
   static constexpr int BUDGET = 232448 - 1024 - BAR_BYTES - STG_BYTES;  // 227 KB per CTA
   static constexpr int STAGES = (BUDGET / STAGE_BYTES) > 8 ? 8 : (BUDGET / STAGE_BYTES);
   static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + STG_BYTES + 1024;  // +1024 alignment slack
@@ -176,6 +182,58 @@ __device__ __forceinline__ void gemm_epilogue_apply(const GemmParams& p, float (
   }
 }
 
+// Scan filter straight from the accumulator registers (thread = one document row, 32 query columns): nothing
+// dense is stored, so the chunk needs no transposition.  Admission is two-phase so that a warp pays ONE atomic
+// round trip per chunk instead of one per admitted score:
+//   reserve: per column j a ballot of the rows that pass threshold[j]; lane j owns column j and reserves
+//            popc(ballot) slots of that query's candidate buffer with a single atomicAdd;
+//   commit : every passing (row, column) writes its packed key at base[j] + (rank of the row in the ballot).
+// ws = 96 words of per-warp shared memory (thresholds | ballots | bases).
+struct FilterTicket {
+  uint32_t ballot;  // lane j: rows of this chunk admitted for column j
+  int base;         // lane j: first reserved slot
+};
+
+__device__ __forceinline__ FilterTicket gemm_filter_reserve(const GemmParams& p, const uint32_t (&acc)[32],
+                                                            uint32_t* ws, int lane, int m, int n0) {
+  const int q = n0 + lane;
+  ws[lane] = __float_as_uint(q < p.N ? __ldg(p.thresh + q) : INFINITY);
+  __syncwarp();
+  const bool row_ok = m < p.M;
+  FilterTicket t;
+  t.ballot = 0u;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const uint32_t b = __ballot_sync(0xffffffffu, row_ok && __uint_as_float(acc[j]) >= __uint_as_float(ws[j]));
+    if (lane == j) t.ballot = b;
+  }
+  t.base = 0;
+  if (t.ballot != 0u) t.base = atomicAdd(p.cand_count + q, __popc(t.ballot));
+  __syncwarp();
+  return t;
+}
+
+__device__ __forceinline__ void gemm_filter_commit(const GemmParams& p, const uint32_t (&acc)[32], uint32_t* ws,
+                                                   int lane, int m, int n0, const FilterTicket& t) {
+  ws[32 + lane] = t.ballot;
+  ws[64 + lane] = static_cast<uint32_t>(t.base);
+  __syncwarp();
+  const unsigned int doc = static_cast<unsigned int>(p.row_base + m);
+  const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const uint32_t b = ws[32 + j];  // warp-uniform
+    if (b != 0u) {
+      if ((b >> lane) & 1u) {
+        const int pos = static_cast<int>(ws[64 + j]) + __popc(b & lt);
+        if (pos < p.cand_cap)
+          p.cand[static_cast<long long>(n0 + j) * p.cand_cap + pos] = pack_score_doc(__uint_as_float(acc[j]), doc);
+      }
+    }
+  }
+  __syncwarp();
+}
+
 template <int EPI>
 constexpr bool GEMM_EPI_HAS_AUX = (EPI == CDR_EPI_BIAS_RESIDUAL || EPI == CDR_EPI_DGELU);
 
@@ -275,10 +333,11 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const u
 }
 
 template <int BN, bool A_MN, bool B_MN, int EPI, int CG>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS<EPI>, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                     const GemmParams p) {
-  using S = GemmSmem<BN, CG>;
+  using S = GemmSmem<BN, CG, GEMM_EW<EPI>>;
+  constexpr int GEMM_EPI_WARPS = GEMM_EW<EPI>;
   constexpr int STAGES = S::STAGES;
   constexpr int BNL = S::B_ROWS;  // B rows staged by this CTA
   extern __shared__ uint8_t smem_raw[];
@@ -468,7 +527,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             else mbar_arrive(&tmem_empty[acc]);
           }
         }
-        if (n0 + c0 * 32 < p.N && !(p.dbg_flags & 1)) {
+        if constexpr (EPI == CDR_EPI_SCAN_FILTER) {
+          // both chunks reserve first (their atomics are in flight together), then both commit
+          uint32_t* fws = reinterpret_cast<uint32_t*>(stg);
+          const bool ok0 = n0 + c0 * 32 < p.N, ok1 = (CPW >= 2) && (n0 + c1 * 32 < p.N);
+          FilterTicket t0{}, t1{};
+          if (ok0) t0 = gemm_filter_reserve(p, r0, fws, lane, mb + lane, n0 + c0 * 32);
+          if (ok1) t1 = gemm_filter_reserve(p, r1, fws + 96, lane, mb + lane, n0 + c1 * 32);
+          if (ok0) gemm_filter_commit(p, r0, fws, lane, mb + lane, n0 + c0 * 32, t0);
+          if (ok1) gemm_filter_commit(p, r1, fws + 96, lane, mb + lane, n0 + c1 * 32, t1);
+        } else if (n0 + c0 * 32 < p.N && !(p.dbg_flags & 1)) {
           gemm_epilogue_chunk<EPI>(p, r0, stg, lane, mb, n0 + c0 * 32, aux[b]);
           if constexpr (CPW >= 2) {
             if (n0 + c1 * 32 < p.N) gemm_epilogue_chunk<EPI>(p, r1, stg, lane, mb, n0 + c1 * 32, aux[b + 1 < CPW ? b + 1 : b]);

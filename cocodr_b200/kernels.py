@@ -287,8 +287,8 @@ def gram_f32(x, gram):
     _count(1)
 
 
-def scan_workspace_bytes(n_docs, n_q, k):
-    return int(_lib_().cdr_scan_workspace_bytes(_i64(n_docs), _i32(n_q), _i32(k)))
+def scan_workspace_bytes(n_docs, n_q, k, dim=768):
+    return int(_lib_().cdr_scan_workspace_bytes(_i64(n_docs), _i32(n_q), _i32(k), _i32(dim)))
 
 
 def scan_exhaustive_docs(k):

@@ -37,7 +37,7 @@ def _scan_once(Q, P, k, doc_base):
     n_q = Q.shape[0]
     D = torch.empty(n_q, k, dtype=torch.float32, device=Q.device)
     I = torch.empty(n_q, k, dtype=torch.int64, device=Q.device)
-    ws = torch.empty(K.scan_workspace_bytes(P.shape[0], n_q, k), dtype=torch.uint8, device=Q.device)
+    ws = torch.empty(K.scan_workspace_bytes(P.shape[0], n_q, k, P.shape[1]), dtype=torch.uint8, device=Q.device)
     status = torch.zeros(1, dtype=torch.int32, device=Q.device)
     K.scan_topk(P, Q, D, I, ws, status, k=k, doc_base=doc_base)
     return D, I, status
@@ -50,6 +50,28 @@ def merge_topk(D, I, k):
     outI = torch.empty(D.shape[0], k, dtype=torch.int64, device=D.device)
     K.topk_merge(D, I, outD, outI, k=k)
     return outD, outI
+
+
+def search_async(Q, P, k, doc_base=0):
+    """One sampled-threshold scan without the host-side status check: returns (D, I, status) where ``status`` is a
+    device int32[1]; the results are valid iff it is 0 (``check_status`` / ``search`` handle the other case).
+    Lets a caller keep several searches in flight and pay one synchronisation for all of them."""
+    if not (torch.is_tensor(Q) and Q.is_cuda and torch.is_tensor(P) and P.is_cuda):
+        raise RuntimeError("cocodr_b200.scan.search needs CUDA tensors (no CPU fallback)")
+    Q, P = _as_f16_cuda(Q).contiguous(), _as_f16_cuda(P)
+    if P.stride(1) != 1:
+        P = P.contiguous()
+    return _scan_once(Q, P, min(k, P.shape[0]), doc_base)
+
+
+def check_status(results, Q, P, k, doc_base=0):
+    """Resolve a list of ``search_async`` results: one host sync; any search whose status is non-zero is redone on
+    the guaranteed (exhaustive, chunked) path."""
+    flags = torch.cat([r[2] for r in results]).cpu().tolist()
+    out = []
+    for (D, I, _), bad in zip(results, flags):
+        out.append(search(Q, P, k, doc_base=doc_base, force_exhaustive=True) if bad else (D, I))
+    return out
 
 
 def search(Q, P, k, doc_base=0, force_exhaustive=False):

@@ -210,7 +210,7 @@ typedef struct cdr_scan_args {
   int32_t n_q, dim, k;
   int32_t reserved;
 } cdr_scan_args;
-size_t cdr_scan_workspace_bytes(int64_t n_docs, int32_t n_q, int32_t k);
+size_t cdr_scan_workspace_bytes(int64_t n_docs, int32_t n_q, int32_t k, int32_t dim);
 /* largest n_docs for which the scan admits every document (no sampling; cannot under/overflow) */
 int64_t cdr_scan_exhaustive_docs(int32_t k);
 int cdr_scan_topk(const cdr_scan_args* args, void* stream);

@@ -61,3 +61,20 @@ def test_scan_edge_cases():
     assert I.shape == (3, 40) and (I.cpu().numpy() == Ir).all()
     with pytest.raises(RuntimeError):
         scan.search(Q, P, 10)  # CPU tensors: no fallback
+
+
+@pytest.mark.parametrize("n_in,k", [(7, 5), (1000, 100), (1500, 1000), (3000, 1000), (8000, 1000), (12000, 2000)])
+def test_topk_merge_register_sort_sizes(n_in, k):
+    """cdr_topk_merge across every keys-per-thread variant of the block sort, with ties and empty slots."""
+    from cocodr_b200 import scan
+    g = torch.Generator().manual_seed(n_in)
+    D = torch.randint(-50, 50, (5, n_in), generator=g).float() / 8.0  # many ties -> id tie-break matters
+    I = torch.stack([torch.randperm(4 * n_in, generator=g)[:n_in] for _ in range(5)]).long()
+    I[:, ::7] = -1  # empty slots
+    Dm, Im = scan.merge_topk(D.cuda(), I.cuda(), k)
+    for r in range(5):
+        valid = I[r] >= 0
+        d, i = D[r][valid], I[r][valid]
+        order = sorted(range(len(d)), key=lambda t: (-d[t].item(), i[t].item()))[:k]
+        exp_i = [i[t].item() for t in order] + [-1] * (k - len(order))
+        assert Im[r].cpu().tolist() == exp_i
