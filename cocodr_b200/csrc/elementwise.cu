@@ -360,6 +360,273 @@ ln_bwd_cols_kernel(const __half* __restrict__ dy, const __half* __restrict__ x, 
   reduce_emit(s3, dcol, true);
 }
 
+// ------------------------------------------------------------------------------------------ staged, persistent
+// Bandwidth-shaped LayerNorm kernels.  A persistent block streams tiles of LNS_ROWS whole rows through a ring of
+// shared-memory stages filled by 1-D bulk copies (cp.async.bulk + mbarrier: the rows of a tile are contiguous in
+// global memory, so one copy per tensor per tile), which keeps ~50-70 KB per block in flight independent of
+// occupancy.  Each row is read from HBM exactly once:
+//   forward : warp per row -> statistics, normalise, store.
+//   backward: phase A, warp per row -> dx and the per-row scalars; phase B, thread per 8 columns over the rows of
+//             the SAME staged tile -> dgamma / dbeta / bias-gradient partial sums kept in registers across all
+//             tiles of the block, one round of atomics per block at the end.
+constexpr int LNS_ROWS = 8;      // rows per tile == warps per block
+constexpr int LNS_THREADS = 256;
+constexpr int LNS_STAGES = 3;
+
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(LNS_THREADS, 2)
+ln_fwd_staged_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     __half* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                     float* __restrict__ cls_out, int rows, int hidden, int seq_len, float eps) {
+  extern __shared__ __align__(128) uint8_t lns_smem[];
+  __shared__ uint64_t full[LNS_STAGES];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nvec = hidden >> 3;
+  const uint32_t row_bytes = static_cast<uint32_t>(hidden) * 2u;
+  const uint32_t tile_bytes = row_bytes * LNS_ROWS;
+  const int n_tiles = (rows + LNS_ROWS - 1) / LNS_ROWS;
+  if (tid == 0) {
+    for (int i = 0; i < LNS_STAGES; ++i) mbar_init(&full[i], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  auto issue = [&](int tile, int stage) {
+    const int r0 = tile * LNS_ROWS;
+    const uint32_t bytes = static_cast<uint32_t>(min(LNS_ROWS, rows - r0)) * row_bytes;
+    mbar_expect_tx(&full[stage], bytes);
+    bulk_load(lns_smem + stage * tile_bytes, x + static_cast<long long>(r0) * hidden, bytes, &full[stage]);
+  };
+  if (tid == 0)
+    for (int i = 0; i < LNS_STAGES; ++i) {
+      const int t = blockIdx.x + i * gridDim.x;
+      if (t < n_tiles) issue(t, i);
+    }
+  float g[VPL][8], b[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+    if (lane + 32 * i < nvec) {
+      load8_f(gamma + 8 * (lane + 32 * i), g[i]);
+      load8_f(beta + 8 * (lane + 32 * i), b[i]);
+    }
+  int it = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int stage = it % LNS_STAGES;
+    mbar_wait(&full[stage], (it / LNS_STAGES) & 1);
+    const int row = tile * LNS_ROWS + warp;
+    if (row < rows) {
+      const __half* xs = reinterpret_cast<const __half*>(lns_smem + stage * tile_bytes) + warp * hidden;
+      float v[VPL][8];
+#pragma unroll
+      for (int i = 0; i < VPL; ++i)
+        if (lane + 32 * i < nvec) load8_h(xs + 8 * (lane + 32 * i), v[i]);
+      float mean, rstd;
+      row_stats<VPL>(v, nvec, lane, hidden, eps, mean, rstd);
+      if (lane == 0) {
+        if (mean_out) mean_out[row] = mean;
+        if (rstd_out) rstd_out[row] = rstd;
+      }
+      const bool is_cls = cls_out != nullptr && (row % seq_len) == 0;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i)
+        if (lane + 32 * i < nvec) {
+          const int c = 8 * (lane + 32 * i);
+          float o[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] = (v[i][k] - mean) * rstd * g[i][k] + b[i][k];
+          store8_h(y + static_cast<long long>(row) * hidden + c, o);
+          if (is_cls) store8_f(cls_out + static_cast<long long>(row / seq_len) * hidden + c, o);
+        }
+    }
+    __syncthreads();  // every warp is done with this stage
+    if (tid == 0) {
+      const int nt = tile + LNS_STAGES * gridDim.x;
+      if (nt < n_tiles) issue(nt, stage);
+    }
+  }
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(LNS_THREADS, 2)
+ln_bwd_staged_kernel(const __half* __restrict__ dy, const __half* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ mean_in, const float* __restrict__ rstd_in, __half* __restrict__ dx,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dcol, int rows,
+                     int hidden, float out_scale) {
+  extern __shared__ __align__(128) uint8_t lns_smem[];  // [stage][dy tile | x tile]
+  __shared__ uint64_t full[LNS_STAGES];
+  __shared__ float4 rowstat[LNS_ROWS];  // mean, rstd, rstd*c1, rstd*c2 of the rows of the current tile
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nvec = hidden >> 3;
+  const uint32_t row_bytes = static_cast<uint32_t>(hidden) * 2u;
+  const uint32_t tile_bytes = row_bytes * LNS_ROWS;
+  const int n_tiles = (rows + LNS_ROWS - 1) / LNS_ROWS;
+  if (tid == 0) {
+    for (int i = 0; i < LNS_STAGES; ++i) mbar_init(&full[i], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  auto issue = [&](int tile, int stage) {
+    const int r0 = tile * LNS_ROWS;
+    const uint32_t bytes = static_cast<uint32_t>(min(LNS_ROWS, rows - r0)) * row_bytes;
+    uint8_t* dst = lns_smem + stage * 2 * tile_bytes;
+    mbar_expect_tx(&full[stage], 2 * bytes);
+    bulk_load(dst, dy + static_cast<long long>(r0) * hidden, bytes, &full[stage]);
+    bulk_load(dst + tile_bytes, x + static_cast<long long>(r0) * hidden, bytes, &full[stage]);
+  };
+  if (tid == 0)
+    for (int i = 0; i < LNS_STAGES; ++i) {
+      const int t = blockIdx.x + i * gridDim.x;
+      if (t < n_tiles) issue(t, i);
+    }
+  float g[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+    if (lane + 32 * i < nvec) load8_f(gamma + 8 * (lane + 32 * i), g[i]);
+  // phase-B ownership: thread -> 8 columns (cgp) of the rows [rh * 4, rh * 4 + 4) of each tile
+  const int cgp = tid % 128, rh = tid / 128;
+  const bool colthread = cgp < nvec;
+  float a_dg[8], a_db[8], a_s3[8], a_s4[8], a_c = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a_dg[k] = a_db[k] = a_s3[k] = a_s4[k] = 0.f;
+
+  // per-row statistics of the NEXT tile are fetched one iteration ahead (their global latency would otherwise
+  // sit on the critical path of every tile)
+  float mean_nx = 0.f, rstd_nx = 0.f;
+  if (blockIdx.x * LNS_ROWS + warp < rows) {
+    mean_nx = mean_in[blockIdx.x * LNS_ROWS + warp];
+    rstd_nx = rstd_in[blockIdx.x * LNS_ROWS + warp];
+  }
+  int it = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int stage = it % LNS_STAGES;
+    const float mean = mean_nx, rstd = rstd_nx;
+    {
+      const long long nrow = static_cast<long long>(tile + gridDim.x) * LNS_ROWS + warp;
+      if (nrow < rows) {
+        mean_nx = mean_in[nrow];
+        rstd_nx = rstd_in[nrow];
+      }
+    }
+    mbar_wait(&full[stage], (it / LNS_STAGES) & 1);
+    const __half* dys = reinterpret_cast<const __half*>(lns_smem + stage * 2 * tile_bytes);
+    const __half* xs = reinterpret_cast<const __half*>(lns_smem + stage * 2 * tile_bytes + tile_bytes);
+    const int r0 = tile * LNS_ROWS;
+    {  // ---- phase A: one row per warp
+      const int row = r0 + warp;
+      if (row < rows) {
+        float xh[VPL][8], gy[VPL][8];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i)
+          if (lane + 32 * i < nvec) {
+            float xv[8], d[8];
+            load8_h(xs + warp * hidden + 8 * (lane + 32 * i), xv);
+            load8_h(dys + warp * hidden + 8 * (lane + 32 * i), d);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              xh[i][k] = (xv[k] - mean) * rstd;
+              gy[i][k] = d[k] * g[i][k];
+              s1 += gy[i][k];
+              s2 += gy[i][k] * xh[i][k];
+            }
+          }
+        const float c1 = warp_sum(s1) / hidden;
+        const float c2 = warp_sum(s2) / hidden;
+        if (lane == 0) rowstat[warp] = make_float4(mean, rstd, rstd * c1, rstd * c2);
+#pragma unroll
+        for (int i = 0; i < VPL; ++i)
+          if (lane + 32 * i < nvec) {
+            float o[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = rstd * (gy[i][k] - c1 - xh[i][k] * c2);
+            store8_h(dx + static_cast<long long>(row) * hidden + 8 * (lane + 32 * i), o);
+          }
+      } else if (lane == 0) {
+        rowstat[warp] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    __syncthreads();
+    if (colthread) {  // ---- phase B: column partial sums from the same staged tile
+#pragma unroll
+      for (int rr = 0; rr < LNS_ROWS / 2; ++rr) {
+        const int r = rh * (LNS_ROWS / 2) + rr;
+        if (r0 + r < rows) {
+          const float4 st = rowstat[r];
+          float d[8], xv[8];
+          load8_h(dys + r * hidden + 8 * cgp, d);
+          load8_h(xs + r * hidden + 8 * cgp, xv);
+          a_c += st.z;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float xh = (xv[k] - st.x) * st.y;
+            a_dg[k] = fmaf(d[k], xh, a_dg[k]);
+            a_db[k] += d[k];
+            a_s3[k] = fmaf(st.y, d[k], a_s3[k]);
+            a_s4[k] = fmaf(st.w, xh, a_s4[k]);
+          }
+        }
+      }
+    }
+    __syncthreads();  // stage and rowstat are free
+    if (tid == 0) {
+      const int nt = tile + LNS_STAGES * gridDim.x;
+      if (nt < n_tiles) issue(nt, stage);
+    }
+  }
+  // ---- block totals: the two row halves meet in shared memory, then one atomic per column and tensor
+  float* red = reinterpret_cast<float*>(lns_smem);  // all bulk copies have been consumed
+  __shared__ float red_c[2];
+  __syncthreads();
+  if (cgp == 0) red_c[rh] = a_c;
+  if (colthread && rh == 1) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      red[(0 * nvec + cgp) * 8 + k] = a_dg[k];
+      red[(1 * nvec + cgp) * 8 + k] = a_db[k];
+      red[(2 * nvec + cgp) * 8 + k] = a_s3[k];
+      red[(3 * nvec + cgp) * 8 + k] = a_s4[k];
+    }
+  }
+  __syncthreads();
+  if (colthread && rh == 0) {
+    const float ctot = red_c[0] + red_c[1];
+    float gg[8], o[8];
+    load8_f(gamma + 8 * cgp, gg);
+    if (dgamma != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = (a_dg[k] + red[(0 * nvec + cgp) * 8 + k]) * out_scale;
+      atomic_add8(dgamma + 8 * cgp, o);
+    }
+    if (dbeta != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = (a_db[k] + red[(1 * nvec + cgp) * 8 + k]) * out_scale;
+      atomic_add8(dbeta + 8 * cgp, o);
+    }
+    if (dcol != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        o[k] = (gg[k] * (a_s3[k] + red[(2 * nvec + cgp) * 8 + k]) - (a_s4[k] + red[(3 * nvec + cgp) * 8 + k]) - ctot) *
+               out_scale;
+      atomic_add8(dcol + 8 * cgp, o);
+    }
+  }
+}
+
+static int lns_grid(int rows, size_t smem_per_block) {
+  const int n_tiles = (rows + LNS_ROWS - 1) / LNS_ROWS;
+  int per_sm = static_cast<int>((200 * 1024) / (smem_per_block + 1024));
+  if (per_sm > 2) per_sm = 2;  // __launch_bounds__(256, 2): two resident blocks per SM
+  if (per_sm < 1) per_sm = 1;
+  const int g = sm_count() * per_sm;
+  return n_tiles < g ? n_tiles : g;
+}
+
 // out[c] += scale * sum_r x[r, c]      (fp16 in, fp32 accumulate; bias gradients)
 __global__ void __launch_bounds__(256)
 colsum_kernel(const __half* __restrict__ x, float* __restrict__ out, int rows, int cols, long long ld, float scale,
@@ -502,6 +769,31 @@ int cdr_ln_fwd(const void* x, const float* gamma, const float* beta, void* y, fl
   if (int rc = check_hidden(hidden)) return rc;
   CDR_REQUIRE(x && gamma && beta && y, "cdr_ln_fwd: null pointer");
   if (n_seq <= 0 || seq_len <= 0) return CDR_OK;
+  if (hidden <= 1024 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const int rows = n_seq * seq_len;
+    const size_t smem = static_cast<size_t>(LNS_STAGES) * LNS_ROWS * hidden * 2;
+    const int vpl = (hidden / 8 + 31) / 32;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid = lns_grid(rows, smem);
+#define LNS_FWD(V)                                                                                                   \
+  do {                                                                                                               \
+    static bool cfg = false;                                                                                         \
+    if (!cfg) {                                                                                                      \
+      CDR_CUDA(cudaFuncSetAttribute(ln_fwd_staged_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); \
+      cfg = true;                                                                                                    \
+    }                                                                                                                \
+    ln_fwd_staged_kernel<V><<<grid, LNS_THREADS, smem, st>>>(static_cast<const __half*>(x), gamma, beta,              \
+                                                            static_cast<__half*>(y), mean, rstd, cls_out, rows,       \
+                                                            hidden, seq_len, eps);                                   \
+  } while (0)
+    if (vpl <= 1) LNS_FWD(1);
+    else if (vpl <= 2) LNS_FWD(2);
+    else if (vpl <= 3) LNS_FWD(3);
+    else LNS_FWD(4);
+#undef LNS_FWD
+    CDR_LAUNCH_CHECK();
+    return CDR_OK;
+  }
   return launch_ln_fwd<0>(static_cast<const __half*>(x), nullptr, nullptr, nullptr, nullptr, gamma, beta,
                           static_cast<__half*>(y), mean, rstd, cls_out, n_seq * seq_len, hidden, seq_len, 0, eps,
                           static_cast<cudaStream_t>(stream));
@@ -513,6 +805,34 @@ int cdr_ln_bwd(const void* dy, const float* dy_cls, const void* x, const float* 
   if (int rc = check_hidden(hidden)) return rc;
   CDR_REQUIRE((dy || dy_cls) && x && gamma && mean && rstd && dx, "cdr_ln_bwd: null pointer");
   if (n_seq <= 0 || seq_len <= 0) return CDR_OK;
+  if (dy != nullptr && dy_cls == nullptr && hidden <= 1024 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(dy) & 15) == 0) {
+    // one staged pass: every row of dy and x is read from HBM once (see ln_bwd_staged_kernel)
+    const int rows = n_seq * seq_len;
+    const size_t smem = static_cast<size_t>(LNS_STAGES) * 2 * LNS_ROWS * hidden * 2;
+    const int vpl = (hidden / 8 + 31) / 32;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid = lns_grid(rows, smem);
+#define LNS_BWD(V)                                                                                                   \
+  do {                                                                                                               \
+    static bool cfg = false;                                                                                         \
+    if (!cfg) {                                                                                                      \
+      CDR_CUDA(cudaFuncSetAttribute(ln_bwd_staged_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024)); \
+      cfg = true;                                                                                                    \
+    }                                                                                                                \
+    ln_bwd_staged_kernel<V><<<grid, LNS_THREADS, smem, st>>>(static_cast<const __half*>(dy),                          \
+                                                            static_cast<const __half*>(x), gamma, mean, rstd,         \
+                                                            static_cast<__half*>(dx), dgamma, dbeta, dbias, rows,     \
+                                                            hidden, out_scale);                                      \
+  } while (0)
+    if (vpl <= 1) LNS_BWD(1);
+    else if (vpl <= 2) LNS_BWD(2);
+    else if (vpl <= 3) LNS_BWD(3);
+    else LNS_BWD(4);
+#undef LNS_BWD
+    CDR_LAUNCH_CHECK();
+    return CDR_OK;
+  }
   if (row_ws != nullptr && dy != nullptr && dy_cls == nullptr) {
     // split path: dx pass + column-sum pass
     cudaStream_t st = static_cast<cudaStream_t>(stream);

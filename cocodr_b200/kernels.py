@@ -127,7 +127,8 @@ def ln_bwd(dy, dy_cls, x, gamma, mean, rstd, dx, dgamma, dbeta, dbias, *, n_seq,
     _run("cdr_ln_bwd", lambda: _lib_().cdr_ln_bwd(_p(dy), _p(dy_cls), _p(x), _p(gamma), _p(mean), _p(rstd), _p(dx), _p(dgamma), _p(dbeta),
                              _p(dbias), _p(row_ws), _i32(n_seq), _i32(seq_len), _i32(hidden), _f32(in_scale),
                              _f32(out_scale), stream_ptr()))
-    _count(2 if (row_ws is not None and dy is not None and dy_cls is None) else 1)
+    staged = dy is not None and dy_cls is None and hidden <= 1024  # one staged pass (elementwise.cu)
+    _count(2 if (not staged and row_ws is not None and dy is not None and dy_cls is None) else 1)
 
 
 def colsum(x, out, *, rows, cols, ld=None, scale=1.0):

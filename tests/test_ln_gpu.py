@@ -6,7 +6,7 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("n_seq,L,H", [(3, 32, 128), (4, 128, 768), (2, 64, 1024)])
+@pytest.mark.parametrize("n_seq,L,H", [(3, 32, 128), (4, 128, 768), (2, 64, 1024), (3, 7, 768), (2, 16, 1536)])
 def test_ln_fwd_bwd(n_seq, L, H):
     from cocodr_b200 import kernels as k
     g = torch.Generator().manual_seed(H + L)
@@ -41,9 +41,11 @@ def test_ln_fwd_bwd(n_seq, L, H):
     assert (dbias - ref).abs().max().item() < 5e-3 * ref.abs().max().item() + 2e-2
 
 
-@pytest.mark.parametrize("n_seq,L,H", [(3, 32, 128), (16, 128, 768), (2, 64, 1024), (5, 8, 64)])
+@pytest.mark.parametrize("n_seq,L,H", [(3, 32, 128), (16, 128, 768), (2, 64, 1024), (5, 8, 64), (3, 7, 768), (1, 1, 768),
+                                       (2, 16, 1536), (64, 128, 768)])
 def test_ln_bwd_split_path(n_seq, L, H):
-    """row_ws given and no fp32 CLS gradient -> two-pass backward (dx pass + column-sum pass)."""
+    """fp16 dy only (no fp32 CLS gradient): the staged single-pass backward for hidden <= 1024 (ragged last tile
+    included), the two-pass backward (dx pass + column-sum pass) above that."""
     from cocodr_b200 import kernels as k
     g = torch.Generator().manual_seed(H + L + 1)
     T = n_seq * L
