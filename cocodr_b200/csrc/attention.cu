@@ -73,7 +73,7 @@ constexpr int ATT_FWD_SMEM = 3 * ATT_TILE_BYTES + 512 + 64 + 1024;
 __global__ void __launch_bounds__(128, 4)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* sQ = smem;
   uint8_t* sK = smem + ATT_TILE_BYTES;
   uint8_t* sV = smem + 2 * ATT_TILE_BYTES;
@@ -216,8 +216,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttParams p) 
 // softmax threads overlap; nothing but the mbarriers below synchronises them.
 // TMEM columns: S [0,128) dP [128,256) dV [256,320) dK [320,384) dQ [384,448).
 // smem: 2 stages x (Q K V dO) = 128 KB | P 32 KB | dS 32 KB | key bias x2 | delta halves | barriers.
-constexpr int ATT_BWD_THREADS = 320;
-constexpr int ATT_BWD_SMEM = 12 * ATT_TILE_BYTES + 2 * 512 + 2 * 512 + 256 + 1024;
+constexpr int ATT_BWD_THREADS = 448;  // producer, MMA issuer, 8 softmax warps, 4 epilogue warps
+constexpr int ATT_BWD_SMEM = 12 * ATT_TILE_BYTES + 8 * 64 * 4 + 2 * 512 + 256 + 1024;
 
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
@@ -254,25 +254,38 @@ __device__ __forceinline__ float warp_colsum32(const float (&v)[32], int lane) {
   return (up ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, up ? a2[0] : a2[1], 1);
 }
 
+// Backward, seq_len <= 128.  Persistent and warp-specialised: one CTA per SM walks (sequence, head) items.
+//   warp 0        : TMA producer -- Q K V dO of item i+1 land in the other smem stage while item i computes
+//   warp 1        : tcgen05.mma issuer (one thread) + TMEM owner
+//   warps 2..9    : softmax threads; thread = (TMEM lane r = query row, half of the 128 key columns):
+//                   P = exp2(S - lse) -> smem;  delta_r = sum_j P dP (exact: the whole row is in one tile; the
+//                   two half-row partials meet through a 64-thread named barrier);  dS = P (dP - delta) scale
+//   warps 10..13  : epilogue threads; thread = key/query row r: dV, dK, dQ rows -> packed fp16 dQKV and the
+//                   QKV bias gradient (column sums in fp32 straight from the accumulators)
+// so that softmax(i+1), the epilogue of item i, the MMAs and the loads all overlap; only mbarriers connect them.
+// MMA order per item: S, dP | dV (as soon as P is in smem) | dK, dQ (once dS is).
+// TMEM columns: S [0,128) dP [128,256) dV [256,320) dK [320,384) dQ [384,448).
+// smem: 2 stages x (Q K V dO) = 128 KB | P 32 KB | dS 32 KB | per-warp key bias | delta halves | barriers.
 __global__ void __launch_bounds__(ATT_BWD_THREADS, 1)
 fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do,
                 const AttParams p, const int n_items) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* sStage = smem;                         // [2][Q K V dO]
   uint8_t* sP = smem + 8 * ATT_TILE_BYTES;        // two [128][64] chunks
   uint8_t* sdS = smem + 10 * ATT_TILE_BYTES;
-  float* sBias = reinterpret_cast<float*>(smem + 12 * ATT_TILE_BYTES);            // [2][128]
-  float* sDelta = reinterpret_cast<float*>(smem + 12 * ATT_TILE_BYTES + 1024);    // [2][128]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 12 * ATT_TILE_BYTES + 2048);
+  float* sBiasW = reinterpret_cast<float*>(smem + 12 * ATT_TILE_BYTES);                  // [8 warps][64]
+  float* sDelta = reinterpret_cast<float*>(smem + 12 * ATT_TILE_BYTES + 8 * 64 * 4);     // [2][128]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 12 * ATT_TILE_BYTES + 8 * 64 * 4 + 1024);
   uint64_t* full_qk = bar;          // [2] TMA -> MMA
   uint64_t* full_vdo = bar + 2;     // [2]
   uint64_t* stage_empty = bar + 4;  // [2] MMA -> TMA
-  uint64_t* sdp_full = bar + 6;     // MMA -> compute
-  uint64_t* sdp_empty = bar + 7;    // compute -> MMA (8 warps)
-  uint64_t* pds_full = bar + 8;     // compute -> MMA (8 warps): P and dS are in smem
-  uint64_t* out_full = bar + 9;     // MMA -> compute
-  uint64_t* out_empty = bar + 10;   // compute -> MMA (8 warps)
+  uint64_t* sdp_full = bar + 6;     // MMA -> softmax
+  uint64_t* sdp_empty = bar + 7;    // softmax -> MMA (8 warps): S / dP have been read
+  uint64_t* p_full = bar + 8;       // softmax -> MMA (8 warps): P is in smem
+  uint64_t* ds_full = bar + 9;      // softmax -> MMA (8 warps): dS is in smem
+  uint64_t* out_full = bar + 10;    // MMA -> epilogue
+  uint64_t* out_empty = bar + 11;   // epilogue -> MMA (4 warps)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 12);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -285,9 +298,10 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
     for (int i = 0; i < 6; ++i) mbar_init(&bar[i], 1);
     mbar_init(sdp_full, 1);
     mbar_init(sdp_empty, 8);
-    mbar_init(pds_full, 8);
+    mbar_init(p_full, 8);
+    mbar_init(ds_full, 8);
     mbar_init(out_full, 1);
-    mbar_init(out_empty, 8);
+    mbar_init(out_empty, 4);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -343,13 +357,15 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
           tc_mma_f16(tmem + 128, make_smem_desc(da + k * 32, 16, 1024), make_smem_desc(va + k * 32, 16, 1024), idesc_s,
                      k > 0);
         tc_commit(sdp_full);
-        mbar_wait(pds_full, ph);
+        mbar_wait(p_full, ph);
         mbar_wait(out_empty, ph ^ 1);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < ATT_T / 16; ++k)  // dV[kv,d] = sum_q P[q,kv] dO[q,d]
           tc_mma_f16(tmem + 256, make_smem_desc(pa + k * 2048, ATT_TILE_BYTES, 1024),
                      make_smem_desc(da + k * 2048, 8192, 1024), idesc_tt, k > 0);
+        mbar_wait(ds_full, ph);
+        tc_fence_after();
 #pragma unroll
         for (int k = 0; k < ATT_T / 16; ++k)  // dK[kv,d] = sum_q dS[q,kv] Q[q,d]
           tc_mma_f16(tmem + 320, make_smem_desc(dsa + k * 2048, ATT_TILE_BYTES, 1024),
@@ -362,34 +378,43 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
         tc_commit(&stage_empty[s]);  // Q K V dO of this stage (and P / dS) are consumed
       }
     }
-  } else {
-    // ===================== softmax / dS / epilogue threads =====================
-    const int cw = warp - 2;
+  } else if (warp < 10) {
+    // ===================== softmax / dS threads =====================
+    const int sw = warp - 2;        // 0..7
     const int quad = warp & 3;      // TMEM lane quadrant this warp may touch
-    const int half = cw >> 2;       // which 64 key columns (softmax) / 32 head-dim columns (epilogue)
-    const int r = quad * 32 + lane; // TMEM lane == query row (S, dP, dQ) == key row (dV, dK)
-    const int ctid = tid - 64;      // 0..255
+    const int half = sw >> 2;       // which 64 key columns
+    const int r = quad * 32 + lane; // TMEM lane == query row
     const uint32_t trow = tmem + (static_cast<uint32_t>(quad * 32) << 16);
     const float sl2 = p.scale * LOG2E;
-    auto load_bias = [&](int item, int buf) {
-      if (ctid < ATT_T) {
-        const int seq = item / p.heads;
-        float b = -INFINITY;
-        if (ctid < L) b = p.key_bias ? p.key_bias[static_cast<long long>(seq) * L + ctid] * LOG2E : 0.f;
-        sBias[buf * ATT_T + ctid] = b;
-      }
+    float* wb = sBiasW + sw * 64;   // this warp's private copy of the 64 key-bias values it needs
+    // values of the NEXT item are fetched one item ahead (global latency off the critical path)
+    auto fetch_bias = [&](int item, int j) -> float {
+      const int c = half * 64 + j * 32 + lane;
+      if (c >= L) return -INFINITY;
+      return p.key_bias ? p.key_bias[static_cast<long long>(item / p.heads) * L + c] : 0.f;  // x LOG2E at use
     };
-    if (blockIdx.x < n_items) load_bias(blockIdx.x, 0);
-    named_bar_sync(1, 256);
+    auto fetch_lse = [&](int item) -> float {
+      return r < L ? p.lse[static_cast<long long>(item) * L + r] : 0.f;  // x LOG2E at use: nothing waits on the load here
+    };
+    float nb0 = 0.f, nb1 = 0.f, nlse = 0.f;
+    if (static_cast<int>(blockIdx.x) < n_items) {
+      nb0 = fetch_bias(blockIdx.x, 0);
+      nb1 = fetch_bias(blockIdx.x, 1);
+      nlse = fetch_lse(blockIdx.x);
+    }
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const uint32_t ph = it & 1;
-      const int seq = item / p.heads, h = item % p.heads;
-      const int row0 = seq * L;
-      const float* bias = sBias + (it & 1) * ATT_T;
-      float lse2 = 0.f;
-      if (r < L) lse2 = p.lse[(static_cast<long long>(seq) * p.heads + h) * L + r] * LOG2E;
-      if (item + static_cast<int>(gridDim.x) < n_items) load_bias(item + gridDim.x, (it + 1) & 1);
+      const float lse2 = nlse * LOG2E;
+      __syncwarp();
+      wb[lane] = nb0 * LOG2E;
+      wb[32 + lane] = nb1 * LOG2E;
+      __syncwarp();
+      if (item + static_cast<int>(gridDim.x) < n_items) {
+        nb0 = fetch_bias(item + gridDim.x, 0);
+        nb1 = fetch_bias(item + gridDim.x, 1);
+        nlse = fetch_lse(item + gridDim.x);
+      }
       mbar_wait(sdp_full, ph);
       tc_fence_after();
       // ---- phase 1: P (fp32 in registers, fp16 to smem) and this half's share of delta
@@ -398,27 +423,38 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         const int c0 = half * 64 + cc * 32;
-        uint32_t sv[32], dv[32];
-        tmem_ld_32x32(trow + c0, sv);
-        tmem_ld_32x32(trow + 128 + c0, dv);
-        tc_wait_ld();
+        {
+          uint32_t sv[32];
+          tmem_ld_32x32(trow + c0, sv);
+          tc_wait_ld();
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float pv[8];
+          for (int g = 0; g < 4; ++g) {
+            float pv[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int c = c0 + g * 8 + j;
-            const bool ok = (r < L) && (c < L);
-            const float pe = ok ? fast_ex2(fmaf(__uint_as_float(sv[g * 8 + j]), sl2, bias[c]) - lse2) : 0.f;
-            pv[j] = pe;
-            pf[cc * 32 + g * 8 + j] = pe;
-            dpart = fmaf(pe, __uint_as_float(dv[g * 8 + j]), dpart);
+            for (int j = 0; j < 8; ++j) {
+              const int cl = cc * 32 + g * 8 + j;
+              // masked keys carry bias = -inf -> P = 0; rows beyond seq_len are zeroed explicitly
+              float pe = fast_ex2(fmaf(__uint_as_float(sv[g * 8 + j]), sl2, wb[cl]) - lse2);
+              pe = (r < L) ? pe : 0.f;
+              pv[j] = pe;
+              pf[cl] = pe;
+            }
+            *reinterpret_cast<uint4*>(sP + swz_off(r, c0 + g * 8)) = pack8(pv);
           }
-          *reinterpret_cast<uint4*>(sP + swz_off(r, c0 + g * 8)) = pack8(pv);
+        }
+        {
+          uint32_t dv[32];
+          tmem_ld_32x32(trow + 128 + c0, dv);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) dpart = fmaf(pf[cc * 32 + j], __uint_as_float(dv[j]), dpart);
         }
       }
       sDelta[half * ATT_T + r] = dpart;
-      named_bar_sync(1, 256);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);  // dV = P^T dO may start while dS is being formed
+      named_bar_sync(1 + quad, 64);        // the two warps that share these 32 rows
       const float delta = sDelta[r] + sDelta[ATT_T + r];
       // ---- phase 2: dS = P (dP - delta) scale
 #pragma unroll
@@ -441,34 +477,48 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(sdp_empty);  // S / dP columns may take item i+1
-        mbar_arrive(pds_full);   // P / dS are in shared memory
+        mbar_arrive(ds_full);    // dS is in shared memory
       }
-      // ---- epilogue: dV, dK, dQ rows -> packed fp16 dQKV, column sums -> QKV bias gradient
+      named_bar_sync(1 + quad, 64);  // sDelta of this item has been read by both warps before it is rewritten
+    }
+  } else {
+    // ===================== epilogue threads: dV, dK, dQ rows -> dQKV + bias gradient =====================
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;  // key row (dV, dK) == query row (dQ)
+    const uint32_t trow = tmem + (static_cast<uint32_t>(quad * 32) << 16);
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const uint32_t ph = it & 1;
+      const int seq = item / p.heads, h = item % p.heads;
+      const int row0 = seq * L;
+      __half* grow = p.dqkv + static_cast<long long>(row0 + r) * (3 * p.hidden) + h * ATT_D;
       mbar_wait(out_full, ph);
       tc_fence_after();
-      __half* grow = p.dqkv + static_cast<long long>(row0 + r) * (3 * p.hidden) + h * ATT_D + half * 32;
 #pragma unroll
       for (int t = 0; t < 3; ++t) {  // t: 0 = dV, 1 = dK, 2 = dQ
-        uint32_t v[32];
-        tmem_ld_32x32(trow + 256 + t * 64 + half * 32, v);
-        tc_wait_ld();
-        float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (r < L) {
-          __half* dst = grow + (2 - t) * p.hidden;
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(trow + 256 + t * 64 + c * 32, v);
+          tc_wait_ld();
+          float f[32];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float e[8];
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (r < L) {
+            __half* dst = grow + (2 - t) * p.hidden + c * 32;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) e[j] = f[g * 8 + j];
-            *reinterpret_cast<uint4*>(dst + g * 8) = pack8(e);
+            for (int g = 0; g < 4; ++g) {
+              float e[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) e[j] = f[g * 8 + j];
+              *reinterpret_cast<uint4*>(dst + g * 8) = pack8(e);
+            }
           }
-        }
-        if (p.dbias != nullptr) {
-          // rows beyond seq_len are exact zeros (their P / dS rows and columns were zeroed)
-          const float tot = warp_colsum32(f, lane);
-          atomicAdd(p.dbias + (2 - t) * p.hidden + h * ATT_D + half * 32 + lane, tot * p.dbias_scale);
+          if (p.dbias != nullptr) {
+            // rows beyond seq_len are exact zeros (their P / dS rows and columns were zeroed)
+            const float tot = warp_colsum32(f, lane);
+            atomicAdd(p.dbias + (2 - t) * p.hidden + h * ATT_D + c * 32 + lane, tot * p.dbias_scale);
+          }
         }
       }
       tc_fence_before();
@@ -498,7 +548,7 @@ constexpr int ATT_FWDM_SMEM = 5 * ATT_TILE_BYTES + 512 + 128 + 1024;  // Q K V |
 __global__ void __launch_bounds__(128, 2)
 fmha_fwd_multi_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttParams p, const int q_tiles) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* sQ = smem;
   uint8_t* sK = smem + ATT_TILE_BYTES;
   uint8_t* sV = smem + 2 * ATT_TILE_BYTES;
@@ -661,7 +711,7 @@ __global__ void __launch_bounds__(256, 1)
 fmha_bwd_multi_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do,
                       const AttParams p, float* __restrict__ dq_ws, const int kv_tiles) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* sK = smem;
   uint8_t* sV = smem + ATT_TILE_BYTES;
   uint8_t* sQ = smem + 2 * ATT_TILE_BYTES;

@@ -47,6 +47,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// First 1024-byte aligned address of the dynamic shared memory (SWIZZLE_128B tiles need it).  The offset is
+// computed on the 32-bit shared address and ADDED to the __shared__ array, so the compiler keeps the shared
+// address space (LDS / STS); rounding the generic pointer through uintptr_t degrades every access to generic LD / ST.
+__device__ __forceinline__ uint8_t* smem_align1024(uint8_t* raw) {
+  const uint32_t base = smem_u32(raw);
+  return raw + ((1024u - (base & 1023u)) & 1023u);
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
