@@ -216,8 +216,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttParams p) 
 // softmax threads overlap; nothing but the mbarriers below synchronises them.
 // TMEM columns: S [0,128) dP [128,256) dV [256,320) dK [320,384) dQ [384,448).
 // smem: 2 stages x (Q K V dO) = 128 KB | P 32 KB | dS 32 KB | key bias x2 | delta halves | barriers.
-constexpr int ATT_BWD_THREADS = 448;  // producer, MMA issuer, 8 softmax warps, 4 epilogue warps
-constexpr int ATT_BWD_SMEM = 12 * ATT_TILE_BYTES + 8 * 64 * 4 + 2 * 512 + 256 + 1024;
+constexpr int ATT_BWD_SM_WARPS = 16;   // softmax warps: 4 per TMEM lane quadrant, 32 key columns per thread
+constexpr int ATT_BWD_THREADS = 64 + 32 * ATT_BWD_SM_WARPS + 128;  // producer, MMA issuer, softmax, 4 epilogue warps
+constexpr int ATT_BWD_SMEM = 12 * ATT_TILE_BYTES + 2048 + 2048 + 256 + 4 * 2048 + 1024;  // tiles | per-warp bias | delta quarters | barriers | epilogue transposition tiles
 
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
@@ -257,13 +258,13 @@ __device__ __forceinline__ float warp_colsum32(const float (&v)[32], int lane) {
 // Backward, seq_len <= 128.  Persistent and warp-specialised: one CTA per SM walks (sequence, head) items.
 //   warp 0        : TMA producer -- Q K V dO of item i+1 land in the other smem stage while item i computes
 //   warp 1        : tcgen05.mma issuer (one thread) + TMEM owner
-//   warps 2..9    : softmax threads; thread = (TMEM lane r = query row, half of the 128 key columns):
+//   warps 2..17   : softmax threads; thread = (TMEM lane r = query row, one quarter of the 128 key columns):
 //                   P = exp2(S - lse) -> smem;  delta_r = sum_j P dP (exact: the whole row is in one tile; the
-//                   two half-row partials meet through a 64-thread named barrier);  dS = P (dP - delta) scale
-//   warps 10..13  : epilogue threads; thread = key/query row r: dV, dK, dQ rows -> packed fp16 dQKV and the
+//                   four quarter-row partials meet through a 128-thread named barrier);  dS = P (dP - delta) scale
+//   warps 18..21  : epilogue threads; thread = key/query row r: dV, dK, dQ rows -> packed fp16 dQKV and the
 //                   QKV bias gradient (column sums in fp32 straight from the accumulators)
 // so that softmax(i+1), the epilogue of item i, the MMAs and the loads all overlap; only mbarriers connect them.
-// MMA order per item: S, dP | dV (as soon as P is in smem) | dK, dQ (once dS is).
+// MMA order: S, dP (i) | dV (i) as soon as P is in smem | S, dP (i+1) | dK, dQ (i) once dS is.
 // TMEM columns: S [0,128) dP [128,256) dV [256,320) dK [320,384) dQ [384,448).
 // smem: 2 stages x (Q K V dO) = 128 KB | P 32 KB | dS 32 KB | per-warp key bias | delta halves | barriers.
 __global__ void __launch_bounds__(ATT_BWD_THREADS, 1)
@@ -274,9 +275,9 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
   uint8_t* sStage = smem;                         // [2][Q K V dO]
   uint8_t* sP = smem + 8 * ATT_TILE_BYTES;        // two [128][64] chunks
   uint8_t* sdS = smem + 10 * ATT_TILE_BYTES;
-  float* sBiasW = reinterpret_cast<float*>(smem + 12 * ATT_TILE_BYTES);                  // [8 warps][64]
-  float* sDelta = reinterpret_cast<float*>(smem + 12 * ATT_TILE_BYTES + 8 * 64 * 4);     // [2][128]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 12 * ATT_TILE_BYTES + 8 * 64 * 4 + 1024);
+  float* sBiasW = reinterpret_cast<float*>(smem + 12 * ATT_TILE_BYTES);           // [16 warps][32]
+  float* sDelta = reinterpret_cast<float*>(smem + 12 * ATT_TILE_BYTES + 2048);    // [4 quarters][128]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 12 * ATT_TILE_BYTES + 4096);
   uint64_t* full_qk = bar;          // [2] TMA -> MMA
   uint64_t* full_vdo = bar + 2;     // [2]
   uint64_t* stage_empty = bar + 4;  // [2] MMA -> TMA
@@ -287,6 +288,7 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
   uint64_t* out_full = bar + 10;    // MMA -> epilogue
   uint64_t* out_empty = bar + 11;   // epilogue -> MMA (4 warps)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 12);
+  uint8_t* sEpi = smem + 12 * ATT_TILE_BYTES + 4096 + 256;  // [4 epilogue warps][32 rows][64 B]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int L = p.seq_len;
@@ -297,9 +299,9 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
 #pragma unroll
     for (int i = 0; i < 6; ++i) mbar_init(&bar[i], 1);
     mbar_init(sdp_full, 1);
-    mbar_init(sdp_empty, 8);
-    mbar_init(p_full, 8);
-    mbar_init(ds_full, 8);
+    mbar_init(sdp_empty, ATT_BWD_SM_WARPS);
+    mbar_init(p_full, ATT_BWD_SM_WARPS);
+    mbar_init(ds_full, ATT_BWD_SM_WARPS);
     mbar_init(out_full, 1);
     mbar_init(out_empty, 4);
     fence_mbar_init();
@@ -338,25 +340,33 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
       constexpr uint32_t idesc_tt = make_idesc_f16(ATT_T, ATT_D, 1, 1);
       constexpr uint32_t idesc_nt = make_idesc_f16(ATT_T, ATT_D, 0, 1);
       const uint32_t pa = smem_u32(sP), dsa = smem_u32(sdS);
-      int it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-        const int s = it & 1;
-        const uint32_t ph = it & 1, phs = (it >> 1) & 1;
+      // S = Q K^T and dP = dO V^T of local item `jt` (stage jt & 1) -> sdp_full
+      auto issue_sdp = [&](int jt) {
+        const int s = jt & 1;
+        const uint32_t phs = (jt >> 1) & 1;
         const uint32_t qa = smem_u32(sStage + s * 4 * ATT_TILE_BYTES), ka = qa + ATT_TILE_BYTES,
                        va = qa + 2 * ATT_TILE_BYTES, da = qa + 3 * ATT_TILE_BYTES;
         mbar_wait(&full_qk[s], phs);
-        mbar_wait(sdp_empty, ph ^ 1);
+        mbar_wait(sdp_empty, (jt & 1) ^ 1);  // the softmax threads hold item jt-1's S / dP in registers
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < ATT_D / 16; ++k)  // S = Q K^T
+        for (int k = 0; k < ATT_D / 16; ++k)
           tc_mma_f16(tmem, make_smem_desc(qa + k * 32, 16, 1024), make_smem_desc(ka + k * 32, 16, 1024), idesc_s, k > 0);
         mbar_wait(&full_vdo[s], phs);
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < ATT_D / 16; ++k)  // dP = dO V^T
+        for (int k = 0; k < ATT_D / 16; ++k)
           tc_mma_f16(tmem + 128, make_smem_desc(da + k * 32, 16, 1024), make_smem_desc(va + k * 32, 16, 1024), idesc_s,
                      k > 0);
         tc_commit(sdp_full);
+      };
+      if (static_cast<int>(blockIdx.x) < n_items) issue_sdp(0);
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int s = it & 1;
+        const uint32_t ph = it & 1;
+        const uint32_t qa = smem_u32(sStage + s * 4 * ATT_TILE_BYTES), ka = qa + ATT_TILE_BYTES,
+                       da = qa + 3 * ATT_TILE_BYTES;
         mbar_wait(p_full, ph);
         mbar_wait(out_empty, ph ^ 1);
         tc_fence_after();
@@ -364,6 +374,8 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
         for (int k = 0; k < ATT_T / 16; ++k)  // dV[kv,d] = sum_q P[q,kv] dO[q,d]
           tc_mma_f16(tmem + 256, make_smem_desc(pa + k * 2048, ATT_TILE_BYTES, 1024),
                      make_smem_desc(da + k * 2048, 8192, 1024), idesc_tt, k > 0);
+        // the next item's S / dP go in between: its softmax never waits for dK / dQ of this one
+        if (item + static_cast<int>(gridDim.x) < n_items) issue_sdp(it + 1);
         mbar_wait(ds_full, ph);
         tc_fence_after();
 #pragma unroll
@@ -378,28 +390,28 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
         tc_commit(&stage_empty[s]);  // Q K V dO of this stage (and P / dS) are consumed
       }
     }
-  } else if (warp < 10) {
+  } else if (warp < 2 + ATT_BWD_SM_WARPS) {
     // ===================== softmax / dS threads =====================
-    const int sw = warp - 2;        // 0..7
+    const int sw = warp - 2;        // 0..15
     const int quad = warp & 3;      // TMEM lane quadrant this warp may touch
-    const int half = sw >> 2;       // which 64 key columns
+    const int qtr = sw >> 2;        // which 32 key columns
     const int r = quad * 32 + lane; // TMEM lane == query row
+    const int c0 = qtr * 32;
     const uint32_t trow = tmem + (static_cast<uint32_t>(quad * 32) << 16);
     const float sl2 = p.scale * LOG2E;
-    float* wb = sBiasW + sw * 64;   // this warp's private copy of the 64 key-bias values it needs
+    float* wb = sBiasW + sw * 32;   // this warp's private copy of the 32 key-bias values it needs
     // values of the NEXT item are fetched one item ahead (global latency off the critical path)
-    auto fetch_bias = [&](int item, int j) -> float {
-      const int c = half * 64 + j * 32 + lane;
+    auto fetch_bias = [&](int item) -> float {
+      const int c = c0 + lane;
       if (c >= L) return -INFINITY;
       return p.key_bias ? p.key_bias[static_cast<long long>(item / p.heads) * L + c] : 0.f;  // x LOG2E at use
     };
     auto fetch_lse = [&](int item) -> float {
       return r < L ? p.lse[static_cast<long long>(item) * L + r] : 0.f;  // x LOG2E at use: nothing waits on the load here
     };
-    float nb0 = 0.f, nb1 = 0.f, nlse = 0.f;
+    float nb = 0.f, nlse = 0.f;
     if (static_cast<int>(blockIdx.x) < n_items) {
-      nb0 = fetch_bias(blockIdx.x, 0);
-      nb1 = fetch_bias(blockIdx.x, 1);
+      nb = fetch_bias(blockIdx.x);
       nlse = fetch_lse(blockIdx.x);
     }
     int it = 0;
@@ -407,91 +419,79 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
       const uint32_t ph = it & 1;
       const float lse2 = nlse * LOG2E;
       __syncwarp();
-      wb[lane] = nb0 * LOG2E;
-      wb[32 + lane] = nb1 * LOG2E;
+      wb[lane] = nb * LOG2E;
       __syncwarp();
       if (item + static_cast<int>(gridDim.x) < n_items) {
-        nb0 = fetch_bias(item + gridDim.x, 0);
-        nb1 = fetch_bias(item + gridDim.x, 1);
+        nb = fetch_bias(item + gridDim.x);
         nlse = fetch_lse(item + gridDim.x);
       }
       mbar_wait(sdp_full, ph);
       tc_fence_after();
-      // ---- phase 1: P (fp32 in registers, fp16 to smem) and this half's share of delta
-      float pf[64];
-      float dpart = 0.f;
+      // ---- S and dP of this thread's 32 columns: both loads in flight together, kept in registers to the end
+      uint32_t sv[32], dv[32];
+      tmem_ld_32x32(trow + c0, sv);
+      tmem_ld_32x32(trow + 128 + c0, dv);
+      tc_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sdp_empty);  // S / dP columns may take item i+1 as soon as every warp has its copy
+      // ---- P (fp32 in place of S, fp16 to smem) and this quarter's share of delta
+      float dp0 = 0.f, dp1 = 0.f, dp2 = 0.f, dp3 = 0.f;
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c0 = half * 64 + cc * 32;
-        {
-          uint32_t sv[32];
-          tmem_ld_32x32(trow + c0, sv);
-          tc_wait_ld();
+      for (int g = 0; g < 4; ++g) {
+        float pv[8];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float pv[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int cl = cc * 32 + g * 8 + j;
-              // masked keys carry bias = -inf -> P = 0; rows beyond seq_len are zeroed explicitly
-              float pe = fast_ex2(fmaf(__uint_as_float(sv[g * 8 + j]), sl2, wb[cl]) - lse2);
-              pe = (r < L) ? pe : 0.f;
-              pv[j] = pe;
-              pf[cl] = pe;
-            }
-            *reinterpret_cast<uint4*>(sP + swz_off(r, c0 + g * 8)) = pack8(pv);
-          }
+        for (int j = 0; j < 8; ++j) {
+          // masked keys carry bias = -inf -> P = 0; rows beyond seq_len are zeroed explicitly
+          float pe = fast_ex2(fmaf(__uint_as_float(sv[g * 8 + j]), sl2, wb[g * 8 + j]) - lse2);
+          pe = (r < L) ? pe : 0.f;
+          pv[j] = pe;
+          sv[g * 8 + j] = __float_as_uint(pe);
         }
-        {
-          uint32_t dv[32];
-          tmem_ld_32x32(trow + 128 + c0, dv);
-          tc_wait_ld();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) dpart = fmaf(pf[cc * 32 + j], __uint_as_float(dv[j]), dpart);
-        }
+        dp0 = fmaf(pv[0], __uint_as_float(dv[g * 8 + 0]), dp0);
+        dp1 = fmaf(pv[1], __uint_as_float(dv[g * 8 + 1]), dp1);
+        dp2 = fmaf(pv[2], __uint_as_float(dv[g * 8 + 2]), dp2);
+        dp3 = fmaf(pv[3], __uint_as_float(dv[g * 8 + 3]), dp3);
+        dp0 = fmaf(pv[4], __uint_as_float(dv[g * 8 + 4]), dp0);
+        dp1 = fmaf(pv[5], __uint_as_float(dv[g * 8 + 5]), dp1);
+        dp2 = fmaf(pv[6], __uint_as_float(dv[g * 8 + 6]), dp2);
+        dp3 = fmaf(pv[7], __uint_as_float(dv[g * 8 + 7]), dp3);
+        *reinterpret_cast<uint4*>(sP + swz_off(r, c0 + g * 8)) = pack8(pv);
       }
-      sDelta[half * ATT_T + r] = dpart;
+      sDelta[qtr * ATT_T + r] = (dp0 + dp1) + (dp2 + dp3);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);  // dV = P^T dO may start while dS is being formed
-      named_bar_sync(1 + quad, 64);        // the two warps that share these 32 rows
-      const float delta = sDelta[r] + sDelta[ATT_T + r];
-      // ---- phase 2: dS = P (dP - delta) scale
+      named_bar_sync(1 + quad, 128);       // the four warps that share these 32 rows
+      const float delta = (sDelta[r] + sDelta[ATT_T + r]) + (sDelta[2 * ATT_T + r] + sDelta[3 * ATT_T + r]);
+      // ---- dS = P (dP - delta) scale
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c0 = half * 64 + cc * 32;
-        uint32_t dv[32];
-        tmem_ld_32x32(trow + 128 + c0, dv);
-        tc_wait_ld();
+      for (int g = 0; g < 4; ++g) {
+        float ds[8];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float ds[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            ds[j] = pf[cc * 32 + g * 8 + j] * (__uint_as_float(dv[g * 8 + j]) - delta) * p.scale;
-          *reinterpret_cast<uint4*>(sdS + swz_off(r, c0 + g * 8)) = pack8(ds);
-        }
+        for (int j = 0; j < 8; ++j)
+          ds[j] = __uint_as_float(sv[g * 8 + j]) * (__uint_as_float(dv[g * 8 + j]) - delta) * p.scale;
+        *reinterpret_cast<uint4*>(sdS + swz_off(r, c0 + g * 8)) = pack8(ds);
       }
       fence_proxy_async();
-      tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(sdp_empty);  // S / dP columns may take item i+1
-        mbar_arrive(ds_full);    // dS is in shared memory
-      }
-      named_bar_sync(1 + quad, 64);  // sDelta of this item has been read by both warps before it is rewritten
+      if (lane == 0) mbar_arrive(ds_full);  // dS is in shared memory
+      named_bar_sync(1 + quad, 128);  // sDelta of this item has been read by all four warps before it is rewritten
     }
   } else {
     // ===================== epilogue threads: dV, dK, dQ rows -> dQKV + bias gradient =====================
+    // tcgen05.ld hands a thread one ROW; 32 lanes storing 16 B each would touch 32 different 128-byte lines per
+    // instruction.  Each warp therefore transposes its 32 x 32 fp16 chunk through a private, XOR-swizzled 2 KB
+    // tile: afterwards 4 neighbouring lanes own one row's 64 bytes and a store instruction covers 8 whole rows.
     const int quad = warp & 3;
     const int r = quad * 32 + lane;  // key row (dV, dK) == query row (dQ)
     const uint32_t trow = tmem + (static_cast<uint32_t>(quad * 32) << 16);
+    uint8_t* tile = sEpi + quad * 2048;
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const uint32_t ph = it & 1;
       const int seq = item / p.heads, h = item % p.heads;
       const int row0 = seq * L;
-      __half* grow = p.dqkv + static_cast<long long>(row0 + r) * (3 * p.hidden) + h * ATT_D;
       mbar_wait(out_full, ph);
       tc_fence_after();
 #pragma unroll
@@ -501,29 +501,66 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
           uint32_t v[32];
           tmem_ld_32x32(trow + 256 + t * 64 + c * 32, v);
           tc_wait_ld();
+          if (t == 2 && c == 1) {  // last read of this item's accumulators: hand them back before the stores
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(out_empty);
+          }
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (r < L) {
-            __half* dst = grow + (2 - t) * p.hidden + c * 32;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float e[8];
+          for (int g = 0; g < 4; ++g) {
+            float e[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) e[j] = f[g * 8 + j];
-              *reinterpret_cast<uint4*>(dst + g * 8) = pack8(e);
+            for (int j = 0; j < 8; ++j) e[j] = f[g * 8 + j];
+            *reinterpret_cast<uint4*>(tile + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) = pack8(e);
+          }
+          __syncwarp();
+          float cs[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) cs[j] = 0.f;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = (lane >> 2) + 8 * i;  // row of the chunk
+            const int pc = lane & 3;             // 16-byte piece of that row
+            const uint4 q = *reinterpret_cast<const uint4*>(tile + rr * 64 + ((pc ^ ((rr >> 1) & 3)) << 4));
+            const int grow_i = quad * 32 + rr;
+            if (grow_i < L)
+              *reinterpret_cast<uint4*>(p.dqkv + static_cast<long long>(row0 + grow_i) * (3 * p.hidden) +
+                                        (2 - t) * p.hidden + h * ATT_D + c * 32 + pc * 8) = q;
+            const __half2* qh = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {  // rows beyond seq_len are exact zeros: no predicate needed
+              const float2 x = __half22float2(qh[j]);
+              cs[2 * j] += x.x;
+              cs[2 * j + 1] += x.y;
             }
           }
           if (p.dbias != nullptr) {
-            // rows beyond seq_len are exact zeros (their P / dS rows and columns were zeroed)
-            const float tot = warp_colsum32(f, lane);
-            atomicAdd(p.dbias + (2 - t) * p.hidden + h * ATT_D + c * 32 + lane, tot * p.dbias_scale);
+            // bias gradient = column sums of the stored values: the 8 lanes that share a piece hold the same 8
+            // columns for different rows; a halving butterfly over lane bits 4,3,2 leaves one column per lane
+            float a4[4], a2[2];
+            {
+              const bool up = (lane & 16) != 0;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                a4[j] = (up ? cs[j + 4] : cs[j]) + __shfl_xor_sync(0xffffffffu, up ? cs[j] : cs[j + 4], 16);
+            }
+            {
+              const bool up = (lane & 8) != 0;
+#pragma unroll
+              for (int j = 0; j < 2; ++j)
+                a2[j] = (up ? a4[j + 2] : a4[j]) + __shfl_xor_sync(0xffffffffu, up ? a4[j] : a4[j + 2], 8);
+            }
+            const bool up = (lane & 4) != 0;
+            const float tot = (up ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, up ? a2[0] : a2[1], 4);
+            const int col = (lane & 3) * 8 + ((lane & 16) ? 4 : 0) + ((lane & 8) ? 2 : 0) + ((lane & 4) ? 1 : 0);
+            atomicAdd(p.dbias + (2 - t) * p.hidden + h * ATT_D + c * 32 + col, tot * p.dbias_scale);
           }
+          __syncwarp();  // the transposition tile is rewritten by the next chunk
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(out_empty);
     }
   }
 

@@ -36,3 +36,5 @@ fw = 4 * L * L * 64 * heads * n_seq
 bench("attn fwd", lambda r: k.attn_fwd(qkv[r], None, out[r], lse[r], n_seq=n_seq, seq_len=L, heads=heads), fw, T * 4 * H * 2)
 bench("attn bwd", lambda r: k.attn_bwd(qkv[r], None, out[r], lse[r], do[r], dqkv[r], n_seq=n_seq, seq_len=L, heads=heads,
                                       dbias=db, dbias_scale=1e-3), 2.5 * fw, T * (3 + 1 + 3) * H * 2)
+bench("bwd no-dbias", lambda r: k.attn_bwd(qkv[r], None, out[r], lse[r], do[r], dqkv[r], n_seq=n_seq, seq_len=L, heads=heads),
+      2.5 * fw, T * (3 + 1 + 3) * H * 2)
