@@ -68,139 +68,233 @@ __device__ __forceinline__ float dot8(const uint4& a, const uint4& b) {
 }
 
 // ------------------------------------------------------------------------------------------ forward
-constexpr int ATT_FWD_SMEM = 3 * ATT_TILE_BYTES + 512 + 64 + 1024;
+// seq_len <= 128.  Persistent and warp-specialised: one CTA per SM walks (sequence, head) items.
+//   warp 0       : TMA producer -- Q K V of item i+1 land in the other smem stage while item i computes
+//   warp 1       : tcgen05.mma issuer (one thread) + TMEM owner
+//   warps 2..5   : softmax group 0 (even items);  warps 6..9 : softmax group 1 (odd items)
+// A softmax thread owns one query row (TMEM lane) end to end: exact row maximum (first pass over S in TMEM),
+// P = exp2(S - max) -> fp16 smem + row sum (second pass), then -- once O = P V of ITS item has landed -- the
+// epilogue O / sum -> ctx rows, coalesced through a warp-private transposition tile.  The two groups alternate
+// items and everything they touch (S / O columns, P buffer, smem stage) is per group, so group 1 runs its softmax
+// while group 0 waits for its P V: no block-wide barrier anywhere.
+// TMEM columns: S[g] at g * 128, O[g] at 256 + g * 64.   smem: 2 x (Q K V) 96 KB | 2 x P 64 KB | small buffers.
+constexpr int ATT_FWD_THREADS = 320;
+constexpr int ATT_FWD_SMEM = 10 * ATT_TILE_BYTES + 8 * 512 + 8 * 2048 + 256 + 1024;
 
-__global__ void __launch_bounds__(128, 4)
-fmha_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttParams p) {
+__global__ void __launch_bounds__(ATT_FWD_THREADS, 1)
+fmha_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttParams p, const int n_items) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_align1024(smem_raw);
-  uint8_t* sQ = smem;
-  uint8_t* sK = smem + ATT_TILE_BYTES;
-  uint8_t* sV = smem + 2 * ATT_TILE_BYTES;
-  uint8_t* sP = smem;  // overlays Q and K once S = Q K^T has retired
-  float* sBias = reinterpret_cast<float*>(smem + 3 * ATT_TILE_BYTES);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 3 * ATT_TILE_BYTES + 512);
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 4);
+  uint8_t* sStage = smem;                                 // [2][Q K V]
+  uint8_t* sPall = smem + 6 * ATT_TILE_BYTES;             // [2][two [128][64] chunks]
+  float* sBiasW = reinterpret_cast<float*>(smem + 10 * ATT_TILE_BYTES);          // [8 warps][128]
+  uint8_t* sEpi = smem + 10 * ATT_TILE_BYTES + 8 * 512;                          // [8 warps][32 rows][64 B]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 10 * ATT_TILE_BYTES + 8 * 512 + 8 * 2048);
+  uint64_t* full_qk = bar;          // [2] TMA -> MMA
+  uint64_t* full_v = bar + 2;       // [2]
+  uint64_t* stage_empty = bar + 4;  // [2] MMA -> TMA
+  uint64_t* s_full = bar + 6;       // [2] MMA -> softmax group
+  uint64_t* s_empty = bar + 8;      // [2] softmax group (4 warps) -> MMA
+  uint64_t* p_full = bar + 10;      // [2] softmax group (4 warps) -> MMA
+  uint64_t* o_full = bar + 12;      // [2] MMA -> softmax group
+  uint64_t* o_empty = bar + 14;     // [2] softmax group (4 warps) -> MMA
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 16);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int seq = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int L = p.seq_len;
-  const int row0 = seq * L;
 
   if (tid == 0) {
     tma_prefetch_desc(&tma_qkv);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) mbar_init(&bar[i], 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&bar[i], 1);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_empty[i], 4);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&o_empty[i], 4);
+    }
     fence_mbar_init();
   }
-  if (warp == 0) {
-    tmem_alloc(tmem_ptr, 128);
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 512);
     tmem_relinquish();
-  }
-  {
-    float b = -INFINITY;
-    if (tid < L) b = p.key_bias ? p.key_bias[static_cast<long long>(seq) * L + tid] * LOG2E : 0.f;
-    sBias[tid] = b;
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
 
-  if (tid == 0) {
-    mbar_expect_tx(&bar[0], 2 * ATT_TILE_BYTES);
-    tma_load_2d(sQ, &tma_qkv, &bar[0], h * ATT_D, row0);
-    tma_load_2d(sK, &tma_qkv, &bar[0], p.hidden + h * ATT_D, row0);
-    mbar_expect_tx(&bar[1], ATT_TILE_BYTES);
-    tma_load_2d(sV, &tma_qkv, &bar[1], 2 * p.hidden + h * ATT_D, row0);
-    mbar_wait(&bar[0], 0);
-    tc_fence_after();
-    constexpr uint32_t idesc = make_idesc_f16(ATT_T, ATT_T, 0, 0);
-    const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK);
-#pragma unroll
-    for (int k = 0; k < ATT_D / 16; ++k)
-      tc_mma_f16(tmem, make_smem_desc(qa + k * 32, 16, 1024), make_smem_desc(ka + k * 32, 16, 1024), idesc, k > 0);
-    tc_commit(&bar[2]);
-  }
-  __syncwarp();
-  mbar_wait(&bar[2], 0);
-  tc_fence_after();
-  __syncwarp();
-
-  const int r = tid;  // TMEM lane == query row
-  const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-  const float sl2 = p.scale * LOG2E;
-  float mx = -INFINITY;
-#pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
-    uint32_t v[32];
-    tmem_ld_32x32(trow + c * 32, v);
-    tc_wait_ld();
-#pragma unroll
-    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaf(__uint_as_float(v[j]), sl2, sBias[c * 32 + j]));
-  }
-  if (mx == -INFINITY) mx = 0.f;  // fully masked row: P = 0, output 0
-  float sum = 0.f;
-#pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
-    uint32_t v[32];
-    tmem_ld_32x32(trow + c * 32, v);
-    tc_wait_ld();
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      float e[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        e[j] = exp2f(fmaf(__uint_as_float(v[g * 8 + j]), sl2, sBias[c * 32 + g * 8 + j]) - mx);
-        sum += e[j];
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int s = it & 1;
+        const int seq = item / p.heads, h = item % p.heads;
+        const int row0 = seq * L;
+        uint8_t* st = sStage + s * 3 * ATT_TILE_BYTES;
+        mbar_wait(&stage_empty[s], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&full_qk[s], 2 * ATT_TILE_BYTES);
+        tma_load_2d(st, &tma_qkv, &full_qk[s], h * ATT_D, row0);
+        tma_load_2d(st + ATT_TILE_BYTES, &tma_qkv, &full_qk[s], p.hidden + h * ATT_D, row0);
+        mbar_expect_tx(&full_v[s], ATT_TILE_BYTES);
+        tma_load_2d(st + 2 * ATT_TILE_BYTES, &tma_qkv, &full_v[s], 2 * p.hidden + h * ATT_D, row0);
       }
-      *reinterpret_cast<uint4*>(sP + swz_off(r, c * 32 + g * 8)) = pack8(e);
     }
-  }
-  if (r < L && p.lse) p.lse[(static_cast<long long>(seq) * p.heads + h) * L + r] = (mx + log2f(sum)) / LOG2E;
-  fence_proxy_async();
-  tc_fence_before();
-  __syncthreads();
-
-  if (tid == 0) {
-    tc_fence_after();
-    mbar_wait(&bar[1], 0);
-    tc_fence_after();
-    constexpr uint32_t idesc = make_idesc_f16(ATT_T, ATT_D, 0, 1);
-    const uint32_t pa = smem_u32(sP), va = smem_u32(sV);
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_f16(ATT_T, ATT_T, 0, 0);
+      constexpr uint32_t idesc_o = make_idesc_f16(ATT_T, ATT_D, 0, 1);
+      auto issue_s = [&](int jt) {  // S = Q K^T of local item jt into the S columns of group jt & 1
+        const int g = jt & 1;
+        const uint32_t k = (jt >> 1) & 1;
+        const uint32_t qa = smem_u32(sStage + g * 3 * ATT_TILE_BYTES), ka = qa + ATT_TILE_BYTES;
+        mbar_wait(&full_qk[g], k);
+        mbar_wait(&s_empty[g], k ^ 1);
+        tc_fence_after();
 #pragma unroll
-    for (int k = 0; k < ATT_T / 16; ++k)
-      tc_mma_f16(tmem, make_smem_desc(pa + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 16, 1024),
-                 make_smem_desc(va + k * 2048, 8192, 1024), idesc, k > 0);
-    tc_commit(&bar[3]);
-  }
-  __syncwarp();
-  mbar_wait(&bar[3], 0);
-  tc_fence_after();
-  __syncwarp();
-
-  const float inv = sum > 0.f ? 1.f / sum : 0.f;
-  __half* orow = p.out + static_cast<long long>(row0 + r) * p.hidden + h * ATT_D;
-#pragma unroll 1
-  for (int c = 0; c < 2; ++c) {
-    uint32_t v[32];
-    tmem_ld_32x32(trow + c * 32, v);
-    tc_wait_ld();
-    if (r < L) {
+        for (int kk = 0; kk < ATT_D / 16; ++kk)
+          tc_mma_f16(tmem + g * 128, make_smem_desc(qa + kk * 32, 16, 1024), make_smem_desc(ka + kk * 32, 16, 1024),
+                     idesc_s, kk > 0);
+        tc_commit(&s_full[g]);
+      };
+      if (static_cast<int>(blockIdx.x) < n_items) issue_s(0);
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int g = it & 1;
+        const uint32_t k = (it >> 1) & 1;
+        if (item + static_cast<int>(gridDim.x) < n_items) issue_s(it + 1);  // the other group's S first
+        const uint32_t pa = smem_u32(sPall + g * 2 * ATT_TILE_BYTES);
+        const uint32_t va = smem_u32(sStage + g * 3 * ATT_TILE_BYTES + 2 * ATT_TILE_BYTES);
+        mbar_wait(&p_full[g], k);
+        mbar_wait(&full_v[g], k);
+        mbar_wait(&o_empty[g], k ^ 1);
+        tc_fence_after();
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
+        for (int kk = 0; kk < ATT_T / 16; ++kk)  // O = P V
+          tc_mma_f16(tmem + 256 + g * 64, make_smem_desc(pa + (kk >> 2) * ATT_TILE_BYTES + (kk & 3) * 32, 16, 1024),
+                     make_smem_desc(va + kk * 2048, 8192, 1024), idesc_o, kk > 0);
+        tc_commit(&o_full[g]);
+        tc_commit(&stage_empty[g]);  // Q K V of this stage are consumed
+      }
+    }
+  } else {
+    // ===================== softmax + epilogue threads =====================
+    const int sw = warp - 2;         // 0..7
+    const int g = sw >> 2;           // group: items with (local index & 1) == g
+    const int quad = warp & 3;       // TMEM lane quadrant this warp may touch
+    const int r = quad * 32 + lane;  // TMEM lane == query row
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t t_s = tmem + lane_off + g * 128;
+    const uint32_t t_o = tmem + lane_off + 256 + g * 64;
+    uint8_t* sP = sPall + g * 2 * ATT_TILE_BYTES;
+    float* wb = sBiasW + sw * 128;   // this warp's private copy of the 128 key-bias values
+    uint8_t* tile = sEpi + sw * 2048;
+    const float sl2 = p.scale * LOG2E;
+    auto fetch_bias = [&](int item, int j) -> float {  // x LOG2E at use: nothing waits on the load here
+      const int c = j * 32 + lane;
+      if (c >= L) return -INFINITY;
+      return p.key_bias ? p.key_bias[static_cast<long long>(item / p.heads) * L + c] : 0.f;
+    };
+    const int first = blockIdx.x + g * gridDim.x, step = 2 * gridDim.x;
+    float nb[4] = {0.f, 0.f, 0.f, 0.f};
+    if (first < n_items) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) nb[j] = fetch_bias(first, j);
+    }
+    uint32_t k = 0;
+    for (int item = first; item < n_items; item += step, k ^= 1) {
+      const int seq = item / p.heads, h = item % p.heads;
+      const int row0 = seq * L;
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wb[j * 32 + lane] = nb[j] * LOG2E;
+      __syncwarp();
+      if (item + step < n_items) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) nb[j] = fetch_bias(item + step, j);
+      }
+      mbar_wait(&s_full[g], k);
+      tc_fence_after();
+      // ---- the whole S row (128 fp32) comes into registers with ONE wait and stays there for both passes;
+      // its TMEM columns are handed back immediately
+      uint32_t v[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32(t_s + c * 32, reinterpret_cast<uint32_t(&)[32]>(v[c * 32]));
+      tc_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[g]);
+      // ---- pass 1: exact row maximum (scores kept as scaled log2 values)
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 128; ++j) {
+        const float sc = fmaf(__uint_as_float(v[j]), sl2, wb[j]);
+        v[j] = __float_as_uint(sc);
+        mx = fmaxf(mx, sc);
+      }
+      if (mx == -INFINITY) mx = 0.f;  // fully masked row: P = 0, output 0
+      // ---- pass 2: P = exp2(S - max) -> smem, row sum
+      float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+      for (int gq = 0; gq < 16; ++gq) {
         float e[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) e[j] = __uint_as_float(v[g * 8 + j]) * inv;
-        *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = pack8(e);
+        for (int j = 0; j < 8; ++j) e[j] = fast_ex2(__uint_as_float(v[gq * 8 + j]) - mx);
+        sum0 += (e[0] + e[1]) + (e[2] + e[3]);
+        sum1 += (e[4] + e[5]) + (e[6] + e[7]);
+        *reinterpret_cast<uint4*>(sP + swz_off(r, gq * 8)) = pack8(e);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[g]);
+      const float sum = sum0 + sum1;
+      if (r < L && p.lse) p.lse[static_cast<long long>(item) * L + r] = (mx + log2f(sum)) / LOG2E;
+      const float inv = sum > 0.f ? 1.f / sum : 0.f;
+      // ---- epilogue of the same item: O / sum -> ctx rows (transposed through the warp's tile for 64-byte row
+      // segments: a store instruction covers 8 whole rows instead of 32 different lines)
+      mbar_wait(&o_full[g], k);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_o + c * 32, v);
+        tc_wait_ld();
+        if (c == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&o_empty[g]);
+        }
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) {
+          float e[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) e[j] = __uint_as_float(v[gq * 8 + j]) * inv;
+          *reinterpret_cast<uint4*>(tile + lane * 64 + ((gq ^ ((lane >> 1) & 3)) << 4)) = pack8(e);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rr = (lane >> 2) + 8 * i;
+          const int pc = lane & 3;
+          const uint4 q = *reinterpret_cast<const uint4*>(tile + rr * 64 + ((pc ^ ((rr >> 1) & 3)) << 4));
+          const int orow = quad * 32 + rr;
+          if (orow < L)
+            *reinterpret_cast<uint4*>(p.out + static_cast<long long>(row0 + orow) * p.hidden + h * ATT_D + c * 32 +
+                                      pc * 8) = q;
+        }
+        __syncwarp();
       }
     }
   }
+
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem, 128);
+    tmem_dealloc(tmem, 512);
   }
 }
 
@@ -998,7 +1092,9 @@ int cdr_attn_fwd(const cdr_attn_args* a, void* stream) {
     CDR_LAUNCH_CHECK();
     return CDR_OK;
   }
-  fmha_fwd_kernel<<<a->n_seq * a->heads, 128, ATT_FWD_SMEM, static_cast<cudaStream_t>(stream)>>>(tq, p);
+  const int n_items = a->n_seq * a->heads;
+  const int grid = n_items < sm_count() ? n_items : sm_count();
+  fmha_fwd_kernel<<<grid, ATT_FWD_THREADS, ATT_FWD_SMEM, static_cast<cudaStream_t>(stream)>>>(tq, p, n_items);
   CDR_LAUNCH_CHECK();
   return CDR_OK;
 }
