@@ -84,10 +84,12 @@ def test_ance_tiny_forward_backward_matches_reference(golden_dir):
         # The triplet-loss gradient is sigma * (b - a): a difference of two nearly identical CLS vectors for a
         # random-init encoder, so the fp16 forward error (<1e-2, asserted above) is amplified several-fold
         # here.  The well-conditioned check of the backward kernels is
-        # test_encoder_backward_fixed_upstream_grad below; this one bounds the end-to-end drift.
+        # test_encoder_backward_fixed_upstream_grad below; this one bounds the end-to-end drift.  The worst entry
+        # (the last LayerNorm's weight) moves between 0.27 and 0.32 with rounding-level changes of the forward
+        # (tools/grad_drift.py; the fixed-upstream-gradient errors stay at 1e-3..3e-3), hence 0.4.
         cos = float((np.ravel(got) * np.ravel(g[key])).sum() /
                     (np.linalg.norm(np.ravel(got)) * np.linalg.norm(np.ravel(g[key])) + 1e-30))
-        assert r < 0.3 and cos > 0.99, f"{key}: rel err {r}, cos {cos}"
+        assert r < 0.4 and cos > 0.99, f"{key}: rel err {r}, cos {cos}"
     print("worst grad rel err", worst)
 
 
