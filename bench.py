@@ -195,8 +195,13 @@ def run_ours(args):
                 dist.broadcast(p_.data, 0)
             sync = GradSync(model)
     use_graph = world == 1 and not args.no_graph
-    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=5e-6, fused=True,
-                            capturable=use_graph)
+    if args.torch_adamw:  # library optimizer (A/B only): torch's fused AdamW + the encoder's own weight-shadow cast
+        opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=5e-6, fused=True,
+                                capturable=use_graph)
+    else:  # our multi-tensor AdamW: one launch updates all parameters AND rewrites the fp16 operand shadows
+        from cocodr_b200 import optim as cdr_optim
+        opt = cdr_optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=5e-6, eps=1e-8,
+                              weight_decay=0.01, semantics="torch").attach_shadows(model)
 
     B, L = PER_GPU_BATCH, SEQ_LEN
     g = torch.Generator().manual_seed(1234 + rank)
@@ -385,7 +390,7 @@ def run_ours(args):
                 "config": {"workload": WORKLOAD, "global_pairs_per_step": B * world,
                            "parallelism": f"dp{world}" + ((" + NCCL all-gather of passage CLS + " + ("DDP all-reduce" if args.ddp else "per-layer NCCL all-reduce of flat gradient buffers overlapped with backward")) if world > 1 else ""),
                            "l2": "per-step working set (~5 GB of activations) exceeds the 126 MB L2; 4 input batches cycled",
-                           "optimizer": "torch fused AdamW inside the timed step",
+                           "optimizer": ("torch fused AdamW" if args.torch_adamw else "cdr_adam_multi (own fused multi-tensor AdamW + fp16 shadow refresh)") + " inside the timed step",
                            "cuda_graph": graphed is not None},
                 "clocks": clocks.summary(),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -410,6 +415,7 @@ def main():
     ap.add_argument("--no-scan", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--ddp", action="store_true", help="N > 1: wrap in DistributedDataParallel instead of GradSync")
+    ap.add_argument("--torch-adamw", action="store_true", help="use torch.optim.AdamW(fused=True) instead of cdr_adam_multi")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -75,6 +75,14 @@ class BertModel(_HFBertModel):
         hf_bert._cdr_init()
         return hf_bert
 
+    def shadow_map(self):
+        """{parameter: (shadow view, is_f32)} of every parameter that has an fp16 / packed operand copy; a fused
+        optimizer (optim.py) writes these together with the parameters."""
+        if len(self._shadows) != len(self.encoder.layer):
+            self._cdr_init()
+        srcs = [shadow_sources(layer) for layer in self.encoder.layer]
+        return {param: (dst, is_f32) for param, dst, is_f32 in self._shadow_set.pairs(srcs)}
+
     # ------------------------------------------------------------------------------------------
     def _check_inputs(self, input_ids, token_type_ids, position_ids, inputs_embeds):
         global _warned_dropout

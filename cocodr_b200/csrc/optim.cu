@@ -1,0 +1,243 @@
+// Fused multi-tensor optimizers for the training step of the hot path (SURVEY f-4): one launch updates every
+// parameter of a group, and writes the fp16 operand shadows the tcgen05 GEMMs read in the same pass, so the
+// separate per-step weight cast disappears.  HBM-bound: AdamW moves 28 B per parameter (+2 B shadow).
+//
+//   CDR_OPT_ADAMW_TORCH : torch.optim.AdamW        p *= 1 - lr wd ; m,v EMA ; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
+//   CDR_OPT_ADAMW_HF    : transformers.AdamW (the `AdamW` the reference imports, ANCE/drivers/run_ann.py:19,139-144)
+//                         m,v EMA ; p -= lr sqrt(bc2)/bc1 * m / (sqrt(v) + eps) ; p -= lr wd p
+//   Lamb (cdr_lamb_multi): ANCE/utils/lamb.py:71-121 -- no bias correction, adam_step = m / (sqrt(v) + eps) + wd p,
+//                         trust = clamp(|p|, 0, 10) / |adam_step| (1 if either norm is 0), p -= lr trust adam_step
+#include "cdr_common.cuh"
+
+namespace cdr {
+
+__device__ __forceinline__ void ld4(const float* p, float (&v)[4]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+__device__ __forceinline__ void st4(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void st_shadow4(const cdr_opt_item& it, long long i, const float (&v)[4]) {
+  if (it.shadow == nullptr) return;
+  if (it.shadow_f32) {
+    st4(static_cast<float*>(it.shadow) + i, v);
+  } else {
+    __half2 lo = __floats2half2_rn(v[0], v[1]), hi = __floats2half2_rn(v[2], v[3]);
+    uint2 q;
+    q.x = *reinterpret_cast<uint32_t*>(&lo);
+    q.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(static_cast<__half*>(it.shadow) + i) = q;
+  }
+}
+
+__global__ void opt_step_inc_kernel(float* step) { step[0] += 1.f; }
+
+struct OptHyper {
+  float beta1, beta2, eps, wd;
+  const float* lr;
+  const float* step;
+  const float* grad_scale;
+  int mode;
+};
+
+// Work decomposition: block b owns chunk b = elements [start, start + CDR_OPT_CHUNK) of tensor `item` (the chunk
+// table is built once per parameter set on the host), so a 23 M-element embedding matrix and a 768-element bias
+// cost proportionally -- no empty blocks, no tail imbalance.
+__global__ void __launch_bounds__(256)
+adam_multi_kernel(const cdr_opt_item* __restrict__ items, const cdr_opt_chunk* __restrict__ chunks, OptHyper h) {
+  const cdr_opt_chunk ck = chunks[blockIdx.x];
+  cdr_opt_item it = items[ck.item];
+  const long long c_end = ck.start + CDR_OPT_CHUNK < it.n ? ck.start + CDR_OPT_CHUNK : it.n;
+  const float lr = h.lr[0], t = h.step[0];
+  const float gs = h.grad_scale ? h.grad_scale[0] : 1.f;
+  const float bc1 = 1.f - powf(h.beta1, t), bc2 = 1.f - powf(h.beta2, t);
+  const float rsq_bc2 = rsqrtf(bc2);
+  const float step_torch = lr / bc1;                  // with denom = sqrt(v)/sqrt(bc2) + eps
+  const float step_hf = lr * sqrtf(bc2) / bc1;        // with denom = sqrt(v) + eps
+  const float decay = 1.f - lr * h.wd;
+  it.n = c_end;
+  for (long long i = ck.start + threadIdx.x * 4; i < c_end; i += 256 * 4) {
+    if (i + 4 <= it.n && !it.reserved) {  // reserved != 0: some pointer of this entry is not 16-byte aligned
+      float p[4], g[4], m[4], v[4];
+      ld4(it.p + i, p); ld4(it.g + i, g); ld4(it.m + i, m); ld4(it.v + i, v);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float gk = g[k] * gs;
+        m[k] = h.beta1 * m[k] + (1.f - h.beta1) * gk;
+        v[k] = h.beta2 * v[k] + (1.f - h.beta2) * gk * gk;
+        if (h.mode == CDR_OPT_ADAMW_TORCH) {
+          p[k] = p[k] * decay - step_torch * m[k] / (sqrtf(v[k]) * rsq_bc2 + h.eps);
+        } else {
+          p[k] = p[k] - step_hf * m[k] / (sqrtf(v[k]) + h.eps);
+          p[k] = p[k] - lr * h.wd * p[k];
+        }
+      }
+      st4(it.p + i, p); st4(it.m + i, m); st4(it.v + i, v);
+      st_shadow4(it, i, p);
+    } else {
+      for (long long j = i; j < it.n && j < i + 4; ++j) {
+        const float gk = it.g[j] * gs;
+        const float mk = h.beta1 * it.m[j] + (1.f - h.beta1) * gk;
+        const float vk = h.beta2 * it.v[j] + (1.f - h.beta2) * gk * gk;
+        float pk = it.p[j];
+        if (h.mode == CDR_OPT_ADAMW_TORCH) {
+          pk = pk * decay - step_torch * mk / (sqrtf(vk) * rsq_bc2 + h.eps);
+        } else {
+          pk = pk - step_hf * mk / (sqrtf(vk) + h.eps);
+          pk = pk - lr * h.wd * pk;
+        }
+        it.p[j] = pk; it.m[j] = mk; it.v[j] = vk;
+        if (it.shadow != nullptr) {
+          if (it.shadow_f32) static_cast<float*>(it.shadow)[j] = pk;
+          else static_cast<__half*>(it.shadow)[j] = __float2half_rn(pk);
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float t = 0.f;
+  if (w == 0) {
+    t = lane < (blockDim.x >> 5) ? red[lane] : 0.f;
+    t = warp_sum(t);
+  }
+  __syncthreads();
+  return t;  // valid in warp 0
+}
+
+// Lamb phase 1: m, v EMA (written); per-tensor sums of p^2 and adam_step^2 -> norms[2 * tensor + {0, 1}]
+__global__ void __launch_bounds__(256)
+lamb_phase1_kernel(const cdr_opt_item* __restrict__ items, const cdr_opt_chunk* __restrict__ chunks, OptHyper h,
+                   float* __restrict__ norms) {
+  __shared__ float red[8];
+  const cdr_opt_chunk ck = chunks[blockIdx.x];
+  const cdr_opt_item it = items[ck.item];
+  const long long c_end = ck.start + CDR_OPT_CHUNK < it.n ? ck.start + CDR_OPT_CHUNK : it.n;
+  const float gs = h.grad_scale ? h.grad_scale[0] : 1.f;
+  float w2 = 0.f, a2 = 0.f;
+  for (long long j = ck.start + threadIdx.x; j < c_end; j += 256) {
+    const float gk = it.g[j] * gs, pk = it.p[j];
+    const float mk = h.beta1 * it.m[j] + (1.f - h.beta1) * gk;
+    const float vk = h.beta2 * it.v[j] + (1.f - h.beta2) * gk * gk;
+    it.m[j] = mk;
+    it.v[j] = vk;
+    const float as = mk / (sqrtf(vk) + h.eps) + h.wd * pk;
+    w2 += pk * pk;
+    a2 += as * as;
+  }
+  const float tw = block_sum(w2, red), ta = block_sum(a2, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(norms + 2 * ck.item, tw);
+    atomicAdd(norms + 2 * ck.item + 1, ta);
+  }
+}
+
+// Lamb phase 2: p -= lr * trust * adam_step (adam_step recomputed from the m, v phase 1 wrote)
+__global__ void __launch_bounds__(256)
+lamb_phase2_kernel(const cdr_opt_item* __restrict__ items, const cdr_opt_chunk* __restrict__ chunks, OptHyper h,
+                   const float* __restrict__ norms, float* __restrict__ trust_out) {
+  const cdr_opt_chunk ck = chunks[blockIdx.x];
+  const cdr_opt_item it = items[ck.item];
+  const long long c_end = ck.start + CDR_OPT_CHUNK < it.n ? ck.start + CDR_OPT_CHUNK : it.n;
+  const float wn = fminf(sqrtf(norms[2 * ck.item]), 10.f), an = sqrtf(norms[2 * ck.item + 1]);
+  const float trust = (wn == 0.f || an == 0.f) ? 1.f : wn / an;
+  if (trust_out != nullptr && ck.start == 0 && threadIdx.x == 0) trust_out[ck.item] = trust;
+  const float scale = h.lr[0] * trust;
+  for (long long j = ck.start + threadIdx.x; j < c_end; j += 256) {
+    float pk = it.p[j];
+    const float as = it.m[j] / (sqrtf(it.v[j]) + h.eps) + h.wd * pk;
+    pk -= scale * as;
+    it.p[j] = pk;
+    if (it.shadow != nullptr) {
+      if (it.shadow_f32) static_cast<float*>(it.shadow)[j] = pk;
+      else static_cast<__half*>(it.shadow)[j] = __float2half_rn(pk);
+    }
+  }
+}
+
+// out[0] += sum over every tensor of the table of g^2  (global gradient norm for clip_grad_norm_)
+__global__ void __launch_bounds__(256)
+grad_sqnorm_kernel(const cdr_opt_item* __restrict__ items, const cdr_opt_chunk* __restrict__ chunks,
+                   float* __restrict__ out) {
+  __shared__ float red[8];
+  const cdr_opt_chunk ck = chunks[blockIdx.x];
+  const cdr_opt_item it = items[ck.item];
+  const long long c_end = ck.start + CDR_OPT_CHUNK < it.n ? ck.start + CDR_OPT_CHUNK : it.n;
+  float s = 0.f;
+  for (long long j = ck.start + threadIdx.x; j < c_end; j += 256) {
+    const float g = it.g[j];
+    s += g * g;
+  }
+  const float t = block_sum(s, red);
+  if (threadIdx.x == 0 && t != 0.f) atomicAdd(out, t);
+}
+
+// coef[0] = min(1, max_norm / (sqrt(sq[0]) + 1e-6))   (torch.nn.utils.clip_grad_norm_)
+__global__ void clip_coef_kernel(const float* sq, float max_norm, float* coef, float* norm_out) {
+  const float n = sqrtf(sq[0]);
+  if (norm_out) norm_out[0] = n;
+  coef[0] = fminf(1.f, max_norm / (n + 1e-6f));
+}
+
+static int opt_check(const cdr_opt_args* a, const char* who) {
+  CDR_REQUIRE(a != nullptr && a->items != nullptr && a->count > 0, "%s: bad table", who);
+  CDR_REQUIRE(a->chunks != nullptr && a->n_chunks > 0, "%s: bad chunk table", who);
+  CDR_REQUIRE(a->lr != nullptr && a->step != nullptr, "%s: lr and step must be device pointers", who);
+  return CDR_OK;
+}
+
+}  // namespace cdr
+
+using namespace cdr;
+
+extern "C" {
+
+int cdr_adam_multi(const cdr_opt_args* a, void* stream) {
+  if (int rc = opt_check(a, "cdr_adam_multi")) return rc;
+  CDR_REQUIRE(a->mode == CDR_OPT_ADAMW_TORCH || a->mode == CDR_OPT_ADAMW_HF, "cdr_adam_multi: unknown mode %d", a->mode);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  opt_step_inc_kernel<<<1, 1, 0, st>>>(a->step);
+  CDR_LAUNCH_CHECK();
+  OptHyper h{a->beta1, a->beta2, a->eps, a->weight_decay, a->lr, a->step, a->grad_scale, a->mode};
+  adam_multi_kernel<<<a->n_chunks, 256, 0, st>>>(a->items, a->chunks, h);
+  CDR_LAUNCH_CHECK();
+  return CDR_OK;
+}
+
+int cdr_lamb_multi(const cdr_opt_args* a, void* stream) {
+  if (int rc = opt_check(a, "cdr_lamb_multi")) return rc;
+  CDR_REQUIRE(a->norms != nullptr, "cdr_lamb_multi: norms scratch (2 floats per tensor) is required");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  opt_step_inc_kernel<<<1, 1, 0, st>>>(a->step);
+  CDR_LAUNCH_CHECK();
+  CDR_CUDA(cudaMemsetAsync(a->norms, 0, sizeof(float) * 2 * a->count, st));
+  OptHyper h{a->beta1, a->beta2, a->eps, a->weight_decay, a->lr, a->step, a->grad_scale, 0};
+  lamb_phase1_kernel<<<a->n_chunks, 256, 0, st>>>(a->items, a->chunks, h, a->norms);
+  CDR_LAUNCH_CHECK();
+  lamb_phase2_kernel<<<a->n_chunks, 256, 0, st>>>(a->items, a->chunks, h, a->norms, a->trust);
+  CDR_LAUNCH_CHECK();
+  return CDR_OK;
+}
+
+int cdr_grad_sqnorm_multi(const cdr_opt_item* items, const cdr_opt_chunk* chunks, int32_t n_chunks, float* sq_accum,
+                          void* stream) {
+  CDR_REQUIRE(items && chunks && n_chunks > 0 && sq_accum, "cdr_grad_sqnorm_multi: bad arguments");
+  grad_sqnorm_kernel<<<n_chunks, 256, 0, static_cast<cudaStream_t>(stream)>>>(items, chunks, sq_accum);
+  CDR_LAUNCH_CHECK();
+  return CDR_OK;
+}
+
+int cdr_grad_clip_coef(const float* sq, float max_norm, float* coef, float* norm_out, void* stream) {
+  CDR_REQUIRE(sq && coef, "cdr_grad_clip_coef: bad arguments");
+  clip_coef_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(sq, max_norm, coef, norm_out);
+  CDR_LAUNCH_CHECK();
+  return CDR_OK;
+}
+
+}  // extern "C"

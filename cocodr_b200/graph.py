@@ -32,7 +32,8 @@ class GraphedTrainStep:
         optimizer.zero_grad(set_to_none=True)
         from . import kernels
         n0 = kernels.launches
-        ops.FORCE_SHADOW_REFRESH = True  # the captured sequence must contain the weight-shadow cast
+        # the captured sequence must contain the weight-shadow cast -- unless the optimizer rewrites the shadows itself
+        ops.FORCE_SHADOW_REFRESH = not getattr(optimizer, "manages_shadows", False)
         try:
             with torch.cuda.graph(self.graph):
                 self.static_loss = self._forward_backward()

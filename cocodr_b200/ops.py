@@ -95,10 +95,28 @@ class ShadowSet:
         for sh in self.layers:
             sh.managed = True
         self.ptr_key = self.ver_key = self.table = None
+        self._srcs = None
         self.max_n = 0
+
+    def mark_fresh(self):
+        """The shadows were just rewritten by a fused optimizer step (optim.py): re-snapshot the parameter versions
+        so the next forward does not cast them again."""
+        if self._srcs is not None:
+            self.ptr_key = tuple(t.data_ptr() for srcs in self._srcs for t in srcs)
+            self.ver_key = tuple(t._version for srcs in self._srcs for t in srcs)
+
+    def pairs(self, per_layer_srcs):
+        """[(parameter, shadow view, is_f32)] for every shadowed parameter (allocates the shadows if needed)."""
+        self.refresh(per_layer_srcs)
+        out = []
+        for sh, srcs in zip(self.layers, per_layer_srcs):
+            for (src, dst), param in zip(sh.pairs(*srcs), srcs):
+                out.append((param, dst, dst.dtype == torch.float32))
+        return out
 
     def refresh(self, per_layer_srcs):
         """per_layer_srcs[i] = (wq, bq, wk, bk, wv, bv, wo, wi, wo2) of layer i."""
+        self._srcs = per_layer_srcs
         ptr_key = tuple(t.data_ptr() for srcs in per_layer_srcs for t in srcs)
         ver_key = tuple(t._version for srcs in per_layer_srcs for t in srcs)
         if ptr_key == self.ptr_key and ver_key == self.ver_key and not FORCE_SHADOW_REFRESH:

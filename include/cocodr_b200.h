@@ -113,6 +113,56 @@ typedef struct cdr_cast_item {
 int cdr_cast_multi(const cdr_cast_item* items_device, int32_t count, int64_t max_n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Fused multi-tensor optimizers (SURVEY f-4).  Replace the per-tensor Python loops of the reference's optimizers
+ * -- utils/lamb.py Lamb.step (ANCE/utils/lamb.py:61-121), transformers.AdamW / torch.optim.AdamW
+ * (ANCE/drivers/run_ann.py:134-147) -- and torch.nn.utils.clip_grad_norm_ (run_ann.py:345-352) with one launch
+ * per parameter group; the same pass writes the fp16 (or packed fp32) operand shadow of each parameter.
+ * The table lives in DEVICE memory; p, g, m, v, shadow must be 16-byte aligned.  lr / step / grad_scale are
+ * device scalars (CUDA-graph friendly); `step` (fp32 counter) is incremented by the call.
+ * ---------------------------------------------------------------------------------------------- */
+enum { CDR_OPT_ADAMW_TORCH = 0, CDR_OPT_ADAMW_HF = 1 };
+typedef struct cdr_opt_item {
+  float* p;        /* parameter, updated in place */
+  const float* g;  /* gradient */
+  float* m;        /* exp_avg */
+  float* v;        /* exp_avg_sq */
+  void* shadow;    /* optional copy of the updated parameter: fp16, or fp32 when shadow_f32 != 0 */
+  int64_t n;
+  int32_t shadow_f32;
+  int32_t reserved; /* set to 1 when p / g / m / v are not all 16-byte aligned (or shadow not 8-byte): scalar path */
+} cdr_opt_item;
+/* Work list: block b of a launch processes elements [start, start + CDR_OPT_CHUNK) of tensor `item`; the caller
+ * enumerates every chunk of every tensor once (ceil(n / CDR_OPT_CHUNK) entries per tensor). */
+#define CDR_OPT_CHUNK 16384
+typedef struct cdr_opt_chunk {
+  int64_t start;
+  int32_t item;
+  int32_t reserved;
+} cdr_opt_chunk;
+typedef struct cdr_opt_args {
+  const cdr_opt_item* items;   /* device */
+  const cdr_opt_chunk* chunks; /* device */
+  int32_t count;               /* tensors */
+  int32_t n_chunks;
+  int32_t mode;                /* cdr_adam_multi: CDR_OPT_ADAMW_* */
+  int32_t reserved;
+  float beta1, beta2, eps, weight_decay;
+  const float* lr;           /* device scalar */
+  float* step;               /* device scalar, += 1 */
+  const float* grad_scale;   /* device scalar multiplied into every gradient (clip coefficient / unscale), or NULL */
+  float* norms;              /* cdr_lamb_multi: device scratch, 2 floats per tensor */
+  float* trust;              /* cdr_lamb_multi: optional device [count] trust ratios (lamb.py:114-116) */
+} cdr_opt_args;
+int cdr_adam_multi(const cdr_opt_args* args, void* stream);
+int cdr_lamb_multi(const cdr_opt_args* args, void* stream);
+/* torch.nn.utils.clip_grad_norm_ in two steps: sq_accum[0] += sum of g^2 over every gradient of a table (call once
+ * per parameter group on a zeroed scalar), then coef[0] = min(1, max_norm / (sqrt(sq[0]) + 1e-6)) and, optionally,
+ * norm_out[0] = sqrt(sq[0]).  The coefficient is consumed on the device as cdr_opt_args.grad_scale. */
+int cdr_grad_sqnorm_multi(const cdr_opt_item* items, const cdr_opt_chunk* chunks, int32_t n_chunks, float* sq_accum,
+                          void* stream);
+int cdr_grad_clip_coef(const float* sq, float max_norm, float* coef, float* norm_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Fused multi-head attention (K3): softmax(Q K^T * scale + key_bias) V on tcgen05, head_dim 64,
  * seq_len <= 512 (one 128 x 128 tile up to 128, tiled above), straight from / to the packed QKV projection.  Replaces HF
  * eager_attention_forward / SDPA inside BertSelfAttention (reached through ANCE/model/models.py:226,
