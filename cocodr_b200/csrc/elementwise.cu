@@ -2,6 +2,7 @@
 // fp16 activations (the LN halves of K4/K6), column sums for bias gradients, fp32->fp16 casts.
 // One warp per row, 16-byte vector accesses, fp32 statistics.  hidden % 8 == 0, hidden <= 1024 * 2.
 #include "cdr_common.cuh"
+#include "peer.cuh"
 
 namespace cdr {
 
@@ -369,6 +370,11 @@ ln_bwd_cols_kernel(const __half* __restrict__ dy, const __half* __restrict__ x, 
 //   backward: phase A, warp per row -> dx and the per-row scalars; phase B, thread per 8 columns over the rows of
 //             the SAME staged tile -> dgamma / dbeta / bias-gradient partial sums kept in registers across all
 //             tiles of the block, one round of atomics per block at the end.
+struct LnPush {          // optional fused all-gather of the CLS rows (cdr_ln_fwd_push); world == 0: off
+  cdr_peer_args pa;
+  int first_seq, n_push;
+};
+
 constexpr int LNS_ROWS = 8;      // rows per tile == warps per block
 constexpr int LNS_THREADS = 256;
 constexpr int LNS_STAGES = 3;
@@ -384,7 +390,7 @@ template <int VPL>
 __global__ void __launch_bounds__(LNS_THREADS, 2)
 ln_fwd_staged_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                      __half* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                     float* __restrict__ cls_out, int rows, int hidden, int seq_len, float eps) {
+                     float* __restrict__ cls_out, int rows, int hidden, int seq_len, float eps, const LnPush push) {
   extern __shared__ __align__(128) uint8_t lns_smem[];
   __shared__ uint64_t full[LNS_STAGES];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -442,6 +448,12 @@ ln_fwd_staged_kernel(const __half* __restrict__ x, const float* __restrict__ gam
           for (int k = 0; k < 8; ++k) o[k] = (v[i][k] - mean) * rstd * g[i][k] + b[i][k];
           store8_h(y + static_cast<long long>(row) * hidden + c, o);
           if (is_cls) store8_f(cls_out + static_cast<long long>(row / seq_len) * hidden + c, o);
+          if (push.pa.world > 0 && (row % seq_len) == 0 && row / seq_len >= push.first_seq) {
+            // fused all-gather: the CLS row goes straight into slot `rank` of every rank's gather buffer (NVLink)
+            const long long slot = static_cast<long long>(push.pa.rank) * push.n_push + (row / seq_len - push.first_seq);
+            for (int r = 0; r < push.pa.world; ++r)
+              store8_f(static_cast<float*>(push.pa.peer_buf[r]) + slot * hidden + c, o);
+          }
         }
     }
     __syncthreads();  // every warp is done with this stage
@@ -450,6 +462,7 @@ ln_fwd_staged_kernel(const __half* __restrict__ x, const float* __restrict__ gam
       if (nt < n_tiles) issue(nt, stage);
     }
   }
+  if (push.pa.world > 0) peer_signal_grid_done(push.pa, 0);
 }
 
 template <int VPL>
@@ -764,11 +777,14 @@ int cdr_embed_ln_bwd(const void* dy, const int64_t* ids, const float* word, cons
                           out_scale, static_cast<cudaStream_t>(stream));
 }
 
-int cdr_ln_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, float* cls_out,
-               int32_t n_seq, int32_t seq_len, int32_t hidden, float eps, void* stream) {
+static int ln_fwd_impl(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                       float* cls_out, int32_t n_seq, int32_t seq_len, int32_t hidden, float eps, const LnPush& push,
+                       void* stream) {
   if (int rc = check_hidden(hidden)) return rc;
   CDR_REQUIRE(x && gamma && beta && y, "cdr_ln_fwd: null pointer");
   if (n_seq <= 0 || seq_len <= 0) return CDR_OK;
+  CDR_REQUIRE(push.pa.world == 0 || (hidden <= 1024 && (reinterpret_cast<uintptr_t>(x) & 15) == 0),
+              "cdr_ln_fwd_push: needs hidden <= 1024 and a 16-byte aligned input");
   if (hidden <= 1024 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
     const int rows = n_seq * seq_len;
     const size_t smem = static_cast<size_t>(LNS_STAGES) * LNS_ROWS * hidden * 2;
@@ -784,7 +800,7 @@ int cdr_ln_fwd(const void* x, const float* gamma, const float* beta, void* y, fl
     }                                                                                                                \
     ln_fwd_staged_kernel<V><<<grid, LNS_THREADS, smem, st>>>(static_cast<const __half*>(x), gamma, beta,              \
                                                             static_cast<__half*>(y), mean, rstd, cls_out, rows,       \
-                                                            hidden, seq_len, eps);                                   \
+                                                            hidden, seq_len, eps, push);                             \
   } while (0)
     if (vpl <= 1) LNS_FWD(1);
     else if (vpl <= 2) LNS_FWD(2);
@@ -797,6 +813,24 @@ int cdr_ln_fwd(const void* x, const float* gamma, const float* beta, void* y, fl
   return launch_ln_fwd<0>(static_cast<const __half*>(x), nullptr, nullptr, nullptr, nullptr, gamma, beta,
                           static_cast<__half*>(y), mean, rstd, cls_out, n_seq * seq_len, hidden, seq_len, 0, eps,
                           static_cast<cudaStream_t>(stream));
+}
+
+int cdr_ln_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, float* cls_out,
+               int32_t n_seq, int32_t seq_len, int32_t hidden, float eps, void* stream) {
+  LnPush push{};
+  return ln_fwd_impl(x, gamma, beta, y, mean, rstd, cls_out, n_seq, seq_len, hidden, eps, push, stream);
+}
+
+int cdr_ln_fwd_push(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                    float* cls_out, int32_t n_seq, int32_t seq_len, int32_t hidden, float eps, int32_t first_seq,
+                    const cdr_peer_args* peers, void* stream) {
+  if (int rc = peer_check(peers, "cdr_ln_fwd_push")) return rc;
+  CDR_REQUIRE(first_seq >= 0 && first_seq < n_seq, "cdr_ln_fwd_push: first_seq out of range");
+  LnPush push{};
+  push.pa = *peers;
+  push.first_seq = first_seq;
+  push.n_push = n_seq - first_seq;
+  return ln_fwd_impl(x, gamma, beta, y, mean, rstd, cls_out, n_seq, seq_len, hidden, eps, push, stream);
 }
 
 int cdr_ln_bwd(const void* dy, const float* dy_cls, const void* x, const float* gamma, const float* mean,

@@ -111,9 +111,20 @@ def embed_ln_bwd(dy, ids, word, pos, type0, gamma, mean, rstd, dword, dpos, dtyp
     _count(1)
 
 
-def ln_fwd(x, gamma, beta, y, mean, rstd, cls_out, *, n_seq, seq_len, hidden, eps):
+def ln_fwd(x, gamma, beta, y, mean, rstd, cls_out, *, n_seq, seq_len, hidden, eps, push=None):
+    """push = (peer.PeerExchange, first_seq): the CLS rows of sequences >= first_seq are also written into every
+    rank's gather buffer by the same kernel (fused all-gather over NVLink, cdr_ln_fwd_push)."""
     _need_cuda(x, y)
     assert x.dtype == torch.float16 and y.dtype == torch.float16
+    if push is not None:
+        xchg, first_seq = push
+        assert n_seq - first_seq == xchg.n_rows and hidden == xchg.dim
+        a = xchg.push_args()
+        _run("cdr_ln_fwd_push", lambda: _lib_().cdr_ln_fwd_push(
+            _p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), _p(cls_out), _i32(n_seq), _i32(seq_len), _i32(hidden),
+            _f32(eps), _i32(first_seq), C.byref(a), stream_ptr()))
+        _count(1)
+        return
     _run("cdr_ln_fwd", lambda: _lib_().cdr_ln_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), _p(cls_out), _i32(n_seq),
                              _i32(seq_len), _i32(hidden), _f32(eps), stream_ptr()))
     _count(1)

@@ -23,7 +23,7 @@ import torch.distributed as dist
 from torch import nn
 from transformers import BertConfig, BertForSequenceClassification, BertTokenizer
 
-from . import ops
+from . import ops, peer
 from .bert import BertModel
 from .dro_loss import AverageMeter, DROGreedyLoss, iDROLoss
 
@@ -205,14 +205,48 @@ class BertDot_InBatch_NLL_LN(BertDot_NLL_LN):
     ``input_ids_b``, when given, are appended to the key set).  ERM / iDRO / DRO-greedy routing of the
     per-sample losses is inherited unchanged."""
 
+    peer_gather = False  # enable_peer_gather(): exchange the passage embeddings through peer memory, not NCCL
+
+    def enable_peer_gather(self, on=True):
+        """Multi-GPU, one node: all-gather the passage CLS embeddings by letting the last LayerNorm kernel store them
+        into every rank's symmetric buffer over NVLink (peer.py) and reduce-scatter their gradients the same way."""
+        self.peer_gather = bool(on)
+        self._xchg = None
+        return self
+
+    def _peer_exchange(self, q_ids, a_ids, b_ids):
+        if not (self.peer_gather and _world() > 1) or b_ids is not None or q_ids.shape != a_ids.shape:
+            return None
+        if not torch.is_grad_enabled():
+            return None
+        B, H = a_ids.shape[0], self.config.hidden_size
+        x = getattr(self, "_xchg", None)
+        if x is None or x.n_rows != B or x.dim != H:
+            x = self._xchg = peer.PeerExchange(B, H, a_ids.device)
+        return x
+
     def forward_model(self, query_ids, attention_mask_q, input_ids_a=None, attention_mask_a=None, input_ids_b=None,
                       attention_mask_b=None, is_query=True, group_ids=None):
         if input_ids_a is None:
             return super().forward_model(query_ids, attention_mask_q, is_query=is_query)
-        embs = self._towers(query_ids, attention_mask_q, input_ids_a, attention_mask_a, input_ids_b, attention_mask_b)
-        q_embs = embs[0]
-        B = q_embs.shape[0]
-        keys = gather_with_grad(embs[1])
+        xchg = self._peer_exchange(query_ids, input_ids_a, input_ids_b)
+        if xchg is not None:
+            # fused path: the last LayerNorm kernel writes the passage CLS rows into every rank's gather buffer
+            xchg.begin_step()
+            ops.CLS_PUSH = (xchg, query_ids.shape[0])
+            try:
+                embs = self._towers(query_ids, attention_mask_q, input_ids_a, attention_mask_a)
+            finally:
+                ops.CLS_PUSH = None
+            q_embs = embs[0]
+            B = q_embs.shape[0]
+            keys = peer.gather_passages(embs[1], xchg)
+        else:
+            embs = self._towers(query_ids, attention_mask_q, input_ids_a, attention_mask_a, input_ids_b,
+                                attention_mask_b)
+            q_embs = embs[0]
+            B = q_embs.shape[0]
+            keys = gather_with_grad(embs[1])
         offset = _rank() * B
         if len(embs) == 3:
             keys = torch.cat([keys, gather_with_grad(embs[2])], 0)

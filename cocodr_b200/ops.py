@@ -17,6 +17,7 @@ from . import kernels as K
 _GRAD_SCALE = 1024.0
 FORCE_SHADOW_REFRESH = False  # set while a CUDA graph is being captured (graph.py)
 GRAD_SYNC = None              # an active gradsync.GradSync collects the flat gradient buffers of each backward
+CLS_PUSH = None               # (peer.PeerExchange, first_seq): the last LayerNorm pushes CLS rows to every rank (peer.py)
 
 
 def set_grad_scale(s: float):
@@ -205,7 +206,8 @@ class BertLayerFn(torch.autograd.Function):
         y = _f16(T, H, dev=dev)
         mean2, rstd2 = _f32(T, dev=dev), _f32(T, dev=dev)
         cls = _f32(n_seq, H, dev=dev) if emit_cls else None
-        K.ln_fwd(y2, g2, be2, y, mean2, rstd2, cls, n_seq=n_seq, seq_len=L, hidden=H, eps=eps)
+        push = CLS_PUSH if emit_cls else None
+        K.ln_fwd(y2, g2, be2, y, mean2, rstd2, cls, n_seq=n_seq, seq_len=L, hidden=H, eps=eps, push=push)
         ctx.save_for_backward(x, key_bias, qkv, att, lse, y1, x1, mean1, rstd1, gp, gl, y2, mean2, rstd2, g1, g2)
         ctx.shadow_w = (sh.wqkv, sh.wo, sh.wi, sh.wo2)
         ctx.meta = (n_seq, L, heads, I, emit_cls, _GRAD_SCALE)

@@ -111,6 +111,27 @@ def main():
             err = (p.grad - ref_g).abs().max().item()
             assert err <= 1e-5 + 1e-3 * ref_g.abs().max().item(), (n, err)
 
+    # 6. peer-memory exchange (cdr_ln_fwd_push / cdr_peer_*): the last LayerNorm pushes the passage CLS rows into
+    #    every rank's symmetric buffer and the gradients come back the same way == the NCCL all-gather path
+    model.zero_grad(set_to_none=True)
+    l_nccl = model(qi, qm, pi, pm, weights=w)[0]
+    l_nccl.backward()
+    g_nccl = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+    model.enable_peer_gather(True)
+    for rep in range(3):  # several rounds: epochs advance, buffers are reused
+        model.zero_grad(set_to_none=True)
+        l_peer = model(qi, qm, pi, pm, weights=w)[0]
+        l_peer.backward()
+        torch.cuda.synchronize()
+        assert model._xchg is not None and model._xchg.epoch == rep + 1
+        assert abs(l_peer.item() - l_nccl.item()) <= 1e-5 * max(1.0, abs(l_nccl.item())), (l_peer.item(), l_nccl.item())
+        for n, p in model.named_parameters():
+            if n in g_nccl:
+                err = (p.grad - g_nccl[n]).abs().max().item()
+                assert err <= 1e-6 + 2e-3 * g_nccl[n].abs().max().item(), (n, err)
+        dist.barrier()
+    model.enable_peer_gather(False)
+
     dist.barrier()
     if rank == 0:
         print(f"MULTIGPU_OK world={world}")
