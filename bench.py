@@ -196,7 +196,8 @@ def run_ours(args):
             sync = GradSync(model)
     if world > 1 and not args.nccl_gather:
         model.enable_peer_gather(True)  # CLS all-gather / gradient reduce-scatter through peer memory (NVLink stores)
-    use_graph = world == 1 and not args.no_graph
+    # N > 1: the NCCL gradient all-reduces and the peer-memory exchange are captured into the same CUDA graph
+    use_graph = not args.no_graph and (world == 1 or not args.ddp)
     if args.torch_adamw:  # library optimizer (A/B only): torch's fused AdamW + the encoder's own weight-shadow cast
         opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=5e-6, fused=True,
                                 capturable=use_graph)
@@ -234,7 +235,8 @@ def run_ours(args):
         # the repo's public step helper: the whole step captured once, replayed per batch
         from cocodr_b200.graph import GraphedTrainStep
         ids0, mask0 = dev_batches[0]
-        graphed = GraphedTrainStep(net, opt, (ids0[:B], mask0[:B], ids0[B:], mask0[B:], None, None, True, None, ones))
+        graphed = GraphedTrainStep(net, opt, (ids0[:B], mask0[:B], ids0[B:], mask0[B:], None, None, True, None, ones),
+                                   backward_ctx=sync)
 
         def step(ids, mask):  # noqa: F811
             return graphed(ids[:B], mask[:B], ids[B:], mask[B:])
@@ -405,6 +407,17 @@ def run_ours(args):
                 "scan": scan_res}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # Teardown after the result is out.  A CUDA graph that captured NCCL work must be released before the
+        # communicator goes away; a watchdog ends the process if the (already useless) teardown ever wedges.
+        def _bail():
+            time.sleep(20)
+            os._exit(0)
+        threading.Thread(target=_bail, daemon=True).start()
+        if graphed is not None:
+            graphed.graph.reset()
+            graphed = None
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
 
 

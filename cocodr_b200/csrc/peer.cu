@@ -15,9 +15,11 @@
 
 namespace cdr {
 
-__global__ void peer_wait_kernel(const uint32_t* flags, int world, uint32_t epoch) {
-  if (threadIdx.x == 0) peer_wait_all(flags, world, epoch);
+__global__ void peer_wait_kernel(const uint32_t* flags, int world, const uint32_t* epoch) {
+  if (threadIdx.x == 0) peer_wait_all(flags, world, *reinterpret_cast<const volatile uint32_t*>(epoch));
 }
+
+__global__ void peer_next_epoch_kernel(uint32_t* epoch) { epoch[0] += 1u; }
 
 // src [world * rows, dim] fp32: row block r -> slot `rank` of rank r's receive buffer [world][rows, dim]
 __global__ void __launch_bounds__(256)
@@ -36,8 +38,8 @@ peer_scatter_kernel(const float* __restrict__ src, long long per_block, cdr_peer
 // out[i] = sum_r recv[r][i] once every rank's contribution for `epoch` has landed
 __global__ void __launch_bounds__(256)
 peer_reduce_kernel(const float* __restrict__ recv, const uint32_t* __restrict__ flags, int world, long long n,
-                   uint32_t epoch, float* __restrict__ out) {
-  if (threadIdx.x == 0) peer_wait_all(flags, world, epoch);
+                   const uint32_t* epoch, float* __restrict__ out) {
+  if (threadIdx.x == 0) peer_wait_all(flags, world, *reinterpret_cast<const volatile uint32_t*>(epoch));
   __syncthreads();
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 4;
   for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
@@ -53,7 +55,7 @@ peer_reduce_kernel(const float* __restrict__ recv, const uint32_t* __restrict__ 
 int peer_check(const cdr_peer_args* pa, const char* who) {
   CDR_REQUIRE(pa != nullptr, "%s: null peer args", who);
   CDR_REQUIRE(pa->world >= 1 && pa->world <= 8 && pa->rank >= 0 && pa->rank < pa->world, "%s: bad world / rank", who);
-  CDR_REQUIRE(pa->done_counter != nullptr, "%s: done_counter is required", who);
+  CDR_REQUIRE(pa->done_counter != nullptr && pa->epoch != nullptr, "%s: done_counter and epoch are required", who);
   for (int r = 0; r < pa->world; ++r)
     CDR_REQUIRE(pa->peer_buf[r] != nullptr && pa->peer_flag[r] != nullptr, "%s: null peer pointer %d", who, r);
   return CDR_OK;
@@ -65,8 +67,15 @@ using namespace cdr;
 
 extern "C" {
 
-int cdr_peer_wait(const uint32_t* local_flags, int32_t world, uint32_t epoch, void* stream) {
-  CDR_REQUIRE(local_flags != nullptr && world >= 1 && world <= 8, "cdr_peer_wait: bad arguments");
+int cdr_peer_next_epoch(uint32_t* epoch, void* stream) {
+  CDR_REQUIRE(epoch != nullptr, "cdr_peer_next_epoch: null pointer");
+  peer_next_epoch_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(epoch);
+  CDR_LAUNCH_CHECK();
+  return CDR_OK;
+}
+
+int cdr_peer_wait(const uint32_t* local_flags, int32_t world, const uint32_t* epoch, void* stream) {
+  CDR_REQUIRE(local_flags != nullptr && epoch != nullptr && world >= 1 && world <= 8, "cdr_peer_wait: bad arguments");
   peer_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(local_flags, world, epoch);
   CDR_LAUNCH_CHECK();
   return CDR_OK;
@@ -84,9 +93,9 @@ int cdr_peer_scatter_rows(const float* src, int32_t rows, int32_t dim, const cdr
   return CDR_OK;
 }
 
-int cdr_peer_reduce_slots(const float* recv, const uint32_t* local_flags, int32_t world, int64_t n, uint32_t epoch,
-                          float* out, void* stream) {
-  CDR_REQUIRE(recv && local_flags && out && world >= 1 && world <= 8 && n > 0 && n % 4 == 0,
+int cdr_peer_reduce_slots(const float* recv, const uint32_t* local_flags, int32_t world, int64_t n,
+                          const uint32_t* epoch, float* out, void* stream) {
+  CDR_REQUIRE(recv && local_flags && epoch && out && world >= 1 && world <= 8 && n > 0 && n % 4 == 0,
               "cdr_peer_reduce_slots: bad arguments (n must be a multiple of 4)");
   long long blocks = (n / 4 + 255) / 256;
   if (blocks > 2 * sm_count()) blocks = 2 * sm_count();

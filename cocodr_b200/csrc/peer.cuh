@@ -23,7 +23,8 @@ __device__ __forceinline__ void peer_signal_grid_done(const cdr_peer_args& pa, i
     const unsigned int prev = atomicAdd(pa.done_counter, 1u);
     if (prev == total - 1) {
       __threadfence_system();
-      for (int r = 0; r < pa.world; ++r) st_release_sys(pa.peer_flag[r] + flag_set * 8 + pa.rank, pa.epoch);
+      const uint32_t epoch = *reinterpret_cast<const volatile uint32_t*>(pa.epoch);
+      for (int r = 0; r < pa.world; ++r) st_release_sys(pa.peer_flag[r] + flag_set * 8 + pa.rank, epoch);
       *pa.done_counter = 0u;
     }
   }

@@ -18,8 +18,10 @@ class GraphedTrainStep:
     calling convention, run_ann.py:320-325).  The optimizer must be capturable (e.g.
     ``torch.optim.AdamW(..., fused=True, capturable=True)``)."""
 
-    def __init__(self, model, optimizer, example_inputs, warmup=3):
-        self.model, self.optimizer = model, optimizer
+    def __init__(self, model, optimizer, example_inputs, warmup=3, backward_ctx=None):
+        """backward_ctx: optional context manager entered around ``loss.backward()`` (e.g. a ``gradsync.GradSync``:
+        its side-stream NCCL all-reduces are captured into the same graph)."""
+        self.model, self.optimizer, self.backward_ctx = model, optimizer, backward_ctx
         self.static_inputs = [t.clone() if torch.is_tensor(t) else t for t in example_inputs]
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -45,7 +47,11 @@ class GraphedTrainStep:
     def _forward_backward(self):
         out = self.model(*self.static_inputs)
         loss = out[0] if isinstance(out, (tuple, list)) else out
-        loss.backward()
+        if self.backward_ctx is not None:
+            with self.backward_ctx:
+                loss.backward()
+        else:
+            loss.backward()
         return loss
 
     def _eager_step(self):

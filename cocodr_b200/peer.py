@@ -22,7 +22,7 @@ from ._lib import check, stream_ptr
 
 
 class PeerArgs(C.Structure):
-    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("epoch", C.c_uint32), ("reserved", C.c_int32),
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("epoch", C.c_void_p),
                 ("peer_buf", C.c_void_p * 8), ("peer_flag", C.c_void_p * 8), ("done_counter", C.c_void_p)]
 
 
@@ -40,13 +40,13 @@ class PeerExchange:
         self.flags.zero_()
         self._h = [symm_mem.rendezvous(t, group=self.group) for t in (self.gather, self.recv, self.flags)]
         self.done = torch.zeros(1, dtype=torch.int32, device=device)
-        self.epoch = 0
+        self.epoch_dev = torch.zeros(1, dtype=torch.int32, device=device)  # advanced on the device: graph capturable
         torch.cuda.synchronize(device)
         dist.barrier(self.group)  # every rank's flags are zeroed before anyone publishes an epoch
 
     def _args(self, which):
         a = PeerArgs()
-        a.world, a.rank, a.epoch = self.world, self.rank, self.epoch
+        a.world, a.rank, a.epoch = self.world, self.rank, self.epoch_dev.data_ptr()
         for r in range(self.world):
             a.peer_buf[r] = self._h[which].buffer_ptrs[r]
             a.peer_flag[r] = self._h[2].buffer_ptrs[r]
@@ -56,7 +56,11 @@ class PeerExchange:
     # ---- forward -------------------------------------------------------------------------------
     def begin_step(self):
         """A new exchange round: call once per training step before the encoder runs."""
-        self.epoch += 1
+        check(_lib.load().cdr_peer_next_epoch(C.c_void_p(self.epoch_dev.data_ptr()), stream_ptr()), "cdr_peer_next_epoch")
+
+    @property
+    def epoch(self):
+        return int(self.epoch_dev.item())
 
     def push_args(self):
         """cdr_peer_args for cdr_ln_fwd_push (target: the gather buffers)."""
@@ -64,7 +68,7 @@ class PeerExchange:
 
     def wait_gather(self):
         check(_lib.load().cdr_peer_wait(C.c_void_p(self.flags.data_ptr()), C.c_int32(self.world),
-                                        C.c_uint32(self.epoch), stream_ptr()), "cdr_peer_wait")
+                                        C.c_void_p(self.epoch_dev.data_ptr()), stream_ptr()), "cdr_peer_wait")
         return self.gather
 
     # ---- backward ------------------------------------------------------------------------------
@@ -78,7 +82,7 @@ class PeerExchange:
         out = torch.empty(self.n_rows, self.dim, dtype=torch.float32, device=g.device)
         check(lib.cdr_peer_reduce_slots(C.c_void_p(self.recv.data_ptr()), C.c_void_p(self.flags[8:].data_ptr()),
                                         C.c_int32(self.world), C.c_int64(self.n_rows * self.dim),
-                                        C.c_uint32(self.epoch), C.c_void_p(out.data_ptr()), stream_ptr()),
+                                        C.c_void_p(self.epoch_dev.data_ptr()), C.c_void_p(out.data_ptr()), stream_ptr()),
               "cdr_peer_reduce_slots")
         return out
 

@@ -106,13 +106,13 @@ int cdr_colsum_f16(const void* x, float* out, int64_t rows, int64_t cols, int64_
  * passage CLS embeddings / reduce-scatter of their gradients (the reference's dist.all_gather in
  * COCO/modeling.py:182-190; K9' uses the same exchange) with stores into symmetric buffers: every rank holds
  * the base pointer of the SAME allocation on every rank (peer_buf[r], peer_flag[r]; index `rank` is its own).
- * peer_flag[r] points at 16 uint32 (two sets of 8: forward, backward), zero-initialised once; `epoch` must grow
- * by one per use.  done_counter: one zero-initialised local uint32 of scratch.
+ * peer_flag[r] points at 16 uint32 (two sets of 8: forward, backward), zero-initialised once.  `epoch` is a LOCAL
+ * device counter (so the whole exchange is CUDA-graph capturable): cdr_peer_next_epoch advances it once per
+ * training step, identically on every rank.  done_counter: one zero-initialised local uint32 of scratch.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct cdr_peer_args {
   int32_t world, rank;
-  uint32_t epoch;
-  int32_t reserved;
+  const uint32_t* epoch;
   void* peer_buf[8];
   uint32_t* peer_flag[8];
   uint32_t* done_counter;
@@ -123,13 +123,14 @@ typedef struct cdr_peer_args {
 int cdr_ln_fwd_push(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
                     float* cls_out, int32_t n_seq, int32_t seq_len, int32_t hidden, float eps, int32_t first_seq,
                     const cdr_peer_args* peers, void* stream);
-/* hold the stream until local_flags[0..world) all carry `epoch` (or a later one) */
-int cdr_peer_wait(const uint32_t* local_flags, int32_t world, uint32_t epoch, void* stream);
+int cdr_peer_next_epoch(uint32_t* epoch, void* stream);
+/* hold the stream until local_flags[0..world) all carry *epoch (or a later one) */
+int cdr_peer_wait(const uint32_t* local_flags, int32_t world, const uint32_t* epoch, void* stream);
 /* reduce-scatter, push side: row block r of src [world*rows, dim] -> slot `rank` of rank r's receive buffer
  * [world][rows, dim]; raises flag set 1.  Pull side: out[rows*dim] = sum over slots once all flags arrived. */
 int cdr_peer_scatter_rows(const float* src, int32_t rows, int32_t dim, const cdr_peer_args* peers, void* stream);
-int cdr_peer_reduce_slots(const float* recv, const uint32_t* local_flags, int32_t world, int64_t n, uint32_t epoch,
-                          float* out, void* stream);
+int cdr_peer_reduce_slots(const float* recv, const uint32_t* local_flags, int32_t world, int64_t n,
+                          const uint32_t* epoch, float* out, void* stream);
 int cdr_cast_f32_f16(const float* src, void* dst, int64_t n, void* stream);
 /* A whole table of casts in one launch (per-step refresh of all fp16 weight shadows).  The table lives in
  * DEVICE memory; every src/dst must be 16-byte aligned.  dst_f32 != 0 copies fp32 -> fp32 instead. */
