@@ -8,7 +8,7 @@ def run():
 
     from oracle import bert_ref, heads_ref, scan_ref
 
-    from . import _lib, kernels, models, ops, scan
+    from . import _lib, kernels, models, ops, optim, scan
 
     _lib.check(_lib.load().cdr_device_check(), "cdr_device_check")
     torch.cuda.set_device(0)
@@ -42,6 +42,15 @@ def run():
     cos = torch.nn.functional.cosine_similarity(got.flatten(), leaf[gname].grad.flatten(), dim=0).item()
     assert err < 1e-2, f"loss {loss.item()} vs oracle {ref.item()}"
     assert gerr < 0.25 and cos > 0.99, f"grad rel err {gerr}, cosine {cos}"
+    # one fused optimizer step (cdr_adam_multi): parameters move, fp16 operand shadows follow in the same launch
+    opt = optim.AdamW([t for t in m.parameters() if t.requires_grad], lr=1e-3, eps=1e-8, semantics="torch").attach_shadows(m)
+    w_before = dict(m.bert.named_parameters())[gname].detach().clone()
+    opt.step()
+    torch.cuda.synchronize()
+    assert (dict(m.bert.named_parameters())[gname] - w_before).abs().max().item() > 1e-5
+    for param, (dst, is_f32) in m.bert.shadow_map().items():
+        want = param.detach() if is_f32 else param.detach().half()
+        assert torch.equal(dst.view_as(want), want)
     # corpus scan, exact-arithmetic corpus => bit-exact ranks
     Q, P = scan_ref.synth_corpus(20000, 16, 128, seed=5, kind="exact")
     D, I = scan.search(Q.cuda(), P.cuda(), 10)

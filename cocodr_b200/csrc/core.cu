@@ -1,5 +1,6 @@
 // Library core: version, thread-local error text, device check, driver entry point for TMA maps.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -17,7 +18,16 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// SMs the persistent kernels size their grids for.  cdr_set_sm_budget(n) (or CDR_SM_BUDGET in the environment)
+// leaves the remaining SMs to concurrent communication kernels: a persistent GEMM CTA takes a whole SM's shared
+// memory, so an NCCL CTA squatting on one SM would otherwise push that GEMM CTA into a second wave.
+static int g_sm_budget = -1;
+
 int sm_count() {
+  if (g_sm_budget < 0) {
+    const char* e = getenv("CDR_SM_BUDGET");
+    g_sm_budget = e ? atoi(e) : 0;
+  }
   static int cached[64] = {0};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
@@ -26,7 +36,9 @@ int sm_count() {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
     cached[dev] = n;
   }
-  return cached[dev];
+  int n = cached[dev];
+  if (g_sm_budget > 0 && g_sm_budget < n) n = g_sm_budget & ~1;  // even: CTA pairs
+  return n;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -78,6 +90,11 @@ int make_tma_2d_f16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t
 extern "C" {
 
 int cdr_version(void) { return 100; }
+
+int cdr_set_sm_budget(int32_t n) {
+  cdr::g_sm_budget = n > 0 ? n : 0;
+  return CDR_OK;
+}
 
 const char* cdr_last_error(void) { return cdr::g_err; }
 

@@ -16,7 +16,7 @@ import ctypes as C
 
 import torch
 
-from . import _lib
+from . import _lib, kernels
 from ._lib import check, stream_ptr
 
 MODE_TORCH, MODE_HF = 0, 1
@@ -200,6 +200,7 @@ class AdamW(_FusedOptimizer):
                 continue
             a = self._args(tab, group, self.mode)
             check(lib.cdr_adam_multi(C.byref(a), stream_ptr()), "cdr_adam_multi")
+            kernels._count(2)  # step counter + update
             self._finish(tab)
         self._after_step()
         return loss
@@ -225,6 +226,7 @@ class Lamb(_FusedOptimizer):
                 continue
             a = self._args(tab, group)
             check(lib.cdr_lamb_multi(C.byref(a), stream_ptr()), "cdr_lamb_multi")
+            kernels._count(3)  # step counter + two phases
             self._finish(tab)
             for i, p in enumerate(tab["params"]):
                 self.state[p]["trust_ratio"] = tab["trust"][i]

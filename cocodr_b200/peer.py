@@ -17,7 +17,7 @@ import ctypes as C
 import torch
 import torch.distributed as dist
 
-from . import _lib
+from . import _lib, kernels
 from ._lib import check, stream_ptr
 
 
@@ -57,6 +57,7 @@ class PeerExchange:
     def begin_step(self):
         """A new exchange round: call once per training step before the encoder runs."""
         check(_lib.load().cdr_peer_next_epoch(C.c_void_p(self.epoch_dev.data_ptr()), stream_ptr()), "cdr_peer_next_epoch")
+        kernels._count(1)
 
     @property
     def epoch(self):
@@ -69,6 +70,7 @@ class PeerExchange:
     def wait_gather(self):
         check(_lib.load().cdr_peer_wait(C.c_void_p(self.flags.data_ptr()), C.c_int32(self.world),
                                         C.c_void_p(self.epoch_dev.data_ptr()), stream_ptr()), "cdr_peer_wait")
+        kernels._count(1)
         return self.gather
 
     # ---- backward ------------------------------------------------------------------------------
@@ -84,6 +86,7 @@ class PeerExchange:
                                         C.c_int32(self.world), C.c_int64(self.n_rows * self.dim),
                                         C.c_void_p(self.epoch_dev.data_ptr()), C.c_void_p(out.data_ptr()), stream_ptr()),
               "cdr_peer_reduce_slots")
+        kernels._count(2)
         return out
 
 

@@ -31,6 +31,8 @@ int cdr_version(void);
 const char* cdr_last_error(void);
 /* CDR_OK iff the current device has compute capability 10.x */
 int cdr_device_check(void);
+/* Size the grids of the persistent kernels for n SMs (0 = all): leaves SMs to overlapped communication kernels. */
+int cdr_set_sm_budget(int32_t n);
 
 /* ------------------------------------------------------------------------------------------------
  * GEMM   D[M,N] = alpha * A[M,K] * B[N,K]^T  (+ fused epilogue), fp16 operands, fp32 accumulate.
