@@ -301,6 +301,21 @@ int cdr_scan_topk(const cdr_scan_args* args, void* stream);
 int cdr_topk_merge(const float* scores, const int64_t* ids, int32_t n_q, int32_t n_in, int32_t k, float* out_scores,
                    int64_t* out_ids, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Token-record reader (host only; SURVEY f-3): the reference's EmbeddingCache files (ANCE/utils/util.py:316-370;
+ * group variant evaluate/utils/util.py:338-369): fixed-size records [len u32 BE][ids int32 x embedding_size]
+ * (or [group u32 BE][len u32 BE][ids ...]).  The file is mapped once; cdr_records_gather copies a batch of
+ * records (any order, repeats allowed) into caller-owned -- typically pinned -- buffers as padded int32 ids
+ * [n, max_len], byte mask [n, max_len] = [1]*len + [0]*pad (optional), lengths [n] (optional, clipped to max_len)
+ * and group ids [n] (optional; -1 without the group header), using n_threads host threads.
+ * cdr_records_open returns NULL on failure (text in cdr_last_error()).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct cdr_records cdr_records;
+cdr_records* cdr_records_open(const char* path, int64_t record_bytes, int64_t total, int32_t group);
+void cdr_records_close(cdr_records* handle);
+int cdr_records_gather(const cdr_records* handle, const int64_t* keys, int64_t n, int32_t max_len, int32_t* ids,
+                       uint8_t* mask, int32_t* lens, int32_t* groups, int32_t n_threads);
+
 #ifdef __cplusplus
 }
 #endif
