@@ -64,6 +64,7 @@ static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, c
   if constexpr (!A_MN && !B_MN) {
     if (epi == CDR_EPI_BIAS_GELU) return launch_gemm<BN, false, false, CDR_EPI_BIAS_GELU>(ta, tb, p, st);
     if (epi == CDR_EPI_SCAN_FILTER) return launch_gemm<BN, false, false, CDR_EPI_SCAN_FILTER>(ta, tb, p, st);
+    if (epi == CDR_EPI_SCAN_FILTER_Q) return launch_gemm<BN, false, false, CDR_EPI_SCAN_FILTER_Q>(ta, tb, p, st);
   }
   if constexpr (!A_MN && B_MN) {
     if (epi == CDR_EPI_DGELU) return launch_gemm<BN, false, true, CDR_EPI_DGELU>(ta, tb, p, st);
@@ -89,7 +90,8 @@ int gemm_run(const cdr_gemm_args& g, GemmParams p, cudaStream_t st) {
   CDR_REQUIRE(g.a && g.b, "cdr_gemm: null operand");
   CDR_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "cdr_gemm: empty problem M=%lld N=%lld K=%lld", (long long)g.M,
               (long long)g.N, (long long)g.K);
-  CDR_REQUIRE(g.N % 8 == 0 || g.epilogue == CDR_EPI_SCAN_FILTER, "cdr_gemm: N must be a multiple of 8 (N=%lld)",
+  CDR_REQUIRE(g.N % 8 == 0 || g.epilogue == CDR_EPI_SCAN_FILTER || g.epilogue == CDR_EPI_SCAN_FILTER_Q,
+              "cdr_gemm: N must be a multiple of 8 (N=%lld)",
               (long long)g.N);
   CDR_REQUIRE(g.M < (1ll << 31) && g.N < (1ll << 31) && g.K < (1ll << 31), "cdr_gemm: dimension overflow");
   const int a_mn = g.a_major, b_mn = g.b_major;
@@ -141,7 +143,7 @@ int gemm_run(const cdr_gemm_args& g, GemmParams p, cudaStream_t st) {
   CUtensorMap ta, tb;
   int rc;
   if (a_mn) rc = make_tma_2d_f16(&ta, g.a, g.M, g.K, g.lda, 64, GEMM_BK);
-  else rc = make_tma_2d_f16(&ta, g.a, g.K, g.M, g.lda, GEMM_BK, GEMM_BM);
+  else rc = make_tma_2d_f16(&ta, g.a, g.K, p.a_rows_alloc > g.M ? p.a_rows_alloc : g.M, g.lda, GEMM_BK, GEMM_BM);
   if (rc != CDR_OK) return rc;
   if (b_mn) rc = make_tma_2d_f16(&tb, g.b, g.N, g.K, g.ldb, 64, GEMM_BK);
   else rc = make_tma_2d_f16(&tb, g.b, g.K, p.b_rows_alloc > g.N ? p.b_rows_alloc : g.N, g.ldb, GEMM_BK, BN / p.cta_group);
@@ -158,7 +160,8 @@ extern "C" int cdr_gemm(const cdr_gemm_args* g, void* stream) {
     cdr::set_error("cdr_gemm: null args");
     return CDR_EINVAL;
   }
-  CDR_REQUIRE(g->epilogue != CDR_EPI_SCAN_FILTER, "cdr_gemm: CDR_EPI_SCAN_FILTER is internal to cdr_scan_topk");
+  CDR_REQUIRE(g->epilogue != CDR_EPI_SCAN_FILTER && g->epilogue != CDR_EPI_SCAN_FILTER_Q,
+              "cdr_gemm: the scan filter epilogues are internal to cdr_scan_topk");
   CDR_REQUIRE(g->out != nullptr, "cdr_gemm: null output");
   const bool f32 = g->epilogue == CDR_EPI_F32_ATOMIC || g->epilogue == CDR_EPI_F32_STORE;
   CDR_REQUIRE(g->ldo % (f32 ? 4 : 8) == 0, "cdr_gemm: ldo must keep rows 16-byte aligned (ldo=%lld)", (long long)g->ldo);

@@ -34,7 +34,7 @@ constexpr int GEMM_BK = 64;
 #define CDR_GEMM_EPI_WARPS 8
 #endif
 template <int EPI>
-constexpr int GEMM_EW = (EPI == CDR_EPI_SCAN_FILTER) ? 16 : CDR_GEMM_EPI_WARPS;
+constexpr int GEMM_EW = (EPI == CDR_EPI_SCAN_FILTER || EPI == CDR_EPI_SCAN_FILTER_Q) ? 16 : CDR_GEMM_EPI_WARPS;
 template <int EPI>
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EW<EPI>;
 
@@ -61,6 +61,7 @@ struct GemmParams {
   long long row_base;           // global doc index of row 0
   // debug overrides for descriptor probing (0 = default)
   int dbg_lbo, dbg_sbo;
+  long long a_rows_alloc;  // same for A
   long long b_rows_alloc;  // rows of B that physically exist (>= N; 0 = N): lets TMA boxes read zero padding instead of going out of bounds
   int dbg_flags;  // CDR_GEMM_DBG (environment): bit 0 = skip the epilogue math and stores (timing experiments only)
 };
@@ -232,6 +233,27 @@ __device__ __forceinline__ void gemm_filter_commit(const GemmParams& p, const ui
     }
   }
   __syncwarp();
+}
+
+// Scan filter with the QUERIES on the accumulator rows (thread = one query, 32 document columns per chunk): the
+// threshold is a per-thread scalar and a thread reserves the slots of BOTH chunks it holds with one atomicAdd (one
+// atomic round trip per tile and warp) -- no cross-lane traffic at all.
+__device__ __forceinline__ uint32_t gemm_filter_rows_mask(const GemmParams& p, const uint32_t (&acc)[32], int n0, float th) {
+  uint32_t mask = 0u;
+#pragma unroll
+  for (int j = 0; j < 32; ++j)
+    if (n0 + j < p.N && __uint_as_float(acc[j]) >= th) mask |= 1u << j;
+  return mask;
+}
+__device__ __forceinline__ void gemm_filter_rows_commit(const GemmParams& p, const uint32_t (&acc)[32], int q, int n0,
+                                                        uint32_t mask, int base) {
+  unsigned long long* dst = p.cand + static_cast<long long>(q) * p.cand_cap;
+#pragma unroll
+  for (int j = 0; j < 32; ++j)
+    if ((mask >> j) & 1u) {
+      const int pos = base + __popc(mask & ((1u << j) - 1u));
+      if (pos < p.cand_cap) dst[pos] = pack_score_doc(__uint_as_float(acc[j]), static_cast<unsigned int>(p.row_base + n0 + j));
+    }
 }
 
 template <int EPI>
@@ -527,7 +549,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             else mbar_arrive(&tmem_empty[acc]);
           }
         }
-        if constexpr (EPI == CDR_EPI_SCAN_FILTER) {
+        if constexpr (EPI == CDR_EPI_SCAN_FILTER_Q) {
+          const int q = mb + lane;
+          const float th = q < p.M ? __ldg(p.thresh + q) : INFINITY;  // rows beyond the queries admit nothing
+          const uint32_t m0 = gemm_filter_rows_mask(p, r0, n0 + c0 * 32, th);
+          uint32_t m1 = 0u;
+          if constexpr (CPW >= 2) m1 = gemm_filter_rows_mask(p, r1, n0 + c1 * 32, th);
+          if ((m0 | m1) != 0u) {
+            const int base = atomicAdd(p.cand_count + q, __popc(m0) + __popc(m1));
+            gemm_filter_rows_commit(p, r0, q, n0 + c0 * 32, m0, base);
+            if constexpr (CPW >= 2) gemm_filter_rows_commit(p, r1, q, n0 + c1 * 32, m1, base + __popc(m0));
+          }
+        } else if constexpr (EPI == CDR_EPI_SCAN_FILTER) {
           // both chunks reserve first (their atomics are in flight together), then both commit
           uint32_t* fws = reinterpret_cast<uint32_t*>(stg);
           const bool ok0 = n0 + c0 * 32 < p.N, ok1 = (CPW >= 2) && (n0 + c1 * 32 < p.N);

@@ -400,7 +400,20 @@ int cdr_scan_topk(const cdr_scan_args* a, void* stream) {
   CDR_CUDA(cudaMemsetAsync(qpad, 0, sizeof(__half) * static_cast<size_t>(pl.q_rows_pad) * a->dim, st));
   CDR_CUDA(cudaMemcpyAsync(qpad, a->queries, sizeof(__half) * static_cast<size_t>(a->n_q) * a->dim,
                            cudaMemcpyDeviceToDevice, st));
-  {
+  if (a->n_q <= 128) {
+    // HBM-bound regime: queries on the accumulator rows (one 128-row tile), documents stream as the B operand in
+    // 256-row tiles -- two thirds of every pipeline stage are document bytes (half in the other orientation) and the
+    // filter needs no cross-lane work (gemm_filter_rows_chunk)
+    cdr_gemm_args g{};
+    g.a = qpad; g.b = a->docs;
+    g.M = a->n_q; g.N = a->n_docs; g.K = a->dim;
+    g.lda = a->dim; g.ldb = a->ld_docs;
+    g.epilogue = CDR_EPI_SCAN_FILTER_Q; g.split_k = 1; g.alpha = 1.f;
+    GemmParams p{};
+    p.thresh = thresh; p.cand = cand; p.cand_count = count; p.cand_cap = pl.cap; p.row_base = 0;
+    p.a_rows_alloc = pl.q_rows_pad;
+    if (int rc = gemm_run(g, p, st)) return rc;
+  } else {
     cdr_gemm_args g{};
     g.a = a->docs; g.b = qpad;
     g.M = a->n_docs; g.N = a->n_q; g.K = a->dim;

@@ -52,7 +52,8 @@ enum {
                                 optional colsum[n] += colsum_scale * sum_m out[m,n] (the bias gradient) */
   CDR_EPI_F32_ATOMIC = 4,    /* out32 += alpha*acc  (red.add, for split-K wgrad)                  */
   CDR_EPI_F32_STORE = 5,     /* out32 = alpha*acc                                                 */
-  CDR_EPI_SCAN_FILTER = 6    /* internal: threshold-filter scores into candidate buffers          */
+  CDR_EPI_SCAN_FILTER = 6,   /* internal: threshold-filter scores into candidate buffers (docs on M, queries on N) */
+  CDR_EPI_SCAN_FILTER_Q = 7  /* internal: the same with queries on M (<= 128 queries: documents stream as the B operand) */
 };
 
 typedef struct cdr_gemm_args {
@@ -300,6 +301,24 @@ int cdr_scan_topk(const cdr_scan_args* args, void* stream);
 /* merge n_in candidates per query (any order; e.g. all-gathered per-shard top-k lists) into the top k */
 int cdr_topk_merge(const float* scores, const int64_t* ids, int32_t n_q, int32_t n_in, int32_t k, float* out_scores,
                    int64_t* out_ids, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * ANN episode on the device (SURVEY f-2): the steps around the scan in the reference's ANN data generation.
+ * cdr_mine_negatives replaces GenerateNegativePassaageID (ANCE/drivers/run_ann_data_gen.py:497-570): per query
+ * row of I [n_q, k] (document rows from the scan, -1 = empty): rr = 1 / rank of the positive passage among all k
+ * results (0 if absent); neg [n_q, n_neg] = the first n_neg distinct passage ids != positive met while walking the
+ * candidates order[q, 0:n_sel] (NULL = 0..n_sel-1, the SelectTopK branch), padded with -1; neg_count [n_q].
+ * cdr_kmeans_assign / _accumulate are the two halves of a Lloyd iteration for the query clustering that yields the
+ * iDRO group ids (faiss.Kmeans + IndexFlatL2.search(q, 1), :340-351): assign[i] = argmax_c scores[i, c] - half_sq[c]
+ * (scores = X C^T from cdr_gemm, ties to the lowest c); sums[g, :] += x[i, :], counts[g] += 1.
+ * ---------------------------------------------------------------------------------------------- */
+int cdr_mine_negatives(const int64_t* I, int32_t n_q, int32_t k, const int64_t* doc_pid, int64_t n_docs,
+                       const int64_t* pos_pid, const int32_t* order, int32_t n_sel, int32_t n_neg, float* rr,
+                       int64_t* neg, int32_t* neg_count, void* stream);
+int cdr_kmeans_assign(const float* scores, int64_t ld, const float* half_sq, int64_t n, int32_t k, int32_t* assign,
+                      void* stream);
+int cdr_kmeans_accumulate(const void* x, const int32_t* assign, int64_t n, int32_t dim, int32_t k, float* sums,
+                          float* counts, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Token-record reader (host only; SURVEY f-3): the reference's EmbeddingCache files (ANCE/utils/util.py:316-370;

@@ -1,0 +1,72 @@
+"""GPU: ANN negative mining / k-means / episode glue (cocodr_b200.mining) against the oracle restatement of the
+reference's GenerateNegativePassaageID and a float64 Lloyd step."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n_q,k,n_neg,shuffled", [(37, 200, 20, False), (64, 100, 5, True), (5, 33, 40, True), (3, 8, 7, False)])
+def test_mine_negatives_matches_reference_walk(n_q, k, n_neg, shuffled):
+    from cocodr_b200 import mining
+    from oracle import mining_ref
+    rng = np.random.RandomState(n_q + k)
+    n_docs = 500
+    doc_pid = rng.permutation(5000)[:n_docs].astype(np.int64)
+    doc_pid[::7] = doc_pid[1]  # several document rows share a passage id (multi-chunk passages): repeats must be skipped
+    I = rng.randint(0, n_docs, size=(n_q, k)).astype(np.int64)
+    I[0, 5:] = -1  # short list
+    pos = doc_pid[rng.randint(0, n_docs, size=n_q)].copy()
+    pos[1] = 999_999  # positive not retrieved
+    I[2, 0] = int(np.where(doc_pid == pos[2])[0][0])  # positive at rank 1
+    order = None
+    if shuffled:
+        order = np.stack([rng.permutation(k) for _ in range(n_q)]).astype(np.int32)
+    neg, cnt, rr = mining.mine_negatives(torch.from_numpy(I).cuda(), torch.from_numpy(doc_pid).cuda(),
+                                         torch.from_numpy(pos).cuda(), n_neg,
+                                         order=None if order is None else torch.from_numpy(order).cuda())
+    neg, cnt, rr = neg.cpu().numpy(), cnt.cpu().numpy(), rr.cpu().numpy()
+    for q in range(n_q):
+        ref_neg, ref_rr = mining_ref.generate_negatives(list(I[q]), doc_pid, pos[q], n_neg,
+                                                        order=None if order is None else list(order[q]))
+        assert cnt[q] == len(ref_neg)
+        assert list(neg[q, :cnt[q]]) == ref_neg and (neg[q, cnt[q]:] == -1).all()
+        assert abs(rr[q] - ref_rr) < 1e-7
+
+
+def test_kmeans_matches_lloyd_steps():
+    from cocodr_b200 import mining
+    from oracle import mining_ref
+    rng = np.random.RandomState(0)
+    k, dim, n = 5, 64, 3000
+    centers = rng.randn(k, dim) * 3.0
+    X = (centers[rng.randint(0, k, size=n)] + 0.3 * rng.randn(n, dim)).astype(np.float16)
+    init = (centers + 0.5 * rng.randn(k, dim)).astype(np.float32)  # well separated: assignments are unambiguous
+    cent, assign = mining.kmeans(torch.from_numpy(X).cuda(), k, niter=4, init=torch.from_numpy(init))
+    c = init.astype(np.float64)
+    for _ in range(4):
+        c, _ = mining_ref.kmeans_step(X, c)
+    _, ref_assign = mining_ref.kmeans_step(X, c)
+    assert (assign.cpu().numpy() == ref_assign).mean() > 0.999  # fp16 centroids in the score GEMM: ties may flip
+    assert np.abs(cent.cpu().numpy() - c).max() < 2e-2
+
+
+def test_episode_on_resident_embeddings():
+    """scan -> negatives -> groups, all on the device: positives planted as each query's nearest passage."""
+    from cocodr_b200 import mining
+    g = torch.Generator().manual_seed(3)
+    n_docs, n_q, dim = 20000, 96, 128
+    P = torch.randn(n_docs, dim, generator=g).half().cuda()
+    pid = (torch.randperm(10 * n_docs, generator=g)[:n_docs]).cuda()
+    rows = torch.randperm(n_docs, generator=g)[:n_q].cuda()
+    Q = (P[rows].float() * 1.5).half()  # the planted passage has the largest inner product
+    out = mining.ann_episode(Q, torch.arange(n_q).cuda(), P, pid, pid[rows], top_k=50, n_neg=8, n_groups=4,
+                             kmeans_iters=3)
+    assert (out["I"][:, 0] == rows).all() and torch.allclose(out["rr"], torch.ones(n_q, device="cuda"))
+    assert (out["neg_count"] == 8).all()
+    assert not (out["neg"] == pid[rows][:, None]).any()
+    assert out["group"].shape == (n_q,) and int(out["group"].max()) < 4
+    shuf = mining.ann_episode(Q, torch.arange(n_q).cuda(), P, pid, pid[rows], top_k=50, n_neg=8, shuffle_seed=1)
+    cand = pid[out["I"]]
+    assert all(set(shuf["neg"][q].tolist()) <= set(cand[q].tolist()) for q in range(n_q))
