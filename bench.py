@@ -116,8 +116,8 @@ def cpu_port_step_fn(n_pairs, threads=None):
     import torch
 
     from oracle import bert_ref, heads_ref
-    if threads:
-        torch.set_num_threads(threads)
+    # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank)
+    torch.set_num_threads(threads or os.cpu_count() or 1)
     cfg = bert_ref.make_config()
     st = {k: v.clone().requires_grad_(True) for k, v in bert_ref.synth_state(cfg, 0).items()}
     opt = torch.optim.AdamW(list(st.values()), lr=5e-6)
