@@ -58,6 +58,36 @@ def test_no_cpu_fallback_anywhere():
         scan.search(torch.randn(2, 8).half(), torch.randn(9, 8).half(), 3)
     with pytest.raises(RuntimeError):
         scan.IndexFlatIP(8).search(np.zeros((1, 8), np.float32), 1)
+    with pytest.raises(RuntimeError):
+        scan.search_async(torch.randn(2, 8).half(), torch.randn(9, 8).half(), 3)
+    # the widened rows (optimizers, ANN episode) are CUDA-only as well
+    from cocodr_b200 import mining, optim
+    with pytest.raises(RuntimeError):
+        mining.mine_negatives(torch.zeros(2, 4, dtype=torch.long), torch.arange(9), torch.zeros(2, dtype=torch.long), 2)
+    with pytest.raises(RuntimeError):
+        mining.kmeans(torch.randn(16, 8).half(), 2)
+    w = torch.nn.Parameter(torch.randn(8, 8))
+    w.grad = torch.randn(8, 8)
+    for opt in (optim.AdamW([w], lr=1e-3), optim.Lamb([w], lr=1e-3)):
+        with pytest.raises(RuntimeError):
+            opt.step()
+
+
+def test_optimizer_surface_matches_the_reference_constructors():
+    """Lamb(params, lr, betas, eps, weight_decay, adam) (ANCE/utils/lamb.py:44-58) and AdamW(params, lr, eps)
+    (ANCE/drivers/run_ann.py:139-144): same keywords, same param_groups defaults, torch state_dict layout."""
+    from cocodr_b200 import optim
+    w = torch.nn.Parameter(torch.zeros(4))
+    lamb = optim.Lamb([{"params": [w]}], lr=5e-6, eps=1e-8, weight_decay=0.01)
+    g = lamb.param_groups[0]
+    assert (g["lr"], g["eps"], g["weight_decay"], g["betas"]) == (5e-6, 1e-8, 0.01, (0.9, 0.999))
+    adamw = optim.AdamW([w], lr=1e-5, eps=1e-8)
+    assert adamw.param_groups[0]["betas"] == (0.9, 0.999) and adamw.mode == optim.MODE_HF
+    assert set(adamw.state_dict()) == {"state", "param_groups"}
+    with pytest.raises(NotImplementedError):
+        optim.Lamb([w], adam=True)
+    with pytest.raises(ValueError):
+        optim.AdamW([w], semantics="nope")
 
 
 def test_unsupported_configs_are_rejected():
