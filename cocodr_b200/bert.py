@@ -49,6 +49,12 @@ def check_config(config):
         raise RuntimeError("cocodr_b200 BERT kernels implement absolute position embeddings only")
 
 
+def run_last_layer_cls(layer, shadow, x, key_bias, n_seq, L, config):
+    """Last BertLayer when only the [CLS] embedding is consumed: FFN / LayerNorms / output projection on n_seq rows."""
+    return ops.BertLastLayerCLSFn.apply(x, key_bias, *layer_params(layer), shadow, n_seq, L,
+                                        config.num_attention_heads, float(config.layer_norm_eps))
+
+
 def run_layer(layer, shadow, x, key_bias, n_seq, L, config, emit_cls=False):
     """One BertLayer (HF module used as the parameter container) on internal fp16 [T, H] activations."""
     return ops.BertLayerFn.apply(x, key_bias, *layer_params(layer), shadow, n_seq, L, config.num_attention_heads,
@@ -102,9 +108,12 @@ class BertModel(_HFBertModel):
                           f"(config asks for {p}).")
             _warned_dropout = True
 
+    cls_only_last_layer = True  # encode_cls(): run the last layer's FFN / LayerNorms on the [CLS] rows only
+
     def encode(self, input_ids, attention_mask=None, token_type_ids=None, position_ids=None, inputs_embeds=None,
-               want_hidden=False, last_layer=None):
-        """Internal entry: returns (cls fp32 [B,H], last hidden fp16 [T,H], [hidden fp16] * (layers+1) or None)."""
+               want_hidden=False, last_layer=None, cls_only=False):
+        """Internal entry: returns (cls fp32 [B,H], last hidden fp16 [T,H], [hidden fp16] * (layers+1) or None).
+        ``cls_only``: the caller only reads ``cls`` -- the last hidden state is not produced (None)."""
         self._check_inputs(input_ids, token_type_ids, position_ids, inputs_embeds)
         if len(self._shadows) != len(self.encoder.layer):
             self._cdr_init()
@@ -119,7 +128,10 @@ class BertModel(_HFBertModel):
         cls = None
         n_layers = len(self.encoder.layer)
         for i, layer in enumerate(self.encoder.layer):
-            if i == n_layers - 1:
+            if i == n_layers - 1 and cls_only and not want_hidden and self.cls_only_last_layer:
+                cls = run_last_layer_cls(layer, self._shadows[i], x, kb, n_seq, L, self.config)
+                x = None
+            elif i == n_layers - 1:
                 x, cls = run_layer(layer, self._shadows[i], x, kb, n_seq, L, self.config, emit_cls=True)
             else:
                 x = run_layer(layer, self._shadows[i], x, kb, n_seq, L, self.config)
@@ -129,7 +141,7 @@ class BertModel(_HFBertModel):
 
     def encode_cls(self, input_ids, attention_mask=None):
         """``self(input_ids, attention_mask)[0][:, 0]`` without materialising the fp32 hidden states."""
-        return self.encode(input_ids, attention_mask)[0]
+        return self.encode(input_ids, attention_mask, cls_only=True)[0]
 
     def forward(self, input_ids=None, attention_mask=None, token_type_ids=None, position_ids=None, inputs_embeds=None,
                 output_hidden_states=None, return_dict=None, **kwargs):

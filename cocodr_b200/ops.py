@@ -278,6 +278,111 @@ class BertLayerFn(torch.autograd.Function):
                 dbo, dg1, dbe1, dwi, dbi, dwo2, dbo2, dg2, dbe2, None, None, None, None, None, None)
 
 
+class BertLastLayerCLSFn(torch.autograd.Function):
+    """The LAST encoder layer when only the [CLS] embedding is consumed (``BertDot_NLL_LN.query_emb / body_emb``:
+    ``self.bert(...)[0][:, 0]``, ANCE/model/models.py:225-232): every token still feeds K and V, but the attention
+    output projection, both LayerNorms and the whole FFN are only needed on the n_seq [CLS] rows -- and so is their
+    backward, because d(hidden) is zero everywhere else.  Same kernels, 128x fewer rows for 6 of the layer's 8
+    backward GEMMs and 3 of its 4 forward GEMMs; the [CLS] rows of ``x`` / ``att`` are read in place through a row
+    stride of L * H (no gather copy).  Results equal ``BertLayerFn(..., emit_cls=True)[1]``.
+
+    forward(x, key_bias, <16 HF parameters>, shadow, n_seq, seq_len, heads, eps) -> cls fp32 [n_seq, H]
+    """
+
+    @staticmethod
+    def forward(ctx, x, key_bias, wq, bq, wk, bk, wv, bv, wo, bo, g1, be1, wi, bi, wo2, bo2, g2, be2, shadow, n_seq,
+                L, heads, eps):
+        T, H = x.shape
+        I = wi.shape[0]
+        dev = x.device
+        sh = shadow.refresh(wq, bq, wk, bk, wv, bv, wo, wi, wo2)
+        x = x.contiguous()
+        qkv = _f16(T, 3 * H, dev=dev)
+        K.gemm(x, sh.wqkv, qkv, M=T, N=3 * H, K=H, bias=sh.bqkv)
+        att = _f16(T, H, dev=dev)
+        lse = _f32(n_seq, heads, L, dev=dev)
+        K.attn_fwd(qkv, key_bias, att, lse, n_seq=n_seq, seq_len=L, heads=heads)
+        xc, attc = x.view(n_seq, L, H)[:, 0], att.view(n_seq, L, H)[:, 0]  # [n_seq, H] views, row stride L * H
+        y1 = _f16(n_seq, H, dev=dev)
+        K.gemm(attc, sh.wo, y1, M=n_seq, N=H, K=H, bias=bo, epilogue=K.EPI_BIAS_RESIDUAL, aux=xc)
+        x1 = _f16(n_seq, H, dev=dev)
+        mean1, rstd1 = _f32(n_seq, dev=dev), _f32(n_seq, dev=dev)
+        K.ln_fwd(y1, g1, be1, x1, mean1, rstd1, None, n_seq=n_seq, seq_len=1, hidden=H, eps=eps)
+        gp, gl = _f16(n_seq, I, dev=dev), _f16(n_seq, I, dev=dev)
+        K.gemm(x1, sh.wi, gl, M=n_seq, N=I, K=H, bias=bi, epilogue=K.EPI_BIAS_GELU, out2=gp)
+        y2 = _f16(n_seq, H, dev=dev)
+        K.gemm(gl, sh.wo2, y2, M=n_seq, N=H, K=I, bias=bo2, epilogue=K.EPI_BIAS_RESIDUAL, aux=x1)
+        y = _f16(n_seq, H, dev=dev)
+        mean2, rstd2 = _f32(n_seq, dev=dev), _f32(n_seq, dev=dev)
+        cls = _f32(n_seq, H, dev=dev)
+        push = None
+        if CLS_PUSH is not None:  # (exchange, first_seq): rows are sequences here (seq_len = 1)
+            push = CLS_PUSH
+        K.ln_fwd(y2, g2, be2, y, mean2, rstd2, cls, n_seq=n_seq, seq_len=1, hidden=H, eps=eps, push=push)
+        ctx.save_for_backward(x, key_bias, qkv, att, lse, y1, x1, mean1, rstd1, gp, gl, y2, mean2, rstd2, g1, g2)
+        ctx.shadow_w = (sh.wqkv, sh.wo, sh.wi, sh.wo2)
+        ctx.meta = (n_seq, L, heads, I, _GRAD_SCALE)
+        return cls
+
+    @staticmethod
+    def backward(ctx, dcls):
+        x, key_bias, qkv, att, lse, y1, x1, mean1, rstd1, gp, gl, y2, mean2, rstd2, g1, g2 = ctx.saved_tensors
+        wqkv, wo, wi, wo2 = ctx.shadow_w
+        n_seq, L, heads, I, S = ctx.meta
+        T, H = x.shape
+        dev = x.device
+        inv = 1.0 / S
+        dcls = dcls.contiguous().float()
+        sizes = (H, H, H, H * I, I, I * H, H, H, H, H * H, 3 * H * H, 3 * H)
+        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        views, off = [], 0
+        for n in sizes:
+            views.append(flat[off:off + n])
+            off += n
+        dg2, dbe2, dbo2, dwo2, dbi, dwi, dg1, dbe1, dbo, dwo, dwqkv, dbqkv = views
+        dwo2, dwi, dwo, dwqkv = dwo2.view(H, I), dwi.view(I, H), dwo.view(H, H), dwqkv.view(3 * H, H)
+        # ---- [CLS] rows only: output LayerNorm, FFN, attention-output LayerNorm and projection
+        dy2 = _f16(n_seq, H, dev=dev)
+        K.ln_bwd(None, dcls, y2, g2, mean2, rstd2, dy2, dg2, dbe2, dbo2, n_seq=n_seq, seq_len=1, hidden=H, in_scale=S,
+                 out_scale=inv)
+        dz = _f16(n_seq, I, dev=dev)
+        K.gemm(dy2, wo2, dz, M=n_seq, N=I, K=H, b_major=1, epilogue=K.EPI_DGELU, aux=gp, colsum=dbi, colsum_scale=inv)
+        K.gemm(dy2, gl, dwo2, M=H, N=I, K=n_seq, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0, alpha=inv)
+        dx1 = _f16(n_seq, H, dev=dev)
+        K.gemm(dz, wi, dx1, M=n_seq, N=H, K=I, b_major=1, epilogue=K.EPI_BIAS_RESIDUAL, aux=dy2)
+        K.gemm(dz, x1, dwi, M=I, N=H, K=n_seq, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0, alpha=inv)
+        dy1 = _f16(n_seq, H, dev=dev)
+        K.ln_bwd(dx1, None, y1, g1, mean1, rstd1, dy1, dg1, dbe1, dbo, n_seq=n_seq, seq_len=1, hidden=H, in_scale=S,
+                 out_scale=inv, row_ws=_f32(2 * n_seq, dev=dev))
+        attc = att.view(n_seq, L, H)[:, 0]
+        datt = torch.zeros(T, H, dtype=torch.float16, device=dev)  # d(ctx) is zero off the [CLS] rows
+        dattc = _f16(n_seq, H, dev=dev)
+        K.gemm(dy1, wo, dattc, M=n_seq, N=H, K=H, b_major=1)
+        K.gemm(dy1, attc, dwo, M=H, N=H, K=n_seq, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0, alpha=inv)
+        datt.view(n_seq, L, H)[:, 0].copy_(dattc)
+        # ---- dense again from here: the [CLS] query attends to every key
+        dqkv = _f16(T, 3 * H, dev=dev)
+        fused_db = L <= 128
+        K.attn_bwd(qkv, key_bias, att, lse, datt, dqkv, n_seq=n_seq, seq_len=L, heads=heads,
+                   dbias=dbqkv if fused_db else None, dbias_scale=inv)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = _f16(T, H, dev=dev)
+            # residual branch: only the [CLS] rows carry it.  datt (zero off the [CLS] rows) has been consumed by the
+            # attention backward: its [CLS] rows now take dy1 and it serves as the residual operand of the epilogue,
+            # so the add happens in fp32 before the single rounding, exactly as in the full layer
+            datt.view(n_seq, L, H)[:, 0].copy_(dy1)
+            K.gemm(dqkv, wqkv, dx, M=T, N=H, K=3 * H, b_major=1, epilogue=K.EPI_BIAS_RESIDUAL, aux=datt)
+        K.gemm(dqkv, x, dwqkv, M=3 * H, N=H, K=T, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0,
+               alpha=inv)
+        if not fused_db:
+            K.colsum(dqkv, dbqkv, rows=T, cols=3 * H, scale=inv)
+        if GRAD_SYNC is not None:
+            GRAD_SYNC.submit(flat)
+        return (dx, None, dwqkv[0:H], dbqkv[0:H], dwqkv[H:2 * H], dbqkv[H:2 * H], dwqkv[2 * H:], dbqkv[2 * H:], dwo,
+                dbo, dg1, dbe1, dwi, dbi, dwo2, dbo2, dg2, dbe2, None, None, None, None, None)
+
+
 class HiddenToFloat(torch.autograd.Function):
     """Boundary between the internal fp16 hidden states (scaled-gradient domain) and caller-visible fp32
     tensors: forward casts, backward multiplies the caller's true gradient by grad_scale."""

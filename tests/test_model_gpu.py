@@ -200,3 +200,32 @@ def test_no_cpu_fallback():
     m = build(TINY)
     with pytest.raises(RuntimeError):
         m.query_emb(torch.zeros(2, 8, dtype=torch.long), torch.ones(2, 8, dtype=torch.long))
+
+
+def test_cls_only_last_layer_equals_full_layer():
+    """encode_cls runs the last layer's FFN / LayerNorms / output projection on the [CLS] rows only
+    (ops.BertLastLayerCLSFn): same embeddings and the same parameter gradients as the full last layer."""
+    from oracle import bert_ref
+    m = build(TINY, "BertDot_InBatch_NLL_LN")
+    m.train()
+    ids, mask = (t.cuda() for t in bert_ref.synth_batch(12, 48, TINY["vocab"], 123))
+    w = torch.ones(6, device="cuda")
+    out = {}
+    for flag in (True, False):
+        m.bert.cls_only_last_layer = flag
+        m.zero_grad(set_to_none=True)
+        with torch.no_grad():
+            emb = m.query_emb(ids, mask).clone()
+        loss = m(ids[:6], mask[:6], ids[6:], mask[6:], weights=w)[0]
+        loss.backward()
+        out[flag] = (emb, loss.item(), {n: p.grad.clone() for n, p in m.bert.named_parameters() if p.grad is not None})
+    m.bert.cls_only_last_layer = True
+    assert torch.equal(out[True][0], out[False][0])  # same kernels, same per-row arithmetic
+    assert out[True][1] == out[False][1]
+    assert out[True][2].keys() == out[False][2].keys()
+    for n, g_full in out[False][2].items():
+        g_cls = out[True][2][n]
+        if "key.bias" in n:
+            continue  # analytically zero: rounding noise on both sides
+        err = (g_cls - g_full).abs().max().item()
+        assert err <= 2e-3 * g_full.abs().max().item() + 1e-7, (n, err)
