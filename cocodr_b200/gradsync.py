@@ -25,6 +25,9 @@ class GradSync:
         self.model, self.group = model, group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.comm = torch.cuda.Stream() if self.world > 1 else None
+        # NCCL averages in the collective itself (ncclAvg); other backends (gloo in the CPU tests) sum, then scale
+        nccl = dist.is_available() and dist.is_initialized() and dist.get_backend(group) == "nccl"
+        self._avg = dist.ReduceOp.AVG if nccl else dist.ReduceOp.SUM
         self._bufs = []
 
     # called from the autograd Functions (ops.GRAD_SYNC.submit) right after a backward has been enqueued
@@ -37,8 +40,9 @@ class GradSync:
         self.comm.wait_event(ev)
         flat.record_stream(self.comm)
         with torch.cuda.stream(self.comm):
-            dist.all_reduce(flat, group=self.group)
-            flat.mul_(1.0 / self.world)
+            dist.all_reduce(flat, op=self._avg, group=self.group)  # averaged inside NCCL: no extra pass over the buffer
+            if self._avg is dist.ReduceOp.SUM:
+                flat.mul_(1.0 / self.world)
         self._bufs.append(flat)
 
     def __enter__(self):
@@ -68,8 +72,9 @@ class GradSync:
             with torch.cuda.stream(self.comm):
                 for g in rest:
                     g.record_stream(self.comm)
-                    dist.all_reduce(g, group=self.group)
-                    g.mul_(1.0 / self.world)
+                    dist.all_reduce(g, op=self._avg, group=self.group)
+                    if self._avg is dist.ReduceOp.SUM:
+                        g.mul_(1.0 / self.world)
         cur.wait_stream(self.comm)
         self._bufs = []
         return False
