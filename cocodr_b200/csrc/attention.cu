@@ -124,6 +124,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttParams p, 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
+  pdl_wait();  // the prologue above overlapped the previous kernel's tail
+  pdl_launch();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -408,6 +410,8 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
+  pdl_wait();  // the prologue above overlapped the previous kernel's tail
+  pdl_launch();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -1094,8 +1098,8 @@ int cdr_attn_fwd(const cdr_attn_args* a, void* stream) {
   }
   const int n_items = a->n_seq * a->heads;
   const int grid = n_items < sm_count() ? n_items : sm_count();
-  fmha_fwd_kernel<<<grid, ATT_FWD_THREADS, ATT_FWD_SMEM, static_cast<cudaStream_t>(stream)>>>(tq, p, n_items);
-  CDR_LAUNCH_CHECK();
+  CDR_CUDA(launch_pdl(fmha_fwd_kernel, dim3(grid), dim3(ATT_FWD_THREADS), ATT_FWD_SMEM, static_cast<cudaStream_t>(stream),
+                      tq, p, n_items));
   return CDR_OK;
 }
 
@@ -1140,8 +1144,8 @@ int cdr_attn_bwd(const cdr_attn_args* a, void* stream) {
   p.dbias_scale = a->dbias_scale;
   const int n_items = a->n_seq * a->heads;
   const int grid = n_items < sm_count() ? n_items : sm_count();
-  fmha_bwd_kernel<<<grid, ATT_BWD_THREADS, ATT_BWD_SMEM, static_cast<cudaStream_t>(stream)>>>(tq, td, p, n_items);
-  CDR_LAUNCH_CHECK();
+  CDR_CUDA(launch_pdl(fmha_bwd_kernel, dim3(grid), dim3(ATT_BWD_THREADS), ATT_BWD_SMEM, static_cast<cudaStream_t>(stream),
+                      tq, td, p, n_items));
   return CDR_OK;
 }
 

@@ -47,6 +47,30 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// Programmatic dependent launch: kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization, so
+// grid N+1 may be scheduled (and run its prologue: barrier init, TMEM allocation, tensor-map prefetch) while grid N
+// drains.  pdl_wait() blocks until the preceding grid has completed and its memory is visible -- NOTHING that a
+// predecessor wrote (or still reads) may be touched before it; pdl_launch() lets the successor start its own prologue.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();  // core.cu: CDR_PDL=0 in the environment turns the launch attribute off
+
+// <<<grid, block, smem, stream>>> with the programmatic-serialization attribute; the kernel must call pdl_wait()
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // First 1024-byte aligned address of the dynamic shared memory (SWIZZLE_128B tiles need it).  The offset is
 // computed on the 32-bit shared address and ADDED to the __shared__ array, so the compiler keeps the shared
 // address space (LDS / STS); rounding the generic pointer through uintptr_t degrades every access to generic LD / ST.

@@ -403,6 +403,8 @@ ln_fwd_staged_kernel(const __half* __restrict__ x, const float* __restrict__ gam
     fence_mbar_init();
   }
   __syncthreads();
+  pdl_wait();
+  pdl_launch();
   auto issue = [&](int tile, int stage) {
     const int r0 = tile * LNS_ROWS;
     const uint32_t bytes = static_cast<uint32_t>(min(LNS_ROWS, rows - r0)) * row_bytes;
@@ -484,6 +486,8 @@ ln_bwd_staged_kernel(const __half* __restrict__ dy, const __half* __restrict__ x
     fence_mbar_init();
   }
   __syncthreads();
+  pdl_wait();
+  pdl_launch();
   auto issue = [&](int tile, int stage) {
     const int r0 = tile * LNS_ROWS;
     const uint32_t bytes = static_cast<uint32_t>(min(LNS_ROWS, rows - r0)) * row_bytes;
@@ -798,9 +802,9 @@ static int ln_fwd_impl(const void* x, const float* gamma, const float* beta, voi
       CDR_CUDA(cudaFuncSetAttribute(ln_fwd_staged_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); \
       cfg = true;                                                                                                    \
     }                                                                                                                \
-    ln_fwd_staged_kernel<V><<<grid, LNS_THREADS, smem, st>>>(static_cast<const __half*>(x), gamma, beta,              \
-                                                            static_cast<__half*>(y), mean, rstd, cls_out, rows,       \
-                                                            hidden, seq_len, eps, push);                             \
+    CDR_CUDA(launch_pdl(ln_fwd_staged_kernel<V>, dim3(grid), dim3(LNS_THREADS), smem, st,                             \
+                        static_cast<const __half*>(x), gamma, beta, static_cast<__half*>(y), mean, rstd, cls_out,     \
+                        rows, hidden, seq_len, eps, push));                                                          \
   } while (0)
     if (vpl <= 1) LNS_FWD(1);
     else if (vpl <= 2) LNS_FWD(2);
@@ -854,10 +858,9 @@ int cdr_ln_bwd(const void* dy, const float* dy_cls, const void* x, const float* 
       CDR_CUDA(cudaFuncSetAttribute(ln_bwd_staged_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024)); \
       cfg = true;                                                                                                    \
     }                                                                                                                \
-    ln_bwd_staged_kernel<V><<<grid, LNS_THREADS, smem, st>>>(static_cast<const __half*>(dy),                          \
-                                                            static_cast<const __half*>(x), gamma, mean, rstd,         \
-                                                            static_cast<__half*>(dx), dgamma, dbeta, dbias, rows,     \
-                                                            hidden, out_scale);                                      \
+    CDR_CUDA(launch_pdl(ln_bwd_staged_kernel<V>, dim3(grid), dim3(LNS_THREADS), smem, st,                             \
+                        static_cast<const __half*>(dy), static_cast<const __half*>(x), gamma, mean, rstd,             \
+                        static_cast<__half*>(dx), dgamma, dbeta, dbias, rows, hidden, out_scale));                   \
   } while (0)
     if (vpl <= 1) LNS_BWD(1);
     else if (vpl <= 2) LNS_BWD(2);

@@ -34,13 +34,15 @@ static int launch_gemm_cg(const CUtensorMap& ta, const CUtensorMap& tb, const Ge
   cfg.blockDim = dim3(GEMM_THREADS<EPI>);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   CDR_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
   return CDR_OK;
 }

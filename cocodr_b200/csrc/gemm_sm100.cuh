@@ -408,6 +408,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();    // everything above overlapped the previous kernel's tail; operands are touched only from here on
+  pdl_launch();
 
   if (warp == 0) {
     // ===================== TMA producer (every CTA stages its own A rows and its share of B) =====
