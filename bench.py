@@ -330,13 +330,13 @@ def run_ours(args):
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     traffic = None  # DRAM bytes per GEMM launch from the committed ncu pass over one step (same command, --no-graph)
     try:
-        with open(os.path.join(ROOT, "profiles", "r01c_gemm_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r01d_gemm_traffic.json")) as f:
             traffic = float(json.load(f)["traffic_bytes_per_launch"])
     except Exception:
         pass
     roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": achieved, "peak": peaks["tensor"],
                 "unit": "TFLOP/s", "frac": achieved / peaks["tensor"], "traffic": traffic,
-                "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, average of the 144 GEMM launches of one step; profiles/r01c_gemm_traffic.json)",
+                "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, average of the 144 GEMM launches of one step; profiles/r01d_gemm_traffic.json)",
                 "peak_source": peaks["source"] + " (bf16 sustained)", "launches_per_step": len(ev),
                 "avg_launch_us": gemm_ms * 1e3 / max(1, len(ev)), "gemm_share_of_step": gemm_ms / step_ms_instr,
                 "algorithmic_tflop_per_step": gemm_flops / 1e12}
