@@ -61,8 +61,44 @@ sgemm_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __
   }
 }
 
+// Same contract, 16 x 16 outputs per block (one per thread): for problems with a handful of 64 x 64 tiles and a long K
+// (the 64 x 64 score matrix of the contrastive head is ONE such tile with K = 768) this spreads the work over 16x
+// more blocks.  Deterministic (no split-K atomics): the loss must not depend on the launch.
+__global__ void __launch_bounds__(256)
+sgemm_small_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M, int N, int K,
+                   long long sam, long long sak, long long sbk, long long sbn, long long ldc, float alpha) {
+  __shared__ float sA[16][65];  // [m][k]
+  __shared__ float sB[16][65];  // [n][k]
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * 16, n0 = blockIdx.x * 16;
+  const int tm = tid >> 4, tn = tid & 15;
+  float acc = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 64) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + i * 256;  // 16 x 64 elements per operand
+      int r, kk;
+      if (sak == 1) { kk = e & 63; r = e >> 6; } else { r = e & 15; kk = e >> 4; }
+      sA[r][kk] = (m0 + r < M && k0 + kk < K) ? A[(m0 + r) * sam + (k0 + kk) * sak] : 0.f;
+      if (sbk == 1) { kk = e & 63; r = e >> 6; } else { r = e & 15; kk = e >> 4; }
+      sB[r][kk] = (n0 + r < N && k0 + kk < K) ? B[(k0 + kk) * sbk + (n0 + r) * sbn] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 16
+    for (int kk = 0; kk < 64; ++kk) acc = fmaf(sA[tm][kk], sB[tn][kk], acc);
+    __syncthreads();
+  }
+  if (m0 + tm < M && n0 + tn < N) C[(m0 + tm) * ldc + n0 + tn] = alpha * acc;
+}
+
 static int sgemm(const float* A, const float* B, float* C, int M, int N, int K, long long sam, long long sak,
                  long long sbk, long long sbn, long long ldc, float alpha, cudaStream_t st) {
+  if (((N + SG_T - 1) / SG_T) * ((M + SG_T - 1) / SG_T) < 16 && K >= 256) {
+    dim3 g16((N + 15) / 16, (M + 15) / 16);
+    sgemm_small_kernel<<<g16, 256, 0, st>>>(A, B, C, M, N, K, sam, sak, sbk, sbn, ldc, alpha);
+    CDR_LAUNCH_CHECK();
+    return CDR_OK;
+  }
   dim3 grid((N + SG_T - 1) / SG_T, (M + SG_T - 1) / SG_T);
   sgemm_kernel<<<grid, 256, 0, st>>>(A, B, C, M, N, K, sam, sak, sbk, sbn, ldc, alpha);
   CDR_LAUNCH_CHECK();
