@@ -452,7 +452,9 @@ ln_fwd_staged_kernel(const __half* __restrict__ x, const float* __restrict__ gam
           if (is_cls) store8_f(cls_out + static_cast<long long>(row / seq_len) * hidden + c, o);
           if (push.pa.world > 0 && (row % seq_len) == 0 && row / seq_len >= push.first_seq) {
             // fused all-gather: the CLS row goes straight into slot `rank` of every rank's gather buffer (NVLink)
-            const long long slot = static_cast<long long>(push.pa.rank) * push.n_push + (row / seq_len - push.first_seq);
+            const long long parity = *reinterpret_cast<const volatile uint32_t*>(push.pa.epoch) & 1u;  // double buffer
+            const long long slot = parity * push.pa.world * push.n_push + static_cast<long long>(push.pa.rank) * push.n_push +
+                                   (row / seq_len - push.first_seq);
             for (int r = 0; r < push.pa.world; ++r)
               store8_f(static_cast<float*>(push.pa.peer_buf[r]) + slot * hidden + c, o);
           }

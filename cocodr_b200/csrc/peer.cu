@@ -21,6 +21,21 @@ __global__ void peer_wait_kernel(const uint32_t* flags, int world, const uint32_
 
 __global__ void peer_next_epoch_kernel(uint32_t* epoch) { epoch[0] += 1u; }
 
+// Wait for the pushes of this epoch, then copy the epoch's half of the double-buffered gather area into a private
+// tensor: the consumer (and its saved-for-backward state) never aliases memory the peers write into, and a peer
+// that is already one step ahead writes the OTHER half.
+__global__ void __launch_bounds__(256)
+peer_wait_fetch_kernel(const uint32_t* __restrict__ flags, int world, const uint32_t* __restrict__ epoch,
+                       const float* __restrict__ gather, long long half_elems, float* __restrict__ out) {
+  const uint32_t ep = *reinterpret_cast<const volatile uint32_t*>(epoch);
+  if (threadIdx.x == 0) peer_wait_all(flags, world, ep);
+  __syncthreads();
+  const float* src = gather + (ep & 1u) * half_elems;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 4;
+  for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < half_elems; i += stride)
+    *reinterpret_cast<float4*>(out + i) = *reinterpret_cast<const float4*>(src + i);
+}
+
 // src [world * rows, dim] fp32: row block r -> slot `rank` of rank r's receive buffer [world][rows, dim]
 __global__ void __launch_bounds__(256)
 peer_scatter_kernel(const float* __restrict__ src, long long per_block, cdr_peer_args pa) {
@@ -77,6 +92,18 @@ int cdr_peer_next_epoch(uint32_t* epoch, void* stream) {
 int cdr_peer_wait(const uint32_t* local_flags, int32_t world, const uint32_t* epoch, void* stream) {
   CDR_REQUIRE(local_flags != nullptr && epoch != nullptr && world >= 1 && world <= 8, "cdr_peer_wait: bad arguments");
   peer_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(local_flags, world, epoch);
+  CDR_LAUNCH_CHECK();
+  return CDR_OK;
+}
+
+int cdr_peer_wait_fetch(const uint32_t* local_flags, int32_t world, const uint32_t* epoch, const float* gather,
+                        int64_t half_elems, float* out, void* stream) {
+  CDR_REQUIRE(local_flags && epoch && gather && out && world >= 1 && world <= 8 && half_elems > 0 && half_elems % 4 == 0,
+              "cdr_peer_wait_fetch: bad arguments (half_elems must be a multiple of 4)");
+  long long blocks = (half_elems / 4 + 255) / 256;
+  if (blocks > 2 * sm_count()) blocks = 2 * sm_count();
+  peer_wait_fetch_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      local_flags, world, epoch, gather, half_elems, out);
   CDR_LAUNCH_CHECK();
   return CDR_OK;
 }

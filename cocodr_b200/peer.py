@@ -3,8 +3,9 @@
 ``PeerExchange`` owns the symmetric buffers (``torch.distributed._symmetric_memory``: the same allocation mapped on
 every rank of the node over NVLink) the kernels write into:
 
-    gather [world * n_rows, dim] fp32   forward : rank r's rows land in slot r on EVERY rank, written by the last
-                                                  LayerNorm kernel itself (cdr_ln_fwd_push)
+    gather [2, world * n_rows, dim] fp32 forward: rank r's rows land in slot r on EVERY rank, written by the last
+                                                  LayerNorm kernel itself (cdr_ln_fwd_push); double-buffered by epoch
+                                                  parity, consumed through a private copy (cdr_peer_wait_fetch)
     recv   [world, n_rows, dim]  fp32   backward: rank r's gradient block for this rank lands in slot r
     flags  [16] uint32                  epochs published by the writers, polled by cdr_peer_wait / _reduce_slots
 
@@ -34,7 +35,7 @@ class PeerExchange:
         if self.world > 8:
             raise RuntimeError("PeerExchange: at most 8 ranks (one NVLink domain)")
         self.n_rows, self.dim, self.device = n_rows, dim, device
-        self.gather = symm_mem.empty((self.world * n_rows, dim), dtype=torch.float32, device=device)
+        self.gather = symm_mem.empty((2, self.world * n_rows, dim), dtype=torch.float32, device=device)
         self.recv = symm_mem.empty((self.world, n_rows, dim), dtype=torch.float32, device=device)
         self.flags = symm_mem.empty((16,), dtype=torch.int32, device=device)
         self.flags.zero_()
@@ -68,10 +69,15 @@ class PeerExchange:
         return self._args(0)
 
     def wait_gather(self):
-        check(_lib.load().cdr_peer_wait(C.c_void_p(self.flags.data_ptr()), C.c_int32(self.world),
-                                        C.c_void_p(self.epoch_dev.data_ptr()), stream_ptr()), "cdr_peer_wait")
+        """Wait for every rank's push of this epoch and return a PRIVATE copy [world * n_rows, dim] of the gathered
+        rows (never aliases memory the peers write into)."""
+        out = torch.empty(self.world * self.n_rows, self.dim, dtype=torch.float32, device=self.device)
+        check(_lib.load().cdr_peer_wait_fetch(C.c_void_p(self.flags.data_ptr()), C.c_int32(self.world),
+                                              C.c_void_p(self.epoch_dev.data_ptr()), C.c_void_p(self.gather.data_ptr()),
+                                              C.c_int64(out.numel()), C.c_void_p(out.data_ptr()), stream_ptr()),
+              "cdr_peer_wait_fetch")
         kernels._count(1)
-        return self.gather
+        return out
 
     # ---- backward ------------------------------------------------------------------------------
     def reduce_scatter(self, g):
@@ -94,8 +100,7 @@ class _GatherPassages(torch.autograd.Function):
     @staticmethod
     def forward(ctx, p_local, xchg):
         ctx.xchg = xchg
-        # p_local already sits in slot `rank` of every gather buffer (pushed by the LayerNorm kernel); the
-        # returned tensor IS the symmetric buffer: it stays valid until the next begin_step()
+        # p_local already sits in slot `rank` of every rank's gather area (pushed by the LayerNorm kernel)
         return xchg.wait_gather()
 
     @staticmethod

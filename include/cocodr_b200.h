@@ -121,12 +121,17 @@ typedef struct cdr_peer_args {
   uint32_t* done_counter;
 } cdr_peer_args;
 /* cdr_ln_fwd that ALSO pushes the fp32 CLS row of every sequence >= first_seq into row
- * rank * (n_seq - first_seq) + (seq - first_seq) of each peer's gather buffer [world * (n_seq - first_seq), hidden]
- * and raises flag set 0 when done (fused compute + all-gather). */
+ * rank * (n_seq - first_seq) + (seq - first_seq) of each peer's gather area and raises flag set 0 when done (fused
+ * compute + all-gather).  The gather area is DOUBLE-BUFFERED: peer_buf[r] points at 2 x [world * (n_seq - first_seq),
+ * hidden] floats and epoch parity selects the half, so a rank that is one step ahead never overwrites rows a slower
+ * peer is still reading.  cdr_peer_wait_fetch waits for the world's pushes of the current epoch and copies that half
+ * into a private [world * rows, hidden] tensor. */
 int cdr_ln_fwd_push(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
                     float* cls_out, int32_t n_seq, int32_t seq_len, int32_t hidden, float eps, int32_t first_seq,
                     const cdr_peer_args* peers, void* stream);
 int cdr_peer_next_epoch(uint32_t* epoch, void* stream);
+int cdr_peer_wait_fetch(const uint32_t* local_flags, int32_t world, const uint32_t* epoch, const float* gather,
+                        int64_t half_elems, float* out, void* stream);
 /* hold the stream until local_flags[0..world) all carry *epoch (or a later one) */
 int cdr_peer_wait(const uint32_t* local_flags, int32_t world, const uint32_t* epoch, void* stream);
 /* reduce-scatter, push side: row block r of src [world*rows, dim] -> slot `rank` of rank r's receive buffer
