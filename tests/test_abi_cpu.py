@@ -59,3 +59,37 @@ def test_bad_arguments_fail_loudly_without_a_gpu(lib):
     assert lib.cdr_attn_fwd(C.byref(a), None) == -1 and b"seq_len" in lib.cdr_last_error()
     with pytest.raises(RuntimeError):
         _lib.check(rc, "cdr_gemm")
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """Every args struct crossing the C ABI: sizeof and every field offset of the ctypes mirror == what gcc lays out
+    from include/cocodr_b200.h (a silent mismatch would shift pointers, not fail)."""
+    import ctypes as C
+    import os
+    import shutil
+    import subprocess
+    from cocodr_b200 import _lib, optim, peer
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    pairs = {"cdr_gemm_args": _lib.GemmArgs, "cdr_attn_args": _lib.AttnArgs, "cdr_simmat_args": _lib.SimmatArgs,
+             "cdr_scan_args": _lib.ScanArgs, "cdr_opt_item": optim.OptItem, "cdr_opt_chunk": optim.OptChunk,
+             "cdr_opt_args": optim.OptArgs, "cdr_peer_args": peer.PeerArgs}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{_lib.HEADER}"', "int main(void) {"]
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src, exe = os.path.join(tmp_path, "abi.c"), os.path.join(tmp_path, "abi")
+    with open(src, "w") as f:
+        f.write("\n".join(lines))
+    subprocess.run(["gcc", "-std=c11", "-o", exe, src], check=True, capture_output=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    seen = 0
+    for line in out.strip().splitlines():
+        cname, field, val = line.split()
+        cls = pairs[cname]
+        want = C.sizeof(cls) if field == "size" else getattr(cls, field).offset
+        assert int(val) == want, f"{cname}.{field}: C {val} vs ctypes {want}"
+        seen += 1
+    assert seen == sum(len(c._fields_) + 1 for c in pairs.values())
