@@ -64,5 +64,8 @@ class GraphedTrainStep:
         for dst, src in zip(self.static_inputs, inputs):
             if torch.is_tensor(dst):
                 dst.copy_(src, non_blocking=True)
+        sync = getattr(self.optimizer, "sync_hyperparams", None)
+        if sync is not None:  # cocodr_b200.optim: scheduler-driven lr changes reach the device scalar the graph reads
+            sync()
         self.graph.replay()
         return self.static_loss

@@ -141,6 +141,16 @@ class _FusedOptimizer(torch.optim.Optimizer):
         a.norms, a.trust = tab["norms"].data_ptr(), tab["trust"].data_ptr()
         return a
 
+    def sync_hyperparams(self):
+        """Mirror host-side ``group['lr']`` changes (LR schedulers) into the device scalars the kernels read.  step()
+        does this itself; a CUDA-graph replay does not run Python, so ``graph.GraphedTrainStep`` calls it before
+        every replay."""
+        for gi, group in enumerate(self.param_groups):
+            tab = self._tables.get(gi)
+            if tab is not None and tab["lr_host"] != float(group["lr"]):
+                tab["lr"].fill_(float(group["lr"]))
+                tab["lr_host"] = float(group["lr"])
+
     def _finish(self, tab):
         for p in tab["params"]:
             self.state[p]["step"] = tab["step"]  # shared device counter (what state_dict() stores)

@@ -120,3 +120,34 @@ def test_optimizer_refreshes_encoder_shadows_and_graph_step():
         assert torch.equal(dst.view_as(want), want)
         n_checked += 1
     assert n_checked == 2 * 9
+
+
+def test_graphed_step_follows_host_lr_changes():
+    """A captured step reads lr from a device scalar; GraphedTrainStep mirrors scheduler-driven host changes before
+    every replay (lr = 0 freezes the parameters, a non-zero lr moves them again)."""
+    from transformers import BertConfig
+    from cocodr_b200 import models, optim
+    from cocodr_b200.graph import GraphedTrainStep
+    cfg = BertConfig(hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256,
+                     vocab_size=500, max_position_embeddings=64, hidden_dropout_prob=0.0,
+                     attention_probs_dropout_prob=0.0, num_labels=2)
+    torch.manual_seed(0)
+    m = models.BertDot_InBatch_NLL_LN(cfg).cuda().train()
+    opt = optim.AdamW([p for p in m.parameters() if p.requires_grad], lr=1e-3, eps=1e-8, semantics="torch").attach_shadows(m)
+    g = torch.Generator().manual_seed(5)
+    ids = torch.randint(5, 500, (8, 32), generator=g).cuda()
+    mask = torch.ones_like(ids)
+    w = torch.ones(4, device="cuda")
+    step = GraphedTrainStep(m, opt, (ids[:4], mask[:4], ids[4:], mask[4:], None, None, True, None, w))
+    probe = m.bert.encoder.layer[0].output.dense.weight
+    step(ids[:4], mask[:4], ids[4:], mask[4:])
+    torch.cuda.synchronize()
+    before = probe.detach().clone()
+    opt.param_groups[0]["lr"] = 0.0
+    step(ids[:4], mask[:4], ids[4:], mask[4:])
+    torch.cuda.synchronize()
+    assert torch.equal(probe.detach(), before)
+    opt.param_groups[0]["lr"] = 1e-3
+    step(ids[:4], mask[:4], ids[4:], mask[4:])
+    torch.cuda.synchronize()
+    assert (probe.detach() - before).abs().max().item() > 1e-5
