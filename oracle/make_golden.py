@@ -226,12 +226,48 @@ def gen_scan():
     print("scan ok")
 
 
+LAMB_SHAPES = [(96, 64), (64,), (7,), (300, 3)]
+
+
+def lamb_inputs(seed):
+    """Seeded parameters and per-step gradients shared by the fixture generator and the tests."""
+    g = torch.Generator().manual_seed(seed)
+    params = [torch.randn(*s, generator=g) * 0.05 for s in LAMB_SHAPES]
+    params[2].zero_()  # an all-zero tensor: weight_norm == 0 -> trust ratio 1 (lamb.py:112-113)
+    grads = [[torch.randn(*s, generator=g) * 0.01 for s in LAMB_SHAPES] for _ in range(3)]
+    return params, grads
+
+
+def gen_lamb():
+    """The reference's own Lamb (ANCE/utils/lamb.py, unmodified; only the absent tensorboardX import is stubbed)
+    driven for 3 steps -> parameters and trust ratios.  Pins oracle/optim_ref.lamb_step and the CUDA Lamb."""
+    import importlib.util
+    sys.modules.setdefault("tensorboardX", types.SimpleNamespace(SummaryWriter=object))
+    spec = importlib.util.spec_from_file_location("ref_lamb", os.path.join(REF, "ANCE", "utils", "lamb.py"))
+    ref_lamb = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_lamb)
+    out = {"seed": 77}
+    for tag, wd in (("wd0", 0.0), ("wd01", 0.01)):
+        params, grads = lamb_inputs(77)
+        ps = [torch.nn.Parameter(p.clone()) for p in params]
+        opt = ref_lamb.Lamb(ps, lr=1e-3, eps=1e-6, weight_decay=wd)
+        for step in range(3):
+            for p, g in zip(ps, grads[step]):
+                p.grad = g.clone()
+            opt.step()
+        for i, p in enumerate(ps):
+            out[f"{tag}.p{i}"] = p.detach().numpy()
+            out[f"{tag}.trust{i}"] = np.float32(float(opt.state[p]["trust_ratio"]))
+    np.savez_compressed(os.path.join(OUT, "lamb_tiny.npz"), **out)
+    print("lamb ok")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     os.environ.setdefault("MASTER_PORT", "29533")
     dist.init_process_group("gloo", rank=0, world_size=1)
-    which = sys.argv[1:] or ["ance", "idro", "greedy", "coco", "contrastive", "scan", "base"]
+    which = sys.argv[1:] or ["ance", "idro", "greedy", "coco", "contrastive", "scan", "base", "lamb"]
     if "ance" in which:
         gen_ance(TINY, "tiny", B=4, L=32, seed=100, full=False, with_grads=True)
     if "idro" in which:
@@ -244,6 +280,8 @@ def main():
         gen_contrastive_only()
     if "scan" in which:
         gen_scan()
+    if "lamb" in which:
+        gen_lamb()
     if "base" in which:
         gen_ance(BASE, "cfg1_base", B=8, L=128, seed=500, full=True, with_grads=False)
     dist.destroy_process_group()

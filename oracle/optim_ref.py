@@ -8,9 +8,11 @@
                      p -= step * m / (sqrt(v) + eps); then p -= lr * wd * p.
 * ``clip_coef``      torch.nn.utils.clip_grad_norm_ (run_ann.py:345-352): min(1, max_norm / (total_norm + 1e-6)).
 
-Parity unpinned for Lamb / HF AdamW: the reference's lamb.py uses the removed ``add_(Number, Tensor)`` overloads and
-imports tensorboardX (absent), and transformers 5.x no longer ships AdamW, so neither class runs in this image; the
-torch-semantics AdamW is checked against the installed ``torch.optim.AdamW`` in tests/test_optim_gpu.py.
+Pinning: ``lamb_step`` is checked against the UNMODIFIED reference class (ANCE/utils/lamb.py runs here once the absent
+tensorboardX import is stubbed; its deprecated ``add_(Number, Tensor)`` overloads still work): fixture
+tests/golden/lamb_tiny.npz written by oracle/make_golden.py, test tests/test_oracle_golden.py.  The torch-semantics
+AdamW is checked against the installed ``torch.optim.AdamW`` (tests/test_optim_gpu.py).  ``hf_adamw_step`` stays
+unpinned: transformers 5.x no longer ships AdamW (restated from transformers==2.3.0 optimization.py).
 """
 import math
 

@@ -151,3 +151,25 @@ def test_graphed_step_follows_host_lr_changes():
     step(ids[:4], mask[:4], ids[4:], mask[4:])
     torch.cuda.synchronize()
     assert (probe.detach() - before).abs().max().item() > 1e-5
+
+
+def test_lamb_matches_reference_fixture(golden_dir):
+    """cdr_lamb_multi vs the UNMODIFIED reference Lamb (fixture tests/golden/lamb_tiny.npz): parameters after 3
+    steps and the last trust ratios, with and without weight decay, including an all-zero tensor (trust ratio 1)."""
+    import os
+    import numpy as np
+    from cocodr_b200 import optim
+    from oracle.make_golden import lamb_inputs
+    g = np.load(os.path.join(golden_dir, "lamb_tiny.npz"))
+    for tag, wd in (("wd0", 0.0), ("wd01", 0.01)):
+        params, grads = lamb_inputs(int(g["seed"]))
+        ps = [torch.nn.Parameter(p.clone().cuda()) for p in params]
+        opt = optim.Lamb(ps, lr=1e-3, eps=1e-6, weight_decay=wd)
+        for step in range(3):
+            for p, gr in zip(ps, grads[step]):
+                p.grad = gr.clone().cuda()
+            opt.step()
+        for i, p in enumerate(ps):
+            np.testing.assert_allclose(p.detach().cpu().numpy(), g[f"{tag}.p{i}"], rtol=2e-5, atol=1e-7)
+            t = float(opt.state[p]["trust_ratio"])
+            assert abs(t - float(g[f"{tag}.trust{i}"])) <= 1e-4 * max(1.0, abs(t))

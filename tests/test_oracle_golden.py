@@ -157,3 +157,24 @@ def test_scan_small(golden_dir):
         for r in range(3):
             order = sorted(range(s.shape[1]), key=lambda j: (-s[r, j], j))[:100]
             assert order == list(I[r])
+
+
+def test_lamb_oracle_matches_reference_fixture(golden_dir):
+    """oracle/optim_ref.lamb_step vs the parameters and trust ratios the UNMODIFIED reference Lamb produced
+    (tests/golden/lamb_tiny.npz, written by oracle/make_golden.py gen_lamb)."""
+    import os
+    import numpy as np
+    import torch
+    from oracle import optim_ref
+    from oracle.make_golden import lamb_inputs
+    g = np.load(os.path.join(golden_dir, "lamb_tiny.npz"))
+    for tag, wd in (("wd0", 0.0), ("wd01", 0.01)):
+        params, grads = lamb_inputs(int(g["seed"]))
+        ms, vs = [torch.zeros_like(p) for p in params], [torch.zeros_like(p) for p in params]
+        trust = [1.0] * len(params)
+        for step in range(3):
+            for i, (p, m, v) in enumerate(zip(params, ms, vs)):
+                trust[i] = optim_ref.lamb_step(p, grads[step][i].clone(), m, v, lr=1e-3, eps=1e-6, weight_decay=wd)
+        for i, p in enumerate(params):
+            np.testing.assert_allclose(p.numpy(), g[f"{tag}.p{i}"], rtol=1e-6, atol=1e-8)
+            assert abs(trust[i] - float(g[f"{tag}.trust{i}"])) <= 1e-5 * max(1.0, abs(trust[i]))
