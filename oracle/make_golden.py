@@ -262,12 +262,56 @@ def gen_lamb():
     print("lamb ok")
 
 
+def gen_mining():
+    """The reference's own GenerateNegativePassaageID (ANCE/drivers/run_ann_data_gen.py:497-570), executed from its
+    source: the driver module does not import here (faiss, pytrec_eval, transformers.AdamW), so the function's AST node
+    is compiled on its own with the names it uses (random, np, trange).  Both branches: SelectTopK, and the shuffled one
+    with Python's ``random`` seeded -- the per-query permutations it draws are replayed and stored so the oracle and the
+    CUDA kernel can walk the candidates in the same order."""
+    import ast
+    import random
+    path = os.path.join(REF, "ANCE", "drivers", "run_ann_data_gen.py")
+    tree = ast.parse(open(path).read())
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "GenerateNegativePassaageID"][0]
+    ns = {"random": random, "np": np, "trange": range, "print": lambda *a, **k: None}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
+    ref_fn = ns["GenerateNegativePassaageID"]
+    rng = np.random.RandomState(5)
+    n_q, k, n_docs, n_neg = 40, 60, 400, 7
+    doc_pid = rng.permutation(4000)[:n_docs].astype(np.int64)
+    doc_pid[::9] = doc_pid[2]  # repeated passage ids
+    I = rng.randint(0, n_docs, size=(n_q, k)).astype(np.int64)
+    qids = np.arange(1000, 1000 + n_q)
+    pos = {int(q): int(doc_pid[rng.randint(0, n_docs)]) for q in qids}
+    pos[int(qids[1])] = 999_999  # positive never retrieved
+    I[2, 0] = int(np.where(doc_pid == pos[int(qids[2])])[0][0])
+    out = {"I": I, "doc_pid": doc_pid, "pos": np.array([pos[int(q)] for q in qids], dtype=np.int64), "n_neg": n_neg}
+    for tag, topk in (("topk", True), ("shuf", False)):
+        args = types.SimpleNamespace(ann_measure_topk_mrr=topk, negative_sample=n_neg, rank=0)
+        random.seed(99)
+        negs, mrr = ref_fn(args, qids, doc_pid, pos, I, set(int(q) for q in qids))
+        table = -np.ones((n_q, n_neg), dtype=np.int64)
+        for i, q in enumerate(qids):
+            table[i, :len(negs[q])] = negs[q]
+        out[f"{tag}.neg"], out[f"{tag}.rr"] = table, np.asarray(mrr, dtype=np.float64)
+        if not topk:  # replay the permutations the function drew (one random.shuffle(list(range(k))) per query)
+            random.seed(99)
+            orders = []
+            for _ in range(n_q):
+                o = list(range(k))
+                random.shuffle(o)
+                orders.append(o)
+            out["shuf.order"] = np.asarray(orders, dtype=np.int32)
+    np.savez_compressed(os.path.join(OUT, "mining_tiny.npz"), **out)
+    print("mining ok")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     os.environ.setdefault("MASTER_PORT", "29533")
     dist.init_process_group("gloo", rank=0, world_size=1)
-    which = sys.argv[1:] or ["ance", "idro", "greedy", "coco", "contrastive", "scan", "base", "lamb"]
+    which = sys.argv[1:] or ["ance", "idro", "greedy", "coco", "contrastive", "scan", "base", "lamb", "mining"]
     if "ance" in which:
         gen_ance(TINY, "tiny", B=4, L=32, seed=100, full=False, with_grads=True)
     if "idro" in which:
@@ -282,6 +326,8 @@ def main():
         gen_scan()
     if "lamb" in which:
         gen_lamb()
+    if "mining" in which:
+        gen_mining()
     if "base" in which:
         gen_ance(BASE, "cfg1_base", B=8, L=128, seed=500, full=True, with_grads=False)
     dist.destroy_process_group()

@@ -7,7 +7,9 @@ selected candidates -- ``top_ann_pid[:negative_sample + 1]`` when SelectTopK, ``
 (:536-541) -- skipping the positive (:551-554) and repeats (:556-557) until ``negative_sample`` ids are kept
 (:559-563).  The reference shuffles with Python's ``random``; the order is an explicit argument here.
 ``kmeans_step`` is one Lloyd iteration (faiss.Kmeans semantics of :340-351: L2 assignment, mean update, ties to the
-lowest index).  Parity unpinned: the reference function needs its driver's ``args`` / faiss and does not import here.
+lowest index).  Pinning: ``generate_negatives`` is checked against the UNMODIFIED reference function (its AST node is
+compiled on its own by oracle/make_golden.py gen_mining; fixture tests/golden/mining_tiny.npz); the k-means step has no
+reference counterpart importable here (faiss) -- parity unpinned for that one.
 """
 import numpy as np
 

@@ -70,3 +70,18 @@ def test_episode_on_resident_embeddings():
     shuf = mining.ann_episode(Q, torch.arange(n_q).cuda(), P, pid, pid[rows], top_k=50, n_neg=8, shuffle_seed=1)
     cand = pid[out["I"]]
     assert all(set(shuf["neg"][q].tolist()) <= set(cand[q].tolist()) for q in range(n_q))
+
+
+def test_mine_negatives_matches_reference_fixture(golden_dir):
+    """cdr_mine_negatives vs the outputs of the UNMODIFIED reference function (tests/golden/mining_tiny.npz)."""
+    import os
+    from cocodr_b200 import mining
+    g = np.load(os.path.join(golden_dir, "mining_tiny.npz"))
+    I, doc_pid, pos = (torch.from_numpy(g[k]).cuda() for k in ("I", "doc_pid", "pos"))
+    n_neg = int(g["n_neg"])
+    for tag in ("topk", "shuf"):
+        order = None if tag == "topk" else torch.from_numpy(g["shuf.order"]).cuda()
+        neg, cnt, rr = mining.mine_negatives(I, doc_pid, pos, n_neg, order=order)
+        assert (neg.cpu().numpy() == g[f"{tag}.neg"]).all()
+        assert (cnt.cpu().numpy() == (g[f"{tag}.neg"] >= 0).sum(1)).all()
+        np.testing.assert_allclose(rr.cpu().numpy(), g[f"{tag}.rr"], rtol=1e-6)

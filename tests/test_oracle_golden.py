@@ -178,3 +178,21 @@ def test_lamb_oracle_matches_reference_fixture(golden_dir):
         for i, p in enumerate(params):
             np.testing.assert_allclose(p.numpy(), g[f"{tag}.p{i}"], rtol=1e-6, atol=1e-8)
             assert abs(trust[i] - float(g[f"{tag}.trust{i}"])) <= 1e-5 * max(1.0, abs(trust[i]))
+
+
+def test_mining_oracle_matches_reference_fixture(golden_dir):
+    """oracle/mining_ref.generate_negatives vs the UNMODIFIED GenerateNegativePassaageID (its AST node executed by
+    oracle/make_golden.py gen_mining): both the SelectTopK and the shuffled branch, per-query negatives and
+    reciprocal ranks."""
+    import os
+    import numpy as np
+    from oracle import mining_ref
+    g = np.load(os.path.join(golden_dir, "mining_tiny.npz"))
+    I, doc_pid, pos, n_neg = g["I"], g["doc_pid"], g["pos"], int(g["n_neg"])
+    for tag in ("topk", "shuf"):
+        for q in range(I.shape[0]):
+            order = None if tag == "topk" else list(g["shuf.order"][q])
+            negs, rr = mining_ref.generate_negatives(list(I[q]), doc_pid, int(pos[q]), n_neg, order=order)
+            want = [int(v) for v in g[f"{tag}.neg"][q] if v >= 0]
+            assert negs == want, (tag, q)
+            assert abs(rr - float(g[f"{tag}.rr"][q])) < 1e-12
