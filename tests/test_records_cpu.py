@@ -94,3 +94,28 @@ def test_matches_the_unmodified_reference_class(tmp_path):
             assert a[0] == b[0] == o[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[1], o[1])
     seeded_ref, seeded = ref_util.EmbeddingCache(path, seed=3), records.EmbeddingCache(path, seed=3)
     assert np.array_equal(seeded_ref.ix_array, seeded.ix_array)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/ANCE/data/msmarco_data.py"), reason="reference tree not present")
+def test_gather_equals_the_reference_processing_fn(tmp_path):
+    """ids / attention mask of a gathered batch == what the UNMODIFIED GetProcessingFn (ANCE/data/msmarco_data.py:297-325,
+    its AST node compiled on its own: the module's other imports are absent here) builds record by record."""
+    import ast
+    import types as _types
+    import torch
+    from torch.utils.data import TensorDataset
+    from cocodr_b200 import records
+    path_ref = "/root/reference/ANCE/data/msmarco_data.py"
+    tree = ast.parse(open(path_ref).read())
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "GetProcessingFn"][0]
+    ns = {"torch": torch, "TensorDataset": TensorDataset}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path_ref, "exec"), ns)
+    path, toks, _ = _make(str(tmp_path), False, n=50, L=32)
+    for query, max_len in ((True, 32), (False, 32)):
+        args = _types.SimpleNamespace(max_query_length=max_len, max_seq_length=max_len)
+        ref_fn = ns["GetProcessingFn"](args, query=query)
+        with records.EmbeddingCache(path) as c:
+            b = c.gather(list(range(50)), max_len=max_len, pin=False)
+            for i in range(50):
+                ids_ref, mask_ref, _tt, idx_ref = ref_fn(c[i], i)[0]
+                assert torch.equal(b["ids"][i], ids_ref) and torch.equal(b["mask"][i], mask_ref) and int(idx_ref) == i
