@@ -4,8 +4,10 @@
 //
 // * one CTA per SM, static round-robin over (m_tile, n_tile, k_split) work items
 // * warp 0  : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx-count)
-// * warp 1  : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, cta_group::1)
-// * warps 2-17: epilogue (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
+// * warp 1  : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16; CG = 2 pairs two CTAs of a
+//             cluster on one 256-row tile with cta_group::2)
+// * warps 2..: epilogue, GEMM_EW<EPI> warps (8; 16 for the scan filters): tcgen05.ld 32x32b -> registers -> TMEM
+//             stage released -> fused epilogue -> global
 // * two TMEM accumulator stages (2 x BN columns) so the epilogue of tile i overlaps the MMAs of
 //   tile i+1
 // * operands may be K-major ([rows, K] row-major, the "NT" case) or MN-major ([K, rows] row-major)
