@@ -9,6 +9,7 @@ G=50 / BERT-base); here every rank reduce-scatters it along P_last, takes the Gr
 and all-reduces the [G, G] result -- the same numbers with half the bytes on NVLink and no full-matrix
 re-read.
 """
+import os
 from collections import defaultdict
 
 import torch
@@ -173,6 +174,129 @@ class iDROLoss(DROGreedyLoss):
                 off += n
         return mat
 
+    def _get_grad_grouped(self, params, gdro_losses_agg, gdro_counts_agg, g, n_towers):
+        """The same [G, P_last] matrix as ``_get_grad`` from ONE partial backward (K11).
+
+        Valid when sample i's loss depends on the encoder outputs of sample i only (the triplet NLL,
+        ANCE/model/models.py:101-108) and the towers ran as one pass over ``n_towers * B`` sequences (sequence s belongs
+        to sample s % B).  Then in the backward of sum_g mean_g every row of an activation gradient carries
+        d mean_{g(row)} only, and the gradient of mean_g w.r.t. a weight is dY[rows of g]^T X[rows of g]: the layer
+        backwards hand over their wgrad operands (ops.GroupCapture), rows are regrouped so that each group is one
+        contiguous K range, and one wgrad GEMM per (weight, present group) stores straight into the group's row of
+        the matrix.  Bias / LayerNorm gradients are per-group column sums: one GEMM with a one-hot [rows, G] operand.
+        """
+        cap = ops.GroupCapture()
+        ops.GROUP_CAPTURE = cap
+        try:
+            torch.autograd.grad(gdro_losses_agg.sum(), params, retain_graph=True, allow_unused=True)
+        finally:
+            ops.GROUP_CAPTURE = None
+        return self._grouped_from_records(cap.records, params, gdro_counts_agg, g, n_towers)
+
+    def _grouped_from_records(self, records, params, gdro_counts_agg, g, n_towers):
+        G = self.n_groups
+        dev = gdro_counts_agg.device
+        offs, dim = {}, 0
+        for p in params:
+            offs[id(p)] = (dim, p)
+            dim += p.numel()
+        mat = torch.zeros(G, dim, dtype=torch.float32, device=dev)
+        covered = {k for rec in records for k in rec["keys"]}
+        if not set(offs) <= covered:
+            raise RuntimeError("iDROLoss: grouped gradients need every selected parameter to belong to an encoder layer "
+                               "that ran through cocodr_b200.ops (set iDROLoss.grouped_wgrad = False otherwise)")
+        seq_group = g.to(torch.int64).repeat(n_towers)  # towers are concatenated: sequence s -> sample s % B
+        order = torch.argsort(seq_group, stable=True)
+        per_group = (gdro_counts_agg.to(torch.int64) * n_towers).tolist()  # sequences per group (one host transfer)
+        Gp = (G + 127) // 128 * 128
+        onehot = {}
+        for rec in records:
+            if any(k in offs for k in rec["keys"]):
+                self._grouped_layer(rec, mat, offs, seq_group, order, per_group, Gp, onehot)
+        return mat
+
+    def _grouped_layer(self, rec, mat, offs, seq_group, order, per_group, Gp, onehot):
+        keys, rps, L, n_seq, S = rec["keys"], rec["rps"], rec["L"], rec["n_seq"], rec["S"]
+        inv = 1.0 / S
+        G = self.n_groups
+        dev = mat.device
+        H = rec["x"].shape[1]
+        if n_seq != seq_group.numel():
+            raise RuntimeError("iDROLoss: grouped gradients need the towers in one encoder pass "
+                               f"({n_seq} sequences in the layer, {seq_group.numel()} expected)")
+
+        def slab(k, gi):  # fp32 view of group gi's gradient of parameter k (None when it is not selected)
+            ent = offs.get(keys[k])
+            if ent is None:
+                return None
+            o, p = ent
+            return mat[gi, o:o + p.numel()].view(p.shape)
+
+        def regroup(t, r):  # [n_seq * r, C] rows -> the sequences of every group contiguous
+            C = t.shape[1]
+            return t.reshape(n_seq, r * C)[order].reshape(n_seq * r, C)
+
+        def wgrad(a, b, out, r0, k):
+            K.gemm(a[r0:r0 + k], b[r0:r0 + k], out, M=a.shape[1], N=b.shape[1], K=k, a_major=1, b_major=1,
+                   epilogue=K.EPI_F32_ATOMIC, split_k=0, alpha=inv)
+
+        # ---- weights: per present group, K = that group's rows
+        dy2, gl, dz, x1, dy1, att = (regroup(rec[n], rps) for n in ("dy2", "gl", "dz", "x1", "dy1", "att"))
+        dqkv, x = regroup(rec["dqkv"], L), regroup(rec["x"], L)
+        o = 0
+        for gi, ns in enumerate(per_group):
+            if ns == 0:
+                continue
+            for k, a, b in ((12, dy2, gl), (10, dz, x1), (6, dy1, att)):  # output.dense, intermediate.dense, attention.output.dense
+                out = slab(k, gi)
+                if out is not None:
+                    wgrad(a, b, out, o * rps, ns * rps)
+            for j, k in enumerate((0, 2, 4)):  # query / key / value: column blocks of dQKV
+                out = slab(k, gi)
+                if out is not None:
+                    wgrad(dqkv[:, j * H:(j + 1) * H], x, out, o * L, ns * L)
+            o += ns
+
+        # ---- vectors: per-group column sums = one-hot^T R, through the same GEMM (exact products, fp32 accumulation)
+        def hot(r):
+            if r not in onehot:
+                e = torch.zeros(n_seq * r, Gp, dtype=torch.float16, device=dev)
+                e.scatter_(1, seq_group.repeat_interleave(r).unsqueeze(1), 1.0)
+                onehot[r] = e
+            return onehot[r]
+
+        def colsums(r, R, alpha, ks):
+            R = R.contiguous()
+            n = R.shape[1]
+            out = torch.zeros(Gp, n, dtype=torch.float32, device=dev)
+            K.gemm(hot(r), R, out, M=Gp, N=n, K=R.shape[0], a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0,
+                   alpha=alpha)
+            w = n // len(ks)
+            for j, k in enumerate(ks):
+                ent = offs.get(keys[k])
+                if ent is not None:
+                    mat[:, ent[0]:ent[0] + w] = out[:G, j * w:(j + 1) * w]
+
+        colsums(rps, rec["dy2"], inv, (13,))          # output.dense.bias
+        colsums(rps, rec["dz"], inv, (11,))           # intermediate.dense.bias
+        colsums(rps, rec["dy1"], inv, (7,))           # attention.output.dense.bias
+        colsums(L, rec["dqkv"], inv, (1, 3, 5))       # query / key / value bias
+        xhat1 = (rec["y1"].float() - rec["mean1"].unsqueeze(1)) * rec["rstd1"].unsqueeze(1)
+        d1 = rec["dx1"].float()
+        colsums(rps, rec["dx1"], inv, (9,))                        # attention.output.LayerNorm.bias
+        colsums(rps, (d1 * xhat1).half(), inv, (8,))               # attention.output.LayerNorm.weight
+        dy, dcls = rec["din2"]
+        if dy is not None:  # fp16, already in the scaled-gradient domain; the [CLS] gradient joins it through S
+            d2, a2 = dy.float(), inv
+            if dcls is not None:
+                d2.view(n_seq, rps, H)[:, 0] += S * dcls
+        else:
+            d2, a2 = torch.zeros(n_seq * rps, H, dtype=torch.float32, device=dev), 1.0
+            d2.view(n_seq, rps, H)[:, 0] = dcls
+        xhat2 = (rec["y2"].float() - rec["mean2"].unsqueeze(1)) * rec["rstd2"].unsqueeze(1)
+        colsums(rps, d2.half(), a2, (15,))                         # output.LayerNorm.bias
+        colsums(rps, (d2 * xhat2).half(), a2, (14,))               # output.LayerNorm.weight
+
     def _gram(self, all_grads):
         """Gram matrix of the rank-summed gradient rows (what :232-237 compute through a full all-reduce)."""
         G, P = all_grads.shape
@@ -194,8 +318,15 @@ class iDROLoss(DROGreedyLoss):
         dist.all_reduce(gram)
         return gram
 
-    def forward(self, model, losses, g):
-        """dro_loss.py:216-254 -> (robust_loss, group mean losses[G] detached, group counts[G])."""
+    # K11: take the group gradients from one shared partial backward + per-group wgrads when the caller vouches that
+    # the per-sample losses do not mix samples (``sample_towers``); False = one partial backward per present group
+    grouped_wgrad = os.environ.get("CDR_IDRO_GROUPED", "1") == "1"
+
+    def forward(self, model, losses, g, sample_towers=0):
+        """dro_loss.py:216-254 -> (robust_loss, group mean losses[G] detached, group counts[G]).
+
+        ``sample_towers``: n > 0 promises that loss i depends on encoder sequences {i, i + B, ..} of ONE pass over
+        n * B sequences only (the triplet NLL), which lets ``_get_grad_grouped`` replace the per-group backwards."""
         if not self.training:
             raise RuntimeError("iDROLoss.forward is only defined in training mode (as in the reference, where "
                                "gdro_counts_agg is undefined otherwise: dro_loss.py:222-226)")
@@ -205,7 +336,10 @@ class iDROLoss(DROGreedyLoss):
 
         mask = (counts > 0).float()
         params = self._params(model)
-        all_grads = self._get_grad(params, means, counts)
+        if sample_towers and self.grouped_wgrad and len(params) > 0:
+            all_grads = self._get_grad_grouped(params, means, counts, g, sample_towers)
+        else:
+            all_grads = self._get_grad(params, means, counts)
         gram = self._gram(all_grads)
         with torch.no_grad():
             norm = torch.sqrt(torch.diagonal(gram).clamp_min(0)).unsqueeze(-1)  # ||G_g||

@@ -112,6 +112,9 @@ class NLL(EmbeddingMixin):
         q_embs, a_embs, b_embs = self._towers(query_ids, attention_mask_q, input_ids_a, attention_mask_a, input_ids_b,
                                               attention_mask_b)
         loss, accs, logit_matrix = ops.pair_nll(q_embs, a_embs, b_embs)
+        # loss i reads the embeddings of triplet i only; when the three towers ran as one pass (sequence s = sample
+        # s % B) iDRO may take its group gradients from one shared backward (dro_loss.iDROLoss._get_grad_grouped)
+        self._sample_towers = 3 if query_ids.shape == input_ids_a.shape == input_ids_b.shape else 0
         return loss, accs, logit_matrix
 
 
@@ -163,7 +166,8 @@ class BertDot_NLL_LN(NLL, BertForSequenceClassification):
                 loss = loss * weights
             return loss.mean(), train_acc, logits
         if self.dro_type == 'idro':
-            robust_loss, group_losses, group_counts = self.loss(self.bert, loss, group_ids)
+            robust_loss, group_losses, group_counts = self.loss(self.bert, loss, group_ids,
+                                                                sample_towers=getattr(self, "_sample_towers", 0))
         else:
             robust_loss, group_losses, group_counts = self.loss(loss, group_ids, weights)
         host = torch.cat([robust_loss.detach().reshape(1), group_losses, group_counts]).tolist()  # one sync
@@ -229,6 +233,7 @@ class BertDot_InBatch_NLL_LN(BertDot_NLL_LN):
                       attention_mask_b=None, is_query=True, group_ids=None):
         if input_ids_a is None:
             return super().forward_model(query_ids, attention_mask_q, is_query=is_query)
+        self._sample_towers = 0  # the in-batch loss of sample i reads every passage: group gradients do not separate
         xchg = self._peer_exchange(query_ids, input_ids_a, input_ids_b)
         if xchg is not None:
             # fused path: the last LayerNorm kernel writes the passage CLS rows into every rank's gather buffer

@@ -18,6 +18,16 @@ _GRAD_SCALE = 1024.0
 FORCE_SHADOW_REFRESH = False  # set while a CUDA graph is being captured (graph.py)
 GRAD_SYNC = None              # an active gradsync.GradSync collects the flat gradient buffers of each backward
 CLS_PUSH = None               # (peer.PeerExchange, first_seq): the last LayerNorm pushes CLS rows to every rank (peer.py)
+GROUP_CAPTURE = None          # a GroupCapture: layer backwards also hand over their wgrad operands (dro_loss.py, K11)
+
+
+class GroupCapture:
+    """Collects, per encoder-layer backward, the operands of its parameter-gradient reductions (the activation
+    gradients and the saved activations), so that iDRO can reduce them per GROUP of samples instead of over the
+    whole batch (dro_loss.iDROLoss._get_grad_grouped) -- one shared dgrad pass instead of one backward per group."""
+
+    def __init__(self):
+        self.records = []
 
 
 def set_grad_scale(s: float):
@@ -211,6 +221,7 @@ class BertLayerFn(torch.autograd.Function):
         ctx.save_for_backward(x, key_bias, qkv, att, lse, y1, x1, mean1, rstd1, gp, gl, y2, mean2, rstd2, g1, g2)
         ctx.shadow_w = (sh.wqkv, sh.wo, sh.wi, sh.wo2)
         ctx.meta = (n_seq, L, heads, I, emit_cls, _GRAD_SCALE)
+        ctx.param_keys = tuple(id(t) for t in (wq, bq, wk, bk, wv, bv, wo, bo, g1, be1, wi, bi, wo2, bo2, g2, be2))
         ctx.set_materialize_grads(False)
         if emit_cls:
             return y, cls
@@ -274,6 +285,11 @@ class BertLayerFn(torch.autograd.Function):
             K.colsum(dqkv, dbqkv, rows=T, cols=3 * H, scale=inv)
         if GRAD_SYNC is not None:
             GRAD_SYNC.submit(flat)
+        if GROUP_CAPTURE is not None:
+            GROUP_CAPTURE.records.append(dict(
+                keys=ctx.param_keys, rps=L, L=L, n_seq=n_seq, S=S, dy2=dy2, gl=gl, dz=dz, x1=x1, dy1=dy1, att=att,
+                dx1=dx1, y1=y1, mean1=mean1, rstd1=rstd1, y2=y2, mean2=mean2, rstd2=rstd2, din2=(dy, dcls), dqkv=dqkv,
+                x=x))
         return (dx, None, dwqkv[0:H], dbqkv[0:H], dwqkv[H:2 * H], dbqkv[H:2 * H], dwqkv[2 * H:], dbqkv[2 * H:], dwo,
                 dbo, dg1, dbe1, dwi, dbi, dwo2, dbo2, dg2, dbe2, None, None, None, None, None, None)
 
@@ -322,6 +338,7 @@ class BertLastLayerCLSFn(torch.autograd.Function):
         ctx.save_for_backward(x, key_bias, qkv, att, lse, y1, x1, mean1, rstd1, gp, gl, y2, mean2, rstd2, g1, g2)
         ctx.shadow_w = (sh.wqkv, sh.wo, sh.wi, sh.wo2)
         ctx.meta = (n_seq, L, heads, I, _GRAD_SCALE)
+        ctx.param_keys = tuple(id(t) for t in (wq, bq, wk, bk, wv, bv, wo, bo, g1, be1, wi, bi, wo2, bo2, g2, be2))
         return cls
 
     @staticmethod
@@ -379,6 +396,11 @@ class BertLastLayerCLSFn(torch.autograd.Function):
             K.colsum(dqkv, dbqkv, rows=T, cols=3 * H, scale=inv)
         if GRAD_SYNC is not None:
             GRAD_SYNC.submit(flat)
+        if GROUP_CAPTURE is not None:  # rows of the post-attention operands are sequences here (one [CLS] row each)
+            GROUP_CAPTURE.records.append(dict(
+                keys=ctx.param_keys, rps=1, L=L, n_seq=n_seq, S=S, dy2=dy2, gl=gl, dz=dz, x1=x1, dy1=dy1,
+                att=attc.contiguous(), dx1=dx1, y1=y1, mean1=mean1, rstd1=rstd1, y2=y2, mean2=mean2, rstd2=rstd2,
+                din2=(None, dcls), dqkv=dqkv, x=x))
         return (dx, None, dwqkv[0:H], dbqkv[0:H], dwqkv[H:2 * H], dbqkv[H:2 * H], dwqkv[2 * H:], dbqkv[2 * H:], dwo,
                 dbo, dg1, dbe1, dwi, dbi, dwo2, dbo2, dg2, dbe2, None, None, None, None, None)
 

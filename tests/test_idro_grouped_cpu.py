@@ -1,0 +1,108 @@
+"""CPU: host logic of the iDRO grouped-gradient path (dro_loss.iDROLoss._grouped_from_records, K11).
+
+The layer backwards hand over their wgrad operands; this test feeds the reducer synthetic operands of a real
+(torch, fp32) post-LN transformer layer whose per-group parameter gradients autograd can compute directly -- the way
+the reference takes them (one ``autograd.grad`` per group, ANCE/model/dro_loss.py:192-204) -- with ``K.gemm`` replaced
+by a torch restatement of the one configuration the reducer uses (both operands MN-major, fp32 accumulate-add).
+What is under test is the row regrouping, the K ranges, the parameter-to-column map, the one-hot column sums and the
+LayerNorm gradient formulas; the CUDA GEMM itself is covered by tests/test_gemm_gpu.py.
+"""
+import types
+
+import pytest
+import torch
+
+from cocodr_b200 import dro_loss
+from cocodr_b200 import kernels as K
+
+
+def _fake_gemm(a, b, out, *, M, N, K, a_major=0, b_major=0, epilogue=0, split_k=1, alpha=1.0, **kw):  # noqa: N803
+    from cocodr_b200 import kernels
+    assert (a_major, b_major, epilogue) == (1, 1, kernels.EPI_F32_ATOMIC)
+    assert a.dtype == torch.float16 and b.dtype == torch.float16 and out.dtype == torch.float32
+    assert a.shape == (K, M) and b.shape == (K, N) and out.shape == (M, N)
+    assert a.stride(1) == 1 and b.stride(1) == 1 and out.is_contiguous()
+    out += alpha * (a.float().t() @ b.float())
+    return out
+
+
+def _layer(x, p, n_seq, L, cls_only):
+    """A post-LN layer restricted to what the reducer sees: y = LN2(x1 + W2 gelu(W1 x1 + b1) + b2),
+    x1 = LN1(x + Wo att + bo), att = a fixed per-sequence mixing of V-like projections, qkv = x Wqkv^T + b."""
+    wq, bq, wk, bk, wv, bv, wo, bo, g1, be1, wi, bi, wo2, bo2, g2, be2 = p
+    qkv = torch.cat([x @ wq.t() + bq, x @ wk.t() + bk, x @ wv.t() + bv], 1)
+    H = x.shape[1]
+    q, k, v = qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:]
+    att = torch.tanh(q) * torch.sigmoid(k) + v  # stand-in for attention (keeps samples separate)
+    att = att + att.view(n_seq, L, H).mean(1, keepdim=True).expand(n_seq, L, H).reshape(-1, H)  # mixes a sequence's rows
+    if cls_only:  # ops.BertLastLayerCLSFn: everything after the attention core runs on row 0 of every sequence
+        x, att = x.view(n_seq, L, H)[:, 0], att.view(n_seq, L, H)[:, 0]
+    y1 = x + att @ wo.t() + bo
+    x1 = torch.nn.functional.layer_norm(y1, (H,), g1, be1, 1e-12)
+    z = x1 @ wi.t() + bi
+    gl = torch.nn.functional.gelu(z)
+    y2 = x1 + gl @ wo2.t() + bo2
+    y = torch.nn.functional.layer_norm(y2, (H,), g2, be2, 1e-12)
+    return dict(qkv=qkv, att=att, y1=y1, x1=x1, z=z, gl=gl, y2=y2, y=y)
+
+
+@pytest.mark.parametrize("rps", [4, 1])
+def test_grouped_reducer_matches_per_group_autograd(monkeypatch, rps):
+    monkeypatch.setattr(K, "gemm", _fake_gemm)
+    torch.manual_seed(3 + rps)
+    B, towers, G, H, I, L = 5, 3, 4, 8, 16, 4  # noqa: E741
+    n_seq = B * towers
+    rows = n_seq * L
+    S = 64.0
+    g = torch.tensor([2, 0, 2, 3, 0])  # group 1 absent
+    counts = torch.bincount(g, minlength=G).float()
+    shapes = [(H, H), (H,), (H, H), (H,), (H, H), (H,), (H, H), (H,), (H,), (H,), (I, H), (I,), (H, I), (H,), (H,), (H,)]
+    params = [torch.nn.Parameter(torch.randn(s) * (0.3 if len(s) == 2 else 0.1) + (1.0 if i in (8, 14) else 0.0))
+              for i, s in enumerate(shapes)]
+    x = torch.randn(rows, H)
+    t = _layer(x, params, n_seq, L, rps == 1)
+    # per-sample loss: a fixed random functional of the sample's own rows; group means as in iDROLoss.forward
+    wsel = torch.randn(n_seq * rps, H)
+    per_seq = (t["y"] * wsel).view(n_seq, -1).sum(1)
+    loss = per_seq.view(towers, B).sum(0)
+    means = torch.zeros(G).index_add(0, g, loss) / (counts + (counts == 0).float())
+    want = torch.zeros(G, sum(p.numel() for p in params))
+    for gi in range(G):
+        if counts[gi] > 0:
+            gr = torch.autograd.grad(means[gi], params, retain_graph=True)
+            want[gi] = torch.cat([v.reshape(-1) for v in gr])
+
+    # the operands a layer backward would hand over, for the backward of means.sum(), in the S-scaled fp16 domain
+    inter = [t[n] for n in ("y", "y2", "z", "x1", "y1", "att", "qkv")]
+    d_y, d_y2, d_z, d_x1tot, d_y1, d_att, d_qkv = torch.autograd.grad(means.sum(), inter, retain_graph=True)
+    # d(x1) as the LayerNorm-1 backward sees it: its incoming gradient is the total d(x1); dx1 in ops.py is exactly that
+    mean1, rstd1 = t["y1"].mean(1), (t["y1"].var(1, unbiased=False) + 1e-12).rsqrt()
+    mean2, rstd2 = t["y2"].mean(1), (t["y2"].var(1, unbiased=False) + 1e-12).rsqrt()
+    h = lambda v: (v * S).half()  # noqa: E731
+    rec = dict(keys=tuple(id(p) for p in params), rps=rps, L=L, n_seq=n_seq, S=S,
+               dy2=h(d_y2), gl=t["gl"].detach().half(), dz=h(d_z), x1=t["x1"].detach().half(), dy1=h(d_y1),
+               att=t["att"].detach().half(), dx1=h(d_x1tot), y1=t["y1"].detach().half(), mean1=mean1.detach(),
+               rstd1=rstd1.detach(), y2=t["y2"].detach().half(), mean2=mean2.detach(), rstd2=rstd2.detach(),
+               din2=(h(d_y), None), dqkv=h(d_qkv), x=x.half())
+    if rps == 1:  # the [CLS]-only layer hands over an unscaled fp32 [CLS] gradient instead of a scaled fp16 one
+        rec["din2"] = (None, d_y.detach().clone())
+
+    crit = dro_loss.iDROLoss(types.SimpleNamespace(model_size="base", local_rank=0), G, 0.25, 0.01, 0.1, 0.05)
+    got = crit._grouped_from_records([rec], params, counts, g, towers)
+    assert got.shape == want.shape
+    assert torch.count_nonzero(got[1]) == 0  # absent group: zero row, as in the reference (dro_loss.py:199-201)
+    off = 0
+    for i, p in enumerate(params):
+        n = p.numel()
+        w_, g_ = want[:, off:off + n], got[:, off:off + n]
+        err = (w_ - g_).abs().max().item()
+        assert err <= 2e-2 * w_.abs().max().item() + 1e-4, (i, tuple(p.shape), err, w_.abs().max().item())
+        off += n
+
+
+def test_grouped_reducer_rejects_uncovered_parameters(monkeypatch):
+    monkeypatch.setattr(K, "gemm", _fake_gemm)
+    crit = dro_loss.iDROLoss(types.SimpleNamespace(model_size="base", local_rank=0), 2, 0.25, 0.01, 0.1, 0.05)
+    p = torch.nn.Parameter(torch.zeros(4))
+    with pytest.raises(RuntimeError):
+        crit._grouped_from_records([], [p], torch.tensor([1.0, 1.0]), torch.tensor([0, 1]), 3)
