@@ -184,3 +184,28 @@ extern "C" int cdr_gemm(const cdr_gemm_args* g, void* stream) {
   p.ldaux = g->ldaux;
   return cdr::gemm_run(*g, p, static_cast<cudaStream_t>(stream));
 }
+
+extern "C" int cdr_gemm_segments(const cdr_gemm_args* base, int32_t n_seg, const int64_t* row_begin,
+                                 const int64_t* row_count, const int64_t* out_offset, void* stream) {
+  if (base == nullptr || n_seg < 0 || (n_seg > 0 && (!row_begin || !row_count || !out_offset))) {
+    cdr::set_error("cdr_gemm_segments: null argument");
+    return CDR_EINVAL;
+  }
+  CDR_REQUIRE(base->a_major == 1 && base->b_major == 1,
+              "cdr_gemm_segments: both operands must be MN-major (the segmented axis is K)");
+  CDR_REQUIRE(base->epilogue == CDR_EPI_F32_ATOMIC || base->epilogue == CDR_EPI_F32_STORE,
+              "cdr_gemm_segments: fp32 epilogues only");
+  for (int32_t i = 0; i < n_seg; ++i) {
+    CDR_REQUIRE(row_begin[i] >= 0 && row_count[i] >= 0 && out_offset[i] >= 0, "cdr_gemm_segments: negative entry %d", i);
+    if (row_count[i] == 0) continue;
+    cdr_gemm_args g = *base;
+    g.a = static_cast<const __half*>(base->a) + row_begin[i] * base->lda;
+    g.b = static_cast<const __half*>(base->b) + row_begin[i] * base->ldb;
+    g.out = static_cast<float*>(base->out) + out_offset[i];
+    g.K = row_count[i];
+    const int rc = cdr_gemm(&g, stream);
+    if (rc != CDR_OK) return rc;
+  }
+  return CDR_OK;
+}
+

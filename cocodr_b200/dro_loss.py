@@ -225,37 +225,32 @@ class iDROLoss(DROGreedyLoss):
             raise RuntimeError("iDROLoss: grouped gradients need the towers in one encoder pass "
                                f"({n_seq} sequences in the layer, {seq_group.numel()} expected)")
 
-        def slab(k, gi):  # fp32 view of group gi's gradient of parameter k (None when it is not selected)
-            ent = offs.get(keys[k])
-            if ent is None:
-                return None
-            o, p = ent
-            return mat[gi, o:o + p.numel()].view(p.shape)
-
         def regroup(t, r):  # [n_seq * r, C] rows -> the sequences of every group contiguous
             C = t.shape[1]
             return t.reshape(n_seq, r * C)[order].reshape(n_seq * r, C)
 
-        def wgrad(a, b, out, r0, k):
-            K.gemm(a[r0:r0 + k], b[r0:r0 + k], out, M=a.shape[1], N=b.shape[1], K=k, a_major=1, b_major=1,
-                   epilogue=K.EPI_F32_ATOMIC, split_k=0, alpha=inv)
+        # ---- weights: per present group one wgrad over that group's rows (K range), stored at the group's row of mat
+        present = [gi for gi, ns in enumerate(per_group) if ns > 0]
+        first, o = {}, 0
+        for gi in present:
+            first[gi] = o
+            o += per_group[gi]
+        dim = mat.shape[1]
 
-        # ---- weights: per present group, K = that group's rows
+        def wgrads(k, a, b, r):
+            ent = offs.get(keys[k])
+            if ent is not None:
+                K.gemm_segments(a, b, mat, M=a.shape[1], N=b.shape[1], row_begin=[first[gi] * r for gi in present],
+                                row_count=[per_group[gi] * r for gi in present],
+                                out_offset=[gi * dim + ent[0] for gi in present], alpha=inv)
+
         dy2, gl, dz, x1, dy1, att = (regroup(rec[n], rps) for n in ("dy2", "gl", "dz", "x1", "dy1", "att"))
         dqkv, x = regroup(rec["dqkv"], L), regroup(rec["x"], L)
-        o = 0
-        for gi, ns in enumerate(per_group):
-            if ns == 0:
-                continue
-            for k, a, b in ((12, dy2, gl), (10, dz, x1), (6, dy1, att)):  # output.dense, intermediate.dense, attention.output.dense
-                out = slab(k, gi)
-                if out is not None:
-                    wgrad(a, b, out, o * rps, ns * rps)
-            for j, k in enumerate((0, 2, 4)):  # query / key / value: column blocks of dQKV
-                out = slab(k, gi)
-                if out is not None:
-                    wgrad(dqkv[:, j * H:(j + 1) * H], x, out, o * L, ns * L)
-            o += ns
+        wgrads(12, dy2, gl, rps)   # output.dense.weight [H, I]
+        wgrads(10, dz, x1, rps)    # intermediate.dense.weight [I, H]
+        wgrads(6, dy1, att, rps)   # attention.output.dense.weight [H, H]
+        for j, k in enumerate((0, 2, 4)):  # query / key / value weights: column blocks of dQKV
+            wgrads(k, dqkv[:, j * H:(j + 1) * H], x, L)
 
         # ---- vectors: per-group column sums = one-hot^T R, through the same GEMM (exact products, fp32 accumulation)
         def hot(r):

@@ -78,6 +78,31 @@ def gemm(a, b, out, *, M, N, K, a_major=0, b_major=0, epilogue=EPI_STORE_F16, bi
     return out
 
 
+def gemm_segments(a, b, out, *, M, N, row_begin, row_count, out_offset, alpha=1.0, epilogue=EPI_F32_ATOMIC,
+                  split_k=0, ldo=None):
+    """cdr_gemm_segments: for every i, out.view(-1)[out_offset[i]:][M, N] (+)= alpha * a[rows_i]^T @ b[rows_i] with
+    rows_i = [row_begin[i], row_begin[i] + row_count[i]) -- both operands MN-major ([rows, M] / [rows, N] fp16),
+    fp32 output; one C call enqueues all segments (iDRO per-group wgrad)."""
+    _need_cuda(a, b, out)
+    assert a.dtype == torch.float16 and b.dtype == torch.float16 and out.dtype == torch.float32
+    n = len(row_begin)
+    assert len(row_count) == n and len(out_offset) == n
+    g = _lib.GemmArgs()
+    g.a, g.b, g.out, g.out2 = a.data_ptr(), b.data_ptr(), out.data_ptr(), 0
+    g.bias, g.aux = 0, 0
+    g.M, g.N, g.K = M, N, 0
+    g.lda, g.ldb, g.ldo, g.ldaux = a.stride(0), b.stride(0), (ldo if ldo is not None else N), 0
+    g.a_major, g.b_major, g.epilogue, g.split_k = 1, 1, epilogue, split_k
+    g.alpha = alpha
+    g.dbg_lbo, g.dbg_sbo = 0, 0
+    g.colsum, g.colsum_scale = 0, 1.0
+    arr = C.c_int64 * n
+    _run("cdr_gemm_segments", lambda: _lib.load().cdr_gemm_segments(C.byref(g), C.c_int32(n), arr(*row_begin),
+                                                                   arr(*row_count), arr(*out_offset), stream_ptr()))
+    _count(sum(1 for c in row_count if c > 0))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # helpers: explicit ctypes scalars (no argtypes are registered, so every scalar is wrapped here)
 # ------------------------------------------------------------------------------------------------

@@ -77,6 +77,15 @@ typedef struct cdr_gemm_args {
 
 int cdr_gemm(const cdr_gemm_args* args, void* stream);
 
+/* Row-segmented reduction (iDRO per-group wgrad, K11: replaces the G partial backwards of
+ * ANCE/model/dro_loss.py:192-204 for the weights).  `base` describes a GEMM whose operands are both MN-major
+ * (a_major = b_major = 1: A [K, M], B [K, N], i.e. K runs over rows) with an fp32 epilogue; for every segment i the
+ * same GEMM is enqueued on rows [row_begin[i], row_begin[i] + row_count[i]) of A and B with its output at
+ * (float*)base->out + out_offset[i] (elements).  The three arrays are HOST arrays of n_seg entries; segments with
+ * row_count 0 are skipped. */
+int cdr_gemm_segments(const cdr_gemm_args* base, int32_t n_seg, const int64_t* row_begin, const int64_t* row_count,
+                      const int64_t* out_offset, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Memory-bound encoder kernels (K1, LN halves of K4/K6, bias gradients, casts).
  * Replace HF BertEmbeddings / nn.LayerNorm (+ their autograd) reached through self.bert(...)

@@ -78,6 +78,24 @@ def test_wgrad_both_mn_major(M, N, K, split):
     _check(out, 1.0 + 0.25 * (dy.float().t() @ x.float()), tol=2e-3, what="wgrad")
 
 
+def test_row_segments():
+    """cdr_gemm_segments: the wgrad GEMM on row ranges of its operands, each into its own fp32 block (iDRO K11)."""
+    from cocodr_b200 import kernels as k
+    rows, M, N = 1000, 128, 192
+    a, b = _rand((rows, 2 * M), 11), _rand((rows, N), 12)
+    a_cols = a[:, M:]  # a column block of a wider tensor (dQKV -> query / key / value), row stride 2M
+    begin, count = [0, 128, 131, 640], [128, 3, 509, 360]
+    out = torch.ones(6, M * N, dtype=torch.float32, device="cuda")
+    offs = [4 * M * N, 0, 2 * M * N, 5 * M * N]
+    k.gemm_segments(a_cols, b, out, M=M, N=N, row_begin=begin, row_count=count, out_offset=offs, alpha=0.5)
+    for r0, n, o in zip(begin, count, offs):
+        ref = 1.0 + 0.5 * (a_cols[r0:r0 + n].float().t() @ b[r0:r0 + n].float())
+        _check(out.view(-1)[o:o + M * N].view(M, N), ref, tol=2e-3, what=f"segment rows {r0}+{n}")
+    assert torch.equal(out[1], torch.ones_like(out[1])) and torch.equal(out[3], torch.ones_like(out[3]))
+    with pytest.raises(RuntimeError):
+        k.gemm_segments(a_cols, b, out, M=M, N=N, row_begin=[0], row_count=[8], out_offset=[0], epilogue=k.EPI_STORE_F16)
+
+
 def test_errors_are_loud():
     from cocodr_b200 import kernels as k
     a, b = _rand((128, 60), 1), _rand((128, 60), 2)

@@ -26,6 +26,18 @@ def _fake_gemm(a, b, out, *, M, N, K, a_major=0, b_major=0, epilogue=0, split_k=
     return out
 
 
+def _fake_gemm_segments(a, b, out, *, M, N, row_begin, row_count, out_offset, alpha=1.0, **kw):  # noqa: N803
+    """cdr_gemm_segments (include/cocodr_b200.h) restated: segment i reduces rows [begin, begin + count) of a and b
+    into the [M, N] fp32 block that starts out_offset[i] elements into out."""
+    assert a.shape[1] == M and b.shape[1] == N and a.stride(1) == 1 and b.stride(1) == 1 and out.is_contiguous()
+    flat = out.view(-1)
+    for rb, rc, off in zip(row_begin, row_count, out_offset):
+        assert rc > 0 and rb + rc <= a.shape[0]
+        _fake_gemm(a[rb:rb + rc], b[rb:rb + rc], flat[off:off + M * N].view(M, N), M=M, N=N, K=rc, a_major=1, b_major=1,
+                   epilogue=K.EPI_F32_ATOMIC, alpha=alpha)
+    return out
+
+
 def _layer(x, p, n_seq, L, cls_only):
     """A post-LN layer restricted to what the reducer sees: y = LN2(x1 + W2 gelu(W1 x1 + b1) + b2),
     x1 = LN1(x + Wo att + bo), att = a fixed per-sequence mixing of V-like projections, qkv = x Wqkv^T + b."""
@@ -49,6 +61,7 @@ def _layer(x, p, n_seq, L, cls_only):
 @pytest.mark.parametrize("rps", [4, 1])
 def test_grouped_reducer_matches_per_group_autograd(monkeypatch, rps):
     monkeypatch.setattr(K, "gemm", _fake_gemm)
+    monkeypatch.setattr(K, "gemm_segments", _fake_gemm_segments)
     torch.manual_seed(3 + rps)
     B, towers, G, H, I, L = 5, 3, 4, 8, 16, 4  # noqa: E741
     n_seq = B * towers
@@ -102,6 +115,7 @@ def test_grouped_reducer_matches_per_group_autograd(monkeypatch, rps):
 
 def test_grouped_reducer_rejects_uncovered_parameters(monkeypatch):
     monkeypatch.setattr(K, "gemm", _fake_gemm)
+    monkeypatch.setattr(K, "gemm_segments", _fake_gemm_segments)
     crit = dro_loss.iDROLoss(types.SimpleNamespace(model_size="base", local_rank=0), 2, 0.25, 0.01, 0.1, 0.05)
     p = torch.nn.Parameter(torch.zeros(4))
     with pytest.raises(RuntimeError):

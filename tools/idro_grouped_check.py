@@ -28,8 +28,9 @@ def main():
     if not args.skip_pytest:  # the pinned 3-step reference trajectory (tests/golden/idro_tiny.npz) through the grouped path
         import pytest
         root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-        rc = pytest.main([os.path.join(root, "tests", "test_model_gpu.py"), "-q", "-x", "-k", "idro", "-p", "no:cacheprovider"])
-        print(json.dumps({"idro_trajectory_pytest_rc": int(rc)}), flush=True)
+        rc = pytest.main([os.path.join(root, "tests", "test_model_gpu.py"), os.path.join(root, "tests", "test_gemm_gpu.py"),
+                          "-q", "-x", "-k", "idro or segments", "-p", "no:cacheprovider"])
+        print(json.dumps({"idro_trajectory_and_segments_pytest_rc": int(rc)}), flush=True)
     B, L, G = 64, 128, 50
     dev = torch.device("cuda:0")
     cfg = BertConfig(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, num_labels=2)
