@@ -73,6 +73,7 @@ static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, c
   }
   if constexpr (A_MN && B_MN) {
     if (epi == CDR_EPI_F32_ATOMIC) return launch_gemm<BN, true, true, CDR_EPI_F32_ATOMIC>(ta, tb, p, st);
+    if (epi == CDR_EPI_F32_GROUPED) return launch_gemm<BN, true, true, CDR_EPI_F32_GROUPED>(ta, tb, p, st);
   }
   set_error("cdr_gemm: epilogue %d not instantiated for layout a_major=%d b_major=%d", epi, (int)A_MN, (int)B_MN);
   return CDR_EINVAL;
@@ -106,7 +107,9 @@ int gemm_run(const cdr_gemm_args& g, GemmParams p, cudaStream_t st) {
   p.n_tiles = (p.N + BN - 1) / BN;
   const int total_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
   int split = g.split_k;
-  if (split <= 0) {
+  if (g.epilogue == CDR_EPI_F32_GROUPED) {
+    split = p.split_k;  // one split per group, ranges from p.seg_kb (cdr_gemm_grouped)
+  } else if (split <= 0) {
     // auto: minimise rounds x (k-blocks per item + a fixed per-item cost for pipeline ramp and the exposed
     // part of the epilogue), i.e. prefer splits whose item count fills whole waves of the persistent grid
     const int tiles = p.m_tiles * p.n_tiles;
@@ -125,10 +128,15 @@ int gemm_run(const cdr_gemm_args& g, GemmParams p, cudaStream_t st) {
       }
     }
   }
-  if (split > total_kb) split = total_kb;
-  p.kb_per_split = (total_kb + split - 1) / split;
-  p.split_k = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
-  CDR_REQUIRE(p.split_k == 1 || g.epilogue == CDR_EPI_F32_ATOMIC, "cdr_gemm: split_k > 1 needs CDR_EPI_F32_ATOMIC");
+  if (g.epilogue == CDR_EPI_F32_GROUPED) {
+    p.kb_per_split = total_kb;
+    p.split_k = split;
+  } else {
+    if (split > total_kb) split = total_kb;
+    p.kb_per_split = (total_kb + split - 1) / split;
+    p.split_k = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
+    CDR_REQUIRE(p.split_k == 1 || g.epilogue == CDR_EPI_F32_ATOMIC, "cdr_gemm: split_k > 1 needs CDR_EPI_F32_ATOMIC");
+  }
   p.alpha = g.alpha;
   p.colsum = g.colsum;
   p.colsum_scale = g.colsum_scale;
@@ -164,6 +172,7 @@ extern "C" int cdr_gemm(const cdr_gemm_args* g, void* stream) {
   }
   CDR_REQUIRE(g->epilogue != CDR_EPI_SCAN_FILTER && g->epilogue != CDR_EPI_SCAN_FILTER_Q,
               "cdr_gemm: the scan filter epilogues are internal to cdr_scan_topk");
+  CDR_REQUIRE(g->epilogue != CDR_EPI_F32_GROUPED, "cdr_gemm: the grouped epilogue is internal to cdr_gemm_grouped");
   CDR_REQUIRE(g->out != nullptr, "cdr_gemm: null output");
   const bool f32 = g->epilogue == CDR_EPI_F32_ATOMIC || g->epilogue == CDR_EPI_F32_STORE;
   CDR_REQUIRE(g->ldo % (f32 ? 4 : 8) == 0, "cdr_gemm: ldo must keep rows 16-byte aligned (ldo=%lld)", (long long)g->ldo);
@@ -207,5 +216,29 @@ extern "C" int cdr_gemm_segments(const cdr_gemm_args* base, int32_t n_seg, const
     if (rc != CDR_OK) return rc;
   }
   return CDR_OK;
+}
+
+extern "C" int cdr_gemm_grouped(const cdr_gemm_args* base, int32_t n_groups, const int32_t* seg_kb,
+                                int64_t out_group_stride, void* stream) {
+  if (base == nullptr || seg_kb == nullptr) {
+    cdr::set_error("cdr_gemm_grouped: null argument");
+    return CDR_EINVAL;
+  }
+  CDR_REQUIRE(n_groups > 0 && n_groups <= 65536, "cdr_gemm_grouped: n_groups=%d out of range", n_groups);
+  CDR_REQUIRE(base->a_major == 1 && base->b_major == 1,
+              "cdr_gemm_grouped: both operands must be MN-major (the grouped axis is K)");
+  CDR_REQUIRE(base->epilogue == CDR_EPI_F32_ATOMIC, "cdr_gemm_grouped: CDR_EPI_F32_ATOMIC only");
+  CDR_REQUIRE(base->out != nullptr && (reinterpret_cast<uintptr_t>(base->out) & 15) == 0 && base->ldo % 4 == 0 &&
+                  out_group_stride % 4 == 0 && out_group_stride >= 0,
+              "cdr_gemm_grouped: out, ldo and the group stride must keep rows 16-byte aligned");
+  cdr_gemm_args g = *base;
+  g.epilogue = CDR_EPI_F32_GROUPED;
+  cdr::GemmParams p{};
+  p.out = g.out;
+  p.ldo = g.ldo;
+  p.split_k = n_groups;
+  p.seg_kb = seg_kb;
+  p.seg_out_stride = out_group_stride;
+  return cdr::gemm_run(g, p, static_cast<cudaStream_t>(stream));
 }
 

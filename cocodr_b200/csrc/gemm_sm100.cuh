@@ -23,6 +23,8 @@
 //             one 2-D TMA box {64 rows, 64 k} per 64-row chunk over the global view {rows, K}.
 //             K-step of 16 = +2048 B on the start address.
 #pragma once
+#include <type_traits>
+
 #include "cdr_common.cuh"
 
 namespace cdr {
@@ -66,7 +68,23 @@ struct GemmParams {
   long long a_rows_alloc;  // same for A
   long long b_rows_alloc;  // rows of B that physically exist (>= N; 0 = N): lets TMA boxes read zero padding instead of going out of bounds
   int dbg_flags;  // CDR_GEMM_DBG (environment): bit 0 = skip the epilogue math and stores (timing experiments only)
+  // CDR_EPI_F32_GROUPED: split s reduces k-blocks [seg_kb[s], seg_kb[s+1]) (device array of split_k + 1 ascending
+  // entries) into out + s * seg_out_stride -- the iDRO per-group wgrad as one launch
+  const int* seg_kb;
+  long long seg_out_stride;
 };
+
+// k-blocks of split `ks`: uniform ranges, or the per-group table of the grouped wgrad
+template <int EPI>
+__device__ __forceinline__ void gemm_split_range(const GemmParams& p, int ks, int total_kb, int& kb0, int& kb1) {
+  if constexpr (EPI == CDR_EPI_F32_GROUPED) {
+    kb0 = __ldg(p.seg_kb + ks);
+    kb1 = min(__ldg(p.seg_kb + ks + 1), total_kb);
+  } else {
+    kb0 = ks * p.kb_per_split;
+    kb1 = min(kb0 + p.kb_per_split, total_kb);
+  }
+}
 
 // host-side entry shared by cdr_gemm and the scan (gemm.cu)
 int gemm_run(const cdr_gemm_args& g, GemmParams p, cudaStream_t st);
@@ -425,8 +443,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         const int tile = item - ks * tiles;
         const int m0 = (tile / p.n_tiles) * (GEMM_BM * CG) + static_cast<int>(cta_rank) * GEMM_BM;
         const int n0 = (tile % p.n_tiles) * BN + static_cast<int>(cta_rank) * BNL;
-        const int kb0 = ks * p.kb_per_split;
-        const int kb1 = min(kb0 + p.kb_per_split, total_kb);
+        int kb0, kb1;
+        gemm_split_range<EPI>(p, ks, total_kb, kb0, kb1);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* da = smem_a + stage * S::A_BYTES;
@@ -486,8 +504,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       uint32_t acc_phase = 0;
       for (int item = worker; item < total_items; item += n_workers) {
         const int ks = item / tiles;
-        const int kb0 = ks * p.kb_per_split;
-        const int kb1 = min(kb0 + p.kb_per_split, total_kb);
+        int kb0, kb1;
+        gemm_split_range<EPI>(p, ks, total_kb, kb0, kb1);
+        if constexpr (EPI == CDR_EPI_F32_GROUPED) {
+          if (kb1 <= kb0) continue;  // absent group: no accumulator is produced (the epilogue skips it too)
+        }
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -520,8 +541,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     int acc = 0;
     uint32_t acc_phase = 0;
     const uint32_t empty_remote = (CG == 2) ? mapa_shared(smem_u32(&tmem_empty[0]), 0) : 0u;
+    // the grouped wgrad runs the fp32 accumulate-add epilogue on a per-group output base
+    constexpr bool GROUPED = EPI == CDR_EPI_F32_GROUPED;
+    constexpr int EPIM = GROUPED ? CDR_EPI_F32_ATOMIC : EPI;
+    struct NoCopy {};
+    std::conditional_t<GROUPED, GemmParams, NoCopy> pg;  // private copy (per-item `out`) for the grouped wgrad only
+    if constexpr (GROUPED) pg = p;
+    const GemmParams& pe = [&]() -> const GemmParams& {
+      if constexpr (GROUPED) return pg; else return p;
+    }();
     for (int item = worker; item < total_items; item += n_workers) {
       const int tile = item % tiles;
+      if constexpr (EPI == CDR_EPI_F32_GROUPED) {
+        const int ks = item / tiles;
+        int kb0, kb1;
+        gemm_split_range<EPI>(p, ks, total_kb, kb0, kb1);
+        if (kb1 <= kb0) continue;
+        pg.out = reinterpret_cast<float*>(p.out) + static_cast<long long>(ks) * p.seg_out_stride;
+      }
       const int m0 = (tile / p.n_tiles) * (GEMM_BM * CG) + static_cast<int>(cta_rank) * GEMM_BM;
       const int n0 = (tile % p.n_tiles) * BN;
       // this warp's chunks: columns (half + NH*j) * 32 of TMEM lane quadrant `quad`, handled two at a time
@@ -533,7 +570,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       uint4 aux[CPW][4];
 #pragma unroll
       for (int j = 0; j < CPW; ++j)  // all in flight while the MMAs of this tile finish
-        gemm_epilogue_load_aux<EPI>(p, aux[j], lane, mb, n0 + (half + NH * j) * 32);
+        gemm_epilogue_load_aux<EPIM>(p, aux[j], lane, mb, n0 + (half + NH * j) * 32);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
 #pragma unroll
@@ -574,9 +611,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           if (ok0) gemm_filter_commit(p, r0, fws, lane, mb + lane, n0 + c0 * 32, t0);
           if (ok1) gemm_filter_commit(p, r1, fws + 96, lane, mb + lane, n0 + c1 * 32, t1);
         } else if (n0 + c0 * 32 < p.N && !(p.dbg_flags & 1)) {
-          gemm_epilogue_chunk<EPI>(p, r0, stg, lane, mb, n0 + c0 * 32, aux[b]);
+          gemm_epilogue_chunk<EPIM>(pe, r0, stg, lane, mb, n0 + c0 * 32, aux[b]);
           if constexpr (CPW >= 2) {
-            if (n0 + c1 * 32 < p.N) gemm_epilogue_chunk<EPI>(p, r1, stg, lane, mb, n0 + c1 * 32, aux[b + 1 < CPW ? b + 1 : b]);
+            if (n0 + c1 * 32 < p.N) gemm_epilogue_chunk<EPIM>(pe, r1, stg, lane, mb, n0 + c1 * 32, aux[b + 1 < CPW ? b + 1 : b]);
           }
         }
       }

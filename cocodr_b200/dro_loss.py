@@ -207,7 +207,10 @@ class iDROLoss(DROGreedyLoss):
                                "that ran through cocodr_b200.ops (set iDROLoss.grouped_wgrad = False otherwise)")
         seq_group = g.to(torch.int64).repeat(n_towers)  # towers are concatenated: sequence s -> sample s % B
         order = torch.argsort(seq_group, stable=True)
-        per_group = (gdro_counts_agg.to(torch.int64) * n_towers).tolist()  # sequences per group (one host transfer)
+        if self.grouped_kernel:  # group sizes stay on the device (cdr_gemm_grouped reads its k-ranges there)
+            per_group = torch.bincount(seq_group, minlength=G)[:G]
+        else:
+            per_group = (gdro_counts_agg.to(torch.int64) * n_towers).tolist()  # sequences per group (one host transfer)
         Gp = (G + 127) // 128 * 128
         onehot = {}
         for rec in records:
@@ -215,15 +218,77 @@ class iDROLoss(DROGreedyLoss):
                 self._grouped_layer(rec, mat, offs, seq_group, order, per_group, Gp, onehot)
         return mat
 
+    @staticmethod
+    def _padded_layout(seq_group, order, cnt_seq, r, n_groups):
+        """Row layout for cdr_gemm_grouped when a sequence owns r rows: every group's rows contiguous and padded to
+        whole 64-row k-blocks.  -> (seg_kb int32 [G + 1], src rows, destination rows, static row bound); all on the
+        device, nothing read back."""
+        n_seq = seq_group.numel()
+        dev = seq_group.device
+        rows = cnt_seq * r
+        padded = (rows + 63) // 64 * 64
+        ends = torch.cumsum(padded, 0)
+        seg_kb = (torch.cat([ends.new_zeros(1), ends]) // 64).to(torch.int32).contiguous()
+        first = torch.cumsum(cnt_seq, 0) - cnt_seq       # first sorted sequence of every group
+        gs = seq_group[order]                            # group of the j-th sorted sequence
+        dest0 = (ends - padded)[gs] + (torch.arange(n_seq, device=dev) - first[gs]) * r
+        ar = torch.arange(r, device=dev)
+        dest = (dest0.unsqueeze(1) + ar).reshape(-1)
+        src = (order.unsqueeze(1) * r + ar).reshape(-1)
+        return seg_kb, src, dest, n_seq * r + 64 * n_groups
+
     def _grouped_layer(self, rec, mat, offs, seq_group, order, per_group, Gp, onehot):
-        keys, rps, L, n_seq, S = rec["keys"], rec["rps"], rec["L"], rec["n_seq"], rec["S"]
-        inv = 1.0 / S
-        G = self.n_groups
-        dev = mat.device
-        H = rec["x"].shape[1]
+        n_seq = rec["n_seq"]
         if n_seq != seq_group.numel():
             raise RuntimeError("iDROLoss: grouped gradients need the towers in one encoder pass "
                                f"({n_seq} sequences in the layer, {seq_group.numel()} expected)")
+        if self.grouped_kernel:
+            self._grouped_weights_one_launch(rec, mat, offs, seq_group, order, per_group, onehot)
+        else:
+            self._grouped_weights_segments(rec, mat, offs, order, per_group)
+        self._grouped_vectors(rec, mat, offs, seq_group, Gp, onehot)
+
+    def _grouped_weights_one_launch(self, rec, mat, offs, seq_group, order, cnt_seq, cache):
+        """Weights through cdr_gemm_grouped: one launch per weight, (tile, group) work items, k-ranges on the device."""
+        keys, rps, L, n_seq, S = rec["keys"], rec["rps"], rec["L"], rec["n_seq"], rec["S"]
+        inv = 1.0 / S
+        G = self.n_groups
+        H = rec["x"].shape[1]
+        dim = mat.shape[1]
+
+        def layout(r):
+            if ("layout", r) not in cache:
+                cache[("layout", r)] = self._padded_layout(seq_group, order, cnt_seq, r, G)
+            return cache[("layout", r)]
+
+        def place(t, r):  # rows regrouped (and zero-padded per group when r is not a whole number of k-blocks)
+            seg_kb, src, dest, bound = layout(r)
+            if r % 64 == 0:
+                C = t.shape[1]
+                return t.reshape(n_seq, r * C)[order].reshape(n_seq * r, C)
+            buf = torch.zeros(bound, t.shape[1], dtype=t.dtype, device=t.device)
+            buf.index_copy_(0, dest, t.index_select(0, src))
+            return buf
+
+        def wgrads(k, a, b, r):
+            ent = offs.get(keys[k])
+            if ent is not None:
+                K.gemm_grouped(a, b, mat, M=a.shape[1], N=b.shape[1], seg_kb=layout(r)[0], n_groups=G,
+                               out_group_stride=dim, out_offset=ent[0], alpha=inv)
+
+        dy2, gl, dz, x1, dy1, att = (place(rec[n], rps) for n in ("dy2", "gl", "dz", "x1", "dy1", "att"))
+        dqkv, x = place(rec["dqkv"], L), place(rec["x"], L)
+        wgrads(12, dy2, gl, rps)
+        wgrads(10, dz, x1, rps)
+        wgrads(6, dy1, att, rps)
+        for j, k in enumerate((0, 2, 4)):
+            wgrads(k, dqkv[:, j * H:(j + 1) * H], x, L)
+
+    def _grouped_weights_segments(self, rec, mat, offs, order, per_group):
+        """Weights through cdr_gemm_segments: one wgrad per (weight, present group), enqueued by one C call per weight."""
+        keys, rps, L, n_seq, S = rec["keys"], rec["rps"], rec["L"], rec["n_seq"], rec["S"]
+        inv = 1.0 / S
+        H = rec["x"].shape[1]
 
         def regroup(t, r):  # [n_seq * r, C] rows -> the sequences of every group contiguous
             C = t.shape[1]
@@ -252,7 +317,15 @@ class iDROLoss(DROGreedyLoss):
         for j, k in enumerate((0, 2, 4)):  # query / key / value weights: column blocks of dQKV
             wgrads(k, dqkv[:, j * H:(j + 1) * H], x, L)
 
-        # ---- vectors: per-group column sums = one-hot^T R, through the same GEMM (exact products, fp32 accumulation)
+    def _grouped_vectors(self, rec, mat, offs, seq_group, Gp, onehot):
+        """Bias / LayerNorm gradients: per-group column sums = one-hot^T R through the same GEMM (exact products, fp32
+        accumulation)."""
+        keys, rps, L, n_seq, S = rec["keys"], rec["rps"], rec["L"], rec["n_seq"], rec["S"]
+        inv = 1.0 / S
+        G = self.n_groups
+        dev = mat.device
+        H = rec["x"].shape[1]
+
         def hot(r):
             if r not in onehot:
                 e = torch.zeros(n_seq * r, Gp, dtype=torch.float16, device=dev)
@@ -316,6 +389,9 @@ class iDROLoss(DROGreedyLoss):
     # K11: take the group gradients from one shared partial backward + per-group wgrads when the caller vouches that
     # the per-sample losses do not mix samples (``sample_towers``); False = one partial backward per present group
     grouped_wgrad = os.environ.get("CDR_IDRO_GROUPED", "1") == "1"
+    # weights of the grouped path through ONE cdr_gemm_grouped launch each (device-side group table, no host transfer);
+    # False = one cdr_gemm_segments wgrad per present group
+    grouped_kernel = os.environ.get("CDR_IDRO_GROUPED_KERNEL", "1") == "1"
 
     def forward(self, model, losses, g, sample_towers=0):
         """dro_loss.py:216-254 -> (robust_loss, group mean losses[G] detached, group counts[G]).

@@ -103,6 +103,29 @@ def gemm_segments(a, b, out, *, M, N, row_begin, row_count, out_offset, alpha=1.
     return out
 
 
+def gemm_grouped(a, b, out, *, M, N, seg_kb, n_groups, out_group_stride, out_offset=0, alpha=1.0, ldo=None):
+    """cdr_gemm_grouped: ONE launch; group g adds alpha * a[rows_g]^T @ b[rows_g] to the [M, N] block at
+    out.view(-1)[out_offset + g * out_group_stride:], rows_g = [64 * seg_kb[g], 64 * seg_kb[g + 1]) -- seg_kb is an int32 DEVICE tensor of n_groups + 1 ascending
+    entries, so nothing about the group sizes crosses to the host; rows padding a group to 64 must be zero."""
+    _need_cuda(a, b, out, seg_kb)
+    assert a.dtype == torch.float16 and b.dtype == torch.float16 and out.dtype == torch.float32
+    assert seg_kb.dtype == torch.int32 and seg_kb.numel() == n_groups + 1 and seg_kb.is_contiguous()
+    assert a.shape[0] == b.shape[0]
+    g = _lib.GemmArgs()
+    g.a, g.b, g.out, g.out2 = a.data_ptr(), b.data_ptr(), out.data_ptr() + 4 * out_offset, 0
+    g.bias, g.aux = 0, 0
+    g.M, g.N, g.K = M, N, a.shape[0]
+    g.lda, g.ldb, g.ldo, g.ldaux = a.stride(0), b.stride(0), (ldo if ldo is not None else N), 0
+    g.a_major, g.b_major, g.epilogue, g.split_k = 1, 1, EPI_F32_ATOMIC, 0
+    g.alpha = alpha
+    g.dbg_lbo, g.dbg_sbo = 0, 0
+    g.colsum, g.colsum_scale = 0, 1.0
+    _run("cdr_gemm_grouped", lambda: _lib.load().cdr_gemm_grouped(C.byref(g), C.c_int32(n_groups), _p(seg_kb),
+                                                                  C.c_int64(out_group_stride), stream_ptr()))
+    _count(1)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # helpers: explicit ctypes scalars (no argtypes are registered, so every scalar is wrapped here)
 # ------------------------------------------------------------------------------------------------

@@ -53,7 +53,8 @@ enum {
   CDR_EPI_F32_ATOMIC = 4,    /* out32 += alpha*acc  (red.add, for split-K wgrad)                  */
   CDR_EPI_F32_STORE = 5,     /* out32 = alpha*acc                                                 */
   CDR_EPI_SCAN_FILTER = 6,   /* internal: threshold-filter scores into candidate buffers (docs on M, queries on N) */
-  CDR_EPI_SCAN_FILTER_Q = 7  /* internal: the same with queries on M (<= 128 queries: documents stream as the B operand) */
+  CDR_EPI_SCAN_FILTER_Q = 7, /* internal: the same with queries on M (<= 128 queries: documents stream as the B operand) */
+  CDR_EPI_F32_GROUPED = 8    /* internal (cdr_gemm_grouped): F32_ATOMIC with per-group K ranges and output bases */
 };
 
 typedef struct cdr_gemm_args {
@@ -85,6 +86,13 @@ int cdr_gemm(const cdr_gemm_args* args, void* stream);
  * row_count 0 are skipped. */
 int cdr_gemm_segments(const cdr_gemm_args* base, int32_t n_seg, const int64_t* row_begin, const int64_t* row_count,
                       const int64_t* out_offset, void* stream);
+/* The same reduction as ONE launch, with the segment table in DEVICE memory (no host transfer of the group sizes):
+ * seg_kb[n_groups + 1] are ascending boundaries in units of 64 rows (k-blocks); group g reduces rows
+ * [64 * seg_kb[g], 64 * seg_kb[g + 1]) of A and B (both MN-major, base->K = total rows) and ADDS alpha * A_g^T B_g to
+ * (float*)base->out + g * out_group_stride (elements); groups with an empty range are left untouched.  Rows that pad a
+ * group to a multiple of 64 must be zero.  base->epilogue must be CDR_EPI_F32_ATOMIC. */
+int cdr_gemm_grouped(const cdr_gemm_args* base, int32_t n_groups, const int32_t* seg_kb, int64_t out_group_stride,
+                     void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Memory-bound encoder kernels (K1, LN halves of K4/K6, bias gradients, casts).

@@ -96,6 +96,29 @@ def test_row_segments():
         k.gemm_segments(a_cols, b, out, M=M, N=N, row_begin=[0], row_count=[8], out_offset=[0], epilogue=k.EPI_STORE_F16)
 
 
+@pytest.mark.parametrize("M,N", [(128, 192), (256, 384), (768, 128)])
+def test_grouped_k_ranges(M, N):
+    """cdr_gemm_grouped: one launch, (tile, group) work items, per-group k-block ranges read from device memory."""
+    from cocodr_b200 import kernels as k
+    kblocks = [2, 0, 1, 5, 0, 3]  # 64-row blocks per group (two empty groups)
+    G, rows = len(kblocks), 64 * sum(kblocks) + 64  # one spare block behind the last group: must not be read
+    a, b = _rand((rows, M), 21), _rand((rows, N), 22)
+    seg = torch.tensor([sum(kblocks[:i]) for i in range(G + 1)], dtype=torch.int32, device="cuda")
+    stride, off = M * N + 64, 32
+    out = torch.ones(G * stride + off, dtype=torch.float32, device="cuda")
+    k.gemm_grouped(a, b, out, M=M, N=N, seg_kb=seg, n_groups=G, out_group_stride=stride, out_offset=off, alpha=0.25)
+    r0 = 0
+    for g, nb in enumerate(kblocks):
+        blk = out[off + g * stride: off + g * stride + M * N].view(M, N)
+        ref = 1.0 + 0.25 * (a[r0:r0 + 64 * nb].float().t() @ b[r0:r0 + 64 * nb].float())
+        _check(blk, ref, tol=2e-3, what=f"group {g} ({nb} k-blocks)")
+        if nb == 0:
+            assert torch.equal(blk, torch.ones_like(blk))
+        tail = out[off + g * stride + M * N: off + (g + 1) * stride]
+        assert torch.equal(tail, torch.ones_like(tail))  # nothing written between the groups' blocks
+        r0 += 64 * nb
+
+
 def test_errors_are_loud():
     from cocodr_b200 import kernels as k
     a, b = _rand((128, 60), 1), _rand((128, 60), 2)

@@ -38,6 +38,21 @@ def _fake_gemm_segments(a, b, out, *, M, N, row_begin, row_count, out_offset, al
     return out
 
 
+def _fake_gemm_grouped(a, b, out, *, M, N, seg_kb, n_groups, out_group_stride, out_offset=0, alpha=1.0, **kw):  # noqa: N803
+    """cdr_gemm_grouped restated: group g adds a[rows_g]^T b[rows_g], rows_g = 64-row k-blocks [seg_kb[g], seg_kb[g+1])."""
+    assert seg_kb.dtype == torch.int32 and seg_kb.numel() == n_groups + 1
+    assert a.shape[1] == M and b.shape[1] == N and a.shape[0] == b.shape[0] and a.stride(1) == 1 and b.stride(1) == 1
+    kb = seg_kb.tolist()
+    assert kb[0] == 0 and all(x <= y for x, y in zip(kb, kb[1:])) and kb[-1] * 64 <= a.shape[0]
+    flat = out.view(-1)
+    for g in range(n_groups):
+        r0, r1 = kb[g] * 64, kb[g + 1] * 64
+        if r1 > r0:
+            o = out_offset + g * out_group_stride
+            flat[o:o + M * N].view(M, N).add_(alpha * (a[r0:r1].float().t() @ b[r0:r1].float()))
+    return out
+
+
 def _layer(x, p, n_seq, L, cls_only):
     """A post-LN layer restricted to what the reducer sees: y = LN2(x1 + W2 gelu(W1 x1 + b1) + b2),
     x1 = LN1(x + Wo att + bo), att = a fixed per-sequence mixing of V-like projections, qkv = x Wqkv^T + b."""
@@ -58,12 +73,16 @@ def _layer(x, p, n_seq, L, cls_only):
     return dict(qkv=qkv, att=att, y1=y1, x1=x1, z=z, gl=gl, y2=y2, y=y)
 
 
-@pytest.mark.parametrize("rps", [4, 1])
-def test_grouped_reducer_matches_per_group_autograd(monkeypatch, rps):
+@pytest.mark.parametrize("cls_only,L,one_launch", [(False, 4, False), (True, 4, False), (False, 4, True),
+                                                  (True, 4, True), (False, 64, True), (True, 64, True)])
+def test_grouped_reducer_matches_per_group_autograd(monkeypatch, cls_only, L, one_launch):  # noqa: N803
     monkeypatch.setattr(K, "gemm", _fake_gemm)
     monkeypatch.setattr(K, "gemm_segments", _fake_gemm_segments)
+    monkeypatch.setattr(K, "gemm_grouped", _fake_gemm_grouped)
+    monkeypatch.setattr(dro_loss.iDROLoss, "grouped_kernel", one_launch)
+    rps = 1 if cls_only else L
     torch.manual_seed(3 + rps)
-    B, towers, G, H, I, L = 5, 3, 4, 8, 16, 4  # noqa: E741
+    B, towers, G, H, I = 5, 3, 4, 8, 16  # noqa: E741
     n_seq = B * towers
     rows = n_seq * L
     S = 64.0

@@ -19,8 +19,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--out", default="gpurun_out/idro_grouped.json")
     ap.add_argument("--skip-pytest", action="store_true")
+    ap.add_argument("--kernel-check", action="store_true")
     args = ap.parse_args()
     os.environ["CDR_IDRO_GROUPED"] = "1"  # read when cocodr_b200.dro_loss is imported
+    if args.kernel_check:
+        os.environ["CDR_IDRO_GROUPED_KERNEL"] = "1"
+    os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
     from transformers import BertConfig
 
     from cocodr_b200 import dro_loss, models, ops, optim
@@ -29,7 +33,7 @@ def main():
         import pytest
         root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
         rc = pytest.main([os.path.join(root, "tests", "test_model_gpu.py"), os.path.join(root, "tests", "test_gemm_gpu.py"),
-                          "-q", "-x", "-k", "idro or segments", "-p", "no:cacheprovider"])
+                          "-q", "-k", "idro or segments or grouped_k", "-p", "no:cacheprovider"])
         print(json.dumps({"idro_trajectory_and_segments_pytest_rc": int(rc)}), flush=True)
     B, L, G = 64, 128, 50
     dev = torch.device("cuda:0")
@@ -57,6 +61,35 @@ def main():
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / n, out
 
+    if args.kernel_check:  # cdr_gemm_grouped (one launch per weight) against cdr_gemm_segments (one per present group)
+        loss, _, _ = model.forward_model(*inp)
+        sums, counts = ops.group_stats(loss, gid, G)
+        means = sums / (counts + (counts == 0).float())
+        params = crit._params(model.bert)
+        out = {}
+        for flag in (False, True):
+            type(crit).grouped_kernel = flag
+            ms, m = ev_time(lambda: crit._get_grad_grouped(params, means, counts, gid, 3), 3)
+            out[flag] = (ms, m)
+        d = (out[True][1] - out[False][1]).abs().max().item()
+        res = {"ms_segments": round(out[False][0], 2), "ms_one_launch": round(out[True][0], 2), "max_abs_diff": d,
+               "max_abs": out[False][1].abs().max().item()}
+        print(json.dumps(res), flush=True)
+        del out
+        opt = optim.AdamW(list(model.bert.parameters()), lr=5e-6, eps=1e-8, weight_decay=0.01,
+                          semantics="torch").attach_shadows(model)
+
+        def kstep():
+            o = model(*inp, group_ids=gid)[0]
+            opt.zero_grad(set_to_none=True)
+            o.backward()
+            opt.step()
+
+        res["ms_step_one_launch"] = round(ev_time(kstep, args.steps)[0], 2)
+        print(json.dumps(res), flush=True)
+        with open(args.out.replace(".json", "_kernel.json"), "w") as f:
+            json.dump(res, f, indent=1)
+        return
     loss, _, _ = model.forward_model(*inp)
     sums, counts = ops.group_stats(loss, gid, G)
     means = sums / (counts + (counts == 0).float())
