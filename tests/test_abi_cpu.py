@@ -59,6 +59,24 @@ def test_bad_arguments_fail_loudly_without_a_gpu(lib):
     assert lib.cdr_attn_fwd(C.byref(a), None) == -1 and b"seq_len" in lib.cdr_last_error()
     with pytest.raises(RuntimeError):
         _lib.check(rc, "cdr_gemm")
+    # the row-segmented / grouped wgrad entry points validate before they touch the device
+    g = _lib.GemmArgs()
+    g.a, g.b, g.out, g.M, g.N, g.K, g.lda, g.ldb, g.ldo = 16, 16, 16, 128, 128, 64, 128, 128, 128
+    g.a_major, g.b_major, g.epilogue = 1, 0, _lib.EPI_F32_ATOMIC
+    one = (C.c_int64 * 1)(0)
+    assert lib.cdr_gemm_segments(C.byref(g), C.c_int32(1), one, one, one, None) == -1
+    assert b"MN-major" in lib.cdr_last_error()
+    assert lib.cdr_gemm_grouped(C.byref(g), C.c_int32(4), C.c_void_p(16), C.c_int64(128 * 128), None) == -1
+    assert b"MN-major" in lib.cdr_last_error()
+    g.b_major, g.epilogue = 1, _lib.EPI_STORE_F16
+    assert lib.cdr_gemm_segments(C.byref(g), C.c_int32(1), one, one, one, None) == -1 and b"fp32" in lib.cdr_last_error()
+    assert lib.cdr_gemm_grouped(C.byref(g), C.c_int32(4), C.c_void_p(16), C.c_int64(128 * 128), None) == -1
+    g.epilogue = 8  # CDR_EPI_F32_GROUPED is internal to cdr_gemm_grouped
+    assert lib.cdr_gemm(C.byref(g), None) == -1 and b"internal" in lib.cdr_last_error()
+    g.epilogue = _lib.EPI_F32_ATOMIC
+    assert lib.cdr_gemm_grouped(C.byref(g), C.c_int32(0), C.c_void_p(16), C.c_int64(128 * 128), None) == -1
+    assert lib.cdr_gemm_grouped(C.byref(g), C.c_int32(4), C.c_void_p(16), C.c_int64(130), None) == -1  # unaligned stride
+    assert lib.cdr_gemm_segments(C.byref(g), C.c_int32(0), None, None, None, None) == 0  # nothing to do
 
 
 def test_ctypes_structs_match_the_c_header(tmp_path):
