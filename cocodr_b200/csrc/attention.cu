@@ -1,7 +1,8 @@
 // Fused multi-head attention (K3) for BERT, head_dim 64, seq_len <= 512, forward and backward, on the
 // sm_100a tensor cores (tcgen05.mma, accumulators in TMEM, operands staged by TMA).
 //
-// One CTA per (sequence, head).  Q/K/V come straight out of the packed QKV projection [T, 3H]
+// A work item is one (sequence, head) (seq_len <= 128: persistent CTAs walk the items; longer sequences: one CTA per
+// (sequence, head, 128-row tile)).  Q/K/V come straight out of the packed QKV projection [T, 3H]
 // (columns [0,H) = Q, [H,2H) = K, [2H,3H) = V; head h owns 64 contiguous columns), so a single 2-D
 // TMA box {64, 128} per operand lands a 128B-swizzled [128 rows][64 halfs] tile that is at the same
 // time
@@ -301,17 +302,6 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttParams p, 
 }
 
 // ----------------------------------------------------------------------------------------- backward
-// Persistent, warp-specialised: one CTA per SM walks (sequence, head) items.
-//   warp 0      : TMA producer -- Q K V dO of item i+1 land in the other smem stage while item i computes
-//   warp 1      : tcgen05.mma issuer (one thread) + TMEM owner
-//   warps 2..9  : 256 compute threads; thread = (TMEM lane r = query/key row, half h of the 128 key columns)
-// Per item:  S = Q K^T, dP = dO V^T  ->  P = exp2(S - lse), delta_r = sum_j P dP (exact for a whole row in
-// one tile), dS = P (dP - delta) scale  ->  dV = P^T dO, dK = dS^T Q, dQ = dS K  ->  fp16 dQKV rows + the
-// QKV bias gradient (column sums, fp32, straight from the accumulators).
-// The S/dP MMAs of item i+1 are queued behind dV/dK/dQ of item i, so the tensor pipe, the TMA and the
-// softmax threads overlap; nothing but the mbarriers below synchronises them.
-// TMEM columns: S [0,128) dP [128,256) dV [256,320) dK [320,384) dQ [384,448).
-// smem: 2 stages x (Q K V dO) = 128 KB | P 32 KB | dS 32 KB | key bias x2 | delta halves | barriers.
 constexpr int ATT_BWD_SM_WARPS = 16;   // softmax warps: 4 per TMEM lane quadrant, 32 key columns per thread
 constexpr int ATT_BWD_THREADS = 64 + 32 * ATT_BWD_SM_WARPS + 128;  // producer, MMA issuer, softmax, 4 epilogue warps
 constexpr int ATT_BWD_SMEM = 12 * ATT_TILE_BYTES + 2048 + 2048 + 256 + 4 * 2048 + 1024;  // tiles | per-warp bias | delta quarters | barriers | epilogue transposition tiles

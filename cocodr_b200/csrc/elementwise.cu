@@ -1,6 +1,9 @@
 // Memory-bound kernels of the encoder: embedding gather + LayerNorm (K1), LayerNorm fwd/bwd over
 // fp16 activations (the LN halves of K4/K6), column sums for bias gradients, fp32->fp16 casts.
-// One warp per row, 16-byte vector accesses, fp32 statistics.  hidden % 8 == 0, hidden <= 1024 * 2.
+// fp32 statistics, 16-byte vector accesses, hidden % 8 == 0, hidden <= 2048.  LayerNorm over hidden <= 1024 runs as
+// staged kernels (ln_fwd_staged_kernel / ln_bwd_staged_kernel: 8-row tiles brought in by cp.async.bulk into a
+// 3-stage mbarrier ring, a warp per row for the statistics, a thread per 8 columns for the column sums); wider rows
+// and the fp32 [CLS]-gradient variant keep the one-warp-per-row kernels.
 #include "cdr_common.cuh"
 #include "peer.cuh"
 

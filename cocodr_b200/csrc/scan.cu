@@ -3,10 +3,12 @@
 //   1. thresholds  : score a strided sample of S documents against every query (tcgen05 GEMM, fp32 out)
 //                    and take the m-th largest sample score per query as the admission threshold
 //                    (m chosen so that ~3k documents of the full corpus are expected above it)
-//   2. filter pass : ONE pass over the corpus -- tcgen05 GEMM, documents on M, queries on N -- whose
+//   2. filter pass : ONE pass over the corpus -- tcgen05 GEMM, documents on M and queries on N (or, for <= 128
+//                    queries, queries on M with the documents streaming as the B operand) -- whose
 //                    epilogue admits (score >= threshold[q]) into per-query candidate buffers as packed
 //                    order-preserving (score, ~doc) 64-bit keys.  Scores never touch HBM.
-//   3. select      : per query, bitonic sort of the candidates in shared memory, emit the first k.
+//   3. select      : per query, bitonic sort of the candidates (register-resident inner stages, shared memory
+//                    between threads), emit the first k.
 //                    If >= k candidates were admitted (and the buffer did not overflow) these are
 //                    exactly the global top-k in (score desc, doc asc) order; otherwise status[0]++.
 //
