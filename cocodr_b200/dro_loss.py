@@ -182,8 +182,10 @@ class iDROLoss(DROGreedyLoss):
         to sample s % B).  Then in the backward of sum_g mean_g every row of an activation gradient carries
         d mean_{g(row)} only, and the gradient of mean_g w.r.t. a weight is dY[rows of g]^T X[rows of g]: the layer
         backwards hand over their wgrad operands (ops.GroupCapture), rows are regrouped so that each group is one
-        contiguous K range, and one wgrad GEMM per (weight, present group) stores straight into the group's row of
-        the matrix.  Bias / LayerNorm gradients are per-group column sums: one GEMM with a one-hot [rows, G] operand.
+        contiguous K range, and the wgrad of every weight adds each group's product into the group's row of the matrix
+        -- as one launch over (tile, group) work items with the k-ranges in device memory (cdr_gemm_grouped,
+        ``grouped_kernel``) or as one launch per present group (cdr_gemm_segments).  Bias / LayerNorm gradients are
+        per-group column sums: one GEMM with a one-hot [rows, G] operand.
         """
         cap = ops.GroupCapture()
         ops.GROUP_CAPTURE = cap
