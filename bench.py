@@ -402,6 +402,7 @@ def run_ours(args):
                            "parallelism": f"dp{world}" + (((" + NCCL all-gather of passage CLS + " if args.nccl_gather else " + passage CLS pushed into every rank's HBM by the last LayerNorm kernel (NVLink peer stores) + ") + ("DDP all-reduce" if args.ddp else "per-layer NCCL all-reduce of flat gradient buffers overlapped with backward")) if world > 1 else ""),
                            "l2": "per-step working set (~5 GB of activations) exceeds the 126 MB L2; 4 input batches cycled",
                            "optimizer": ("torch fused AdamW" if args.torch_adamw else "cdr_adam_multi (own fused multi-tensor AdamW + fp16 shadow refresh)") + " inside the timed step",
+                           "dropout": "p = 0 (the parity configuration; fused dropout is not implemented, DESIGN.md section 7)",
                            "cuda_graph": graphed is not None},
                 "clocks": clocks.summary(),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
