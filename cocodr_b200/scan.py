@@ -114,11 +114,13 @@ def search_sharded(Q, P_local, k, doc_base, group=None):
         pad = k - D.shape[1]
         D = torch.cat([D, D.new_full((D.shape[0], pad), float("-inf"))], 1)
         I = torch.cat([I, I.new_full((I.shape[0], pad), -1)], 1)
-    allD = torch.empty(W, *D.shape, dtype=D.dtype, device=D.device)
-    allI = torch.empty(W, *I.shape, dtype=I.dtype, device=I.device)
+    n_q = D.shape[0]
+    allD = torch.empty(W * n_q, k, dtype=D.dtype, device=D.device)  # rank-major blocks of [n_q, k]
+    allI = torch.empty(W * n_q, k, dtype=I.dtype, device=I.device)
     dist.all_gather_into_tensor(allD, D.contiguous(), group=group)
     dist.all_gather_into_tensor(allI, I.contiguous(), group=group)
-    return merge_topk(allD.permute(1, 0, 2).reshape(D.shape[0], -1), allI.permute(1, 0, 2).reshape(I.shape[0], -1), k)
+    return merge_topk(allD.view(W, n_q, k).permute(1, 0, 2).reshape(n_q, -1),
+                      allI.view(W, n_q, k).permute(1, 0, 2).reshape(n_q, -1), k)
 
 
 class IndexFlatIP:

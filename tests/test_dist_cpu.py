@@ -5,6 +5,9 @@
   * iDROLoss._gram: reduce-scatter of column shards + local Gram + all-reduce == Gram of the all-reduced
     [G, P] matrix (what dro_loss.py:232-237 computes); the CUDA Gram kernel is replaced by a torch stand-in
     here because only the sharding / collective logic is under test
+  * scan.search_sharded: documents split unevenly over the ranks (one shard smaller than k), per-rank top-k with
+    global ids, all-gather of the candidate lists, k-way merge == the single-process oracle scan of the whole corpus,
+    ids bit-exact in (score desc, id asc) order; the per-shard scan and the merge kernel are replaced by the oracle
 """
 import os
 import types
@@ -65,7 +68,38 @@ def _gram_worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("worker,port", [(_gather_worker, 29641), (_gram_worker, 29643)])
+def _scan_worker(rank, world, port, ret):
+    _init(rank, world, port)
+    import numpy as np
+    from cocodr_b200 import scan
+    from oracle import scan_ref
+
+    def search_cpu(Q, P, k, doc_base=0, force_exhaustive=False):  # the per-shard scan: oracle, global ids
+        k_eff = min(k, P.shape[0])
+        D, I = scan_ref.search(Q, P, k_eff)
+        return torch.from_numpy(np.asarray(D, dtype=np.float32)), torch.from_numpy(np.asarray(I, dtype=np.int64)) + doc_base
+
+    def merge_cpu(D, I, k):  # (score desc, id asc), ids < 0 = empty slots
+        outD, outI = torch.empty(D.shape[0], k), torch.empty(D.shape[0], k, dtype=torch.int64)
+        for r in range(D.shape[0]):
+            live = [(-float(d), int(i)) for d, i in zip(D[r].tolist(), I[r].tolist()) if i >= 0]
+            live.sort()
+            outD[r] = torch.tensor([-d for d, _ in live[:k]])
+            outI[r] = torch.tensor([i for _, i in live[:k]])
+        return outD, outI
+
+    scan.search, scan.merge_topk = search_cpu, merge_cpu
+    k, n_docs = 40, 1000
+    Q, P = scan_ref.synth_corpus(n_docs, 7, 64, seed=11, kind="exact")  # exact arithmetic, many ties
+    cut = n_docs - 25  # rank 1 holds fewer documents than k: its list is padded with empty slots
+    lo, hi = (0, cut) if rank == 0 else (cut, n_docs)
+    D, I = scan.search_sharded(Q, P[lo:hi], k, doc_base=lo)
+    Dr, Ir = scan_ref.search(Q, P, k)
+    ret[rank] = bool((I.numpy() == np.asarray(Ir)).all() and (D.numpy() == np.asarray(Dr, dtype=np.float32)).all())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("worker,port", [(_gather_worker, 29641), (_gram_worker, 29643), (_scan_worker, 29645)])
 def test_world2_gloo(worker, port):
     world = 2
     with mp.Manager() as mgr:
