@@ -5,6 +5,9 @@
   * iDROLoss._gram: reduce-scatter of column shards + local Gram + all-reduce == Gram of the all-reduced
     [G, P] matrix (what dro_loss.py:232-237 computes); the CUDA Gram kernel is replaced by a torch stand-in
     here because only the sharding / collective logic is under test
+  * CoCondenserForPretraining._gather_tensor / gather_tensors (COCO/modeling.py:182-190): the own slot keeps its
+    autograd edge, remote slots carry none; with the reference's loss x world scaling the local-row gradients, once
+    DDP's mean over ranks is applied, equal the single-process gradient of the full 2BW-span batch
   * scan.search_sharded: documents split unevenly over the ranks (one shard smaller than k), per-rank top-k with
     global ids, all-gather of the candidate lists, k-way merge == the single-process oracle scan of the whole corpus,
     ids bit-exact in (score desc, id asc) order; the per-shard scan and the merge kernel are replaced by the oracle
@@ -68,6 +71,29 @@ def _gram_worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
+def _coco_worker(rank, world, port, ret):
+    _init(rank, world, port)
+    from cocodr_b200 import modeling
+    from oracle import heads_ref
+    torch.manual_seed(0)
+    n, H = 6, 16  # 3 documents = 6 spans per rank
+    E = torch.randn(world * n, H)
+    e = E[rank * n:(rank + 1) * n].clone().requires_grad_(True)
+    me = types.SimpleNamespace(train_args=types.SimpleNamespace(local_rank=rank))
+    me._gather_tensor = lambda t: modeling.CoCondenserForPretraining._gather_tensor(me, t)
+    all_e = modeling.CoCondenserForPretraining.gather_tensors(me, e)[0]
+    ok = torch.equal(all_e.detach(), E)
+    loss = heads_ref.coco_contrastive(all_e, world_size=world).mean()  # every rank scores all rows, x world
+    loss.backward()
+    Ef = E.clone().requires_grad_(True)
+    ref = heads_ref.coco_contrastive(Ef, world_size=1).mean()
+    ref.backward()
+    ok = ok and torch.allclose(e.grad / world, Ef.grad[rank * n:(rank + 1) * n], atol=1e-6)  # DDP's mean over ranks
+    ok = ok and abs(loss.item() / world - ref.item()) < 1e-6
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
 def _scan_worker(rank, world, port, ret):
     _init(rank, world, port)
     import numpy as np
@@ -99,7 +125,8 @@ def _scan_worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("worker,port", [(_gather_worker, 29641), (_gram_worker, 29643), (_scan_worker, 29645)])
+@pytest.mark.parametrize("worker,port", [(_gather_worker, 29641), (_gram_worker, 29643), (_scan_worker, 29645),
+                                         (_coco_worker, 29647)])
 def test_world2_gloo(worker, port):
     world = 2
     with mp.Manager() as mgr:
