@@ -8,6 +8,9 @@
   * CoCondenserForPretraining._gather_tensor / gather_tensors (COCO/modeling.py:182-190): the own slot keeps its
     autograd edge, remote slots carry none; with the reference's loss x world scaling the local-row gradients, once
     DDP's mean over ranks is applied, equal the single-process gradient of the full 2BW-span batch
+  * DROGreedyLoss.forward (dro_loss.py:49-120): the group statistics are exchanged as one all-reduce of per-group
+    sums / counts instead of the reference's two all_gathers of per-sample values (:64-65); h_fun, the EMA losses and
+    the EMA counts after two steps equal the oracle fed with the gathered batch
   * scan.search_sharded: documents split unevenly over the ranks (one shard smaller than k), per-rank top-k with
     global ids, all-gather of the candidate lists, k-way merge == the single-process oracle scan of the whole corpus,
     ids bit-exact in (score desc, id asc) order; the per-shard scan and the merge kernel are replaced by the oracle
@@ -94,6 +97,31 @@ def _coco_worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
+def _greedy_worker(rank, world, port, ret):
+    _init(rank, world, port)
+    from cocodr_b200 import dro_loss, ops
+    from oracle import heads_ref
+    ops.group_stats = lambda losses, g, n: heads_ref.group_stats(losses, g, n)[:2]  # stand-in for the CUDA kernel
+    G, B = 6, 8
+    crit = dro_loss.DROGreedyLoss(types.SimpleNamespace(model_size="base", local_rank=rank), G, 0.25, 0.01, 0.1, True)
+    crit.train()
+    h, sl, cc = torch.ones(G), torch.zeros(G), torch.ones(G)
+    ok = True
+    for step in range(2):
+        gen = torch.Generator().manual_seed(100 + step)
+        losses_all = torch.rand(world * B, generator=gen) * 3
+        g_all = torch.randint(0, G - 1, (world * B,), generator=gen)  # the last group never appears
+        mine = slice(rank * B, (rank + 1) * B)
+        robust, gl, gc = crit(losses_all[mine].clone().requires_grad_(True), g_all[mine])
+        r_ref, gl_ref, gc_ref, h, sl, cc = heads_ref.dro_greedy_forward(losses_all[mine], g_all[mine], h, sl, cc, G, 0.25,
+                                                                        0.01, 0.1, True, gathered=(g_all, losses_all))
+        ok = ok and torch.allclose(robust, r_ref, atol=1e-6) and torch.allclose(gl, gl_ref, atol=1e-6)
+        ok = ok and torch.equal(gc, gc_ref) and torch.allclose(crit.h_fun, h, atol=1e-6)
+        ok = ok and torch.allclose(crit.sum_losses, sl, atol=1e-6) and torch.allclose(crit.count_cat, cc, atol=1e-6)
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
 def _scan_worker(rank, world, port, ret):
     _init(rank, world, port)
     import numpy as np
@@ -126,7 +154,7 @@ def _scan_worker(rank, world, port, ret):
 
 
 @pytest.mark.parametrize("worker,port", [(_gather_worker, 29641), (_gram_worker, 29643), (_scan_worker, 29645),
-                                         (_coco_worker, 29647)])
+                                         (_coco_worker, 29647), (_greedy_worker, 29649)])
 def test_world2_gloo(worker, port):
     world = 2
     with mp.Manager() as mgr:
