@@ -11,6 +11,8 @@
   * DROGreedyLoss.forward (dro_loss.py:49-120): the group statistics are exchanged as one all-reduce of per-group
     sums / counts instead of the reference's two all_gathers of per-sample values (:64-65); h_fun, the EMA losses and
     the EMA counts after two steps equal the oracle fed with the gathered batch
+  * iDROLoss.forward end to end (dro_loss.py:216-254) on a small torch model: local group means, rank-summed group
+    gradients through the sharded Gram, h_fun after two steps == the oracle that all-reduces the [G, P] matrix
   * scan.search_sharded: documents split unevenly over the ranks (one shard smaller than k), per-rank top-k with
     global ids, all-gather of the candidate lists, k-way merge == the single-process oracle scan of the whole corpus,
     ids bit-exact in (score desc, id asc) order; the per-shard scan and the merge kernel are replaced by the oracle
@@ -122,6 +124,52 @@ def _greedy_worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
+def _idro_worker(rank, world, port, ret):
+    _init(rank, world, port)
+    from cocodr_b200 import dro_loss, kernels, ops
+    from oracle import heads_ref
+
+    def gram_cpu(x, gram):
+        gram += x @ x.t()
+    kernels.gram_f32 = gram_cpu
+    ops.group_stats = lambda losses, g, n: heads_ref.group_stats(losses, g, n)[:2]
+
+    class Net(torch.nn.Module):  # parameter names layer.0 .. layer.11: iDRO selects layer.9 / .10 / .11
+        def __init__(self):
+            super().__init__()
+            self.layer = torch.nn.ModuleList(torch.nn.Linear(8, 8, bias=(i % 2 == 0)) for i in range(12))
+
+        def forward(self, x):
+            for lin in self.layer:
+                x = torch.tanh(lin(x))
+            return x.pow(2).sum(1)
+
+    torch.manual_seed(0)
+    net = Net()
+    G, B = 5, 6
+    crit = dro_loss.iDROLoss(types.SimpleNamespace(model_size="base", local_rank=rank), G, 0.25, 0.01, 0.1, 0.05)
+    crit.train()
+    h = torch.ones(G)
+    names = heads_ref.idro_param_names([n for n, _ in net.named_parameters()])
+    params = [dict(net.named_parameters())[n] for n in names]
+    ok = len(params) == 4  # layer.9 weight, layer.10 weight + bias, layer.11 weight
+
+    def summed(m):
+        dist.all_reduce(m)
+        return m
+
+    for step in range(2):
+        gen = torch.Generator().manual_seed(10 * step + rank)
+        x = torch.randn(B, 8, generator=gen)
+        g = torch.randint(0, G - 1, (B,), generator=gen)
+        robust, means, counts = crit(net, net(x), g)
+        r_ref, m_ref, c_ref, h = heads_ref.idro_forward(net(x), g, params, h, G, 0.25, 0.1, 0.05, 0.01, all_reduce=summed)
+        ok = ok and torch.allclose(robust, r_ref, atol=1e-6) and torch.allclose(means, m_ref, atol=1e-6)
+        ok = ok and torch.equal(counts, c_ref) and torch.allclose(crit.h_fun, h, rtol=1e-5, atol=1e-7)
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
 def _scan_worker(rank, world, port, ret):
     _init(rank, world, port)
     import numpy as np
@@ -154,7 +202,8 @@ def _scan_worker(rank, world, port, ret):
 
 
 @pytest.mark.parametrize("worker,port", [(_gather_worker, 29641), (_gram_worker, 29643), (_scan_worker, 29645),
-                                         (_coco_worker, 29647), (_greedy_worker, 29649)])
+                                         (_coco_worker, 29647), (_greedy_worker, 29649),
+                                         (_idro_worker, 29651)])
 def test_world2_gloo(worker, port):
     world = 2
     with mp.Manager() as mgr:
