@@ -210,7 +210,7 @@ class iDROLoss(DROGreedyLoss):
         seq_group = g.to(torch.int64).repeat(n_towers)  # towers are concatenated: sequence s -> sample s % B
         order = torch.argsort(seq_group, stable=True)
         if self.grouped_kernel:  # group sizes stay on the device (cdr_gemm_grouped reads its k-ranges there)
-            per_group = torch.bincount(seq_group, minlength=G)[:G]
+            per_group = torch.zeros(G, dtype=torch.int64, device=dev).scatter_add_(0, seq_group, torch.ones_like(seq_group))
         else:
             per_group = (gdro_counts_agg.to(torch.int64) * n_towers).tolist()  # sequences per group (one host transfer)
         Gp = (G + 127) // 128 * 128
