@@ -111,11 +111,11 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU port
-def cpu_port_step_fn(n_pairs, threads=None):
+def cpu_port_step_fn(n_pairs, threads=None, dropout=0.1):
     """One contrastive step of the CPU oracle port on ``n_pairs`` pairs; returns a callable step()."""
     import torch
 
-    from oracle import bert_ref, heads_ref
+    from oracle import bert_ref, dropout_ref, heads_ref
     # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank)
     torch.set_num_threads(threads or os.cpu_count() or 1)
     cfg = bert_ref.make_config()
@@ -124,8 +124,10 @@ def cpu_port_step_fn(n_pairs, threads=None):
     q, mq = bert_ref.synth_batch(n_pairs, SEQ_LEN, cfg["vocab"], 1234, full=True)
     p, mp = bert_ref.synth_batch(n_pairs, SEQ_LEN, cfg["vocab"], 1235, full=True)
 
+    drop = dropout_ref.TorchDropSpec(dropout, dropout) if dropout > 0 else None  # the reference's nn.Dropout work
+
     def step():
-        e = bert_ref.cls_embedding(st, torch.cat([q, p]), torch.cat([mq, mp]), cfg)
+        e = bert_ref.cls_embedding(st, torch.cat([q, p]), torch.cat([mq, mp]), cfg, drop=drop)
         loss = heads_ref.qp_infonce(e[:n_pairs], e[n_pairs:]).mean()
         opt.zero_grad(set_to_none=True)
         loss.backward()
@@ -135,8 +137,8 @@ def cpu_port_step_fn(n_pairs, threads=None):
     return step, torch.get_num_threads()
 
 
-def time_cpu_port(n_pairs, steps, warmup):
-    step, threads = cpu_port_step_fn(n_pairs)
+def time_cpu_port(n_pairs, steps, warmup, dropout=0.1):
+    step, threads = cpu_port_step_fn(n_pairs, dropout=dropout)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
@@ -152,11 +154,12 @@ def run_reference(args):
         return
     n_pairs = 8
     steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
-    v, dt, threads = time_cpu_port(n_pairs, steps, warmup)
+    v, dt, threads = time_cpu_port(n_pairs, steps, warmup, args.dropout)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": f"{n_pairs} pairs per step on the host CPU"},
+            "config": {"workload": WORKLOAD, "sample": f"{n_pairs} pairs per step on the host CPU",
+                       "dropout": f"p={args.dropout} (torch CPU Bernoulli masks at HF's four nn.Dropout sites)"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"{steps} steps of {n_pairs} q+p pairs (BERT-base, L=128, fp32, AdamW)"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -181,7 +184,7 @@ def run_ours(args):
     _lib.check(_lib.load().cdr_device_check(), "cdr_device_check")
 
     torch.manual_seed(0)
-    cfg = BertConfig(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, num_labels=2)
+    cfg = BertConfig(hidden_dropout_prob=args.dropout, attention_probs_dropout_prob=args.dropout, num_labels=2)
     model = models.BertDot_InBatch_NLL_LN(cfg).to(dev).train()
     net = model
     sync = None
@@ -390,7 +393,7 @@ def run_ours(args):
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        v, dt, threads = time_cpu_port(8, 3, 1)
+        v, dt, threads = time_cpu_port(8, 3, 1, args.dropout)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                         "sample": "3 steps of 8 q+p pairs (BERT-base, L=128, fp32, AdamW), oracle port on host CPU"}
 
@@ -402,7 +405,9 @@ def run_ours(args):
                            "parallelism": f"dp{world}" + (((" + NCCL all-gather of passage CLS + " if args.nccl_gather else " + passage CLS pushed into every rank's HBM by the last LayerNorm kernel (NVLink peer stores) + ") + ("DDP all-reduce" if args.ddp else "per-layer NCCL all-reduce of flat gradient buffers overlapped with backward")) if world > 1 else ""),
                            "l2": "per-step working set (~5 GB of activations) exceeds the 126 MB L2; 4 input batches cycled",
                            "optimizer": ("torch fused AdamW" if args.torch_adamw else "cdr_adam_multi (own fused multi-tensor AdamW + fp16 shadow refresh)") + " inside the timed step",
-                           "dropout": "p = 0 (the parity configuration; fused dropout is not implemented, DESIGN.md section 7)",
+                           "dropout": (f"p={args.dropout} fused (HF defaults: embeddings, attention probabilities, both dense outputs "
+                                       "of every layer; Philox4x32-10 masks regenerated in the backward, offset advanced on the "
+                                       "device inside the captured graph)") if args.dropout > 0 else "p=0 (--dropout 0)",
                            "cuda_graph": graphed is not None},
                 "clocks": clocks.summary(),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -436,6 +441,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-scan", action="store_true")
+    ap.add_argument("--dropout", type=float, default=0.1, help="hidden / attention dropout probability (HF default 0.1; 0 = off)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--ddp", action="store_true", help="N > 1: wrap in DistributedDataParallel instead of GradSync")
     ap.add_argument("--torch-adamw", action="store_true", help="use torch.optim.AdamW(fused=True) instead of cdr_adam_multi")

@@ -15,14 +15,21 @@ _lib = None
 
 # epilogue enum (keep in sync with include/cocodr_b200.h)
 EPI_STORE_F16, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_DGELU, EPI_F32_ATOMIC, EPI_F32_STORE, EPI_SCAN_FILTER = range(7)
+EPI_BIAS_DROP_RESIDUAL = 9
 CDR_EOVERFLOW = -5
+
+
+class Dropout(C.Structure):
+    """cdr_dropout: counter-based dropout descriptor (state = device {seed, offset})."""
+    _fields_ = [("state", C.c_void_p), ("site", C.c_uint32), ("threshold", C.c_uint32), ("scale", C.c_float),
+                ("row_mul", C.c_int32)]
 
 
 class AttnArgs(C.Structure):
     _fields_ = [("qkv", C.c_void_p), ("key_bias", C.c_void_p), ("out", C.c_void_p), ("lse", C.c_void_p),
                 ("d_out", C.c_void_p), ("dqkv", C.c_void_p), ("dq_workspace", C.c_void_p),
                 ("n_seq", C.c_int32), ("seq_len", C.c_int32), ("heads", C.c_int32), ("head_dim", C.c_int32),
-                ("scale", C.c_float), ("dbias_scale", C.c_float), ("dbias_qkv", C.c_void_p)]
+                ("scale", C.c_float), ("dbias_scale", C.c_float), ("dbias_qkv", C.c_void_p), ("drop", Dropout)]
 
 
 class SimmatArgs(C.Structure):
@@ -47,7 +54,7 @@ class GemmArgs(C.Structure):
                 ("lda", C.c_int64), ("ldb", C.c_int64), ("ldo", C.c_int64), ("ldaux", C.c_int64),
                 ("a_major", C.c_int32), ("b_major", C.c_int32), ("epilogue", C.c_int32), ("split_k", C.c_int32),
                 ("alpha", C.c_float), ("dbg_lbo", C.c_int32), ("dbg_sbo", C.c_int32),
-                ("colsum", C.c_void_p), ("colsum_scale", C.c_float), ("reserved", C.c_int32)]
+                ("colsum", C.c_void_p), ("colsum_scale", C.c_float), ("reserved", C.c_int32), ("drop", Dropout)]
 
 
 def declared_symbols():

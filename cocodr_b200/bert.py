@@ -6,16 +6,19 @@ The reference never implements the encoder: it calls HuggingFace ``BertModel`` t
 and ``state_dict`` go (the HF-named fp32 parameters stay the source of truth) -- only ``forward`` is replaced:
 embeddings+LN (K1), packed-QKV GEMM (K2), fused attention (K3), output / FFN GEMMs with fused
 bias / GELU / residual epilogues + LayerNorm (K4-K6) and fp32 CLS pooling (K7), all through the C ABI.
-"""
-import warnings
 
+Dropout: in ``train()`` mode the four nn.Dropout sites of HF BERT (embeddings, attention probabilities, both dense
+outputs of every layer; ``hidden_dropout_prob`` / ``attention_probs_dropout_prob``) are applied inside the kernels
+with counter-based masks (``ops.DropSpec``; include/cocodr_b200.h ``cdr_dropout``): every encoder pass advances a
+device-resident (seed, offset) state, so a CUDA-graph replay draws fresh masks and the backward regenerates the
+forward's.  ``set_dropout_seed`` fixes the stream; ``eval()`` or p = 0 turns it off.
+"""
 import torch
+import torch.distributed as dist
 from transformers import BertModel as _HFBertModel
 from transformers.modeling_outputs import BaseModelOutputWithPoolingAndCrossAttentions
 
 from . import ops
-
-_warned_dropout = False
 
 
 def key_bias_from_mask(attention_mask):
@@ -49,16 +52,41 @@ def check_config(config):
         raise RuntimeError("cocodr_b200 BERT kernels implement absolute position embeddings only")
 
 
-def run_last_layer_cls(layer, shadow, x, key_bias, n_seq, L, config):
+def run_last_layer_cls(layer, shadow, x, key_bias, n_seq, L, config, drop=None, layer_index=0):
     """Last BertLayer when only the [CLS] embedding is consumed: FFN / LayerNorms / output projection on n_seq rows."""
     return ops.BertLastLayerCLSFn.apply(x, key_bias, *layer_params(layer), shadow, n_seq, L,
-                                        config.num_attention_heads, float(config.layer_norm_eps))
+                                        config.num_attention_heads, float(config.layer_norm_eps), drop, layer_index)
 
 
-def run_layer(layer, shadow, x, key_bias, n_seq, L, config, emit_cls=False):
-    """One BertLayer (HF module used as the parameter container) on internal fp16 [T, H] activations."""
+def run_layer(layer, shadow, x, key_bias, n_seq, L, config, emit_cls=False, drop=None, layer_index=0):
+    """One BertLayer (HF module used as the parameter container) on internal fp16 [T, H] activations.
+    ``drop`` (ops.DropSpec) / ``layer_index`` select the layer's dropout sites; None = no dropout."""
     return ops.BertLayerFn.apply(x, key_bias, *layer_params(layer), shadow, n_seq, L, config.num_attention_heads,
-                                 float(config.layer_norm_eps), emit_cls)
+                                 float(config.layer_norm_eps), emit_cls, drop, layer_index)
+
+
+class DropoutState:
+    """Device-resident (seed, offset) of the counter-based dropout.  ``next()`` advances the offset ON THE DEVICE (so a
+    captured CUDA graph draws new masks at every replay) and returns a snapshot that the pass's forward and backward
+    kernels both read -- later passes do not disturb it."""
+
+    def __init__(self):
+        self.seed = None
+        self.state = None
+
+    def set_seed(self, seed):
+        self.seed = int(seed) & 0x7FFFFFFFFFFFFFFF
+        self.state = None
+
+    def next(self, device):
+        if self.state is None or self.state.device != device:
+            seed = self.seed
+            if seed is None:  # default: torch's seed, decorrelated across data-parallel ranks
+                rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+                seed = (torch.initial_seed() + 0x9E3779B97F4A7C15 * rank) & 0x7FFFFFFFFFFFFFFF
+            self.state = torch.tensor([seed, 0], dtype=torch.int64, device=device)
+        self.state[1] += 1
+        return self.state.clone()
 
 
 class BertModel(_HFBertModel):
@@ -72,6 +100,21 @@ class BertModel(_HFBertModel):
     def _cdr_init(self):
         object.__setattr__(self, "_shadow_set", ops.ShadowSet(len(self.encoder.layer)))
         object.__setattr__(self, "_shadows", self._shadow_set.layers)
+        if not hasattr(self, "_dropout_state"):
+            object.__setattr__(self, "_dropout_state", DropoutState())
+
+    def set_dropout_seed(self, seed):
+        """Fix the dropout stream (default: torch.initial_seed(), decorrelated per rank); offset restarts at 0."""
+        self._dropout_state.set_seed(seed)
+
+    def dropout_spec(self, training, device):
+        """ops.DropSpec of the next pass (advances the device-side offset), or None in eval mode / with p = 0."""
+        ph, pa = float(self.config.hidden_dropout_prob), float(self.config.attention_probs_dropout_prob)
+        if not training or (ph <= 0.0 and pa <= 0.0):
+            return None
+        if not (0.0 <= ph < 1.0 and 0.0 <= pa < 1.0):
+            raise RuntimeError("dropout probabilities must be in [0, 1)")
+        return ops.DropSpec(self._dropout_state.next(device), ph, pa)
 
     @classmethod
     def adopt(cls, hf_bert):
@@ -91,7 +134,6 @@ class BertModel(_HFBertModel):
 
     # ------------------------------------------------------------------------------------------
     def _check_inputs(self, input_ids, token_type_ids, position_ids, inputs_embeds):
-        global _warned_dropout
         if inputs_embeds is not None or input_ids is None:
             raise NotImplementedError("cocodr_b200.BertModel takes input_ids (inputs_embeds is not supported)")
         if not input_ids.is_cuda:
@@ -102,11 +144,6 @@ class BertModel(_HFBertModel):
             raise NotImplementedError("non-zero token_type_ids are not supported (the reference never passes them)")
         if input_ids.shape[1] > self.config.max_position_embeddings:
             raise RuntimeError("sequence longer than max_position_embeddings")
-        p = max(self.config.hidden_dropout_prob, self.config.attention_probs_dropout_prob)
-        if self.training and p > 0 and not _warned_dropout:
-            warnings.warn("cocodr_b200: dropout is not implemented in the sm_100a kernels yet; training runs with p=0 "
-                          f"(config asks for {p}).")
-            _warned_dropout = True
 
     cls_only_last_layer = True  # encode_cls(): run the last layer's FFN / LayerNorms on the [CLS] rows only
 
@@ -120,21 +157,23 @@ class BertModel(_HFBertModel):
         n_seq, L = input_ids.shape
         e = self.embeddings
         self._shadow_set.refresh([shadow_sources(layer) for layer in self.encoder.layer])
+        drop = self.dropout_spec(self.training, input_ids.device)
         x = ops.EmbedLN.apply(input_ids.long(), e.word_embeddings.weight, e.position_embeddings.weight,
                               e.token_type_embeddings.weight, e.LayerNorm.weight, e.LayerNorm.bias,
-                              float(self.config.layer_norm_eps))
+                              float(self.config.layer_norm_eps), drop)
         kb = key_bias_from_mask(attention_mask)
         hidden = [x] if want_hidden else None
         cls = None
         n_layers = len(self.encoder.layer)
         for i, layer in enumerate(self.encoder.layer):
             if i == n_layers - 1 and cls_only and not want_hidden and self.cls_only_last_layer:
-                cls = run_last_layer_cls(layer, self._shadows[i], x, kb, n_seq, L, self.config)
+                cls = run_last_layer_cls(layer, self._shadows[i], x, kb, n_seq, L, self.config, drop, i)
                 x = None
             elif i == n_layers - 1:
-                x, cls = run_layer(layer, self._shadows[i], x, kb, n_seq, L, self.config, emit_cls=True)
+                x, cls = run_layer(layer, self._shadows[i], x, kb, n_seq, L, self.config, emit_cls=True, drop=drop,
+                                   layer_index=i)
             else:
-                x = run_layer(layer, self._shadows[i], x, kb, n_seq, L, self.config)
+                x = run_layer(layer, self._shadows[i], x, kb, n_seq, L, self.config, drop=drop, layer_index=i)
             if want_hidden:
                 hidden.append(x)
         return cls, x, hidden

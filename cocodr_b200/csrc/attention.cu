@@ -16,8 +16,12 @@
 // they are neutralised by the key bias (-inf) on columns and by explicit zeroing of P/dS rows.
 //
 // Replaces HF eager_attention_forward / SDPA reached through self.bert(...) in
-// ANCE/model/models.py:226 and COCO/modeling.py:199-204 (dropout p = 0 / eval-mode semantics).
+// ANCE/model/models.py:226 and COCO/modeling.py:199-204.  DROP = true adds the dropout of the attention
+// probabilities (HF BertSelfAttention: dropout(softmax(S)) V; masks regenerated from Philox counters, dropout.cuh):
+//   forward   P~ = mask . P is what multiplies V, the row sum stays that of the undropped P, O = P~ V * s / sum
+//   backward  dP = mask . s . (dO V^T);  dV = (mask . s . P)^T dO;  delta = rowsum(P . dP) = rowsum(dO . O) as before
 #include "cdr_common.cuh"
+#include "dropout.cuh"
 #include "tma_host.h"
 
 namespace cdr {
@@ -40,7 +44,14 @@ struct AttParams {
   __half* dqkv;           // [T, 3*hidden]
   float* dbias;           // optional fp32 [3*hidden]: += dbias_scale * column sums of dqkv
   float dbias_scale;
+  cdr_dropout drop;       // attention-probability dropout (DROP kernels)
 };
+
+// Philox group of the 8 probabilities (item = seq * heads + head, query row r, keys [8 * kg, 8 * kg + 8))
+__device__ __forceinline__ uint32_t att_drop_group(int item, int L, int r, int kg) {
+  return (static_cast<uint32_t>(item) * static_cast<uint32_t>(L) + static_cast<uint32_t>(r)) * 64u +
+         static_cast<uint32_t>(kg);
+}
 
 // byte offset of element (r, c), c in [0,128), inside two 128B-swizzled [128][64-half] chunks
 __device__ __forceinline__ uint32_t swz_off(int r, int c) {
@@ -82,6 +93,7 @@ __device__ __forceinline__ float dot8(const uint4& a, const uint4& b) {
 constexpr int ATT_FWD_THREADS = 320;
 constexpr int ATT_FWD_SMEM = 10 * ATT_TILE_BYTES + 8 * 512 + 8 * 2048 + 256 + 1024;
 
+template <bool DROP>
 __global__ void __launch_bounds__(ATT_FWD_THREADS, 1)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttParams p, const int n_items) {
   extern __shared__ uint8_t smem_raw[];
@@ -196,6 +208,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttParams p, 
     float* wb = sBiasW + sw * 128;   // this warp's private copy of the 128 key-bias values
     uint8_t* tile = sEpi + sw * 2048;
     const float sl2 = p.scale * LOG2E;
+    DropCtx dc{};
+    if constexpr (DROP) dc = drop_load(p.drop);
     auto fetch_bias = [&](int item, int j) -> float {  // x LOG2E at use: nothing waits on the load here
       const int c = j * 32 + lane;
       if (c >= L) return -INFINITY;
@@ -218,6 +232,12 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttParams p, 
       if (item + step < n_items) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) nb[j] = fetch_bias(item + step, j);
+      }
+      uint32_t keepw[4] = {0u, 0u, 0u, 0u};  // DROP: bit c of word w = key 32 * w + c of this query row is kept
+      if constexpr (DROP) {  // the 16 Philox calls of the row run while the tensor core still forms S
+#pragma unroll 2  // two interleaved Philox chains: more would spill next to the 128-score row
+        for (int gq = 0; gq < 16; ++gq)
+          keepw[gq >> 2] |= drop_keep8(dc, att_drop_group(item, L, r, gq)) << (8 * (gq & 3));
       }
       mbar_wait(&s_full[g], k);
       tc_fence_after();
@@ -248,6 +268,11 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttParams p, 
         for (int j = 0; j < 8; ++j) e[j] = fast_ex2(__uint_as_float(v[gq * 8 + j]) - mx);
         sum0 += (e[0] + e[1]) + (e[2] + e[3]);
         sum1 += (e[4] + e[5]) + (e[6] + e[7]);
+        if constexpr (DROP) {  // the row sum is that of the undropped probabilities; 1 / (1 - p) joins 1 / sum below
+          const uint32_t keep = keepw[gq >> 2] >> (8 * (gq & 3));
+#pragma unroll
+          for (int j = 0; j < 8; ++j) e[j] = ((keep >> j) & 1u) ? e[j] : 0.f;
+        }
         *reinterpret_cast<uint4*>(sP + swz_off(r, gq * 8)) = pack8(e);
       }
       fence_proxy_async();
@@ -255,7 +280,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttParams p, 
       if (lane == 0) mbar_arrive(&p_full[g]);
       const float sum = sum0 + sum1;
       if (r < L && p.lse) p.lse[static_cast<long long>(item) * L + r] = (mx + log2f(sum)) / LOG2E;
-      const float inv = sum > 0.f ? 1.f / sum : 0.f;
+      const float inv = (sum > 0.f ? 1.f / sum : 0.f) * (DROP ? dc.scale : 1.f);
       // ---- epilogue of the same item: O / sum -> ctx rows (transposed through the warp's tile for 64-byte row
       // segments: a store instruction covers 8 whole rows instead of 32 different lines)
       mbar_wait(&o_full[g], k);
@@ -353,6 +378,7 @@ __device__ __forceinline__ float warp_colsum32(const float (&v)[32], int lane) {
 // MMA order: S, dP (i) | dV (i) as soon as P is in smem | S, dP (i+1) | dK, dQ (i) once dS is.
 // TMEM columns: S [0,128) dP [128,256) dV [256,320) dK [320,384) dQ [384,448).
 // smem: 2 stages x (Q K V dO) = 128 KB | P 32 KB | dS 32 KB | per-warp key bias | delta halves | barriers.
+template <bool DROP>
 __global__ void __launch_bounds__(ATT_BWD_THREADS, 1)
 fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do,
                 const AttParams p, const int n_items) {
@@ -488,6 +514,8 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
     const uint32_t trow = tmem + (static_cast<uint32_t>(quad * 32) << 16);
     const float sl2 = p.scale * LOG2E;
     float* wb = sBiasW + sw * 32;   // this warp's private copy of the 32 key-bias values it needs
+    DropCtx dc{};
+    if constexpr (DROP) dc = drop_load(p.drop);
     // values of the NEXT item are fetched one item ahead (global latency off the critical path)
     auto fetch_bias = [&](int item) -> float {
       const int c = c0 + lane;
@@ -513,6 +541,12 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
         nb = fetch_bias(item + gridDim.x);
         nlse = fetch_lse(item + gridDim.x);
       }
+      uint32_t keep32 = 0xffffffffu;  // DROP: bit c = key column c0 + c of this row survived the forward dropout
+      if constexpr (DROP) {  // regenerated while the tensor core forms S / dP
+        keep32 = 0u;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) keep32 |= drop_keep8(dc, att_drop_group(item, L, r, (c0 >> 3) + g)) << (8 * g);
+      }
       mbar_wait(sdp_full, ph);
       tc_fence_after();
       // ---- S and dP of this thread's 32 columns: both loads in flight together, kept in registers to the end
@@ -527,23 +561,29 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
       float dp0 = 0.f, dp1 = 0.f, dp2 = 0.f, dp3 = 0.f;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        float pv[8];
+        float pv[8], pu[8];  // pv: what multiplied V in the forward (-> smem, dV); pu: the undropped probabilities
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           // masked keys carry bias = -inf -> P = 0; rows beyond seq_len are zeroed explicitly
           float pe = fast_ex2(fmaf(__uint_as_float(sv[g * 8 + j]), sl2, wb[g * 8 + j]) - lse2);
           pe = (r < L) ? pe : 0.f;
-          pv[j] = pe;
           sv[g * 8 + j] = __float_as_uint(pe);
+          pu[j] = pe;
+          if constexpr (DROP) {  // forward used mask . P / (1 - p); dP = mask / (1 - p) . (dO V^T)
+            const float mj = ((keep32 >> (g * 8 + j)) & 1u) ? dc.scale : 0.f;
+            pe *= mj;
+            dv[g * 8 + j] = __float_as_uint(__uint_as_float(dv[g * 8 + j]) * mj);
+          }
+          pv[j] = pe;
         }
-        dp0 = fmaf(pv[0], __uint_as_float(dv[g * 8 + 0]), dp0);
-        dp1 = fmaf(pv[1], __uint_as_float(dv[g * 8 + 1]), dp1);
-        dp2 = fmaf(pv[2], __uint_as_float(dv[g * 8 + 2]), dp2);
-        dp3 = fmaf(pv[3], __uint_as_float(dv[g * 8 + 3]), dp3);
-        dp0 = fmaf(pv[4], __uint_as_float(dv[g * 8 + 4]), dp0);
-        dp1 = fmaf(pv[5], __uint_as_float(dv[g * 8 + 5]), dp1);
-        dp2 = fmaf(pv[6], __uint_as_float(dv[g * 8 + 6]), dp2);
-        dp3 = fmaf(pv[7], __uint_as_float(dv[g * 8 + 7]), dp3);
+        dp0 = fmaf(pu[0], __uint_as_float(dv[g * 8 + 0]), dp0);
+        dp1 = fmaf(pu[1], __uint_as_float(dv[g * 8 + 1]), dp1);
+        dp2 = fmaf(pu[2], __uint_as_float(dv[g * 8 + 2]), dp2);
+        dp3 = fmaf(pu[3], __uint_as_float(dv[g * 8 + 3]), dp3);
+        dp0 = fmaf(pu[4], __uint_as_float(dv[g * 8 + 4]), dp0);
+        dp1 = fmaf(pu[5], __uint_as_float(dv[g * 8 + 5]), dp1);
+        dp2 = fmaf(pu[6], __uint_as_float(dv[g * 8 + 6]), dp2);
+        dp3 = fmaf(pu[7], __uint_as_float(dv[g * 8 + 7]), dp3);
         *reinterpret_cast<uint4*>(sP + swz_off(r, c0 + g * 8)) = pack8(pv);
       }
       sDelta[qtr * ATT_T + r] = (dp0 + dp1) + (dp2 + dp3);
@@ -670,6 +710,7 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
 // dq_convert_kernel folds into the packed fp16 dQKV afterwards.
 constexpr int ATT_FWDM_SMEM = 5 * ATT_TILE_BYTES + 512 + 128 + 1024;  // Q K V | P (2 tiles)
 
+template <bool DROP>
 __global__ void __launch_bounds__(128, 2)
 fmha_fwd_multi_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttParams p, const int q_tiles) {
   extern __shared__ uint8_t smem_raw[];
@@ -713,6 +754,8 @@ fmha_fwd_multi_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttPara
   const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
   const float sl2 = p.scale * LOG2E;
   uint32_t ph_k = 0, ph_s = 0, ph_o = 0;
+  DropCtx dc{};
+  if constexpr (DROP) dc = drop_load(p.drop);
 
   if (tid == 0) {
     mbar_expect_tx(&bar[0], ATT_TILE_BYTES);
@@ -774,6 +817,11 @@ fmha_fwd_multi_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttPara
               e[t] = exp2f(fmaf(__uint_as_float(v[g * 8 + t]), sl2, sBias[c * 32 + g * 8 + t]) - m_use);
               sum += e[t];
             }
+            if constexpr (DROP) {
+              const uint32_t keep = drop_keep8(dc, att_drop_group(sh, L, q0 + r, (k0 >> 3) + c * 4 + g));
+#pragma unroll
+              for (int t = 0; t < 8; ++t) e[t] = ((keep >> t) & 1u) ? e[t] : 0.f;
+            }
             *reinterpret_cast<uint4*>(sP + swz_off(r, c * 32 + g * 8)) = pack8(e);
           }
         }
@@ -803,7 +851,7 @@ fmha_fwd_multi_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttPara
     const float m_use = (mx == -INFINITY) ? 0.f : mx;
     p.lse[(static_cast<long long>(seq) * p.heads + h) * L + qrow] = (m_use + log2f(sum)) / LOG2E;
   }
-  const float inv = sum > 0.f ? 1.f / sum : 0.f;
+  const float inv = (sum > 0.f ? 1.f / sum : 0.f) * (DROP ? dc.scale : 1.f);
   __half* orow = p.out + static_cast<long long>(row0 + qrow) * p.hidden + h * ATT_D;
   const uint32_t trow_o = tmem_o + (static_cast<uint32_t>(warp * 32) << 16);
 #pragma unroll 1
@@ -832,6 +880,7 @@ fmha_fwd_multi_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttPara
 // smem: K V (fixed) | Q dO (per query tile) | P then dS (32 KB)
 constexpr int ATT_BWDM_SMEM = 6 * ATT_TILE_BYTES + 1024 + 128 + 1024;
 
+template <bool DROP>
 __global__ void __launch_bounds__(256, 1)
 fmha_bwd_multi_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do,
                       const AttParams p, float* __restrict__ dq_ws, const int kv_tiles) {
@@ -886,6 +935,8 @@ fmha_bwd_multi_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_
   const int half = warp >> 2;
   const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
   const float sl2 = p.scale * LOG2E;
+  DropCtx dc{};
+  if constexpr (DROP) dc = drop_load(p.drop);
 
   if (tid == 0) {
     mbar_expect_tx(&bar[0], 2 * ATT_TILE_BYTES);
@@ -937,13 +988,16 @@ fmha_bwd_multi_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         float pv[8], ds[8];
+        uint32_t keep = 0xffu;
+        if constexpr (DROP) keep = drop_keep8(dc, att_drop_group(sh, L, qrow, ((k0 + c0) >> 3) + g));
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
           const int c = c0 + g * 8 + t;
           const bool ok = (qrow < L) && (k0 + c < L);
           const float pe = ok ? exp2f(fmaf(__uint_as_float(s[g * 8 + t]), sl2, sBias[c]) - lse2) : 0.f;
-          pv[t] = pe;
-          ds[t] = ok ? pe * (__uint_as_float(d[g * 8 + t]) - delta) * p.scale : 0.f;
+          const float mj = DROP ? (((keep >> t) & 1u) ? dc.scale : 0.f) : 1.f;
+          pv[t] = pe * mj;
+          ds[t] = ok ? pe * (mj * __uint_as_float(d[g * 8 + t]) - delta) * p.scale : 0.f;
         }
         *reinterpret_cast<uint4*>(sP + swz_off(rl, c0 + g * 8)) = pack8(pv);
         ds_keep[cc * 4 + g] = pack8(ds);
@@ -1047,6 +1101,11 @@ __global__ void dq_convert_kernel(const float* __restrict__ ws, __half* __restri
 
 static int att_check(const cdr_attn_args* a) {
   CDR_REQUIRE(a != nullptr, "cdr_attn: null args");
+  if (a->drop.state != nullptr && a->drop.threshold > 0) {
+    CDR_REQUIRE(a->drop.threshold < 65536, "cdr_attn: drop.threshold out of range");
+    CDR_REQUIRE(static_cast<long long>(a->n_seq) * a->heads * a->seq_len * 64 < (1ll << 32),
+                "cdr_attn: dropout group index overflows 32 bits");
+  }
   CDR_REQUIRE(a->qkv != nullptr, "cdr_attn: null qkv");
   CDR_REQUIRE(a->n_seq > 0 && a->seq_len > 0 && a->heads > 0, "cdr_attn: empty problem");
   CDR_REQUIRE(a->seq_len <= 512, "cdr_attn: seq_len %d > 512 not supported", a->seq_len);
@@ -1073,23 +1132,27 @@ int cdr_attn_fwd(const cdr_attn_args* a, void* stream) {
   p.scale = a->scale;
   p.out = static_cast<__half*>(a->out);
   p.lse = a->lse;
+  p.drop = a->drop;
+  const bool drop = drop_on(a->drop);
   static bool configured = false;
   if (!configured) {
-    CDR_CUDA(cudaFuncSetAttribute(fmha_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWD_SMEM));
-    CDR_CUDA(cudaFuncSetAttribute(fmha_fwd_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWDM_SMEM));
+    CDR_CUDA(cudaFuncSetAttribute(fmha_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWD_SMEM));
+    CDR_CUDA(cudaFuncSetAttribute(fmha_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWD_SMEM));
+    CDR_CUDA(cudaFuncSetAttribute(fmha_fwd_multi_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWDM_SMEM));
+    CDR_CUDA(cudaFuncSetAttribute(fmha_fwd_multi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWDM_SMEM));
     configured = true;
   }
   if (a->seq_len > ATT_T) {
     const int q_tiles = (a->seq_len + ATT_T - 1) / ATT_T;
-    fmha_fwd_multi_kernel<<<a->n_seq * a->heads * q_tiles, 128, ATT_FWDM_SMEM, static_cast<cudaStream_t>(stream)>>>(
-        tq, p, q_tiles);
+    auto kern = drop ? fmha_fwd_multi_kernel<true> : fmha_fwd_multi_kernel<false>;
+    kern<<<a->n_seq * a->heads * q_tiles, 128, ATT_FWDM_SMEM, static_cast<cudaStream_t>(stream)>>>(tq, p, q_tiles);
     CDR_LAUNCH_CHECK();
     return CDR_OK;
   }
   const int n_items = a->n_seq * a->heads;
   const int grid = n_items < sm_count() ? n_items : sm_count();
-  CDR_CUDA(launch_pdl(fmha_fwd_kernel, dim3(grid), dim3(ATT_FWD_THREADS), ATT_FWD_SMEM, static_cast<cudaStream_t>(stream),
-                      tq, p, n_items));
+  CDR_CUDA(launch_pdl(drop ? fmha_fwd_kernel<true> : fmha_fwd_kernel<false>, dim3(grid), dim3(ATT_FWD_THREADS),
+                      ATT_FWD_SMEM, static_cast<cudaStream_t>(stream), tq, p, n_items));
   return CDR_OK;
 }
 
@@ -1110,10 +1173,14 @@ int cdr_attn_bwd(const cdr_attn_args* a, void* stream) {
   p.o = static_cast<const __half*>(a->out);
   p.d_o = static_cast<const __half*>(a->d_out);
   p.dqkv = static_cast<__half*>(a->dqkv);
+  p.drop = a->drop;
+  const bool drop = drop_on(a->drop);
   static bool configured = false;
   if (!configured) {
-    CDR_CUDA(cudaFuncSetAttribute(fmha_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWD_SMEM));
-    CDR_CUDA(cudaFuncSetAttribute(fmha_bwd_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWDM_SMEM));
+    CDR_CUDA(cudaFuncSetAttribute(fmha_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWD_SMEM));
+    CDR_CUDA(cudaFuncSetAttribute(fmha_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWD_SMEM));
+    CDR_CUDA(cudaFuncSetAttribute(fmha_bwd_multi_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWDM_SMEM));
+    CDR_CUDA(cudaFuncSetAttribute(fmha_bwd_multi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWDM_SMEM));
     configured = true;
   }
   if (a->seq_len > ATT_T) {
@@ -1122,8 +1189,8 @@ int cdr_attn_bwd(const cdr_attn_args* a, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int kv_tiles = (a->seq_len + ATT_T - 1) / ATT_T;
     CDR_CUDA(cudaMemsetAsync(a->dq_workspace, 0, sizeof(float) * static_cast<size_t>(T) * hidden, st));
-    fmha_bwd_multi_kernel<<<a->n_seq * a->heads * kv_tiles, 256, ATT_BWDM_SMEM, st>>>(tq, td, p, a->dq_workspace,
-                                                                                    kv_tiles);
+    auto kern = drop ? fmha_bwd_multi_kernel<true> : fmha_bwd_multi_kernel<false>;
+    kern<<<a->n_seq * a->heads * kv_tiles, 256, ATT_BWDM_SMEM, st>>>(tq, td, p, a->dq_workspace, kv_tiles);
     CDR_LAUNCH_CHECK();
     const long long n8 = (static_cast<long long>(T) * hidden + 7) / 8;
     dq_convert_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, st>>>(a->dq_workspace, p.dqkv, T, hidden);
@@ -1134,8 +1201,8 @@ int cdr_attn_bwd(const cdr_attn_args* a, void* stream) {
   p.dbias_scale = a->dbias_scale;
   const int n_items = a->n_seq * a->heads;
   const int grid = n_items < sm_count() ? n_items : sm_count();
-  CDR_CUDA(launch_pdl(fmha_bwd_kernel, dim3(grid), dim3(ATT_BWD_THREADS), ATT_BWD_SMEM, static_cast<cudaStream_t>(stream),
-                      tq, td, p, n_items));
+  CDR_CUDA(launch_pdl(drop ? fmha_bwd_kernel<true> : fmha_bwd_kernel<false>, dim3(grid), dim3(ATT_BWD_THREADS),
+                      ATT_BWD_SMEM, static_cast<cudaStream_t>(stream), tq, td, p, n_items));
   return CDR_OK;
 }
 

@@ -5,6 +5,7 @@
 // 3-stage mbarrier ring, a warp per row for the statistics, a thread per 8 columns for the column sums); wider rows
 // and the fp32 [CLS]-gradient variant keep the one-warp-per-row kernels.
 #include "cdr_common.cuh"
+#include "dropout.cuh"
 #include "peer.cuh"
 
 namespace cdr {
@@ -472,15 +473,20 @@ ln_fwd_staged_kernel(const __half* __restrict__ x, const float* __restrict__ gam
   if (push.pa.world > 0) peer_signal_grid_done(push.pa, 0);
 }
 
-template <int VPL>
+// DROP: the LayerNorm input was x + dropout(d) (HF BertSelfOutput / BertOutput).  dx stays the gradient of the residual
+// branch; dxm = mask . dx / (1 - p) is the gradient of the dense output d (operand of its dgrad / wgrad GEMMs) and dcol
+// becomes the column sum of dxm (the dense bias gradient) -- phase B recomputes dx from the staged tile and the row
+// statistics and applies the keep bits phase A left in shared memory.
+template <int VPL, bool DROP>
 __global__ void __launch_bounds__(LNS_THREADS, 2)
 ln_bwd_staged_kernel(const __half* __restrict__ dy, const __half* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ mean_in, const float* __restrict__ rstd_in, __half* __restrict__ dx,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dcol, int rows,
-                     int hidden, float out_scale) {
+                     int hidden, float out_scale, __half* __restrict__ dxm, const cdr_dropout drop) {
   extern __shared__ __align__(128) uint8_t lns_smem[];  // [stage][dy tile | x tile]
   __shared__ uint64_t full[LNS_STAGES];
   __shared__ float4 rowstat[LNS_ROWS];  // mean, rstd, rstd*c1, rstd*c2 of the rows of the current tile
+  __shared__ uint8_t keepb[DROP ? LNS_ROWS : 1][DROP ? 128 : 1];  // DROP: keep bits of (row of the tile, column group)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nvec = hidden >> 3;
   const uint32_t row_bytes = static_cast<uint32_t>(hidden) * 2u;
@@ -513,9 +519,17 @@ ln_bwd_staged_kernel(const __half* __restrict__ dy, const __half* __restrict__ x
   // phase-B ownership: thread -> 8 columns (cgp) of the rows [rh * 4, rh * 4 + 4) of each tile
   const int cgp = tid % 128, rh = tid / 128;
   const bool colthread = cgp < nvec;
-  float a_dg[8], a_db[8], a_s3[8], a_s4[8], a_c = 0.f;
+  float a_dg[8], a_db[8], a_s3[8], a_s4[8], a_c = 0.f;  // DROP: a_s3 accumulates the masked dx directly
 #pragma unroll
   for (int k = 0; k < 8; ++k) a_dg[k] = a_db[k] = a_s3[k] = a_s4[k] = 0.f;
+  DropCtx dc{};
+  float gcol[8];
+  if constexpr (DROP) {
+    dc = drop_load(drop);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) gcol[k] = 0.f;
+    if (colthread) load8_f(gamma + 8 * cgp, gcol);
+  }
 
   // per-row statistics of the NEXT tile are fetched one iteration ahead (their global latency would otherwise
   // sit on the critical path of every tile)
@@ -568,6 +582,12 @@ ln_bwd_staged_kernel(const __half* __restrict__ dy, const __half* __restrict__ x
 #pragma unroll
             for (int k = 0; k < 8; ++k) o[k] = rstd * (gy[i][k] - c1 - xh[i][k] * c2);
             store8_h(dx + static_cast<long long>(row) * hidden + 8 * (lane + 32 * i), o);
+            if constexpr (DROP) {
+              const uint32_t keep = drop_keep8(dc, drop_group(dc, row, 8 * (lane + 32 * i), hidden));
+              keepb[warp][lane + 32 * i] = static_cast<uint8_t>(keep);
+              drop_apply8(dc, keep, o);
+              store8_h(dxm + static_cast<long long>(row) * hidden + 8 * (lane + 32 * i), o);
+            }
           }
       } else if (lane == 0) {
         rowstat[warp] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -583,14 +603,21 @@ ln_bwd_staged_kernel(const __half* __restrict__ dy, const __half* __restrict__ x
           float d[8], xv[8];
           load8_h(dys + r * hidden + 8 * cgp, d);
           load8_h(xs + r * hidden + 8 * cgp, xv);
-          a_c += st.z;
+          uint32_t keep = 0u;
+          if constexpr (DROP) keep = keepb[r][cgp];
+          else a_c += st.z;
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const float xh = (xv[k] - st.x) * st.y;
             a_dg[k] = fmaf(d[k], xh, a_dg[k]);
             a_db[k] += d[k];
-            a_s3[k] = fmaf(st.y, d[k], a_s3[k]);
-            a_s4[k] = fmaf(st.w, xh, a_s4[k]);
+            if constexpr (DROP) {  // dx of this element again (what phase A stored), summed where it was kept
+              const float dxv = fmaf(st.y * gcol[k], d[k], -st.z) - st.w * xh;
+              a_s3[k] += ((keep >> k) & 1u) ? dxv : 0.f;
+            } else {
+              a_s3[k] = fmaf(st.y, d[k], a_s3[k]);
+              a_s4[k] = fmaf(st.w, xh, a_s4[k]);
+            }
           }
         }
       }
@@ -632,9 +659,13 @@ ln_bwd_staged_kernel(const __half* __restrict__ dy, const __half* __restrict__ x
     }
     if (dcol != nullptr) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        o[k] = (gg[k] * (a_s3[k] + red[(2 * nvec + cgp) * 8 + k]) - (a_s4[k] + red[(3 * nvec + cgp) * 8 + k]) - ctot) *
-               out_scale;
+      for (int k = 0; k < 8; ++k) {
+        if constexpr (DROP)
+          o[k] = (a_s3[k] + red[(2 * nvec + cgp) * 8 + k]) * dc.scale * out_scale;
+        else
+          o[k] = (gg[k] * (a_s3[k] + red[(2 * nvec + cgp) * 8 + k]) - (a_s4[k] + red[(3 * nvec + cgp) * 8 + k]) - ctot) *
+                 out_scale;
+      }
       atomic_add8(dcol + 8 * cgp, o);
     }
   }
@@ -668,6 +699,22 @@ colsum_kernel(const __half* __restrict__ x, float* __restrict__ out, int rows, i
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] *= scale;
   atomic_add8(out + c, acc);
+}
+
+// out = dropout(x) on a contiguous fp16 [rows, cols] tensor, one Philox group (8 elements, 16 bytes) per thread step
+__global__ void __launch_bounds__(256)
+dropout_kernel(const __half* __restrict__ x, __half* __restrict__ out, long long groups, int groups_per_row,
+               const cdr_dropout drop) {
+  const DropCtx dc = drop_load(drop);
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long gi = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; gi < groups; gi += stride) {
+    const long long m = gi / groups_per_row;
+    const int cg = static_cast<int>(gi - m * groups_per_row);
+    float v[8];
+    load8_h(x + gi * 8, v);
+    drop_apply8(dc, drop_keep8(dc, static_cast<uint32_t>(m * dc.row_mul * groups_per_row + cg)), v);
+    store8_h(out + gi * 8, v);
+  }
 }
 
 __global__ void cast_f32_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long n) {
@@ -860,12 +907,14 @@ int cdr_ln_bwd(const void* dy, const float* dy_cls, const void* x, const float* 
   do {                                                                                                               \
     static bool cfg = false;                                                                                         \
     if (!cfg) {                                                                                                      \
-      CDR_CUDA(cudaFuncSetAttribute(ln_bwd_staged_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024)); \
+      CDR_CUDA(cudaFuncSetAttribute(ln_bwd_staged_kernel<V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                    112 * 1024));                                                                    \
       cfg = true;                                                                                                    \
     }                                                                                                                \
-    CDR_CUDA(launch_pdl(ln_bwd_staged_kernel<V>, dim3(grid), dim3(LNS_THREADS), smem, st,                             \
+    CDR_CUDA(launch_pdl(ln_bwd_staged_kernel<V, false>, dim3(grid), dim3(LNS_THREADS), smem, st,                      \
                         static_cast<const __half*>(dy), static_cast<const __half*>(x), gamma, mean, rstd,             \
-                        static_cast<__half*>(dx), dgamma, dbeta, dbias, rows, hidden, out_scale));                   \
+                        static_cast<__half*>(dx), dgamma, dbeta, dbias, rows, hidden, out_scale,                     \
+                        static_cast<__half*>(nullptr), cdr_dropout{}));                                              \
   } while (0)
     if (vpl <= 1) LNS_BWD(1);
     else if (vpl <= 2) LNS_BWD(2);
@@ -909,6 +958,64 @@ int cdr_ln_bwd(const void* dy, const float* dy_cls, const void* x, const float* 
                           nullptr, gamma, mean, rstd, dy_cls, static_cast<__half*>(dx), dgamma, dbeta, dbias, nullptr,
                           nullptr, n_seq, hidden, seq_len, 0, -1, in_scale, out_scale,
                           static_cast<cudaStream_t>(stream));
+}
+
+int cdr_ln_bwd_drop(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, void* dx,
+                    void* dx_drop, float* dgamma, float* dbeta, float* dbias, int32_t rows, int32_t hidden,
+                    float out_scale, const cdr_dropout* drop, void* stream) {
+  if (int rc = check_hidden(hidden)) return rc;
+  CDR_REQUIRE(dy && x && gamma && mean && rstd && dx && dx_drop && drop, "cdr_ln_bwd_drop: null pointer");
+  CDR_REQUIRE(drop->state != nullptr && drop->threshold > 0 && drop->threshold < 65536,
+              "cdr_ln_bwd_drop: needs drop.state and 0 < drop.threshold < 65536");
+  CDR_REQUIRE(hidden <= 1024 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(dx) & 15) == 0 && (reinterpret_cast<uintptr_t>(dx_drop) & 15) == 0,
+              "cdr_ln_bwd_drop: needs hidden <= 1024 and 16-byte aligned tensors");
+  CDR_REQUIRE(static_cast<long long>(rows) * (drop->row_mul > 0 ? drop->row_mul : 1) * (hidden / 8) < (1ll << 32),
+              "cdr_ln_bwd_drop: dropout group index overflows 32 bits");
+  if (rows <= 0) return CDR_OK;
+  const size_t smem = static_cast<size_t>(LNS_STAGES) * 2 * LNS_ROWS * hidden * 2;
+  const int vpl = (hidden / 8 + 31) / 32;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = lns_grid(rows, smem);
+#define LNS_BWD_DROP(V)                                                                                              \
+  do {                                                                                                               \
+    static bool cfg = false;                                                                                         \
+    if (!cfg) {                                                                                                      \
+      CDR_CUDA(cudaFuncSetAttribute(ln_bwd_staged_kernel<V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                    112 * 1024));                                                                    \
+      cfg = true;                                                                                                    \
+    }                                                                                                                \
+    CDR_CUDA(launch_pdl(ln_bwd_staged_kernel<V, true>, dim3(grid), dim3(LNS_THREADS), smem, st,                       \
+                        static_cast<const __half*>(dy), static_cast<const __half*>(x), gamma, mean, rstd,             \
+                        static_cast<__half*>(dx), dgamma, dbeta, dbias, rows, hidden, out_scale,                     \
+                        static_cast<__half*>(dx_drop), *drop));                                                      \
+  } while (0)
+  if (vpl <= 1) LNS_BWD_DROP(1);
+  else if (vpl <= 2) LNS_BWD_DROP(2);
+  else if (vpl <= 3) LNS_BWD_DROP(3);
+  else LNS_BWD_DROP(4);
+#undef LNS_BWD_DROP
+  CDR_LAUNCH_CHECK();
+  return CDR_OK;
+}
+
+int cdr_dropout_f16(const void* x, void* out, int64_t rows, int32_t cols, const cdr_dropout* drop, void* stream) {
+  CDR_REQUIRE(x && out && drop, "cdr_dropout_f16: null pointer");
+  CDR_REQUIRE(cols > 0 && cols % 8 == 0, "cdr_dropout_f16: cols must be a positive multiple of 8");
+  CDR_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+              "cdr_dropout_f16: tensors must be 16-byte aligned");
+  CDR_REQUIRE(drop->state != nullptr && drop->threshold < 65536, "cdr_dropout_f16: needs drop.state, threshold < 65536");
+  CDR_REQUIRE(rows * (drop->row_mul > 0 ? drop->row_mul : 1) * (cols / 8) < (1ll << 32),
+              "cdr_dropout_f16: dropout group index overflows 32 bits");
+  if (rows <= 0) return CDR_OK;
+  const long long groups = rows * (cols / 8);
+  long long blocks = (groups + 255) / 256;
+  const long long cap = static_cast<long long>(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  dropout_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), static_cast<__half*>(out), groups, cols / 8, *drop);
+  CDR_LAUNCH_CHECK();
+  return CDR_OK;
 }
 
 int cdr_colsum_f16(const void* x, float* out, int64_t rows, int64_t cols, int64_t ld, float scale, void* stream) {

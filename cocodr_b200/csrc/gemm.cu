@@ -64,6 +64,7 @@ static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, c
     default: break;
   }
   if constexpr (!A_MN && !B_MN) {
+    if (epi == CDR_EPI_BIAS_DROP_RESIDUAL) return launch_gemm<BN, false, false, CDR_EPI_BIAS_DROP_RESIDUAL>(ta, tb, p, st);
     if (epi == CDR_EPI_BIAS_GELU) return launch_gemm<BN, false, false, CDR_EPI_BIAS_GELU>(ta, tb, p, st);
     if (epi == CDR_EPI_SCAN_FILTER) return launch_gemm<BN, false, false, CDR_EPI_SCAN_FILTER>(ta, tb, p, st);
     if (epi == CDR_EPI_SCAN_FILTER_Q) return launch_gemm<BN, false, false, CDR_EPI_SCAN_FILTER_Q>(ta, tb, p, st);
@@ -140,6 +141,7 @@ int gemm_run(const cdr_gemm_args& g, GemmParams p, cudaStream_t st) {
   p.alpha = g.alpha;
   p.colsum = g.colsum;
   p.colsum_scale = g.colsum_scale;
+#ifdef CDR_GEMM_DEBUG  // experiment builds only (tools/build_variant.sh): descriptor overrides, work-skipping flags
   p.dbg_lbo = g.dbg_lbo; p.dbg_sbo = g.dbg_sbo;
   {
     static int dbg = -1;
@@ -149,6 +151,7 @@ int gemm_run(const cdr_gemm_args& g, GemmParams p, cudaStream_t st) {
     }
     p.dbg_flags = dbg;
   }
+#endif
 
   CUtensorMap ta, tb;
   int rc;
@@ -177,7 +180,13 @@ extern "C" int cdr_gemm(const cdr_gemm_args* g, void* stream) {
   const bool f32 = g->epilogue == CDR_EPI_F32_ATOMIC || g->epilogue == CDR_EPI_F32_STORE;
   CDR_REQUIRE(g->ldo % (f32 ? 4 : 8) == 0, "cdr_gemm: ldo must keep rows 16-byte aligned (ldo=%lld)", (long long)g->ldo);
   CDR_REQUIRE((reinterpret_cast<uintptr_t>(g->out) & 15) == 0, "cdr_gemm: out must be 16-byte aligned");
-  if (g->epilogue == CDR_EPI_BIAS_RESIDUAL || g->epilogue == CDR_EPI_DGELU) {
+  if (g->epilogue == CDR_EPI_BIAS_DROP_RESIDUAL) {
+    CDR_REQUIRE(g->drop.state != nullptr && g->drop.threshold > 0 && g->drop.threshold < 65536 && g->drop.row_mul >= 0,
+                "cdr_gemm: CDR_EPI_BIAS_DROP_RESIDUAL needs drop.state and 0 < drop.threshold < 65536");
+    CDR_REQUIRE(g->M * (g->drop.row_mul > 0 ? g->drop.row_mul : 1) * (g->N / 8) < (1ll << 32),
+                "cdr_gemm: dropout group index overflows 32 bits");
+  }
+  if (g->epilogue == CDR_EPI_BIAS_RESIDUAL || g->epilogue == CDR_EPI_DGELU || g->epilogue == CDR_EPI_BIAS_DROP_RESIDUAL) {
     CDR_REQUIRE(g->aux != nullptr && g->ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(g->aux) & 15) == 0,
                 "cdr_gemm: epilogue %d needs a 16-byte aligned aux operand", g->epilogue);
   }
@@ -191,6 +200,7 @@ extern "C" int cdr_gemm(const cdr_gemm_args* g, void* stream) {
   p.aux = static_cast<const __half*>(g->aux);
   p.ldo = g->ldo;
   p.ldaux = g->ldaux;
+  p.drop = g->drop;
   return cdr::gemm_run(*g, p, static_cast<cudaStream_t>(stream));
 }
 

@@ -26,6 +26,7 @@
 #include <type_traits>
 
 #include "cdr_common.cuh"
+#include "dropout.cuh"
 
 namespace cdr {
 
@@ -41,6 +42,14 @@ template <int EPI>
 constexpr int GEMM_EW = (EPI == CDR_EPI_SCAN_FILTER || EPI == CDR_EPI_SCAN_FILTER_Q) ? 16 : CDR_GEMM_EPI_WARPS;
 template <int EPI>
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EW<EPI>;
+
+#ifdef CDR_GEMM_DEBUG
+#define CDR_DBG(p, bit) ((p).dbg_flags & (bit))
+#define CDR_DBG_OR(v, dflt) ((v) ? (v) : (dflt))
+#else
+#define CDR_DBG(p, bit) 0
+#define CDR_DBG_OR(v, dflt) (dflt)
+#endif
 
 struct GemmParams {
   int M, N, K;          // problem size (K = reduction length)
@@ -63,11 +72,13 @@ struct GemmParams {
   int* cand_count;              // [N]
   int cand_cap;
   long long row_base;           // global doc index of row 0
-  // debug overrides for descriptor probing (0 = default)
+  // descriptor probing / timing experiments: honoured by -DCDR_GEMM_DEBUG builds only (tools/build_variant.sh); the
+  // release kernels ignore them, so no environment variable or argument can make a product kernel skip work
   int dbg_lbo, dbg_sbo;
   long long a_rows_alloc;  // same for A
   long long b_rows_alloc;  // rows of B that physically exist (>= N; 0 = N): lets TMA boxes read zero padding instead of going out of bounds
-  int dbg_flags;  // CDR_GEMM_DBG (environment): bit 0 = skip the epilogue math and stores (timing experiments only)
+  int dbg_flags;  // CDR_GEMM_DEBUG builds: CDR_GEMM_DBG (environment) bit 0 = skip the epilogue math and stores
+  cdr_dropout drop;  // CDR_EPI_BIAS_DROP_RESIDUAL
   // CDR_EPI_F32_GROUPED: split s reduces k-blocks [seg_kb[s], seg_kb[s+1]) (device array of split_k + 1 ascending
   // entries) into out + s * seg_out_stride -- the iDRO per-group wgrad as one launch
   const int* seg_kb;
@@ -132,7 +143,7 @@ __device__ __forceinline__ float4* stg_piece(float* stg, int r, int j) {
 // 8 consecutive columns [n, n+8) of row m; v = raw accumulators
 template <int EPI>
 __device__ __forceinline__ void gemm_epilogue_apply(const GemmParams& p, float (&v)[8], int m, int n,
-                                                    const float (&bias)[8], const uint4& auxq) {
+                                                    const float (&bias)[8], const uint4& auxq, const DropCtx& dc) {
   if constexpr (EPI == CDR_EPI_SCAN_FILTER) {
     // rows = documents, columns = queries; bias[] holds the admission thresholds of the 8 queries
 #pragma unroll
@@ -150,18 +161,20 @@ __device__ __forceinline__ void gemm_epilogue_apply(const GemmParams& p, float (
     const float4 lo = make_float4(v[0] * p.alpha, v[1] * p.alpha, v[2] * p.alpha, v[3] * p.alpha);
     const float4 hi = make_float4(v[4] * p.alpha, v[5] * p.alpha, v[6] * p.alpha, v[7] * p.alpha);
     if constexpr (EPI == CDR_EPI_F32_ATOMIC) {
-      if (p.dbg_flags & 2) return;
+      if (CDR_DBG(p, 2)) return;
       atomicAdd(reinterpret_cast<float4*>(o), lo);
       atomicAdd(reinterpret_cast<float4*>(o + 4), hi);
     } else {
-      if (p.dbg_flags & 2) return;
+      if (CDR_DBG(p, 2)) return;
       *reinterpret_cast<float4*>(o) = lo;
       *reinterpret_cast<float4*>(o + 4) = hi;
     }
   } else {
 #pragma unroll
     for (int t = 0; t < 8; ++t) v[t] = fmaf(v[t], p.alpha, bias[t]);
-    if constexpr (EPI == CDR_EPI_BIAS_RESIDUAL) {
+    if constexpr (EPI == CDR_EPI_BIAS_DROP_RESIDUAL)  // HF BertSelfOutput / BertOutput: LN(x + dropout(dense(h)))
+      drop_apply8(dc, drop_keep8(dc, drop_group(dc, m, n, p.N)), v);
+    if constexpr (EPI == CDR_EPI_BIAS_RESIDUAL || EPI == CDR_EPI_BIAS_DROP_RESIDUAL) {
       const __half2* rh = reinterpret_cast<const __half2*>(&auxq);
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
@@ -183,7 +196,7 @@ __device__ __forceinline__ void gemm_epilogue_apply(const GemmParams& p, float (
       float d[8];
 #pragma unroll
       for (int t = 0; t < 8; ++t) gelu_erf_both(v[t], v[t], d[t]);
-      if (p.out2 != nullptr && !(p.dbg_flags & 2)) {
+      if (p.out2 != nullptr && !CDR_DBG(p, 2)) {
         uint4 dq;
         __half2* dh = reinterpret_cast<__half2*>(&dq);
 #pragma unroll
@@ -195,7 +208,7 @@ __device__ __forceinline__ void gemm_epilogue_apply(const GemmParams& p, float (
     __half2* qh = reinterpret_cast<__half2*>(&q);
 #pragma unroll
     for (int t = 0; t < 4; ++t) qh[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
-    if (p.dbg_flags & 2) {
+    if (CDR_DBG(p, 2)) {
       if (q.x == 0x12345678u && q.y == 0x9abcdef0u) reinterpret_cast<uint4*>(p.out)[0] = q;  // keep the math alive
       return;
     }
@@ -277,7 +290,8 @@ __device__ __forceinline__ void gemm_filter_rows_commit(const GemmParams& p, con
 }
 
 template <int EPI>
-constexpr bool GEMM_EPI_HAS_AUX = (EPI == CDR_EPI_BIAS_RESIDUAL || EPI == CDR_EPI_DGELU);
+constexpr bool GEMM_EPI_HAS_AUX =
+    (EPI == CDR_EPI_BIAS_RESIDUAL || EPI == CDR_EPI_DGELU || EPI == CDR_EPI_BIAS_DROP_RESIDUAL);
 
 // The residual / saved-derivative operand of one 32 x 32 chunk, in the post-transpose thread mapping
 // (thread -> 8 columns of rows (lane>>2) + 8i).  Issued BEFORE the accumulator is waited for, so the global
@@ -291,7 +305,7 @@ __device__ __forceinline__ void gemm_epilogue_load_aux(const GemmParams& p, uint
     for (int i = 0; i < 4; ++i) {
       const int m = m_base + (lane >> 2) + 8 * i;
       auxq[i] = make_uint4(0u, 0u, 0u, 0u);
-      if (n < p.N && m < p.M && !(p.dbg_flags & 4)) auxq[i] = *reinterpret_cast<const uint4*>(p.aux + static_cast<long long>(m) * p.ldaux + n);
+      if (n < p.N && m < p.M && !CDR_DBG(p, 4)) auxq[i] = *reinterpret_cast<const uint4*>(p.aux + static_cast<long long>(m) * p.ldaux + n);
     }
   }
 }
@@ -299,7 +313,8 @@ __device__ __forceinline__ void gemm_epilogue_load_aux(const GemmParams& p, uint
 // One warp, one 32 x 32 chunk: rows [m_base, m_base+32), columns [n0, n0+32).  acc = this thread's row.
 template <int EPI>
 __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const uint32_t (&acc)[32], float* stg,
-                                                    int lane, int m_base, int n0, const uint4 (&auxq)[4]) {
+                                                    int lane, int m_base, int n0, const uint4 (&auxq)[4],
+                                                    const DropCtx& dc) {
 #pragma unroll
   for (int j = 0; j < 8; ++j)
     *stg_piece(stg, lane, j) = make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]),
@@ -333,7 +348,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const u
     const float4 hi = *stg_piece(stg, r, 2 * seg + 1);
     float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
     if (col_ok && m < p.M) {
-      gemm_epilogue_apply<EPI>(p, v, m, n, bias, auxq[i]);
+      gemm_epilogue_apply<EPI>(p, v, m, n, bias, auxq[i], dc);
       if constexpr (EPI == CDR_EPI_DGELU) {
 #pragma unroll
         for (int t = 0; t < 8; ++t) csum[t] += v[t];
@@ -493,9 +508,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     if (lane == 0 && cta_rank == 0) {
       constexpr uint32_t idesc = make_idesc_f16(GEMM_BM * CG, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       // descriptor geometry
-      const uint32_t a_lbo = A_MN ? (p.dbg_lbo ? p.dbg_lbo : GEMM_BK * 128) : 16;
-      const uint32_t b_lbo = B_MN ? (p.dbg_lbo ? p.dbg_lbo : GEMM_BK * 128) : 16;
-      const uint32_t sbo = p.dbg_sbo ? p.dbg_sbo : 1024;
+      const uint32_t a_lbo = A_MN ? CDR_DBG_OR(p.dbg_lbo, GEMM_BK * 128) : 16;
+      const uint32_t b_lbo = B_MN ? CDR_DBG_OR(p.dbg_lbo, GEMM_BK * 128) : 16;
+      const uint32_t sbo = CDR_DBG_OR(p.dbg_sbo, 1024);
       constexpr uint32_t a_kstep = A_MN ? 2048 : 32;   // bytes per UMMA_K = 16
       constexpr uint32_t b_kstep = B_MN ? 2048 : 32;
       int stage = 0;
@@ -550,6 +565,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     const GemmParams& pe = [&]() -> const GemmParams& {
       if constexpr (GROUPED) return pg; else return p;
     }();
+    DropCtx dc{};
+    if constexpr (EPI == CDR_EPI_BIAS_DROP_RESIDUAL) dc = drop_load(p.drop);
     for (int item = worker; item < total_items; item += n_workers) {
       const int tile = item % tiles;
       if constexpr (EPI == CDR_EPI_F32_GROUPED) {
@@ -610,10 +627,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           if (ok1) t1 = gemm_filter_reserve(p, r1, fws + 96, lane, mb + lane, n0 + c1 * 32);
           if (ok0) gemm_filter_commit(p, r0, fws, lane, mb + lane, n0 + c0 * 32, t0);
           if (ok1) gemm_filter_commit(p, r1, fws + 96, lane, mb + lane, n0 + c1 * 32, t1);
-        } else if (n0 + c0 * 32 < p.N && !(p.dbg_flags & 1)) {
-          gemm_epilogue_chunk<EPIM>(pe, r0, stg, lane, mb, n0 + c0 * 32, aux[b]);
+        } else if (n0 + c0 * 32 < p.N && !CDR_DBG(p, 1)) {
+          gemm_epilogue_chunk<EPIM>(pe, r0, stg, lane, mb, n0 + c0 * 32, aux[b], dc);
           if constexpr (CPW >= 2) {
-            if (n0 + c1 * 32 < p.N) gemm_epilogue_chunk<EPIM>(pe, r1, stg, lane, mb, n0 + c1 * 32, aux[b + 1 < CPW ? b + 1 : b]);
+            if (n0 + c1 * 32 < p.N) gemm_epilogue_chunk<EPIM>(pe, r1, stg, lane, mb, n0 + c1 * 32, aux[b + 1 < CPW ? b + 1 : b], dc);
           }
         }
       }

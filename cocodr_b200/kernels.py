@@ -8,8 +8,8 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_DGELU, EPI_F32_ATOMIC, EPI_F32_STORE,  # noqa: F401
-                   EPI_STORE_F16, check, ptr, stream_ptr)
+from ._lib import (EPI_BIAS_DROP_RESIDUAL, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_DGELU, EPI_F32_ATOMIC,  # noqa: F401
+                   EPI_F32_STORE, EPI_STORE_F16, check, ptr, stream_ptr)
 
 
 # ---- instrumentation used by bench.py: kernel-launch counter and optional per-GEMM CUDA-event timing
@@ -38,6 +38,16 @@ def _run(name, call):
     check(rc, name)
 
 
+def drop_args(state, site, p, row_mul=1):
+    """cdr_dropout descriptor: ``state`` = int64 device tensor {seed, offset}; keep iff u16 >= round(p * 65536)."""
+    assert state.is_cuda and state.dtype == torch.int64 and state.numel() == 2 and state.is_contiguous()
+    assert 0.0 < p < 1.0
+    d = _lib.Dropout()
+    d.state, d.site, d.threshold, d.scale, d.row_mul = state.data_ptr(), site, int(round(p * 65536.0)), 1.0 / (1.0 - p), row_mul
+    assert 0 < d.threshold < 65536
+    return d
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -46,8 +56,9 @@ def _need_cuda(*ts):
 
 def gemm(a, b, out, *, M, N, K, a_major=0, b_major=0, epilogue=EPI_STORE_F16, bias=None, aux=None, out2=None,
          alpha=1.0, split_k=1, lda=None, ldb=None, ldo=None, ldaux=None, dbg_lbo=0, dbg_sbo=0, colsum=None,
-         colsum_scale=1.0):
-    """out[M,N] = alpha * A[M,K] @ B[N,K]^T with a fused epilogue (see include/cocodr_b200.h)."""
+         colsum_scale=1.0, drop=None):
+    """out[M,N] = alpha * A[M,K] @ B[N,K]^T with a fused epilogue (see include/cocodr_b200.h).
+    ``drop`` (a drop_args descriptor) goes with EPI_BIAS_DROP_RESIDUAL."""
     _need_cuda(a, b, out)
     assert a.dtype == torch.float16 and b.dtype == torch.float16
     g = _lib.GemmArgs()
@@ -64,6 +75,8 @@ def gemm(a, b, out, *, M, N, K, a_major=0, b_major=0, epilogue=EPI_STORE_F16, bi
     g.dbg_lbo, g.dbg_sbo = dbg_lbo, dbg_sbo
     g.colsum = colsum.data_ptr() if colsum is not None else 0
     g.colsum_scale = colsum_scale
+    if drop is not None:
+        g.drop = drop
     if bias is not None:
         assert bias.dtype == torch.float32
     if gemm_events is not None:
@@ -190,6 +203,28 @@ def ln_bwd(dy, dy_cls, x, gamma, mean, rstd, dx, dgamma, dbeta, dbias, *, n_seq,
     _count(2 if (not staged and row_ws is not None and dy is not None and dy_cls is None) else 1)
 
 
+def ln_bwd_drop(dy, x, gamma, mean, rstd, dx, dx_drop, dgamma, dbeta, dbias, *, rows, hidden, out_scale, drop):
+    """LayerNorm backward after a dropped dense output: dx (residual branch), dx_drop = dropout'(dx) and
+    dbias += out_scale * colsum(dx_drop) in one staged pass (cdr_ln_bwd_drop)."""
+    _need_cuda(dy, x, dx, dx_drop)
+    assert dy.dtype == torch.float16 and dy.is_contiguous() and x.is_contiguous()
+    _run("cdr_ln_bwd_drop", lambda: _lib_().cdr_ln_bwd_drop(
+        _p(dy), _p(x), _p(gamma), _p(mean), _p(rstd), _p(dx), _p(dx_drop), _p(dgamma), _p(dbeta), _p(dbias), _i32(rows),
+        _i32(hidden), _f32(out_scale), C.byref(drop), stream_ptr()))
+    _count(1)
+
+
+def dropout_f16(x, out, *, drop):
+    """out = dropout(x) for a contiguous fp16 [rows, cols] tensor (may alias)."""
+    _need_cuda(x, out)
+    assert x.dtype == torch.float16 and out.dtype == torch.float16 and x.is_contiguous() and out.is_contiguous()
+    assert x.dim() == 2 and x.shape == out.shape
+    _run("cdr_dropout_f16", lambda: _lib_().cdr_dropout_f16(_p(x), _p(out), _i64(x.shape[0]), _i32(x.shape[1]),
+                                                           C.byref(drop), stream_ptr()))
+    _count(1)
+    return out
+
+
 def colsum(x, out, *, rows, cols, ld=None, scale=1.0):
     _need_cuda(x, out)
     assert x.dtype == torch.float16 and out.dtype == torch.float32
@@ -234,16 +269,19 @@ def _attn_args(qkv, key_bias, out, lse, n_seq, seq_len, heads, scale, d_out=None
     return a
 
 
-def attn_fwd(qkv, key_bias, out, lse, *, n_seq, seq_len, heads, scale=0.125):
+def attn_fwd(qkv, key_bias, out, lse, *, n_seq, seq_len, heads, scale=0.125, drop=None):
     _need_cuda(qkv, out, lse)
     assert qkv.dtype == torch.float16 and out.dtype == torch.float16 and lse.dtype == torch.float32
     assert qkv.is_contiguous() and out.is_contiguous()
     a = _attn_args(qkv, key_bias, out, lse, n_seq, seq_len, heads, scale)
+    if drop is not None:
+        a.drop = drop
     _run("cdr_attn_fwd", lambda: _lib_().cdr_attn_fwd(C.byref(a), stream_ptr()))
     _count(1)
 
 
-def attn_bwd(qkv, key_bias, out, lse, d_out, dqkv, *, n_seq, seq_len, heads, scale=0.125, dbias=None, dbias_scale=1.0):
+def attn_bwd(qkv, key_bias, out, lse, d_out, dqkv, *, n_seq, seq_len, heads, scale=0.125, dbias=None, dbias_scale=1.0,
+             drop=None):
     """dbias (optional fp32 [3*heads*64], seq_len <= 128): += dbias_scale * column sums of dqkv, fused."""
     _need_cuda(qkv, out, lse, d_out, dqkv)
     assert d_out.dtype == torch.float16 and dqkv.dtype == torch.float16 and d_out.is_contiguous()
@@ -251,6 +289,8 @@ def attn_bwd(qkv, key_bias, out, lse, d_out, dqkv, *, n_seq, seq_len, heads, sca
     if seq_len > 128:  # tiled backward: key tiles add their dQ shares in an fp32 scratch
         dq_ws = torch.empty(n_seq * seq_len, heads * 64, dtype=torch.float32, device=qkv.device)
     a = _attn_args(qkv, key_bias, out, lse, n_seq, seq_len, heads, scale, d_out, dqkv, dq_ws)
+    if drop is not None:
+        a.drop = drop
     if dbias is not None:
         assert dbias.dtype == torch.float32 and dbias.numel() == 3 * heads * 64
         a.dbias_qkv, a.dbias_scale = dbias.data_ptr(), dbias_scale

@@ -59,8 +59,11 @@ class CondenserForPretraining(nn.Module):
         h = torch.where(is_cls, last, skip)
         kb = key_bias_from_mask(model_input.get('attention_mask'))
         cfg = self.lm.config
-        for layer, shadow in zip(self.c_head, self._c_shadows):
-            h = run_layer(layer, shadow, h, kb, n_seq, L, cfg)
+        # the head layers are ordinary BertLayers of THIS module: they drop in train() mode even though the reference
+        # puts the backbone in eval() (COCO/modeling.py:198, 216-220); their sites continue the backbone's numbering
+        drop = self._backbone().dropout_spec(self.training, ids.device)
+        for i, (layer, shadow) in enumerate(zip(self.c_head, self._c_shadows)):
+            h = run_layer(layer, shadow, h, kb, n_seq, L, cfg, drop=drop, layer_index=cfg.num_hidden_layers + i)
         return h
 
     def _mlm_rows(self, labels):

@@ -10,6 +10,8 @@ parameters, biases and parameter gradients; the CLS embedding leaves the last La
 power-of-two ``grad_scale`` (they would underflow otherwise); every parameter gradient is divided by it
 again inside the producing kernel (GEMM alpha / LN out_scale), so callers only ever see true gradients.
 """
+from collections import namedtuple
+
 import torch
 
 from . import kernels as K
@@ -19,6 +21,47 @@ FORCE_SHADOW_REFRESH = False  # set while a CUDA graph is being captured (graph.
 GRAD_SYNC = None              # an active gradsync.GradSync collects the flat gradient buffers of each backward
 CLS_PUSH = None               # (peer.PeerExchange, first_seq): the last LayerNorm pushes CLS rows to every rank (peer.py)
 GROUP_CAPTURE = None          # a GroupCapture: layer backwards also hand over their wgrad operands (dro_loss.py, K11)
+
+
+# Dropout of one encoder pass: ``state`` = int64 device tensor {seed, offset} (a snapshot taken by the pass, so the
+# backward regenerates the forward's masks whatever ran in between), p_hidden / p_attn = HF's hidden_dropout_prob /
+# attention_probs_dropout_prob.  Sites: 0 embeddings; layer l: 4l + 1 attention probabilities, 4l + 2 attention-output
+# dense, 4l + 3 FFN-output dense (include/cocodr_b200.h cdr_dropout; oracle/dropout_ref.py regenerates the same masks).
+DropSpec = namedtuple("DropSpec", "state p_hidden p_attn")
+
+
+def _site(drop, layer_index, which, row_mul=1):
+    """cdr_dropout descriptor of site ``which`` (1 attention probs, 2 attention-output dense, 3 FFN-output dense, 0 with
+    layer_index 0 = embeddings), or None when that dropout is off."""
+    if drop is None:
+        return None
+    p = drop.p_attn if which == 1 else drop.p_hidden
+    if p <= 0.0:
+        return None
+    return K.drop_args(drop.state, 4 * layer_index + which, p, row_mul)
+
+
+def _ln_bwd_after_dropout(dy, dcls, y, gamma, mean, rstd, dgamma, dbeta, dbias, *, n_seq, seq_len, S, site, row_ws=None):
+    """LayerNorm backward where the LN input was x + dropout(d): -> (dx, dx_drop); dbias += colsum(dx_drop) / S.
+    One staged kernel when the fast path applies (fp16 dy only), else LN backward + mask + column sum."""
+    rows, H = y.shape
+    dev = y.device
+    inv = 1.0 / S
+    dx = _f16(rows, H, dev=dev)
+    if site is None:
+        K.ln_bwd(dy, dcls, y, gamma, mean, rstd, dx, dgamma, dbeta, dbias, n_seq=n_seq, seq_len=seq_len, hidden=H,
+                 in_scale=S, out_scale=inv, row_ws=row_ws)
+        return dx, dx
+    dxm = _f16(rows, H, dev=dev)
+    if dy is not None and dcls is None and H <= 1024:
+        K.ln_bwd_drop(dy, y, gamma, mean, rstd, dx, dxm, dgamma, dbeta, dbias, rows=rows, hidden=H, out_scale=inv,
+                      drop=site)
+    else:
+        K.ln_bwd(dy, dcls, y, gamma, mean, rstd, dx, dgamma, dbeta, None, n_seq=n_seq, seq_len=seq_len, hidden=H,
+                 in_scale=S, out_scale=inv, row_ws=row_ws)
+        K.dropout_f16(dx, dxm, drop=site)
+        K.colsum(dxm, dbias, rows=rows, cols=H, scale=inv)
+    return dx, dxm
 
 
 class GroupCapture:
@@ -148,7 +191,7 @@ class EmbedLN(torch.autograd.Function):
     """K1: LayerNorm(word[ids] + pos[0:L] + type[0]) -> fp16 [n_seq*L, H]  (HF BertEmbeddings)."""
 
     @staticmethod
-    def forward(ctx, ids, word, pos, typ, gamma, beta, eps):
+    def forward(ctx, ids, word, pos, typ, gamma, beta, eps, drop=None):
         n_seq, L = ids.shape
         H = word.shape[1]
         dev = word.device
@@ -157,6 +200,10 @@ class EmbedLN(torch.autograd.Function):
         mean, rstd = _f32(n_seq * L, dev=dev), _f32(n_seq * L, dev=dev)
         K.embed_ln_fwd(ids, word, pos, typ, gamma, beta, out, mean, rstd, n_seq=n_seq, seq_len=L, hidden=H,
                        vocab=word.shape[0], eps=eps)
+        ctx.drop = _site(drop, 0, 0)
+        ctx.drop_state = drop.state if ctx.drop is not None else None  # keeps the device state alive
+        if ctx.drop is not None:  # HF BertEmbeddings: dropout(LayerNorm(...))
+            K.dropout_f16(out, out, drop=ctx.drop)
         ctx.save_for_backward(ids, word, pos, typ, gamma, mean, rstd)
         ctx.eps = eps
         ctx.scale = _GRAD_SCALE
@@ -176,12 +223,15 @@ class EmbedLN(torch.autograd.Function):
             off += n
         dword, dpos, dtyp = views[0].view_as(word), views[1].view_as(pos), views[2].view_as(typ)
         dgamma, dbeta = views[3], views[4]
-        K.embed_ln_bwd(dy.contiguous(), ids, word, pos, typ, gamma, mean, rstd, dword, dpos, dtyp, dgamma, dbeta,
+        dy = dy.contiguous()
+        if ctx.drop is not None:
+            dy = K.dropout_f16(dy, torch.empty_like(dy), drop=ctx.drop)
+        K.embed_ln_bwd(dy, ids, word, pos, typ, gamma, mean, rstd, dword, dpos, dtyp, dgamma, dbeta,
                        n_seq=n_seq, seq_len=L, hidden=H, vocab=word.shape[0], pad_id=0, in_scale=1.0,
                        out_scale=1.0 / ctx.scale)
         if GRAD_SYNC is not None:
             GRAD_SYNC.submit(flat)
-        return None, dword, dpos, dtyp, dgamma, dbeta, None
+        return None, dword, dpos, dtyp, dgamma, dbeta, None, None
 
 
 class BertLayerFn(torch.autograd.Function):
@@ -193,26 +243,29 @@ class BertLayerFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, key_bias, wq, bq, wk, bk, wv, bv, wo, bo, g1, be1, wi, bi, wo2, bo2, g2, be2, shadow, n_seq,
-                L, heads, eps, emit_cls):
+                L, heads, eps, emit_cls, drop=None, layer_index=0):
         T, H = x.shape
         I = wi.shape[0]
         dev = x.device
         sh = shadow.refresh(wq, bq, wk, bk, wv, bv, wo, wi, wo2)
         x = x.contiguous()
+        da, db, dc = (_site(drop, layer_index, w) for w in (1, 2, 3))
         qkv = _f16(T, 3 * H, dev=dev)
         K.gemm(x, sh.wqkv, qkv, M=T, N=3 * H, K=H, bias=sh.bqkv)
         att = _f16(T, H, dev=dev)
         lse = _f32(n_seq, heads, L, dev=dev)
-        K.attn_fwd(qkv, key_bias, att, lse, n_seq=n_seq, seq_len=L, heads=heads)
-        y1 = _f16(T, H, dev=dev)  # x + attn_out, pre-LayerNorm
-        K.gemm(att, sh.wo, y1, M=T, N=H, K=H, bias=bo, epilogue=K.EPI_BIAS_RESIDUAL, aux=x)
+        K.attn_fwd(qkv, key_bias, att, lse, n_seq=n_seq, seq_len=L, heads=heads, drop=da)
+        y1 = _f16(T, H, dev=dev)  # x + dropout(attn_out), pre-LayerNorm
+        K.gemm(att, sh.wo, y1, M=T, N=H, K=H, bias=bo, aux=x, drop=db,
+               epilogue=K.EPI_BIAS_RESIDUAL if db is None else K.EPI_BIAS_DROP_RESIDUAL)
         x1 = _f16(T, H, dev=dev)
         mean1, rstd1 = _f32(T, dev=dev), _f32(T, dev=dev)
         K.ln_fwd(y1, g1, be1, x1, mean1, rstd1, None, n_seq=n_seq, seq_len=L, hidden=H, eps=eps)
         gp, gl = _f16(T, I, dev=dev), _f16(T, I, dev=dev)  # gelu'(z) (saved for the backward), gelu(z)
         K.gemm(x1, sh.wi, gl, M=T, N=I, K=H, bias=bi, epilogue=K.EPI_BIAS_GELU, out2=gp)
         y2 = _f16(T, H, dev=dev)
-        K.gemm(gl, sh.wo2, y2, M=T, N=H, K=I, bias=bo2, epilogue=K.EPI_BIAS_RESIDUAL, aux=x1)
+        K.gemm(gl, sh.wo2, y2, M=T, N=H, K=I, bias=bo2, aux=x1, drop=dc,
+               epilogue=K.EPI_BIAS_RESIDUAL if dc is None else K.EPI_BIAS_DROP_RESIDUAL)
         y = _f16(T, H, dev=dev)
         mean2, rstd2 = _f32(T, dev=dev), _f32(T, dev=dev)
         cls = _f32(n_seq, H, dev=dev) if emit_cls else None
@@ -220,6 +273,7 @@ class BertLayerFn(torch.autograd.Function):
         K.ln_fwd(y2, g2, be2, y, mean2, rstd2, cls, n_seq=n_seq, seq_len=L, hidden=H, eps=eps, push=push)
         ctx.save_for_backward(x, key_bias, qkv, att, lse, y1, x1, mean1, rstd1, gp, gl, y2, mean2, rstd2, g1, g2)
         ctx.shadow_w = (sh.wqkv, sh.wo, sh.wi, sh.wo2)
+        ctx.drop = (da, db, dc, drop.state if drop is not None else None)
         ctx.meta = (n_seq, L, heads, I, emit_cls, _GRAD_SCALE)
         ctx.param_keys = tuple(id(t) for t in (wq, bq, wk, bk, wv, bv, wo, bo, g1, be1, wi, bi, wo2, bo2, g2, be2))
         ctx.set_materialize_grads(False)
@@ -249,31 +303,31 @@ class BertLayerFn(torch.autograd.Function):
         dg2, dbe2, dbo2, dwo2, dbi, dwi, dg1, dbe1, dbo, dwo, dwqkv, dbqkv = views
         dwo2, dwi, dwo, dwqkv = dwo2.view(H, I), dwi.view(I, H), dwo.view(H, H), dwqkv.view(3 * H, H)
         row_ws = _f32(2 * T, dev=dev)
-        # ---- output LayerNorm; column sums of its dx are the FFN-down bias gradient
-        dy2 = _f16(T, H, dev=dev)
-        K.ln_bwd(dy, dcls, y2, g2, mean2, rstd2, dy2, dg2, dbe2, dbo2, n_seq=n_seq, seq_len=L, hidden=H, in_scale=S,
-                 out_scale=inv, row_ws=row_ws)
-        # ---- FFN down: dZ = (dy2 W2) * gelu'(z) with db1 = colsum(dZ) fused into the epilogue, dW2 = dy2^T G
+        da, db, dc, _ = ctx.drop
+        # ---- output LayerNorm; column sums of its (dropped) dx are the FFN-down bias gradient.  dy2 = gradient of the
+        # residual branch, dy2m = dropout'(dy2) = gradient of the dense output (same tensor without dropout)
+        dy2, dy2m = _ln_bwd_after_dropout(dy, dcls, y2, g2, mean2, rstd2, dg2, dbe2, dbo2, n_seq=n_seq, seq_len=L, S=S,
+                                          site=dc, row_ws=row_ws)
+        # ---- FFN down: dZ = (dy2m W2) * gelu'(z) with db1 = colsum(dZ) fused into the epilogue, dW2 = dy2m^T G
         dz = _f16(T, I, dev=dev)
-        K.gemm(dy2, wo2, dz, M=T, N=I, K=H, b_major=1, epilogue=K.EPI_DGELU, aux=gp, colsum=dbi, colsum_scale=inv)
-        K.gemm(dy2, gl, dwo2, M=H, N=I, K=T, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0, alpha=inv)
+        K.gemm(dy2m, wo2, dz, M=T, N=I, K=H, b_major=1, epilogue=K.EPI_DGELU, aux=gp, colsum=dbi, colsum_scale=inv)
+        K.gemm(dy2m, gl, dwo2, M=H, N=I, K=T, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0, alpha=inv)
         # ---- FFN up: dx1 = dZ W1 + dy2 (residual), dW1 = dZ^T x1
         dx1 = _f16(T, H, dev=dev)
         K.gemm(dz, wi, dx1, M=T, N=H, K=I, b_major=1, epilogue=K.EPI_BIAS_RESIDUAL, aux=dy2)
         K.gemm(dz, x1, dwi, M=I, N=H, K=T, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0, alpha=inv)
         # ---- attention-output LayerNorm
-        dy1 = _f16(T, H, dev=dev)
-        K.ln_bwd(dx1, None, y1, g1, mean1, rstd1, dy1, dg1, dbe1, dbo, n_seq=n_seq, seq_len=L, hidden=H, in_scale=S,
-                 out_scale=inv, row_ws=row_ws)
+        dy1, dy1m = _ln_bwd_after_dropout(dx1, None, y1, g1, mean1, rstd1, dg1, dbe1, dbo, n_seq=n_seq, seq_len=L, S=S,
+                                          site=db, row_ws=row_ws)
         # ---- attention output projection
         datt = _f16(T, H, dev=dev)
-        K.gemm(dy1, wo, datt, M=T, N=H, K=H, b_major=1)
-        K.gemm(dy1, att, dwo, M=H, N=H, K=T, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0, alpha=inv)
+        K.gemm(dy1m, wo, datt, M=T, N=H, K=H, b_major=1)
+        K.gemm(dy1m, att, dwo, M=H, N=H, K=T, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0, alpha=inv)
         # ---- attention core
         dqkv = _f16(T, 3 * H, dev=dev)
         fused_db = L <= 128  # the one-tile backward also emits the QKV bias gradient (column sums of dQKV)
         K.attn_bwd(qkv, key_bias, att, lse, datt, dqkv, n_seq=n_seq, seq_len=L, heads=heads,
-                   dbias=dbqkv if fused_db else None, dbias_scale=inv)
+                   dbias=dbqkv if fused_db else None, dbias_scale=inv, drop=da)
         # ---- QKV projection: dx = dQKV Wqkv + dy1 (residual)
         dx = None
         if ctx.needs_input_grad[0]:
@@ -287,11 +341,11 @@ class BertLayerFn(torch.autograd.Function):
             GRAD_SYNC.submit(flat)
         if GROUP_CAPTURE is not None:
             GROUP_CAPTURE.records.append(dict(
-                keys=ctx.param_keys, rps=L, L=L, n_seq=n_seq, S=S, dy2=dy2, gl=gl, dz=dz, x1=x1, dy1=dy1, att=att,
+                keys=ctx.param_keys, rps=L, L=L, n_seq=n_seq, S=S, dy2=dy2m, gl=gl, dz=dz, x1=x1, dy1=dy1m, att=att,
                 dx1=dx1, y1=y1, mean1=mean1, rstd1=rstd1, y2=y2, mean2=mean2, rstd2=rstd2, din2=(dy, dcls), dqkv=dqkv,
                 x=x))
         return (dx, None, dwqkv[0:H], dbqkv[0:H], dwqkv[H:2 * H], dbqkv[H:2 * H], dwqkv[2 * H:], dbqkv[2 * H:], dwo,
-                dbo, dg1, dbe1, dwi, dbi, dwo2, dbo2, dg2, dbe2, None, None, None, None, None, None)
+                dbo, dg1, dbe1, dwi, dbi, dwo2, dbo2, dg2, dbe2, None, None, None, None, None, None, None, None)
 
 
 class BertLastLayerCLSFn(torch.autograd.Function):
@@ -307,27 +361,32 @@ class BertLastLayerCLSFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, key_bias, wq, bq, wk, bk, wv, bv, wo, bo, g1, be1, wi, bi, wo2, bo2, g2, be2, shadow, n_seq,
-                L, heads, eps):
+                L, heads, eps, drop=None, layer_index=0):
         T, H = x.shape
         I = wi.shape[0]
         dev = x.device
         sh = shadow.refresh(wq, bq, wk, bk, wv, bv, wo, wi, wo2)
         x = x.contiguous()
+        # the dense-output masks are those of the full layer: [CLS] row of sequence s is row s * L of the [T, H] tensor
+        da = _site(drop, layer_index, 1)
+        db, dc = _site(drop, layer_index, 2, row_mul=L), _site(drop, layer_index, 3, row_mul=L)
         qkv = _f16(T, 3 * H, dev=dev)
         K.gemm(x, sh.wqkv, qkv, M=T, N=3 * H, K=H, bias=sh.bqkv)
         att = _f16(T, H, dev=dev)
         lse = _f32(n_seq, heads, L, dev=dev)
-        K.attn_fwd(qkv, key_bias, att, lse, n_seq=n_seq, seq_len=L, heads=heads)
+        K.attn_fwd(qkv, key_bias, att, lse, n_seq=n_seq, seq_len=L, heads=heads, drop=da)
         xc, attc = x.view(n_seq, L, H)[:, 0], att.view(n_seq, L, H)[:, 0]  # [n_seq, H] views, row stride L * H
         y1 = _f16(n_seq, H, dev=dev)
-        K.gemm(attc, sh.wo, y1, M=n_seq, N=H, K=H, bias=bo, epilogue=K.EPI_BIAS_RESIDUAL, aux=xc)
+        K.gemm(attc, sh.wo, y1, M=n_seq, N=H, K=H, bias=bo, aux=xc, drop=db,
+               epilogue=K.EPI_BIAS_RESIDUAL if db is None else K.EPI_BIAS_DROP_RESIDUAL)
         x1 = _f16(n_seq, H, dev=dev)
         mean1, rstd1 = _f32(n_seq, dev=dev), _f32(n_seq, dev=dev)
         K.ln_fwd(y1, g1, be1, x1, mean1, rstd1, None, n_seq=n_seq, seq_len=1, hidden=H, eps=eps)
         gp, gl = _f16(n_seq, I, dev=dev), _f16(n_seq, I, dev=dev)
         K.gemm(x1, sh.wi, gl, M=n_seq, N=I, K=H, bias=bi, epilogue=K.EPI_BIAS_GELU, out2=gp)
         y2 = _f16(n_seq, H, dev=dev)
-        K.gemm(gl, sh.wo2, y2, M=n_seq, N=H, K=I, bias=bo2, epilogue=K.EPI_BIAS_RESIDUAL, aux=x1)
+        K.gemm(gl, sh.wo2, y2, M=n_seq, N=H, K=I, bias=bo2, aux=x1, drop=dc,
+               epilogue=K.EPI_BIAS_RESIDUAL if dc is None else K.EPI_BIAS_DROP_RESIDUAL)
         y = _f16(n_seq, H, dev=dev)
         mean2, rstd2 = _f32(n_seq, dev=dev), _f32(n_seq, dev=dev)
         cls = _f32(n_seq, H, dev=dev)
@@ -337,6 +396,7 @@ class BertLastLayerCLSFn(torch.autograd.Function):
         K.ln_fwd(y2, g2, be2, y, mean2, rstd2, cls, n_seq=n_seq, seq_len=1, hidden=H, eps=eps, push=push)
         ctx.save_for_backward(x, key_bias, qkv, att, lse, y1, x1, mean1, rstd1, gp, gl, y2, mean2, rstd2, g1, g2)
         ctx.shadow_w = (sh.wqkv, sh.wo, sh.wi, sh.wo2)
+        ctx.drop = (da, db, dc, drop.state if drop is not None else None)
         ctx.meta = (n_seq, L, heads, I, _GRAD_SCALE)
         ctx.param_keys = tuple(id(t) for t in (wq, bq, wk, bk, wv, bv, wo, bo, g1, be1, wi, bi, wo2, bo2, g2, be2))
         return cls
@@ -358,30 +418,29 @@ class BertLastLayerCLSFn(torch.autograd.Function):
             off += n
         dg2, dbe2, dbo2, dwo2, dbi, dwi, dg1, dbe1, dbo, dwo, dwqkv, dbqkv = views
         dwo2, dwi, dwo, dwqkv = dwo2.view(H, I), dwi.view(I, H), dwo.view(H, H), dwqkv.view(3 * H, H)
+        da, db, dc, _ = ctx.drop
         # ---- [CLS] rows only: output LayerNorm, FFN, attention-output LayerNorm and projection
-        dy2 = _f16(n_seq, H, dev=dev)
-        K.ln_bwd(None, dcls, y2, g2, mean2, rstd2, dy2, dg2, dbe2, dbo2, n_seq=n_seq, seq_len=1, hidden=H, in_scale=S,
-                 out_scale=inv)
+        dy2, dy2m = _ln_bwd_after_dropout(None, dcls, y2, g2, mean2, rstd2, dg2, dbe2, dbo2, n_seq=n_seq, seq_len=1, S=S,
+                                          site=dc)
         dz = _f16(n_seq, I, dev=dev)
-        K.gemm(dy2, wo2, dz, M=n_seq, N=I, K=H, b_major=1, epilogue=K.EPI_DGELU, aux=gp, colsum=dbi, colsum_scale=inv)
-        K.gemm(dy2, gl, dwo2, M=H, N=I, K=n_seq, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0, alpha=inv)
+        K.gemm(dy2m, wo2, dz, M=n_seq, N=I, K=H, b_major=1, epilogue=K.EPI_DGELU, aux=gp, colsum=dbi, colsum_scale=inv)
+        K.gemm(dy2m, gl, dwo2, M=H, N=I, K=n_seq, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0, alpha=inv)
         dx1 = _f16(n_seq, H, dev=dev)
         K.gemm(dz, wi, dx1, M=n_seq, N=H, K=I, b_major=1, epilogue=K.EPI_BIAS_RESIDUAL, aux=dy2)
         K.gemm(dz, x1, dwi, M=I, N=H, K=n_seq, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0, alpha=inv)
-        dy1 = _f16(n_seq, H, dev=dev)
-        K.ln_bwd(dx1, None, y1, g1, mean1, rstd1, dy1, dg1, dbe1, dbo, n_seq=n_seq, seq_len=1, hidden=H, in_scale=S,
-                 out_scale=inv, row_ws=_f32(2 * n_seq, dev=dev))
+        dy1, dy1m = _ln_bwd_after_dropout(dx1, None, y1, g1, mean1, rstd1, dg1, dbe1, dbo, n_seq=n_seq, seq_len=1, S=S,
+                                          site=db, row_ws=_f32(2 * n_seq, dev=dev))
         attc = att.view(n_seq, L, H)[:, 0]
         datt = torch.zeros(T, H, dtype=torch.float16, device=dev)  # d(ctx) is zero off the [CLS] rows
         dattc = _f16(n_seq, H, dev=dev)
-        K.gemm(dy1, wo, dattc, M=n_seq, N=H, K=H, b_major=1)
-        K.gemm(dy1, attc, dwo, M=H, N=H, K=n_seq, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0, alpha=inv)
+        K.gemm(dy1m, wo, dattc, M=n_seq, N=H, K=H, b_major=1)
+        K.gemm(dy1m, attc, dwo, M=H, N=H, K=n_seq, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0, alpha=inv)
         datt.view(n_seq, L, H)[:, 0].copy_(dattc)
         # ---- dense again from here: the [CLS] query attends to every key
         dqkv = _f16(T, 3 * H, dev=dev)
         fused_db = L <= 128
         K.attn_bwd(qkv, key_bias, att, lse, datt, dqkv, n_seq=n_seq, seq_len=L, heads=heads,
-                   dbias=dbqkv if fused_db else None, dbias_scale=inv)
+                   dbias=dbqkv if fused_db else None, dbias_scale=inv, drop=da)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = _f16(T, H, dev=dev)
@@ -398,11 +457,11 @@ class BertLastLayerCLSFn(torch.autograd.Function):
             GRAD_SYNC.submit(flat)
         if GROUP_CAPTURE is not None:  # rows of the post-attention operands are sequences here (one [CLS] row each)
             GROUP_CAPTURE.records.append(dict(
-                keys=ctx.param_keys, rps=1, L=L, n_seq=n_seq, S=S, dy2=dy2, gl=gl, dz=dz, x1=x1, dy1=dy1,
+                keys=ctx.param_keys, rps=1, L=L, n_seq=n_seq, S=S, dy2=dy2m, gl=gl, dz=dz, x1=x1, dy1=dy1m,
                 att=attc.contiguous(), dx1=dx1, y1=y1, mean1=mean1, rstd1=rstd1, y2=y2, mean2=mean2, rstd2=rstd2,
                 din2=(None, dcls), dqkv=dqkv, x=x))
         return (dx, None, dwqkv[0:H], dbqkv[0:H], dwqkv[H:2 * H], dbqkv[H:2 * H], dwqkv[2 * H:], dbqkv[2 * H:], dwo,
-                dbo, dg1, dbe1, dwi, dbi, dwo2, dbo2, dg2, dbe2, None, None, None, None, None)
+                dbo, dg1, dbe1, dwi, dbi, dwo2, dbo2, dg2, dbe2, None, None, None, None, None, None, None)
 
 
 class HiddenToFloat(torch.autograd.Function):

@@ -35,6 +35,30 @@ int cdr_device_check(void);
 int cdr_set_sm_budget(int32_t n);
 
 /* ------------------------------------------------------------------------------------------------
+ * Counter-based dropout.  Replaces the nn.Dropout modules of HF BERT that the reference trains with (p = 0.1 on the
+ * embeddings, on the attention probabilities and on both dense outputs of every layer: BertEmbeddings,
+ * BertSelfAttention, BertSelfOutput, BertOutput reached through self.bert(...) in ANCE/model/models.py:226 under
+ * model.train(), ANCE/drivers/run_ann.py:320; COCO/modeling.py:216-220 for the c_head layers).  No mask is stored:
+ * forward and backward kernels regenerate it with Philox4x32-10 from
+ *     counter = (group index, site, offset lo, offset hi), key = (seed lo, seed hi)
+ * where one call covers a group of 8 consecutive elements of a row (8 x 16 random bits); element j is kept iff its
+ * 16 bits are >= threshold (= round(p * 65536)) and kept values are multiplied by `scale` (= 1 / (1 - p)).
+ * Group index of element (m, n) of a [rows, cols] activation: (m * row_mul) * (cols / 8) + n / 8; of attention
+ * probability (seq, head, query row r, key c): ((seq * heads + head) * seq_len + r) * 64 + c / 8.
+ * `state` is a DEVICE array {seed, offset} read by the kernels (the step counter advances on the device, so a CUDA
+ * graph replays with fresh masks); state == NULL or threshold == 0 disables dropout.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct cdr_dropout {
+  const uint64_t* state; /* device {seed, offset}, or NULL */
+  uint32_t site;         /* which dropout module (distinct per layer and position) */
+  uint32_t threshold;    /* 0 .. 65535 */
+  float scale;
+  int32_t row_mul;       /* >= 1 (0 is read as 1) */
+} cdr_dropout;
+/* out[m, :] = dropout(x[m, :]) on a contiguous fp16 [rows, cols] tensor (cols % 8 == 0); out may alias x. */
+int cdr_dropout_f16(const void* x, void* out, int64_t rows, int32_t cols, const cdr_dropout* drop, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * GEMM   D[M,N] = alpha * A[M,K] * B[N,K]^T  (+ fused epilogue), fp16 operands, fp32 accumulate.
  * Replaces the nn.Linear / torch.matmul calls inside HF BertLayer that the reference reaches through
  * self.bert(...) (ANCE/model/models.py:226, COCO/modeling.py:199-204) and their autograd backward.
@@ -54,7 +78,8 @@ enum {
   CDR_EPI_F32_STORE = 5,     /* out32 = alpha*acc                                                 */
   CDR_EPI_SCAN_FILTER = 6,   /* internal: threshold-filter scores into candidate buffers (docs on M, queries on N) */
   CDR_EPI_SCAN_FILTER_Q = 7, /* internal: the same with queries on M (<= 128 queries: documents stream as the B operand) */
-  CDR_EPI_F32_GROUPED = 8    /* internal (cdr_gemm_grouped): F32_ATOMIC with per-group K ranges and output bases */
+  CDR_EPI_F32_GROUPED = 8,   /* internal (cdr_gemm_grouped): F32_ATOMIC with per-group K ranges and output bases */
+  CDR_EPI_BIAS_DROP_RESIDUAL = 9 /* out16 = dropout(alpha*acc + bias) + aux[m,n]   (args.drop; HF BertSelfOutput / BertOutput) */
 };
 
 typedef struct cdr_gemm_args {
@@ -70,10 +95,11 @@ typedef struct cdr_gemm_args {
   int32_t epilogue;
   int32_t split_k; /* 0 = auto (wgrad), 1 = none */
   float alpha;
-  int32_t dbg_lbo, dbg_sbo; /* 0; test-only descriptor overrides */
+  int32_t dbg_lbo, dbg_sbo; /* 0; descriptor overrides honoured only by -DCDR_GEMM_DEBUG builds (tools/build_variant.sh) */
   float* colsum;      /* optional fp32 [N], CDR_EPI_DGELU only: accumulates the column sums of the output */
   float colsum_scale;
   int32_t reserved;
+  cdr_dropout drop;   /* CDR_EPI_BIAS_DROP_RESIDUAL only */
 } cdr_gemm_args;
 
 int cdr_gemm(const cdr_gemm_args* args, void* stream);
@@ -112,6 +138,13 @@ int cdr_embed_ln_bwd(const void* dy, const int64_t* ids, const float* word, cons
  * ANCE/model/models.py:228, COCO/modeling.py:206) */
 int cdr_ln_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, float* cls_out,
                int32_t n_seq, int32_t seq_len, int32_t hidden, float eps, void* stream);
+/* cdr_ln_bwd (below) for the LayerNorm that follows a dropped dense output y = x + dropout(d): besides dx (the
+ * gradient of the residual branch) it writes dx_drop = dropout'(dx) -- the operand of the dense layer's dgrad / wgrad
+ * GEMMs, mask regenerated from `drop` -- and dbias += out_scale * column sums of dx_drop.  Staged path only: fp16 dy,
+ * hidden <= 1024, 16-byte aligned operands (CDR_EINVAL otherwise). */
+int cdr_ln_bwd_drop(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, void* dx,
+                    void* dx_drop, float* dgamma, float* dbeta, float* dbias, int32_t rows, int32_t hidden,
+                    float out_scale, const cdr_dropout* drop, void* stream);
 /* dx = LN'(dy [+ in_scale * dy_cls on row 0 of every sequence]); dbias (optional) += column sums of dx.
  * dy (fp16) is already in the scaled-gradient domain; dy_cls (fp32) enters it through in_scale. */
 /* row_ws: optional scratch of 2*n_seq*seq_len floats; when given (and dy_cls is NULL) the backward runs as two
@@ -222,7 +255,7 @@ int cdr_grad_clip_coef(const float* sq, float max_norm, float* coef, float* norm
  * Fused multi-head attention (K3): softmax(Q K^T * scale + key_bias) V on tcgen05, head_dim 64,
  * seq_len <= 512 (one 128 x 128 tile up to 128, tiled above), straight from / to the packed QKV projection.  Replaces HF
  * eager_attention_forward / SDPA inside BertSelfAttention (reached through ANCE/model/models.py:226,
- * COCO/modeling.py:199-204); dropout p = 0.
+ * COCO/modeling.py:199-204), including the dropout of the attention probabilities (args.drop).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct cdr_attn_args {
   const void* qkv;       /* fp16 [n_seq*seq_len, 3*heads*64]  (Q | K | V) */
@@ -236,6 +269,7 @@ typedef struct cdr_attn_args {
   float scale;
   float dbias_scale;     /* bwd, seq_len <= 128: multiplies the column sums below */
   float* dbias_qkv;      /* bwd, optional fp32 [3*heads*64]: += dbias_scale * column sums of dqkv (QKV bias gradient) */
+  cdr_dropout drop;      /* dropout of the attention probabilities (after the softmax, HF BertSelfAttention) */
 } cdr_attn_args;
 int cdr_attn_fwd(const cdr_attn_args* args, void* stream);
 int cdr_attn_bwd(const cdr_attn_args* args, void* stream);

@@ -12,7 +12,10 @@ arithmetic restated here follows the installed transformers 5.5.0
   BertSelfOutput.forward            :287-298  LN(x + dense(ctx))
   BertIntermediate.forward          :330-342  gelu_erf(dense(x))
   BertOutput.forward                :345-356  LN(x + dense(h))
-Dropout is the identity here (parity runs use p = 0 / eval mode).
+Dropout: every function takes an optional ``drop`` (``oracle.dropout_ref.DropSpec``): the four nn.Dropout sites
+(embeddings :110, attention probabilities :133, BertSelfOutput :296, BertOutput :354) then multiply by the
+counter-based masks of ``oracle/dropout_ref.py`` -- the same masks the CUDA kernels regenerate -- so training-mode
+parity is exact in the mask and fp16-vs-fp32 in the arithmetic.  ``drop=None`` is eval mode / p = 0.
 
 All functions take a plain ``dict`` state (HF parameter names *without* the
 ``bert.`` prefix) so the same weights can be loaded into the reference, the
@@ -117,19 +120,25 @@ def gelu_erf(x):
     return 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))
 
 
-def embeddings_fwd(st, ids, cfg):
+def embeddings_fwd(st, ids, cfg, drop=None):
     L = ids.shape[1]
     H = cfg["hidden"]
     # nn.Embedding(padding_idx=pad_token_id=0): the pad row receives no gradient (:58)
     x = (F.embedding(ids, st["embeddings.word_embeddings.weight"], padding_idx=0)
          + st["embeddings.token_type_embeddings.weight"][0][None, None, :]
          + st["embeddings.position_embeddings.weight"][:L][None, :, :])
-    return F.layer_norm(x, (H,), st["embeddings.LayerNorm.weight"],
-                        st["embeddings.LayerNorm.bias"], LN_EPS)
+    x = F.layer_norm(x, (H,), st["embeddings.LayerNorm.weight"],
+                     st["embeddings.LayerNorm.bias"], LN_EPS)
+    if drop is not None:
+        m = drop.hidden(ids.shape[0] * L, H, 0)
+        if m is not None:
+            x = x * m.view(ids.shape[0], L, H)
+    return x
 
 
-def layer_fwd(st, prefix, x, add_mask, cfg):
-    """One BertLayer.  ``prefix`` e.g. 'encoder.layer.3.' or 'c_head.0.'."""
+def layer_fwd(st, prefix, x, add_mask, cfg, drop=None, layer_index=0):
+    """One BertLayer.  ``prefix`` e.g. 'encoder.layer.3.' or 'c_head.0.'; ``layer_index`` numbers the dropout sites
+    (4 * layer_index + 1 attention probabilities, + 2 attention output dense, + 3 FFN output dense)."""
     B, L, H = x.shape
     nh = cfg["heads"]
     d = H // nh
@@ -139,12 +148,25 @@ def layer_fwd(st, prefix, x, add_mask, cfg):
     v = lin(x, "attention.self.value").view(B, L, nh, d).transpose(1, 2)
     s = torch.matmul(q, k.transpose(2, 3)) * (d ** -0.5) + add_mask
     p = torch.softmax(s, dim=-1)
+    ma = mb = mc = None
+    if drop is not None:
+        ma = drop.attn(B, nh, L, 4 * layer_index + 1)
+        mb = drop.hidden(B * L, H, 4 * layer_index + 2)
+        mc = drop.hidden(B * L, H, 4 * layer_index + 3)
+    if ma is not None:
+        p = p * ma
     ctx = torch.matmul(p, v).transpose(1, 2).reshape(B, L, H)
-    x1 = F.layer_norm(x + lin(ctx, "attention.output.dense"), (H,),
+    so = lin(ctx, "attention.output.dense")
+    if mb is not None:
+        so = so * mb.view(B, L, H)
+    x1 = F.layer_norm(x + so, (H,),
                       st[prefix + "attention.output.LayerNorm.weight"],
                       st[prefix + "attention.output.LayerNorm.bias"], LN_EPS)
     h = gelu_erf(lin(x1, "intermediate.dense"))
-    x2 = F.layer_norm(x1 + lin(h, "output.dense"), (H,),
+    fo = lin(h, "output.dense")
+    if mc is not None:
+        fo = fo * mc.view(B, L, H)
+    x2 = F.layer_norm(x1 + fo, (H,),
                       st[prefix + "output.LayerNorm.weight"],
                       st[prefix + "output.LayerNorm.bias"], LN_EPS)
     return x2
@@ -155,20 +177,20 @@ def additive_mask(mask, dtype=torch.float32):
     return (1.0 - mask[:, None, None, :].to(dtype)) * torch.finfo(dtype).min
 
 
-def encoder_fwd(st, ids, mask, cfg, output_hidden_states: bool = False):
+def encoder_fwd(st, ids, mask, cfg, output_hidden_states: bool = False, drop=None):
     """Returns last hidden state [B,L,H] (and list of L+1 hidden states)."""
-    x = embeddings_fwd(st, ids, cfg)
+    x = embeddings_fwd(st, ids, cfg, drop)
     am = additive_mask(mask, x.dtype)
     hs = [x]
     for i in range(cfg["layers"]):
-        x = layer_fwd(st, f"encoder.layer.{i}.", x, am, cfg)
+        x = layer_fwd(st, f"encoder.layer.{i}.", x, am, cfg, drop, i)
         hs.append(x)
     return (x, hs) if output_hidden_states else x
 
 
-def cls_embedding(st, ids, mask, cfg):
+def cls_embedding(st, ids, mask, cfg, drop=None):
     """BertDot_NLL_LN.query_emb / body_emb: last_hidden[:, 0] (models.py:225-232)."""
-    return encoder_fwd(st, ids, mask, cfg)[:, 0]
+    return encoder_fwd(st, ids, mask, cfg, drop=drop)[:, 0]
 
 
 def mlm_head_fwd(st, hidden, cfg, prefix="cls.predictions."):

@@ -77,6 +77,17 @@ def test_bad_arguments_fail_loudly_without_a_gpu(lib):
     assert lib.cdr_gemm_grouped(C.byref(g), C.c_int32(0), C.c_void_p(16), C.c_int64(128 * 128), None) == -1
     assert lib.cdr_gemm_grouped(C.byref(g), C.c_int32(4), C.c_void_p(16), C.c_int64(130), None) == -1  # unaligned stride
     assert lib.cdr_gemm_segments(C.byref(g), C.c_int32(0), None, None, None, None) == 0  # nothing to do
+    # the dropout epilogue refuses to run without a counter state / with a degenerate threshold
+    g.a_major, g.b_major, g.epilogue, g.aux, g.ldaux = 0, 0, _lib.EPI_BIAS_DROP_RESIDUAL, 16, 128
+    assert lib.cdr_gemm(C.byref(g), None) == -1 and b"drop" in lib.cdr_last_error()
+    d = _lib.Dropout()
+    d.state, d.threshold = 16, 70000
+    assert lib.cdr_dropout_f16(C.c_void_p(16), C.c_void_p(16), C.c_int64(4), C.c_int32(64), C.byref(d), None) == -1
+    assert lib.cdr_dropout_f16(C.c_void_p(16), C.c_void_p(16), C.c_int64(4), C.c_int32(60), C.byref(d), None) == -1
+    d.threshold = 6554
+    assert lib.cdr_ln_bwd_drop(C.c_void_p(16), C.c_void_p(16), C.c_void_p(16), C.c_void_p(16), C.c_void_p(16),
+                               C.c_void_p(16), C.c_void_p(16), None, None, None, C.c_int32(8), C.c_int32(2048),
+                               C.c_float(1.0), C.byref(d), None) == -1
 
 
 def test_ctypes_structs_match_the_c_header(tmp_path):
@@ -91,7 +102,7 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
         pytest.skip("gcc not available")
     pairs = {"cdr_gemm_args": _lib.GemmArgs, "cdr_attn_args": _lib.AttnArgs, "cdr_simmat_args": _lib.SimmatArgs,
              "cdr_scan_args": _lib.ScanArgs, "cdr_opt_item": optim.OptItem, "cdr_opt_chunk": optim.OptChunk,
-             "cdr_opt_args": optim.OptArgs, "cdr_peer_args": peer.PeerArgs}
+             "cdr_opt_args": optim.OptArgs, "cdr_peer_args": peer.PeerArgs, "cdr_dropout": _lib.Dropout}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{_lib.HEADER}"', "int main(void) {"]
     for cname, cls in pairs.items():
         lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
