@@ -151,6 +151,18 @@ simmat_ce_grad_kernel(const float* __restrict__ S, const float* __restrict__ lse
   for (int j = threadIdx.x; j < n_keys; j += blockDim.x) out[j] = g * (expf(row[j] - l) - (j == t ? 1.f : 0.f));
 }
 
+// dk_own[i, :] = dloss[i] * (exp(-loss[i]) - 1) * q[i, :]   (softmax_i,own = exp(s_own - lse_i) = exp(-loss_i))
+__global__ void __launch_bounds__(128)
+own_key_grad_kernel(const float* __restrict__ q, const float* __restrict__ loss, const float* __restrict__ dloss, int n,
+                    int dim, float* __restrict__ dk) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const float c = dloss[i] * (expf(-loss[i]) - 1.f);
+  const long long o = static_cast<long long>(i) * dim;
+  for (int d = lane; d < dim; d += 32) dk[o + d] = c * q[o + d];
+}
+
 // ------------------------------------------------------------------------------ vocabulary CE (K14)
 // MLM head loss (HF BertForMaskedLM: CE(logits.view(-1, V), labels.view(-1)), COCO/modeling.py:87-93) on
 // the gathered masked rows only: logits[M, ld] fp32 straight from the decoder GEMM, bias[n_cols] fp32
@@ -402,6 +414,16 @@ int cdr_simmat_ce_bwd(const cdr_simmat_args* a, void* stream) {
   if (a->dk)  // dk[j,d] = sum_i G[i,j] q[i,d]
     if (int rc = sgemm(a->gmat, a->q, a->dk, a->n_keys, a->dim, a->n_rows, 1, a->n_keys, a->dim, 1, a->dim, 1.f, st))
       return rc;
+  return CDR_OK;
+}
+
+int cdr_simmat_own_key_grad(const float* q, const float* loss, const float* dloss, int32_t n, int32_t dim, float* dk_own,
+                            void* stream) {
+  CDR_REQUIRE(q && loss && dloss && dk_own, "cdr_simmat_own_key_grad: null pointer");
+  CDR_REQUIRE(n >= 0 && dim > 0, "cdr_simmat_own_key_grad: bad shape");
+  if (n == 0) return CDR_OK;
+  own_key_grad_kernel<<<(n + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(q, loss, dloss, n, dim, dk_own);
+  CDR_LAUNCH_CHECK();
   return CDR_OK;
 }
 

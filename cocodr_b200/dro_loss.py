@@ -395,11 +395,15 @@ class iDROLoss(DROGreedyLoss):
     # False = one cdr_gemm_segments wgrad per present group
     grouped_kernel = os.environ.get("CDR_IDRO_GROUPED_KERNEL", "1") == "1"
 
-    def forward(self, model, losses, g, sample_towers=0):
+    def forward(self, model, losses, g, sample_towers=0, grad_losses=None):
         """dro_loss.py:216-254 -> (robust_loss, group mean losses[G] detached, group counts[G]).
 
         ``sample_towers``: n > 0 promises that loss i depends on encoder sequences {i, i + B, ..} of ONE pass over
-        n * B sequences only (the triplet NLL), which lets ``_get_grad_grouped`` replace the per-group backwards."""
+        n * B sequences only (the triplet NLL), which lets ``_get_grad_grouped`` replace the per-group backwards.
+        ``grad_losses``: the same per-sample loss VALUES on a different autograd graph, used for the group gradients
+        only (the robust loss and the training gradient always come from ``losses``).  The in-batch head passes a view
+        whose graph contains no collective (per-group partial backwards must not issue rank-dependent collectives) --
+        see models.BertDot_InBatch_NLL_LN."""
         if not self.training:
             raise RuntimeError("iDROLoss.forward is only defined in training mode (as in the reference, where "
                                "gdro_counts_agg is undefined otherwise: dro_loss.py:222-226)")
@@ -409,10 +413,14 @@ class iDROLoss(DROGreedyLoss):
 
         mask = (counts > 0).float()
         params = self._params(model)
+        gmeans = means
+        if grad_losses is not None:
+            gsums, _ = ops.group_stats(grad_losses, g, self.n_groups)
+            gmeans = gsums / (counts + (counts == 0).float())
         if sample_towers and self.grouped_wgrad and len(params) > 0:
-            all_grads = self._get_grad_grouped(params, means, counts, g, sample_towers)
+            all_grads = self._get_grad_grouped(params, gmeans, counts, g, sample_towers)
         else:
-            all_grads = self._get_grad(params, means, counts)
+            all_grads = self._get_grad(params, gmeans, counts)
         gram = self._gram(all_grads)
         with torch.no_grad():
             norm = torch.sqrt(torch.diagonal(gram).clamp_min(0)).unsqueeze(-1)  # ||G_g||

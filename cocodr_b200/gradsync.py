@@ -11,6 +11,14 @@ layers i-1, i-2, ... -- no bucket copies, no unused-parameter search, one collec
         loss.backward()
     optimizer.step()           # the compute stream has waited for the last all-reduce
 
+Reducing a flat buffer IN PLACE while backward is still running is only sound when autograd adopts its views as the
+parameters' ``.grad`` and nothing adds to them afterwards.  That holds exactly when (a) the layer's Function ran once in
+the forward this backward belongs to and (b) none of its parameters has a gradient yet.  ``submit`` checks both (the
+forward counts come from ``ops.FWD_CALLS``); everything else -- the reference's default q_len != p_len (towers cannot be
+fused, every layer runs 2-3 times per backward), gradient accumulation over several backwards, the tied word
+embedding of the COCO model (MLM head + embedding table) -- is DEFERRED: those parameters' final ``.grad`` tensors are
+reduced in ``__exit__``, after backward has finished with them.
+
 ``DistributedDataParallel(model, find_unused_parameters=True)`` (what the reference's driver does,
 run_ann.py:178-184) keeps working on the same modules; this is the faster native path.
 """
@@ -24,57 +32,107 @@ class GradSync:
     def __init__(self, model, group=None):
         self.model, self.group = model, group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
-        self.comm = torch.cuda.Stream() if self.world > 1 else None
+        self.comm = torch.cuda.Stream() if self.world > 1 and torch.cuda.is_available() else None
         # NCCL averages in the collective itself (ncclAvg); other backends (gloo in the CPU tests) sum, then scale
         nccl = dist.is_available() and dist.is_initialized() and dist.get_backend(group) == "nccl"
         self._avg = dist.ReduceOp.AVG if nccl else dist.ReduceOp.SUM
         self._bufs = []
+        self._deferred = {}   # id(param) -> param whose final .grad is reduced in __exit__
+        self.stats = {"overlapped": 0, "deferred": 0}
+
+    def _reduce(self, t):
+        dist.all_reduce(t, op=self._avg, group=self.group)  # averaged inside NCCL: no extra pass over the buffer
+        if self._avg is dist.ReduceOp.SUM:
+            t.mul_(1.0 / self.world)
 
     # called from the autograd Functions (ops.GRAD_SYNC.submit) right after a backward has been enqueued
-    def submit(self, flat):
+    def submit(self, flat, params=None, fwd_calls=1):
+        """flat: the zero-initialised buffer the Function's parameter gradients are views of; params: those
+        parameters; fwd_calls: how many times the Function ran on them in the current forward (ops.FWD_CALLS)."""
         if self.world == 1:
             return
-        cur = torch.cuda.current_stream()
-        ev = torch.cuda.Event()
-        ev.record(cur)
-        self.comm.wait_event(ev)
-        flat.record_stream(self.comm)
-        with torch.cuda.stream(self.comm):
-            dist.all_reduce(flat, op=self._avg, group=self.group)  # averaged inside NCCL: no extra pass over the buffer
-            if self._avg is dist.ReduceOp.SUM:
-                flat.mul_(1.0 / self.world)
+        safe = params is not None and fwd_calls == 1 and all(p.grad is None and id(p) not in self._deferred for p in params)
+        if not safe:
+            # autograd will ADD this buffer's views to existing gradients (or other buffers' views to these): the
+            # parameters' final .grad is reduced once backward is over
+            for p in (params or ()):
+                self._deferred[id(p)] = p
+            self.stats["deferred"] += 1
+            return
+        self.stats["overlapped"] += 1
+        if self.comm is None:  # CPU tensors (gloo tests): no stream to overlap on
+            self._reduce(flat)
+        else:
+            cur = torch.cuda.current_stream()
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self.comm.wait_event(ev)
+            flat.record_stream(self.comm)
+            with torch.cuda.stream(self.comm):
+                self._reduce(flat)
         self._bufs.append(flat)
 
     def __enter__(self):
         self._bufs = []
+        self._deferred = {}
         ops.GRAD_SYNC = self
         return self
 
     def __exit__(self, *exc):
         ops.GRAD_SYNC = None
+        ops.FWD_CALLS.clear()
         if self.world == 1:
             return False
-        cur = torch.cuda.current_stream()
-        # parameters whose gradient did not come through a flat buffer (heads outside the encoder, or a
-        # gradient autograd had to copy instead of adopting the view): reduce them individually
+        # parameters whose gradient did not come through an overlapped flat buffer (heads outside the encoder,
+        # deferred layers, or a gradient autograd had to copy instead of adopting the view): reduce them now
         covered = [(b.data_ptr(), b.data_ptr() + b.numel() * 4) for b in self._bufs]
         rest = []
         for p in self.model.parameters():
             if p.grad is None:
                 continue
             a = p.grad.data_ptr()
-            if not any(lo <= a < hi for lo, hi in covered):
+            if id(p) in self._deferred or not any(lo <= a < hi for lo, hi in covered):
                 rest.append(p.grad)
         if rest:
-            ev = torch.cuda.Event()
-            ev.record(cur)
-            self.comm.wait_event(ev)
-            with torch.cuda.stream(self.comm):
+            if self.comm is None:
                 for g in rest:
-                    g.record_stream(self.comm)
-                    dist.all_reduce(g, op=self._avg, group=self.group)
-                    if self._avg is dist.ReduceOp.SUM:
-                        g.mul_(1.0 / self.world)
-        cur.wait_stream(self.comm)
+                    self._reduce(g)
+            else:
+                cur = torch.cuda.current_stream()
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                self.comm.wait_event(ev)
+                with torch.cuda.stream(self.comm):
+                    for g in self._coalesce(rest):
+                        g.record_stream(self.comm)
+                        self._reduce(g)
+        if self.comm is not None:
+            torch.cuda.current_stream().wait_stream(self.comm)
         self._bufs = []
+        self._deferred = {}
         return False
+
+    @staticmethod
+    def _coalesce(grads):
+        """Gradients that are adjacent views of one allocation (a layer's flat buffer adopted by autograd) are reduced
+        as one tensor: one collective per layer instead of sixteen."""
+        out, run = [], None
+        for g in sorted((g for g in grads if g.is_contiguous()), key=lambda t: t.data_ptr()):
+            if (run is not None and g.dtype == run[0].dtype and g.untyped_storage().data_ptr() == run[0].untyped_storage().data_ptr()
+                    and g.data_ptr() == run[1]):
+                run[1] = g.data_ptr() + g.numel() * g.element_size()
+                run[2] += g.numel()
+            else:
+                if run is not None:
+                    out.append(run)
+                run = [g, g.data_ptr() + g.numel() * g.element_size(), g.numel()]
+        if run is not None:
+            out.append(run)
+        merged = []
+        for first, _, n in out:
+            if n == first.numel():
+                merged.append(first)
+            else:  # a view over the whole adjacent run, sharing the storage
+                merged.append(torch.as_strided(first, (n,), (1,), first.storage_offset()))
+        merged += [g for g in grads if not g.is_contiguous()]
+        return merged

@@ -45,6 +45,7 @@ def drop_args(state, site, p, row_mul=1):
     d = _lib.Dropout()
     d.state, d.site, d.threshold, d.scale, d.row_mul = state.data_ptr(), site, int(round(p * 65536.0)), 1.0 / (1.0 - p), row_mul
     assert 0 < d.threshold < 65536
+    d._keepalive = state  # the descriptor only carries a raw pointer: the tensor must outlive every launch that uses it
     return d
 
 
@@ -341,6 +342,16 @@ def simmat_ce_bwd(q, k, scores, lse, dloss, gmat, dq, dk, *, mode, row_offset=0,
     a.dk = dk.data_ptr() if dk is not None else 0
     _run("cdr_simmat_ce_bwd", lambda: _lib_().cdr_simmat_ce_bwd(C.byref(a), stream_ptr()))
     _count(3)
+
+
+def own_key_grad(q, loss, dloss, dk_own):
+    """dk_own[i, :] = dloss[i] * (exp(-loss[i]) - 1) * q[i, :]: the gradient an in-batch InfoNCE row sends to its own
+    (positive) key (cdr_simmat_own_key_grad)."""
+    _need_cuda(q, loss, dloss, dk_own)
+    assert q.dtype == torch.float32 and q.is_contiguous() and dk_own.is_contiguous() and dk_own.shape == q.shape
+    _run("cdr_simmat_own_key_grad", lambda: _lib_().cdr_simmat_own_key_grad(
+        _p(q), _p(loss), _p(dloss), _i32(q.shape[0]), _i32(q.shape[1]), _p(dk_own), stream_ptr()))
+    _count(1)
 
 
 def vocab_ce_fwd(logits, bias, labels, loss, lse, *, n_cols):

@@ -167,7 +167,9 @@ class BertDot_NLL_LN(NLL, BertForSequenceClassification):
             return loss.mean(), train_acc, logits
         if self.dro_type == 'idro':
             robust_loss, group_losses, group_counts = self.loss(self.bert, loss, group_ids,
-                                                                sample_towers=getattr(self, "_sample_towers", 0))
+                                                                sample_towers=getattr(self, "_sample_towers", 0),
+                                                                grad_losses=getattr(self, "_idro_grad_losses", None))
+            self._idro_grad_losses = None
         else:
             robust_loss, group_losses, group_counts = self.loss(loss, group_ids, weights)
         host = torch.cat([robust_loss.detach().reshape(1), group_losses, group_counts]).tolist()  # one sync
@@ -206,10 +208,28 @@ class BertDot_InBatch_NLL_LN(BertDot_NLL_LN):
     """q x p in-batch InfoNCE with cross-GPU all-gathered passages (K9').
 
     ``loss_i = CE(q_i . P_all^T, rank*B + i)`` over the passages of every rank (hard negatives
-    ``input_ids_b``, when given, are appended to the key set).  ERM / iDRO / DRO-greedy routing of the
-    per-sample losses is inherited unchanged."""
+    ``input_ids_b``, when given, are appended to the key set).  ERM / DRO-greedy routing of the per-sample
+    losses is inherited unchanged.
+
+    iDRO differentiates every group's mean loss w.r.t. the last layers, one partial backward per group
+    (ANCE/model/dro_loss.py:192-204).  Through the gathered keys those backwards would issue collectives
+    (reduce-scatter of the key gradients) a rank-dependent number of times -- a hang or a mismatch as soon as two ranks
+    hold different groups.  The group gradients are therefore taken from a VIEW of the same loss values whose graph
+    stays on this rank (the robust loss and the training gradient still use the fully differentiable gather):
+
+      ``idro_group_grads = "local-batch"`` (default): keys of other ranks are constants, this rank's passages keep
+          their graph -- exactly what the reference's own gather convention does (``all_tensors[rank] = t``,
+          COCO/modeling.py:182-186).  Every local passage is a negative of every local query, so an activation-gradient
+          row of the passage tower mixes all groups: K11 (one shared backward + grouped wgrad) cannot apply, and the
+          gradients are G_present partial backwards through the last layers.
+      ``idro_group_grads = "own-pair"``: in addition the in-batch negatives are constants -- sample i's loss view
+          depends on (q_i, p_i) only, the same locality the reference's triplet loss has by construction
+          (models.py:101-108) -- so K11 applies and the [G, P_last] matrix costs one partial backward.  This changes
+          the gradient-similarity statistics that drive ``h_fun`` (the negatives' share of each group gradient is
+          dropped), not the loss or its training gradient."""
 
     peer_gather = False  # enable_peer_gather(): exchange the passage embeddings through peer memory, not NCCL
+    idro_group_grads = "local-batch"
 
     def enable_peer_gather(self, on=True):
         """Multi-GPU, one node: all-gather the passage CLS embeddings by letting the last LayerNorm kernel store them
@@ -256,6 +276,21 @@ class BertDot_InBatch_NLL_LN(BertDot_NLL_LN):
         if len(embs) == 3:
             keys = torch.cat([keys, gather_with_grad(embs[2])], 0)
         loss = ops.qp_infonce(q_embs, keys, row_offset=offset)
+        self._idro_grad_losses = None
+        if group_ids is not None and self.dro_type == 'idro' and torch.is_grad_enabled():
+            if self.idro_group_grads == "own-pair" and len(embs) == 2:
+                self._idro_grad_losses = ops.OwnPairCE.apply(q_embs, embs[1], keys, offset)
+                if query_ids.shape == input_ids_a.shape:
+                    self._sample_towers = 2  # loss view i reads sequences {i, B + i} of the fused pass only
+            elif self.idro_group_grads in ("own-pair", "local-batch"):
+                kd = keys.detach()
+                n_all = kd.shape[0] // (len(embs) - 1)  # gathered passages (| gathered hard negatives)
+                parts = [kd[:offset], embs[1], kd[offset + B:n_all]]
+                if len(embs) == 3:
+                    parts += [kd[n_all:n_all + offset], embs[2], kd[n_all + offset + B:]]
+                self._idro_grad_losses = ops.qp_infonce(q_embs, torch.cat(parts, 0), row_offset=offset)
+            else:
+                raise ValueError(f"idro_group_grads must be 'local-batch' or 'own-pair', not {self.idro_group_grads!r}")
         with torch.no_grad():
             pos = (q_embs * embs[1]).sum(-1)
             neg = (q_embs * embs[2]).sum(-1) if len(embs) == 3 else pos

@@ -21,6 +21,22 @@ FORCE_SHADOW_REFRESH = False  # set while a CUDA graph is being captured (graph.
 GRAD_SYNC = None              # an active gradsync.GradSync collects the flat gradient buffers of each backward
 CLS_PUSH = None               # (peer.PeerExchange, first_seq): the last LayerNorm pushes CLS rows to every rank (peer.py)
 GROUP_CAPTURE = None          # a GroupCapture: layer backwards also hand over their wgrad operands (dro_loss.py, K11)
+FWD_CALLS = {}                # id(first parameter of a Function) -> forwards since the last GradSync exit (gradsync.py)
+
+
+def _note_forward(ctx, params):
+    """Count the forwards of a parameter set that autograd records (grad mode is off INSIDE Function.forward, so the
+    Function's needs_input_grad is the signal): GradSync only reduces a layer's flat gradient buffer in place when the
+    layer ran exactly once (otherwise autograd accumulates several buffers into one .grad)."""
+    if any(ctx.needs_input_grad):
+        k = id(params[0])
+        FWD_CALLS[k] = FWD_CALLS.get(k, 0) + 1
+    return params
+
+
+def _submit(ctx, flat):
+    if GRAD_SYNC is not None:
+        GRAD_SYNC.submit(flat, ctx.params, FWD_CALLS.get(id(ctx.params[0]), 1))
 
 
 # Dropout of one encoder pass: ``state`` = int64 device tensor {seed, offset} (a snapshot taken by the pass, so the
@@ -205,6 +221,7 @@ class EmbedLN(torch.autograd.Function):
         if ctx.drop is not None:  # HF BertEmbeddings: dropout(LayerNorm(...))
             K.dropout_f16(out, out, drop=ctx.drop)
         ctx.save_for_backward(ids, word, pos, typ, gamma, mean, rstd)
+        ctx.params = _note_forward(ctx, (word, pos, typ, gamma, beta))
         ctx.eps = eps
         ctx.scale = _GRAD_SCALE
         return out
@@ -229,8 +246,7 @@ class EmbedLN(torch.autograd.Function):
         K.embed_ln_bwd(dy, ids, word, pos, typ, gamma, mean, rstd, dword, dpos, dtyp, dgamma, dbeta,
                        n_seq=n_seq, seq_len=L, hidden=H, vocab=word.shape[0], pad_id=0, in_scale=1.0,
                        out_scale=1.0 / ctx.scale)
-        if GRAD_SYNC is not None:
-            GRAD_SYNC.submit(flat)
+        _submit(ctx, flat)
         return None, dword, dpos, dtyp, dgamma, dbeta, None, None
 
 
@@ -275,7 +291,8 @@ class BertLayerFn(torch.autograd.Function):
         ctx.shadow_w = (sh.wqkv, sh.wo, sh.wi, sh.wo2)
         ctx.drop = (da, db, dc, drop.state if drop is not None else None)
         ctx.meta = (n_seq, L, heads, I, emit_cls, _GRAD_SCALE)
-        ctx.param_keys = tuple(id(t) for t in (wq, bq, wk, bk, wv, bv, wo, bo, g1, be1, wi, bi, wo2, bo2, g2, be2))
+        ctx.params = _note_forward(ctx, (wq, bq, wk, bk, wv, bv, wo, bo, g1, be1, wi, bi, wo2, bo2, g2, be2))
+        ctx.param_keys = tuple(id(t) for t in ctx.params)
         ctx.set_materialize_grads(False)
         if emit_cls:
             return y, cls
@@ -337,8 +354,7 @@ class BertLayerFn(torch.autograd.Function):
                alpha=inv)
         if not fused_db:
             K.colsum(dqkv, dbqkv, rows=T, cols=3 * H, scale=inv)
-        if GRAD_SYNC is not None:
-            GRAD_SYNC.submit(flat)
+        _submit(ctx, flat)
         if GROUP_CAPTURE is not None:
             GROUP_CAPTURE.records.append(dict(
                 keys=ctx.param_keys, rps=L, L=L, n_seq=n_seq, S=S, dy2=dy2m, gl=gl, dz=dz, x1=x1, dy1=dy1m, att=att,
@@ -398,7 +414,8 @@ class BertLastLayerCLSFn(torch.autograd.Function):
         ctx.shadow_w = (sh.wqkv, sh.wo, sh.wi, sh.wo2)
         ctx.drop = (da, db, dc, drop.state if drop is not None else None)
         ctx.meta = (n_seq, L, heads, I, _GRAD_SCALE)
-        ctx.param_keys = tuple(id(t) for t in (wq, bq, wk, bk, wv, bv, wo, bo, g1, be1, wi, bi, wo2, bo2, g2, be2))
+        ctx.params = _note_forward(ctx, (wq, bq, wk, bk, wv, bv, wo, bo, g1, be1, wi, bi, wo2, bo2, g2, be2))
+        ctx.param_keys = tuple(id(t) for t in ctx.params)
         return cls
 
     @staticmethod
@@ -453,8 +470,7 @@ class BertLastLayerCLSFn(torch.autograd.Function):
                alpha=inv)
         if not fused_db:
             K.colsum(dqkv, dbqkv, rows=T, cols=3 * H, scale=inv)
-        if GRAD_SYNC is not None:
-            GRAD_SYNC.submit(flat)
+        _submit(ctx, flat)
         if GROUP_CAPTURE is not None:  # rows of the post-attention operands are sequences here (one [CLS] row each)
             GROUP_CAPTURE.records.append(dict(
                 keys=ctx.param_keys, rps=1, L=L, n_seq=n_seq, S=S, dy2=dy2m, gl=gl, dz=dz, x1=x1, dy1=dy1m,
@@ -561,6 +577,36 @@ class GroupStats(torch.autograd.Function):
         dloss = _f32(g.numel(), dev=g.device)
         K.group_reduce_bwd(dsums.contiguous().float(), g, dloss, n_groups=ctx.n_groups)
         return dloss, None, None
+
+
+class OwnPairCE(torch.autograd.Function):
+    """Per-sample in-batch InfoNCE values ``CE(q_i K^T, row_offset + i)`` whose autograd graph reaches only the sample's
+    OWN pair: dq_i = sum_j dS_ij k_j over all keys, dp_i = dS_i,own q_i, every other key a constant.  This is the
+    loss view iDRO takes its group gradients from when the keys are in-batch passages (each sample's loss then depends
+    on encoder sequences {i, i + B} only, so the grouped wgrad K11 applies); ``p_own`` must equal
+    ``keys[row_offset : row_offset + B]``."""
+
+    @staticmethod
+    def forward(ctx, q, p_own, keys, row_offset):
+        q, keys = q.contiguous().float(), keys.detach().contiguous().float()
+        n, m = q.shape[0], keys.shape[0]
+        dev = q.device
+        scores, loss, lse = _f32(n, m, dev=dev), _f32(n, dev=dev), _f32(n, dev=dev)
+        K.simmat_ce_fwd(q, keys, scores, loss, lse, mode=K.SIM_QP, row_offset=row_offset, loss_scale=1.0)
+        ctx.save_for_backward(q, keys, scores, lse, loss)
+        ctx.row_offset = row_offset
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        q, keys, scores, lse, loss = ctx.saved_tensors
+        dloss = dloss.contiguous().float()
+        dq = torch.empty_like(q)
+        K.simmat_ce_bwd(q, keys, scores, lse, dloss, torch.empty_like(scores), dq, None, mode=K.SIM_QP,
+                        row_offset=ctx.row_offset, loss_scale=1.0)
+        dp = torch.empty_like(q)
+        K.own_key_grad(q, loss, dloss, dp)  # dS_i,own = dloss_i * (softmax_i,own - 1) = dloss_i * (exp(-loss_i) - 1)
+        return dq, dp, None, None
 
 
 def pair_nll(q, a, b):

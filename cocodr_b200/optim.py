@@ -91,16 +91,31 @@ class _FusedOptimizer(torch.optim.Optimizer):
         if tab is not None and tab["key"] == key:
             return tab
         n = len(params)
-        if tab is None or tab["host"].numel() != n * C.sizeof(OptItem):
+        if tab is None or tab["host_ring"][0].numel() != n * C.sizeof(OptItem):
             dev = params[0].device
-            tab = {"host": torch.empty(n * C.sizeof(OptItem), dtype=torch.uint8).pin_memory(),
+            # the pinned staging copy of the table is a small RING: in eager mode the gradient pointers change almost
+            # every step, and the non-blocking H2D copy of step n may still be queued when step n + 1 rewrites the
+            # host side -- each slot is rewritten only after the event recorded behind its last copy has completed
+            tab = {"host_ring": [torch.empty(n * C.sizeof(OptItem), dtype=torch.uint8).pin_memory() for _ in range(4)],
+                   "host_ev": [None] * 4, "host_i": 0,
                    "dev": torch.empty(n * C.sizeof(OptItem), dtype=torch.uint8, device=dev),
                    "step": torch.zeros((), dtype=torch.float32, device=dev),
                    "lr": torch.zeros((), dtype=torch.float32, device=dev), "lr_host": None,
                    "norms": torch.zeros(2 * n, dtype=torch.float32, device=dev),
                    "trust": torch.zeros(n, dtype=torch.float32, device=dev)}
             self._tables[gi] = tab
-        arr = (OptItem * n).from_address(tab["host"].data_ptr())
+        capturing = torch.cuda.is_current_stream_capturing()
+        if capturing:
+            # a captured H2D copy is replayed from this host buffer at every graph launch: it gets a buffer of its own
+            # that is never rewritten (kept alive by the table)
+            host = torch.empty(n * C.sizeof(OptItem), dtype=torch.uint8).pin_memory()
+            tab.setdefault("host_captured", []).append(host)
+        else:
+            slot = tab["host_i"] = (tab["host_i"] + 1) % len(tab["host_ring"])
+            if tab["host_ev"][slot] is not None:
+                tab["host_ev"][slot].synchronize()  # (long done in practice: the ring is 4 steps deep)
+            host = tab["host_ring"][slot]
+        arr = (OptItem * n).from_address(host.data_ptr())
         for i, p in enumerate(params):
             st = self._state_for(p)
             sh = self._shadow_of.get(id(p))
@@ -111,7 +126,10 @@ class _FusedOptimizer(torch.optim.Optimizer):
             arr[i].n = p.numel()
             arr[i].reserved = int(any(a & 15 for a in (arr[i].p, arr[i].g, arr[i].m, arr[i].v)) or
                                   bool((arr[i].shadow or 0) & 15))  # unaligned entries take the scalar path
-        tab["dev"].copy_(tab["host"], non_blocking=True)
+        tab["dev"].copy_(host, non_blocking=True)
+        if not capturing:
+            tab["host_ev"][slot] = torch.cuda.Event()
+            tab["host_ev"][slot].record()
         sizes = tuple(p.numel() for p in params)
         if tab.get("sizes") != sizes:  # chunk work list: depends on the tensor sizes only
             import numpy as np
@@ -123,7 +141,8 @@ class _FusedOptimizer(torch.optim.Optimizer):
             tab["n_chunks"], tab["sizes"] = len(ck), sizes
         tab["key"], tab["params"] = key, params
         # one fp32 step counter per group on the device; seeded from the per-parameter state (state_dict round trips)
-        tab["step"].copy_(self.state[params[0]]["step"].to(torch.float32))
+        # (a reference-format optimizer.pt stores ``step`` as a python int: ANCE/utils/lamb.py:93, transformers AdamW)
+        tab["step"].copy_(torch.as_tensor(self.state[params[0]]["step"], dtype=torch.float32, device=tab["step"].device))
         return tab
 
     def _args(self, tab, group, mode=0):

@@ -305,6 +305,13 @@ typedef struct cdr_simmat_args {
 } cdr_simmat_args;
 int cdr_simmat_ce_fwd(const cdr_simmat_args* args, void* stream);
 int cdr_simmat_ce_bwd(const cdr_simmat_args* args, void* stream);
+/* CDR_SIM_QP, gradient of row i towards its OWN key only: dk_own[i, :] = dloss[i] * (softmax_i,own - 1) * q[i, :] with
+ * softmax_i,own = exp(-loss[i]) (loss from cdr_simmat_ce_fwd with loss_scale 1).  With cdr_simmat_ce_bwd(dk = NULL)
+ * this is the backward of the loss view "every key but the sample's own positive is a constant", from which iDRO
+ * takes its group gradients for the in-batch head (ANCE/model/dro_loss.py:192-204 differentiates the group means;
+ * see cocodr_b200/models.py BertDot_InBatch_NLL_LN). */
+int cdr_simmat_own_key_grad(const float* q, const float* loss, const float* dloss, int32_t n, int32_t dim, float* dk_own,
+                            void* stream);
 
 /* K14 MLM head loss on gathered masked rows (HF BertForMaskedLM cross-entropy reached through
  * COCO/modeling.py:87-93, 199-204): logits fp32 [n_rows, ld] from the decoder GEMM, bias fp32 [n_cols] added

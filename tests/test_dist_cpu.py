@@ -13,6 +13,8 @@
     the EMA counts after two steps equal the oracle fed with the gathered batch
   * iDROLoss.forward end to end (dro_loss.py:216-254) on a small torch model: local group means, rank-summed group
     gradients through the sharded Gram, h_fun after two steps == the oracle that all-reduces the [G, P] matrix
+  * gradsync.GradSync: mean-over-ranks gradients whether a layer's flat buffer can be reduced in place during
+    backward (one use, no prior gradient) or must be deferred (layer used twice, accumulation, tied parameters)
   * scan.search_sharded: documents split unevenly over the ranks (one shard smaller than k), per-rank top-k with
     global ids, all-gather of the candidate lists, k-way merge == the single-process oracle scan of the whole corpus,
     ids bit-exact in (score desc, id asc) order; the per-shard scan and the merge kernel are replaced by the oracle
@@ -201,9 +203,99 @@ def _scan_worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
+def _gradsync_worker(rank, world, port, ret):
+    """GradSync must give mean-over-ranks gradients in every autograd pattern, not only "each layer once, no prior
+    gradient": a toy Function with the same flat-buffer protocol as ops.BertLayerFn (views of one zero-filled buffer,
+    ops._note_forward / ops._submit) is driven through (1) one use per layer, (2) the same layer twice in one forward
+    (unfused q / p towers), (3) two backward passes accumulating into .grad, (4) a parameter that already received a
+    gradient from an op outside the protocol (the tied word embedding of the COCO model)."""
+    _init(rank, world, port)
+    from cocodr_b200 import ops
+    from cocodr_b200.gradsync import GradSync
+
+    class ToyLayer(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, w, b):
+            ctx.save_for_backward(x, w)
+            ctx.params = ops._note_forward(ctx, (w, b))
+            return torch.tanh(x @ w.t() + b)
+
+        @staticmethod
+        def backward(ctx, dy):
+            x, w = ctx.saved_tensors
+            y = torch.tanh(x @ w.t() + ctx.params[1])
+            dz = dy * (1 - y * y)
+            flat = torch.zeros(w.numel() + w.shape[0])
+            dw, db = flat[:w.numel()].view_as(w), flat[w.numel():]
+            dw += dz.t() @ x
+            db += dz.sum(0)
+            ops._submit(ctx, flat)
+            return dz @ w, dw, db
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.ParameterList(torch.nn.Parameter(torch.randn(6, 6) * 0.5) for _ in range(3))
+            self.b = torch.nn.ParameterList(torch.nn.Parameter(torch.randn(6) * 0.1) for _ in range(3))
+            self.head = torch.nn.Linear(6, 1)
+
+        def tower(self, x):
+            for w, b in zip(self.w, self.b):
+                x = ToyLayer.apply(x, w, b)
+            return x
+
+    torch.manual_seed(0)
+    net = Net()
+    ref_net = Net()
+    ref_net.load_state_dict(net.state_dict())
+    gen = torch.Generator().manual_seed(100 + rank)
+    xs = [torch.randn(5, 6, generator=gen) for _ in range(4)]
+
+    def losses(n):
+        return {
+            "once": lambda: n.head(n.tower(xs[0])).sum(),
+            "twice": lambda: (n.head(n.tower(xs[0])) * n.tower(xs[1]).sum(1, keepdim=True)).sum(),
+            "tied": lambda: (n.head(n.tower(xs[0])).sum() + (n.w[0] ** 2).sum() * 0.1),
+        }
+
+    def reference(names, n_backward):
+        ref_net.zero_grad(set_to_none=True)
+        for _ in range(n_backward):
+            for nm in names:
+                losses(ref_net)[nm]().backward()
+        out = {}
+        for k, p in ref_net.named_parameters():
+            g = p.grad.clone()
+            dist.all_reduce(g)
+            out[k] = g / world
+        return out
+
+    sync = GradSync(net)
+    ok = True
+    checks = {"once": (["once"], 1, True), "twice": (["twice"], 1, False), "accumulate": (["once"], 2, None),
+              "tied": (["tied"], 1, None)}
+    for label, (names, n_backward, expect_overlap) in checks.items():
+        net.zero_grad(set_to_none=True)
+        sync.stats = {"overlapped": 0, "deferred": 0}
+        for _ in range(n_backward):
+            for nm in names:
+                loss = losses(net)[nm]()
+                with sync:
+                    loss.backward()
+        want = reference(names, n_backward)
+        for k, p in net.named_parameters():
+            ok = ok and torch.allclose(p.grad, want[k], rtol=1e-5, atol=1e-6)
+        if expect_overlap is True:
+            ok = ok and sync.stats["overlapped"] == 3 and sync.stats["deferred"] == 0
+        if expect_overlap is False:
+            ok = ok and sync.stats["overlapped"] == 0 and sync.stats["deferred"] == 6
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
 @pytest.mark.parametrize("worker,port", [(_gather_worker, 29641), (_gram_worker, 29643), (_scan_worker, 29645),
                                          (_coco_worker, 29647), (_greedy_worker, 29649),
-                                         (_idro_worker, 29651)])
+                                         (_idro_worker, 29651), (_gradsync_worker, 29653)])
 def test_world2_gloo(worker, port):
     world = 2
     with mp.Manager() as mgr:

@@ -229,3 +229,48 @@ def test_cls_only_last_layer_equals_full_layer():
             continue  # analytically zero: rounding noise on both sides
         err = (g_cls - g_full).abs().max().item()
         assert err <= 2e-3 * g_full.abs().max().item() + 1e-7, (n, err)
+
+
+@pytest.mark.parametrize("mode", ["local-batch", "own-pair"])
+def test_inbatch_idro_group_gradient_views(mode):
+    """iDRO on the in-batch head: group gradients come from a collective-free VIEW of the per-sample losses
+    (models.BertDot_InBatch_NLL_LN): 'local-batch' = the loss itself on one rank (per-group partial backwards),
+    'own-pair' = in-batch negatives held constant (one shared backward + grouped wgrad, K11).  Oracle: autograd per group
+    (heads_ref.idro_forward, dro_loss.py:192-254) on the same view built in torch."""
+    from oracle import bert_ref, heads_ref
+    m = build(TINY, "BertDot_InBatch_NLL_LN").train()
+    m.idro_group_grads = mode
+    G, B, L = 6, 8, 32
+    alpha, eps, ema, rho = 0.25, 0.01, 0.1, 0.05
+    m.add_group_loss(types.SimpleNamespace(model_size="base", local_rank=0), G, "idro", alpha, eps, ema, rho)
+    q, mq = bert_ref.synth_batch(B, L, TINY["vocab"], 31)
+    p, mp = bert_ref.synth_batch(B, L, TINY["vocab"], 32)
+    gid = torch.tensor([0, 1, 1, 3, 0, 4, 3, 3])
+    h0 = m.loss.h_fun.clone().cpu()
+    robust, acc, gl, gc = m(q.cuda(), mq.cuda(), p.cuda(), mp.cuda(), group_ids=gid.cuda(), weights=torch.ones(B, device="cuda"))
+    robust.backward()
+    assert all(torch.isfinite(t.grad).all() for t in m.bert.parameters() if t.grad is not None)
+    leaf = {k: v.clone().requires_grad_(True) for k, v in bert_ref.synth_state(TINY, 0).items()}
+    qe, pe = bert_ref.cls_embedding(leaf, q, mq, TINY), bert_ref.cls_embedding(leaf, p, mp, TINY)
+    if mode == "local-batch":
+        view = heads_ref.qp_infonce(qe, pe)
+    else:
+        S = qe @ pe.detach().t()
+        S = S - torch.diag(torch.diagonal(S)) + torch.diag((qe * pe).sum(-1))  # only the own positive keeps its graph
+        view = torch.nn.functional.cross_entropy(S, torch.arange(B), reduction="none")
+    names = heads_ref.idro_param_names(["bert." + n for n in leaf], "base")
+    params = [leaf[n[5:]] for n in names]
+    r_ref, m_ref, c_ref, h_ref = heads_ref.idro_forward(view, gid, params, h0, G, alpha, ema, rho, eps)
+    assert abs(robust.item() - r_ref.item()) < 1e-2 * abs(r_ref.item())
+    np.testing.assert_allclose(gl.cpu().numpy(), m_ref.numpy(), rtol=1e-2, atol=2e-3)
+    np.testing.assert_array_equal(gc.cpu().numpy(), c_ref.numpy())
+    np.testing.assert_allclose(m.loss.h_fun.cpu().numpy(), h_ref.numpy(), rtol=1e-2, atol=1e-4)
+    # the training gradient is that of the full in-batch loss in both modes
+    full = heads_ref.qp_infonce(qe, pe)
+    _, _, means = heads_ref.group_stats(full, gid, G)
+    (means * h0).sum().backward()
+    name = "encoder.layer.2.intermediate.dense.weight"
+    got = dict(m.bert.named_parameters())[name].grad.cpu().numpy()
+    cos = float((got.ravel() * leaf[name].grad.numpy().ravel()).sum() /
+                (np.linalg.norm(got) * np.linalg.norm(leaf[name].grad.numpy()) + 1e-30))
+    assert cos > 0.99, cos

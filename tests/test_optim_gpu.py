@@ -173,3 +173,35 @@ def test_lamb_matches_reference_fixture(golden_dir):
             np.testing.assert_allclose(p.detach().cpu().numpy(), g[f"{tag}.p{i}"], rtol=2e-5, atol=1e-7)
             t = float(opt.state[p]["trust_ratio"])
             assert abs(t - float(g[f"{tag}.trust{i}"])) <= 1e-4 * max(1.0, abs(t))
+
+
+@pytest.mark.parametrize("kind", ["adamw", "lamb"])
+def test_resume_from_reference_format_state_dict(kind):
+    """The reference's optimizers store ``state['step']`` as a python int (ANCE/utils/lamb.py:93, transformers AdamW)
+    and run_ann.py reloads optimizer.pt on resume: loading such a state dict and stepping must continue from it."""
+    from cocodr_b200 import optim
+    mk = (lambda ps: optim.AdamW(ps, lr=1e-3, eps=1e-8, semantics="torch")) if kind == "adamw" else \
+         (lambda ps: optim.Lamb(ps, lr=1e-3, eps=1e-6))
+    a, b = _params(7), _params(7)
+    oa, ob = mk(a), mk(b)
+    for step in range(2):
+        _grads(a, 40 + step)
+        _grads(b, 40 + step)
+        oa.step()
+        ob.step()
+    sd = copy.deepcopy(oa.state_dict())
+    for st in sd["state"].values():  # reference layout: python int step, tensors for the moments
+        st["step"] = int(round(float(st["step"])))
+        st.pop("trust_ratio", None)
+    c = _params(7)
+    for p, q in zip(c, a):
+        p.data.copy_(q.data)
+    oc = mk(c)
+    oc.load_state_dict(sd)
+    _grads(b, 50)
+    _grads(c, 50)
+    ob.step()
+    oc.step()
+    for p, q in zip(c, b):
+        assert (p - q).abs().max().item() <= 2e-6 * max(1.0, q.abs().max().item())
+    assert float(oc.state_dict()["state"][0]["step"]) == 3.0
