@@ -4,6 +4,8 @@
 // staged kernels (ln_fwd_staged_kernel / ln_bwd_staged_kernel: 8-row tiles brought in by cp.async.bulk into a
 // 3-stage mbarrier ring, a warp per row for the statistics, a thread per 8 columns for the column sums); wider rows
 // and the fp32 [CLS]-gradient variant keep the one-warp-per-row kernels.
+#include <stdlib.h>
+
 #include "cdr_common.cuh"
 #include "dropout.cuh"
 #include "peer.cuh"
@@ -671,6 +673,188 @@ ln_bwd_staged_kernel(const __half* __restrict__ dy, const __half* __restrict__ x
   }
 }
 
+
+// ------------------------------------------------------------------------------------------ staged, row-owner backward
+// Second generation of the staged backward: a warp owns a row end to end AND the column partial sums of the rows it
+// has processed (dgamma, dbeta, bias gradient: 3 x hidden / 32 accumulators per lane), so every staged element is read
+// from shared memory once and no value is recomputed (the two-phase kernel above re-reads the tile and re-derives
+// xhat / dx per column thread, which made it issue-bound at half of the HBM rate).  One block of 8 warps per SM, a
+// deeper ring (all the shared memory of the SM in flight), cross-warp reduction of the accumulators once per block.
+constexpr int LNR_THREADS = 256;
+
+template <int VPL, bool DROP>
+__global__ void __launch_bounds__(LNR_THREADS, 1)
+ln_bwd_rows_kernel(const __half* __restrict__ dy, const __half* __restrict__ x, const float* __restrict__ gamma,
+                   const float* __restrict__ mean_in, const float* __restrict__ rstd_in, __half* __restrict__ dx,
+                   float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dcol, int rows, int hidden,
+                   float out_scale, __half* __restrict__ dxm, const cdr_dropout drop, int stages) {
+  extern __shared__ __align__(128) uint8_t lns_smem[];  // [stage][dy tile | x tile]
+  __shared__ uint64_t full[8];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nvec = hidden >> 3;
+  const uint32_t row_bytes = static_cast<uint32_t>(hidden) * 2u;
+  const uint32_t tile_bytes = row_bytes * LNS_ROWS;
+  const int n_tiles = (rows + LNS_ROWS - 1) / LNS_ROWS;
+  if (tid == 0) {
+    for (int i = 0; i < stages; ++i) mbar_init(&full[i], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  pdl_wait();
+  pdl_launch();
+  auto issue = [&](int tile, int stage) {
+    const int r0 = tile * LNS_ROWS;
+    const uint32_t bytes = static_cast<uint32_t>(min(LNS_ROWS, rows - r0)) * row_bytes;
+    uint8_t* dst = lns_smem + stage * 2 * tile_bytes;
+    mbar_expect_tx(&full[stage], 2 * bytes);
+    bulk_load(dst, dy + static_cast<long long>(r0) * hidden, bytes, &full[stage]);
+    bulk_load(dst + tile_bytes, x + static_cast<long long>(r0) * hidden, bytes, &full[stage]);
+  };
+  if (tid == 0)
+    for (int i = 0; i < stages; ++i) {
+      const int t = blockIdx.x + i * gridDim.x;
+      if (t < n_tiles) issue(t, i);
+    }
+  float g[VPL][8], a_dg[VPL][8], a_db[VPL][8], a_dc[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g[i][k] = a_dg[i][k] = a_db[i][k] = a_dc[i][k] = 0.f;
+    if (lane + 32 * i < nvec) load8_f(gamma + 8 * (lane + 32 * i), g[i]);
+  }
+  DropCtx dc{};
+  if constexpr (DROP) dc = drop_load(drop);
+  float mean_nx = 0.f, rstd_nx = 0.f;
+  if (blockIdx.x * LNS_ROWS + warp < rows) {
+    mean_nx = mean_in[blockIdx.x * LNS_ROWS + warp];
+    rstd_nx = rstd_in[blockIdx.x * LNS_ROWS + warp];
+  }
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const float mean = mean_nx, rstd = rstd_nx;
+    {
+      const long long nrow = static_cast<long long>(tile + gridDim.x) * LNS_ROWS + warp;
+      if (nrow < rows) {
+        mean_nx = mean_in[nrow];
+        rstd_nx = rstd_in[nrow];
+      }
+    }
+    mbar_wait(&full[stage], phase);
+    const __half* dys = reinterpret_cast<const __half*>(lns_smem + stage * 2 * tile_bytes) + warp * hidden;
+    const __half* xs = reinterpret_cast<const __half*>(lns_smem + stage * 2 * tile_bytes + tile_bytes) + warp * hidden;
+    const int row = tile * LNS_ROWS + warp;
+    if (row < rows) {
+      float xh[VPL][8], d[VPL][8];
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i)
+        if (lane + 32 * i < nvec) {
+          float xv[8];
+          load8_h(xs + 8 * (lane + 32 * i), xv);
+          load8_h(dys + 8 * (lane + 32 * i), d[i]);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            xh[i][k] = (xv[k] - mean) * rstd;
+            const float gy = d[i][k] * g[i][k];
+            s1 += gy;
+            s2 = fmaf(gy, xh[i][k], s2);
+            a_dg[i][k] = fmaf(d[i][k], xh[i][k], a_dg[i][k]);
+            a_db[i][k] += d[i][k];
+          }
+        }
+      const float c1 = warp_sum(s1) / hidden;
+      const float c2 = warp_sum(s2) / hidden;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i)
+        if (lane + 32 * i < nvec) {
+          float o[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] = rstd * (fmaf(d[i][k], g[i][k], -c1) - xh[i][k] * c2);
+          store8_h(dx + static_cast<long long>(row) * hidden + 8 * (lane + 32 * i), o);
+          if constexpr (DROP) {
+            const uint32_t keep = drop_keep8(dc, drop_group(dc, row, 8 * (lane + 32 * i), hidden));
+            drop_apply8(dc, keep, o);
+            store8_h(dxm + static_cast<long long>(row) * hidden + 8 * (lane + 32 * i), o);
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) a_dc[i][k] += o[k];  // DROP: the dropped (and rescaled) gradient
+        }
+    }
+    __syncthreads();  // every warp is done with this stage
+    if (tid == 0) {
+      const int nt = tile + stages * gridDim.x;
+      if (nt < n_tiles) issue(nt, stage);
+    }
+    if (++stage == stages) { stage = 0; phase ^= 1; }
+  }
+  // ---- block totals: warp partials meet in shared memory (all bulk copies have been consumed), one atomic per column
+  float* red = reinterpret_cast<float*>(lns_smem);  // [8 warps][hidden]
+  auto reduce_emit = [&](float (&acc)[VPL][8], float* dst) {
+    if (dst == nullptr) return;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < VPL; ++i)
+      if (lane + 32 * i < nvec) store8_f(red + warp * hidden + 8 * (lane + 32 * i), acc[i]);
+    __syncthreads();
+    for (int c = tid; c < hidden; c += LNR_THREADS) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < LNS_ROWS; ++w) t += red[w * hidden + c];
+      atomicAdd(dst + c, t * out_scale);
+    }
+  };
+  reduce_emit(a_dg, dgamma);
+  reduce_emit(a_db, dbeta);
+  reduce_emit(a_dc, dcol);
+}
+
+static int lnr_stages(int hidden) {
+  const size_t stage = static_cast<size_t>(2) * LNS_ROWS * hidden * 2;
+  int s = static_cast<int>((200 * 1024) / stage);
+  if (s > 8) s = 8;
+  if (s < 2) s = 2;
+  return s;
+}
+
+template <bool DROP>
+static int launch_ln_bwd_rows(const __half* dy, const __half* x, const float* gamma, const float* mean, const float* rstd,
+                              __half* dx, float* dgamma, float* dbeta, float* dcol, int rows, int hidden, float out_scale,
+                              __half* dxm, const cdr_dropout& drop, cudaStream_t st) {
+  const int stages = lnr_stages(hidden);
+  const size_t smem = static_cast<size_t>(stages) * 2 * LNS_ROWS * hidden * 2;
+  const int n_tiles = (rows + LNS_ROWS - 1) / LNS_ROWS;
+  const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
+  const int vpl = (hidden / 8 + 31) / 32;
+#define LNR_BWD(V)                                                                                                   \
+  do {                                                                                                               \
+    static bool cfg = false;                                                                                         \
+    if (!cfg) {                                                                                                      \
+      CDR_CUDA(cudaFuncSetAttribute(ln_bwd_rows_kernel<V, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                    200 * 1024));                                                                    \
+      cfg = true;                                                                                                    \
+    }                                                                                                                \
+    CDR_CUDA(launch_pdl(ln_bwd_rows_kernel<V, DROP>, dim3(grid), dim3(LNR_THREADS), smem, st, dy, x, gamma, mean,     \
+                        rstd, dx, dgamma, dbeta, dcol, rows, hidden, out_scale, dxm, drop, stages));                 \
+  } while (0)
+  if (vpl <= 1) LNR_BWD(1);
+  else if (vpl <= 2) LNR_BWD(2);
+  else if (vpl <= 3) LNR_BWD(3);
+  else LNR_BWD(4);
+#undef LNR_BWD
+  CDR_LAUNCH_CHECK();
+  return CDR_OK;
+}
+
+static bool ln_bwd_rows_enabled() {  // CDR_LN_BWD=phases selects the first-generation two-phase kernel (A/B runs)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CDR_LN_BWD");
+    v = (e != nullptr && e[0] == 'p') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 static int lns_grid(int rows, size_t smem_per_block) {
   const int n_tiles = (rows + LNS_ROWS - 1) / LNS_ROWS;
   int per_sm = static_cast<int>((200 * 1024) / (smem_per_block + 1024));
@@ -897,8 +1081,12 @@ int cdr_ln_bwd(const void* dy, const float* dy_cls, const void* x, const float* 
   if (n_seq <= 0 || seq_len <= 0) return CDR_OK;
   if (dy != nullptr && dy_cls == nullptr && hidden <= 1024 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(dy) & 15) == 0) {
-    // one staged pass: every row of dy and x is read from HBM once (see ln_bwd_staged_kernel)
+    // one staged pass: every row of dy and x is read from HBM once
     const int rows = n_seq * seq_len;
+    if (ln_bwd_rows_enabled())
+      return launch_ln_bwd_rows<false>(static_cast<const __half*>(dy), static_cast<const __half*>(x), gamma, mean, rstd,
+                                       static_cast<__half*>(dx), dgamma, dbeta, dbias, rows, hidden, out_scale, nullptr,
+                                       cdr_dropout{}, static_cast<cudaStream_t>(stream));
     const size_t smem = static_cast<size_t>(LNS_STAGES) * 2 * LNS_ROWS * hidden * 2;
     const int vpl = (hidden / 8 + 31) / 32;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -973,6 +1161,10 @@ int cdr_ln_bwd_drop(const void* dy, const void* x, const float* gamma, const flo
   CDR_REQUIRE(static_cast<long long>(rows) * (drop->row_mul > 0 ? drop->row_mul : 1) * (hidden / 8) < (1ll << 32),
               "cdr_ln_bwd_drop: dropout group index overflows 32 bits");
   if (rows <= 0) return CDR_OK;
+  if (ln_bwd_rows_enabled())
+    return launch_ln_bwd_rows<true>(static_cast<const __half*>(dy), static_cast<const __half*>(x), gamma, mean, rstd,
+                                    static_cast<__half*>(dx), dgamma, dbeta, dbias, rows, hidden, out_scale,
+                                    static_cast<__half*>(dx_drop), *drop, static_cast<cudaStream_t>(stream));
   const size_t smem = static_cast<size_t>(LNS_STAGES) * 2 * LNS_ROWS * hidden * 2;
   const int vpl = (hidden / 8 + 31) / 32;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

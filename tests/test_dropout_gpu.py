@@ -182,9 +182,12 @@ def test_encoder_train_mode_matches_oracle_with_same_masks(p_hidden, p_attn):
     leaf = {k: v.clone().requires_grad_(True) for k, v in bert_ref.synth_state(TINY, 0).items()}
     ref_cls = bert_ref.cls_embedding(leaf, ids.cpu(), mask.cpu(), TINY, drop=spec)
     (ref_cls * dcls).sum().backward()
-    assert _rel(cls.detach().cpu().numpy(), ref_cls.detach().numpy()) < 1e-2
-    # ... and it is NOT the eval-mode embedding
-    assert _rel(cls.detach().cpu().numpy(), bert_ref.cls_embedding(leaf, ids.cpu(), mask.cpu(), TINY).detach().numpy()) > 3e-2
+    err = _rel(cls.detach().cpu().numpy(), ref_cls.detach().numpy())
+    assert err < 1e-2
+    # ... and it is NOT the eval-mode embedding: the distance to the undropped oracle is several times the error
+    # against the oracle that applies the same masks
+    off = _rel(cls.detach().cpu().numpy(), bert_ref.cls_embedding(leaf, ids.cpu(), mask.cpu(), TINY).detach().numpy())
+    assert off > 4 * max(err, 1e-3), (off, err)
     named = dict(m.bert.named_parameters())
     for name, ref in leaf.items():
         r = _rel(named[name].grad.cpu().numpy(), ref.grad.numpy(), floor=1e-4)

@@ -35,3 +35,7 @@ def bench(name, fn, bytes_, iters=60):
 
 bench("ln fwd", lambda r: k.ln_fwd(x[r], gamma, beta, y[r], mean, rstd, None, n_seq=n_seq, seq_len=L, hidden=H, eps=1e-12), T * H * 4)
 bench("ln bwd", lambda r: k.ln_bwd(dy[r], None, x[r], gamma, mean, rstd, y[r], dg, db, dc, n_seq=n_seq, seq_len=L, hidden=H, row_ws=ws), T * H * 6)
+state = torch.tensor([1, 1], dtype=torch.int64, device="cuda")
+dxm = [torch.empty(T, H, device="cuda", dtype=torch.float16) for _ in range(ROT)]
+drop = k.drop_args(state, 3, 0.1)
+bench("ln bwd drop", lambda r: k.ln_bwd_drop(dy[r], x[r], gamma, mean, rstd, y[r], dxm[r], dg, db, dc, rows=T, hidden=H, out_scale=1.0, drop=drop), T * H * 8)
