@@ -1,109 +1,10 @@
 // Contrastive heads and DRO statistics (K8, K9/K9', K10, K12).  fp32 CUDA-core kernels: these ops are
 // latency-bound (<= 1 GFLOP, <= 2 MB) except the Gram matrix, which streams the [G, P_last] gradient
 // matrix once from HBM.  Logits stay fp32 because trained CLS dot products are ~217 with gaps ~0.3.
+// The similarity matrix of K9 / K9' is never materialised: score tiles live in registers / shared memory.
 #include "cdr_common.cuh"
 
 namespace cdr {
-
-// ------------------------------------------------------------------------------ small fp32 GEMM
-// C[m,n] (=|+=) alpha * sum_k A(m,k) * B(k,n),  A(m,k) = A[m*sam + k*sak], B(k,n) = B[k*sbk + n*sbn].
-// 64x64 tile, 256 threads, 4x4 register micro-tile, K step 16.
-constexpr int SG_T = 64, SG_K = 16;
-
-__global__ void __launch_bounds__(256)
-sgemm_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M, int N, int K,
-             long long sam, long long sak, long long sbk, long long sbn, long long ldc, float alpha) {
-  __shared__ float sA[SG_K][SG_T + 4];
-  __shared__ float sB[SG_K][SG_T + 4];
-  const int tid = threadIdx.x;
-  const int m0 = blockIdx.y * SG_T, n0 = blockIdx.x * SG_T;
-  const int tx = tid & 15, ty = tid >> 4;
-  float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += SG_K) {
-    // 64x16 elements per operand, 4 per thread; pick the thread->element map that is contiguous in
-    // memory for the operand's layout
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int e = tid + i * 256;
-      int mm, kk;
-      if (sak == 1) { kk = e & 15; mm = e >> 4; } else { mm = e & 63; kk = e >> 6; }
-      const int gm = m0 + mm, gk = k0 + kk;
-      sA[kk][mm] = (gm < M && gk < K) ? A[gm * sam + gk * sak] : 0.f;
-      int nn, kb;
-      if (sbk == 1) { kb = e & 15; nn = e >> 4; } else { nn = e & 63; kb = e >> 6; }
-      const int gn = n0 + nn, gkb = k0 + kb;
-      sB[kb][nn] = (gn < N && gkb < K) ? B[gkb * sbk + gn * sbn] : 0.f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < SG_K; ++kk) {
-      float a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = sA[kk][ty * 4 + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = sB[kk][tx * 4 + j];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
-    if (m >= M) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
-      if (n < N) C[m * ldc + n] = alpha * acc[i][j];
-    }
-  }
-}
-
-// Same contract, 16 x 16 outputs per block (one per thread): for problems with a handful of 64 x 64 tiles and a long K
-// (the 64 x 64 score matrix of the contrastive head is ONE such tile with K = 768) this spreads the work over 16x
-// more blocks.  Deterministic (no split-K atomics): the loss must not depend on the launch.
-__global__ void __launch_bounds__(256)
-sgemm_small_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M, int N, int K,
-                   long long sam, long long sak, long long sbk, long long sbn, long long ldc, float alpha) {
-  __shared__ float sA[16][65];  // [m][k]
-  __shared__ float sB[16][65];  // [n][k]
-  const int tid = threadIdx.x;
-  const int m0 = blockIdx.y * 16, n0 = blockIdx.x * 16;
-  const int tm = tid >> 4, tn = tid & 15;
-  float acc = 0.f;
-  for (int k0 = 0; k0 < K; k0 += 64) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int e = tid + i * 256;  // 16 x 64 elements per operand
-      int r, kk;
-      if (sak == 1) { kk = e & 63; r = e >> 6; } else { r = e & 15; kk = e >> 4; }
-      sA[r][kk] = (m0 + r < M && k0 + kk < K) ? A[(m0 + r) * sam + (k0 + kk) * sak] : 0.f;
-      if (sbk == 1) { kk = e & 63; r = e >> 6; } else { r = e & 15; kk = e >> 4; }
-      sB[r][kk] = (n0 + r < N && k0 + kk < K) ? B[(k0 + kk) * sbk + (n0 + r) * sbn] : 0.f;
-    }
-    __syncthreads();
-#pragma unroll 16
-    for (int kk = 0; kk < 64; ++kk) acc = fmaf(sA[tm][kk], sB[tn][kk], acc);
-    __syncthreads();
-  }
-  if (m0 + tm < M && n0 + tn < N) C[(m0 + tm) * ldc + n0 + tn] = alpha * acc;
-}
-
-static int sgemm(const float* A, const float* B, float* C, int M, int N, int K, long long sam, long long sak,
-                 long long sbk, long long sbn, long long ldc, float alpha, cudaStream_t st) {
-  if (((N + SG_T - 1) / SG_T) * ((M + SG_T - 1) / SG_T) < 16 && K >= 256) {
-    dim3 g16((N + 15) / 16, (M + 15) / 16);
-    sgemm_small_kernel<<<g16, 256, 0, st>>>(A, B, C, M, N, K, sam, sak, sbk, sbn, ldc, alpha);
-    CDR_LAUNCH_CHECK();
-    return CDR_OK;
-  }
-  dim3 grid((N + SG_T - 1) / SG_T, (M + SG_T - 1) / SG_T);
-  sgemm_kernel<<<grid, 256, 0, st>>>(A, B, C, M, N, K, sam, sak, sbk, sbn, ldc, alpha);
-  CDR_LAUNCH_CHECK();
-  return CDR_OK;
-}
 
 __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -118,37 +19,219 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) 
 
 __device__ __forceinline__ int sim_target(int mode, int gi) { return mode == CDR_SIM_COCO ? (gi ^ 1) : gi; }
 
-// one block per row: mask the diagonal (COCO), log-sum-exp, loss
-__global__ void __launch_bounds__(256)
-simmat_ce_row_kernel(float* __restrict__ S, float* __restrict__ loss, float* __restrict__ lse, int n_keys, int mode,
-                     int row_offset, float loss_scale) {
-  __shared__ float red[8];
-  const int i = blockIdx.x, gi = row_offset + i;
-  float* row = S + static_cast<long long>(i) * n_keys;
-  if (mode == CDR_SIM_COCO && threadIdx.x == 0 && gi < n_keys) row[gi] = -INFINITY;
-  __syncthreads();
-  float mx = -INFINITY;
-  for (int j = threadIdx.x; j < n_keys; j += blockDim.x) mx = fmaxf(mx, row[j]);
-  mx = block_reduce(mx, red, true);
-  float s = 0.f;
-  for (int j = threadIdx.x; j < n_keys; j += blockDim.x) s += expf(row[j] - mx);
-  s = block_reduce(s, red, false);
-  if (threadIdx.x == 0) {
-    const float l = mx + logf(s);
-    lse[i] = l;
-    loss[i] = loss_scale * (l - row[sim_target(mode, gi)]);
+// ------------------------------------------------------------------------------ fused similarity matrix + CE (K9 / K9')
+// S = q k^T is never written to memory (COCO/modeling.py:244-248 materialises it: matmul, fill_diagonal_, cross_entropy).
+// All three kernels share one tile step: a block keeps SIM_TO "outer" vectors resident in shared memory ([16][dim] fp32)
+// and streams "inner" vectors in tiles of SIM_TI = 64, 32 dimensions at a time; thread (o, ic) of 256 holds the four
+// products A[o][ic + 16 u] in registers.
+//   forward  (rows outer, keys inner): online softmax over the key tiles of the block's key range -> per (row, split)
+//            partial (max, sum) + the target logit; simmat_combine_kernel folds the splits into lse / loss
+//   backward (rows outer -> dq, keys outer -> dk): the tile of S is recomputed, turned into
+//            G = dloss * loss_scale * (exp(S - lse) - [key == target]) in shared memory, and the block accumulates
+//            G (or G^T) times the SAME streamed inner vectors into its outer gradient rows (registers, 2 dims per
+//            thread and 32-dim chunk); splits of the inner range add into the zero-filled output with atomics
+constexpr int SIM_TO = 16, SIM_TI = 64, SIM_DC = 32, SIM_THREADS = 256;
+constexpr int SIM_MAX_DIM = 2048;
+
+struct SimParams {
+  const float* q;      // [n_rows, dim]
+  const float* k;      // [n_keys, dim]
+  const float* lse;    // [n_rows]   (backward)
+  const float* dloss;  // [n_rows]   (backward)
+  float* part;         // forward: [n_rows, n_splits, 2] partial (max, sum)
+  float* tgt;          // forward: [n_rows] target logit
+  float* out;          // backward: dq [n_rows, dim] or dk [n_keys, dim]
+  int n_rows, n_keys, dim, mode, row_offset, n_splits, inner_per_split;
+  float loss_scale;
+};
+
+// A[o][ic + 16 u] (u < 4) for the outer tile in sX and inner vectors Y[i0 .. i0 + 64)
+__device__ __forceinline__ void sim_tile_products(const float* __restrict__ sX, float (*sY)[SIM_DC + 1],
+                                                  const float* __restrict__ Y, int n_inner, int i0, int dim, int o,
+                                                  int ic, float (&acc)[4]) {
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) acc[u] = 0.f;
+  for (int c0 = 0; c0 < dim; c0 += SIM_DC) {
+    __syncthreads();  // the previous chunk (or the caller's use of sY) is finished
+#pragma unroll
+    for (int e = 0; e < SIM_TI * SIM_DC / SIM_THREADS; ++e) {
+      const int idx = tid + e * SIM_THREADS;
+      const int j = idx >> 5, dd = idx & 31;
+      sY[j][dd] = (i0 + j < n_inner && c0 + dd < dim) ? Y[static_cast<long long>(i0 + j) * dim + c0 + dd] : 0.f;
+    }
+    __syncthreads();
+    const int nd = min(SIM_DC, dim - c0);
+    for (int dd = 0; dd < nd; ++dd) {
+      const float x = sX[o * dim + c0 + dd];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] = fmaf(x, sY[ic + 16 * u][dd], acc[u]);
+    }
   }
 }
 
-__global__ void __launch_bounds__(256)
-simmat_ce_grad_kernel(const float* __restrict__ S, const float* __restrict__ lse, const float* __restrict__ dloss,
-                      float* __restrict__ G, int n_keys, int mode, int row_offset, float loss_scale) {
-  const int i = blockIdx.x, gi = row_offset + i;
-  const float l = lse[i], g = dloss[i] * loss_scale;
-  const int t = sim_target(mode, gi);
-  const float* row = S + static_cast<long long>(i) * n_keys;
-  float* out = G + static_cast<long long>(i) * n_keys;
-  for (int j = threadIdx.x; j < n_keys; j += blockDim.x) out[j] = g * (expf(row[j] - l) - (j == t ? 1.f : 0.f));
+__device__ __forceinline__ void sim_load_outer(float* sX, const float* __restrict__ X, int n_outer, int o0, int dim) {
+  for (int e = threadIdx.x; e < SIM_TO * dim; e += SIM_THREADS) {
+    const int o = e / dim, d = e - o * dim;
+    sX[e] = (o0 + o < n_outer) ? X[static_cast<long long>(o0 + o) * dim + d] : 0.f;
+  }
+}
+
+__device__ __forceinline__ float half_warp_max(float v) {
+#pragma unroll
+  for (int s = 8; s > 0; s >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, s));
+  return v;
+}
+__device__ __forceinline__ float half_warp_sum(float v) {
+#pragma unroll
+  for (int s = 8; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+  return v;
+}
+
+__global__ void __launch_bounds__(SIM_THREADS)
+simmat_fused_fwd_kernel(const SimParams p) {
+  extern __shared__ float sim_smem[];
+  float* sX = sim_smem;                                                        // [16][dim]
+  float (*sY)[SIM_DC + 1] = reinterpret_cast<float (*)[SIM_DC + 1]>(sim_smem + SIM_TO * p.dim);  // [64][33]
+  const int o = threadIdx.x >> 4, ic = threadIdx.x & 15;
+  const int r0 = blockIdx.x * SIM_TO, split = blockIdx.y;
+  const int k_begin = split * p.inner_per_split, k_end = min(p.n_keys, k_begin + p.inner_per_split);
+  sim_load_outer(sX, p.q, p.n_rows, r0, p.dim);
+  const int row = r0 + o, gi = p.row_offset + row;
+  const int t = sim_target(p.mode, gi);
+  float m = -INFINITY, l = 0.f;
+  for (int j0 = k_begin; j0 < k_end; j0 += SIM_TI) {
+    float a[4];
+    sim_tile_products(sX, sY, p.k, k_end, j0, p.dim, o, ic, a);
+    float tmax = -INFINITY;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int key = j0 + ic + 16 * u;
+      if (key >= k_end || (p.mode == CDR_SIM_COCO && key == gi)) a[u] = -INFINITY;
+      if (key == t && key < k_end && row < p.n_rows) p.tgt[row] = a[u];
+      tmax = fmaxf(tmax, a[u]);
+    }
+    tmax = half_warp_max(tmax);
+    const float m_new = fmaxf(m, tmax);
+    float s = 0.f;
+    if (m_new > -INFINITY) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) s += expf(a[u] - m_new);
+      l = l * expf(m - m_new);
+    }
+    l += half_warp_sum(s);
+    m = m_new;
+  }
+  if (ic == 0 && row < p.n_rows) {
+    float* dst = p.part + (static_cast<long long>(row) * p.n_splits + split) * 2;
+    dst[0] = m;
+    dst[1] = l;
+  }
+}
+
+__global__ void simmat_combine_kernel(const float* __restrict__ part, const float* __restrict__ tgt, int n_rows,
+                                      int n_splits, float loss_scale, float* __restrict__ loss, float* __restrict__ lse) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows) return;
+  const float* pr = part + static_cast<long long>(i) * n_splits * 2;
+  float m = -INFINITY;
+  for (int s = 0; s < n_splits; ++s) m = fmaxf(m, pr[2 * s]);
+  float l = 0.f;
+  for (int s = 0; s < n_splits; ++s)
+    if (pr[2 * s] > -INFINITY) l += pr[2 * s + 1] * expf(pr[2 * s] - m);
+  const float v = m + logf(l);
+  lse[i] = v;
+  loss[i] = loss_scale * (v - tgt[i]);
+}
+
+// KEYS_OUTER = false: outer = query rows (out = dq), inner = keys.  true: outer = keys (out = dk), inner = rows.
+template <bool KEYS_OUTER>
+__global__ void __launch_bounds__(SIM_THREADS)
+simmat_fused_bwd_kernel(const SimParams p) {
+  extern __shared__ float sim_smem[];
+  float* sX = sim_smem;                                                                        // [16][dim]
+  float (*sY)[SIM_DC + 1] = reinterpret_cast<float (*)[SIM_DC + 1]>(sim_smem + SIM_TO * p.dim);  // [64][33]
+  float (*sG)[SIM_TI + 1] = reinterpret_cast<float (*)[SIM_TI + 1]>(sim_smem + SIM_TO * p.dim + SIM_TI * (SIM_DC + 1));
+  const int o = threadIdx.x >> 4, ic = threadIdx.x & 15;
+  const int o0 = blockIdx.x * SIM_TO, split = blockIdx.y;
+  const float* X = KEYS_OUTER ? p.k : p.q;
+  const float* Y = KEYS_OUTER ? p.q : p.k;
+  const int n_outer = KEYS_OUTER ? p.n_keys : p.n_rows;
+  const int n_inner = KEYS_OUTER ? p.n_rows : p.n_keys;
+  const int i_begin = split * p.inner_per_split, i_end = min(n_inner, i_begin + p.inner_per_split);
+  sim_load_outer(sX, X, n_outer, o0, p.dim);
+  const int n_chunks = (p.dim + SIM_DC - 1) / SIM_DC;
+  float acc2[SIM_MAX_DIM / SIM_DC][2];
+#pragma unroll
+  for (int c = 0; c < SIM_MAX_DIM / SIM_DC; ++c) acc2[c][0] = acc2[c][1] = 0.f;
+  for (int i0 = i_begin; i0 < i_end; i0 += SIM_TI) {
+    float a[4];
+    sim_tile_products(sX, sY, Y, i_end, i0, p.dim, o, ic, a);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int inner = i0 + ic + 16 * u;
+      const int row = KEYS_OUTER ? inner : o0 + o;
+      const int key = KEYS_OUTER ? o0 + o : inner;
+      float gval = 0.f;
+      if (row < p.n_rows && key < p.n_keys && inner < i_end) {
+        const int gi = p.row_offset + row;
+        const float sc = (p.mode == CDR_SIM_COCO && key == gi) ? -INFINITY : a[u];
+        gval = __ldg(p.dloss + row) * p.loss_scale * (expf(sc - __ldg(p.lse + row)) - (key == sim_target(p.mode, gi) ? 1.f : 0.f));
+      }
+      sG[o][ic + 16 * u] = gval;
+    }
+    // out[o][d] += sum_i G[o][i] * Y[i][d], the inner tile streamed once more in 32-dim chunks
+    for (int c = 0; c < n_chunks; ++c) {
+      __syncthreads();  // sG complete (first chunk) / previous chunk consumed
+#pragma unroll
+      for (int e = 0; e < SIM_TI * SIM_DC / SIM_THREADS; ++e) {
+        const int idx = threadIdx.x + e * SIM_THREADS;
+        const int j = idx >> 5, dd = idx & 31;
+        sY[j][dd] = (i0 + j < i_end && c * SIM_DC + dd < p.dim) ? Y[static_cast<long long>(i0 + j) * p.dim + c * SIM_DC + dd] : 0.f;
+      }
+      __syncthreads();
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+      for (int j = 0; j < SIM_TI; ++j) {
+        const float gv = sG[o][j];
+        s0 = fmaf(gv, sY[j][2 * ic], s0);
+        s1 = fmaf(gv, sY[j][2 * ic + 1], s1);
+      }
+      // (acc2 is indexed by the chunk loop: keep the loop bounded by a compile-time maximum so it stays in registers)
+#pragma unroll
+      for (int cc = 0; cc < SIM_MAX_DIM / SIM_DC; ++cc)
+        if (cc == c) {
+          acc2[cc][0] += s0;
+          acc2[cc][1] += s1;
+        }
+    }
+  }
+  if (o0 + o < n_outer) {
+    float* dst = p.out + static_cast<long long>(o0 + o) * p.dim;
+#pragma unroll
+    for (int c = 0; c < SIM_MAX_DIM / SIM_DC; ++c) {
+      const int d = c * SIM_DC + 2 * ic;
+      if (c < n_chunks && d < p.dim) {
+        if (p.n_splits > 1) {
+          atomicAdd(dst + d, acc2[c][0]);
+          if (d + 1 < p.dim) atomicAdd(dst + d + 1, acc2[c][1]);
+        } else {
+          dst[d] = acc2[c][0];
+          if (d + 1 < p.dim) dst[d + 1] = acc2[c][1];
+        }
+      }
+    }
+  }
+}
+
+static int sim_splits(int n_outer, int n_inner) {
+  const int tiles = (n_outer + SIM_TO - 1) / SIM_TO;
+  const int max_splits = (n_inner + SIM_TI - 1) / SIM_TI;
+  int s = (2 * sm_count() + tiles - 1) / tiles;
+  if (s > max_splits) s = max_splits;
+  if (s > 64) s = 64;
+  if (s < 1) s = 1;
+  return s;
 }
 
 // dk_own[i, :] = dloss[i] * (exp(-loss[i]) - 1) * q[i, :]   (softmax_i,own = exp(s_own - lse_i) = exp(-loss_i))
@@ -377,8 +460,9 @@ int cdr_pair_nll_bwd(const float* q, const float* a, const float* b, const float
 
 static int simmat_check(const cdr_simmat_args* a, const char* who) {
   CDR_REQUIRE(a != nullptr, "%s: null args", who);
-  CDR_REQUIRE(a->q && a->k && a->scores && a->lse, "%s: null pointer", who);
+  CDR_REQUIRE(a->q && a->k && a->lse, "%s: null pointer", who);
   CDR_REQUIRE(a->n_rows > 0 && a->n_keys > 0 && a->dim > 0, "%s: empty problem", who);
+  CDR_REQUIRE(a->dim <= SIM_MAX_DIM, "%s: dim %d > %d", who, a->dim, SIM_MAX_DIM);
   CDR_REQUIRE(a->mode == CDR_SIM_QP || a->mode == CDR_SIM_COCO, "%s: bad mode %d", who, a->mode);
   CDR_REQUIRE(a->row_offset >= 0 && a->row_offset + a->n_rows <= a->n_keys,
               "%s: rows [%d, %d) are not a subset of the %d keys", who, a->row_offset, a->row_offset + a->n_rows,
@@ -388,32 +472,75 @@ static int simmat_check(const cdr_simmat_args* a, const char* who) {
   return CDR_OK;
 }
 
+size_t cdr_simmat_workspace_bytes(int32_t n_rows, int32_t n_keys) {
+  if (n_rows <= 0 || n_keys <= 0) return 0;
+  return static_cast<size_t>(n_rows) * (2 * static_cast<size_t>(sim_splits(n_rows, n_keys)) + 1) * sizeof(float);
+}
+
+static size_t sim_smem_bytes(int dim, bool bwd) {
+  return sizeof(float) * (static_cast<size_t>(SIM_TO) * dim + SIM_TI * (SIM_DC + 1) + (bwd ? SIM_TO * (SIM_TI + 1) : 0));
+}
+
+static void sim_params(const cdr_simmat_args* a, SimParams& p) {
+  p.q = a->q; p.k = a->k; p.lse = a->lse; p.dloss = a->dloss;
+  p.n_rows = a->n_rows; p.n_keys = a->n_keys; p.dim = a->dim; p.mode = a->mode; p.row_offset = a->row_offset;
+  p.loss_scale = a->loss_scale;
+}
+
 int cdr_simmat_ce_fwd(const cdr_simmat_args* a, void* stream) {
   if (int rc = simmat_check(a, "cdr_simmat_ce_fwd")) return rc;
-  CDR_REQUIRE(a->loss != nullptr, "cdr_simmat_ce_fwd: null loss");
+  CDR_REQUIRE(a->loss != nullptr && a->scores != nullptr, "cdr_simmat_ce_fwd: null loss / workspace");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // S[i,j] = <q_i, k_j>
-  if (int rc = sgemm(a->q, a->k, a->scores, a->n_rows, a->n_keys, a->dim, a->dim, 1, 1, a->dim, a->n_keys, 1.f, st))
-    return rc;
-  simmat_ce_row_kernel<<<a->n_rows, 256, 0, st>>>(a->scores, a->loss, a->lse, a->n_keys, a->mode, a->row_offset,
-                                                  a->loss_scale);
+  SimParams p{};
+  sim_params(a, p);
+  p.n_splits = sim_splits(a->n_rows, a->n_keys);
+  p.inner_per_split = ((a->n_keys + p.n_splits - 1) / p.n_splits + SIM_TI - 1) / SIM_TI * SIM_TI;
+  p.n_splits = (a->n_keys + p.inner_per_split - 1) / p.inner_per_split;
+  p.part = a->scores;  // workspace: [n_rows, n_splits, 2] partials | [n_rows] target logits
+  p.tgt = a->scores + static_cast<size_t>(a->n_rows) * p.n_splits * 2;
+  const size_t smem = sim_smem_bytes(a->dim, false);
+  static bool cfg = false;
+  if (!cfg) {
+    CDR_CUDA(cudaFuncSetAttribute(simmat_fused_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CDR_CUDA(cudaFuncSetAttribute(simmat_fused_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CDR_CUDA(cudaFuncSetAttribute(simmat_fused_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    cfg = true;
+  }
+  simmat_fused_fwd_kernel<<<dim3((a->n_rows + SIM_TO - 1) / SIM_TO, p.n_splits), SIM_THREADS, smem, st>>>(p);
+  CDR_LAUNCH_CHECK();
+  simmat_combine_kernel<<<(a->n_rows + 127) / 128, 128, 0, st>>>(p.part, p.tgt, a->n_rows, p.n_splits, a->loss_scale,
+                                                                a->loss, a->lse);
   CDR_LAUNCH_CHECK();
   return CDR_OK;
 }
 
 int cdr_simmat_ce_bwd(const cdr_simmat_args* a, void* stream) {
   if (int rc = simmat_check(a, "cdr_simmat_ce_bwd")) return rc;
-  CDR_REQUIRE(a->gmat && a->dloss, "cdr_simmat_ce_bwd: null pointer");
+  CDR_REQUIRE(a->dloss != nullptr, "cdr_simmat_ce_bwd: null dloss");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  simmat_ce_grad_kernel<<<a->n_rows, 256, 0, st>>>(a->scores, a->lse, a->dloss, a->gmat, a->n_keys, a->mode,
-                                                   a->row_offset, a->loss_scale);
-  CDR_LAUNCH_CHECK();
-  if (a->dq)  // dq[i,d] = sum_j G[i,j] k[j,d]
-    if (int rc = sgemm(a->gmat, a->k, a->dq, a->n_rows, a->dim, a->n_keys, a->n_keys, 1, a->dim, 1, a->dim, 1.f, st))
-      return rc;
-  if (a->dk)  // dk[j,d] = sum_i G[i,j] q[i,d]
-    if (int rc = sgemm(a->gmat, a->q, a->dk, a->n_keys, a->dim, a->n_rows, 1, a->n_keys, a->dim, 1, a->dim, 1.f, st))
-      return rc;
+  const size_t smem = sim_smem_bytes(a->dim, true);
+  static bool cfg = false;
+  if (!cfg) {
+    CDR_CUDA(cudaFuncSetAttribute(simmat_fused_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CDR_CUDA(cudaFuncSetAttribute(simmat_fused_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    cfg = true;
+  }
+  for (int pass = 0; pass < 2; ++pass) {
+    float* out = pass == 0 ? a->dq : a->dk;
+    if (out == nullptr) continue;
+    const int n_outer = pass == 0 ? a->n_rows : a->n_keys, n_inner = pass == 0 ? a->n_keys : a->n_rows;
+    SimParams p{};
+    sim_params(a, p);
+    p.out = out;
+    p.n_splits = sim_splits(n_outer, n_inner);
+    p.inner_per_split = ((n_inner + p.n_splits - 1) / p.n_splits + SIM_TI - 1) / SIM_TI * SIM_TI;
+    p.n_splits = (n_inner + p.inner_per_split - 1) / p.inner_per_split;
+    if (p.n_splits > 1) CDR_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * static_cast<size_t>(n_outer) * a->dim, st));
+    const dim3 grid((n_outer + SIM_TO - 1) / SIM_TO, p.n_splits);
+    if (pass == 0) simmat_fused_bwd_kernel<false><<<grid, SIM_THREADS, smem, st>>>(p);
+    else simmat_fused_bwd_kernel<true><<<grid, SIM_THREADS, smem, st>>>(p);
+    CDR_LAUNCH_CHECK();
+  }
   return CDR_OK;
 }
 

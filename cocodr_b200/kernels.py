@@ -317,31 +317,39 @@ def pair_nll_bwd(q, a, b, logits, dloss, dq, da, db):
 SIM_QP, SIM_COCO = 0, 1
 
 
-def _simmat_args(q, k, scores, lse, mode, row_offset, loss_scale):
+def _simmat_args(q, k, lse, mode, row_offset, loss_scale):
     a = _lib.SimmatArgs()
-    a.q, a.k, a.scores, a.lse = q.data_ptr(), k.data_ptr(), scores.data_ptr(), lse.data_ptr()
+    a.q, a.k, a.lse = q.data_ptr(), k.data_ptr(), lse.data_ptr()
     a.n_rows, a.n_keys, a.dim = q.shape[0], k.shape[0], q.shape[1]
     a.mode, a.row_offset, a.loss_scale = mode, row_offset, loss_scale
     return a
 
 
-def simmat_ce_fwd(q, k, scores, loss, lse, *, mode, row_offset=0, loss_scale=1.0):
-    _need_cuda(q, k, scores, loss, lse)
+def simmat_workspace(n_rows, n_keys, device):
+    """fp32 workspace of the fused similarity / cross-entropy forward (per-split softmax partials, NOT the scores)."""
+    n = int(_lib_().cdr_simmat_workspace_bytes(_i32(n_rows), _i32(n_keys)))
+    return torch.empty(max(1, n // 4), dtype=torch.float32, device=device)
+
+
+def simmat_ce_fwd(q, k, loss, lse, *, mode, row_offset=0, loss_scale=1.0, workspace=None):
+    _need_cuda(q, k, loss, lse)
     assert q.dtype == torch.float32 and k.dtype == torch.float32 and q.is_contiguous() and k.is_contiguous()
-    a = _simmat_args(q, k, scores, lse, mode, row_offset, loss_scale)
-    a.loss = loss.data_ptr()
+    ws = workspace if workspace is not None else simmat_workspace(q.shape[0], k.shape[0], q.device)
+    a = _simmat_args(q, k, lse, mode, row_offset, loss_scale)
+    a.loss, a.scores = loss.data_ptr(), ws.data_ptr()
     _run("cdr_simmat_ce_fwd", lambda: _lib_().cdr_simmat_ce_fwd(C.byref(a), stream_ptr()))
     _count(2)
 
 
-def simmat_ce_bwd(q, k, scores, lse, dloss, gmat, dq, dk, *, mode, row_offset=0, loss_scale=1.0):
-    _need_cuda(q, k, scores, dloss, gmat)
-    a = _simmat_args(q, k, scores, lse, mode, row_offset, loss_scale)
-    a.dloss, a.gmat = dloss.data_ptr(), gmat.data_ptr()
+def simmat_ce_bwd(q, k, lse, dloss, dq, dk, *, mode, row_offset=0, loss_scale=1.0):
+    _need_cuda(q, k, lse, dloss)
+    assert dloss.dtype == torch.float32 and dloss.is_contiguous()
+    a = _simmat_args(q, k, lse, mode, row_offset, loss_scale)
+    a.dloss = dloss.data_ptr()
     a.dq = dq.data_ptr() if dq is not None else 0
     a.dk = dk.data_ptr() if dk is not None else 0
     _run("cdr_simmat_ce_bwd", lambda: _lib_().cdr_simmat_ce_bwd(C.byref(a), stream_ptr()))
-    _count(3)
+    _count((dq is not None) + (dk is not None))
 
 
 def own_key_grad(q, loss, dloss, dk_own):

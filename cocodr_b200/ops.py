@@ -532,27 +532,27 @@ class PairNLL(torch.autograd.Function):
 
 
 class SimmatCE(torch.autograd.Function):
-    """K9 / K9': per-row softmax cross-entropy over the similarity matrix q k^T (fp32)."""
+    """K9 / K9': per-row softmax cross-entropy over the similarity matrix q k^T (fp32), fused: the scores are never
+    written to memory (forward: online softmax over key tiles; backward: tiles recomputed from q, k and the row lse)."""
 
     @staticmethod
     def forward(ctx, q, k, mode, row_offset, loss_scale):
         q, k = q.contiguous().float(), k.contiguous().float()
-        n, m = q.shape[0], k.shape[0]
+        n = q.shape[0]
         dev = q.device
-        scores, loss, lse = _f32(n, m, dev=dev), _f32(n, dev=dev), _f32(n, dev=dev)
-        K.simmat_ce_fwd(q, k, scores, loss, lse, mode=mode, row_offset=row_offset, loss_scale=loss_scale)
-        ctx.save_for_backward(q, k, scores, lse)
+        loss, lse = _f32(n, dev=dev), _f32(n, dev=dev)
+        K.simmat_ce_fwd(q, k, loss, lse, mode=mode, row_offset=row_offset, loss_scale=loss_scale)
+        ctx.save_for_backward(q, k, lse)
         ctx.cfg = (mode, row_offset, loss_scale)
         return loss
 
     @staticmethod
     def backward(ctx, dloss):
-        q, k, scores, lse = ctx.saved_tensors
+        q, k, lse = ctx.saved_tensors
         mode, row_offset, loss_scale = ctx.cfg
-        gmat = torch.empty_like(scores)
         dq = torch.empty_like(q) if ctx.needs_input_grad[0] else None
         dk = torch.empty_like(k) if ctx.needs_input_grad[1] else None
-        K.simmat_ce_bwd(q, k, scores, lse, dloss.contiguous().float(), gmat, dq, dk, mode=mode, row_offset=row_offset,
+        K.simmat_ce_bwd(q, k, lse, dloss.contiguous().float(), dq, dk, mode=mode, row_offset=row_offset,
                         loss_scale=loss_scale)
         return dq, dk, None, None, None
 
@@ -589,21 +589,20 @@ class OwnPairCE(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, p_own, keys, row_offset):
         q, keys = q.contiguous().float(), keys.detach().contiguous().float()
-        n, m = q.shape[0], keys.shape[0]
+        n = q.shape[0]
         dev = q.device
-        scores, loss, lse = _f32(n, m, dev=dev), _f32(n, dev=dev), _f32(n, dev=dev)
-        K.simmat_ce_fwd(q, keys, scores, loss, lse, mode=K.SIM_QP, row_offset=row_offset, loss_scale=1.0)
-        ctx.save_for_backward(q, keys, scores, lse, loss)
+        loss, lse = _f32(n, dev=dev), _f32(n, dev=dev)
+        K.simmat_ce_fwd(q, keys, loss, lse, mode=K.SIM_QP, row_offset=row_offset, loss_scale=1.0)
+        ctx.save_for_backward(q, keys, lse, loss)
         ctx.row_offset = row_offset
         return loss
 
     @staticmethod
     def backward(ctx, dloss):
-        q, keys, scores, lse, loss = ctx.saved_tensors
+        q, keys, lse, loss = ctx.saved_tensors
         dloss = dloss.contiguous().float()
         dq = torch.empty_like(q)
-        K.simmat_ce_bwd(q, keys, scores, lse, dloss, torch.empty_like(scores), dq, None, mode=K.SIM_QP,
-                        row_offset=ctx.row_offset, loss_scale=1.0)
+        K.simmat_ce_bwd(q, keys, lse, dloss, dq, None, mode=K.SIM_QP, row_offset=ctx.row_offset, loss_scale=1.0)
         dp = torch.empty_like(q)
         K.own_key_grad(q, loss, dloss, dp)  # dS_i,own = dloss_i * (softmax_i,own - 1) = dloss_i * (exp(-loss_i) - 1)
         return dq, dp, None, None

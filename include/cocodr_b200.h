@@ -288,13 +288,17 @@ int cdr_pair_nll_bwd(const float* q, const float* a, const float* b, const float
  *   CDR_SIM_COCO (COCO/modeling.py:244-248): S = q k^T, S[i, row_offset+i] = -inf,
  *                target_i = (row_offset+i) ^ 1, loss_i = loss_scale * CE(S[i,:], target_i)
  *   CDR_SIM_QP   (in-batch q x p InfoNCE over all-gathered passages): target_i = row_offset + i.
- * bwd: dq (optional) = dS k, dk (optional) = dS^T q with dS = loss_scale*dloss_i*(softmax - onehot). */
+ * bwd: dq (optional) = dS k, dk (optional) = dS^T q with dS = loss_scale*dloss_i*(softmax - onehot), the score tiles
+ * recomputed from q, k and the saved row log-sum-exps (fused gather -> q k^T -> softmax-CE, SURVEY K9: S is never
+ * materialised; dim <= 2048). */
 enum { CDR_SIM_QP = 0, CDR_SIM_COCO = 1 };
 typedef struct cdr_simmat_args {
   const float* q;     /* [n_rows, dim] */
   const float* k;     /* [n_keys, dim] */
-  float* scores;      /* [n_rows, n_keys] workspace: fwd writes, bwd reads */
-  float* gmat;        /* [n_rows, n_keys] workspace: bwd scratch */
+  float* scores;      /* fwd: workspace of cdr_simmat_workspace_bytes(n_rows, n_keys) bytes (per-split softmax partials;
+                         the score matrix itself is NEVER written: tiles of q k^T live in registers / shared memory, in
+                         the forward and again in the backward).  bwd: unused, may be NULL */
+  float* gmat;        /* unused (kept for layout compatibility), may be NULL */
   float* loss;        /* [n_rows] fwd out */
   float* lse;         /* [n_rows] fwd out, bwd in */
   const float* dloss; /* [n_rows] bwd in */
@@ -303,6 +307,7 @@ typedef struct cdr_simmat_args {
   int32_t n_rows, n_keys, dim, mode, row_offset;
   float loss_scale;
 } cdr_simmat_args;
+size_t cdr_simmat_workspace_bytes(int32_t n_rows, int32_t n_keys);
 int cdr_simmat_ce_fwd(const cdr_simmat_args* args, void* stream);
 int cdr_simmat_ce_bwd(const cdr_simmat_args* args, void* stream);
 /* CDR_SIM_QP, gradient of row i towards its OWN key only: dk_own[i, :] = dloss[i] * (softmax_i,own - 1) * q[i, :] with

@@ -132,6 +132,55 @@ def main():
         dist.barrier()
     model.enable_peer_gather(False)
 
+    # 7. GradSync when a layer's flat gradient buffer must NOT be reduced in place during backward: (a) unfused towers
+    #    (q_len != p_len, the reference's default 64 / 128: every layer runs twice per backward), (b) gradient
+    #    accumulation over two backward passes.  Reference: all-reduce of the locally accumulated gradients.
+    qs, qsm = (t.to(dev) for t in bert_ref.synth_batch(4, 16, 2000, 300 + rank))
+
+    def two_steps(use_sync):
+        model.zero_grad(set_to_none=True)
+        s_ = GradSync(model) if use_sync else None
+        for rep in range(2):
+            loss = model(qs, qsm, pi, pm, weights=w)[0]  # 16-token queries, 32-token passages: towers run separately
+            if s_ is not None:
+                with s_:
+                    loss.backward()
+            else:
+                loss.backward()
+        torch.cuda.synchronize()
+        return {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}, s_
+
+    ref_g, _ = two_steps(False)
+    for t in ref_g.values():
+        dist.all_reduce(t)
+        t /= world
+    got_g, s_ = two_steps(True)
+    assert s_.stats["overlapped"] == 0 and s_.stats["deferred"] > 0, s_.stats  # second backward of two: all deferred
+    for n, t in ref_g.items():
+        err = (got_g[n] - t).abs().max().item()
+        assert err <= 1e-5 + 2e-3 * t.abs().max().item(), (n, err)
+
+    # 8. iDRO on the in-batch head at world > 1: ranks hold DIFFERENT groups, so per-group partial backwards through the
+    #    gathered keys would issue mismatched collectives; the group gradients come from collective-free loss views
+    #    (models.BertDot_InBatch_NLL_LN.idro_group_grads).  Must not hang or produce non-finite weights / gradients.
+    for mode in ("own-pair", "local-batch"):
+        model.idro_group_grads = mode
+        model.add_group_loss(types.SimpleNamespace(model_size="base", local_rank=local), 6, "idro", 0.25, 0.01, 0.1, 0.05)
+        model.loss.para_name = {}
+        gid = torch.tensor([0, 1, 1, 2] if rank == 0 else [3, 3, 4, 0], device=dev)
+        for rep in range(2):
+            model.zero_grad(set_to_none=True)
+            robust = model(qi, qm, pi, pm, group_ids=gid, weights=w)[0]
+            s2 = GradSync(model)
+            with s2:
+                robust.backward()
+        torch.cuda.synchronize()
+        # (h_fun is per rank: the reference mixes LOCAL group means / masks with the rank-summed gradients)
+        h = model.loss.h_fun.clone()
+        assert torch.isfinite(h).all() and abs(h.sum().item() - 1.0) < 0.2, (mode, h)
+        assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
+    model.dro_type = 'erm'
+
     dist.barrier()
     if rank == 0:
         print(f"MULTIGPU_OK world={world}")

@@ -46,12 +46,11 @@ def _coco(e, row_offset=0, n_rows=None, loss_scale=1.0, dloss=None):
     n_rows = n if n_rows is None else n_rows
     ec = e.cuda().contiguous()
     q = ec[row_offset:row_offset + n_rows]
-    scores, gmat = torch.empty(n_rows, n, device="cuda"), torch.empty(n_rows, n, device="cuda")
     loss, lse = torch.empty(n_rows, device="cuda"), torch.empty(n_rows, device="cuda")
-    k.simmat_ce_fwd(q, ec, scores, loss, lse, mode=k.SIM_COCO, row_offset=row_offset, loss_scale=loss_scale)
+    k.simmat_ce_fwd(q, ec, loss, lse, mode=k.SIM_COCO, row_offset=row_offset, loss_scale=loss_scale)
     dq, dk = torch.empty(n_rows, h, device="cuda"), torch.empty(n, h, device="cuda")
     dl = torch.full((n_rows,), 1.0 / n_rows, device="cuda") if dloss is None else dloss.cuda()
-    k.simmat_ce_bwd(q, ec, scores, lse, dl, gmat, dq, dk, mode=k.SIM_COCO, row_offset=row_offset, loss_scale=loss_scale)
+    k.simmat_ce_bwd(q, ec, lse, dl, dq, dk, mode=k.SIM_COCO, row_offset=row_offset, loss_scale=loss_scale)
     return loss.cpu(), dq.cpu(), dk.cpu()
 
 
@@ -86,12 +85,11 @@ def test_qp_infonce_matches_oracle():
     w = torch.rand(B)
     (ref * w).sum().backward()
     Qc, Pc = Q.detach().cuda(), P.detach().cuda()
-    scores, gmat = torch.empty(B, B * W, device="cuda"), torch.empty(B, B * W, device="cuda")
     loss, lse = torch.empty(B, device="cuda"), torch.empty(B, device="cuda")
-    k.simmat_ce_fwd(Qc, Pc, scores, loss, lse, mode=k.SIM_QP, row_offset=r * B)
+    k.simmat_ce_fwd(Qc, Pc, loss, lse, mode=k.SIM_QP, row_offset=r * B)
     np.testing.assert_allclose(loss.cpu().numpy(), ref.detach().numpy(), rtol=1e-4, atol=1e-5)
     dq, dk = torch.empty(B, h, device="cuda"), torch.empty(B * W, h, device="cuda")
-    k.simmat_ce_bwd(Qc, Pc, scores, lse, w.cuda(), gmat, dq, dk, mode=k.SIM_QP, row_offset=r * B)
+    k.simmat_ce_bwd(Qc, Pc, lse, w.cuda(), dq, dk, mode=k.SIM_QP, row_offset=r * B)
     np.testing.assert_allclose(dq.cpu().numpy(), Q.grad.numpy(), rtol=1e-3, atol=1e-5)
     np.testing.assert_allclose(dk.cpu().numpy(), P.grad.numpy(), rtol=1e-3, atol=1e-5)
 
@@ -117,3 +115,41 @@ def test_group_reduce_and_gram():
     k.gram_f32(X.cuda(), gram)
     ref = (X.double() @ X.double().t()).float()
     np.testing.assert_allclose(gram.cpu().numpy(), ref.numpy(), rtol=2e-4, atol=2e-2)
+
+
+@pytest.mark.parametrize("n_rows,n_keys,dim,mode,off", [(64, 512, 768, "qp", 128), (7, 23, 40, "qp", 5), (37, 130, 96, "qp", 0),
+                                                        (512, 512, 1024, "coco", 0), (20, 64, 128, "coco", 16),
+                                                        (3, 6, 8, "coco", 2), (200, 1000, 2048, "qp", 300)])
+def test_fused_simmat_ragged_shapes(n_rows, n_keys, dim, mode, off):
+    """The fused K9 / K9' kernels (score tiles in registers, online softmax, recomputed in the backward) on shapes that
+    do not divide the 16 x 64 x 32 tiling, with few and many key splits, vs the torch restatement."""
+    from cocodr_b200 import kernels as k
+    g = torch.Generator().manual_seed(n_rows * 7 + n_keys)
+    K_ = (torch.randn(n_keys, dim, generator=g) * (3.0 / dim ** 0.5)).requires_grad_(True)
+    if mode == "coco":
+        Q = K_[off:off + n_rows]
+        S = Q @ K_.t()
+        idx = torch.arange(n_rows)
+        S = S.masked_fill(torch.nn.functional.one_hot(off + idx, n_keys).bool(), float("-inf"))
+        tgt = (off + idx) ^ 1
+        Qd = Q.detach()
+    else:
+        Qd = (torch.randn(n_rows, dim, generator=g) * (3.0 / dim ** 0.5)).requires_grad_(True)
+        S = Qd @ K_.t()
+        tgt = off + torch.arange(n_rows)
+    ref = torch.nn.functional.cross_entropy(S, tgt, reduction="none") * 2.0
+    w = torch.rand(n_rows, generator=g)
+    (ref * w).sum().backward()
+    qc, kc = Qd.detach().cuda().contiguous(), K_.detach().cuda()
+    loss, lse = torch.empty(n_rows, device="cuda"), torch.empty(n_rows, device="cuda")
+    k.simmat_ce_fwd(qc, kc, loss, lse, mode=k.SIM_COCO if mode == "coco" else k.SIM_QP, row_offset=off, loss_scale=2.0)
+    np.testing.assert_allclose(loss.cpu().numpy(), ref.detach().numpy(), rtol=1e-4, atol=1e-4)
+    dq, dk = torch.full((n_rows, dim), 7.0, device="cuda"), torch.full((n_keys, dim), 7.0, device="cuda")
+    k.simmat_ce_bwd(qc, kc, lse, w.cuda(), dq, dk, mode=k.SIM_COCO if mode == "coco" else k.SIM_QP, row_offset=off, loss_scale=2.0)
+    if mode == "coco":  # rows are a slice of the keys: autograd sums both roles into K_.grad
+        tot = dk.cpu().clone()
+        tot[off:off + n_rows] += dq.cpu()
+        np.testing.assert_allclose(tot.numpy(), K_.grad.numpy(), rtol=2e-3, atol=2e-5)
+    else:
+        np.testing.assert_allclose(dq.cpu().numpy(), Qd.grad.numpy(), rtol=2e-3, atol=2e-5)
+        np.testing.assert_allclose(dk.cpu().numpy(), K_.grad.numpy(), rtol=2e-3, atol=2e-5)
