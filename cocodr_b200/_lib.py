@@ -29,7 +29,8 @@ class AttnArgs(C.Structure):
     _fields_ = [("qkv", C.c_void_p), ("key_bias", C.c_void_p), ("out", C.c_void_p), ("lse", C.c_void_p),
                 ("d_out", C.c_void_p), ("dqkv", C.c_void_p), ("dq_workspace", C.c_void_p),
                 ("n_seq", C.c_int32), ("seq_len", C.c_int32), ("heads", C.c_int32), ("head_dim", C.c_int32),
-                ("scale", C.c_float), ("dbias_scale", C.c_float), ("dbias_qkv", C.c_void_p), ("drop", Dropout)]
+                ("scale", C.c_float), ("dbias_scale", C.c_float), ("dbias_qkv", C.c_void_p), ("drop", Dropout),
+                ("drop_bits", C.c_void_p)]
 
 
 class SimmatArgs(C.Structure):

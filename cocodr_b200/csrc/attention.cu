@@ -17,9 +17,14 @@
 //
 // Replaces HF eager_attention_forward / SDPA reached through self.bert(...) in
 // ANCE/model/models.py:226 and COCO/modeling.py:199-204.  DROP = true adds the dropout of the attention
-// probabilities (HF BertSelfAttention: dropout(softmax(S)) V; masks regenerated from Philox counters, dropout.cuh):
+// probabilities (HF BertSelfAttention: dropout(softmax(S)) V):
 //   forward   P~ = mask . P is what multiplies V, the row sum stays that of the undropped P, O = P~ V * s / sum
 //   backward  dP = mask . s . (dO V^T);  dV = (mask . s . P)^T dO;  delta = rowsum(P . dP) = rowsum(dO . O) as before
+// The keep bits come from Philox counters (dropout.cuh), but NOT inside these kernels: the softmax warps sit on the
+// critical path of every item, and 16 Philox calls per query row there cost +0.4 ms per training step (measured).  A
+// bandwidth-trivial pre-pass (att_keep_bits_kernel, ~3 M Philox calls per layer at full issue rate) writes one bit per
+// probability into a caller-provided buffer (16 B per query row at L <= 128) that the forward and the backward read
+// with one vector load per row.
 #include "cdr_common.cuh"
 #include "dropout.cuh"
 #include "tma_host.h"
@@ -45,6 +50,8 @@ struct AttParams {
   float* dbias;           // optional fp32 [3*hidden]: += dbias_scale * column sums of dqkv
   float dbias_scale;
   cdr_dropout drop;       // attention-probability dropout (DROP kernels)
+  const uint8_t* keep_bits;  // DROP: [n_seq * heads * seq_len rows][bits_stride bytes], bit c of a row = key c is kept
+  int bits_stride;           // bytes per row: ceil(seq_len / 8) rounded up to 16
 };
 
 // Philox group of the 8 probabilities (item = seq * heads + head, query row r, keys [8 * kg, 8 * kg + 8))
@@ -208,8 +215,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttParams p, 
     float* wb = sBiasW + sw * 128;   // this warp's private copy of the 128 key-bias values
     uint8_t* tile = sEpi + sw * 2048;
     const float sl2 = p.scale * LOG2E;
-    DropCtx dc{};
-    if constexpr (DROP) dc = drop_load(p.drop);
+    const float drop_scale = DROP ? p.drop.scale : 1.f;
     auto fetch_bias = [&](int item, int j) -> float {  // x LOG2E at use: nothing waits on the load here
       const int c = j * 32 + lane;
       if (c >= L) return -INFINITY;
@@ -233,12 +239,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttParams p, 
 #pragma unroll
         for (int j = 0; j < 4; ++j) nb[j] = fetch_bias(item + step, j);
       }
-      uint32_t keepw[4] = {0u, 0u, 0u, 0u};  // DROP: bit c of word w = key 32 * w + c of this query row is kept
-      if constexpr (DROP) {  // the 16 Philox calls of the row run while the tensor core still forms S
-#pragma unroll 2  // two interleaved Philox chains: more would spill next to the 128-score row
-        for (int gq = 0; gq < 16; ++gq)
-          keepw[gq >> 2] |= drop_keep8(dc, att_drop_group(item, L, r, gq)) << (8 * (gq & 3));
-      }
+      uint4 keepw = make_uint4(0u, 0u, 0u, 0u);  // DROP: bit c of word w = key 32 * w + c of this query row is kept
+      if constexpr (DROP)  // (in flight while the tensor core still forms S)
+        keepw = __ldg(reinterpret_cast<const uint4*>(p.keep_bits + (static_cast<long long>(item) * L + min(r, L - 1)) * 16));
       mbar_wait(&s_full[g], k);
       tc_fence_after();
       // ---- the whole S row (128 fp32) comes into registers with ONE wait and stays there for both passes;
@@ -269,7 +272,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttParams p, 
         sum0 += (e[0] + e[1]) + (e[2] + e[3]);
         sum1 += (e[4] + e[5]) + (e[6] + e[7]);
         if constexpr (DROP) {  // the row sum is that of the undropped probabilities; 1 / (1 - p) joins 1 / sum below
-          const uint32_t keep = keepw[gq >> 2] >> (8 * (gq & 3));
+          const uint32_t kw = (gq >> 2) == 0 ? keepw.x : (gq >> 2) == 1 ? keepw.y : (gq >> 2) == 2 ? keepw.z : keepw.w;
+          const uint32_t keep = kw >> (8 * (gq & 3));
 #pragma unroll
           for (int j = 0; j < 8; ++j) e[j] = ((keep >> j) & 1u) ? e[j] : 0.f;
         }
@@ -280,7 +284,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttParams p, 
       if (lane == 0) mbar_arrive(&p_full[g]);
       const float sum = sum0 + sum1;
       if (r < L && p.lse) p.lse[static_cast<long long>(item) * L + r] = (mx + log2f(sum)) / LOG2E;
-      const float inv = (sum > 0.f ? 1.f / sum : 0.f) * (DROP ? dc.scale : 1.f);
+      const float inv = (sum > 0.f ? 1.f / sum : 0.f) * drop_scale;
       // ---- epilogue of the same item: O / sum -> ctx rows (transposed through the warp's tile for 64-byte row
       // segments: a store instruction covers 8 whole rows instead of 32 different lines)
       mbar_wait(&o_full[g], k);
@@ -514,8 +518,7 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
     const uint32_t trow = tmem + (static_cast<uint32_t>(quad * 32) << 16);
     const float sl2 = p.scale * LOG2E;
     float* wb = sBiasW + sw * 32;   // this warp's private copy of the 32 key-bias values it needs
-    DropCtx dc{};
-    if constexpr (DROP) dc = drop_load(p.drop);
+    const float ds_scale = p.scale * (DROP ? p.drop.scale : 1.f);
     // values of the NEXT item are fetched one item ahead (global latency off the critical path)
     auto fetch_bias = [&](int item) -> float {
       const int c = c0 + lane;
@@ -542,11 +545,9 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
         nlse = fetch_lse(item + gridDim.x);
       }
       uint32_t keep32 = 0xffffffffu;  // DROP: bit c = key column c0 + c of this row survived the forward dropout
-      if constexpr (DROP) {  // regenerated while the tensor core forms S / dP
-        keep32 = 0u;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) keep32 |= drop_keep8(dc, att_drop_group(item, L, r, (c0 >> 3) + g)) << (8 * g);
-      }
+      if constexpr (DROP)
+        keep32 = __ldg(reinterpret_cast<const uint32_t*>(p.keep_bits + (static_cast<long long>(item) * L + min(r, L - 1)) * 16 +
+                                                         qtr * 4));
       mbar_wait(sdp_full, ph);
       tc_fence_after();
       // ---- S and dP of this thread's 32 columns: both loads in flight together, kept in registers to the end
@@ -569,10 +570,12 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
           pe = (r < L) ? pe : 0.f;
           sv[g * 8 + j] = __float_as_uint(pe);
           pu[j] = pe;
-          if constexpr (DROP) {  // forward used mask . P / (1 - p); dP = mask / (1 - p) . (dO V^T)
-            const float mj = ((keep32 >> (g * 8 + j)) & 1u) ? dc.scale : 0.f;
-            pe *= mj;
-            dv[g * 8 + j] = __float_as_uint(__uint_as_float(dv[g * 8 + j]) * mj);
+          if constexpr (DROP) {
+            // forward used mask . P / (1 - p) and dP = mask / (1 - p) . (dO V^T): both masks are applied here as
+            // selects, the two 1 / (1 - p) factors are folded into the dV epilogue and the dS scale
+            const bool kept = ((keep32 >> (g * 8 + j)) & 1u) != 0u;
+            pe = kept ? pe : 0.f;
+            dv[g * 8 + j] = kept ? dv[g * 8 + j] : 0u;
           }
           pv[j] = pe;
         }
@@ -598,7 +601,7 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
         float ds[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          ds[j] = __uint_as_float(sv[g * 8 + j]) * (__uint_as_float(dv[g * 8 + j]) - delta) * p.scale;
+          ds[j] = __uint_as_float(sv[g * 8 + j]) * (__uint_as_float(dv[g * 8 + j]) - delta) * ds_scale;
         *reinterpret_cast<uint4*>(sdS + swz_off(r, c0 + g * 8)) = pack8(ds);
       }
       fence_proxy_async();
@@ -635,8 +638,9 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
             if (lane == 0) mbar_arrive(out_empty);
           }
           float f[32];
+          const float osc = (DROP && t == 0) ? p.drop.scale : 1.f;  // dV = (mask . P)^T dO / (1 - p)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * osc;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             float e[8];
@@ -754,8 +758,8 @@ fmha_fwd_multi_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttPara
   const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
   const float sl2 = p.scale * LOG2E;
   uint32_t ph_k = 0, ph_s = 0, ph_o = 0;
-  DropCtx dc{};
-  if constexpr (DROP) dc = drop_load(p.drop);
+  const float drop_scale = DROP ? p.drop.scale : 1.f;
+  const uint8_t* bits_row = DROP ? p.keep_bits + (static_cast<long long>(sh) * L + min(q0 + r, L - 1)) * p.bits_stride : nullptr;
 
   if (tid == 0) {
     mbar_expect_tx(&bar[0], ATT_TILE_BYTES);
@@ -808,6 +812,8 @@ fmha_fwd_multi_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttPara
         for (int c = 0; c < 4; ++c) {
           uint32_t v[32];
           tmem_ld_32x32(trow + c * 32, v);
+          uint32_t kw = 0xffffffffu;
+          if constexpr (DROP) kw = __ldg(reinterpret_cast<const uint32_t*>(bits_row + (k0 >> 3) + c * 4));
           tc_wait_ld();
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
@@ -818,7 +824,7 @@ fmha_fwd_multi_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttPara
               sum += e[t];
             }
             if constexpr (DROP) {
-              const uint32_t keep = drop_keep8(dc, att_drop_group(sh, L, q0 + r, (k0 >> 3) + c * 4 + g));
+              const uint32_t keep = kw >> (8 * g);
 #pragma unroll
               for (int t = 0; t < 8; ++t) e[t] = ((keep >> t) & 1u) ? e[t] : 0.f;
             }
@@ -851,7 +857,7 @@ fmha_fwd_multi_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttPara
     const float m_use = (mx == -INFINITY) ? 0.f : mx;
     p.lse[(static_cast<long long>(seq) * p.heads + h) * L + qrow] = (m_use + log2f(sum)) / LOG2E;
   }
-  const float inv = (sum > 0.f ? 1.f / sum : 0.f) * (DROP ? dc.scale : 1.f);
+  const float inv = (sum > 0.f ? 1.f / sum : 0.f) * drop_scale;
   __half* orow = p.out + static_cast<long long>(row0 + qrow) * p.hidden + h * ATT_D;
   const uint32_t trow_o = tmem_o + (static_cast<uint32_t>(warp * 32) << 16);
 #pragma unroll 1
@@ -935,8 +941,7 @@ fmha_bwd_multi_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_
   const int half = warp >> 2;
   const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
   const float sl2 = p.scale * LOG2E;
-  DropCtx dc{};
-  if constexpr (DROP) dc = drop_load(p.drop);
+  const float drop_scale = DROP ? p.drop.scale : 1.f;
 
   if (tid == 0) {
     mbar_expect_tx(&bar[0], 2 * ATT_TILE_BYTES);
@@ -984,18 +989,21 @@ fmha_bwd_multi_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_
       uint32_t s[32], d[32];
       tmem_ld_32x32(t_s + lane_off + c0, s);
       tmem_ld_32x32(t_dp + lane_off + c0, d);
+      uint32_t kw = 0xffffffffu;
+      if constexpr (DROP)
+        kw = __ldg(reinterpret_cast<const uint32_t*>(p.keep_bits + (static_cast<long long>(sh) * L + min(qrow, L - 1)) * p.bits_stride +
+                                                     ((k0 + c0) >> 3)));
       tc_wait_ld();
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         float pv[8], ds[8];
-        uint32_t keep = 0xffu;
-        if constexpr (DROP) keep = drop_keep8(dc, att_drop_group(sh, L, qrow, ((k0 + c0) >> 3) + g));
+        const uint32_t keep = kw >> (8 * g);
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
           const int c = c0 + g * 8 + t;
           const bool ok = (qrow < L) && (k0 + c < L);
           const float pe = ok ? exp2f(fmaf(__uint_as_float(s[g * 8 + t]), sl2, sBias[c]) - lse2) : 0.f;
-          const float mj = DROP ? (((keep >> t) & 1u) ? dc.scale : 0.f) : 1.f;
+          const float mj = DROP ? (((keep >> t) & 1u) ? drop_scale : 0.f) : 1.f;
           pv[t] = pe * mj;
           ds[t] = ok ? pe * (mj * __uint_as_float(d[g * 8 + t]) - delta) * p.scale : 0.f;
         }
@@ -1099,10 +1107,27 @@ __global__ void dq_convert_kernel(const float* __restrict__ ws, __half* __restri
   *reinterpret_cast<uint4*>(dqkv + r * 3 * hidden + c) = pack8(v);
 }
 
+// keep bits of the attention-probability dropout: byte kg of row (item * L + r) = Philox group (item * L + r) * 64 + kg
+__global__ void __launch_bounds__(256)
+att_keep_bits_kernel(uint8_t* __restrict__ bits, long long n_rows, int groups_per_row, int stride, const cdr_dropout drop) {
+  const DropCtx dc = drop_load(drop);
+  const long long total = n_rows * groups_per_row;
+  const long long step = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += step) {
+    const long long row = i / groups_per_row;
+    const int kg = static_cast<int>(i - row * groups_per_row);
+    bits[row * stride + kg] = static_cast<uint8_t>(drop_keep8(dc, static_cast<uint32_t>(row) * 64u + static_cast<uint32_t>(kg)));
+  }
+}
+
+static int att_bits_stride(int seq_len) { return ((seq_len + 7) / 8 + 15) / 16 * 16; }
+
 static int att_check(const cdr_attn_args* a) {
   CDR_REQUIRE(a != nullptr, "cdr_attn: null args");
   if (a->drop.state != nullptr && a->drop.threshold > 0) {
     CDR_REQUIRE(a->drop.threshold < 65536, "cdr_attn: drop.threshold out of range");
+    CDR_REQUIRE(a->drop_bits != nullptr && (reinterpret_cast<uintptr_t>(a->drop_bits) & 15) == 0,
+                "cdr_attn: dropout needs drop_bits (16-byte aligned, cdr_attn_dropout_bits_bytes() bytes)");
     CDR_REQUIRE(static_cast<long long>(a->n_seq) * a->heads * a->seq_len * 64 < (1ll << 32),
                 "cdr_attn: dropout group index overflows 32 bits");
   }
@@ -1119,6 +1144,11 @@ using namespace cdr;
 
 extern "C" {
 
+size_t cdr_attn_dropout_bits_bytes(int32_t n_seq, int32_t heads, int32_t seq_len) {
+  if (n_seq <= 0 || heads <= 0 || seq_len <= 0) return 0;
+  return static_cast<size_t>(n_seq) * heads * seq_len * att_bits_stride(seq_len);
+}
+
 int cdr_attn_fwd(const cdr_attn_args* a, void* stream) {
   if (int rc = att_check(a)) return rc;
   CDR_REQUIRE(a->out != nullptr && a->lse != nullptr, "cdr_attn_fwd: null output");
@@ -1134,6 +1164,17 @@ int cdr_attn_fwd(const cdr_attn_args* a, void* stream) {
   p.lse = a->lse;
   p.drop = a->drop;
   const bool drop = drop_on(a->drop);
+  if (drop) {  // pre-pass: one keep bit per attention probability (read again by cdr_attn_bwd)
+    p.keep_bits = static_cast<const uint8_t*>(a->drop_bits);
+    p.bits_stride = att_bits_stride(a->seq_len);
+    const long long n_rows = static_cast<long long>(a->n_seq) * a->heads * a->seq_len;
+    const int gpr = (a->seq_len + 7) / 8;
+    long long blocks = (n_rows * gpr + 255) / 256;
+    if (blocks > 32LL * sm_count()) blocks = 32LL * sm_count();
+    att_keep_bits_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<uint8_t*>(a->drop_bits), n_rows, gpr, p.bits_stride, a->drop);
+    CDR_LAUNCH_CHECK();
+  }
   static bool configured = false;
   if (!configured) {
     CDR_CUDA(cudaFuncSetAttribute(fmha_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWD_SMEM));
@@ -1175,6 +1216,8 @@ int cdr_attn_bwd(const cdr_attn_args* a, void* stream) {
   p.dqkv = static_cast<__half*>(a->dqkv);
   p.drop = a->drop;
   const bool drop = drop_on(a->drop);
+  p.keep_bits = static_cast<const uint8_t*>(a->drop_bits);
+  p.bits_stride = att_bits_stride(a->seq_len);
   static bool configured = false;
   if (!configured) {
     CDR_CUDA(cudaFuncSetAttribute(fmha_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWD_SMEM));

@@ -270,19 +270,27 @@ def _attn_args(qkv, key_bias, out, lse, n_seq, seq_len, heads, scale, d_out=None
     return a
 
 
-def attn_fwd(qkv, key_bias, out, lse, *, n_seq, seq_len, heads, scale=0.125, drop=None):
+def attn_dropout_bits(n_seq, heads, seq_len, device):
+    """Buffer for the keep bits of the attention-probability dropout (filled by attn_fwd, read by attn_bwd)."""
+    n = int(_lib_().cdr_attn_dropout_bits_bytes(_i32(n_seq), _i32(heads), _i32(seq_len)))
+    return torch.empty(n, dtype=torch.uint8, device=device)
+
+
+def attn_fwd(qkv, key_bias, out, lse, *, n_seq, seq_len, heads, scale=0.125, drop=None, drop_bits=None):
+    """drop (a drop_args descriptor) needs drop_bits = attn_dropout_bits(...): fwd fills it, bwd reads it."""
     _need_cuda(qkv, out, lse)
     assert qkv.dtype == torch.float16 and out.dtype == torch.float16 and lse.dtype == torch.float32
     assert qkv.is_contiguous() and out.is_contiguous()
     a = _attn_args(qkv, key_bias, out, lse, n_seq, seq_len, heads, scale)
     if drop is not None:
-        a.drop = drop
+        assert drop_bits is not None and drop_bits.is_cuda and drop_bits.dtype == torch.uint8
+        a.drop, a.drop_bits = drop, drop_bits.data_ptr()
     _run("cdr_attn_fwd", lambda: _lib_().cdr_attn_fwd(C.byref(a), stream_ptr()))
-    _count(1)
+    _count(1 if drop is None else 2)
 
 
 def attn_bwd(qkv, key_bias, out, lse, d_out, dqkv, *, n_seq, seq_len, heads, scale=0.125, dbias=None, dbias_scale=1.0,
-             drop=None):
+             drop=None, drop_bits=None):
     """dbias (optional fp32 [3*heads*64], seq_len <= 128): += dbias_scale * column sums of dqkv, fused."""
     _need_cuda(qkv, out, lse, d_out, dqkv)
     assert d_out.dtype == torch.float16 and dqkv.dtype == torch.float16 and d_out.is_contiguous()
@@ -291,7 +299,8 @@ def attn_bwd(qkv, key_bias, out, lse, d_out, dqkv, *, n_seq, seq_len, heads, sca
         dq_ws = torch.empty(n_seq * seq_len, heads * 64, dtype=torch.float32, device=qkv.device)
     a = _attn_args(qkv, key_bias, out, lse, n_seq, seq_len, heads, scale, d_out, dqkv, dq_ws)
     if drop is not None:
-        a.drop = drop
+        assert drop_bits is not None
+        a.drop, a.drop_bits = drop, drop_bits.data_ptr()
     if dbias is not None:
         assert dbias.dtype == torch.float32 and dbias.numel() == 3 * heads * 64
         a.dbias_qkv, a.dbias_scale = dbias.data_ptr(), dbias_scale

@@ -270,7 +270,8 @@ class BertLayerFn(torch.autograd.Function):
         K.gemm(x, sh.wqkv, qkv, M=T, N=3 * H, K=H, bias=sh.bqkv)
         att = _f16(T, H, dev=dev)
         lse = _f32(n_seq, heads, L, dev=dev)
-        K.attn_fwd(qkv, key_bias, att, lse, n_seq=n_seq, seq_len=L, heads=heads, drop=da)
+        bits = K.attn_dropout_bits(n_seq, heads, L, dev) if da is not None else None
+        K.attn_fwd(qkv, key_bias, att, lse, n_seq=n_seq, seq_len=L, heads=heads, drop=da, drop_bits=bits)
         y1 = _f16(T, H, dev=dev)  # x + dropout(attn_out), pre-LayerNorm
         K.gemm(att, sh.wo, y1, M=T, N=H, K=H, bias=bo, aux=x, drop=db,
                epilogue=K.EPI_BIAS_RESIDUAL if db is None else K.EPI_BIAS_DROP_RESIDUAL)
@@ -289,7 +290,7 @@ class BertLayerFn(torch.autograd.Function):
         K.ln_fwd(y2, g2, be2, y, mean2, rstd2, cls, n_seq=n_seq, seq_len=L, hidden=H, eps=eps, push=push)
         ctx.save_for_backward(x, key_bias, qkv, att, lse, y1, x1, mean1, rstd1, gp, gl, y2, mean2, rstd2, g1, g2)
         ctx.shadow_w = (sh.wqkv, sh.wo, sh.wi, sh.wo2)
-        ctx.drop = (da, db, dc, drop.state if drop is not None else None)
+        ctx.drop = (da, db, dc, (drop.state if drop is not None else None, bits))
         ctx.meta = (n_seq, L, heads, I, emit_cls, _GRAD_SCALE)
         ctx.params = _note_forward(ctx, (wq, bq, wk, bk, wv, bv, wo, bo, g1, be1, wi, bi, wo2, bo2, g2, be2))
         ctx.param_keys = tuple(id(t) for t in ctx.params)
@@ -320,7 +321,7 @@ class BertLayerFn(torch.autograd.Function):
         dg2, dbe2, dbo2, dwo2, dbi, dwi, dg1, dbe1, dbo, dwo, dwqkv, dbqkv = views
         dwo2, dwi, dwo, dwqkv = dwo2.view(H, I), dwi.view(I, H), dwo.view(H, H), dwqkv.view(3 * H, H)
         row_ws = _f32(2 * T, dev=dev)
-        da, db, dc, _ = ctx.drop
+        da, db, dc, (_, bits) = ctx.drop
         # ---- output LayerNorm; column sums of its (dropped) dx are the FFN-down bias gradient.  dy2 = gradient of the
         # residual branch, dy2m = dropout'(dy2) = gradient of the dense output (same tensor without dropout)
         dy2, dy2m = _ln_bwd_after_dropout(dy, dcls, y2, g2, mean2, rstd2, dg2, dbe2, dbo2, n_seq=n_seq, seq_len=L, S=S,
@@ -344,7 +345,7 @@ class BertLayerFn(torch.autograd.Function):
         dqkv = _f16(T, 3 * H, dev=dev)
         fused_db = L <= 128  # the one-tile backward also emits the QKV bias gradient (column sums of dQKV)
         K.attn_bwd(qkv, key_bias, att, lse, datt, dqkv, n_seq=n_seq, seq_len=L, heads=heads,
-                   dbias=dbqkv if fused_db else None, dbias_scale=inv, drop=da)
+                   dbias=dbqkv if fused_db else None, dbias_scale=inv, drop=da, drop_bits=bits)
         # ---- QKV projection: dx = dQKV Wqkv + dy1 (residual)
         dx = None
         if ctx.needs_input_grad[0]:
@@ -390,7 +391,8 @@ class BertLastLayerCLSFn(torch.autograd.Function):
         K.gemm(x, sh.wqkv, qkv, M=T, N=3 * H, K=H, bias=sh.bqkv)
         att = _f16(T, H, dev=dev)
         lse = _f32(n_seq, heads, L, dev=dev)
-        K.attn_fwd(qkv, key_bias, att, lse, n_seq=n_seq, seq_len=L, heads=heads, drop=da)
+        bits = K.attn_dropout_bits(n_seq, heads, L, dev) if da is not None else None
+        K.attn_fwd(qkv, key_bias, att, lse, n_seq=n_seq, seq_len=L, heads=heads, drop=da, drop_bits=bits)
         xc, attc = x.view(n_seq, L, H)[:, 0], att.view(n_seq, L, H)[:, 0]  # [n_seq, H] views, row stride L * H
         y1 = _f16(n_seq, H, dev=dev)
         K.gemm(attc, sh.wo, y1, M=n_seq, N=H, K=H, bias=bo, aux=xc, drop=db,
@@ -412,7 +414,7 @@ class BertLastLayerCLSFn(torch.autograd.Function):
         K.ln_fwd(y2, g2, be2, y, mean2, rstd2, cls, n_seq=n_seq, seq_len=1, hidden=H, eps=eps, push=push)
         ctx.save_for_backward(x, key_bias, qkv, att, lse, y1, x1, mean1, rstd1, gp, gl, y2, mean2, rstd2, g1, g2)
         ctx.shadow_w = (sh.wqkv, sh.wo, sh.wi, sh.wo2)
-        ctx.drop = (da, db, dc, drop.state if drop is not None else None)
+        ctx.drop = (da, db, dc, (drop.state if drop is not None else None, bits))
         ctx.meta = (n_seq, L, heads, I, _GRAD_SCALE)
         ctx.params = _note_forward(ctx, (wq, bq, wk, bk, wv, bv, wo, bo, g1, be1, wi, bi, wo2, bo2, g2, be2))
         ctx.param_keys = tuple(id(t) for t in ctx.params)
@@ -435,7 +437,7 @@ class BertLastLayerCLSFn(torch.autograd.Function):
             off += n
         dg2, dbe2, dbo2, dwo2, dbi, dwi, dg1, dbe1, dbo, dwo, dwqkv, dbqkv = views
         dwo2, dwi, dwo, dwqkv = dwo2.view(H, I), dwi.view(I, H), dwo.view(H, H), dwqkv.view(3 * H, H)
-        da, db, dc, _ = ctx.drop
+        da, db, dc, (_, bits) = ctx.drop
         # ---- [CLS] rows only: output LayerNorm, FFN, attention-output LayerNorm and projection
         dy2, dy2m = _ln_bwd_after_dropout(None, dcls, y2, g2, mean2, rstd2, dg2, dbe2, dbo2, n_seq=n_seq, seq_len=1, S=S,
                                           site=dc)
@@ -457,7 +459,7 @@ class BertLastLayerCLSFn(torch.autograd.Function):
         dqkv = _f16(T, 3 * H, dev=dev)
         fused_db = L <= 128
         K.attn_bwd(qkv, key_bias, att, lse, datt, dqkv, n_seq=n_seq, seq_len=L, heads=heads,
-                   dbias=dbqkv if fused_db else None, dbias_scale=inv, drop=da)
+                   dbias=dbqkv if fused_db else None, dbias_scale=inv, drop=da, drop_bits=bits)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = _f16(T, H, dev=dev)

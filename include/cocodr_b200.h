@@ -270,7 +270,11 @@ typedef struct cdr_attn_args {
   float dbias_scale;     /* bwd, seq_len <= 128: multiplies the column sums below */
   float* dbias_qkv;      /* bwd, optional fp32 [3*heads*64]: += dbias_scale * column sums of dqkv (QKV bias gradient) */
   cdr_dropout drop;      /* dropout of the attention probabilities (after the softmax, HF BertSelfAttention) */
+  void* drop_bits;       /* with dropout: cdr_attn_dropout_bits_bytes() bytes, 16-byte aligned.  cdr_attn_fwd FILLS it (one
+                            keep bit per probability, from the Philox counters of `drop`) and reads it; cdr_attn_bwd reads
+                            the same buffer -- the softmax threads never run the generator themselves */
 } cdr_attn_args;
+size_t cdr_attn_dropout_bits_bytes(int32_t n_seq, int32_t heads, int32_t seq_len);
 int cdr_attn_fwd(const cdr_attn_args* args, void* stream);
 int cdr_attn_bwd(const cdr_attn_args* args, void* stream);
 
