@@ -67,23 +67,23 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-int make_tma_2d_f16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
-                    uint32_t box_inner, uint32_t box_outer) {
+static int make_tma_2d(CUtensorMap* map, const void* base, CUtensorMapDataType dt, uint64_t esize, uint64_t inner,
+                       uint64_t outer, uint64_t ld_elems, uint32_t box_inner, uint32_t box_outer) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled entry point unavailable");
     return CDR_ECUDA;
   }
-  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld_elems * 2) % 16 != 0) {
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld_elems * esize) % 16 != 0) {
     set_error("TMA operand must be 16-byte aligned with a 16-byte multiple row stride (base=%p ld=%llu)", base,
               (unsigned long long)ld_elems);
     return CDR_EINVAL;
   }
   cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint64_t strides[1] = {ld_elems * esize};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = fn(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -92,6 +92,16 @@ int make_tma_2d_f16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t
     return CDR_ECUDA;
   }
   return CDR_OK;
+}
+
+int make_tma_2d_f16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
+                    uint32_t box_inner, uint32_t box_outer) {
+  return make_tma_2d(map, base, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, inner, outer, ld_elems, box_inner, box_outer);
+}
+
+int make_tma_2d_f32(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
+                    uint32_t box_inner, uint32_t box_outer) {
+  return make_tma_2d(map, base, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, inner, outer, ld_elems, box_inner, box_outer);
 }
 
 }  // namespace cdr

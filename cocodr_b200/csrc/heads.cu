@@ -22,15 +22,16 @@ __device__ __forceinline__ int sim_target(int mode, int gi) { return mode == CDR
 // ------------------------------------------------------------------------------ fused similarity matrix + CE (K9 / K9')
 // S = q k^T is never written to memory (COCO/modeling.py:244-248 materialises it: matmul, fill_diagonal_, cross_entropy).
 // All three kernels share one tile step: a block keeps SIM_TO "outer" vectors resident in shared memory ([16][dim] fp32)
-// and streams "inner" vectors in tiles of SIM_TI = 64, 32 dimensions at a time; thread (o, ic) of 256 holds the four
+// and streams "inner" vectors in tiles of SIM_TI = 64, SIM_DC = 128 dimensions at a time (the chunk loop is latency
+// bound: global -> shared, barrier, FMAs, barrier; wide chunks mean few trips); thread (o, ic) of 256 holds the four
 // products A[o][ic + 16 u] in registers.
 //   forward  (rows outer, keys inner): online softmax over the key tiles of the block's key range -> per (row, split)
 //            partial (max, sum) + the target logit; simmat_combine_kernel folds the splits into lse / loss
 //   backward (rows outer -> dq, keys outer -> dk): the tile of S is recomputed, turned into
 //            G = dloss * loss_scale * (exp(S - lse) - [key == target]) in shared memory, and the block accumulates
-//            G (or G^T) times the SAME streamed inner vectors into its outer gradient rows (registers, 2 dims per
-//            thread and 32-dim chunk); splits of the inner range add into the zero-filled output with atomics
-constexpr int SIM_TO = 16, SIM_TI = 64, SIM_DC = 32, SIM_THREADS = 256;
+//            G (or G^T) times the SAME streamed inner vectors into its outer gradient rows (registers, 8 dims per
+//            thread and chunk); splits of the inner range add into the zero-filled output with atomics
+constexpr int SIM_TO = 16, SIM_TI = 64, SIM_DC = 128, SIM_THREADS = 256, SIM_DPT = SIM_DC / 16;
 constexpr int SIM_MAX_DIM = 2048;
 
 struct SimParams {
@@ -54,14 +55,15 @@ __device__ __forceinline__ void sim_tile_products(const float* __restrict__ sX, 
   for (int u = 0; u < 4; ++u) acc[u] = 0.f;
   for (int c0 = 0; c0 < dim; c0 += SIM_DC) {
     __syncthreads();  // the previous chunk (or the caller's use of sY) is finished
-#pragma unroll
+#pragma unroll 8
     for (int e = 0; e < SIM_TI * SIM_DC / SIM_THREADS; ++e) {
       const int idx = tid + e * SIM_THREADS;
-      const int j = idx >> 5, dd = idx & 31;
+      const int j = idx / SIM_DC, dd = idx % SIM_DC;
       sY[j][dd] = (i0 + j < n_inner && c0 + dd < dim) ? Y[static_cast<long long>(i0 + j) * dim + c0 + dd] : 0.f;
     }
     __syncthreads();
     const int nd = min(SIM_DC, dim - c0);
+#pragma unroll 4
     for (int dd = 0; dd < nd; ++dd) {
       const float x = sX[o * dim + c0 + dd];
 #pragma unroll
@@ -161,9 +163,11 @@ simmat_fused_bwd_kernel(const SimParams p) {
   const int i_begin = split * p.inner_per_split, i_end = min(n_inner, i_begin + p.inner_per_split);
   sim_load_outer(sX, X, n_outer, o0, p.dim);
   const int n_chunks = (p.dim + SIM_DC - 1) / SIM_DC;
-  float acc2[SIM_MAX_DIM / SIM_DC][2];
+  float acc2[SIM_MAX_DIM / SIM_DC][SIM_DPT];  // out[o][c * 128 + ic + 16 t]
 #pragma unroll
-  for (int c = 0; c < SIM_MAX_DIM / SIM_DC; ++c) acc2[c][0] = acc2[c][1] = 0.f;
+  for (int c = 0; c < SIM_MAX_DIM / SIM_DC; ++c)
+#pragma unroll
+    for (int t = 0; t < SIM_DPT; ++t) acc2[c][t] = 0.f;
   for (int i0 = i_begin; i0 < i_end; i0 += SIM_TI) {
     float a[4];
     sim_tile_products(sX, sY, Y, i_end, i0, p.dim, o, ic, a);
@@ -183,44 +187,43 @@ simmat_fused_bwd_kernel(const SimParams p) {
     // out[o][d] += sum_i G[o][i] * Y[i][d], the inner tile streamed once more in 32-dim chunks
     for (int c = 0; c < n_chunks; ++c) {
       __syncthreads();  // sG complete (first chunk) / previous chunk consumed
-#pragma unroll
+#pragma unroll 8
       for (int e = 0; e < SIM_TI * SIM_DC / SIM_THREADS; ++e) {
         const int idx = threadIdx.x + e * SIM_THREADS;
-        const int j = idx >> 5, dd = idx & 31;
+        const int j = idx / SIM_DC, dd = idx % SIM_DC;
         sY[j][dd] = (i0 + j < i_end && c * SIM_DC + dd < p.dim) ? Y[static_cast<long long>(i0 + j) * p.dim + c * SIM_DC + dd] : 0.f;
       }
       __syncthreads();
-      float s0 = 0.f, s1 = 0.f;
-#pragma unroll 8
+      float sacc[SIM_DPT];
+#pragma unroll
+      for (int t = 0; t < SIM_DPT; ++t) sacc[t] = 0.f;
+#pragma unroll 4
       for (int j = 0; j < SIM_TI; ++j) {
         const float gv = sG[o][j];
-        s0 = fmaf(gv, sY[j][2 * ic], s0);
-        s1 = fmaf(gv, sY[j][2 * ic + 1], s1);
+#pragma unroll
+        for (int t = 0; t < SIM_DPT; ++t) sacc[t] = fmaf(gv, sY[j][ic + 16 * t], sacc[t]);
       }
       // (acc2 is indexed by the chunk loop: keep the loop bounded by a compile-time maximum so it stays in registers)
 #pragma unroll
       for (int cc = 0; cc < SIM_MAX_DIM / SIM_DC; ++cc)
         if (cc == c) {
-          acc2[cc][0] += s0;
-          acc2[cc][1] += s1;
+#pragma unroll
+          for (int t = 0; t < SIM_DPT; ++t) acc2[cc][t] += sacc[t];
         }
     }
   }
   if (o0 + o < n_outer) {
     float* dst = p.out + static_cast<long long>(o0 + o) * p.dim;
 #pragma unroll
-    for (int c = 0; c < SIM_MAX_DIM / SIM_DC; ++c) {
-      const int d = c * SIM_DC + 2 * ic;
-      if (c < n_chunks && d < p.dim) {
-        if (p.n_splits > 1) {
-          atomicAdd(dst + d, acc2[c][0]);
-          if (d + 1 < p.dim) atomicAdd(dst + d + 1, acc2[c][1]);
-        } else {
-          dst[d] = acc2[c][0];
-          if (d + 1 < p.dim) dst[d + 1] = acc2[c][1];
+    for (int c = 0; c < SIM_MAX_DIM / SIM_DC; ++c)
+#pragma unroll
+      for (int t = 0; t < SIM_DPT; ++t) {
+        const int d = c * SIM_DC + ic + 16 * t;
+        if (c < n_chunks && d < p.dim) {
+          if (p.n_splits > 1) atomicAdd(dst + d, acc2[c][t]);
+          else dst[d] = acc2[c][t];
         }
       }
-    }
   }
 }
 
@@ -430,6 +433,8 @@ gram_kernel(const float* __restrict__ X, int G, long long P, long long ldx, floa
     }
 }
 
+int gram_tf32_launch(const float* x, int g, long long p, long long ldx, float* gram, cudaStream_t st);  // gram.cu
+
 }  // namespace cdr
 
 using namespace cdr;
@@ -613,6 +618,10 @@ int cdr_gram_f32(const float* x, int32_t g, int64_t p, int64_t ldx, float* gram,
   CDR_REQUIRE(x && gram, "cdr_gram_f32: null pointer");
   CDR_REQUIRE(g > 0 && g <= GR_G, "cdr_gram_f32: 1 <= groups <= %d (got %d)", GR_G, g);
   if (p <= 0) return CDR_OK;
+  {  // tensor-core path (gram.cu: tcgen05 kind::tf32, HBM-bound); layouts it cannot take fall through to the fp32 kernel
+    const int rc = gram_tf32_launch(x, g, p, ldx, gram, static_cast<cudaStream_t>(stream));
+    if (rc <= 0) return rc;
+  }
   long long blocks = 4LL * sm_count();
   long long cpb = (p + blocks - 1) / blocks;
   cpb = ((cpb + GR_C - 1) / GR_C) * GR_C;

@@ -110,11 +110,30 @@ def test_group_reduce_and_gram():
     k.group_reduce_bwd(ds.cuda(), g.cuda(), dl, n_groups=G)
     np.testing.assert_array_equal(dl.cpu().numpy(), ds[g].numpy())
 
-    X = torch.randn(G, 100003)
+    X = torch.randn(G, 100003)  # row stride not a multiple of 4 floats: the fp32 CUDA-core kernel
     gram = torch.zeros(G, G, device="cuda")
     k.gram_f32(X.cuda(), gram)
     ref = (X.double() @ X.double().t()).float()
     np.testing.assert_allclose(gram.cpu().numpy(), ref.numpy(), rtol=2e-4, atol=2e-2)
+
+
+@pytest.mark.parametrize("G,P", [(50, 1_000_000), (64, 4096), (7, 100_004), (1, 130), (33, 21_263_616 // 8)])
+def test_gram_tensor_core_path(G, P):
+    """cdr_gram_f32 through tcgen05 kind::tf32 (16-byte aligned rows): operands keep 10 mantissa bits, accumulation is
+    fp32 -- entries within 2e-3 of the fp64 Gram relative to the row norms, ragged column tail and G < 64 included;
+    accumulates into the given matrix."""
+    from cocodr_b200 import kernels as k
+    g = torch.Generator().manual_seed(G + P)
+    X = torch.randn(G, P, generator=g)
+    X[:, ::3] *= 0.01
+    if G > 2:
+        X[2] = 0.5 * X[1] + 0.1 * X[2]  # a strongly correlated pair
+    gram = torch.ones(G, G, device="cuda")
+    k.gram_f32(X.cuda(), gram)
+    ref = X.double() @ X.double().t()
+    nrm = torch.sqrt(torch.diagonal(ref))
+    err = ((gram.cpu().double() - 1.0 - ref).abs() / (nrm[:, None] * nrm[None, :])).max().item()
+    assert err < 2e-3, err
 
 
 @pytest.mark.parametrize("n_rows,n_keys,dim,mode,off", [(64, 512, 768, "qp", 128), (7, 23, 40, "qp", 5), (37, 130, 96, "qp", 0),
