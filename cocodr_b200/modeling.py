@@ -66,12 +66,30 @@ class CondenserForPretraining(nn.Module):
             h = run_layer(layer, shadow, h, kb, n_seq, L, cfg, drop=drop, layer_index=cfg.num_hidden_layers + i)
         return h
 
-    def _mlm_rows(self, labels):
-        lab = labels.reshape(-1)
-        idx = torch.nonzero(lab != -100).flatten()  # (one host sync: the row count sizes the GEMMs)
-        return idx, lab.index_select(0, idx)
+    # Fraction of the positions the MLM head is sized for when set (e.g. 0.25 for 15 % masking): the masked rows are
+    # then gathered into a FIXED-size buffer (unused slots carry label -100 and contribute nothing), no host
+    # synchronisation sizes the GEMMs and the whole step can be captured into a CUDA graph.  None = exact dynamic size
+    # (one host sync per step).  ``mlm_overflow`` counts the masked positions that did not fit (must stay 0).
+    mlm_capacity = None
 
-    def _mlm(self, hidden_internal, idx, row_labels):
+    def _mlm_rows(self, labels):
+        """-> (row indices, their labels, number of valid rows or None)."""
+        lab = labels.reshape(-1)
+        if self.mlm_capacity is None:
+            idx = torch.nonzero(lab != -100).flatten()  # (one host sync: the row count sizes the GEMMs)
+            return idx, lab.index_select(0, idx), None
+        cap = min(lab.numel(), (int(self.mlm_capacity * lab.numel()) + 63) // 64 * 64)
+        valid = lab != -100
+        count = valid.sum()
+        idx = torch.nonzero_static(valid, size=cap, fill_value=0).flatten()
+        row_labels = torch.where(torch.arange(cap, device=lab.device) < count, lab.index_select(0, idx),
+                                 torch.full((cap,), -100, dtype=lab.dtype, device=lab.device))
+        if not hasattr(self, "mlm_overflow") or self.mlm_overflow.device != lab.device:
+            object.__setattr__(self, "mlm_overflow", torch.zeros((), dtype=torch.int64, device=lab.device))
+        self.mlm_overflow += (count - cap).clamp(min=0)
+        return idx, row_labels, count
+
+    def _mlm(self, hidden_internal, idx, row_labels, count=None):
         """mean CE over the masked rows == CrossEntropyLoss()(scores.view(-1, V), labels.view(-1)) (:87-93)."""
         p = self.lm.cls.predictions
         if idx.numel() == 0:
@@ -80,19 +98,21 @@ class CondenserForPretraining(nn.Module):
         per_row = ops.MLMHead.apply(rows, row_labels, p.transform.dense.weight, p.transform.dense.bias,
                                     p.transform.LayerNorm.weight, p.transform.LayerNorm.bias, p.decoder.weight, p.bias,
                                     self._mlm_shadow, float(self.lm.config.layer_norm_eps))
-        return per_row.mean()
+        if count is None:
+            return per_row.mean()
+        return per_row.sum() / count.to(per_row.dtype)  # slots with label -100 are exact zeros (0 / 0 = nan like the reference)
 
     def mlm_loss(self, hiddens, labels):
         """Reference signature (:87-93): ``hiddens`` fp32 [B, L, H] as returned to callers."""
-        idx, row_labels = self._mlm_rows(labels)
-        return self._mlm(ops.FloatToHidden.apply(hiddens), idx, row_labels)
+        idx, row_labels, count = self._mlm_rows(labels)
+        return self._mlm(ops.FloatToHidden.apply(hiddens), idx, row_labels, count)
 
     def forward(self, model_input, labels, groups=None, **kwargs):
         cls, last, hidden = self._encode(model_input)
-        idx, row_labels = self._mlm_rows(labels)
-        loss = self._mlm(self._head(last, hidden, model_input), idx, row_labels)
+        idx, row_labels, count = self._mlm_rows(labels)
+        loss = self._mlm(self._head(last, hidden, model_input), idx, row_labels, count)
         if self.model_args.late_mlm:
-            loss = loss + self._mlm(last, idx, row_labels)
+            loss = loss + self._mlm(last, idx, row_labels, count)
         return loss
 
     # ---- persistence (modeling.py:96-131) -----------------------------------------------------
@@ -149,10 +169,10 @@ class CoCondenserForPretraining(CondenserForPretraining):
             co_cls_hiddens = self.gather_tensors(cls.contiguous())[0]
         else:
             co_cls_hiddens = cls
-        idx, row_labels = self._mlm_rows(labels)
-        loss = self._mlm(self._head(last, hidden, model_input), idx, row_labels)
+        idx, row_labels, count = self._mlm_rows(labels)
+        loss = self._mlm(self._head(last, hidden, model_input), idx, row_labels, count)
         if self.model_args.late_mlm:
-            loss = loss + self._mlm(last, idx, row_labels)
+            loss = loss + self._mlm(last, idx, row_labels, count)
         co_loss = self.compute_contrastive_loss(co_cls_hiddens).mean()
         return loss + co_loss
 

@@ -732,5 +732,5 @@ class GatherRows(torch.autograd.Function):
     def backward(ctx, g):
         (idx,) = ctx.saved_tensors
         out = torch.zeros(ctx.rows, g.shape[1], dtype=g.dtype, device=g.device)
-        out.index_copy_(0, idx, g)
+        out.index_add_(0, idx, g)  # (add, not copy: fixed-capacity gathers repeat row 0 in their unused slots)
         return out, None

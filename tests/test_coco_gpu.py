@@ -59,8 +59,8 @@ def test_cocondenser_forward_backward_matches_reference(golden_dir):
     with torch.no_grad():
         cls, last, hidden = m._encode(inp)
         co = m.compute_contrastive_loss(cls)
-        idx, row_labels = m._mlm_rows(labels)
-        lm_mlm = m._mlm(last, idx, row_labels)
+        idx, row_labels, count = m._mlm_rows(labels)
+        lm_mlm = m._mlm(last, idx, row_labels, count)
     assert rel(cls.cpu().numpy(), g["cls"]) < 1e-2
     np.testing.assert_allclose(co.cpu().numpy(), g["co_loss"], rtol=1e-2, atol=5e-3)
     assert abs(lm_mlm.item() - float(g["lm_mlm_loss"])) < 1e-2 * float(g["lm_mlm_loss"])
@@ -132,3 +132,38 @@ def test_cocondenser_large_shape_l256_runs():
         cls = m._encode({"input_ids": ids, "attention_mask": mask})[0]
         co = m.compute_contrastive_loss(cls)
     np.testing.assert_allclose(co.cpu().numpy(), heads_ref.coco_contrastive(cls.cpu()).numpy(), rtol=1e-4, atol=1e-4)
+
+
+def test_fixed_capacity_mlm_gather_equals_dynamic_and_is_graph_capturable(golden_dir):
+    """mlm_capacity: masked rows gathered into a fixed-size buffer (no host sync) -> same loss and gradients as the
+    exact dynamic gather; the whole step replays from a CUDA graph with fresh dropout masks per replay."""
+    from oracle import bert_ref
+    from cocodr_b200.graph import GraphedTrainStep
+    g = np.load(os.path.join(golden_dir, "coco_tiny.npz"))
+    m = build_from_golden(g)
+    m.eval()  # no dropout: the two gathers must agree exactly up to summation order
+    n_docs, L = int(g["n_docs"]), int(g["L"])
+    ids, mask = (t.cuda() for t in bert_ref.synth_batch(2 * n_docs, L, TINY["vocab"], int(g["seed"])))
+    labels = torch.from_numpy(g["labels"]).cuda()
+    inp = {"input_ids": ids, "attention_mask": mask}
+    out = {}
+    for cap in (None, 0.5):
+        m.mlm_capacity = cap
+        m.zero_grad(set_to_none=True)
+        loss = m(inp, labels)
+        loss.backward()
+        out[cap] = (loss.item(), {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None})
+    assert abs(out[None][0] - out[0.5][0]) < 1e-5 * abs(out[None][0])
+    for n, gr in out[None][1].items():
+        err = (out[0.5][1][n] - gr).abs().max().item()
+        assert err <= 1e-6 + 2e-3 * gr.abs().max().item(), (n, err)
+    assert int(m.mlm_overflow) == 0
+    m.mlm_capacity = 0.01  # too small on purpose: the overflow counter must say so
+    m(inp, labels)
+    assert int(m.mlm_overflow) > 0
+    m.mlm_capacity = 0.5
+    m.train()
+    opt = torch.optim.SGD([p for p in m.parameters() if p.requires_grad], lr=0.0)
+    step = GraphedTrainStep(lambda i, a, l: m({"input_ids": i, "attention_mask": a}, l), opt, (ids, mask, labels))
+    losses = [step(ids, mask, labels).item() for _ in range(3)]
+    assert all(np.isfinite(losses)) and len(set(losses)) == 3  # c_head dropout draws new masks at every replay

@@ -86,7 +86,8 @@ def test_attention_dropout_fwd_bwd(n_seq, L, heads, masked):
     drop = k.drop_args(_state(), site, P)
     out = torch.zeros(T, H, dtype=torch.float16, device="cuda")
     lse = torch.zeros(n_seq, heads, L, dtype=torch.float32, device="cuda")
-    k.attn_fwd(qkv, bias, out, lse, n_seq=n_seq, seq_len=L, heads=heads, drop=drop)
+    bits = k.attn_dropout_bits(n_seq, heads, L, "cuda")  # filled by the forward, read by the backward
+    k.attn_fwd(qkv, bias, out, lse, n_seq=n_seq, seq_len=L, heads=heads, drop=drop, drop_bits=bits)
     mask = dropout_ref.attention_mask(n_seq, heads, L, site, SEED, OFF, P).cuda()
     qf = qkv.float().requires_grad_(True)
     o_ref, lse_ref = _attn_ref(qf, bias, n_seq, L, heads, mask)
@@ -96,7 +97,7 @@ def test_attention_dropout_fwd_bwd(n_seq, L, heads, masked):
     dqkv = torch.zeros(T, 3 * H, dtype=torch.float16, device="cuda")
     dbias = torch.zeros(3 * H, dtype=torch.float32, device="cuda") if L <= 128 else None
     k.attn_bwd(qkv, bias, out, lse, d_out, dqkv, n_seq=n_seq, seq_len=L, heads=heads, dbias=dbias, dbias_scale=1.0,
-               drop=drop)
+               drop=drop, drop_bits=bits)
     (o_ref * d_out.float()).sum().backward()
     ref = qf.grad
     for nm, sl in (("dq", slice(0, H)), ("dk", slice(H, 2 * H)), ("dv", slice(2 * H, 3 * H))):

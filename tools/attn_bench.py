@@ -38,3 +38,10 @@ bench("attn bwd", lambda r: k.attn_bwd(qkv[r], None, out[r], lse[r], do[r], dqkv
                                       dbias=db, dbias_scale=1e-3), 2.5 * fw, T * (3 + 1 + 3) * H * 2)
 bench("bwd no-dbias", lambda r: k.attn_bwd(qkv[r], None, out[r], lse[r], do[r], dqkv[r], n_seq=n_seq, seq_len=L, heads=heads),
       2.5 * fw, T * (3 + 1 + 3) * H * 2)
+state = torch.tensor([1, 1], dtype=torch.int64, device="cuda")
+drop = k.drop_args(state, 5, 0.1)
+bits = k.attn_dropout_bits(n_seq, heads, L, "cuda")
+bench("fwd drop", lambda r: k.attn_fwd(qkv[r], None, out[r], lse[r], n_seq=n_seq, seq_len=L, heads=heads, drop=drop, drop_bits=bits),
+      fw, T * 4 * H * 2)
+bench("bwd drop", lambda r: k.attn_bwd(qkv[r], None, out[r], lse[r], do[r], dqkv[r], n_seq=n_seq, seq_len=L, heads=heads,
+                                      dbias=db, dbias_scale=1e-3, drop=drop, drop_bits=bits), 2.5 * fw, T * (3 + 1 + 3) * H * 2)

@@ -20,7 +20,8 @@ for blk in range((L + 63) // 64):
     qkv = qkv.reshape(T, 3 * H).half().cuda()
     out = torch.zeros(T, H, dtype=torch.float16, device="cuda")
     lse = torch.zeros(n_seq, heads, L, device="cuda")
-    k.attn_fwd(qkv, None, out, lse, n_seq=n_seq, seq_len=L, heads=heads, drop=k.drop_args(state, site, P))
+    k.attn_fwd(qkv, None, out, lse, n_seq=n_seq, seq_len=L, heads=heads, drop=k.drop_args(state, site, P),
+               drop_bits=k.attn_dropout_bits(n_seq, heads, L, "cuda"))
     o = out.float().cpu().view(n_seq, L, heads, 64).permute(0, 2, 1, 3) * L  # [n_seq, heads, L, 64] ~ mask * scale
     w = min(64, L - blk * 64)
     got[:, :, :, blk * 64:blk * 64 + w] = o[:, :, :, :w]
