@@ -17,7 +17,7 @@
 
 namespace cdr {
 
-constexpr int SCAN_CAP_MIN = 8192;     // candidate slots per query (>= 8k)
+constexpr int SCAN_CAP_MIN = 2048;     // candidate slots per query: 8 k, at least 2048 (expected admissions: max(3 k, 1024))
 constexpr int SCAN_SAMPLE = 8192;      // sampled documents for the thresholds
 constexpr int SCAN_SORT_MAX = 16384;   // bitonic sort capacity (128 KB of keys)
 
@@ -296,6 +296,73 @@ topk_merge_kernel(const float* __restrict__ scores, const long long* __restrict_
       });
 }
 
+// ---- sharded search: per-shard lists travel as packed keys, one all-gather, merged where they land
+// keys[q * ks + j] = packed (score, id) of D[q, j] / I[q, j] (0 = empty slot, also pads k_in < ks);
+// keys[n_q * ks] = *status (the shard scan's failure count), keys[n_q * ks + 1] = all_returned (the shard holds no
+// document beyond its list)
+__global__ void topk_pack_kernel(const float* __restrict__ D, const long long* __restrict__ I, int n_q, int k_in, int ks,
+                                 const int* __restrict__ status, int all_returned, unsigned long long* __restrict__ keys) {
+  const long long n = static_cast<long long>(n_q) * ks;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int q = static_cast<int>(i / ks), j = static_cast<int>(i - static_cast<long long>(q) * ks);
+    unsigned long long key = 0ull;
+    if (j < k_in) {
+      const long long id = I[static_cast<long long>(q) * k_in + j];
+      if (id >= 0) key = pack_score_doc(D[static_cast<long long>(q) * k_in + j], static_cast<unsigned int>(id));
+    }
+    keys[i] = key;
+  }
+  if (i == 0) {
+    keys[n] = static_cast<unsigned long long>(*status);
+    keys[n + 1] = static_cast<unsigned long long>(all_returned != 0);
+  }
+}
+
+// all[w] = the key block of shard w (stride = n_q * ks + 2, the layout all_gather leaves).  One block per query: sort the
+// W * ks gathered keys, emit the first k.  The result is exact iff no shard can hold an unreturned document that beats
+// the k-th merged key: every shard that truncated its list (all_returned == 0) must have a LAST key <= the k-th merged
+// key.  Violations (and the shards' own failure counts) are added to *flag; the caller then re-searches with ks = k.
+__global__ void __launch_bounds__(SORT_THREADS)
+topk_merge_keys_kernel(const unsigned long long* __restrict__ all, int W, int n_q, int ks, int k,
+                       float* __restrict__ out_s, long long* __restrict__ out_i, int* __restrict__ flag) {
+  extern __shared__ unsigned long long xch[];
+  __shared__ unsigned long long kth;
+  const int q = blockIdx.x;
+  const long long stride = static_cast<long long>(n_q) * ks + 2;
+  const int n_in = W * ks;
+  if (threadIdx.x == 0) kth = 0ull;
+  __syncthreads();
+  block_topk_sorted(
+      n_in, k, xch,
+      [&](int i) {
+        if (i >= n_in) return 0ull;
+        const int w = i / ks, j = i - w * ks;
+        return all[w * stride + static_cast<long long>(q) * ks + j];
+      },
+      [&](int i, unsigned long long key) {
+        float s = -INFINITY;
+        long long id = -1;
+        if (key != 0ull) {
+          s = unflip_score(static_cast<unsigned int>(key >> 32));
+          id = static_cast<long long>(~static_cast<unsigned int>(key));
+        }
+        out_s[static_cast<long long>(q) * k + i] = s;
+        out_i[static_cast<long long>(q) * k + i] = id;
+        if (i == k - 1) kth = key;
+      });
+  __syncthreads();
+  if (static_cast<int>(threadIdx.x) < W) {
+    const int w = threadIdx.x;
+    int bad = 0;
+    if (q == 0) bad += static_cast<int>(all[w * stride + static_cast<long long>(n_q) * ks]);  // the shard scan's own status
+    const bool all_returned = all[w * stride + static_cast<long long>(n_q) * ks + 1] != 0ull;
+    const unsigned long long last = all[w * stride + static_cast<long long>(q) * ks + ks - 1];
+    if (!all_returned && last != 0ull && last > kth) bad += 1;
+    if (bad) atomicAdd(flag, bad);
+  }
+}
+
 // shared memory of the register sort: two exchange buffers of n keys (n = 1024 * E covers the element count)
 static size_t sort_smem_bytes(int n_valid) {
   int n = SORT_THREADS;
@@ -450,6 +517,36 @@ int cdr_topk_merge(const float* scores, const int64_t* ids, int32_t n_q, int32_t
   }
   topk_merge_kernel<<<n_q, SORT_THREADS, sort_smem_bytes(n_in), static_cast<cudaStream_t>(stream)>>>(
       scores, reinterpret_cast<const long long*>(ids), n_in, k, out_scores, reinterpret_cast<long long*>(out_ids));
+  CDR_LAUNCH_CHECK();
+  return CDR_OK;
+}
+
+int cdr_topk_pack(const float* scores, const int64_t* ids, int32_t n_q, int32_t k_in, int32_t ks, const int32_t* status,
+                  int32_t all_returned, uint64_t* keys, void* stream) {
+  CDR_REQUIRE(scores && ids && status && keys, "cdr_topk_pack: null pointer");
+  CDR_REQUIRE(n_q > 0 && k_in > 0 && ks >= k_in, "cdr_topk_pack: need n_q > 0 and 0 < k_in <= ks");
+  const long long n = static_cast<long long>(n_q) * ks;
+  topk_pack_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      scores, reinterpret_cast<const long long*>(ids), n_q, k_in, ks, status, all_returned,
+      reinterpret_cast<unsigned long long*>(keys));
+  CDR_LAUNCH_CHECK();
+  return CDR_OK;
+}
+
+int cdr_topk_merge_keys(const uint64_t* gathered, int32_t world, int32_t n_q, int32_t ks, int32_t k, float* out_scores,
+                        int64_t* out_ids, int32_t* flag, void* stream) {
+  CDR_REQUIRE(gathered && out_scores && out_ids && flag, "cdr_topk_merge_keys: null pointer");
+  CDR_REQUIRE(world > 0 && world <= SORT_THREADS && n_q > 0 && ks > 0 && k > 0, "cdr_topk_merge_keys: empty problem");
+  CDR_REQUIRE(static_cast<long long>(world) * ks <= SCAN_SORT_MAX && k <= world * ks,
+              "cdr_topk_merge_keys: need k <= world * ks <= %d (world=%d ks=%d k=%d)", SCAN_SORT_MAX, world, ks, k);
+  static bool cfg = false;
+  if (!cfg) {
+    if (int rc = set_smem(topk_merge_keys_kernel, SORT_SMEM_MAX)) return rc;
+    cfg = true;
+  }
+  topk_merge_keys_kernel<<<n_q, SORT_THREADS, sort_smem_bytes(world * ks), static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const unsigned long long*>(gathered), world, n_q, ks, k, out_scores,
+      reinterpret_cast<long long*>(out_ids), flag);
   CDR_LAUNCH_CHECK();
   return CDR_OK;
 }

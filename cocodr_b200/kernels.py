@@ -443,3 +443,22 @@ def topk_merge(scores, ids, out_scores, out_ids, *, k):
     _run("cdr_topk_merge", lambda: _lib_().cdr_topk_merge(_p(scores), _p(ids), _i32(n_q), _i32(n_in), _i32(k), _p(out_scores), _p(out_ids),
                                  stream_ptr()))
     _count(1)
+
+
+def topk_pack(scores, ids, status, keys, *, ks, all_returned):
+    """[n_q, k_in] shard result -> u64 keys [n_q * ks + 2] (cdr_topk_pack)."""
+    _need_cuda(scores, ids, status, keys)
+    n_q, k_in = scores.shape
+    assert keys.dtype == torch.int64 and keys.numel() == n_q * ks + 2 and scores.is_contiguous() and ids.is_contiguous()
+    _run("cdr_topk_pack", lambda: _lib_().cdr_topk_pack(_p(scores), _p(ids), _i32(n_q), _i32(k_in), _i32(ks), _p(status),
+                                                       _i32(int(all_returned)), _p(keys), stream_ptr()))
+    _count(1)
+
+
+def topk_merge_keys(gathered, out_scores, out_ids, flag, *, world, n_q, ks, k):
+    """Merge the all-gathered key blocks of every shard into the global top k (cdr_topk_merge_keys)."""
+    _need_cuda(gathered, out_scores, out_ids, flag)
+    assert gathered.dtype == torch.int64 and gathered.numel() == world * (n_q * ks + 2) and flag.dtype == torch.int32
+    _run("cdr_topk_merge_keys", lambda: _lib_().cdr_topk_merge_keys(_p(gathered), _i32(world), _i32(n_q), _i32(ks), _i32(k),
+                                                                   _p(out_scores), _p(out_ids), _p(flag), stream_ptr()))
+    _count(1)

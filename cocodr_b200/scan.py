@@ -102,19 +102,58 @@ def search(Q, P, k, doc_base=0, force_exhaustive=False):
     return runD, runI
 
 
+def shard_list_len(k, world):
+    """Entries each shard contributes to a sharded top-k: a shard of a randomly split corpus holds ~k / W of the global
+    top k (binomial), so 1.5 k / W + 64 covers it with a wide margin; the merge VERIFIES that it sufficed."""
+    if world * k <= 2048:
+        return k
+    return min(k, (int(1.5 * k / world) + 64 + 63) // 64 * 64)
+
+
+def _shard_keys(Q, P_local, ks, doc_base):
+    """This shard's top-ks as packed keys (+ status words); everything stays enqueued on the stream."""
+    k_eff = min(ks, P_local.shape[0])
+    D, I, status = search_async(Q, P_local, k_eff, doc_base=doc_base)
+    keys = torch.empty(Q.shape[0] * ks + 2, dtype=torch.int64, device=Q.device)
+    K.topk_pack(D, I, status, keys, ks=ks, all_returned=(k_eff == P_local.shape[0]))
+    return keys
+
+
+def _merge_gathered(allk, world, n_q, ks, k):
+    outD = torch.empty(n_q, k, dtype=torch.float32, device=allk.device)
+    outI = torch.empty(n_q, k, dtype=torch.int64, device=allk.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=allk.device)
+    K.topk_merge_keys(allk, outD, outI, flag, world=world, n_q=n_q, ks=ks, k=k)
+    return outD, outI, flag
+
+
 def search_sharded(Q, P_local, k, doc_base, group=None):
-    """Documents sharded over ranks: local top-k with global ids, all-gather of the [nq,k]
-    candidate lists (12 B per entry), k-way merge on every rank.  No document embedding crosses NVLink."""
+    """Documents sharded over ranks: every rank scans its shard for a SHORT list (``shard_list_len``), the
+    lists travel as packed 8-byte keys in ONE all-gather, and each rank merges them where they land.  The merge kernel
+    proves exactness (no truncated shard can hold a better document than the k-th merged one) and the host reads one
+    flag per search; if the proof fails -- a corpus clustered by shard, or a shard scan that overflowed -- the search is
+    repeated with full-length lists through the guaranteed path.  No document embedding crosses NVLink.  Results are
+    bit-identical to a single-device search: same total order (score desc, id asc)."""
     import torch.distributed as dist
-    D, I = search(Q, P_local, k, doc_base=doc_base)
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return D, I
+        return search(Q, P_local, k, doc_base=doc_base)
     W = dist.get_world_size(group)
+    n_q = Q.shape[0]
+    for ks in dict.fromkeys((shard_list_len(k, W), k)):
+        if ks == k and W * ks > 16384:
+            break
+        mine = _shard_keys(Q, P_local, ks, doc_base)
+        allk = torch.empty(W * mine.numel(), dtype=torch.int64, device=mine.device)
+        dist.all_gather_into_tensor(allk, mine, group=group)
+        D, I, flag = _merge_gathered(allk, W, n_q, ks, min(k, W * ks))
+        if int(flag.item()) == 0:  # (identical on every rank: all ranks merge the same gathered keys)
+            return D, I
+    # guaranteed path: exact per-shard top-k (chunked exhaustive scan if need be), gathered and merged
+    D, I = search(Q, P_local, k, doc_base=doc_base)
     if D.shape[1] < k:  # ragged shards: pad with empty slots
         pad = k - D.shape[1]
         D = torch.cat([D, D.new_full((D.shape[0], pad), float("-inf"))], 1)
         I = torch.cat([I, I.new_full((I.shape[0], pad), -1)], 1)
-    n_q = D.shape[0]
     allD = torch.empty(W * n_q, k, dtype=D.dtype, device=D.device)  # rank-major blocks of [n_q, k]
     allI = torch.empty(W * n_q, k, dtype=I.dtype, device=I.device)
     dist.all_gather_into_tensor(allD, D.contiguous(), group=group)

@@ -373,6 +373,17 @@ int cdr_scan_topk(const cdr_scan_args* args, void* stream);
 /* merge n_in candidates per query (any order; e.g. all-gathered per-shard top-k lists) into the top k */
 int cdr_topk_merge(const float* scores, const int64_t* ids, int32_t n_q, int32_t n_in, int32_t k, float* out_scores,
                    int64_t* out_ids, void* stream);
+/* Sharded search (documents split over ranks; replaces the reference's per-rank pickles + numpy merge,
+ * ANCE/utils/util.py:87-155).  cdr_topk_pack turns a shard's [n_q, k_in] result into order-preserving u64 keys
+ * [n_q * ks + 2] (k_in <= ks, missing columns = empty; the two trailing words carry *status and `all_returned` = "this
+ * shard holds no document beyond its list") -- ONE all-gather moves every shard's block.  cdr_topk_merge_keys sorts
+ * the world * ks gathered keys of each query straight from that layout and writes the global top k; with ks < k the
+ * merge is exact iff every truncated shard's last key is <= the k-th merged key, otherwise (or when a shard scan
+ * reported a failure) *flag (device int32, caller-zeroed) is raised and the caller repeats the search with ks = k. */
+int cdr_topk_pack(const float* scores, const int64_t* ids, int32_t n_q, int32_t k_in, int32_t ks, const int32_t* status,
+                  int32_t all_returned, uint64_t* keys, void* stream);
+int cdr_topk_merge_keys(const uint64_t* gathered, int32_t world, int32_t n_q, int32_t ks, int32_t k, float* out_scores,
+                        int64_t* out_ids, int32_t* flag, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * ANN episode on the device (SURVEY f-2): the steps around the scan in the reference's ANN data generation.

@@ -15,9 +15,10 @@
     gradients through the sharded Gram, h_fun after two steps == the oracle that all-reduces the [G, P] matrix
   * gradsync.GradSync: mean-over-ranks gradients whether a layer's flat buffer can be reduced in place during
     backward (one use, no prior gradient) or must be deferred (layer used twice, accumulation, tied parameters)
-  * scan.search_sharded: documents split unevenly over the ranks (one shard smaller than k), per-rank top-k with
-    global ids, all-gather of the candidate lists, k-way merge == the single-process oracle scan of the whole corpus,
-    ids bit-exact in (score desc, id asc) order; the per-shard scan and the merge kernel are replaced by the oracle
+  * scan.search_sharded: per-rank lists as packed keys, one all-gather, merge with the exactness proof; full-length
+    lists with a shard smaller than k, short lists on an even split, and short lists on a corpus clustered by shard
+    (proof fails -> guaranteed path) all == the single-process oracle scan, ids bit-exact in (score desc, id asc) order;
+    the per-shard scan, the pack and the merge kernels are replaced by numpy stand-ins with the same key layout
 """
 import os
 import types
@@ -178,12 +179,44 @@ def _scan_worker(rank, world, port, ret):
     from cocodr_b200 import scan
     from oracle import scan_ref
 
-    def search_cpu(Q, P, k, doc_base=0, force_exhaustive=False):  # the per-shard scan: oracle, global ids
+    def flip(sc):
+        u = np.asarray(sc, dtype=np.float32).view(np.uint32).astype(np.uint64)
+        return np.where(u & np.uint64(0x80000000), ~u & np.uint64(0xFFFFFFFF), u | np.uint64(0x80000000))
+
+    def shard_keys_cpu(Q, P, ks, doc_base):  # stand-in for search_async + cdr_topk_pack (same key layout)
+        k_eff = min(ks, P.shape[0])
+        D, I = scan_ref.search(Q, P, k_eff)
+        n_q = Q.shape[0]
+        keys = np.zeros((n_q, ks), dtype=np.uint64)
+        ids = (np.asarray(I, dtype=np.int64) + doc_base).astype(np.uint64)
+        keys[:, :k_eff] = (flip(D) << np.uint64(32)) | (~ids & np.uint64(0xFFFFFFFF))
+        out = np.concatenate([keys.reshape(-1), np.array([0, int(k_eff == P.shape[0])], dtype=np.uint64)])
+        return torch.from_numpy(out.view(np.int64))
+
+    def merge_cpu(allk, W, n_q, ks, k):  # stand-in for cdr_topk_merge_keys, incl. the exactness proof
+        a = allk.numpy().view(np.uint64).reshape(W, n_q * ks + 2)
+        flag = int(a[:, n_q * ks].sum())
+        D, I = np.full((n_q, k), -np.inf, dtype=np.float32), np.full((n_q, k), -1, dtype=np.int64)
+        for q in range(n_q):
+            cand = np.sort(np.concatenate([a[w, q * ks:(q + 1) * ks] for w in range(W)]))[::-1][:k]
+            kth = cand[k - 1] if len(cand) >= k else np.uint64(0)
+            for w in range(W):
+                last = a[w, q * ks + ks - 1]
+                if a[w, n_q * ks + 1] == 0 and last != 0 and last > kth:
+                    flag += 1
+            live = cand[cand != 0]
+            u = (live >> np.uint64(32)).astype(np.uint32)
+            u = np.where(u & np.uint32(0x80000000), u & np.uint32(0x7FFFFFFF), ~u)
+            D[q, :len(live)] = u.view(np.float32)
+            I[q, :len(live)] = (~live & np.uint64(0xFFFFFFFF)).astype(np.int64)
+        return torch.from_numpy(D), torch.from_numpy(I), torch.tensor([flag], dtype=torch.int32)
+
+    def search_cpu(Q, P, k, doc_base=0, force_exhaustive=False):  # the per-shard scan of the guaranteed path
         k_eff = min(k, P.shape[0])
         D, I = scan_ref.search(Q, P, k_eff)
         return torch.from_numpy(np.asarray(D, dtype=np.float32)), torch.from_numpy(np.asarray(I, dtype=np.int64)) + doc_base
 
-    def merge_cpu(D, I, k):  # (score desc, id asc), ids < 0 = empty slots
+    def merge_topk_cpu(D, I, k):  # (score desc, id asc), ids < 0 = empty slots
         outD, outI = torch.empty(D.shape[0], k), torch.empty(D.shape[0], k, dtype=torch.int64)
         for r in range(D.shape[0]):
             live = [(-float(d), int(i)) for d, i in zip(D[r].tolist(), I[r].tolist()) if i >= 0]
@@ -192,14 +225,29 @@ def _scan_worker(rank, world, port, ret):
             outI[r] = torch.tensor([i for _, i in live[:k]])
         return outD, outI
 
-    scan.search, scan.merge_topk = search_cpu, merge_cpu
+    scan._shard_keys, scan._merge_gathered, scan.search, scan.merge_topk = shard_keys_cpu, merge_cpu, search_cpu, merge_topk_cpu
     k, n_docs = 40, 1000
     Q, P = scan_ref.synth_corpus(n_docs, 7, 64, seed=11, kind="exact")  # exact arithmetic, many ties
-    cut = n_docs - 25  # rank 1 holds fewer documents than k: its list is padded with empty slots
+    Dr, Ir = scan_ref.search(Q, P, k)
+    ok = True
+    # (a) full-length lists; rank 1 holds fewer documents than k: its list is padded with empty slots
+    cut = n_docs - 25
     lo, hi = (0, cut) if rank == 0 else (cut, n_docs)
     D, I = scan.search_sharded(Q, P[lo:hi], k, doc_base=lo)
-    Dr, Ir = scan_ref.search(Q, P, k)
-    ret[rank] = bool((I.numpy() == np.asarray(Ir)).all() and (D.numpy() == np.asarray(Dr, dtype=np.float32)).all())
+    ok = ok and bool((I.numpy() == np.asarray(Ir)).all() and (D.numpy() == np.asarray(Dr, dtype=np.float32)).all())
+    # (b) short lists (24 < k per shard), even split: the proof holds or the search silently repeats with full lists
+    scan.shard_list_len = lambda k_, w_: 24
+    lo, hi = (0, n_docs // 2) if rank == 0 else (n_docs // 2, n_docs)
+    D, I = scan.search_sharded(Q, P[lo:hi], k, doc_base=lo)
+    ok = ok and bool((I.numpy() == np.asarray(Ir)).all() and (D.numpy() == np.asarray(Dr, dtype=np.float32)).all())
+    # (c) short lists on a corpus CLUSTERED by shard (every query's best documents sit on rank 0): the proof must fail
+    #     and the fallback must still return the exact answer
+    order = np.argsort(-(np.asarray(Q[:1], dtype=np.float32) @ np.asarray(P, dtype=np.float32).T)[0], kind="stable")
+    Ps = P[torch.from_numpy(order.copy())]
+    Drs, Irs = scan_ref.search(Q[:1], Ps, k)
+    D, I = scan.search_sharded(Q[:1], Ps[lo:hi], k, doc_base=lo)
+    ok = ok and bool((I.numpy() == np.asarray(Irs)).all() and (D.numpy() == np.asarray(Drs, dtype=np.float32)).all())
+    ret[rank] = ok
     dist.destroy_process_group()
 
 

@@ -85,3 +85,34 @@ def test_mine_negatives_matches_reference_fixture(golden_dir):
         assert (neg.cpu().numpy() == g[f"{tag}.neg"]).all()
         assert (cnt.cpu().numpy() == (g[f"{tag}.neg"] >= 0).sum(1)).all()
         np.testing.assert_allclose(rr.cpu().numpy(), g[f"{tag}.rr"], rtol=1e-6)
+
+
+def test_encode_inference_loop_matches_oracle_embeddings():
+    """mining.encode == the reference's InferenceEmbeddingFromStreamDataLoader loop
+    (evaluate/drivers/run_ann_data_gen.py:152-206): batches in GetProcessingFn's format (int32 ids, bool mask, uint8
+    type ids, int64 idx; host tensors are copied inside the loop), eval() mode even when the model is in train(),
+    ids and embeddings returned in order; embeddings vs the fp32 oracle at 1e-2, fp16 and fp32 outputs."""
+    from cocodr_b200 import mining
+    from oracle import bert_ref
+    import test_model_gpu as T
+    m = T.build(T.TINY).train()  # train(): encode must switch dropout-free eval() on and restore the mode
+    cfg = T.TINY
+    batches, ref_ids, ref_embs = [], [], []
+    st = bert_ref.synth_state(cfg, 0)
+    for b, (n, L) in enumerate([(5, 32), (7, 32), (3, 48)]):  # ragged batch sizes and two sequence lengths
+        ids, mask = bert_ref.synth_batch(n, L, cfg["vocab"], 40 + b)
+        idx = torch.arange(100 * b, 100 * b + n)
+        batches.append((ids.int(), mask.bool(), torch.zeros(n, L, dtype=torch.uint8), idx))
+        ref_ids.append(idx)
+        with torch.no_grad():
+            ref_embs.append(bert_ref.cls_embedding(st, ids, mask, cfg))
+    ref = torch.cat(ref_embs).numpy()
+    for dtype in (torch.float16, torch.float32):
+        emb, ids = mining.encode(m, [tuple(t.pin_memory() for t in bt) for bt in batches], is_query=False, out_dtype=dtype)
+        assert emb.is_cuda and emb.dtype == dtype and emb.shape == ref.shape
+        assert torch.equal(ids.cpu(), torch.cat(ref_ids))
+        assert np.abs(emb.float().cpu().numpy() - ref).max() / np.abs(ref).max() < 1e-2
+    assert m.training
+    q_emb, _ = mining.encode(m, batches[:1], is_query=True)  # 3-tuples / device tensors are accepted as well
+    q2, _ = mining.encode(m, [(batches[0][0].cuda(), batches[0][1].cuda(), batches[0][3])], is_query=True)
+    assert torch.equal(q_emb, q2)
