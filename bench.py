@@ -198,7 +198,9 @@ class Ctx:
         torch.cuda.set_device(self.local)
         self.dev = torch.device("cuda", self.local)
         if self.world > 1:
-            dist.init_process_group("nccl", device_id=self.dev)
+            import datetime
+            # a mismatched collective must abort within minutes, not hold N GPUs for NCCL's default 10
+            dist.init_process_group("nccl", device_id=self.dev, timeout=datetime.timedelta(seconds=180))
         self.peaks = measured_peaks()
 
     def barrier(self):

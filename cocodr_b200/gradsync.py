@@ -95,7 +95,7 @@ class GradSync:
                 rest.append(p.grad)
         if rest:
             if self.comm is None:
-                for g in rest:
+                for g in self._coalesce(rest):
                     self._reduce(g)
             else:
                 cur = torch.cuda.current_stream()
@@ -115,24 +115,31 @@ class GradSync:
     @staticmethod
     def _coalesce(grads):
         """Gradients that are adjacent views of one allocation (a layer's flat buffer adopted by autograd) are reduced
-        as one tensor: one collective per layer instead of sixteen."""
-        out, run = [], None
-        for g in sorted((g for g in grads if g.is_contiguous()), key=lambda t: t.data_ptr()):
-            if (run is not None and g.dtype == run[0].dtype and g.untyped_storage().data_ptr() == run[0].untyped_storage().data_ptr()
-                    and g.data_ptr() == run[1]):
-                run[1] = g.data_ptr() + g.numel() * g.element_size()
-                run[2] += g.numel()
-            else:
-                if run is not None:
-                    out.append(run)
-                run = [g, g.data_ptr() + g.numel() * g.element_size(), g.numel()]
-        if run is not None:
-            out.append(run)
-        merged = []
-        for first, _, n in out:
-            if n == first.numel():
-                merged.append(first)
-            else:  # a view over the whole adjacent run, sharing the storage
-                merged.append(torch.as_strided(first, (n,), (1,), first.storage_offset()))
-        merged += [g for g in grads if not g.is_contiguous()]
-        return merged
+        as one tensor: one collective per layer instead of sixteen.  The ORDER of the returned tensors must be the same
+        on every rank (collectives are matched by issue order), so nothing here may depend on addresses: groups follow
+        the first appearance of their storage in parameter order, members are ordered by storage offset."""
+        groups, order = {}, []
+        for g in grads:
+            key = g.untyped_storage().data_ptr() if g.is_contiguous() else ("nc", id(g))
+            if key not in groups:
+                groups[key] = []
+                order.append(key)
+            groups[key].append(g)
+        out = []
+        for key in order:
+            members = groups[key]
+            if isinstance(key, tuple) or len(members) == 1:
+                out.extend(members)
+                continue
+            members = sorted(members, key=lambda t: t.storage_offset())
+            run_first, run_n = members[0], members[0].numel()
+            for g in members[1:]:
+                if g.dtype == run_first.dtype and g.storage_offset() == run_first.storage_offset() + run_n:
+                    run_n += g.numel()
+                else:
+                    out.append(run_first if run_n == run_first.numel() else
+                               torch.as_strided(run_first, (run_n,), (1,), run_first.storage_offset()))
+                    run_first, run_n = g, g.numel()
+            out.append(run_first if run_n == run_first.numel() else
+                       torch.as_strided(run_first, (run_n,), (1,), run_first.storage_offset()))
+        return out

@@ -22,7 +22,8 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    import datetime
+    dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=90))  # a mismatch must fail fast
     from cocodr_b200 import dro_loss, models, ops, scan
     from oracle import heads_ref, scan_ref
 
@@ -62,7 +63,9 @@ def main():
     summed = local_m.clone()
     dist.all_reduce(summed)
     refg = (summed.double() @ summed.double().t()).float()
-    np.testing.assert_allclose(got.cpu().numpy(), refg.cpu().numpy(), rtol=3e-4, atol=5e-2)
+    # (the local Gram runs on tcgen05 kind::tf32: operands keep 10 mantissa bits -> ~1e-3 of the row norms)
+    nrm = torch.sqrt(torch.diagonal(refg)).cpu().numpy()
+    assert (np.abs(got.cpu().numpy() - refg.cpu().numpy()) / (nrm[:, None] * nrm[None, :])).max() < 2e-3
 
     # 4. COCO contrastive, reference gather convention
     n_loc = 6

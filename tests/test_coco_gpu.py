@@ -158,8 +158,8 @@ def test_fixed_capacity_mlm_gather_equals_dynamic_and_is_graph_capturable(golden
         err = (out[0.5][1][n] - gr).abs().max().item()
         assert err <= 1e-6 + 2e-3 * gr.abs().max().item(), (n, err)
     assert int(m.mlm_overflow) == 0
-    m.mlm_capacity = 0.01  # too small on purpose: the overflow counter must say so
-    m(inp, labels)
+    m.mlm_capacity = 0.01  # too small on purpose (every position labelled): the overflow counter must say so
+    m(inp, torch.where(mask.bool(), ids, torch.full_like(ids, -100)))
     assert int(m.mlm_overflow) > 0
     m.mlm_capacity = 0.5
     m.train()
