@@ -43,6 +43,67 @@ class AverageMeter(object):
         self.avg = self.sum / self.count if self.count > 0 else 0.
 
 
+class MeterBank:
+    """The (2 + 2G) ``.item()`` host reads per step of the reference's meters (ANCE/model/models.py:269-271) kept on
+    the device: ``add`` accumulates (val, val * n, n) per meter with three tiny device ops -- no synchronisation, so a
+    whole DRO step can be captured into a CUDA graph -- and the host values are fetched (one transfer for all meters)
+    only when somebody READS a meter."""
+
+    def __init__(self, n):
+        self.n = n
+        self.dev = None
+        self.host = [[0.0, 0.0, 0.0] for _ in range(n)]  # val, sum, count contributed through update() on the host
+        self.snap = None                                  # last device snapshot
+        self.dirty = False
+
+    def add(self, vals, ns):
+        """vals, ns: device tensors [n]."""
+        if self.dev is None or self.dev.device != vals.device:
+            self.dev = torch.zeros(self.n, 3, dtype=torch.float64, device=vals.device)
+        v, c = vals.detach().to(torch.float64), ns.detach().to(torch.float64)
+        self.dev[:, 0] = v
+        self.dev[:, 1] += v * c
+        self.dev[:, 2] += c
+        self.dirty = True
+
+    def read(self, i):
+        if self.dirty:
+            self.snap = self.dev.tolist()
+            self.dirty = False
+        d = self.snap[i] if self.snap is not None else (0.0, 0.0, 0.0)
+        h = self.host[i]
+        return (d[0] if self.snap is not None else h[0]), h[1] + d[1], h[2] + d[2]
+
+    def meters(self):
+        return [BankMeter(self, i) for i in range(self.n)]
+
+
+class BankMeter(object):
+    """AverageMeter look-alike (val / sum / count / avg / update / reset) backed by a MeterBank slot."""
+
+    def __init__(self, bank, i):
+        self._bank, self._i = bank, i
+
+    val = property(lambda self: self._bank.read(self._i)[0])
+    sum = property(lambda self: self._bank.read(self._i)[1])
+    count = property(lambda self: self._bank.read(self._i)[2])
+
+    @property
+    def avg(self):
+        _, s, c = self._bank.read(self._i)
+        return s / c if c > 0 else 0.
+
+    def update(self, val, n=1):
+        h = self._bank.host[self._i]
+        h[0], h[1], h[2] = val, h[1] + val * n, h[2] + n
+
+    def reset(self):
+        self._bank.host[self._i] = [0.0, 0.0, 0.0]
+        if self._bank.dev is not None:
+            self._bank.dev[self._i].zero_()
+            self._bank.dirty = True
+
+
 class DROGreedyLoss(nn.Module):
     def __init__(self, args, n_groups, alpha, eps, ema=0.1, weight_ema=False, weight_cutoff=True, fraction=None):
         super().__init__()
@@ -82,7 +143,9 @@ class DROGreedyLoss(nn.Module):
             losses = losses * w
         batch_size = losses.size(0)
         gdro_losses, gdro_counts = ops.group_stats(losses, g, self.n_groups)
-        robust_loss = (gdro_losses * self.h_fun).sum() / batch_size
+        # (the state buffers are updated IN PLACE below -- a captured CUDA graph must find them at the same address at
+        # every replay -- so the loss multiplies a copy: autograd saves it for the backward)
+        robust_loss = (gdro_losses * self.h_fun.clone()).sum() / batch_size
         with torch.no_grad():
             if self.training:
                 if _world() > 1:
@@ -94,10 +157,10 @@ class DROGreedyLoss(nn.Module):
                     losses_agg, counts_agg = gdro_losses.detach(), gdro_counts
                 group_losses_agg = losses_agg / (counts_agg + (counts_agg == 0).float())
                 valid = counts_agg > 0
-                self.sum_losses = torch.where(valid, self.sum_losses * (1 - self.ema) + group_losses_agg * self.ema,
-                                              self.sum_losses)
+                self.sum_losses.copy_(torch.where(valid, self.sum_losses * (1 - self.ema) + group_losses_agg * self.ema,
+                                                  self.sum_losses))
                 if self.count_cat is not None:
-                    self.count_cat = self.count_cat * (1 - self.ema) + counts_agg * self.ema
+                    self.count_cat.copy_(self.count_cat * (1 - self.ema) + counts_agg * self.ema)
                 self.update_mw()
             group_losses = gdro_losses.detach() / (gdro_counts + (gdro_counts == 0).float())
         return robust_loss, group_losses, gdro_counts
@@ -124,9 +187,9 @@ class DROGreedyLoss(nn.Module):
         tmp[sort_id] = tmp_sorted
         if self.weight_ema:
             tmp = torch.clamp(tmp, min=self.eps)
-            self.h_fun = self.h_fun * (1 - self.ema) + tmp * self.ema
+            self.h_fun.copy_(self.h_fun * (1 - self.ema) + tmp * self.ema)
         else:
-            self.h_fun = tmp
+            self.h_fun.copy_(tmp)
 
 
 class iDROLoss(DROGreedyLoss):
@@ -409,7 +472,7 @@ class iDROLoss(DROGreedyLoss):
                                "gdro_counts_agg is undefined otherwise: dro_loss.py:222-226)")
         sums, counts = ops.group_stats(losses, g, self.n_groups)
         means = sums / (counts + (counts == 0).float())
-        robust_loss = (means * self.h_fun).sum()
+        robust_loss = (means * self.h_fun.clone()).sum()  # pre-update weights; h_fun itself is updated in place below
 
         mask = (counts > 0).float()
         params = self._params(model)
@@ -434,5 +497,5 @@ class iDROLoss(DROGreedyLoss):
             weight = torch.exp(_exp)
             h = torch.pow(self.h_fun, self.ema) * weight * (counts != 0).float()
             h = h / h.sum()
-            self.h_fun = torch.clamp(h, min=self.eps)
+            self.h_fun.copy_(torch.clamp(h, min=self.eps))
         return robust_loss, means.detach(), counts.detach()

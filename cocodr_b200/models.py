@@ -25,7 +25,7 @@ from transformers import BertConfig, BertForSequenceClassification, BertTokenize
 
 from . import ops, peer
 from .bert import BertModel
-from .dro_loss import AverageMeter, DROGreedyLoss, iDROLoss
+from .dro_loss import AverageMeter, DROGreedyLoss, MeterBank, iDROLoss
 
 logger = logging.getLogger(__name__)
 
@@ -146,8 +146,11 @@ class BertDot_NLL_LN(NLL, BertForSequenceClassification):
         if hasattr(self, "loss"):
             self.loss.to(self.bert.embeddings.word_embeddings.weight.device)
         self.n_groups = n_groups
-        self.accum_loss = AverageMeter()
-        self.accum_group_loss = [AverageMeter() for _ in range(n_groups)]
+        # same attributes as the reference (AverageMeter API), backed by device accumulators: no host sync per step
+        self._meters = MeterBank(1 + n_groups)
+        meters = self._meters.meters()
+        self.accum_loss = meters[0]
+        self.accum_group_loss = meters[1:]
 
     def query_emb(self, input_ids, attention_mask):
         """``self.bert(input_ids, attention_mask)[0][:, 0]`` (models.py:225-229), fp32 [B, H]."""
@@ -172,11 +175,10 @@ class BertDot_NLL_LN(NLL, BertForSequenceClassification):
             self._idro_grad_losses = None
         else:
             robust_loss, group_losses, group_counts = self.loss(loss, group_ids, weights)
-        host = torch.cat([robust_loss.detach().reshape(1), group_losses, group_counts]).tolist()  # one sync
-        self.accum_loss.update(host[0], loss.size(0))
-        G = self.n_groups
-        for i in range(G):
-            self.accum_group_loss[i].update(host[1 + i], host[1 + G + i])
+        # the reference's accum_loss.update(robust.item(), B) / accum_group_loss[i].update(gl[i].item(), gc[i].item())
+        # (:269-271), accumulated on the device and fetched when a meter is read (logging time)
+        self._meters.add(torch.cat([robust_loss.detach().reshape(1), group_losses]),
+                         torch.cat([group_counts.new_full((1,), float(loss.size(0))), group_counts]))
         return robust_loss, train_acc, group_losses, group_counts
 
     def forward(self, query_ids, attention_mask_q, input_ids_a=None, attention_mask_a=None, input_ids_b=None,

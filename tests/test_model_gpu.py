@@ -274,3 +274,37 @@ def test_inbatch_idro_group_gradient_views(mode):
     cos = float((got.ravel() * leaf[name].grad.numpy().ravel()).sum() /
                 (np.linalg.norm(got) * np.linalg.norm(leaf[name].grad.numpy()) + 1e-30))
     assert cos > 0.99, cos
+
+
+def test_idro_step_is_graph_capturable_and_meters_stay_on_device():
+    """The whole iDRO training step (forward, shared partial backward + grouped wgrad, Gram, in-place h_fun update,
+    backward, optimizer) replays from one CUDA graph: no host synchronisation is left in it (the reference reads
+    2 + 2G meters per step, ANCE/model/models.py:269-271; here they accumulate on the device until read).  Five
+    updates through warm-up + replays == five eager updates."""
+    from cocodr_b200.graph import GraphedTrainStep
+    G, B, L = 6, 8, 32
+    gid = torch.tensor([0, 1, 1, 3, 0, 4, 3, 3]).cuda()
+    batch = triplet(TINY, B, L, 61)
+
+    def make():
+        m = build(TINY).train()
+        m.add_group_loss(types.SimpleNamespace(model_size="base", local_rank=0), G, "idro", 0.25, 0.01, 0.1, 0.05)
+        opt = torch.optim.SGD([p for p in m.parameters() if p.requires_grad], lr=0.0)
+        return m, opt
+
+    eager, opt_e = make()
+    for _ in range(5):
+        opt_e.zero_grad(set_to_none=True)
+        eager(*batch, group_ids=gid)[0].backward()
+    m, opt = make()
+    step = GraphedTrainStep(m, opt, (*batch, True, gid), warmup=3)  # 3 eager warm-up steps, then capture
+    for _ in range(2):
+        loss = step(*batch)
+    np.testing.assert_allclose(m.loss.h_fun.cpu().numpy(), eager.loss.h_fun.cpu().numpy(), rtol=2e-3, atol=1e-6)
+    assert torch.isfinite(loss)
+    assert m.accum_loss.count == 5 * B == eager.accum_loss.count
+    assert abs(m.accum_loss.avg - eager.accum_loss.avg) < 1e-3 * abs(eager.accum_loss.avg)
+    h_fun, sum_loss = m.output_state()
+    assert abs(sum_loss["group3"] - eager.accum_group_loss[3].avg) < 1e-3 * abs(eager.accum_group_loss[3].avg) + 1e-6
+    m.accum_loss.reset()
+    assert m.accum_loss.count == 0 and m.accum_group_loss[1].count > 0
