@@ -199,6 +199,11 @@ class Ctx:
         self.dev = torch.device("cuda", self.local)
         if self.world > 1:
             import datetime
+            if args.nccl_ctas > 0:
+                # NCCL's kernels and the persistent one-CTA-per-SM GEMMs cannot share an SM (shared memory): cap the
+                # collective's CTAs and size the persistent grids for the remaining SMs, so no GEMM runs a second wave
+                os.environ["NCCL_MAX_CTAS"] = str(args.nccl_ctas)
+                os.environ["NCCL_MIN_CTAS"] = "1"
             # a mismatched collective must abort within minutes, not hold N GPUs for NCCL's default 10
             dist.init_process_group("nccl", device_id=self.dev, timeout=datetime.timedelta(seconds=180))
         self.peaks = measured_peaks()
@@ -290,6 +295,8 @@ def run_ours(args):
     cx = Ctx(args)
     dist, world, rank, dev = cx.dist, cx.world, cx.rank, cx.dev
     _lib.check(_lib.load().cdr_device_check(), "cdr_device_check")
+    if world > 1 and args.nccl_ctas > 0:
+        _lib.check(_lib.load().cdr_set_sm_budget(148 - args.nccl_ctas), "cdr_set_sm_budget")
 
     torch.manual_seed(0)
     cfg = BertConfig(hidden_dropout_prob=args.dropout, attention_probs_dropout_prob=args.dropout, num_labels=2)
@@ -425,6 +432,7 @@ def run_ours(args):
                                        "of every layer; Philox4x32-10 masks regenerated in the backward, offset advanced on the "
                                        "device inside the captured graph)") if args.dropout > 0 else "p=0 (--dropout 0)",
                            "cuda_graph": graphed is not None,
+                           "nccl_ctas": args.nccl_ctas,
                            "timed_region": f">= {MIN_REGION_MS / 1e3:.0f} s: the K steps are repeated inner_repeats times inside one event pair"},
                 "clocks": clocks.summary(),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -938,6 +946,7 @@ def main():
     ap.add_argument("--torch-adamw", action="store_true", help="use torch.optim.AdamW(fused=True) instead of cdr_adam_multi")
     ap.add_argument("--nccl-gather", action="store_true", help="N > 1: NCCL all-gather of the CLS embeddings instead of the fused peer-memory push")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--nccl-ctas", type=int, default=0, help="N > 1: cap NCCL at this many CTAs and leave that many SMs free of persistent kernels (0 = off)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -17,7 +17,8 @@
 
 namespace cdr {
 
-constexpr int SCAN_CAP_MIN = 2048;     // candidate slots per query: 8 k, at least 2048 (expected admissions: max(3 k, 1024))
+constexpr int SCAN_CAP_MIN = 8192;     // candidate slots per query (>= 8k)
+constexpr int SCAN_CAP_SMALL = 2048;   // short lists on small shards (see scan_plan)
 constexpr int SCAN_SAMPLE = 8192;      // sampled documents for the thresholds
 constexpr int SCAN_SORT_MAX = 16384;   // bitonic sort capacity (128 KB of keys)
 
@@ -383,6 +384,11 @@ static ScanPlan scan_plan(long long n_docs, int n_q, int k, int dim) {
   ScanPlan p{};
   p.cap = scan_cap(k);
   p.exhaustive = n_docs <= p.cap;
+  // Short lists on a small shard (the sharded search asks every rank for ~1.5 k / W entries): the expected admissions
+  // are max(3 k, 1024) and the threshold is the m-th largest of 8192 samples with m >= 32 when n_docs <= 262144, i.e.
+  // known to ~1 / sqrt(m) <= 18 % -- a 2048-slot buffer then has > 5 sigma of headroom and the per-query sort is 4x
+  // shorter.  (For larger corpora m is small, the admitted count scatters by tens of percent, and the 8192 slots stay.)
+  if (!p.exhaustive && k <= 256 && n_docs <= 262144) p.cap = SCAN_CAP_SMALL;
   p.S = static_cast<int>(n_docs < SCAN_SAMPLE ? (n_docs / 8) * 8 : SCAN_SAMPLE);
   if (p.S < 8) p.S = 8;
   p.step = n_docs / p.S;

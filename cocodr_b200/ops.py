@@ -118,11 +118,13 @@ class LayerShadow:
     the shadow is rebuilt whenever a parameter's storage or version counter changes -- by its owner
     (``ShadowSet.refresh``: one launch for all layers) or, standalone, by ``refresh``."""
 
-    __slots__ = ("key", "wqkv", "bqkv", "wo", "wi", "wo2", "managed")
+    __slots__ = ("key", "wqkv", "bqkv", "wo", "wi", "wo2", "managed", "table", "table_key", "max_n")
 
     def __init__(self):
         self.key = None
         self.managed = False
+        self.table = self.table_key = None
+        self.max_n = 0
 
     def _alloc(self, wq, wi):
         dev = wq.device
@@ -147,12 +149,17 @@ class LayerShadow:
             return self
         srcs = (wq, bq, wk, bk, wv, bv, wo, wi, wo2)
         key = tuple((t.data_ptr(), t._version) for t in srcs)
-        if key == self.key:
+        if key == self.key and not FORCE_SHADOW_REFRESH:
             return self
-        self._alloc(wq, wi)
+        realloc = self._alloc(wq, wi)
+        ptr_key = tuple(t.data_ptr() for t in srcs)
         with torch.no_grad():
-            table, max_n = K.cast_table(self.pairs(*srcs), wq.device)
-            K.cast_multi(table, max_n)
+            if realloc or self.table is None or self.table_key != ptr_key:
+                # (host -> device copy of the pointer table: only when a parameter moved, never inside a graph capture
+                # that follows warm-up steps)
+                self.table, self.max_n = K.cast_table(self.pairs(*srcs), wq.device)
+                self.table_key = ptr_key
+            K.cast_multi(self.table, self.max_n)
         self.key = key
         return self
 
@@ -635,6 +642,8 @@ class MLMShadow:
 
     def __init__(self):
         self.key = None
+        self.table = self.table_key = None
+        self.max_n = 0
 
     def refresh(self, wt, emb, bv):
         key = tuple((t.data_ptr(), t._version) for t in (wt, emb, bv))
@@ -643,15 +652,19 @@ class MLMShadow:
         dev = wt.device
         V, H = emb.shape
         vp = (V + 63) // 64 * 64
-        if self.key is None or self.emb.shape != (vp, H) or self.emb.device != dev:
+        realloc = self.key is None or self.emb.shape != (vp, H) or self.emb.device != dev
+        if realloc:
             self.vp = vp
             self.wt = _f16(H, H, dev=dev)
             self.emb = torch.zeros(vp, H, dtype=torch.float16, device=dev)
             self.bias = torch.full((vp,), float("-inf"), dtype=torch.float32, device=dev)
+        ptr_key = tuple(t.data_ptr() for t in (wt, emb, bv))
         with torch.no_grad():
-            table, max_n = K.cast_table([(wt.detach(), self.wt), (emb.detach(), self.emb[:V]),
-                                         (bv.detach(), self.bias[:V])], dev)
-            K.cast_multi(table, max_n)
+            if realloc or self.table is None or self.table_key != ptr_key:  # pointer table: rebuilt only when a parameter moved
+                self.table, self.max_n = K.cast_table([(wt.detach(), self.wt), (emb.detach(), self.emb[:V]),
+                                                       (bv.detach(), self.bias[:V])], dev)
+                self.table_key = ptr_key
+            K.cast_multi(self.table, self.max_n)
         self.key = key
         return self
 

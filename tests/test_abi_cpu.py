@@ -41,12 +41,12 @@ def test_struct_layouts_match_the_header(lib, tmp_path):
 
 def test_host_only_entry_points(lib):
     from cocodr_b200 import kernels as K
-    assert K.scan_exhaustive_docs(100) == 2048 and K.scan_exhaustive_docs(1000) == 8192
+    assert K.scan_exhaustive_docs(100) == 8192 and K.scan_exhaustive_docs(1000) == 8192
     assert K.scan_exhaustive_docs(2000) == 16384
     small = K.scan_workspace_bytes(6000, 37, 100)
     big = K.scan_workspace_bytes(1_000_000, 1000, 1000)
     assert 0 < small < big
-    assert big >= 1000 * 8192 * 8 + 1000 * 8192 * 4 and small >= 37 * 2048 * 8
+    assert big >= 1000 * 8192 * 8 + 1000 * 8192 * 4
     assert K.scan_workspace_bytes(0, 10, 10) == 0
 
 
