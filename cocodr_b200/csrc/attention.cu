@@ -99,22 +99,6 @@ __device__ __forceinline__ float dot8(const uint4& a, const uint4& b) {
 // TMEM columns: S[g] at g * 128, O[g] at 256 + g * 64.   smem: 2 x (Q K V) 96 KB | 2 x P 64 KB | small buffers.
 constexpr int ATT_FWD_THREADS = 320;
 constexpr int ATT_FWD_SMEM = 10 * ATT_TILE_BYTES + 8 * 512 + 8 * 2048 + 256 + 1024;
-constexpr int ATT_LUT16_BYTES = 256 * 16;  // DROP: keep byte -> four half2 AND-masks (0xFFFF keeps a half, 0 drops it)
-
-// 8 keep bits -> AND-masks for the 8 packed fp16 values of a group: applying the dropout mask to a group costs one
-// shared-memory load and four LOP3s instead of eight bit tests and selects (the softmax threads are the critical path)
-__device__ __forceinline__ void att_build_lut16(uint4* lut) {
-  for (int b = threadIdx.x; b < 256; b += blockDim.x) {
-    uint32_t w[4];
-#pragma unroll
-    for (int t = 0; t < 4; ++t)
-      w[t] = (((b >> (2 * t)) & 1) ? 0x0000FFFFu : 0u) | (((b >> (2 * t + 1)) & 1) ? 0xFFFF0000u : 0u);
-    lut[b] = make_uint4(w[0], w[1], w[2], w[3]);
-  }
-}
-__device__ __forceinline__ uint4 and4(const uint4& a, const uint4& m) {
-  return make_uint4(a.x & m.x, a.y & m.y, a.z & m.z, a.w & m.w);
-}
 
 template <bool DROP>
 __global__ void __launch_bounds__(ATT_FWD_THREADS, 1)
@@ -135,8 +119,6 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttParams p, 
   uint64_t* o_full = bar + 12;      // [2] MMA -> softmax group
   uint64_t* o_empty = bar + 14;     // [2] softmax group (4 warps) -> MMA
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 16);
-  uint4* sLut = reinterpret_cast<uint4*>(smem + ATT_FWD_SMEM - 1024);  // DROP only (the launch adds ATT_LUT16_BYTES)
-  if constexpr (DROP) att_build_lut16(sLut);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int L = p.seq_len;
@@ -289,12 +271,13 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttParams p, 
         for (int j = 0; j < 8; ++j) e[j] = fast_ex2(__uint_as_float(v[gq * 8 + j]) - mx);
         sum0 += (e[0] + e[1]) + (e[2] + e[3]);
         sum1 += (e[4] + e[5]) + (e[6] + e[7]);
-        uint4 pk = pack8(e);
         if constexpr (DROP) {  // the row sum is that of the undropped probabilities; 1 / (1 - p) joins 1 / sum below
           const uint32_t kw = (gq >> 2) == 0 ? keepw.x : (gq >> 2) == 1 ? keepw.y : (gq >> 2) == 2 ? keepw.z : keepw.w;
-          pk = and4(pk, sLut[(kw >> (8 * (gq & 3))) & 0xffu]);
+          const uint32_t keep = kw >> (8 * (gq & 3));
+#pragma unroll
+          for (int j = 0; j < 8; ++j) e[j] = ((keep >> j) & 1u) ? e[j] : 0.f;
         }
-        *reinterpret_cast<uint4*>(sP + swz_off(r, gq * 8)) = pk;
+        *reinterpret_cast<uint4*>(sP + swz_off(r, gq * 8)) = pack8(e);
       }
       fence_proxy_async();
       __syncwarp();
@@ -351,7 +334,6 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttParams p, 
 constexpr int ATT_BWD_SM_WARPS = 16;   // softmax warps: 4 per TMEM lane quadrant, 32 key columns per thread
 constexpr int ATT_BWD_THREADS = 64 + 32 * ATT_BWD_SM_WARPS + 128;  // producer, MMA issuer, softmax, 4 epilogue warps
 constexpr int ATT_BWD_SMEM = 12 * ATT_TILE_BYTES + 2048 + 2048 + 256 + 4 * 2048 + 1024;  // tiles | per-warp bias | delta quarters | barriers | epilogue transposition tiles
-constexpr int ATT_LUT32_BYTES = 256 * 32;  // DROP: keep byte -> eight 32-bit AND-masks (for the fp32 dP values)
 
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
@@ -423,15 +405,6 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
   uint64_t* out_empty = bar + 11;   // epilogue -> MMA (4 warps)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 12);
   uint8_t* sEpi = smem + 12 * ATT_TILE_BYTES + 4096 + 256;  // [4 epilogue warps][32 rows][64 B]
-  uint4* sLut16 = reinterpret_cast<uint4*>(smem + ATT_BWD_SMEM - 1024);  // DROP only (the launch adds both tables)
-  uint4* sLut32 = reinterpret_cast<uint4*>(smem + ATT_BWD_SMEM - 1024 + ATT_LUT16_BYTES);
-  if constexpr (DROP) {
-    att_build_lut16(sLut16);
-    for (int b = threadIdx.x; b < 256; b += blockDim.x) {
-      sLut32[2 * b] = make_uint4((b & 1) ? ~0u : 0u, (b & 2) ? ~0u : 0u, (b & 4) ? ~0u : 0u, (b & 8) ? ~0u : 0u);
-      sLut32[2 * b + 1] = make_uint4((b & 16) ? ~0u : 0u, (b & 32) ? ~0u : 0u, (b & 64) ? ~0u : 0u, (b & 128) ? ~0u : 0u);
-    }
-  }
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int L = p.seq_len;
@@ -597,18 +570,14 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
           pe = (r < L) ? pe : 0.f;
           sv[g * 8 + j] = __float_as_uint(pe);
           pu[j] = pe;
+          if constexpr (DROP) {
+            // forward used mask . P / (1 - p) and dP = mask / (1 - p) . (dO V^T): both masks are applied here as
+            // selects, the two 1 / (1 - p) factors are folded into the dV epilogue and the dS scale
+            const bool kept = ((keep32 >> (g * 8 + j)) & 1u) != 0u;
+            pe = kept ? pe : 0.f;
+            dv[g * 8 + j] = kept ? dv[g * 8 + j] : 0u;
+          }
           pv[j] = pe;
-        }
-        uint4 pk = pack8(pv);
-        if constexpr (DROP) {
-          // forward used mask . P / (1 - p) and dP = mask / (1 - p) . (dO V^T): both masks are applied as bitwise ANDs
-          // with table entries of the group's keep byte; the two 1 / (1 - p) factors are folded into the dV epilogue
-          // and the dS scale
-          const uint32_t kb = (keep32 >> (8 * g)) & 0xffu;
-          pk = and4(pk, sLut16[kb]);
-          const uint4 m0 = sLut32[2 * kb], m1 = sLut32[2 * kb + 1];
-          dv[g * 8 + 0] &= m0.x; dv[g * 8 + 1] &= m0.y; dv[g * 8 + 2] &= m0.z; dv[g * 8 + 3] &= m0.w;
-          dv[g * 8 + 4] &= m1.x; dv[g * 8 + 5] &= m1.y; dv[g * 8 + 6] &= m1.z; dv[g * 8 + 7] &= m1.w;
         }
         dp0 = fmaf(pu[0], __uint_as_float(dv[g * 8 + 0]), dp0);
         dp1 = fmaf(pu[1], __uint_as_float(dv[g * 8 + 1]), dp1);
@@ -618,7 +587,7 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
         dp1 = fmaf(pu[5], __uint_as_float(dv[g * 8 + 5]), dp1);
         dp2 = fmaf(pu[6], __uint_as_float(dv[g * 8 + 6]), dp2);
         dp3 = fmaf(pu[7], __uint_as_float(dv[g * 8 + 7]), dp3);
-        *reinterpret_cast<uint4*>(sP + swz_off(r, c0 + g * 8)) = pk;
+        *reinterpret_cast<uint4*>(sP + swz_off(r, c0 + g * 8)) = pack8(pv);
       }
       sDelta[qtr * ATT_T + r] = (dp0 + dp1) + (dp2 + dp3);
       fence_proxy_async();
@@ -1139,15 +1108,24 @@ __global__ void dq_convert_kernel(const float* __restrict__ ws, __half* __restri
 }
 
 // keep bits of the attention-probability dropout: byte kg of row (item * L + r) = Philox group (item * L + r) * 64 + kg
+// (a thread produces one 32-bit word = 4 groups: four independent Philox chains in flight, one 4-byte store)
 __global__ void __launch_bounds__(256)
 att_keep_bits_kernel(uint8_t* __restrict__ bits, long long n_rows, int groups_per_row, int stride, const cdr_dropout drop) {
   const DropCtx dc = drop_load(drop);
-  const long long total = n_rows * groups_per_row;
+  const int words_per_row = stride >> 2;
+  const long long total = n_rows * words_per_row;
   const long long step = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += step) {
-    const long long row = i / groups_per_row;
-    const int kg = static_cast<int>(i - row * groups_per_row);
-    bits[row * stride + kg] = static_cast<uint8_t>(drop_keep8(dc, static_cast<uint32_t>(row) * 64u + static_cast<uint32_t>(kg)));
+    const long long row = i / words_per_row;
+    const int w = static_cast<int>(i - row * words_per_row);
+    uint32_t word = 0u;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int kg = 4 * w + b;
+      if (kg < groups_per_row)
+        word |= drop_keep8(dc, static_cast<uint32_t>(row) * 64u + static_cast<uint32_t>(kg)) << (8 * b);
+    }
+    *reinterpret_cast<uint32_t*>(bits + row * stride + 4 * w) = word;
   }
 }
 
@@ -1200,7 +1178,7 @@ int cdr_attn_fwd(const cdr_attn_args* a, void* stream) {
     p.bits_stride = att_bits_stride(a->seq_len);
     const long long n_rows = static_cast<long long>(a->n_seq) * a->heads * a->seq_len;
     const int gpr = (a->seq_len + 7) / 8;
-    long long blocks = (n_rows * gpr + 255) / 256;
+    long long blocks = (n_rows * (p.bits_stride / 4) + 255) / 256;
     if (blocks > 32LL * sm_count()) blocks = 32LL * sm_count();
     att_keep_bits_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<uint8_t*>(a->drop_bits), n_rows, gpr, p.bits_stride, a->drop);
@@ -1209,8 +1187,7 @@ int cdr_attn_fwd(const cdr_attn_args* a, void* stream) {
   static bool configured = false;
   if (!configured) {
     CDR_CUDA(cudaFuncSetAttribute(fmha_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWD_SMEM));
-    CDR_CUDA(cudaFuncSetAttribute(fmha_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  ATT_FWD_SMEM + ATT_LUT16_BYTES));
+    CDR_CUDA(cudaFuncSetAttribute(fmha_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWD_SMEM));
     CDR_CUDA(cudaFuncSetAttribute(fmha_fwd_multi_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWDM_SMEM));
     CDR_CUDA(cudaFuncSetAttribute(fmha_fwd_multi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWDM_SMEM));
     configured = true;
@@ -1225,7 +1202,7 @@ int cdr_attn_fwd(const cdr_attn_args* a, void* stream) {
   const int n_items = a->n_seq * a->heads;
   const int grid = n_items < sm_count() ? n_items : sm_count();
   CDR_CUDA(launch_pdl(drop ? fmha_fwd_kernel<true> : fmha_fwd_kernel<false>, dim3(grid), dim3(ATT_FWD_THREADS),
-                      ATT_FWD_SMEM + (drop ? ATT_LUT16_BYTES : 0), static_cast<cudaStream_t>(stream), tq, p, n_items));
+                      ATT_FWD_SMEM, static_cast<cudaStream_t>(stream), tq, p, n_items));
   return CDR_OK;
 }
 
@@ -1253,8 +1230,7 @@ int cdr_attn_bwd(const cdr_attn_args* a, void* stream) {
   static bool configured = false;
   if (!configured) {
     CDR_CUDA(cudaFuncSetAttribute(fmha_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWD_SMEM));
-    CDR_CUDA(cudaFuncSetAttribute(fmha_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  ATT_BWD_SMEM + ATT_LUT16_BYTES + ATT_LUT32_BYTES));
+    CDR_CUDA(cudaFuncSetAttribute(fmha_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWD_SMEM));
     CDR_CUDA(cudaFuncSetAttribute(fmha_bwd_multi_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWDM_SMEM));
     CDR_CUDA(cudaFuncSetAttribute(fmha_bwd_multi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWDM_SMEM));
     configured = true;
@@ -1278,8 +1254,7 @@ int cdr_attn_bwd(const cdr_attn_args* a, void* stream) {
   const int n_items = a->n_seq * a->heads;
   const int grid = n_items < sm_count() ? n_items : sm_count();
   CDR_CUDA(launch_pdl(drop ? fmha_bwd_kernel<true> : fmha_bwd_kernel<false>, dim3(grid), dim3(ATT_BWD_THREADS),
-                      ATT_BWD_SMEM + (drop ? ATT_LUT16_BYTES + ATT_LUT32_BYTES : 0), static_cast<cudaStream_t>(stream), tq,
-                      td, p, n_items));
+                      ATT_BWD_SMEM, static_cast<cudaStream_t>(stream), tq, td, p, n_items));
   return CDR_OK;
 }
 

@@ -161,6 +161,8 @@ def test_fixed_capacity_mlm_gather_equals_dynamic_and_is_graph_capturable(golden
     m.mlm_capacity = 0.01  # too small on purpose (every position labelled): the overflow counter must say so
     m(inp, torch.where(mask.bool(), ids, torch.full_like(ids, -100)))
     assert int(m.mlm_overflow) > 0
+    del loss, out, m  # (autograd nodes of the eager default-stream passes must not outlive into the capture)
+    m = build_from_golden(g)
     m.mlm_capacity = 0.5
     m.train()
     opt = torch.optim.SGD([p for p in m.parameters() if p.requires_grad], lr=0.0)
