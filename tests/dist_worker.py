@@ -166,23 +166,27 @@ def main():
     # 8. iDRO on the in-batch head at world > 1: ranks hold DIFFERENT groups, so per-group partial backwards through the
     #    gathered keys would issue mismatched collectives; the group gradients come from collective-free loss views
     #    (models.BertDot_InBatch_NLL_LN.idro_group_grads).  Must not hang or produce non-finite weights / gradients.
+    tiny12 = dict(tiny, layers=12)  # iDRO differentiates layers 9-11 (dro_loss.py:176-190)
+    hf12 = BertConfig(vocab_size=2000, hidden_size=128, num_hidden_layers=12, num_attention_heads=2, intermediate_size=512,
+                      max_position_embeddings=64, hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1, num_labels=2)
+    m12 = models.BertDot_InBatch_NLL_LN(hf12)
+    m12.bert.load_state_dict(bert_ref.synth_state(tiny12, 0), strict=False)
+    m12 = m12.to(dev).train()
     for mode in ("own-pair", "local-batch"):
-        model.idro_group_grads = mode
-        model.add_group_loss(types.SimpleNamespace(model_size="base", local_rank=local), 6, "idro", 0.25, 0.01, 0.1, 0.05)
-        model.loss.para_name = {}
+        m12.idro_group_grads = mode
+        m12.add_group_loss(types.SimpleNamespace(model_size="base", local_rank=local), 6, "idro", 0.25, 0.01, 0.1, 0.05)
         gid = torch.tensor([0, 1, 1, 2] if rank == 0 else [3, 3, 4, 0], device=dev)
         for rep in range(2):
-            model.zero_grad(set_to_none=True)
-            robust = model(qi, qm, pi, pm, group_ids=gid, weights=w)[0]
-            s2 = GradSync(model)
+            m12.zero_grad(set_to_none=True)
+            robust = m12(qi, qm, pi, pm, group_ids=gid, weights=w)[0]
+            s2 = GradSync(m12)
             with s2:
                 robust.backward()
         torch.cuda.synchronize()
         # (h_fun is per rank: the reference mixes LOCAL group means / masks with the rank-summed gradients)
-        h = model.loss.h_fun.clone()
+        h = m12.loss.h_fun.clone()
         assert torch.isfinite(h).all() and abs(h.sum().item() - 1.0) < 0.2, (mode, h)
-        assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
-    model.dro_type = 'erm'
+        assert all(torch.isfinite(p.grad).all() for p in m12.parameters() if p.grad is not None)
 
     dist.barrier()
     if rank == 0:
