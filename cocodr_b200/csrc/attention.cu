@@ -88,47 +88,59 @@ __device__ __forceinline__ float dot8(const uint4& a, const uint4& b) {
 
 // ------------------------------------------------------------------------------------------ forward
 // seq_len <= 128.  Persistent and warp-specialised: one CTA per SM walks (sequence, head) items.
-//   warp 0       : TMA producer -- Q K V of item i+1 land in the other smem stage while item i computes
+//   warp 0       : TMA producer -- a 3-stage ring of (Q, K) tile pairs and a 3-stage ring of V tiles.  (Q, K) of a
+//                  stage are handed back as soon as S = Q K^T has been formed (long before the item ends), V after
+//                  O = P V, so the loads run up to three items ahead of the softmax; with the earlier 2-stage ring of
+//                  whole (Q K V) stages a stage was refilled only after the item's P V and the softmax warps spent most
+//                  of their time waiting for the next S (ncu: the s_full wait was the top stall, DRAM at 31 %).
 //   warp 1       : tcgen05.mma issuer (one thread) + TMEM owner
 //   warps 2..5   : softmax group 0 (even items);  warps 6..9 : softmax group 1 (odd items)
 // A softmax thread owns one query row (TMEM lane) end to end: exact row maximum (first pass over S in TMEM),
 // P = exp2(S - max) -> fp16 smem + row sum (second pass), then -- once O = P V of ITS item has landed -- the
-// epilogue O / sum -> ctx rows, coalesced through a warp-private transposition tile.  The two groups alternate
-// items and everything they touch (S / O columns, P buffer, smem stage) is per group, so group 1 runs its softmax
+// epilogue O / sum -> ctx rows, coalesced through a warp-private transposition tile (the first 2 KB of the warp's own
+// rows of the group's P buffer, which is dead between P V and the next softmax).  The two groups alternate
+// items and everything they touch (S / O columns, P buffer) is per group, so group 1 runs its softmax
 // while group 0 waits for its P V: no block-wide barrier anywhere.
-// TMEM columns: S[g] at g * 128, O[g] at 256 + g * 64.   smem: 2 x (Q K V) 96 KB | 2 x P 64 KB | small buffers.
+// TMEM columns: S[g] at g * 128, O[g] at 256 + g * 64.   smem: 3 x (Q K) 96 KB | 3 x V 48 KB | 2 x P 64 KB | small buffers.
 constexpr int ATT_FWD_THREADS = 320;
-constexpr int ATT_FWD_SMEM = 10 * ATT_TILE_BYTES + 8 * 512 + 8 * 2048 + 256 + 1024;
+constexpr int ATT_FWD_NST = 3;  // ring depth (both rings)
+constexpr int ATT_FWD_SMEM = (3 * ATT_FWD_NST + 4) * ATT_TILE_BYTES + 8 * 512 + 256 + 1024;
 
 template <bool DROP>
 __global__ void __launch_bounds__(ATT_FWD_THREADS, 1)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttParams p, const int n_items) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_align1024(smem_raw);
-  uint8_t* sStage = smem;                                 // [2][Q K V]
-  uint8_t* sPall = smem + 6 * ATT_TILE_BYTES;             // [2][two [128][64] chunks]
-  float* sBiasW = reinterpret_cast<float*>(smem + 10 * ATT_TILE_BYTES);          // [8 warps][128]
-  uint8_t* sEpi = smem + 10 * ATT_TILE_BYTES + 8 * 512;                          // [8 warps][32 rows][64 B]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 10 * ATT_TILE_BYTES + 8 * 512 + 8 * 2048);
-  uint64_t* full_qk = bar;          // [2] TMA -> MMA
-  uint64_t* full_v = bar + 2;       // [2]
-  uint64_t* stage_empty = bar + 4;  // [2] MMA -> TMA
-  uint64_t* s_full = bar + 6;       // [2] MMA -> softmax group
-  uint64_t* s_empty = bar + 8;      // [2] softmax group (4 warps) -> MMA
-  uint64_t* p_full = bar + 10;      // [2] softmax group (4 warps) -> MMA
-  uint64_t* o_full = bar + 12;      // [2] MMA -> softmax group
-  uint64_t* o_empty = bar + 14;     // [2] softmax group (4 warps) -> MMA
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 16);
+  constexpr int NST = ATT_FWD_NST;
+  uint8_t* sQK = smem;                                    // [NST][Q K]
+  uint8_t* sV = smem + 2 * NST * ATT_TILE_BYTES;          // [NST]
+  uint8_t* sPall = smem + 3 * NST * ATT_TILE_BYTES;       // [2][two [128][64] chunks]
+  float* sBiasW = reinterpret_cast<float*>(smem + (3 * NST + 4) * ATT_TILE_BYTES);  // [8 warps][128]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (3 * NST + 4) * ATT_TILE_BYTES + 8 * 512);
+  uint64_t* full_qk = bar;                // [NST] TMA -> MMA
+  uint64_t* full_v = bar + NST;           // [NST]
+  uint64_t* qk_empty = bar + 2 * NST;     // [NST] MMA -> TMA: S of the item has been formed
+  uint64_t* v_empty = bar + 3 * NST;      // [NST] MMA -> TMA: O of the item has been formed
+  uint64_t* s_full = bar + 4 * NST;       // [2] MMA -> softmax group
+  uint64_t* s_empty = s_full + 2;         // [2] softmax group (4 warps) -> MMA
+  uint64_t* p_full = s_full + 4;          // [2] softmax group (4 warps) -> MMA
+  uint64_t* o_full = s_full + 6;          // [2] MMA -> softmax group
+  uint64_t* o_empty = s_full + 8;         // [2] softmax group (4 warps) -> MMA
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(s_full + 10);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int L = p.seq_len;
+  const int n_local = static_cast<int>(blockIdx.x) < n_items
+                          ? (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)
+                          : 0;
 
   if (tid == 0) {
     tma_prefetch_desc(&tma_qkv);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) mbar_init(&bar[i], 1);
+    for (int i = 0; i < 4 * NST; ++i) mbar_init(&bar[i], 1);
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
       mbar_init(&s_empty[i], 4);
       mbar_init(&p_full[i], 4);
       mbar_init(&o_full[i], 1);
@@ -149,19 +161,31 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttParams p, 
 
   if (warp == 0) {
     // ===================== TMA producer =====================
+    // Issue order (Q, K)(i + 1) before V(i): the MMA thread forms S(i - 2) before O(i - 3), so neither wait below
+    // ever holds back a load whose stage is already free.
     if (lane == 0) {
-      int it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-        const int s = it & 1;
+      auto load_qk = [&](int it) {
+        const int s = it % NST;
+        const int item = blockIdx.x + it * gridDim.x;
         const int seq = item / p.heads, h = item % p.heads;
-        const int row0 = seq * L;
-        uint8_t* st = sStage + s * 3 * ATT_TILE_BYTES;
-        mbar_wait(&stage_empty[s], ((it >> 1) & 1) ^ 1);
+        uint8_t* st = sQK + s * 2 * ATT_TILE_BYTES;
+        mbar_wait(&qk_empty[s], ((it / NST) & 1) ^ 1);
         mbar_expect_tx(&full_qk[s], 2 * ATT_TILE_BYTES);
-        tma_load_2d(st, &tma_qkv, &full_qk[s], h * ATT_D, row0);
-        tma_load_2d(st + ATT_TILE_BYTES, &tma_qkv, &full_qk[s], p.hidden + h * ATT_D, row0);
+        tma_load_2d(st, &tma_qkv, &full_qk[s], h * ATT_D, seq * L);
+        tma_load_2d(st + ATT_TILE_BYTES, &tma_qkv, &full_qk[s], p.hidden + h * ATT_D, seq * L);
+      };
+      auto load_v = [&](int it) {
+        const int s = it % NST;
+        const int item = blockIdx.x + it * gridDim.x;
+        const int seq = item / p.heads, h = item % p.heads;
+        mbar_wait(&v_empty[s], ((it / NST) & 1) ^ 1);
         mbar_expect_tx(&full_v[s], ATT_TILE_BYTES);
-        tma_load_2d(st + 2 * ATT_TILE_BYTES, &tma_qkv, &full_v[s], 2 * p.hidden + h * ATT_D, row0);
+        tma_load_2d(sV + s * ATT_TILE_BYTES, &tma_qkv, &full_v[s], 2 * p.hidden + h * ATT_D, seq * L);
+      };
+      if (n_local > 0) load_qk(0);
+      for (int it = 0; it < n_local; ++it) {
+        if (it + 1 < n_local) load_qk(it + 1);
+        load_v(it);
       }
     }
   } else if (warp == 1) {
@@ -171,27 +195,28 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttParams p, 
       constexpr uint32_t idesc_o = make_idesc_f16(ATT_T, ATT_D, 0, 1);
       auto issue_s = [&](int jt) {  // S = Q K^T of local item jt into the S columns of group jt & 1
         const int g = jt & 1;
-        const uint32_t k = (jt >> 1) & 1;
-        const uint32_t qa = smem_u32(sStage + g * 3 * ATT_TILE_BYTES), ka = qa + ATT_TILE_BYTES;
-        mbar_wait(&full_qk[g], k);
-        mbar_wait(&s_empty[g], k ^ 1);
+        const int s = jt % NST;
+        const uint32_t qa = smem_u32(sQK + s * 2 * ATT_TILE_BYTES), ka = qa + ATT_TILE_BYTES;
+        mbar_wait(&full_qk[s], (jt / NST) & 1);
+        mbar_wait(&s_empty[g], ((jt >> 1) & 1) ^ 1);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < ATT_D / 16; ++kk)
           tc_mma_f16(tmem + g * 128, make_smem_desc(qa + kk * 32, 16, 1024), make_smem_desc(ka + kk * 32, 16, 1024),
                      idesc_s, kk > 0);
         tc_commit(&s_full[g]);
+        tc_commit(&qk_empty[s]);  // Q and K of this stage are consumed
       };
-      if (static_cast<int>(blockIdx.x) < n_items) issue_s(0);
-      int it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      if (n_local > 0) issue_s(0);
+      for (int it = 0; it < n_local; ++it) {
         const int g = it & 1;
+        const int s = it % NST;
         const uint32_t k = (it >> 1) & 1;
-        if (item + static_cast<int>(gridDim.x) < n_items) issue_s(it + 1);  // the other group's S first
+        if (it + 1 < n_local) issue_s(it + 1);  // the other group's S first
         const uint32_t pa = smem_u32(sPall + g * 2 * ATT_TILE_BYTES);
-        const uint32_t va = smem_u32(sStage + g * 3 * ATT_TILE_BYTES + 2 * ATT_TILE_BYTES);
+        const uint32_t va = smem_u32(sV + s * ATT_TILE_BYTES);
         mbar_wait(&p_full[g], k);
-        mbar_wait(&full_v[g], k);
+        mbar_wait(&full_v[s], (it / NST) & 1);
         mbar_wait(&o_empty[g], k ^ 1);
         tc_fence_after();
 #pragma unroll
@@ -199,7 +224,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttParams p, 
           tc_mma_f16(tmem + 256 + g * 64, make_smem_desc(pa + (kk >> 2) * ATT_TILE_BYTES + (kk & 3) * 32, 16, 1024),
                      make_smem_desc(va + kk * 2048, 8192, 1024), idesc_o, kk > 0);
         tc_commit(&o_full[g]);
-        tc_commit(&stage_empty[g]);  // Q K V of this stage are consumed
+        tc_commit(&v_empty[s]);  // V of this stage is consumed
       }
     }
   } else {
@@ -213,7 +238,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttParams p, 
     const uint32_t t_o = tmem + lane_off + 256 + g * 64;
     uint8_t* sP = sPall + g * 2 * ATT_TILE_BYTES;
     float* wb = sBiasW + sw * 128;   // this warp's private copy of the 128 key-bias values
-    uint8_t* tile = sEpi + sw * 2048;
+    uint8_t* tile = sP + quad * 4096;  // the first 16 of this warp's own P rows (chunk 0): dead once O has landed
     const float sl2 = p.scale * LOG2E;
     const float drop_scale = DROP ? p.drop.scale : 1.f;
     auto fetch_bias = [&](int item, int j) -> float {  // x LOG2E at use: nothing waits on the load here
@@ -254,23 +279,37 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttParams p, 
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[g]);
       // ---- pass 1: exact row maximum (scores kept as scaled log2 values)
-      float mx = -INFINITY;
+      // (packed fp32 pairs -- FFMA2 / FADD2 -- wherever two columns go through the same arithmetic: these threads are
+      // bound by fp32-pipe issue slots and dependent-issue latency, not by the MUFU)
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four chains: the maximum is latency-, not issue-bound
+      f32x2 vp[64];
+      {
+        const f32x2 sl2p = pk2(sl2);
 #pragma unroll
-      for (int j = 0; j < 128; ++j) {
-        const float sc = fmaf(__uint_as_float(v[j]), sl2, wb[j]);
-        v[j] = __float_as_uint(sc);
-        mx = fmaxf(mx, sc);
+        for (int j = 0; j < 64; ++j) {
+          float a, b;
+          vp[j] = fma2(pk2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), sl2p, pk2(wb[2 * j], wb[2 * j + 1]));
+          upk2(vp[j], a, b);
+          mx4[j & 3] = fmaxf(mx4[j & 3], fmaxf(a, b));
+        }
       }
+      float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       if (mx == -INFINITY) mx = 0.f;  // fully masked row: P = 0, output 0
       // ---- pass 2: P = exp2(S - max) -> smem, row sum
-      float sum0 = 0.f, sum1 = 0.f;
+      f32x2 sum01 = pk2(0.f), sum23 = pk2(0.f);
+      const f32x2 nmx = pk2(-mx);
 #pragma unroll
       for (int gq = 0; gq < 16; ++gq) {
         float e[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) e[j] = fast_ex2(__uint_as_float(v[gq * 8 + j]) - mx);
-        sum0 += (e[0] + e[1]) + (e[2] + e[3]);
-        sum1 += (e[4] + e[5]) + (e[6] + e[7]);
+        for (int j = 0; j < 4; ++j) {
+          float a, b;
+          upk2(add2(vp[gq * 4 + j], nmx), a, b);
+          e[2 * j] = fast_ex2(a);
+          e[2 * j + 1] = fast_ex2(b);
+        }
+        sum01 = add2(sum01, add2(pk2(e[0], e[1]), pk2(e[2], e[3])));
+        sum23 = add2(sum23, add2(pk2(e[4], e[5]), pk2(e[6], e[7])));
         if constexpr (DROP) {  // the row sum is that of the undropped probabilities; 1 / (1 - p) joins 1 / sum below
           const uint32_t kw = (gq >> 2) == 0 ? keepw.x : (gq >> 2) == 1 ? keepw.y : (gq >> 2) == 2 ? keepw.z : keepw.w;
           const uint32_t keep = kw >> (8 * (gq & 3));
@@ -278,6 +317,14 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttParams p, 
           for (int j = 0; j < 8; ++j) e[j] = ((keep >> j) & 1u) ? e[j] : 0.f;
         }
         *reinterpret_cast<uint4*>(sP + swz_off(r, gq * 8)) = pack8(e);
+      }
+      float sum0, sum1;
+      {
+        float s0, s1, s2, s3;
+        upk2(sum01, s0, s1);
+        upk2(sum23, s2, s3);
+        sum0 = s0 + s1;
+        sum1 = s2 + s3;
       }
       fence_proxy_async();
       __syncwarp();
@@ -333,7 +380,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttParams p, 
 // ----------------------------------------------------------------------------------------- backward
 constexpr int ATT_BWD_SM_WARPS = 16;   // softmax warps: 4 per TMEM lane quadrant, 32 key columns per thread
 constexpr int ATT_BWD_THREADS = 64 + 32 * ATT_BWD_SM_WARPS + 128;  // producer, MMA issuer, softmax, 4 epilogue warps
-constexpr int ATT_BWD_SMEM = 12 * ATT_TILE_BYTES + 2048 + 2048 + 256 + 4 * 2048 + 1024;  // tiles | per-warp bias | delta quarters | barriers | epilogue transposition tiles
+constexpr int ATT_BWD_PRE_BYTES = ATT_BWD_SM_WARPS * 2 * 3 * 128;  // per softmax warp: 2 buffers x (bias | lse | keep bits) x 32 words
+constexpr int ATT_BWD_SMEM = 12 * ATT_TILE_BYTES + 2048 + 2048 + 256 + 4 * 2048 + ATT_BWD_PRE_BYTES + 1024;  // tiles | per-warp bias | delta quarters | barriers | epilogue transposition tiles | prefetch slots
 
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
@@ -403,8 +451,10 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
   uint64_t* ds_full = bar + 9;      // softmax -> MMA (8 warps): dS is in smem
   uint64_t* out_full = bar + 10;    // MMA -> epilogue
   uint64_t* out_empty = bar + 11;   // epilogue -> MMA (4 warps)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 12);
+  uint64_t* dv_done = bar + 12;     // MMA -> softmax: dV of the item has been formed (the P buffer is free)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 13);
   uint8_t* sEpi = smem + 12 * ATT_TILE_BYTES + 4096 + 256;  // [4 epilogue warps][32 rows][64 B]
+  uint32_t* sPre = reinterpret_cast<uint32_t*>(sEpi + 4 * 2048);  // [16 softmax warps][2][bias | lse | keep][32]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int L = p.seq_len;
@@ -420,6 +470,7 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
     mbar_init(ds_full, ATT_BWD_SM_WARPS);
     mbar_init(out_full, 1);
     mbar_init(out_empty, 4);
+    mbar_init(dv_done, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -485,15 +536,31 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
         const uint32_t ph = it & 1;
         const uint32_t qa = smem_u32(sStage + s * 4 * ATT_TILE_BYTES), ka = qa + ATT_TILE_BYTES,
                        da = qa + 3 * ATT_TILE_BYTES;
-        mbar_wait(p_full, ph);
+        // S / dP of the NEXT item are issued as soon as its operands have landed and the softmax threads have copied
+        // this item's S / dP out of TMEM -- normally while they still form P, so the next softmax never waits for the
+        // tensor core (with the fixed order dV(i), S / dP(i+1) the softmax threads spent a third of their time in the
+        // sdp_full wait).  The probes are non-blocking: P of this item must not wait for a late load either.
+        bool sdp_issued = item + static_cast<int>(gridDim.x) >= n_items;
+        for (;;) {
+          if (!sdp_issued) {
+            const int s1 = (it + 1) & 1;
+            const uint32_t ph1 = ((it + 1) >> 1) & 1;
+            if (mbar_test_wait(&full_qk[s1], ph1) && mbar_test_wait(&full_vdo[s1], ph1) &&
+                mbar_test_wait(sdp_empty, ((it + 1) & 1) ^ 1)) {
+              issue_sdp(it + 1);
+              sdp_issued = true;
+            }
+          }
+          if (mbar_test_wait(p_full, ph)) break;
+        }
         mbar_wait(out_empty, ph ^ 1);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < ATT_T / 16; ++k)  // dV[kv,d] = sum_q P[q,kv] dO[q,d]
           tc_mma_f16(tmem + 256, make_smem_desc(pa + k * 2048, ATT_TILE_BYTES, 1024),
                      make_smem_desc(da + k * 2048, 8192, 1024), idesc_tt, k > 0);
-        // the next item's S / dP go in between: its softmax never waits for dK / dQ of this one
-        if (item + static_cast<int>(gridDim.x) < n_items) issue_sdp(it + 1);
+        tc_commit(dv_done);
+        if (!sdp_issued) issue_sdp(it + 1);
         mbar_wait(ds_full, ph);
         tc_fence_after();
 #pragma unroll
@@ -519,35 +586,35 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
     const float sl2 = p.scale * LOG2E;
     float* wb = sBiasW + sw * 32;   // this warp's private copy of the 32 key-bias values it needs
     const float ds_scale = p.scale * (DROP ? p.drop.scale : 1.f);
-    // values of the NEXT item are fetched one item ahead (global latency off the critical path)
-    auto fetch_bias = [&](int item) -> float {
+    // Per-item scalars (key bias of this warp's 32 columns, lse of this thread's row, DROP: the row's keep bits of these
+    // columns) are fetched ONE ITEM AHEAD with cp.async straight into a per-warp shared-memory slot: no register
+    // carries them across the item (at 80 registers per thread the compiler spilled them, and the spill store waited
+    // for the global load -- 13 % of the softmax threads' time).
+    uint32_t* pre = sPre + sw * (2 * 3 * 32);
+    auto prefetch = [&](int item, int buf) {
+      uint32_t* dst = pre + buf * 96;
       const int c = c0 + lane;
-      if (c >= L) return -INFINITY;
-      return p.key_bias ? p.key_bias[static_cast<long long>(item / p.heads) * L + c] : 0.f;  // x LOG2E at use
+      if (c < L && p.key_bias != nullptr) cp_async4(dst + lane, p.key_bias + static_cast<long long>(item / p.heads) * L + c);
+      else dst[lane] = __float_as_uint(c < L ? 0.f : -INFINITY);
+      if (r < L) cp_async4(dst + 32 + lane, p.lse + static_cast<long long>(item) * L + r);
+      else dst[32 + lane] = 0u;
+      if constexpr (DROP)
+        cp_async4(dst + 64 + lane, p.keep_bits + (static_cast<long long>(item) * L + min(r, L - 1)) * 16 + qtr * 4);
+      cp_async_commit();
     };
-    auto fetch_lse = [&](int item) -> float {
-      return r < L ? p.lse[static_cast<long long>(item) * L + r] : 0.f;  // x LOG2E at use: nothing waits on the load here
-    };
-    float nb = 0.f, nlse = 0.f;
-    if (static_cast<int>(blockIdx.x) < n_items) {
-      nb = fetch_bias(blockIdx.x);
-      nlse = fetch_lse(blockIdx.x);
-    }
+    if (static_cast<int>(blockIdx.x) < n_items) prefetch(blockIdx.x, 0);
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const uint32_t ph = it & 1;
-      const float lse2 = nlse * LOG2E;
-      __syncwarp();
-      wb[lane] = nb * LOG2E;
-      __syncwarp();
-      if (item + static_cast<int>(gridDim.x) < n_items) {
-        nb = fetch_bias(item + gridDim.x);
-        nlse = fetch_lse(item + gridDim.x);
-      }
+      uint32_t* cur = pre + (it & 1) * 96;
+      cp_async_wait_all();
+      const float lse2 = __uint_as_float(cur[32 + lane]) * LOG2E;
       uint32_t keep32 = 0xffffffffu;  // DROP: bit c = key column c0 + c of this row survived the forward dropout
-      if constexpr (DROP)
-        keep32 = __ldg(reinterpret_cast<const uint32_t*>(p.keep_bits + (static_cast<long long>(item) * L + min(r, L - 1)) * 16 +
-                                                         qtr * 4));
+      if constexpr (DROP) keep32 = cur[64 + lane];
+      __syncwarp();
+      wb[lane] = __uint_as_float(cur[lane]) * LOG2E;
+      __syncwarp();
+      if (item + static_cast<int>(gridDim.x) < n_items) prefetch(item + gridDim.x, (it + 1) & 1);
       mbar_wait(sdp_full, ph);
       tc_fence_after();
       // ---- S and dP of this thread's 32 columns: both loads in flight together, kept in registers to the end
@@ -558,51 +625,70 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(sdp_empty);  // S / dP columns may take item i+1 as soon as every warp has its copy
-      // ---- P (fp32 in place of S, fp16 to smem) and this quarter's share of delta
-      float dp0 = 0.f, dp1 = 0.f, dp2 = 0.f, dp3 = 0.f;
+      // ---- P (fp32, in registers as packed pairs) and this quarter's share of delta.  Nothing is written to shared
+      // memory yet: S / dP of this item may have been formed BEFORE dV of the previous item was issued (the MMA
+      // thread's early issue), so the P buffer may still be in use.
+      f32x2 pp[16], dd[16];  // P (undropped) and dP (DROP: masked) of columns c0 + 2 i, c0 + 2 i + 1
+      f32x2 dacc0 = pk2(0.f), dacc1 = pk2(0.f);
+      {
+        const f32x2 sl2p = pk2(sl2), nlse = pk2(-lse2);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float a0, a1;
+          upk2(add2(fma2(pk2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), sl2p, pk2(wb[2 * i], wb[2 * i + 1])), nlse),
+               a0, a1);
+          // masked keys carry bias = -inf -> P = 0; rows beyond seq_len are zeroed explicitly
+          float p0 = fast_ex2(a0), p1 = fast_ex2(a1);
+          p0 = (r < L) ? p0 : 0.f;
+          p1 = (r < L) ? p1 : 0.f;
+          uint32_t d0 = dv[2 * i], d1 = dv[2 * i + 1];
+          if constexpr (DROP) {
+            // forward used mask . P / (1 - p) and dP = mask / (1 - p) . (dO V^T): both masks are applied as selects,
+            // the two 1 / (1 - p) factors are folded into the dV epilogue and the dS scale
+            d0 = ((keep32 >> (2 * i)) & 1u) ? d0 : 0u;
+            d1 = ((keep32 >> (2 * i + 1)) & 1u) ? d1 : 0u;
+          }
+          pp[i] = pk2(p0, p1);
+          dd[i] = pk2(__uint_as_float(d0), __uint_as_float(d1));
+          if (i & 1) dacc1 = fma2(pp[i], dd[i], dacc1);
+          else dacc0 = fma2(pp[i], dd[i], dacc0);
+        }
+      }
+      {
+        float t0, t1;
+        upk2(add2(dacc0, dacc1), t0, t1);
+        sDelta[qtr * ATT_T + r] = t0 + t1;
+      }
+      if (it > 0) mbar_wait(dv_done, (it - 1) & 1);  // dV of the previous item has read the P buffer
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        float pv[8], pu[8];  // pv: what multiplied V in the forward (-> smem, dV); pu: the undropped probabilities
+        float pv[8];  // what multiplied V in the forward
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          // masked keys carry bias = -inf -> P = 0; rows beyond seq_len are zeroed explicitly
-          float pe = fast_ex2(fmaf(__uint_as_float(sv[g * 8 + j]), sl2, wb[g * 8 + j]) - lse2);
-          pe = (r < L) ? pe : 0.f;
-          sv[g * 8 + j] = __float_as_uint(pe);
-          pu[j] = pe;
+        for (int j = 0; j < 4; ++j) {
+          upk2(pp[g * 4 + j], pv[2 * j], pv[2 * j + 1]);
           if constexpr (DROP) {
-            // forward used mask . P / (1 - p) and dP = mask / (1 - p) . (dO V^T): both masks are applied here as
-            // selects, the two 1 / (1 - p) factors are folded into the dV epilogue and the dS scale
-            const bool kept = ((keep32 >> (g * 8 + j)) & 1u) != 0u;
-            pe = kept ? pe : 0.f;
-            dv[g * 8 + j] = kept ? dv[g * 8 + j] : 0u;
+            pv[2 * j] = ((keep32 >> (g * 8 + 2 * j)) & 1u) ? pv[2 * j] : 0.f;
+            pv[2 * j + 1] = ((keep32 >> (g * 8 + 2 * j + 1)) & 1u) ? pv[2 * j + 1] : 0.f;
           }
-          pv[j] = pe;
         }
-        dp0 = fmaf(pu[0], __uint_as_float(dv[g * 8 + 0]), dp0);
-        dp1 = fmaf(pu[1], __uint_as_float(dv[g * 8 + 1]), dp1);
-        dp2 = fmaf(pu[2], __uint_as_float(dv[g * 8 + 2]), dp2);
-        dp3 = fmaf(pu[3], __uint_as_float(dv[g * 8 + 3]), dp3);
-        dp0 = fmaf(pu[4], __uint_as_float(dv[g * 8 + 4]), dp0);
-        dp1 = fmaf(pu[5], __uint_as_float(dv[g * 8 + 5]), dp1);
-        dp2 = fmaf(pu[6], __uint_as_float(dv[g * 8 + 6]), dp2);
-        dp3 = fmaf(pu[7], __uint_as_float(dv[g * 8 + 7]), dp3);
         *reinterpret_cast<uint4*>(sP + swz_off(r, c0 + g * 8)) = pack8(pv);
       }
-      sDelta[qtr * ATT_T + r] = (dp0 + dp1) + (dp2 + dp3);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);  // dV = P^T dO may start while dS is being formed
       named_bar_sync(1 + quad, 128);       // the four warps that share these 32 rows
       const float delta = (sDelta[r] + sDelta[ATT_T + r]) + (sDelta[2 * ATT_T + r] + sDelta[3 * ATT_T + r]);
       // ---- dS = P (dP - delta) scale
+      if (it > 0) mbar_wait(out_full, (it - 1) & 1);  // dK / dQ of the previous item have read the dS buffer
+      {
+        const f32x2 scp = pk2(ds_scale), nds = pk2(-delta * ds_scale);
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        float ds[8];
+        for (int g = 0; g < 4; ++g) {
+          float ds[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          ds[j] = __uint_as_float(sv[g * 8 + j]) * (__uint_as_float(dv[g * 8 + j]) - delta) * ds_scale;
-        *reinterpret_cast<uint4*>(sdS + swz_off(r, c0 + g * 8)) = pack8(ds);
+          for (int j = 0; j < 4; ++j) upk2(mul2(pp[g * 4 + j], fma2(dd[g * 4 + j], scp, nds)), ds[2 * j], ds[2 * j + 1]);
+          *reinterpret_cast<uint4*>(sdS + swz_off(r, c0 + g * 8)) = pack8(ds);
+        }
       }
       fence_proxy_async();
       __syncwarp();

@@ -108,6 +108,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking probe (try_wait may suspend the thread for a while; a thread that polls SEVERAL barriers must not)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// 4-byte asynchronous global -> shared copy (no register in between), grouped with commit / wait
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
@@ -301,6 +321,59 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   gelu_tail(x, tail, e);
   const float cdf = x > 0.f ? 1.0f - tail : tail;
   return fmaf(x * 0.3989422804014327f, e, cdf);
+}
+
+// ---- packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2): one instruction works on TWO fp32 values held in a 64-bit
+// register pair.  The epilogues and the softmax threads are bound by fp32-pipe issue slots, not by latency, so the
+// arithmetic that can be paired is (IEEE fp32 per half, same results as the scalar forms).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 pk2(float a) { return pk2(a, a); }
+__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// gelu_erf_both for two values at once: same A-S 7.1.26 evaluation, arranged so that everything but the two MUFU
+// calls per element is a packed operation.  With c = 1 / sqrt(2 pi):  e' = c exp(-x^2/2) comes out of ONE ex2 (the
+// factor is an addend of the exponent), tail = Phi(-|x|) = (poly(t) / c) t e', Phi(x) = 1/2 + sign(x) (1/2 - tail),
+// gelu = x Phi(x), gelu' = Phi(x) + x e'.
+__device__ __forceinline__ void gelu_erf_both2(float x0, float x1, f32x2& y, f32x2& dy) {
+  const f32x2 x = pk2(x0, x1);
+  const f32x2 ax = pk2(fabsf(x0), fabsf(x1));
+  float a0, a1, n0, n1;
+  upk2(fma2(mul2(ax, ax), pk2(-0.72134752044448170f), pk2(-1.3257480647361593f)), a0, a1);  // -x^2 log2(e)/2 + log2(c)
+  upk2(fma2(ax, pk2(0.23164189f), pk2(1.0f)), n0, n1);
+  const f32x2 e = pk2(fast_ex2(a0), fast_ex2(a1));
+  const f32x2 t = pk2(fast_rcp(n0), fast_rcp(n1));
+  f32x2 poly = fma2(t, pk2(1.3302744929f), pk2(-1.8212559978f));  // 0.5 * A-S coefficients / c
+  poly = fma2(t, poly, pk2(1.7814779315f));
+  poly = fma2(t, poly, pk2(-0.3565637813f));
+  poly = fma2(t, poly, pk2(0.3193815300f));
+  const f32x2 tail = mul2(mul2(poly, t), e);
+  const f32x2 half = pk2(0.5f);
+  const f32x2 sgn = pk2(copysignf(1.0f, x0), copysignf(1.0f, x1));
+  const f32x2 cdf = fma2(sgn, fma2(tail, pk2(-1.0f), half), half);
+  y = mul2(x, cdf);
+  dy = fma2(x, e, cdf);
 }
 
 // value and derivative from one shared tail / pdf evaluation (the forward GELU epilogue stores both)

@@ -38,8 +38,13 @@ constexpr int GEMM_BK = 64;
 #ifndef CDR_GEMM_EPI_WARPS
 #define CDR_GEMM_EPI_WARPS 8
 #endif
+#ifndef CDR_GEMM_GELU_EPI_WARPS  // the GELU epilogue (value + derivative, ~24 instructions per element) is issue-bound
+#define CDR_GEMM_GELU_EPI_WARPS CDR_GEMM_EPI_WARPS
+#endif
 template <int EPI>
-constexpr int GEMM_EW = (EPI == CDR_EPI_SCAN_FILTER || EPI == CDR_EPI_SCAN_FILTER_Q) ? 16 : CDR_GEMM_EPI_WARPS;
+constexpr int GEMM_EW = (EPI == CDR_EPI_SCAN_FILTER || EPI == CDR_EPI_SCAN_FILTER_Q) ? 16
+                        : (EPI == CDR_EPI_BIAS_GELU)                                  ? CDR_GEMM_GELU_EPI_WARPS
+                                                                                      : CDR_GEMM_EPI_WARPS;
 template <int EPI>
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EW<EPI>;
 
@@ -170,17 +175,25 @@ __device__ __forceinline__ void gemm_epilogue_apply(const GemmParams& p, float (
       *reinterpret_cast<float4*>(o + 4) = hi;
     }
   } else {
+    // packed fp32 pairs (FFMA2): the epilogue warps are bound by fp32-pipe issue slots
+    f32x2 w[4];
+    {
+      const f32x2 al = pk2(p.alpha);
 #pragma unroll
-    for (int t = 0; t < 8; ++t) v[t] = fmaf(v[t], p.alpha, bias[t]);
-    if constexpr (EPI == CDR_EPI_BIAS_DROP_RESIDUAL)  // HF BertSelfOutput / BertOutput: LN(x + dropout(dense(h)))
-      drop_apply8(dc, drop_keep8(dc, drop_group(dc, m, n, p.N)), v);
+      for (int t = 0; t < 4; ++t) w[t] = fma2(pk2(v[2 * t], v[2 * t + 1]), al, pk2(bias[2 * t], bias[2 * t + 1]));
+    }
+    if constexpr (EPI == CDR_EPI_BIAS_DROP_RESIDUAL) {  // HF BertSelfOutput / BertOutput: LN(x + dropout(dense(h)))
+      const uint32_t keep = drop_keep8(dc, drop_group(dc, m, n, p.N));
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        w[t] = mul2(w[t], pk2(((keep >> (2 * t)) & 1u) ? dc.scale : 0.f, ((keep >> (2 * t + 1)) & 1u) ? dc.scale : 0.f));
+    }
     if constexpr (EPI == CDR_EPI_BIAS_RESIDUAL || EPI == CDR_EPI_BIAS_DROP_RESIDUAL) {
       const __half2* rh = reinterpret_cast<const __half2*>(&auxq);
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const float2 f = __half22float2(rh[t]);
-        v[2 * t] += f.x;
-        v[2 * t + 1] += f.y;
+        w[t] = add2(w[t], pk2(f.x, f.y));
       }
     }
     if constexpr (EPI == CDR_EPI_DGELU) {
@@ -188,22 +201,31 @@ __device__ __forceinline__ void gemm_epilogue_apply(const GemmParams& p, float (
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const float2 f = __half22float2(gh[t]);
-        v[2 * t] *= f.x;
-        v[2 * t + 1] *= f.y;
+        w[t] = mul2(w[t], pk2(f.x, f.y));
       }
     }
     if constexpr (EPI == CDR_EPI_BIAS_GELU) {
-      float d[8];
+      f32x2 d[4];
 #pragma unroll
-      for (int t = 0; t < 8; ++t) gelu_erf_both(v[t], v[t], d[t]);
+      for (int t = 0; t < 4; ++t) {
+        float z0, z1;
+        upk2(w[t], z0, z1);
+        gelu_erf_both2(z0, z1, w[t], d[t]);
+      }
       if (p.out2 != nullptr && !CDR_DBG(p, 2)) {
         uint4 dq;
         __half2* dh = reinterpret_cast<__half2*>(&dq);
 #pragma unroll
-        for (int t = 0; t < 4; ++t) dh[t] = __floats2half2_rn(d[2 * t], d[2 * t + 1]);
+        for (int t = 0; t < 4; ++t) {
+          float d0, d1;
+          upk2(d[t], d0, d1);
+          dh[t] = __floats2half2_rn(d0, d1);
+        }
         *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out2) + static_cast<long long>(m) * p.ldo + n) = dq;
       }
     }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) upk2(w[t], v[2 * t], v[2 * t + 1]);
     uint4 q;
     __half2* qh = reinterpret_cast<__half2*>(&q);
 #pragma unroll
@@ -315,11 +337,14 @@ template <int EPI>
 __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const uint32_t (&acc)[32], float* stg,
                                                     int lane, int m_base, int n0, const uint4 (&auxq)[4],
                                                     const DropCtx& dc) {
+  const bool no_stage = CDR_DBG(p, 16);  // smem-contention experiment: skip the transposition (wrong values, same math)
+  if (!no_stage) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
-    *stg_piece(stg, lane, j) = make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]),
-                                           __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
-  __syncwarp();
+    for (int j = 0; j < 8; ++j)
+      *stg_piece(stg, lane, j) = make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]),
+                                             __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
+    __syncwarp();
+  }
   const int seg = lane & 3;
   const int n = n0 + seg * 8;
   const bool col_ok = n < p.N;
@@ -344,8 +369,14 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const u
   for (int i = 0; i < 4; ++i) {
     const int r = (lane >> 2) + 8 * i;
     const int m = m_base + r;
-    const float4 lo = *stg_piece(stg, r, 2 * seg);
-    const float4 hi = *stg_piece(stg, r, 2 * seg + 1);
+    float4 lo, hi;
+    if (no_stage) {
+      lo = make_float4(__uint_as_float(acc[8 * i]), __uint_as_float(acc[8 * i + 1]), __uint_as_float(acc[8 * i + 2]), __uint_as_float(acc[8 * i + 3]));
+      hi = make_float4(__uint_as_float(acc[8 * i + 4]), __uint_as_float(acc[8 * i + 5]), __uint_as_float(acc[8 * i + 6]), __uint_as_float(acc[8 * i + 7]));
+    } else {
+      lo = *stg_piece(stg, r, 2 * seg);
+      hi = *stg_piece(stg, r, 2 * seg + 1);
+    }
     float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
     if (col_ok && m < p.M) {
       gemm_epilogue_apply<EPI>(p, v, m, n, bias, auxq[i], dc);
@@ -467,7 +498,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           if constexpr (CG == 2) {
             // completion bytes of BOTH CTAs are posted on the leader's barrier
             const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
-            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);
+            const bool skip_b = CDR_DBG(p, 8) && (kb & 1);  // feed experiment: odd k-blocks reuse stale B tiles
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], skip_b ? 2 * S::A_BYTES : 2 * S::STAGE_BYTES);
             if constexpr (A_MN) {
 #pragma unroll
               for (int c = 0; c < GEMM_BM / 64; ++c)
@@ -475,7 +507,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             } else {
               tma_load_2d_cg2(da, &tma_a, bar, kb * GEMM_BK, m0);
             }
-            if constexpr (B_MN) {
+            if (skip_b) {
+            } else if constexpr (B_MN) {
 #pragma unroll
               for (int c = 0; c < BNL / 64; ++c)
                 tma_load_2d_cg2(db + c * (GEMM_BK * 128), &tma_b, bar, n0 + c * 64, kb * GEMM_BK);

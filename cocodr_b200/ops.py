@@ -24,6 +24,38 @@ GROUP_CAPTURE = None          # a GroupCapture: layer backwards also hand over t
 FWD_CALLS = {}                # id(first parameter of a Function) -> forwards since the last GradSync exit (gradsync.py)
 
 
+# Parameter-gradient GEMMs (wgrad) of a layer are independent of the activation-gradient chain.  With WGRAD_OVERLAP they
+# are enqueued on a second stream (forked / joined with events, also inside a CUDA graph capture), so the persistent
+# one-CTA-per-SM GEMMs of the two streams fill each other's last partial wave (a [16384, 768] output is 192 tiles on 74
+# CTA pairs = 2.6 waves).  CDR_WGRAD_OVERLAP=0 keeps everything on one stream.
+import os as _os
+WGRAD_OVERLAP = _os.environ.get("CDR_WGRAD_OVERLAP", "0") != "0"
+_WGRAD_STREAMS = {}
+
+
+def _wgrad_stream(dev):
+    st = _WGRAD_STREAMS.get(dev)
+    if st is None:
+        st = _WGRAD_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    return st
+
+
+def _wgrad(a, b, out, **kw):
+    """dW += a^T b on the wgrad stream, after everything enqueued so far on the current stream."""
+    if not WGRAD_OVERLAP:
+        return K.gemm(a, b, out, **kw)
+    side = _wgrad_stream(a.device)
+    side.wait_event(torch.cuda.current_stream().record_event())
+    with torch.cuda.stream(side):
+        K.gemm(a, b, out, **kw)
+
+
+def _wgrad_join(dev):
+    """The current stream waits for the wgrad stream (end of a layer backward: operands die, gradients are consumed)."""
+    if WGRAD_OVERLAP:
+        torch.cuda.current_stream().wait_event(_wgrad_stream(dev).record_event())
+
+
 def _note_forward(ctx, params):
     """Count the forwards of a parameter set that autograd records (grad mode is off INSIDE Function.forward, so the
     Function's needs_input_grad is the signal): GradSync only reduces a layer's flat gradient buffer in place when the
@@ -334,34 +366,36 @@ class BertLayerFn(torch.autograd.Function):
         dy2, dy2m = _ln_bwd_after_dropout(dy, dcls, y2, g2, mean2, rstd2, dg2, dbe2, dbo2, n_seq=n_seq, seq_len=L, S=S,
                                           site=dc, row_ws=row_ws)
         # ---- FFN down: dZ = (dy2m W2) * gelu'(z) with db1 = colsum(dZ) fused into the epilogue, dW2 = dy2m^T G
+        # (every wgrad is enqueued as soon as its operands exist, ahead of the dgrad that shares them)
+        _wgrad(dy2m, gl, dwo2, M=H, N=I, K=T, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0, alpha=inv)
         dz = _f16(T, I, dev=dev)
         K.gemm(dy2m, wo2, dz, M=T, N=I, K=H, b_major=1, epilogue=K.EPI_DGELU, aux=gp, colsum=dbi, colsum_scale=inv)
-        K.gemm(dy2m, gl, dwo2, M=H, N=I, K=T, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0, alpha=inv)
         # ---- FFN up: dx1 = dZ W1 + dy2 (residual), dW1 = dZ^T x1
+        _wgrad(dz, x1, dwi, M=I, N=H, K=T, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0, alpha=inv)
         dx1 = _f16(T, H, dev=dev)
         K.gemm(dz, wi, dx1, M=T, N=H, K=I, b_major=1, epilogue=K.EPI_BIAS_RESIDUAL, aux=dy2)
-        K.gemm(dz, x1, dwi, M=I, N=H, K=T, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0, alpha=inv)
         # ---- attention-output LayerNorm
         dy1, dy1m = _ln_bwd_after_dropout(dx1, None, y1, g1, mean1, rstd1, dg1, dbe1, dbo, n_seq=n_seq, seq_len=L, S=S,
                                           site=db, row_ws=row_ws)
         # ---- attention output projection
+        _wgrad(dy1m, att, dwo, M=H, N=H, K=T, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0, alpha=inv)
         datt = _f16(T, H, dev=dev)
         K.gemm(dy1m, wo, datt, M=T, N=H, K=H, b_major=1)
-        K.gemm(dy1m, att, dwo, M=H, N=H, K=T, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0, alpha=inv)
         # ---- attention core
         dqkv = _f16(T, 3 * H, dev=dev)
         fused_db = L <= 128  # the one-tile backward also emits the QKV bias gradient (column sums of dQKV)
         K.attn_bwd(qkv, key_bias, att, lse, datt, dqkv, n_seq=n_seq, seq_len=L, heads=heads,
                    dbias=dbqkv if fused_db else None, dbias_scale=inv, drop=da, drop_bits=bits)
         # ---- QKV projection: dx = dQKV Wqkv + dy1 (residual)
+        _wgrad(dqkv, x, dwqkv, M=3 * H, N=H, K=T, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0,
+               alpha=inv)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = _f16(T, H, dev=dev)
             K.gemm(dqkv, wqkv, dx, M=T, N=H, K=3 * H, b_major=1, epilogue=K.EPI_BIAS_RESIDUAL, aux=dy1)
-        K.gemm(dqkv, x, dwqkv, M=3 * H, N=H, K=T, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, split_k=0,
-               alpha=inv)
         if not fused_db:
             K.colsum(dqkv, dbqkv, rows=T, cols=3 * H, scale=inv)
+        _wgrad_join(dev)
         _submit(ctx, flat)
         if GROUP_CAPTURE is not None:
             GROUP_CAPTURE.records.append(dict(

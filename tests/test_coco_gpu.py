@@ -164,6 +164,7 @@ def test_fixed_capacity_mlm_gather_equals_dynamic_and_is_graph_capturable(golden
     del loss, out, m  # (autograd nodes of the eager default-stream passes must not outlive into the capture)
     m = build_from_golden(g)
     m.mlm_capacity = 0.5
+    m.lm.config.hidden_dropout_prob = m.lm.config.attention_probs_dropout_prob = 0.1  # (the fixture model has p = 0)
     m.train()
     opt = torch.optim.SGD([p for p in m.parameters() if p.requires_grad], lr=0.0)
     step = GraphedTrainStep(lambda i, a, l: m({"input_ids": i, "attention_mask": a}, l), opt, (ids, mask, labels))

