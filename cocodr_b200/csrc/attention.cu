@@ -380,6 +380,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttParams p, 
 // ----------------------------------------------------------------------------------------- backward
 constexpr int ATT_BWD_SM_WARPS = 16;   // softmax warps: 4 per TMEM lane quadrant, 32 key columns per thread
 constexpr int ATT_BWD_THREADS = 64 + 32 * ATT_BWD_SM_WARPS + 128;  // producer, MMA issuer, softmax, 4 epilogue warps
+// (setmaxnreg was tried to move registers from the single-thread roles to the softmax threads, whose loop state spills
+// at 80 registers: ptxas fails to allocate any split in which a role shrinks below the launch-time count)
 constexpr int ATT_BWD_PRE_BYTES = ATT_BWD_SM_WARPS * 2 * 3 * 128;  // per softmax warp: 2 buffers x (bias | lse | keep bits) x 32 words
 constexpr int ATT_BWD_SMEM = 12 * ATT_TILE_BYTES + 2048 + 2048 + 256 + 4 * 2048 + ATT_BWD_PRE_BYTES + 1024;  // tiles | per-warp bias | delta quarters | barriers | epilogue transposition tiles | prefetch slots
 
@@ -541,6 +543,7 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
         // tensor core (with the fixed order dV(i), S / dP(i+1) the softmax threads spent a third of their time in the
         // sdp_full wait).  The probes are non-blocking: P of this item must not wait for a late load either.
         bool sdp_issued = item + static_cast<int>(gridDim.x) >= n_items;
+        bool dv_issued = false;
         for (;;) {
           if (!sdp_issued) {
             const int s1 = (it + 1) & 1;
@@ -551,17 +554,17 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
               sdp_issued = true;
             }
           }
-          if (mbar_test_wait(p_full, ph)) break;
-        }
-        mbar_wait(out_empty, ph ^ 1);
-        tc_fence_after();
+          if (!dv_issued && mbar_test_wait(p_full, ph) && mbar_test_wait(out_empty, ph ^ 1)) {
+            tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < ATT_T / 16; ++k)  // dV[kv,d] = sum_q P[q,kv] dO[q,d]
-          tc_mma_f16(tmem + 256, make_smem_desc(pa + k * 2048, ATT_TILE_BYTES, 1024),
-                     make_smem_desc(da + k * 2048, 8192, 1024), idesc_tt, k > 0);
-        tc_commit(dv_done);
-        if (!sdp_issued) issue_sdp(it + 1);
-        mbar_wait(ds_full, ph);
+            for (int k = 0; k < ATT_T / 16; ++k)  // dV[kv,d] = sum_q P[q,kv] dO[q,d]
+              tc_mma_f16(tmem + 256, make_smem_desc(pa + k * 2048, ATT_TILE_BYTES, 1024),
+                         make_smem_desc(da + k * 2048, 8192, 1024), idesc_tt, k > 0);
+            tc_commit(dv_done);
+            dv_issued = true;
+          }
+          if (dv_issued && mbar_test_wait(ds_full, ph)) break;
+        }
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < ATT_T / 16; ++k)  // dK[kv,d] = sum_q dS[q,kv] Q[q,d]
@@ -573,6 +576,7 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
                      make_smem_desc(ka + k * 2048, 8192, 1024), idesc_nt, k > 0);
         tc_commit(out_full);
         tc_commit(&stage_empty[s]);  // Q K V dO of this stage (and P / dS) are consumed
+        if (!sdp_issued) issue_sdp(it + 1);  // still pending (late loads): now it is the only thing left to do
       }
     }
   } else if (warp < 2 + ATT_BWD_SM_WARPS) {
@@ -619,8 +623,13 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
       tc_fence_after();
       // ---- S and dP of this thread's 32 columns: both loads in flight together, kept in registers to the end
       uint32_t sv[32], dv[32];
-      tmem_ld_32x32(trow + c0, sv);
-      tmem_ld_32x32(trow + 128 + c0, dv);
+      {
+        // (the TMEM address is re-derived from shared memory per item: kept in a register across the item it was
+        // spilled to local memory, and with ~10 KB of L1 next to 217 KB of shared memory the reload went to L2)
+        const uint32_t ta = *reinterpret_cast<volatile uint32_t*>(tmem_ptr) + (static_cast<uint32_t>(quad * 32) << 16) + c0;
+        tmem_ld_32x32(ta, sv);
+        tmem_ld_32x32(ta + 128, dv);
+      }
       tc_wait_ld();
       tc_fence_before();
       __syncwarp();

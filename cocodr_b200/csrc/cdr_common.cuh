@@ -108,6 +108,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Warpgroup register reallocation (sm_90+): all four warps of a warpgroup give registers back to / take registers from
+// the CTA's pool.  Roles that run on one thread (TMA producer, MMA issuer) shrink, the register-hungry role grows.
+template <int N>
+__device__ __forceinline__ void reg_dealloc() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void reg_alloc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
 // non-blocking probe (try_wait may suspend the thread for a while; a thread that polls SEVERAL barriers must not)
 __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;

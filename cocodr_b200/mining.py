@@ -25,27 +25,94 @@ def _p(t):
     return C.c_void_p(0 if t is None else t.data_ptr())
 
 
+def plan_buckets(sorted_lens, token_budget=16384, max_seqs=1024, multiple=16, max_len=None):
+    """Split sequences SORTED BY LENGTH (ascending) into consecutive groups that are each run at their own padded
+    length: group = [a, b) with L = round_up(longest, multiple) and (b - a) * L <= token_budget.  Returns
+    [(a, b, L)].  Pure host logic (tests/test_host_cpu.py)."""
+    n = len(sorted_lens)
+    out, a = [], 0
+    while a < n:
+        b = a
+        while b < n:
+            L = -(-max(int(sorted_lens[b]), 1) // multiple) * multiple
+            if max_len is not None:
+                L = min(L, max_len)
+            if b > a and ((b - a + 1) * L > token_budget or b - a + 1 > max_seqs):
+                break
+            b += 1
+        L = -(-max(int(sorted_lens[b - 1]), 1) // multiple) * multiple
+        if max_len is not None:
+            L = min(L, max_len)
+        out.append((a, b, L))
+        a = b
+    return out
+
+
 @torch.no_grad()
-def encode(model, batches, is_query=True, out_dtype=torch.float16):
+def encode(model, batches, is_query=True, out_dtype=torch.float16, trim=True, pool=16, token_budget=16384):
     """``batches`` yields the reference's inference tuples ``(input_ids, attention_mask, token_type_ids, idx)`` (or
-    ``(input_ids, attention_mask, idx)``); returns ``(emb [N, H] out_dtype, ids int64 [N])`` on the model's device.
-    Host tensors are copied asynchronously; nothing is copied back."""
+    ``(input_ids, attention_mask, idx)``); returns ``(emb [N, H] out_dtype, ids int64 [N])`` on the model's device, rows
+    in the order the batches delivered them.  Host tensors are copied asynchronously; nothing is copied back.
+
+    ``trim`` (SURVEY 8d mode B, MS-MARCO-shaped lengths): the reference pads every sequence to max_seq_length
+    (evaluate/data/msmarco_data.py GetProcessingFn) and runs the encoder on the padding (queries average 8 of 64
+    positions, passages 75 of 128).  Padded positions never reach a [CLS] embedding -- keys are masked, every other
+    operator is row-wise -- so ``pool`` batches at a time are sorted by real length on the device and re-batched into
+    groups of similar length, each run at its own padded length (a multiple of 16) with ~``token_budget`` tokens per
+    encoder pass (the GEMMs keep their full-wave shapes).  One host synchronisation per pool (the group boundaries);
+    the embeddings are the same as the padded run's.  Masks that are not right-padded fall back to the padded run."""
     mod = model.module if hasattr(model, "module") else model
     dev = next(mod.parameters()).device
     was_training = mod.training
     mod.eval()
+    fwd = mod.query_emb if is_query else mod.body_emb
     embs, ids = [], []
+
+    def to_out(e):
+        if out_dtype == torch.float16:
+            h = torch.empty(e.shape, dtype=torch.float16, device=dev)
+            K.cast_f32_f16(e.contiguous(), h)
+            return h
+        return e.to(out_dtype)
+
+    def flush(pending):
+        if not pending:
+            return
+        Lmax = max(t.shape[1] for t, _ in pending)
+        if any(t.shape[1] != Lmax for t, _ in pending):  # ragged pools: pad to the widest batch
+            pending = [(torch.nn.functional.pad(t, (0, Lmax - t.shape[1])), torch.nn.functional.pad(m, (0, Lmax - m.shape[1])))
+                       for t, m in pending]
+        inp = torch.cat([t for t, _ in pending], 0)
+        mask = torch.cat([m for _, m in pending], 0)
+        lens = mask.sum(1)
+        prefix_ok = (mask[:, :-1] >= mask[:, 1:]).all() if Lmax > 1 else torch.ones((), dtype=torch.bool, device=dev)
+        slen, order = torch.sort(lens)
+        host = torch.cat([slen, prefix_ok.reshape(1).long()]).cpu()  # the pool's ONE host synchronisation
+        if not bool(host[-1]):
+            for t, m in pending:
+                embs.append(to_out(fwd(input_ids=t, attention_mask=m)))
+            return
+        out = torch.empty(inp.shape[0], mod.config.hidden_size, dtype=out_dtype, device=dev)
+        for a, b, L in plan_buckets(host[:-1].tolist(), token_budget=token_budget, max_len=Lmax):
+            sel = order[a:b]
+            e = fwd(input_ids=inp[sel, :L].contiguous(), attention_mask=mask[sel, :L].contiguous())
+            out[sel] = to_out(e)
+        embs.append(out)
+
+    pending = []
     for batch in batches:
         inp, mask, idx = batch[0], batch[1], batch[-1]
         inp = inp.to(dev, non_blocking=True).long()
         mask = mask.to(dev, non_blocking=True).long()
-        e = mod.query_emb(input_ids=inp, attention_mask=mask) if is_query else mod.body_emb(input_ids=inp, attention_mask=mask)
-        if out_dtype == torch.float16:
-            h = torch.empty(e.shape, dtype=torch.float16, device=dev)
-            K.cast_f32_f16(e.contiguous(), h)
-            e = h
-        embs.append(e)
         ids.append(idx.to(dev, non_blocking=True).long().reshape(-1))
+        if not trim:
+            embs.append(to_out(fwd(input_ids=inp, attention_mask=mask)))
+            continue
+        pending.append((inp, mask))
+        if len(pending) >= pool:
+            flush(pending)
+            pending = []
+    flush(pending)
     mod.train(was_training)
     return torch.cat(embs, 0), torch.cat(ids, 0)
 

@@ -133,3 +133,20 @@ def test_bench_reference_arm_contract():
     assert abs(bench.fwd_flops_per_seq() / 1e9 - 22.347) < 0.01  # SURVEY.md §8d / BASELINE.md §3
     p = bench.measured_peaks()
     assert p["tensor"] > 1000 and p["hbm"] > 5000
+
+
+def test_plan_buckets_covers_all_sequences_within_the_token_budget():
+    """mining.plan_buckets (length-bucketed inference, SURVEY 8d mode B): consecutive groups over the sorted lengths,
+    padded length = longest of the group rounded up to 16, tokens per group within the budget."""
+    import random
+    from cocodr_b200.mining import plan_buckets
+    rng = random.Random(0)
+    for n, lo, hi, budget in ((0, 1, 1, 1024), (1, 5, 5, 1024), (2048, 16, 128, 16384), (2048, 4, 16, 16384), (300, 1, 512, 4096)):
+        lens = sorted(rng.randint(lo, hi) for _ in range(n))
+        plan = plan_buckets(lens, token_budget=budget, max_len=hi)
+        assert [a for a, _, _ in plan] == [0] * (n > 0) + [b for _, b, _ in plan][:-1]  # consecutive, starts at 0
+        assert (plan[-1][1] if plan else 0) == n
+        for a, b, L in plan:
+            assert b > a and L % 16 == 0 or L == hi
+            assert L >= lens[b - 1] and (L - lens[b - 1] < 16 or L == hi)
+            assert (b - a) * L <= budget or b - a == 1

@@ -116,3 +116,36 @@ def test_encode_inference_loop_matches_oracle_embeddings():
     q_emb, _ = mining.encode(m, batches[:1], is_query=True)  # 3-tuples / device tensors are accepted as well
     q2, _ = mining.encode(m, [(batches[0][0].cuda(), batches[0][1].cuda(), batches[0][3])], is_query=True)
     assert torch.equal(q_emb, q2)
+
+
+def test_encode_trimmed_equals_padded_run():
+    """SURVEY 8d mode B: re-batching by real length (mining.encode trim=True) must not change an embedding -- padded
+    positions reach a [CLS] row only as masked keys.  Several groups per pool (small token budget), fp32 outputs
+    compared with the padded run of the same sequences; a mask that is not right-padded falls back to the padded run."""
+    from cocodr_b200 import mining
+    from oracle import bert_ref
+    import test_model_gpu as T
+    m = T.build(T.TINY).eval()
+    cfg = T.TINY
+    g = torch.Generator().manual_seed(5)
+    batches = []
+    for b in range(4):
+        n, L = 24, 64
+        lens = torch.randint(1, L + 1, (n,), generator=g)
+        lens[0] = L
+        ids = torch.randint(1000, cfg["vocab"], (n, L), generator=g, dtype=torch.int32)
+        mask = torch.arange(L)[None, :] < lens[:, None]
+        ids = ids * mask
+        ids[:, 0] = 101
+        batches.append((ids.cuda(), mask.cuda(), torch.arange(b * n, (b + 1) * n)))
+    pad, ids_pad = mining.encode(m, batches, is_query=False, out_dtype=torch.float32, trim=False)
+    for budget in (16384, 512, 64):  # one group, several groups, one sequence per group
+        tr, ids_tr = mining.encode(m, batches, is_query=False, out_dtype=torch.float32, trim=True, token_budget=budget)
+        assert torch.equal(ids_tr, ids_pad)
+        err = (tr - pad).abs().max().item() / pad.abs().max().item()
+        assert err < 2e-3, (budget, err)  # (different GEMM tile shapes: summation order, not values)
+    holes = [(i, mk.clone(), idx) for i, mk, idx in batches]
+    holes[1][1][3, 1] = False  # a hole in the mask: not a right-padded batch
+    a, _ = mining.encode(m, holes, is_query=False, out_dtype=torch.float32, trim=True)
+    b_, _ = mining.encode(m, holes, is_query=False, out_dtype=torch.float32, trim=False)
+    assert torch.equal(a, b_)
