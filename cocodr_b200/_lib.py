@@ -30,7 +30,7 @@ class AttnArgs(C.Structure):
                 ("d_out", C.c_void_p), ("dqkv", C.c_void_p), ("dq_workspace", C.c_void_p),
                 ("n_seq", C.c_int32), ("seq_len", C.c_int32), ("heads", C.c_int32), ("head_dim", C.c_int32),
                 ("scale", C.c_float), ("dbias_scale", C.c_float), ("dbias_qkv", C.c_void_p), ("drop", Dropout),
-                ("drop_bits", C.c_void_p)]
+                ("drop_bits", C.c_void_p), ("drop_bits_ready", C.c_int32), ("reserved", C.c_int32)]
 
 
 class SimmatArgs(C.Structure):

@@ -158,6 +158,8 @@ class BertModel(_HFBertModel):
         e = self.embeddings
         self._shadow_set.refresh([shadow_sources(layer) for layer in self.encoder.layer])
         drop = self.dropout_spec(self.training, input_ids.device)
+        drop = ops.prefill_attn_bits(drop, len(self.encoder.layer), n_seq, self.config.num_attention_heads, L,
+                                     input_ids.device)
         x = ops.EmbedLN.apply(input_ids.long(), e.word_embeddings.weight, e.position_embeddings.weight,
                               e.token_type_embeddings.weight, e.LayerNorm.weight, e.LayerNorm.bias,
                               float(self.config.layer_norm_eps), drop)

@@ -1226,6 +1226,18 @@ att_keep_bits_kernel(uint8_t* __restrict__ bits, long long n_rows, int groups_pe
 
 static int att_bits_stride(int seq_len) { return ((seq_len + 7) / 8 + 15) / 16 * 16; }
 
+static int att_fill_bits(const cdr_attn_args* a, void* stream) {
+  const int stride = att_bits_stride(a->seq_len);
+  const long long n_rows = static_cast<long long>(a->n_seq) * a->heads * a->seq_len;
+  const int gpr = (a->seq_len + 7) / 8;
+  long long blocks = (n_rows * (stride / 4) + 255) / 256;
+  if (blocks > 32LL * sm_count()) blocks = 32LL * sm_count();
+  att_keep_bits_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<uint8_t*>(a->drop_bits), n_rows, gpr, stride, a->drop);
+  CDR_LAUNCH_CHECK();
+  return CDR_OK;
+}
+
 static int att_check(const cdr_attn_args* a) {
   CDR_REQUIRE(a != nullptr, "cdr_attn: null args");
   if (a->drop.state != nullptr && a->drop.threshold > 0) {
@@ -1271,13 +1283,9 @@ int cdr_attn_fwd(const cdr_attn_args* a, void* stream) {
   if (drop) {  // pre-pass: one keep bit per attention probability (read again by cdr_attn_bwd)
     p.keep_bits = static_cast<const uint8_t*>(a->drop_bits);
     p.bits_stride = att_bits_stride(a->seq_len);
-    const long long n_rows = static_cast<long long>(a->n_seq) * a->heads * a->seq_len;
-    const int gpr = (a->seq_len + 7) / 8;
-    long long blocks = (n_rows * (p.bits_stride / 4) + 255) / 256;
-    if (blocks > 32LL * sm_count()) blocks = 32LL * sm_count();
-    att_keep_bits_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<uint8_t*>(a->drop_bits), n_rows, gpr, p.bits_stride, a->drop);
-    CDR_LAUNCH_CHECK();
+    if (!a->drop_bits_ready) {
+      if (int rc = att_fill_bits(a, stream)) return rc;
+    }
   }
   static bool configured = false;
   if (!configured) {
@@ -1299,6 +1307,17 @@ int cdr_attn_fwd(const cdr_attn_args* a, void* stream) {
   CDR_CUDA(launch_pdl(drop ? fmha_fwd_kernel<true> : fmha_fwd_kernel<false>, dim3(grid), dim3(ATT_FWD_THREADS),
                       ATT_FWD_SMEM, static_cast<cudaStream_t>(stream), tq, p, n_items));
   return CDR_OK;
+}
+
+int cdr_attn_dropout_bits_fill(const cdr_attn_args* a, void* stream) {
+  CDR_REQUIRE(a != nullptr, "cdr_attn_dropout_bits_fill: null args");
+  CDR_REQUIRE(drop_on(a->drop) && a->drop.threshold < 65536, "cdr_attn_dropout_bits_fill: no dropout configured");
+  CDR_REQUIRE(a->drop_bits != nullptr && (reinterpret_cast<uintptr_t>(a->drop_bits) & 15) == 0,
+              "cdr_attn_dropout_bits_fill: drop_bits must be 16-byte aligned");
+  CDR_REQUIRE(a->n_seq > 0 && a->seq_len > 0 && a->heads > 0, "cdr_attn_dropout_bits_fill: empty problem");
+  CDR_REQUIRE(static_cast<long long>(a->n_seq) * a->heads * a->seq_len * 64 < (1ll << 32),
+              "cdr_attn_dropout_bits_fill: dropout group index overflows 32 bits");
+  return att_fill_bits(a, stream);
 }
 
 int cdr_attn_bwd(const cdr_attn_args* a, void* stream) {

@@ -276,8 +276,19 @@ def attn_dropout_bits(n_seq, heads, seq_len, device):
     return torch.empty(n, dtype=torch.uint8, device=device)
 
 
-def attn_fwd(qkv, key_bias, out, lse, *, n_seq, seq_len, heads, scale=0.125, drop=None, drop_bits=None):
-    """drop (a drop_args descriptor) needs drop_bits = attn_dropout_bits(...): fwd fills it, bwd reads it."""
+def attn_fill_bits(drop_bits, *, n_seq, seq_len, heads, drop):
+    """The generator pass of attn_fwd on its own (current stream): afterwards attn_fwd(..., bits_ready=True)."""
+    assert drop_bits.is_cuda and drop_bits.dtype == torch.uint8 and drop is not None
+    a = _lib.AttnArgs()
+    a.n_seq, a.seq_len, a.heads, a.head_dim = n_seq, seq_len, heads, 64
+    a.drop, a.drop_bits = drop, drop_bits.data_ptr()
+    _run("cdr_attn_dropout_bits_fill", lambda: _lib_().cdr_attn_dropout_bits_fill(C.byref(a), stream_ptr()))
+    _count(1)
+
+
+def attn_fwd(qkv, key_bias, out, lse, *, n_seq, seq_len, heads, scale=0.125, drop=None, drop_bits=None, bits_ready=False):
+    """drop (a drop_args descriptor) needs drop_bits = attn_dropout_bits(...): fwd fills it (unless bits_ready: filled
+    earlier by attn_fill_bits), bwd reads it."""
     _need_cuda(qkv, out, lse)
     assert qkv.dtype == torch.float16 and out.dtype == torch.float16 and lse.dtype == torch.float32
     assert qkv.is_contiguous() and out.is_contiguous()
@@ -285,8 +296,9 @@ def attn_fwd(qkv, key_bias, out, lse, *, n_seq, seq_len, heads, scale=0.125, dro
     if drop is not None:
         assert drop_bits is not None and drop_bits.is_cuda and drop_bits.dtype == torch.uint8
         a.drop, a.drop_bits = drop, drop_bits.data_ptr()
+        a.drop_bits_ready = 1 if bits_ready else 0
     _run("cdr_attn_fwd", lambda: _lib_().cdr_attn_fwd(C.byref(a), stream_ptr()))
-    _count(1 if drop is None else 2)
+    _count(1 if drop is None or bits_ready else 2)
 
 
 def attn_bwd(qkv, key_bias, out, lse, d_out, dqkv, *, n_seq, seq_len, heads, scale=0.125, dbias=None, dbias_scale=1.0,

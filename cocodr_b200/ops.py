@@ -75,7 +75,43 @@ def _submit(ctx, flat):
 # backward regenerates the forward's masks whatever ran in between), p_hidden / p_attn = HF's hidden_dropout_prob /
 # attention_probs_dropout_prob.  Sites: 0 embeddings; layer l: 4l + 1 attention probabilities, 4l + 2 attention-output
 # dense, 4l + 3 FFN-output dense (include/cocodr_b200.h cdr_dropout; oracle/dropout_ref.py regenerates the same masks).
-DropSpec = namedtuple("DropSpec", "state p_hidden p_attn")
+DropSpec = namedtuple("DropSpec", "state p_hidden p_attn attn_bits", defaults=(None,))
+# attn_bits: optional {layer_index: (keep-bit buffer, event)} -- the attention keep bits of those layers are being
+# generated on a second stream (prefill_attn_bits); the layer waits for the event instead of running the generator.
+
+# Generating the keep bits of the attention dropout is 3 M Philox calls per layer (19 us) that depend on nothing but the
+# dropout state: the encoder enqueues them for ALL its layers on a second stream at the start of the pass, where they
+# share the SMs with the tensor-core GEMMs (whose fp32 / integer pipes are mostly idle) instead of standing between the
+# QKV projection and the attention kernel of every layer.  CDR_ATTN_BITS_PREFILL=0 keeps the generator in cdr_attn_fwd.
+ATTN_BITS_PREFILL = _os.environ.get("CDR_ATTN_BITS_PREFILL", "1") != "0"
+_BITS_STREAMS = {}
+
+
+def prefill_attn_bits(drop, n_layers, n_seq, heads, L, dev):
+    """-> drop with attn_bits for layers 0 .. n_layers-1 (or drop unchanged when there is nothing to generate)."""
+    if drop is None or drop.p_attn <= 0.0 or not ATTN_BITS_PREFILL or L > 128:
+        return drop
+    st = _BITS_STREAMS.get(dev)
+    if st is None:
+        st = _BITS_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    one = K.attn_dropout_bits(n_seq, heads, L, dev).numel()
+    buf = torch.empty(n_layers, one, dtype=torch.uint8, device=dev)  # (allocated on the caller's stream)
+    st.wait_event(torch.cuda.current_stream().record_event())       # the dropout-state snapshot exists
+    table = {}
+    with torch.cuda.stream(st):
+        for i in range(n_layers):
+            K.attn_fill_bits(buf[i], n_seq=n_seq, seq_len=L, heads=heads, drop=_site(drop, i, 1))
+            table[i] = (buf[i], st.record_event())
+    return drop._replace(attn_bits=table)
+
+
+def _attn_bits(drop, layer_index, n_seq, heads, L, dev):
+    """(bits, ready) for a layer's attention dropout: the prefilled buffer (after waiting for its event) or a new one."""
+    if drop is not None and drop.attn_bits is not None and layer_index in drop.attn_bits:
+        bits, ev = drop.attn_bits[layer_index]
+        torch.cuda.current_stream().wait_event(ev)
+        return bits, True
+    return K.attn_dropout_bits(n_seq, heads, L, dev), False
 
 
 def _site(drop, layer_index, which, row_mul=1):
@@ -309,8 +345,9 @@ class BertLayerFn(torch.autograd.Function):
         K.gemm(x, sh.wqkv, qkv, M=T, N=3 * H, K=H, bias=sh.bqkv)
         att = _f16(T, H, dev=dev)
         lse = _f32(n_seq, heads, L, dev=dev)
-        bits = K.attn_dropout_bits(n_seq, heads, L, dev) if da is not None else None
-        K.attn_fwd(qkv, key_bias, att, lse, n_seq=n_seq, seq_len=L, heads=heads, drop=da, drop_bits=bits)
+        bits, bits_ready = _attn_bits(drop, layer_index, n_seq, heads, L, dev) if da is not None else (None, False)
+        K.attn_fwd(qkv, key_bias, att, lse, n_seq=n_seq, seq_len=L, heads=heads, drop=da, drop_bits=bits,
+                   bits_ready=bits_ready)
         y1 = _f16(T, H, dev=dev)  # x + dropout(attn_out), pre-LayerNorm
         K.gemm(att, sh.wo, y1, M=T, N=H, K=H, bias=bo, aux=x, drop=db,
                epilogue=K.EPI_BIAS_RESIDUAL if db is None else K.EPI_BIAS_DROP_RESIDUAL)
@@ -432,8 +469,9 @@ class BertLastLayerCLSFn(torch.autograd.Function):
         K.gemm(x, sh.wqkv, qkv, M=T, N=3 * H, K=H, bias=sh.bqkv)
         att = _f16(T, H, dev=dev)
         lse = _f32(n_seq, heads, L, dev=dev)
-        bits = K.attn_dropout_bits(n_seq, heads, L, dev) if da is not None else None
-        K.attn_fwd(qkv, key_bias, att, lse, n_seq=n_seq, seq_len=L, heads=heads, drop=da, drop_bits=bits)
+        bits, bits_ready = _attn_bits(drop, layer_index, n_seq, heads, L, dev) if da is not None else (None, False)
+        K.attn_fwd(qkv, key_bias, att, lse, n_seq=n_seq, seq_len=L, heads=heads, drop=da, drop_bits=bits,
+                   bits_ready=bits_ready)
         xc, attc = x.view(n_seq, L, H)[:, 0], att.view(n_seq, L, H)[:, 0]  # [n_seq, H] views, row stride L * H
         y1 = _f16(n_seq, H, dev=dev)
         K.gemm(attc, sh.wo, y1, M=n_seq, N=H, K=H, bias=bo, aux=xc, drop=db,

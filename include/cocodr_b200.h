@@ -273,8 +273,14 @@ typedef struct cdr_attn_args {
   void* drop_bits;       /* with dropout: cdr_attn_dropout_bits_bytes() bytes, 16-byte aligned.  cdr_attn_fwd FILLS it (one
                             keep bit per probability, from the Philox counters of `drop`) and reads it; cdr_attn_bwd reads
                             the same buffer -- the softmax threads never run the generator themselves */
+  int32_t drop_bits_ready; /* fwd: nonzero = drop_bits was already filled by cdr_attn_dropout_bits_fill (e.g. on another
+                              stream, overlapped with the preceding GEMMs); cdr_attn_fwd then only reads it */
+  int32_t reserved;
 } cdr_attn_args;
 size_t cdr_attn_dropout_bits_bytes(int32_t n_seq, int32_t heads, int32_t seq_len);
+/* Fills args->drop_bits from args->drop for (n_seq, heads, seq_len): the generator pass of cdr_attn_fwd on its own.  It
+ * depends on nothing but the dropout state, so a caller may run it ahead of time on a second stream. */
+int cdr_attn_dropout_bits_fill(const cdr_attn_args* args, void* stream);
 int cdr_attn_fwd(const cdr_attn_args* args, void* stream);
 int cdr_attn_bwd(const cdr_attn_args* args, void* stream);
 
