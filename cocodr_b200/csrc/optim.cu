@@ -8,6 +8,7 @@
 //   Lamb (cdr_lamb_multi): ANCE/utils/lamb.py:71-121 -- no bias correction, adam_step = m / (sqrt(v) + eps) + wd p,
 //                         trust = clamp(|p|, 0, 10) / |adam_step| (1 if either norm is 0), p -= lr trust adam_step
 #include "cdr_common.cuh"
+#include "peer.cuh"
 
 namespace cdr {
 
@@ -93,6 +94,133 @@ adam_multi_kernel(const cdr_opt_item* __restrict__ items, const cdr_opt_chunk* _
           else static_cast<__half*>(it.shadow)[j] = __float2half_rn(pk);
         }
       }
+    }
+  }
+}
+
+// ---- AdamW with the data-parallel gradient exchange fused in (cdr_adam_multi_peer, include/cocodr_b200.h)
+__global__ void opt_step_epoch_inc_kernel(float* step, uint32_t* epoch) {
+  step[0] += 1.f;
+  epoch[0] += 1u;
+}
+
+struct PeerOpt {
+  int world, rank;
+  long long delta[8];      // byte offset from a local arena address to rank r's copy
+  uint32_t* peer_flag[8];  // flag words of rank r: [0, 8) set 0, [8, 16) set 1
+  uint32_t* local_flag;
+  const uint32_t* epoch;
+  uint32_t* done;
+  uint32_t* err;
+};
+
+// bounded spin (a peer that never launches must not hang the GPU): false after ~10 s
+__device__ __forceinline__ bool peer_wait_bounded(const uint32_t* flags, int world, uint32_t epoch) {
+  const long long t0 = clock64();
+  for (int r = 0; r < world; ++r)
+    while (static_cast<int>(ld_acquire_sys(flags + r) - epoch) < 0) {
+      if (clock64() - t0 > 20000000000ll) return false;
+    }
+  return true;
+}
+
+template <typename T>
+__device__ __forceinline__ T* peer_ptr(T* p, long long delta) {
+  return reinterpret_cast<T*>(reinterpret_cast<char*>(p) + delta);
+}
+template <typename T>
+__device__ __forceinline__ const T* peer_ptr(const T* p, long long delta) {
+  return reinterpret_cast<const T*>(reinterpret_cast<const char*>(p) + delta);
+}
+
+__global__ void __launch_bounds__(256)
+adam_multi_peer_kernel(const cdr_opt_item* __restrict__ items, const cdr_opt_chunk* __restrict__ chunks, int n_chunks,
+                       OptHyper h, PeerOpt po) {
+  __shared__ int ok;
+  const uint32_t epoch = *reinterpret_cast<const volatile uint32_t*>(po.epoch);
+  if (threadIdx.x == 0) {
+    if (blockIdx.x == 0) {
+      // every gradient of this rank was written by kernels that precede this one on the stream
+      __threadfence_system();
+      for (int r = 0; r < po.world; ++r) st_release_sys(po.peer_flag[r] + po.rank, epoch);
+    }
+    ok = peer_wait_bounded(po.local_flag, po.world, epoch) ? 1 : 0;
+    if (!ok && po.err != nullptr) *po.err = 1u;
+  }
+  __syncthreads();
+  const int c = blockIdx.x * po.world + po.rank;  // chunks are dealt round-robin to the ranks
+  if (ok && c < n_chunks) {
+    const cdr_opt_chunk ck = chunks[c];
+    const cdr_opt_item it = items[ck.item];
+    const long long c_end = ck.start + CDR_OPT_CHUNK < it.n ? ck.start + CDR_OPT_CHUNK : it.n;
+    const float lr = h.lr[0], t = h.step[0];
+    const float gs = (h.grad_scale ? h.grad_scale[0] : 1.f) / static_cast<float>(po.world);  // mean over ranks (DDP)
+    const float bc1 = 1.f - powf(h.beta1, t), bc2 = 1.f - powf(h.beta2, t);
+    const float rsq_bc2 = rsqrtf(bc2);
+    const float step_torch = lr / bc1, step_hf = lr * sqrtf(bc2) / bc1;
+    const float decay = 1.f - lr * h.wd;
+    auto update = [&](float& pk, float& mk, float& vk, float gsum) {
+      const float gk = gsum * gs;
+      mk = h.beta1 * mk + (1.f - h.beta1) * gk;
+      vk = h.beta2 * vk + (1.f - h.beta2) * gk * gk;
+      if (h.mode == CDR_OPT_ADAMW_TORCH) {
+        pk = pk * decay - step_torch * mk / (sqrtf(vk) * rsq_bc2 + h.eps);
+      } else {
+        pk = pk - step_hf * mk / (sqrtf(vk) + h.eps);
+        pk = pk - lr * h.wd * pk;
+      }
+    };
+    for (long long i = ck.start + threadIdx.x * 4; i < c_end; i += 256 * 4) {
+      if (i + 4 <= c_end && !it.reserved) {
+        float p[4], m[4], v[4], g[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int r = 0; r < po.world; ++r) {  // fixed order: every rank would form the same sum
+          float gr[4];
+          ld4(peer_ptr(it.g, po.delta[r]) + i, gr);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) g[k] += gr[k];
+        }
+        ld4(it.p + i, p); ld4(it.m + i, m); ld4(it.v + i, v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) update(p[k], m[k], v[k], g[k]);
+        st4(it.m + i, m); st4(it.v + i, v);
+        for (int r = 0; r < po.world; ++r) {
+          st4(peer_ptr(it.p, po.delta[r]) + i, p);
+          if (it.shadow != nullptr) {
+            cdr_opt_item pit = it;
+            pit.shadow = peer_ptr(static_cast<char*>(it.shadow), po.delta[r]);
+            st_shadow4(pit, i, p);
+          }
+        }
+      } else {
+        for (long long j = i; j < c_end && j < i + 4; ++j) {
+          float gsum = 0.f;
+          for (int r = 0; r < po.world; ++r) gsum += peer_ptr(it.g, po.delta[r])[j];
+          float pk = it.p[j], mk = it.m[j], vk = it.v[j];
+          update(pk, mk, vk, gsum);
+          it.m[j] = mk; it.v[j] = vk;
+          for (int r = 0; r < po.world; ++r) {
+            peer_ptr(it.p, po.delta[r])[j] = pk;
+            if (it.shadow != nullptr) {
+              if (it.shadow_f32) peer_ptr(static_cast<float*>(it.shadow), po.delta[r])[j] = pk;
+              else peer_ptr(static_cast<__half*>(it.shadow), po.delta[r])[j] = __float2half_rn(pk);
+            }
+          }
+        }
+      }
+    }
+  }
+  // ---- the last block of the grid tells every peer that this rank's updates have landed (and that it has read all the
+  // gradients it needs), then holds the kernel until every peer said the same: afterwards parameters and shadows
+  // are complete on this rank and its gradient buffers may be overwritten
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(po.done, 1u);
+    if (prev == gridDim.x - 1) {
+      __threadfence_system();
+      for (int r = 0; r < po.world; ++r) st_release_sys(po.peer_flag[r] + 8 + po.rank, epoch);
+      *po.done = 0u;
+      if (!peer_wait_bounded(po.local_flag + 8, po.world, epoch) && po.err != nullptr) *po.err = 1u;
     }
   }
 }
@@ -206,6 +334,32 @@ int cdr_adam_multi(const cdr_opt_args* a, void* stream) {
   CDR_LAUNCH_CHECK();
   OptHyper h{a->beta1, a->beta2, a->eps, a->weight_decay, a->lr, a->step, a->grad_scale, a->mode};
   adam_multi_kernel<<<a->n_chunks, 256, 0, st>>>(a->items, a->chunks, h);
+  CDR_LAUNCH_CHECK();
+  return CDR_OK;
+}
+
+int cdr_adam_multi_peer(const cdr_opt_args* a, const cdr_peer_args* pa, uint32_t* epoch_rw, uint32_t* err, void* stream) {
+  if (int rc = opt_check(a, "cdr_adam_multi_peer")) return rc;
+  if (int rc = peer_check(pa, "cdr_adam_multi_peer")) return rc;
+  CDR_REQUIRE(a->mode == CDR_OPT_ADAMW_TORCH || a->mode == CDR_OPT_ADAMW_HF, "cdr_adam_multi_peer: unknown mode %d", a->mode);
+  CDR_REQUIRE(epoch_rw != nullptr && epoch_rw == pa->epoch, "cdr_adam_multi_peer: epoch_rw must be peers->epoch (it is incremented)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  opt_step_epoch_inc_kernel<<<1, 1, 0, st>>>(a->step, epoch_rw);
+  CDR_LAUNCH_CHECK();
+  OptHyper h{a->beta1, a->beta2, a->eps, a->weight_decay, a->lr, a->step, a->grad_scale, a->mode};
+  PeerOpt po{};
+  po.world = pa->world;
+  po.rank = pa->rank;
+  for (int r = 0; r < pa->world; ++r) {
+    po.delta[r] = static_cast<long long>(reinterpret_cast<intptr_t>(pa->peer_buf[r]) - reinterpret_cast<intptr_t>(pa->peer_buf[pa->rank]));
+    po.peer_flag[r] = pa->peer_flag[r];
+  }
+  po.local_flag = pa->peer_flag[pa->rank];
+  po.epoch = pa->epoch;
+  po.done = pa->done_counter;
+  po.err = err;
+  const int blocks = (a->n_chunks + pa->world - 1) / pa->world;
+  adam_multi_peer_kernel<<<blocks, 256, 0, st>>>(a->items, a->chunks, a->n_chunks, h, po);
   CDR_LAUNCH_CHECK();
   return CDR_OK;
 }

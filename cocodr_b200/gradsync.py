@@ -28,9 +28,16 @@ import torch.distributed as dist
 from . import ops
 
 
+import os as _os
+_SKIP = _os.environ.get("CDR_GRADSYNC_SKIP", "0") != "0"
+_AT_END = _os.environ.get("CDR_GRADSYNC_AT_END", "0") != "0"
+
+
 class GradSync:
-    def __init__(self, model, group=None):
-        self.model, self.group = model, group
+    def __init__(self, model, group=None, arena=None):
+        """arena: a peeropt.PeerArena -- gradients the backward writes into it are NOT reduced here (the optimizer's
+        cdr_adam_multi_peer reads every rank's copy over NVLink); everything else still goes through NCCL."""
+        self.model, self.group, self.arena = model, group, arena
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.comm = torch.cuda.Stream() if self.world > 1 and torch.cuda.is_available() else None
         # NCCL averages in the collective itself (ncclAvg); other backends (gloo in the CPU tests) sum, then scale
@@ -41,6 +48,8 @@ class GradSync:
         self.stats = {"overlapped": 0, "deferred": 0}
 
     def _reduce(self, t):
+        if _SKIP:  # timing experiment only (tools / bench A-B): gradients stay local
+            return
         dist.all_reduce(t, op=self._avg, group=self.group)  # averaged inside NCCL: no extra pass over the buffer
         if self._avg is dist.ReduceOp.SUM:
             t.mul_(1.0 / self.world)
@@ -51,7 +60,12 @@ class GradSync:
         parameters; fwd_calls: how many times the Function ran on them in the current forward (ops.FWD_CALLS)."""
         if self.world == 1:
             return
+        if self.arena is not None and self.arena.contains(flat):
+            self.stats["peer"] = self.stats.get("peer", 0) + 1
+            return
         safe = params is not None and fwd_calls == 1 and all(p.grad is None and id(p) not in self._deferred for p in params)
+        if _AT_END:  # experiment: no overlap with backward, everything reduced in __exit__
+            safe = False
         if not safe:
             # autograd will ADD this buffer's views to existing gradients (or other buffers' views to these): the
             # parameters' final .grad is reduced once backward is over
@@ -89,6 +103,15 @@ class GradSync:
         rest = []
         for p in self.model.parameters():
             if p.grad is None:
+                continue
+            if self.arena is not None and self.arena.contains(p):
+                # exchanged inside the optimizer kernel, which reads the gradient of every rank from the arena: a
+                # gradient autograd accumulated elsewhere (unfused towers, accumulation steps) is moved in first
+                if not self.arena.contains(p.grad):
+                    slot = self.arena.grad_slot(p)
+                    slot.copy_(p.grad)
+                    p.grad = slot
+                    self.stats["peer_copied"] = self.stats.get("peer_copied", 0) + 1
                 continue
             a = p.grad.data_ptr()
             if id(p) in self._deferred or not any(lo <= a < hi for lo, hi in covered):

@@ -66,6 +66,18 @@ def _note_forward(ctx, params):
     return params
 
 
+def _grad_flat(ctx, n, dev):
+    """Zeroed fp32 [n] buffer the parameter gradients of one Function backward are views of.  Inside a GradSync that
+    owns a peer arena (peeropt.PeerArena) it is the Function's persistent slice of the symmetric arena -- provided
+    autograd will ADOPT the views as .grad (single forward call, no gradient yet); the optimizer then reads every
+    rank's copy over NVLink instead of a collective."""
+    gs = GRAD_SYNC
+    arena = getattr(gs, "arena", None) if gs is not None else None
+    if arena is not None and FWD_CALLS.get(id(ctx.params[0]), 1) == 1 and all(p.grad is None for p in ctx.params):
+        return arena.flat(ctx.params[0], n, dev)
+    return torch.zeros(n, dtype=torch.float32, device=dev)
+
+
 def _submit(ctx, flat):
     if GRAD_SYNC is not None:
         GRAD_SYNC.submit(flat, ctx.params, FWD_CALLS.get(id(ctx.params[0]), 1))
@@ -167,6 +179,9 @@ def get_grad_scale() -> float:
     return _GRAD_SCALE
 
 
+SHADOW_ALLOC = None  # peeropt.PeerArena: operand shadows are allocated from the symmetric arena while this is set
+
+
 def _f16(*shape, dev):
     return torch.empty(*shape, dtype=torch.float16, device=dev)
 
@@ -198,8 +213,14 @@ class LayerShadow:
         dev = wq.device
         H, I = wq.shape[0], wi.shape[0]
         if self.key is None or self.wqkv.device != dev or self.wqkv.shape != (3 * H, H):
-            self.wqkv, self.bqkv = _f16(3 * H, H, dev=dev), _f32(3 * H, dev=dev)
-            self.wo, self.wi, self.wo2 = _f16(H, H, dev=dev), _f16(I, H, dev=dev), _f16(H, I, dev=dev)
+            if SHADOW_ALLOC is not None:
+                f16 = lambda *sh: SHADOW_ALLOC(sh, torch.float16)  # noqa: E731
+                f32 = lambda *sh: SHADOW_ALLOC(sh, torch.float32)  # noqa: E731
+            else:
+                f16 = lambda *sh: _f16(*sh, dev=dev)  # noqa: E731
+                f32 = lambda *sh: _f32(*sh, dev=dev)  # noqa: E731
+            self.wqkv, self.bqkv = f16(3 * H, H), f32(3 * H)
+            self.wo, self.wi, self.wo2 = f16(H, H), f16(I, H), f16(H, I)
             return True
         return False
 
@@ -308,7 +329,7 @@ class EmbedLN(torch.autograd.Function):
         H = word.shape[1]
         dev = word.device
         sizes = (word.numel(), pos.numel(), typ.numel(), H, H)
-        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        flat = _grad_flat(ctx, sum(sizes), dev)
         views, off = [], 0
         for n in sizes:
             views.append(flat[off:off + n])
@@ -389,7 +410,7 @@ class BertLayerFn(torch.autograd.Function):
             dcls = dcls.contiguous().float()
         # ---- one zero-fill for every parameter-gradient accumulator of the layer (views below)
         sizes = (H, H, H, H * I, I, I * H, H, H, H, H * H, 3 * H * H, 3 * H)
-        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        flat = _grad_flat(ctx, sum(sizes), dev)
         views, off = [], 0
         for n in sizes:
             views.append(flat[off:off + n])
@@ -509,7 +530,7 @@ class BertLastLayerCLSFn(torch.autograd.Function):
         inv = 1.0 / S
         dcls = dcls.contiguous().float()
         sizes = (H, H, H, H * I, I, I * H, H, H, H, H * H, 3 * H * H, 3 * H)
-        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        flat = _grad_flat(ctx, sum(sizes), dev)
         views, off = [], 0
         for n in sizes:
             views.append(flat[off:off + n])

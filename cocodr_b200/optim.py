@@ -52,6 +52,7 @@ class _FusedOptimizer(torch.optim.Optimizer):
         self._tables = {}         # group index -> dict(key, dev table, pinned host table, max_n, params)
         self._clip = None         # device [3]: sum of squares scratch, coefficient, norm
         self._use_clip = False
+        self.peer = None          # a peeropt.PeerArena: AdamW.step exchanges the gradients inside cdr_adam_multi_peer
 
     # ------------------------------------------------------------------------------------------ shadows
     def attach_shadows(self, *models):
@@ -77,8 +78,15 @@ class _FusedOptimizer(torch.optim.Optimizer):
             st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
         return st
 
-    def _table(self, gi, group):
+    def _table(self, gi, group, subset=None):
+        """subset: None (all parameters of the group with a gradient), or 'peer' / 'local' = those whose parameter,
+        gradient and shadow all live in the peer arena / the rest (tables are cached per (group, subset))."""
         params = [p for p in group["params"] if p.grad is not None]
+        if subset is not None:
+            in_arena = lambda p: (self.peer.contains(p) and self.peer.contains(p.grad) and  # noqa: E731
+                                  (id(p) not in self._shadow_of or self.peer.contains(self._shadow_of[id(p)][0])))
+            params = [p for p in params if in_arena(p) == (subset == "peer")]
+            gi = (gi, subset)
         if not params:
             return None
         for p in params:
@@ -139,7 +147,7 @@ class _FusedOptimizer(torch.optim.Optimizer):
             ck["start"] = np.concatenate([np.arange(c, dtype=np.int64) * OPT_CHUNK for c in per])
             tab["chunks"] = torch.from_numpy(ck.view(np.uint8)).to(tab["dev"].device)
             tab["n_chunks"], tab["sizes"] = len(ck), sizes
-        tab["key"], tab["params"] = key, params
+        tab["key"], tab["params"], tab["peer"] = key, params, subset == "peer"
         # one fp32 step counter per group on the device; seeded from the per-parameter state (state_dict round trips)
         # (a reference-format optimizer.pt stores ``step`` as a python int: ANCE/utils/lamb.py:93, transformers AdamW)
         tab["step"].copy_(torch.as_tensor(self.state[params[0]]["step"], dtype=torch.float32, device=tab["step"].device))
@@ -164,9 +172,9 @@ class _FusedOptimizer(torch.optim.Optimizer):
         """Mirror host-side ``group['lr']`` changes (LR schedulers) into the device scalars the kernels read.  step()
         does this itself; a CUDA-graph replay does not run Python, so ``graph.GraphedTrainStep`` calls it before
         every replay."""
-        for gi, group in enumerate(self.param_groups):
-            tab = self._tables.get(gi)
-            if tab is not None and tab["lr_host"] != float(group["lr"]):
+        for key, tab in self._tables.items():
+            group = self.param_groups[key[0] if isinstance(key, tuple) else key]
+            if tab["lr_host"] != float(group["lr"]):
                 tab["lr"].fill_(float(group["lr"]))
                 tab["lr_host"] = float(group["lr"])
 
@@ -224,7 +232,17 @@ class AdamW(_FusedOptimizer):
         loss = closure() if closure is not None else None
         lib = _lib.load()
         for gi, group in enumerate(self.param_groups):
-            tab = self._table(gi, group)
+            if self.peer is not None:
+                if self._use_clip:
+                    raise NotImplementedError("gradient clipping needs the reduced gradients before the update: not "
+                                              "available with the peer-memory optimizer (use GradSync without an arena)")
+                tab = self._table(gi, group, "peer")
+                if tab is not None:
+                    self.peer.adam_step(self._args(tab, group, self.mode))
+                    self._finish(tab)
+                tab = self._table(gi, group, "local")  # gradients outside the arena were all-reduced by GradSync
+            else:
+                tab = self._table(gi, group)
             if tab is None:
                 continue
             a = self._args(tab, group, self.mode)

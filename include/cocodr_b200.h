@@ -244,6 +244,19 @@ typedef struct cdr_opt_args {
 } cdr_opt_args;
 int cdr_adam_multi(const cdr_opt_args* args, void* stream);
 int cdr_lamb_multi(const cdr_opt_args* args, void* stream);
+/* Data-parallel AdamW with the gradient exchange INSIDE the optimizer kernel (replaces DistributedDataParallel's
+ * bucketed all-reduce -- ANCE/drivers/run_ann.py:178-184 -- plus the replicated optimizer step, :345-353).  Every
+ * p / g / shadow of the table lies in a symmetric arena with the same layout on every rank (peers->peer_buf[r] = arena
+ * base of rank r, so rank r's copy of a local address a is a + (peer_buf[r] - peer_buf[rank])).  Rank r owns the chunks
+ * c with c % world == r: it reads that chunk of the gradient from EVERY rank over NVLink, averages, updates its own
+ * exp_avg / exp_avg_sq and writes the new parameter (and shadow) into every rank's arena -- reduce-scatter, optimizer
+ * on 1 / world of the parameters, all-gather, in one pass over peer memory with no collective kernel competing with
+ * the GEMMs of the backward.  Flag set 0 of peers->peer_flag publishes "my gradients are final", set 1 "my updates
+ * have landed everywhere and I have read everything I need"; the call returns (stream-wise) only after all ranks
+ * signalled set 1.  m / v / step of chunks a rank does not own are not touched (cdr_opt_item.m / .v may be stale
+ * there).  err (optional device uint32) is set to 1 if a peer did not arrive within ~10 s. */
+int cdr_adam_multi_peer(const cdr_opt_args* args, const cdr_peer_args* peers, uint32_t* epoch_rw, uint32_t* err,
+                        void* stream);
 /* torch.nn.utils.clip_grad_norm_ in two steps: sq_accum[0] += sum of g^2 over every gradient of a table (call once
  * per parameter group on a zeroed scalar), then coef[0] = min(1, max_norm / (sqrt(sq[0]) + 1e-6)) and, optionally,
  * norm_out[0] = sqrt(sq[0]).  The coefficient is consumed on the device as cdr_opt_args.grad_scale. */

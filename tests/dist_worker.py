@@ -188,6 +188,76 @@ def main():
         assert torch.isfinite(h).all() and abs(h.sum().item() - 1.0) < 0.2, (mode, h)
         assert all(torch.isfinite(p.grad).all() for p in m12.parameters() if p.grad is not None)
 
+    # 9. gradient exchange fused into the optimizer (peeropt.PeerArena + cdr_adam_multi_peer): parameters, shadows and
+    #    gradient buffers in one symmetric arena, every rank updates its chunks from all ranks' gradients and stores
+    #    the result everywhere == GradSync's NCCL all-reduce + the same AdamW on every rank.  Three steps, fused and
+    #    unfused towers (the unfused step leaves its gradients outside the arena -> NCCL + local update), then the
+    #    sharded optimizer state is consolidated and compared as well.
+    import copy
+
+    from cocodr_b200 import optim, peeropt
+
+    def make():
+        m = models.BertDot_InBatch_NLL_LN(hf)
+        m.bert.load_state_dict(bert_ref.synth_state(tiny, 0), strict=False)
+        return m.to(dev).train()
+
+    def run(m, opt, sync, steps):
+        for q_ids, q_mask in steps:
+            opt.zero_grad(set_to_none=True)
+            loss = m(q_ids, q_mask, pi, pm, weights=w)[0]
+            with sync:
+                loss.backward()
+            opt.step()
+        torch.cuda.synchronize()
+
+    def worst(a_, b_):
+        out = (0.0, "")
+        for (n, x), (_, y) in zip(a_.named_parameters(), b_.named_parameters()):
+            if x.grad is None and y.grad is None:
+                continue
+            e = (x - y).abs().max().item() / max(y.abs().max().item(), 1e-3)
+            if e > out[0]:
+                out = (e, n)
+        return out
+
+    steps = [(qi, qm), (qi, qm), (qs, qsm), (qi, qm)]
+    m_ref, m_ref2, m_peer = make(), make(), make()
+    o_ref = optim.AdamW(m_ref.parameters(), lr=1e-3, weight_decay=0.01).attach_shadows(m_ref)
+    o_ref2 = optim.AdamW(m_ref2.parameters(), lr=1e-3, weight_decay=0.01).attach_shadows(m_ref2)
+    o_peer = optim.AdamW(m_peer.parameters(), lr=1e-3, weight_decay=0.01)
+    arena = peeropt.PeerArena(m_peer, o_peer)
+    s_ref, s_ref2, sync_p = GradSync(m_ref), GradSync(m_ref2), GradSync(m_peer, arena=arena)
+    # one step: the update is a smooth function of the gradients -> tight agreement
+    for m_, o_, s_x in ((m_ref, o_ref, s_ref), (m_ref2, o_ref2, s_ref2), (m_peer, o_peer, sync_p)):
+        run(m_, o_, s_x, steps[:1])
+    e1 = worst(m_peer, m_ref)
+    assert e1[0] < 2e-5, ("peer adam, first step", e1)
+    # more steps: Adam's normalised update amplifies the run-to-run noise of the atomically accumulated gradients, so
+    # two runs of the SAME (NCCL) path drift apart; the peer path must stay as close to the reference as that
+    for m_, o_, s_x in ((m_ref, o_ref, s_ref), (m_ref2, o_ref2, s_ref2), (m_peer, o_peer, sync_p)):
+        run(m_, o_, s_x, steps[1:])
+    arena.check()
+    assert sync_p.stats.get("peer", 0) > 0 and sync_p.stats.get("peer_copied", 0) > 0, sync_p.stats
+    e_rr, e_pr = worst(m_ref2, m_ref), worst(m_peer, m_ref)
+    assert e_pr[0] <= 3.0 * e_rr[0] + 1e-5, ("peer adam", e_pr, "reference vs itself", e_rr)
+    ref_p = dict(m_ref.named_parameters())
+    # every rank holds the same parameters and the same fp16 shadows
+    flat_p = torch.cat([p_.detach().reshape(-1) for p_ in m_peer.parameters()])
+    lo_, hi_ = flat_p.clone(), flat_p.clone()
+    dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+    assert torch.equal(lo_, hi_), "parameters differ across ranks"
+    sh_ref, sh_peer = m_ref.bert._shadows[1], m_peer.bert._shadows[1]
+    assert arena.contains(sh_peer.wqkv) and (sh_peer.wqkv.float() - sh_ref.wqkv.float()).abs().max().item() < 1e-3
+    arena.consolidate_state(o_peer)
+    for (n, p_), (_, pr) in zip(m_peer.named_parameters(), m_ref.named_parameters()):
+        if pr.grad is None or not arena.contains(p_.grad):
+            continue
+        a_, b_ = o_peer.state[p_]["exp_avg"], o_ref.state[pr]["exp_avg"]
+        assert (a_ - b_).abs().max().item() <= 1e-7 + 5e-2 * b_.abs().max().item(), ("exp_avg", n)  # (same drift)
+    del copy
+
     dist.barrier()
     if rank == 0:
         print(f"MULTIGPU_OK world={world}")
