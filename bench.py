@@ -303,6 +303,7 @@ def run_ours(args):
     model = models.BertDot_InBatch_NLL_LN(cfg).to(dev).train()
     net = model
     sync = None
+    arena = None
     if world > 1:
         if args.ddp:
             net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[cx.local], find_unused_parameters=True,
@@ -312,6 +313,11 @@ def run_ours(args):
             for p_ in model.parameters():  # identical initial weights on every rank
                 dist.broadcast(p_.data, 0)
             sync = GradSync(model)
+            if not args.torch_adamw and not args.nccl_grads:
+                # gradient exchange inside the optimizer kernel over NVLink peer memory (cocodr_b200.peeropt): the
+                # parameters, shadows and gradient buffers move into one symmetric arena; no NCCL all-reduce runs
+                from cocodr_b200 import peeropt
+                arena = peeropt.PeerArena(model)
     if world > 1 and not args.nccl_gather:
         model.enable_peer_gather(True)  # CLS all-gather / gradient reduce-scatter through peer memory (NVLink stores)
     # N > 1: the NCCL gradient all-reduces and the peer-memory exchange are captured into the same CUDA graph
@@ -335,6 +341,12 @@ def run_ours(args):
     parity = None
     if world > 1 and sync is not None and not args.no_parity:
         parity = _safe("parity", lambda: multi_gpu_parity(cx, model, sync, dev_batches[0], ones))
+        if arena is not None and isinstance(parity, dict) and "error" not in parity:
+            parity["peer_adam"] = _safe("peer_adam", lambda: peer_adam_parity(cx, model, arena, dev_batches[0], ones))
+    if arena is not None:
+        from cocodr_b200.gradsync import GradSync
+        arena.attach(opt)
+        sync = GradSync(model, arena=arena)
 
     def step(ids, mask):
         loss = net(ids[:B], mask[:B], ids[B:], mask[B:], weights=ones)[0]
@@ -420,7 +432,10 @@ def run_ours(args):
         if world > 1:
             par += (" + NCCL all-gather of passage CLS + " if args.nccl_gather else
                     " + passage CLS pushed into every rank's HBM by the last LayerNorm kernel (NVLink peer stores) + ")
-            par += "DDP all-reduce" if args.ddp else "per-layer NCCL all-reduce of flat gradient buffers overlapped with backward"
+            par += ("DDP all-reduce" if args.ddp else
+                    "gradient exchange inside the AdamW kernel over NVLink peer memory (reduce-scatter + sharded update + "
+                    "all-gather in one pass, no NCCL kernel)" if arena is not None else
+                    "per-layer NCCL all-reduce of flat gradient buffers overlapped with backward")
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": warm, "ms_per_step": ms / n_timed, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
@@ -484,6 +499,60 @@ def run_ours(args):
 
 
 # ------------------------------------------------------------------------------------------------ N > 1 parity
+def peer_adam_parity(cx, model, arena, batch, ones):
+    """One optimizer step through the peer-memory path (cdr_adam_multi_peer) vs the NCCL path (GradSync all-reduce +
+    the same AdamW on every rank) from the same weights, batch and dropout masks: max relative parameter difference.
+    (One step only: Adam's normalised update amplifies run-to-run summation noise over several steps.)"""
+    torch, dist = cx.torch, cx.dist
+    from cocodr_b200 import optim as cdr_optim
+    from cocodr_b200.gradsync import GradSync
+    B = ones.shape[0]
+    ids, mask = batch
+    named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+    params = [p for _, p in named]
+    saved = [p.detach().clone() for p in params]
+    # (the key bias has an analytically zero gradient -- softmax is invariant to it -- so Adam normalises pure rounding
+    # noise there and the sign of its update is arbitrary: excluded, as in the gradient comparison above)
+    skip = {i for i, (n, _) in enumerate(named) if "key.bias" in n}
+
+    def one_step(use_peer):
+        with torch.no_grad():
+            for p, s0 in zip(params, saved):
+                p.copy_(s0)
+        opt = cdr_optim.AdamW(params, lr=1e-4, eps=1e-8, weight_decay=0.01, semantics="torch")
+        if use_peer:
+            arena.attach(opt)
+            sync = GradSync(model, arena=arena)
+        else:
+            opt.attach_shadows(model)
+            sync = GradSync(model)
+        model.bert.set_dropout_seed(4321 + cx.rank)
+        opt.zero_grad(set_to_none=True)
+        loss = model(ids[:B], mask[:B], ids[B:], mask[B:], weights=ones)[0]
+        with sync:
+            loss.backward()
+        opt.step()
+        torch.cuda.synchronize()
+        out = {i: p.detach().clone() for i, p in enumerate(params) if p.grad is not None}
+        opt.zero_grad(set_to_none=True)
+        return out
+
+    a = one_step(True)
+    arena.check()
+    b = one_step(False)
+    with torch.no_grad():
+        for p, s0 in zip(params, saved):
+            p.copy_(s0)
+    model.bert.set_dropout_seed(torch.initial_seed() + 977 * cx.rank)
+    worst = max((a[i] - b[i]).abs().max().item() / max(b[i].abs().max().item(), 1e-6) for i in b if i not in skip)
+    upd = max((b[i] - saved[i]).abs().max().item() for i in b)
+    st = torch.tensor([worst], device=cx.dev)
+    dist.all_reduce(st, op=dist.ReduceOp.MAX)
+    return {"param_max_rel_after_one_step": st.item(), "largest_update": upd,
+            "compared": "cdr_adam_multi_peer (gradients read from every rank's arena, sharded update, stores to all "
+                        "ranks) vs NCCL all-reduce + replicated cdr_adam_multi; lr 1e-4, one step, max over ranks"}
+
+
 def multi_gpu_parity(cx, model, sync, batch, ones):
     """One training step's loss and gradients through (a) the peer-memory CLS exchange + GradSync and (b) NCCL
     all-gather / reduce-scatter + an explicit all-reduce of the local gradients; same weights, inputs and dropout masks.
@@ -972,6 +1041,7 @@ def main():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--ddp", action="store_true", help="N > 1: wrap in DistributedDataParallel instead of GradSync")
     ap.add_argument("--torch-adamw", action="store_true", help="use torch.optim.AdamW(fused=True) instead of cdr_adam_multi")
+    ap.add_argument("--nccl-grads", action="store_true", help="N > 1: NCCL all-reduce of the gradients (GradSync) + the same AdamW on every rank instead of the peer-memory optimizer")
     ap.add_argument("--nccl-gather", action="store_true", help="N > 1: NCCL all-gather of the CLS embeddings instead of the fused peer-memory push")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--nccl-ctas", type=int, default=0, help="N > 1: cap NCCL at this many CTAs and leave that many SMs free of persistent kernels (0 = off)")

@@ -81,12 +81,14 @@ class GradSync:
             ev = torch.cuda.Event()
             ev.record(cur)
             self.comm.wait_event(ev)
+            self._comm_used = True
             flat.record_stream(self.comm)
             with torch.cuda.stream(self.comm):
                 self._reduce(flat)
         self._bufs.append(flat)
 
     def __enter__(self):
+        self._comm_used = False
         self._bufs = []
         self._deferred = {}
         ops.GRAD_SYNC = self
@@ -125,11 +127,12 @@ class GradSync:
                 ev = torch.cuda.Event()
                 ev.record(cur)
                 self.comm.wait_event(ev)
+                self._comm_used = True
                 with torch.cuda.stream(self.comm):
                     for g in self._coalesce(rest):
                         g.record_stream(self.comm)
                         self._reduce(g)
-        if self.comm is not None:
+        if self.comm is not None and self._comm_used:  # (nothing to join when every gradient went through the arena)
             torch.cuda.current_stream().wait_stream(self.comm)
         self._bufs = []
         self._deferred = {}

@@ -97,11 +97,20 @@ class PeerArena:
             ops.SHADOW_ALLOC = prev
         self._grad_lo = self._off
         self._flats = {}
+        self.model = model
         if optimizer is not None:
-            optimizer.attach_shadows(model)
-            optimizer.peer = self
+            self.attach(optimizer)
         torch.cuda.synchronize(dev)
         dist.barrier(self.group)  # every rank's flags are zero and its parameters are in place
+
+    def attach(self, optimizer):
+        """Make ``optimizer`` (a cocodr_b200.optim.AdamW over this model's parameters) exchange gradients in its kernel."""
+        from .optim import AdamW
+        if not isinstance(optimizer, AdamW):
+            raise NotImplementedError("PeerArena: only cocodr_b200.optim.AdamW exchanges gradients in its kernel")
+        optimizer.attach_shadows(self.model)
+        optimizer.peer = self
+        return optimizer
 
     # ------------------------------------------------------------------------------------------ allocation
     def _take(self, nbytes):
