@@ -78,3 +78,36 @@ def test_topk_merge_register_sort_sizes(n_in, k):
         order = sorted(range(len(d)), key=lambda t: (-d[t].item(), i[t].item()))[:k]
         exp_i = [i[t].item() for t in order] + [-1] * (k - len(order))
         assert Im[r].cpu().tolist() == exp_i
+
+
+def test_fp16_corpus_keeps_the_fp32_ranking_on_trained_like_embeddings():
+    """IndexFlatIP.add stores fp32 embeddings as fp16 (half the bytes of the HBM-bound scan).  Trained COCO-DR
+    embeddings are a large shared component plus small per-item differences (norm ~14.7, dot products ~217, gaps ~0.3:
+    SURVEY H4 / 8d), the case where that rounding could reorder results.  Against the reference semantics (fp32 inner
+    products, evaluate_beir.py:220-224): the top-k SETS agree except for boundary ties, and two documents may only
+    swap places where their fp32 scores differ by less than 1e-3 relative (SURVEY 8d's criterion)."""
+    from cocodr_b200 import scan
+    g = torch.Generator().manual_seed(3)
+    H, n_docs, n_q, k = 768, 50_000, 64, 100
+    base = torch.randn(H, generator=g) * 14.7 / H ** 0.5
+    P = base[None, :] + 0.015 * torch.randn(n_docs, H, generator=g)
+    Q = base[None, :] + 0.015 * torch.randn(n_q, H, generator=g)
+    index = scan.IndexFlatIP(H)
+    index.add(P.cuda())
+    D, I = index.search(Q.cuda(), k)
+    I = I.cpu().numpy() if torch.is_tensor(I) else np.asarray(I)
+    S = (Q.double() @ P.double().T).numpy()  # reference scores (fp32 inputs, exact accumulation)
+    assert 200 < np.median(S) < 235
+    ref_order = np.argsort(-S, axis=1, kind="stable")[:, :k]
+    recall = np.mean([len(set(I[q]) & set(ref_order[q])) / k for q in range(n_q)])
+    assert recall > 0.97, recall
+    worst = 0.0
+    for q in range(n_q):
+        s = S[q, I[q]]                       # reference scores in OUR order: must be non-increasing up to the tolerance
+        inv = np.maximum.accumulate(s[::-1])[::-1]  # max of everything ranked at or below position i
+        worst = max(worst, float(((inv - s) / np.abs(s)).max()))
+        missing = set(ref_order[q]) - set(I[q])
+        if missing:                          # a missed document must sit within the tolerance of the k-th score
+            kth = S[q, I[q]].min()
+            worst = max(worst, float(max((S[q, d] - kth) / abs(kth) for d in missing)))
+    assert worst < 1e-3, worst
