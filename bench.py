@@ -205,7 +205,7 @@ class Ctx:
                 os.environ["NCCL_MAX_CTAS"] = str(args.nccl_ctas)
                 os.environ["NCCL_MIN_CTAS"] = "1"
             # a mismatched collective must abort within minutes, not hold N GPUs for NCCL's default 10
-            dist.init_process_group("nccl", device_id=self.dev, timeout=datetime.timedelta(seconds=180))
+            dist.init_process_group("nccl", device_id=self.dev, timeout=datetime.timedelta(seconds=90))
         self.peaks = measured_peaks()
 
     def barrier(self):
@@ -558,6 +558,7 @@ def multi_gpu_parity(cx, model, sync, batch, ones):
     all-gather / reduce-scatter + an explicit all-reduce of the local gradients; same weights, inputs and dropout masks.
     Returns the relative disagreement (the checks of tests/dist_worker.py #2 / #5 / #6, here on the benchmarked job)."""
     torch, dist, world = cx.torch, cx.dist, cx.world
+    from cocodr_b200 import ops
     B = PER_GPU_BATCH
     ids, mask = batch
 
@@ -571,6 +572,7 @@ def multi_gpu_parity(cx, model, sync, batch, ones):
                 loss.backward()
         else:
             loss.backward()
+            ops.FWD_CALLS.clear()  # (no GradSync exit on this path: do not leave forward counts behind)
             for p in model.parameters():
                 if p.grad is not None:
                     dist.all_reduce(p.grad)

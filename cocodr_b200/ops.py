@@ -21,7 +21,11 @@ FORCE_SHADOW_REFRESH = False  # set while a CUDA graph is being captured (graph.
 GRAD_SYNC = None              # an active gradsync.GradSync collects the flat gradient buffers of each backward
 CLS_PUSH = None               # (peer.PeerExchange, first_seq): the last LayerNorm pushes CLS rows to every rank (peer.py)
 GROUP_CAPTURE = None          # a GroupCapture: layer backwards also hand over their wgrad operands (dro_loss.py, K11)
-FWD_CALLS = {}                # id(first parameter of a Function) -> forwards since the last GradSync exit (gradsync.py)
+# first parameter of a Function -> forwards since the last GradSync exit (gradsync.py).  Keyed by the parameter OBJECT
+# (weakly): keyed by id(), a stale entry of a deleted model could be inherited by a new parameter that happens to get
+# the same id -- on some ranks only, which changed the order of GradSync's collectives there (an N = 8 hang).
+from torch.utils.weak import WeakIdKeyDictionary as _WeakIdKeyDictionary  # noqa: E402
+FWD_CALLS = _WeakIdKeyDictionary()
 
 
 # Parameter-gradient GEMMs (wgrad) of a layer are independent of the activation-gradient chain.  With WGRAD_OVERLAP they
@@ -61,7 +65,7 @@ def _note_forward(ctx, params):
     Function's needs_input_grad is the signal): GradSync only reduces a layer's flat gradient buffer in place when the
     layer ran exactly once (otherwise autograd accumulates several buffers into one .grad)."""
     if any(ctx.needs_input_grad):
-        k = id(params[0])
+        k = params[0]
         FWD_CALLS[k] = FWD_CALLS.get(k, 0) + 1
     return params
 
@@ -73,14 +77,14 @@ def _grad_flat(ctx, n, dev):
     rank's copy over NVLink instead of a collective."""
     gs = GRAD_SYNC
     arena = getattr(gs, "arena", None) if gs is not None else None
-    if arena is not None and FWD_CALLS.get(id(ctx.params[0]), 1) == 1 and all(p.grad is None for p in ctx.params):
+    if arena is not None and FWD_CALLS.get(ctx.params[0], 1) == 1 and all(p.grad is None for p in ctx.params):
         return arena.flat(ctx.params[0], n, dev)
     return torch.zeros(n, dtype=torch.float32, device=dev)
 
 
 def _submit(ctx, flat):
     if GRAD_SYNC is not None:
-        GRAD_SYNC.submit(flat, ctx.params, FWD_CALLS.get(id(ctx.params[0]), 1))
+        GRAD_SYNC.submit(flat, ctx.params, FWD_CALLS.get(ctx.params[0], 1))
 
 
 # Dropout of one encoder pass: ``state`` = int64 device tensor {seed, offset} (a snapshot taken by the pass, so the
