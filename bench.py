@@ -544,12 +544,14 @@ def peer_adam_parity(cx, model, arena, batch, ones):
         for p, s0 in zip(params, saved):
             p.copy_(s0)
     model.bert.set_dropout_seed(torch.initial_seed() + 977 * cx.rank)
-    worst = max((a[i] - b[i]).abs().max().item() for i in b if i not in skip)
     upd = max((b[i] - saved[i]).abs().max().item() for i in b)
-    st = torch.tensor([worst], device=cx.dev)
+    diffs = torch.cat([(a[i] - b[i]).abs().reshape(-1) for i in b if i not in skip]) / max(upd, 1e-30)
+    # (first Adam step: every element moves by ~lr * sign(g); where the rank-summed gradient is pure cancellation noise
+    # the two summation orders may disagree on the sign, i.e. differ by up to 2 updates -- a handful of elements)
+    st = torch.stack([diffs.max(), diffs.mean(), (diffs > 0.01).float().mean()])
     dist.all_reduce(st, op=dist.ReduceOp.MAX)
-    return {"param_max_abs_diff_after_one_step": st.item(), "largest_update": upd,
-            "diff_in_units_of_the_largest_update": st.item() / max(upd, 1e-30),
+    return {"largest_update": upd, "max_diff_in_updates": st[0].item(), "mean_diff_in_updates": st[1].item(),
+            "fraction_of_elements_off_by_more_than_1pct_of_an_update": st[2].item(),
             "compared": "cdr_adam_multi_peer (gradients read from every rank's arena, sharded update, stores to all "
                         "ranks) vs NCCL all-reduce + replicated cdr_adam_multi; lr 1e-4, one step, max over ranks"}
 
