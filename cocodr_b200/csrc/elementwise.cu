@@ -680,6 +680,7 @@ ln_bwd_staged_kernel(const __half* __restrict__ dy, const __half* __restrict__ x
 // from shared memory once and no value is recomputed (the two-phase kernel above re-reads the tile and re-derives
 // xhat / dx per column thread, which made it issue-bound at half of the HBM rate).  One block of 8 warps per SM, a
 // deeper ring (all the shared memory of the SM in flight), cross-warp reduction of the accumulators once per block.
+// Round 2: per-stage "empty" mbarriers instead of a __syncthreads per tile, arithmetic on packed fp32 pairs.
 constexpr int LNR_THREADS = 256;
 
 template <int VPL, bool DROP>
@@ -689,14 +690,17 @@ ln_bwd_rows_kernel(const __half* __restrict__ dy, const __half* __restrict__ x, 
                    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dcol, int rows, int hidden,
                    float out_scale, __half* __restrict__ dxm, const cdr_dropout drop, int stages) {
   extern __shared__ __align__(128) uint8_t lns_smem[];  // [stage][dy tile | x tile]
-  __shared__ uint64_t full[8];
+  __shared__ uint64_t full[8], empty[8];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nvec = hidden >> 3;
   const uint32_t row_bytes = static_cast<uint32_t>(hidden) * 2u;
   const uint32_t tile_bytes = row_bytes * LNS_ROWS;
   const int n_tiles = (rows + LNS_ROWS - 1) / LNS_ROWS;
   if (tid == 0) {
-    for (int i = 0; i < stages; ++i) mbar_init(&full[i], 1);
+    for (int i = 0; i < stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], LNS_ROWS);  // one arrival per row-owner warp: its row of the stage sits in registers
+    }
     fence_mbar_init();
   }
   __syncthreads();
@@ -715,12 +719,19 @@ ln_bwd_rows_kernel(const __half* __restrict__ dy, const __half* __restrict__ x, 
       const int t = blockIdx.x + i * gridDim.x;
       if (t < n_tiles) issue(t, i);
     }
-  float g[VPL][8], a_dg[VPL][8], a_db[VPL][8], a_dc[VPL][8];
+  // column partial sums and gamma as packed fp32 pairs (FFMA2 / FADD2: half the fp32-pipe instructions)
+  f32x2 g[VPL][4], a_dg[VPL][4], a_db[VPL][4], a_dc[VPL][4];
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
+    float gv[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) g[i][k] = a_dg[i][k] = a_db[i][k] = a_dc[i][k] = 0.f;
-    if (lane + 32 * i < nvec) load8_f(gamma + 8 * (lane + 32 * i), g[i]);
+    for (int k = 0; k < 8; ++k) gv[k] = 0.f;
+    if (lane + 32 * i < nvec) load8_f(gamma + 8 * (lane + 32 * i), gv);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      g[i][k] = pk2(gv[2 * k], gv[2 * k + 1]);
+      a_dg[i][k] = a_db[i][k] = a_dc[i][k] = pk2(0.f);
+    }
   }
   DropCtx dc{};
   if constexpr (DROP) dc = drop_load(drop);
@@ -729,9 +740,20 @@ ln_bwd_rows_kernel(const __half* __restrict__ dy, const __half* __restrict__ x, 
     mean_nx = mean_in[blockIdx.x * LNS_ROWS + warp];
     rstd_nx = rstd_in[blockIdx.x * LNS_ROWS + warp];
   }
-  int stage = 0;
+  // No block-wide barrier in the tile loop: a warp releases its share of a stage (mbarrier arrive) as soon as its row
+  // is in registers, and thread 0 refills the stage of the PREVIOUS tile at the top of its next iteration -- it waits
+  // for rows that were read a whole tile ago, so the warps drift apart instead of meeting after every tile.
+  int stage = 0, it = 0;
   uint32_t phase = 0;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    if (tid == 0 && it > 0) {
+      const int ps = (it - 1) % stages;
+      const int nt = tile + (stages - 1) * gridDim.x;  // (tile - gridDim.x) + stages * gridDim.x
+      if (nt < n_tiles) {
+        mbar_wait(&empty[ps], ((it - 1) / stages) & 1);
+        issue(nt, ps);
+      }
+    }
     const float mean = mean_nx, rstd = rstd_nx;
     {
       const long long nrow = static_cast<long long>(tile + gridDim.x) * LNS_ROWS + warp;
@@ -744,33 +766,45 @@ ln_bwd_rows_kernel(const __half* __restrict__ dy, const __half* __restrict__ x, 
     const __half* dys = reinterpret_cast<const __half*>(lns_smem + stage * 2 * tile_bytes) + warp * hidden;
     const __half* xs = reinterpret_cast<const __half*>(lns_smem + stage * 2 * tile_bytes + tile_bytes) + warp * hidden;
     const int row = tile * LNS_ROWS + warp;
-    if (row < rows) {
-      float xh[VPL][8], d[VPL][8];
-      float s1 = 0.f, s2 = 0.f;
+    const bool live = row < rows;
+    f32x2 xh[VPL][4], d[VPL][4];
+    f32x2 s1p = pk2(0.f), s2p = pk2(0.f);
+    if (live) {
+      const f32x2 nmean = pk2(-mean), rs = pk2(rstd);
 #pragma unroll
       for (int i = 0; i < VPL; ++i)
         if (lane + 32 * i < nvec) {
-          float xv[8];
+          float xv[8], dv[8];
           load8_h(xs + 8 * (lane + 32 * i), xv);
-          load8_h(dys + 8 * (lane + 32 * i), d[i]);
+          load8_h(dys + 8 * (lane + 32 * i), dv);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            xh[i][k] = (xv[k] - mean) * rstd;
-            const float gy = d[i][k] * g[i][k];
-            s1 += gy;
-            s2 = fmaf(gy, xh[i][k], s2);
-            a_dg[i][k] = fmaf(d[i][k], xh[i][k], a_dg[i][k]);
-            a_db[i][k] += d[i][k];
+          for (int k = 0; k < 4; ++k) {
+            xh[i][k] = mul2(add2(pk2(xv[2 * k], xv[2 * k + 1]), nmean), rs);
+            d[i][k] = pk2(dv[2 * k], dv[2 * k + 1]);
+            const f32x2 gy = mul2(d[i][k], g[i][k]);
+            s1p = add2(s1p, gy);
+            s2p = fma2(gy, xh[i][k], s2p);
+            a_dg[i][k] = fma2(d[i][k], xh[i][k], a_dg[i][k]);
+            a_db[i][k] = add2(a_db[i][k], d[i][k]);
           }
         }
-      const float c1 = warp_sum(s1) / hidden;
-      const float c2 = warp_sum(s2) / hidden;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[stage]);  // this warp's row has been read: its share of the stage is free
+    if (live) {
+      float s1a, s1b, s2a, s2b;
+      upk2(s1p, s1a, s1b);
+      upk2(s2p, s2a, s2b);
+      const float c1 = warp_sum(s1a + s1b) / hidden;
+      const float c2 = warp_sum(s2a + s2b) / hidden;
+      const f32x2 nc1 = pk2(-c1), nc2 = pk2(-c2), rs = pk2(rstd);
 #pragma unroll
       for (int i = 0; i < VPL; ++i)
         if (lane + 32 * i < nvec) {
           float o[8];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) o[k] = rstd * (fmaf(d[i][k], g[i][k], -c1) - xh[i][k] * c2);
+          for (int k = 0; k < 4; ++k)  // rstd * (dy * gamma - c1 - xhat * c2)
+            upk2(mul2(rs, fma2(xh[i][k], nc2, fma2(d[i][k], g[i][k], nc1))), o[2 * k], o[2 * k + 1]);
           store8_h(dx + static_cast<long long>(row) * hidden + 8 * (lane + 32 * i), o);
           if constexpr (DROP) {
             const uint32_t keep = drop_keep8(dc, drop_group(dc, row, 8 * (lane + 32 * i), hidden));
@@ -778,24 +812,24 @@ ln_bwd_rows_kernel(const __half* __restrict__ dy, const __half* __restrict__ x, 
             store8_h(dxm + static_cast<long long>(row) * hidden + 8 * (lane + 32 * i), o);
           }
 #pragma unroll
-          for (int k = 0; k < 8; ++k) a_dc[i][k] += o[k];  // DROP: the dropped (and rescaled) gradient
+          for (int k = 0; k < 4; ++k) a_dc[i][k] = add2(a_dc[i][k], pk2(o[2 * k], o[2 * k + 1]));  // DROP: the dropped (and rescaled) gradient
         }
-    }
-    __syncthreads();  // every warp is done with this stage
-    if (tid == 0) {
-      const int nt = tile + stages * gridDim.x;
-      if (nt < n_tiles) issue(nt, stage);
     }
     if (++stage == stages) { stage = 0; phase ^= 1; }
   }
   // ---- block totals: warp partials meet in shared memory (all bulk copies have been consumed), one atomic per column
   float* red = reinterpret_cast<float*>(lns_smem);  // [8 warps][hidden]
-  auto reduce_emit = [&](float (&acc)[VPL][8], float* dst) {
+  auto reduce_emit = [&](f32x2 (&acc)[VPL][4], float* dst) {
     if (dst == nullptr) return;
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < VPL; ++i)
-      if (lane + 32 * i < nvec) store8_f(red + warp * hidden + 8 * (lane + 32 * i), acc[i]);
+      if (lane + 32 * i < nvec) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) upk2(acc[i][k], v[2 * k], v[2 * k + 1]);
+        store8_f(red + warp * hidden + 8 * (lane + 32 * i), v);
+      }
     __syncthreads();
     for (int c = tid; c < hidden; c += LNR_THREADS) {
       float t = 0.f;
