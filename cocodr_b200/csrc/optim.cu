@@ -99,6 +99,7 @@ adam_multi_kernel(const cdr_opt_item* __restrict__ items, const cdr_opt_chunk* _
 }
 
 // ---- AdamW with the data-parallel gradient exchange fused in (cdr_adam_multi_peer, include/cocodr_b200.h)
+__global__ void opt_epoch_inc_kernel(uint32_t* epoch) { epoch[0] += 1u; }
 __global__ void opt_step_epoch_inc_kernel(float* step, uint32_t* epoch) {
   step[0] += 1.f;
   epoch[0] += 1u;
@@ -112,7 +113,30 @@ struct PeerOpt {
   const uint32_t* epoch;
   uint32_t* done;
   uint32_t* err;
+  // mode 0: gradient exchange + update in one pass.  Gradient clipping needs the norm of the REDUCED gradient before
+  // any update, so it splits the pass: mode 1 reduces the owned chunks (mean over ranks written back into this rank's
+  // own gradient buffer), exchanges the partial sums of squares and leaves clip coefficient and norm in clip_out;
+  // mode 2 updates from those local reduced chunks (no peer loads) and stores the result everywhere.
+  int mode;
+  float max_norm;
+  float* sq_local;          // device scratch (zero between calls)
+  float* peer_norm[8];      // [2][8] floats on every rank: partial sums of squares, double-buffered by epoch parity
+  float* clip_out;          // local: [0] = coefficient min(1, max_norm / (norm + 1e-6)), [1] = norm
 };
+
+__device__ __forceinline__ float block_sum_f(float v, float* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float t = 0.f;
+  if (w == 0) {
+    t = lane < (blockDim.x >> 5) ? red[lane] : 0.f;
+    t = warp_sum(t);
+  }
+  __syncthreads();
+  return t;  // valid in warp 0
+}
 
 // bounded spin (a peer that never launches must not hang the GPU): false after ~10 s
 __device__ __forceinline__ bool peer_wait_bounded(const uint32_t* flags, int world, uint32_t epoch) {
@@ -137,24 +161,31 @@ __global__ void __launch_bounds__(256)
 adam_multi_peer_kernel(const cdr_opt_item* __restrict__ items, const cdr_opt_chunk* __restrict__ chunks, int n_chunks,
                        OptHyper h, PeerOpt po) {
   __shared__ int ok;
+  __shared__ float red[8];
   const uint32_t epoch = *reinterpret_cast<const volatile uint32_t*>(po.epoch);
   if (threadIdx.x == 0) {
-    if (blockIdx.x == 0) {
-      // every gradient of this rank was written by kernels that precede this one on the stream
-      __threadfence_system();
-      for (int r = 0; r < po.world; ++r) st_release_sys(po.peer_flag[r] + po.rank, epoch);
+    ok = 1;
+    if (po.mode != 2) {  // (mode 2 reads no peer gradients: nothing to wait for at the start)
+      if (blockIdx.x == 0) {
+        // every gradient of this rank was written by kernels that precede this one on the stream
+        __threadfence_system();
+        for (int r = 0; r < po.world; ++r) st_release_sys(po.peer_flag[r] + po.rank, epoch);
+      }
+      ok = peer_wait_bounded(po.local_flag, po.world, epoch) ? 1 : 0;
+      if (!ok && po.err != nullptr) *po.err = 1u;
     }
-    ok = peer_wait_bounded(po.local_flag, po.world, epoch) ? 1 : 0;
-    if (!ok && po.err != nullptr) *po.err = 1u;
   }
   __syncthreads();
+  float sq = 0.f;
   const int c = blockIdx.x * po.world + po.rank;  // chunks are dealt round-robin to the ranks
   if (ok && c < n_chunks) {
     const cdr_opt_chunk ck = chunks[c];
     const cdr_opt_item it = items[ck.item];
     const long long c_end = ck.start + CDR_OPT_CHUNK < it.n ? ck.start + CDR_OPT_CHUNK : it.n;
     const float lr = h.lr[0], t = h.step[0];
-    const float gs = (h.grad_scale ? h.grad_scale[0] : 1.f) / static_cast<float>(po.world);  // mean over ranks (DDP)
+    const float inv_world = 1.f / static_cast<float>(po.world);
+    // mean over ranks (DDP); in mode 2 the local buffer already holds the mean
+    const float gs = (h.grad_scale ? h.grad_scale[0] : 1.f) * (po.mode == 2 ? 1.f : inv_world);
     const float bc1 = 1.f - powf(h.beta1, t), bc2 = 1.f - powf(h.beta2, t);
     const float rsq_bc2 = rsqrtf(bc2);
     const float step_torch = lr / bc1, step_hf = lr * sqrtf(bc2) / bc1;
@@ -173,11 +204,24 @@ adam_multi_peer_kernel(const cdr_opt_item* __restrict__ items, const cdr_opt_chu
     for (long long i = ck.start + threadIdx.x * 4; i < c_end; i += 256 * 4) {
       if (i + 4 <= c_end && !it.reserved) {
         float p[4], m[4], v[4], g[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int r = 0; r < po.world; ++r) {  // fixed order: every rank would form the same sum
-          float gr[4];
-          ld4(peer_ptr(it.g, po.delta[r]) + i, gr);
+        if (po.mode == 2) {
+          ld4(it.g + i, g);
+        } else {
+          for (int r = 0; r < po.world; ++r) {  // fixed order: every rank would form the same sum
+            float gr[4];
+            ld4(peer_ptr(it.g, po.delta[r]) + i, gr);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) g[k] += gr[k];
+            for (int k = 0; k < 4; ++k) g[k] += gr[k];
+          }
+        }
+        if (po.mode == 1) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            g[k] *= inv_world;
+            sq = fmaf(g[k], g[k], sq);
+          }
+          st4(const_cast<float*>(it.g) + i, g);  // this rank's copy of the chunks it owns now holds the mean
+          continue;
         }
         ld4(it.p + i, p); ld4(it.m + i, m); ld4(it.v + i, v);
 #pragma unroll
@@ -194,7 +238,14 @@ adam_multi_peer_kernel(const cdr_opt_item* __restrict__ items, const cdr_opt_chu
       } else {
         for (long long j = i; j < c_end && j < i + 4; ++j) {
           float gsum = 0.f;
-          for (int r = 0; r < po.world; ++r) gsum += peer_ptr(it.g, po.delta[r])[j];
+          if (po.mode == 2) gsum = it.g[j];
+          else for (int r = 0; r < po.world; ++r) gsum += peer_ptr(it.g, po.delta[r])[j];
+          if (po.mode == 1) {
+            gsum *= inv_world;
+            sq = fmaf(gsum, gsum, sq);
+            const_cast<float*>(it.g)[j] = gsum;
+            continue;
+          }
           float pk = it.p[j], mk = it.m[j], vk = it.v[j];
           update(pk, mk, vk, gsum);
           it.m[j] = mk; it.v[j] = vk;
@@ -212,15 +263,34 @@ adam_multi_peer_kernel(const cdr_opt_item* __restrict__ items, const cdr_opt_chu
   // ---- the last block of the grid tells every peer that this rank's updates have landed (and that it has read all the
   // gradients it needs), then holds the kernel until every peer said the same: afterwards parameters and shadows
   // are complete on this rank and its gradient buffers may be overwritten
+  if (po.mode == 1) {  // this block's share of the squared norm of the reduced gradient
+    const float t = block_sum_f(sq, red);
+    if (threadIdx.x == 0 && t != 0.f) atomicAdd(po.sq_local, t);
+  }
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned int prev = atomicAdd(po.done, 1u);
     if (prev == gridDim.x - 1) {
       __threadfence_system();
+      const int half = static_cast<int>(epoch & 1u) * 8;
+      if (po.mode == 1) {  // partial sum of squares of the chunks this rank owns -> slot `rank` on every rank
+        const float mine = *reinterpret_cast<volatile float*>(po.sq_local);
+        *po.sq_local = 0.f;
+        for (int r = 0; r < po.world; ++r) po.peer_norm[r][half + po.rank] = mine;
+        __threadfence_system();
+      }
       for (int r = 0; r < po.world; ++r) st_release_sys(po.peer_flag[r] + 8 + po.rank, epoch);
       *po.done = 0u;
-      if (!peer_wait_bounded(po.local_flag + 8, po.world, epoch) && po.err != nullptr) *po.err = 1u;
+      const bool arrived = peer_wait_bounded(po.local_flag + 8, po.world, epoch);
+      if (!arrived && po.err != nullptr) *po.err = 1u;
+      if (po.mode == 1) {
+        float total = 0.f;
+        for (int r = 0; r < po.world; ++r) total += reinterpret_cast<volatile float*>(po.peer_norm[po.rank])[half + r];
+        const float n = sqrtf(total);
+        po.clip_out[0] = fminf(1.f, po.max_norm / (n + 1e-6f));
+        po.clip_out[1] = n;
+      }
     }
   }
 }
@@ -338,16 +408,25 @@ int cdr_adam_multi(const cdr_opt_args* a, void* stream) {
   return CDR_OK;
 }
 
-int cdr_adam_multi_peer(const cdr_opt_args* a, const cdr_peer_args* pa, uint32_t* epoch_rw, uint32_t* err, void* stream) {
-  if (int rc = opt_check(a, "cdr_adam_multi_peer")) return rc;
-  if (int rc = peer_check(pa, "cdr_adam_multi_peer")) return rc;
-  CDR_REQUIRE(a->mode == CDR_OPT_ADAMW_TORCH || a->mode == CDR_OPT_ADAMW_HF, "cdr_adam_multi_peer: unknown mode %d", a->mode);
-  CDR_REQUIRE(epoch_rw != nullptr && epoch_rw == pa->epoch, "cdr_adam_multi_peer: epoch_rw must be peers->epoch (it is incremented)");
+static int adam_peer_launch(const cdr_opt_args* a, const cdr_peer_args* pa, uint32_t* epoch_rw, uint32_t* err, int mode,
+                            float max_norm, float* sq_scratch, float* const* peer_norm, float* clip_out, void* stream,
+                            const char* who) {
+  if (int rc = opt_check(a, who)) return rc;
+  if (int rc = peer_check(pa, who)) return rc;
+  CDR_REQUIRE(a->mode == CDR_OPT_ADAMW_TORCH || a->mode == CDR_OPT_ADAMW_HF, "%s: unknown mode %d", who, a->mode);
+  CDR_REQUIRE(epoch_rw != nullptr && epoch_rw == pa->epoch, "%s: epoch_rw must be peers->epoch (it is incremented)", who);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  opt_step_epoch_inc_kernel<<<1, 1, 0, st>>>(a->step, epoch_rw);
+  if (mode == 1) opt_epoch_inc_kernel<<<1, 1, 0, st>>>(epoch_rw);
+  else opt_step_epoch_inc_kernel<<<1, 1, 0, st>>>(a->step, epoch_rw);
   CDR_LAUNCH_CHECK();
   OptHyper h{a->beta1, a->beta2, a->eps, a->weight_decay, a->lr, a->step, a->grad_scale, a->mode};
   PeerOpt po{};
+  po.mode = mode;
+  po.max_norm = max_norm;
+  po.sq_local = sq_scratch;
+  po.clip_out = clip_out;
+  if (peer_norm != nullptr)
+    for (int r = 0; r < pa->world; ++r) po.peer_norm[r] = peer_norm[r];
   po.world = pa->world;
   po.rank = pa->rank;
   for (int r = 0; r < pa->world; ++r) {
@@ -362,6 +441,26 @@ int cdr_adam_multi_peer(const cdr_opt_args* a, const cdr_peer_args* pa, uint32_t
   adam_multi_peer_kernel<<<blocks, 256, 0, st>>>(a->items, a->chunks, a->n_chunks, h, po);
   CDR_LAUNCH_CHECK();
   return CDR_OK;
+}
+
+int cdr_adam_multi_peer(const cdr_opt_args* a, const cdr_peer_args* pa, uint32_t* epoch_rw, uint32_t* err, void* stream) {
+  return adam_peer_launch(a, pa, epoch_rw, err, 0, 0.f, nullptr, nullptr, nullptr, stream, "cdr_adam_multi_peer");
+}
+
+int cdr_grad_reduce_clip_peer(const cdr_opt_args* a, const cdr_peer_args* pa, uint32_t* epoch_rw, float max_norm,
+                              float* sq_scratch, float* const* peer_norm, float* clip_out, uint32_t* err, void* stream) {
+  CDR_REQUIRE(sq_scratch != nullptr && peer_norm != nullptr && clip_out != nullptr && max_norm > 0.f,
+              "cdr_grad_reduce_clip_peer: scratch, norm slots, clip_out and a positive max_norm are required");
+  if (pa != nullptr)
+    for (int r = 0; r < pa->world && r < 8; ++r)
+      CDR_REQUIRE(peer_norm[r] != nullptr, "cdr_grad_reduce_clip_peer: null norm slot pointer %d", r);
+  return adam_peer_launch(a, pa, epoch_rw, err, 1, max_norm, sq_scratch, peer_norm, clip_out, stream,
+                          "cdr_grad_reduce_clip_peer");
+}
+
+int cdr_adam_multi_peer_reduced(const cdr_opt_args* a, const cdr_peer_args* pa, uint32_t* epoch_rw, uint32_t* err,
+                                void* stream) {
+  return adam_peer_launch(a, pa, epoch_rw, err, 2, 0.f, nullptr, nullptr, nullptr, stream, "cdr_adam_multi_peer_reduced");
 }
 
 int cdr_lamb_multi(const cdr_opt_args* a, void* stream) {

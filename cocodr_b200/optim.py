@@ -51,7 +51,9 @@ class _FusedOptimizer(torch.optim.Optimizer):
         self._shadow_sets = []    # ops.ShadowSet objects to re-snapshot after a step
         self._tables = {}         # group index -> dict(key, dev table, pinned host table, max_n, params)
         self._clip = None         # device [3]: sum of squares scratch, coefficient, norm
+        self._scale = None        # device scalar the next step() multiplies into every gradient (clip coefficient)
         self._use_clip = False
+        self._peer_reduced = False  # peer path: clip_grad_norm_ already reduced the owned chunks in place
         self.peer = None          # a peeropt.PeerArena: AdamW.step exchanges the gradients inside cdr_adam_multi_peer
 
     # ------------------------------------------------------------------------------------------ shadows
@@ -164,7 +166,7 @@ class _FusedOptimizer(torch.optim.Optimizer):
         a.beta1, a.beta2 = group["betas"]
         a.eps, a.weight_decay = group["eps"], group["weight_decay"]
         a.lr, a.step = tab["lr"].data_ptr(), tab["step"].data_ptr()
-        a.grad_scale = self._clip[1:].data_ptr() if self._use_clip else 0
+        a.grad_scale = self._scale.data_ptr() if self._use_clip else 0
         a.norms, a.trust = tab["norms"].data_ptr(), tab["trust"].data_ptr()
         return a
 
@@ -185,6 +187,7 @@ class _FusedOptimizer(torch.optim.Optimizer):
 
     def _after_step(self):
         self._use_clip = False
+        self._peer_reduced = False
         for ss in self._shadow_sets:
             ss.mark_fresh()
 
@@ -193,6 +196,8 @@ class _FusedOptimizer(torch.optim.Optimizer):
         """torch.nn.utils.clip_grad_norm_(all parameters of this optimizer, max_norm) without touching the
         gradients: the coefficient stays on the device and is folded into the next step().  Returns the norm
         (device scalar tensor)."""
+        if self.peer is not None:
+            return self._clip_peer(max_norm)
         tabs = [t for t in (self._table(gi, g) for gi, g in enumerate(self.param_groups)) if t is not None]
         if not tabs:
             return None
@@ -208,8 +213,28 @@ class _FusedOptimizer(torch.optim.Optimizer):
         check(lib.cdr_grad_clip_coef(C.c_void_p(self._clip.data_ptr()), C.c_float(max_norm),  # ... -> coefficient
                                      C.c_void_p(self._clip[1:].data_ptr()), C.c_void_p(self._clip[2:].data_ptr()),
                                      stream_ptr()), "cdr_grad_clip_coef")
+        self._scale = self._clip[1:]
         self._use_clip = True
         return self._clip[2]
+
+
+    def _clip_peer(self, max_norm):
+        """clip_grad_norm_ with the peer-memory optimizer: phase 1 of the split pass (peeropt.PeerArena.reduce_clip) --
+        every rank reduces the chunks it owns in place and the partial squared norms are exchanged; step() then runs
+        phase 2 with the coefficient.  One parameter group whose gradients all live in the arena."""
+        if len(self.param_groups) != 1:
+            raise NotImplementedError("peer-memory clipping supports a single parameter group")
+        group = self.param_groups[0]
+        if self._table(0, group, "local") is not None:
+            raise NotImplementedError("peer-memory clipping needs every gradient in the arena")
+        tab = self._table(0, group, "peer")
+        if tab is None:
+            return None
+        self.peer.reduce_clip(self._args(tab, group, getattr(self, "mode", 0)), float(max_norm))
+        self._scale = self.peer.clip  # [coefficient, norm]: _args hands the coefficient to the update as grad_scale
+        self._use_clip = True
+        self._peer_reduced = True
+        return self.peer.clip[1]
 
 
 class AdamW(_FusedOptimizer):
@@ -233,12 +258,12 @@ class AdamW(_FusedOptimizer):
         lib = _lib.load()
         for gi, group in enumerate(self.param_groups):
             if self.peer is not None:
-                if self._use_clip:
-                    raise NotImplementedError("gradient clipping needs the reduced gradients before the update: not "
-                                              "available with the peer-memory optimizer (use GradSync without an arena)")
                 tab = self._table(gi, group, "peer")
                 if tab is not None:
-                    self.peer.adam_step(self._args(tab, group, self.mode))
+                    if self._peer_reduced:  # clip_grad_norm_ ran phase 1: update from the local reduced chunks
+                        self.peer.adam_step_reduced(self._args(tab, group, self.mode))
+                    else:
+                        self.peer.adam_step(self._args(tab, group, self.mode))
                     self._finish(tab)
                 tab = self._table(gi, group, "local")  # gradients outside the arena were all-reduced by GradSync
             else:

@@ -18,8 +18,10 @@ N = 2, the overlapped all-reduce still costs 0.75 of the 0.92 ms it takes alone.
 
 ``exp_avg`` / ``exp_avg_sq`` of chunks a rank does not own stay at their initial zeros: ``consolidate_state`` sums
 them over the ranks (what ``optimizer.state_dict()`` should save), ``shard_state`` re-zeroes the foreign chunks after a
-``load_state_dict``.  Gradient clipping (a global norm BEFORE the update) and Lamb (per-tensor norms) are not
-supported in this mode: use the NCCL path (plain ``GradSync``) for them.  No CPU path.
+``load_state_dict``.  Gradient clipping (``optimizer.clip_grad_norm_``: a global norm BEFORE the update) splits the
+pass in two kernels -- reduce the owned chunks in place + exchange partial squared norms, then update from the local
+reduced chunks; Lamb (per-tensor norms) is not supported in this mode: use the NCCL path (plain ``GradSync``).  No CPU
+path.
 """
 import ctypes as C
 
@@ -71,8 +73,13 @@ class PeerArena:
         self.arena = symm_mem.empty((total,), dtype=torch.uint8, device=dev)
         self.flags = symm_mem.empty((16,), dtype=torch.int32, device=dev)
         self.flags.zero_()
+        self.norms = symm_mem.empty((16,), dtype=torch.float32, device=dev)  # [2][8] partial sums of squares (clipping)
+        self.norms.zero_()
         self._h_arena = symm_mem.rendezvous(self.arena, group=self.group)
         self._h_flags = symm_mem.rendezvous(self.flags, group=self.group)
+        self._h_norms = symm_mem.rendezvous(self.norms, group=self.group)
+        self.sq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.clip = torch.zeros(2, dtype=torch.float32, device=dev)  # coefficient, norm of the reduced gradient
         self.base = self.arena.data_ptr()
         self.total = total
         self.epoch_dev = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -159,6 +166,25 @@ class PeerArena:
         pa = self.peer_args()
         check(_lib.load().cdr_adam_multi_peer(C.byref(opt_args), C.byref(pa), C.c_void_p(self.epoch_dev.data_ptr()),
                                               C.c_void_p(self.err.data_ptr()), stream_ptr()), "cdr_adam_multi_peer")
+        kernels._count(2)
+
+    def reduce_clip(self, opt_args, max_norm):
+        """Phase 1 of the clipped step: reduce the owned chunks in place, exchange the partial squared norms; afterwards
+        ``self.clip`` = (coefficient, norm) on the device."""
+        pa = self.peer_args()
+        slots = (C.c_void_p * 8)(*[self._h_norms.buffer_ptrs[r] if r < self.world else 0 for r in range(8)])
+        check(_lib.load().cdr_grad_reduce_clip_peer(C.byref(opt_args), C.byref(pa), C.c_void_p(self.epoch_dev.data_ptr()),
+                                                    C.c_float(max_norm), C.c_void_p(self.sq.data_ptr()), slots,
+                                                    C.c_void_p(self.clip.data_ptr()), C.c_void_p(self.err.data_ptr()),
+                                                    stream_ptr()), "cdr_grad_reduce_clip_peer")
+        kernels._count(2)
+
+    def adam_step_reduced(self, opt_args):
+        """Phase 2: the update from the locally reduced gradients (opt_args.grad_scale = the clip coefficient)."""
+        pa = self.peer_args()
+        check(_lib.load().cdr_adam_multi_peer_reduced(C.byref(opt_args), C.byref(pa), C.c_void_p(self.epoch_dev.data_ptr()),
+                                                      C.c_void_p(self.err.data_ptr()), stream_ptr()),
+              "cdr_adam_multi_peer_reduced")
         kernels._count(2)
 
     def check(self):

@@ -257,6 +257,18 @@ int cdr_lamb_multi(const cdr_opt_args* args, void* stream);
  * there).  err (optional device uint32) is set to 1 if a peer did not arrive within ~10 s. */
 int cdr_adam_multi_peer(const cdr_opt_args* args, const cdr_peer_args* peers, uint32_t* epoch_rw, uint32_t* err,
                         void* stream);
+/* The same with gradient clipping (torch.nn.utils.clip_grad_norm_ before optimizer.step(), run_ann.py:345-353): the
+ * norm of the REDUCED gradient must exist before any update, so the pass splits in two.
+ * cdr_grad_reduce_clip_peer: every rank reduces the chunks it owns (mean over ranks, written back into ITS OWN gradient
+ * buffer), adds up their squares, publishes that partial sum in slot `rank` of every rank's peer_norm area ([2][8]
+ * floats per rank, double-buffered by epoch parity; peer_norm[r] = rank r's area) and, once all partial sums arrived,
+ * leaves clip_out[0] = min(1, max_norm / (norm + 1e-6)), clip_out[1] = norm.  sq_scratch: one zeroed device float.
+ * cdr_adam_multi_peer_reduced: the update of the owned chunks from those local reduced gradients (args->grad_scale =
+ * clip_out), stored into every rank's arena; same completion semantics as cdr_adam_multi_peer. */
+int cdr_grad_reduce_clip_peer(const cdr_opt_args* args, const cdr_peer_args* peers, uint32_t* epoch_rw, float max_norm,
+                              float* sq_scratch, float* const* peer_norm, float* clip_out, uint32_t* err, void* stream);
+int cdr_adam_multi_peer_reduced(const cdr_opt_args* args, const cdr_peer_args* peers, uint32_t* epoch_rw, uint32_t* err,
+                                void* stream);
 /* torch.nn.utils.clip_grad_norm_ in two steps: sq_accum[0] += sum of g^2 over every gradient of a table (call once
  * per parameter group on a zeroed scalar), then coef[0] = min(1, max_norm / (sqrt(sq[0]) + 1e-6)) and, optionally,
  * norm_out[0] = sqrt(sq[0]).  The coefficient is consumed on the device as cdr_opt_args.grad_scale. */

@@ -250,6 +250,29 @@ def main():
     assert torch.equal(lo_, hi_), "parameters differ across ranks"
     sh_ref, sh_peer = m_ref.bert._shadows[1], m_peer.bert._shadows[1]
     assert arena.contains(sh_peer.wqkv) and (sh_peer.wqkv.float() - sh_ref.wqkv.float()).abs().max().item() < 1e-3
+    # clipped step (torch.nn.utils.clip_grad_norm_ semantics: norm of the rank-averaged gradient): two-phase peer path
+    # vs NCCL all-reduce + cdr_grad_sqnorm_multi / clip coefficient, from identical weights
+    with torch.no_grad():
+        for p_, pr in zip(m_peer.parameters(), m_ref.parameters()):
+            pr.copy_(p_)
+    for st_ in (o_ref.state, o_peer.state):
+        for v_ in st_.values():
+            v_["exp_avg"].zero_()
+            v_["exp_avg_sq"].zero_()
+    norms = []
+    for m_, o_, s_x in ((m_ref, o_ref, s_ref), (m_peer, o_peer, sync_p)):
+        o_.zero_grad(set_to_none=True)
+        loss = m_(qi, qm, pi, pm, weights=w)[0]
+        with s_x:
+            loss.backward()
+        norms.append(o_.clip_grad_norm_(0.01))
+        o_.step()
+    torch.cuda.synchronize()
+    arena.check()
+    n_ref, n_peer = norms[0].item(), norms[1].item()
+    assert n_ref > 0.01 and abs(n_peer - n_ref) <= 1e-4 * n_ref, ("clip norm", n_peer, n_ref)
+    e_clip = worst(m_peer, m_ref)
+    assert e_clip[0] < 5e-5, ("peer adam, clipped step", e_clip)
     arena.consolidate_state(o_peer)
     for (n, p_), (_, pr) in zip(m_peer.named_parameters(), m_ref.named_parameters()):
         if pr.grad is None or not arena.contains(p_.grad):
