@@ -227,6 +227,104 @@ simmat_fused_bwd_kernel(const SimParams p) {
   }
 }
 
+// ---- small problems (the in-batch heads of the training step: 64 x 64 .. 512 x 512 scores): ONE BLOCK PER VECTOR.
+// The tiled kernels above give a 64-row problem 4 blocks that each walk their chunks serially (105 us per launch, 0.19 ms
+// of an 11 ms step); here every query row (forward, dq) or key (dk) gets its own block: warp w forms the dot products
+// with inner vectors w, w + 8, ... (lanes stride the dimension: coalesced 128-byte reads), the block turns them into
+// the loss or into G, and thread d accumulates out[d] = sum_i G_i Y[i][d] over the same inner vectors.  fp32 throughout.
+constexpr int SIMS_THREADS = 256;
+constexpr int SIMS_MAX_INNER = 2048;
+
+// s[i] = <x, Y_i> for i < n_inner (x in shared memory); called by the whole block
+__device__ __forceinline__ void sims_dots(const float* __restrict__ sx, const float* __restrict__ Y, int n_inner, int dim,
+                                          float* __restrict__ s) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = warp; i < n_inner; i += SIMS_THREADS / 32) {
+    const float* y = Y + static_cast<long long>(i) * dim;
+    float acc = 0.f;
+    for (int d = lane; d < dim; d += 32) acc = fmaf(sx[d], __ldg(y + d), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) s[i] = acc;
+  }
+}
+
+__device__ __forceinline__ float sims_block_reduce(float v, float* red, bool is_max) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  v = is_max ? warp_max(v) : warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = red[0];
+#pragma unroll
+  for (int w = 1; w < SIMS_THREADS / 32; ++w) t = is_max ? fmaxf(t, red[w]) : t + red[w];
+  return t;
+}
+
+__global__ void __launch_bounds__(SIMS_THREADS)
+simmat_small_fwd_kernel(const SimParams p, float* __restrict__ loss, float* __restrict__ lse) {
+  extern __shared__ float sims_smem[];
+  float* sx = sims_smem;          // [dim]
+  float* s = sims_smem + p.dim;   // [n_keys]
+  __shared__ float red[SIMS_THREADS / 32];
+  const int row = blockIdx.x, gi = p.row_offset + row;
+  for (int d = threadIdx.x; d < p.dim; d += SIMS_THREADS) sx[d] = p.q[static_cast<long long>(row) * p.dim + d];
+  __syncthreads();
+  sims_dots(sx, p.k, p.n_keys, p.dim, s);
+  __syncthreads();
+  float m = -INFINITY;
+  for (int j = threadIdx.x; j < p.n_keys; j += SIMS_THREADS)
+    if (!(p.mode == CDR_SIM_COCO && j == gi)) m = fmaxf(m, s[j]);
+  m = sims_block_reduce(m, red, true);
+  float l = 0.f;
+  for (int j = threadIdx.x; j < p.n_keys; j += SIMS_THREADS)
+    if (!(p.mode == CDR_SIM_COCO && j == gi)) l += expf(s[j] - m);
+  l = sims_block_reduce(l, red, false);
+  if (threadIdx.x == 0) {
+    const float v = m + logf(l);
+    lse[row] = v;
+    loss[row] = p.loss_scale * (v - s[sim_target(p.mode, gi)]);
+  }
+}
+
+// KEYS_OUTER = false: block = query row, out = dq[row];  true: block = key, out = dk[key]
+template <bool KEYS_OUTER>
+__global__ void __launch_bounds__(SIMS_THREADS)
+simmat_small_bwd_kernel(const SimParams p) {
+  extern __shared__ float sims_smem[];
+  float* sx = sims_smem;          // [dim]
+  float* s = sims_smem + p.dim;   // [n_inner]: scores, then G
+  const int o = blockIdx.x;
+  const float* X = KEYS_OUTER ? p.k : p.q;
+  const float* Y = KEYS_OUTER ? p.q : p.k;
+  const int n_inner = KEYS_OUTER ? p.n_rows : p.n_keys;
+  for (int d = threadIdx.x; d < p.dim; d += SIMS_THREADS) sx[d] = X[static_cast<long long>(o) * p.dim + d];
+  __syncthreads();
+  sims_dots(sx, Y, n_inner, p.dim, s);
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_inner; i += SIMS_THREADS) {
+    const int row = KEYS_OUTER ? i : o, key = KEYS_OUTER ? o : i;
+    const int gi = p.row_offset + row;
+    const float sc = (p.mode == CDR_SIM_COCO && key == gi) ? -INFINITY : s[i];
+    s[i] = __ldg(p.dloss + row) * p.loss_scale * (expf(sc - __ldg(p.lse + row)) - (key == sim_target(p.mode, gi) ? 1.f : 0.f));
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < p.dim; d += SIMS_THREADS) {
+    float a0 = 0.f, a1 = 0.f;
+    int i = 0;
+    for (; i + 1 < n_inner; i += 2) {
+      a0 = fmaf(s[i], __ldg(Y + static_cast<long long>(i) * p.dim + d), a0);
+      a1 = fmaf(s[i + 1], __ldg(Y + static_cast<long long>(i + 1) * p.dim + d), a1);
+    }
+    if (i < n_inner) a0 = fmaf(s[i], __ldg(Y + static_cast<long long>(i) * p.dim + d), a0);
+    p.out[static_cast<long long>(o) * p.dim + d] = a0 + a1;
+  }
+}
+
+static bool sim_small(const cdr_simmat_args* a) {
+  return a->n_rows <= SIMS_MAX_INNER && a->n_keys <= SIMS_MAX_INNER &&
+         static_cast<long long>(a->n_rows) * a->n_keys <= 1024 * 1024;
+}
+
 static int sim_splits(int n_outer, int n_inner) {
   const int tiles = (n_outer + SIM_TO - 1) / SIM_TO;
   const int max_splits = (n_inner + SIM_TI - 1) / SIM_TI;
@@ -498,6 +596,11 @@ int cdr_simmat_ce_fwd(const cdr_simmat_args* a, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SimParams p{};
   sim_params(a, p);
+  if (sim_small(a)) {
+    simmat_small_fwd_kernel<<<a->n_rows, SIMS_THREADS, sizeof(float) * (a->dim + a->n_keys), st>>>(p, a->loss, a->lse);
+    CDR_LAUNCH_CHECK();
+    return CDR_OK;
+  }
   p.n_splits = sim_splits(a->n_rows, a->n_keys);
   p.inner_per_split = ((a->n_keys + p.n_splits - 1) / p.n_splits + SIM_TI - 1) / SIM_TI * SIM_TI;
   p.n_splits = (a->n_keys + p.inner_per_split - 1) / p.inner_per_split;
@@ -537,6 +640,13 @@ int cdr_simmat_ce_bwd(const cdr_simmat_args* a, void* stream) {
     SimParams p{};
     sim_params(a, p);
     p.out = out;
+    if (sim_small(a)) {
+      const size_t sm = sizeof(float) * (a->dim + n_inner);
+      if (pass == 0) simmat_small_bwd_kernel<false><<<n_outer, SIMS_THREADS, sm, st>>>(p);
+      else simmat_small_bwd_kernel<true><<<n_outer, SIMS_THREADS, sm, st>>>(p);
+      CDR_LAUNCH_CHECK();
+      continue;
+    }
     p.n_splits = sim_splits(n_outer, n_inner);
     p.inner_per_split = ((n_inner + p.n_splits - 1) / p.n_splits + SIM_TI - 1) / SIM_TI * SIM_TI;
     p.n_splits = (n_inner + p.inner_per_split - 1) / p.inner_per_split;

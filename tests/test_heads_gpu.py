@@ -138,10 +138,14 @@ def test_gram_tensor_core_path(G, P):
 
 @pytest.mark.parametrize("n_rows,n_keys,dim,mode,off", [(64, 512, 768, "qp", 128), (7, 23, 40, "qp", 5), (37, 130, 96, "qp", 0),
                                                         (512, 512, 1024, "coco", 0), (20, 64, 128, "coco", 16),
-                                                        (3, 6, 8, "coco", 2), (200, 1000, 2048, "qp", 300)])
+                                                        (3, 6, 8, "coco", 2), (200, 1000, 2048, "qp", 300),
+                                                        # > 2^20 scores: the tiled kernels (smaller problems take the
+                                                        # one-block-per-vector kernels)
+                                                        (1100, 1200, 96, "qp", 50), (1024, 2048, 64, "coco", 512)])
 def test_fused_simmat_ragged_shapes(n_rows, n_keys, dim, mode, off):
-    """The fused K9 / K9' kernels (score tiles in registers, online softmax, recomputed in the backward) on shapes that
-    do not divide the 16 x 64 x 32 tiling, with few and many key splits, vs the torch restatement."""
+    """The fused K9 / K9' kernels (scores never written; small problems: one block per vector, large ones: score tiles in
+    registers, online softmax, recomputed in the backward) on shapes that do not divide the tilings, with few and many
+    key splits, vs the torch restatement."""
     from cocodr_b200 import kernels as k
     g = torch.Generator().manual_seed(n_rows * 7 + n_keys)
     K_ = (torch.randn(n_keys, dim, generator=g) * (3.0 / dim ** 0.5)).requires_grad_(True)
