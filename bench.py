@@ -317,7 +317,15 @@ def run_ours(args):
                 # gradient exchange inside the optimizer kernel over NVLink peer memory (cocodr_b200.peeropt): the
                 # parameters, shadows and gradient buffers move into one symmetric arena; no NCCL all-reduce runs
                 from cocodr_b200 import peeropt
-                arena = peeropt.PeerArena(model)
+                try:
+                    arena = peeropt.PeerArena(model)
+                except Exception as e:  # noqa: BLE001  (no symmetric memory on this box: every rank falls back together)
+                    sys.stderr.write(f"[bench] peer-memory optimizer unavailable ({type(e).__name__}: {e}); NCCL gradient path\n")
+                    arena = None
+                ok = torch.tensor([1 if arena is not None else 0], device=dev)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                if int(ok.item()) == 0:
+                    arena = None
     if world > 1 and not args.nccl_gather:
         model.enable_peer_gather(True)  # CLS all-gather / gradient reduce-scatter through peer memory (NVLink stores)
     # N > 1: the NCCL gradient all-reduces and the peer-memory exchange are captured into the same CUDA graph
