@@ -146,49 +146,72 @@ def mine_negatives(I, doc_pid, pos_pid, n_neg, n_sel=None, order=None):
     return neg, cnt, rr
 
 
-def kmeans(X, k, niter=20, init=None, seed=0):
+def kmeans(X, k, niter=20, init=None, seed=0, nredo=1, check_every=10):
     """Lloyd k-means of fp16 rows X [n, dim] (the train-query embeddings) -> (centroids fp32 [k, dim], assign int32 [n]).
 
-    Assignment = nearest centroid in L2 (``argmax_c x.c - |c|^2/2``; the x.c matrix comes from the tcgen05 GEMM
-    against fp16 centroids), update = mean of the members (empty clusters keep their centroid).  ``init`` [k, dim]
-    fixes the starting centroids; otherwise k distinct rows are drawn with ``seed``."""
+    Mirrors ``faiss.Kmeans(dim, k, nredo=5, niter=500).train(q)`` + ``IndexFlatL2(centroids).search(q, 1)`` of
+    ANCE/drivers/run_ann_data_gen.py:340-351: ``nredo`` runs from different random initialisations (k distinct rows drawn
+    with ``seed + redo``), the run with the smallest sum of squared distances wins; ``niter`` Lloyd iterations each,
+    stopping early once the assignment no longer changes (checked every ``check_every`` iterations: one host
+    synchronisation per check).  Assignment = nearest centroid in L2 (``argmax_c x.c - |c|^2/2``; the x.c matrix comes
+    from the tcgen05 GEMM against fp16 centroids), update = mean of the members.  Empty clusters keep their centroid
+    (faiss re-seeds them by splitting a large cluster); faiss is not importable here, so this step is NOT pinned against
+    the reference's outputs.  ``init`` [k, dim] fixes the starting centroids (then nredo must be 1)."""
     if not X.is_cuda or X.dtype != torch.float16:
         raise RuntimeError("cocodr_b200.mining.kmeans needs a CUDA fp16 matrix (no CPU fallback)")
+    if init is not None and nredo != 1:
+        raise ValueError("kmeans: an explicit init and nredo > 1 exclude each other")
     X = X.contiguous()
     n, dim = X.shape
     dev = X.device
-    if init is None:
-        g = torch.Generator(device="cpu").manual_seed(seed)
-        init = X[torch.randperm(n, generator=g)[:k].to(dev)].float()
-    cent = init.to(dev).float().contiguous().clone()
     kp = (k + 63) // 64 * 64
     c16 = torch.zeros(kp, dim, dtype=torch.float16, device=dev)
     scores = torch.empty(n, kp, dtype=torch.float32, device=dev)
-    assign = torch.empty(n, dtype=torch.int32, device=dev)
     sums = torch.empty(k, dim, dtype=torch.float32, device=dev)
     counts = torch.empty(k, dtype=torch.float32, device=dev)
     lib = load()
-    for it in range(niter + 1):
-        K.cast_f32_f16(cent, c16[:k])
-        K.gemm(X, c16, scores, M=n, N=kp, K=dim, epilogue=K.EPI_F32_STORE)
-        half_sq = 0.5 * (c16[:k].float() ** 2).sum(1)
-        check(lib.cdr_kmeans_assign(_p(scores), C.c_int64(kp), _p(half_sq), C.c_int64(n), C.c_int32(k), _p(assign),
-                                    stream_ptr()), "cdr_kmeans_assign")
-        K._count(1)
-        if it == niter:
-            break
-        sums.zero_()
-        counts.zero_()
-        check(lib.cdr_kmeans_accumulate(_p(X), _p(assign), C.c_int64(n), C.c_int32(dim), C.c_int32(k), _p(sums),
-                                        _p(counts), stream_ptr()), "cdr_kmeans_accumulate")
-        K._count(1)
-        nz = counts > 0
-        cent = torch.where(nz[:, None], sums / counts.clamp(min=1.0)[:, None], cent)
-    return cent, assign
+    best = None
+    for redo in range(max(1, nredo)):
+        if init is None:
+            g = torch.Generator(device="cpu").manual_seed(seed + redo)
+            start = X[torch.randperm(n, generator=g)[:k].to(dev)].float()
+        else:
+            start = init
+        cent = start.to(dev).float().contiguous().clone()
+        assign = torch.empty(n, dtype=torch.int32, device=dev)
+        prev = None
+        for it in range(niter + 1):
+            K.cast_f32_f16(cent, c16[:k])
+            K.gemm(X, c16, scores, M=n, N=kp, K=dim, epilogue=K.EPI_F32_STORE)
+            half_sq = 0.5 * (c16[:k].float() ** 2).sum(1)
+            check(lib.cdr_kmeans_assign(_p(scores), C.c_int64(kp), _p(half_sq), C.c_int64(n), C.c_int32(k), _p(assign),
+                                        stream_ptr()), "cdr_kmeans_assign")
+            K._count(1)
+            if it == niter:
+                break
+            if check_every > 0 and it % check_every == check_every - 1:
+                if prev is not None and torch.equal(prev, assign):  # converged: later iterations would change nothing
+                    break
+                prev = assign.clone()
+            sums.zero_()
+            counts.zero_()
+            check(lib.cdr_kmeans_accumulate(_p(X), _p(assign), C.c_int64(n), C.c_int32(dim), C.c_int32(k), _p(sums),
+                                            _p(counts), stream_ptr()), "cdr_kmeans_accumulate")
+            K._count(1)
+            nz = counts > 0
+            cent = torch.where(nz[:, None], sums / counts.clamp(min=1.0)[:, None], cent)
+        if nredo <= 1:
+            return cent, assign
+        # sum of squared distances up to the constant sum |x|^2:  -2 * sum_i (x_i . c_a - |c_a|^2 / 2)
+        a64 = assign.long()
+        obj = -2.0 * (scores.gather(1, a64[:, None]).squeeze(1) - half_sq[a64]).double().sum()
+        if best is None or float(obj) < best[0]:
+            best = (float(obj), cent, assign)
+    return best[1], best[2]
 
 
 def ann_episode(query_emb, query_ids, passage_emb, passage_ids, positive_pid, top_k, n_neg, shuffle_seed=None,
-                n_groups=0, kmeans_iters=20):
+                n_groups=0, kmeans_iters=500, kmeans_redo=5):
     """One ANN data-generation episode on resident embeddings: scan -> (MRR, negatives) [-> group ids].
 
     positive_pid [n_q] int64: positive passage id of every query row.  Returns a dict of CUDA tensors:
@@ -202,5 +225,5 @@ def ann_episode(query_emb, query_ids, passage_emb, passage_ids, positive_pid, to
     neg, cnt, rr = mine_negatives(I, passage_ids, positive_pid, n_neg, order=order)
     out = {"neg": neg, "neg_count": cnt, "rr": rr, "I": I, "D": D}
     if n_groups > 0:
-        out["centroids"], out["group"] = kmeans(query_emb, n_groups, niter=kmeans_iters)
+        out["centroids"], out["group"] = kmeans(query_emb, n_groups, niter=kmeans_iters, nredo=kmeans_redo)
     return out

@@ -149,3 +149,26 @@ def test_encode_trimmed_equals_padded_run():
     a, _ = mining.encode(m, holes, is_query=False, out_dtype=torch.float32, trim=True)
     b_, _ = mining.encode(m, holes, is_query=False, out_dtype=torch.float32, trim=False)
     assert torch.equal(a, b_)
+
+
+def test_kmeans_restarts_keep_the_best_objective():
+    """faiss.Kmeans(nredo=5, niter=500) semantics (run_ann_data_gen.py:340-351): several random initialisations, the
+    smallest sum of squared distances wins; iterations stop once the assignment is stable."""
+    from cocodr_b200 import mining
+    g = torch.Generator().manual_seed(11)
+    k, dim = 8, 64
+    centers = torch.randn(k, dim, generator=g) * 3.0
+    X = (centers[torch.randint(0, k, (4000,), generator=g)] + 0.3 * torch.randn(4000, dim, generator=g)).half().cuda()
+
+    def objective(cent, assign):
+        return ((X.float() - cent[assign.long()]) ** 2).sum().item()
+
+    singles = [objective(*mining.kmeans(X, k, niter=100, seed=s)) for s in range(3)]
+    cent, assign = mining.kmeans(X, k, niter=100, seed=0, nredo=3)
+    best = objective(cent, assign)
+    assert best <= min(singles) * (1 + 1e-4), (best, singles)
+    # the winner is a fixed point: one more assignment against its centroids changes nothing
+    d2 = ((X.float()[:, None, :] - cent[None, :, :]) ** 2).sum(-1)
+    assert (d2.argmin(1).int() == assign).float().mean().item() > 0.999
+    with pytest.raises(ValueError):
+        mining.kmeans(X, k, init=cent, nredo=2)
