@@ -90,6 +90,31 @@ def test_bad_arguments_fail_loudly_without_a_gpu(lib):
                                C.c_float(1.0), C.byref(d), None) == -1
 
 
+def test_round2_entry_points_validate_without_a_gpu(lib):
+    """cdr_attn_dropout_bits_fill and the peer-memory optimizer entry points reject bad arguments before touching the
+    device (no dropout configured / null tables / an epoch pointer that is not the peers' one)."""
+    from cocodr_b200 import _lib, optim, peer
+    a = _lib.AttnArgs()
+    a.n_seq, a.seq_len, a.heads, a.head_dim, a.drop_bits = 2, 32, 2, 64, 32
+    assert lib.cdr_attn_dropout_bits_fill(C.byref(a), None) == -1 and b"dropout" in lib.cdr_last_error()
+    assert lib.cdr_attn_dropout_bits_fill(None, None) == -1
+    a.drop.state, a.drop.threshold, a.drop_bits = 16, 6554, 24  # misaligned bit buffer
+    assert lib.cdr_attn_dropout_bits_fill(C.byref(a), None) == -1 and b"aligned" in lib.cdr_last_error()
+    o = optim.OptArgs()
+    pa = peer.PeerArgs()
+    assert lib.cdr_adam_multi_peer(C.byref(o), C.byref(pa), None, None, None) == -1  # empty table
+    o.items, o.chunks, o.count, o.n_chunks, o.lr, o.step, o.mode = 16, 16, 1, 1, 16, 16, 0
+    assert lib.cdr_adam_multi_peer(C.byref(o), C.byref(pa), None, None, None) == -1 and b"world" in lib.cdr_last_error()
+    pa.world, pa.rank, pa.epoch, pa.done_counter = 2, 0, 64, 16
+    for r in range(2):
+        pa.peer_buf[r], pa.peer_flag[r] = 4096 * (r + 1), 256 * (r + 1)
+    assert lib.cdr_adam_multi_peer(C.byref(o), C.byref(pa), C.c_void_p(128), None, None) == -1
+    assert b"epoch" in lib.cdr_last_error()
+    assert lib.cdr_grad_reduce_clip_peer(C.byref(o), C.byref(pa), C.c_void_p(64), C.c_float(1.0), None, None, None, None,
+                                         None) == -1 and b"scratch" in lib.cdr_last_error()
+    assert lib.cdr_adam_multi_peer_reduced(C.byref(o), None, C.c_void_p(64), None, None) == -1
+
+
 def test_ctypes_structs_match_the_c_header(tmp_path):
     """Every args struct crossing the C ABI: sizeof and every field offset of the ctypes mirror == what gcc lays out
     from include/cocodr_b200.h (a silent mismatch would shift pointers, not fail)."""
