@@ -22,7 +22,7 @@ CDR_EOVERFLOW = -5
 class Dropout(C.Structure):
     """cdr_dropout: counter-based dropout descriptor (state = device {seed, offset})."""
     _fields_ = [("state", C.c_void_p), ("site", C.c_uint32), ("threshold", C.c_uint32), ("scale", C.c_float),
-                ("row_mul", C.c_int32)]
+                ("row_mul", C.c_int32), ("keep_bits", C.c_void_p)]
 
 
 class AttnArgs(C.Structure):

@@ -21,6 +21,7 @@ struct DropCtx {
   uint32_t site, thr;
   float scale;
   int row_mul;
+  uint8_t* keep_bits;  // optional [rows, cols / 8] stored masks (GEMM epilogue -> LayerNorm backward)
 };
 
 // state = device [seed, offset]; must be read after pdl_wait() (a preceding kernel of the stream may have written it)
@@ -35,6 +36,7 @@ __device__ __forceinline__ DropCtx drop_load(const cdr_dropout& d) {
   c.thr = d.threshold;
   c.scale = d.scale;
   c.row_mul = d.row_mul > 0 ? d.row_mul : 1;
+  c.keep_bits = static_cast<uint8_t*>(d.keep_bits);
   return c;
 }
 

@@ -769,6 +769,16 @@ ln_bwd_rows_kernel(const __half* __restrict__ dy, const __half* __restrict__ x, 
     const bool live = row < rows;
     f32x2 xh[VPL][4], d[VPL][4];
     f32x2 s1p = pk2(0.f), s2p = pk2(0.f);
+    uint32_t kb[VPL];  // DROP with stored masks (written by the forward GEMM epilogue): one byte per 8 elements
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) kb[i] = 0u;
+    if constexpr (DROP) {
+      if (live && dc.keep_bits != nullptr) {
+#pragma unroll
+        for (int i = 0; i < VPL; ++i)
+          if (lane + 32 * i < nvec) kb[i] = __ldg(dc.keep_bits + static_cast<long long>(row) * nvec + lane + 32 * i);
+      }
+    }
     if (live) {
       const f32x2 nmean = pk2(-mean), rs = pk2(rstd);
 #pragma unroll
@@ -807,7 +817,8 @@ ln_bwd_rows_kernel(const __half* __restrict__ dy, const __half* __restrict__ x, 
             upk2(mul2(rs, fma2(xh[i][k], nc2, fma2(d[i][k], g[i][k], nc1))), o[2 * k], o[2 * k + 1]);
           store8_h(dx + static_cast<long long>(row) * hidden + 8 * (lane + 32 * i), o);
           if constexpr (DROP) {
-            const uint32_t keep = drop_keep8(dc, drop_group(dc, row, 8 * (lane + 32 * i), hidden));
+            const uint32_t keep = dc.keep_bits != nullptr ? kb[i]
+                                                          : drop_keep8(dc, drop_group(dc, row, 8 * (lane + 32 * i), hidden));
             drop_apply8(dc, keep, o);
             store8_h(dxm + static_cast<long long>(row) * hidden + 8 * (lane + 32 * i), o);
           }

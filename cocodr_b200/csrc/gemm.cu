@@ -185,6 +185,8 @@ extern "C" int cdr_gemm(const cdr_gemm_args* g, void* stream) {
                 "cdr_gemm: CDR_EPI_BIAS_DROP_RESIDUAL needs drop.state and 0 < drop.threshold < 65536");
     CDR_REQUIRE(g->M * (g->drop.row_mul > 0 ? g->drop.row_mul : 1) * (g->N / 8) < (1ll << 32),
                 "cdr_gemm: dropout group index overflows 32 bits");
+    CDR_REQUIRE(g->drop.keep_bits == nullptr || (g->N % 32 == 0 && (reinterpret_cast<uintptr_t>(g->drop.keep_bits) & 3) == 0),
+                "cdr_gemm: drop.keep_bits needs N %% 32 == 0 and a 4-byte aligned buffer");
   }
   if (g->epilogue == CDR_EPI_BIAS_RESIDUAL || g->epilogue == CDR_EPI_DGELU || g->epilogue == CDR_EPI_BIAS_DROP_RESIDUAL) {
     CDR_REQUIRE(g->aux != nullptr && g->ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(g->aux) & 15) == 0,

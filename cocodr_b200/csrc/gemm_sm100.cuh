@@ -148,7 +148,8 @@ __device__ __forceinline__ float4* stg_piece(float* stg, int r, int j) {
 // 8 consecutive columns [n, n+8) of row m; v = raw accumulators
 template <int EPI>
 __device__ __forceinline__ void gemm_epilogue_apply(const GemmParams& p, float (&v)[8], int m, int n,
-                                                    const float (&bias)[8], const uint4& auxq, const DropCtx& dc) {
+                                                    const float (&bias)[8], const uint4& auxq, const DropCtx& dc,
+                                                    uint32_t keep = 0xffu) {
   if constexpr (EPI == CDR_EPI_SCAN_FILTER) {
     // rows = documents, columns = queries; bias[] holds the admission thresholds of the 8 queries
 #pragma unroll
@@ -183,7 +184,6 @@ __device__ __forceinline__ void gemm_epilogue_apply(const GemmParams& p, float (
       for (int t = 0; t < 4; ++t) w[t] = fma2(pk2(v[2 * t], v[2 * t + 1]), al, pk2(bias[2 * t], bias[2 * t + 1]));
     }
     if constexpr (EPI == CDR_EPI_BIAS_DROP_RESIDUAL) {  // HF BertSelfOutput / BertOutput: LN(x + dropout(dense(h)))
-      const uint32_t keep = drop_keep8(dc, drop_group(dc, m, n, p.N));
 #pragma unroll
       for (int t = 0; t < 4; ++t)
         w[t] = mul2(w[t], pk2(((keep >> (2 * t)) & 1u) ? dc.scale : 0.f, ((keep >> (2 * t + 1)) & 1u) ? dc.scale : 0.f));
@@ -378,8 +378,21 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const u
       hi = *stg_piece(stg, r, 2 * seg + 1);
     }
     float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    uint32_t keep = 0xffu;
+    if constexpr (EPI == CDR_EPI_BIAS_DROP_RESIDUAL) {
+      keep = (col_ok && m < p.M) ? drop_keep8(dc, drop_group(dc, m, n, p.N)) : 0u;
+      if (dc.keep_bits != nullptr) {
+        // the 4 lanes of a row hold the keep bytes of 32 consecutive columns: one 4-byte store per row (all lanes
+        // shuffle; N % 32 == 0 is checked by the host, so a row's 4 bytes are all valid or all out of range)
+        uint32_t b = keep;
+        b |= __shfl_down_sync(0xffffffffu, b, 1) << 8;
+        b |= __shfl_down_sync(0xffffffffu, b, 2) << 16;
+        if (seg == 0 && col_ok && m < p.M)
+          *reinterpret_cast<uint32_t*>(dc.keep_bits + static_cast<long long>(m) * (p.N >> 3) + (n >> 3)) = b;
+      }
+    }
     if (col_ok && m < p.M) {
-      gemm_epilogue_apply<EPI>(p, v, m, n, bias, auxq[i], dc);
+      gemm_epilogue_apply<EPI>(p, v, m, n, bias, auxq[i], dc, keep);
       if constexpr (EPI == CDR_EPI_DGELU) {
 #pragma unroll
         for (int t = 0; t < 8; ++t) csum[t] += v[t];

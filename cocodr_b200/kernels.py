@@ -38,14 +38,19 @@ def _run(name, call):
     check(rc, name)
 
 
-def drop_args(state, site, p, row_mul=1):
-    """cdr_dropout descriptor: ``state`` = int64 device tensor {seed, offset}; keep iff u16 >= round(p * 65536)."""
+def drop_args(state, site, p, row_mul=1, keep_bits=None):
+    """cdr_dropout descriptor: ``state`` = int64 device tensor {seed, offset}; keep iff u16 >= round(p * 65536).
+    ``keep_bits`` (uint8 [rows * cols / 8]): the dropout GEMM epilogue stores its masks there and cdr_ln_bwd_drop reads
+    them back instead of regenerating them."""
     assert state.is_cuda and state.dtype == torch.int64 and state.numel() == 2 and state.is_contiguous()
     assert 0.0 < p < 1.0
     d = _lib.Dropout()
     d.state, d.site, d.threshold, d.scale, d.row_mul = state.data_ptr(), site, int(round(p * 65536.0)), 1.0 / (1.0 - p), row_mul
     assert 0 < d.threshold < 65536
-    d._keepalive = state  # the descriptor only carries a raw pointer: the tensor must outlive every launch that uses it
+    if keep_bits is not None:
+        assert keep_bits.is_cuda and keep_bits.dtype == torch.uint8 and keep_bits.is_contiguous()
+        d.keep_bits = keep_bits.data_ptr()
+    d._keepalive = (state, keep_bits)  # the descriptor only carries raw pointers: the tensors must outlive every launch
     return d
 
 

@@ -100,6 +100,7 @@ DropSpec = namedtuple("DropSpec", "state p_hidden p_attn attn_bits", defaults=(N
 # share the SMs with the tensor-core GEMMs (whose fp32 / integer pipes are mostly idle) instead of standing between the
 # QKV projection and the attention kernel of every layer.  CDR_ATTN_BITS_PREFILL=0 keeps the generator in cdr_attn_fwd.
 ATTN_BITS_PREFILL = _os.environ.get("CDR_ATTN_BITS_PREFILL", "1") != "0"
+STORE_DENSE_MASKS = _os.environ.get("CDR_STORE_DENSE_MASKS", "1") != "0"  # cdr_dropout.keep_bits for the dense outputs
 _BITS_STREAMS = {}
 
 
@@ -130,15 +131,16 @@ def _attn_bits(drop, layer_index, n_seq, heads, L, dev):
     return K.attn_dropout_bits(n_seq, heads, L, dev), False
 
 
-def _site(drop, layer_index, which, row_mul=1):
+def _site(drop, layer_index, which, row_mul=1, keep_bits=None):
     """cdr_dropout descriptor of site ``which`` (1 attention probs, 2 attention-output dense, 3 FFN-output dense, 0 with
-    layer_index 0 = embeddings), or None when that dropout is off."""
+    layer_index 0 = embeddings), or None when that dropout is off.  ``keep_bits``: buffer the dropout GEMM epilogue
+    stores its masks in for the LayerNorm backward of the same site."""
     if drop is None:
         return None
     p = drop.p_attn if which == 1 else drop.p_hidden
     if p <= 0.0:
         return None
-    return K.drop_args(drop.state, 4 * layer_index + which, p, row_mul)
+    return K.drop_args(drop.state, 4 * layer_index + which, p, row_mul, keep_bits)
 
 
 def _ln_bwd_after_dropout(dy, dcls, y, gamma, mean, rstd, dgamma, dbeta, dbias, *, n_seq, seq_len, S, site, row_ws=None):
@@ -365,7 +367,14 @@ class BertLayerFn(torch.autograd.Function):
         dev = x.device
         sh = shadow.refresh(wq, bq, wk, bk, wv, bv, wo, wi, wo2)
         x = x.contiguous()
-        da, db, dc = (_site(drop, layer_index, w) for w in (1, 2, 3))
+        da = _site(drop, layer_index, 1)
+        # the masks of the two dense-output dropouts are stored by their GEMM epilogues (one bit per element, 1.5 MB per
+        # site at 16 384 x 768) and read back by the LayerNorm backward instead of 3 Philox calls per row and lane
+        keep_b = keep_c = None
+        if drop is not None and drop.p_hidden > 0.0 and H % 32 == 0 and STORE_DENSE_MASKS:
+            keep_b = torch.empty(T * (H // 8), dtype=torch.uint8, device=dev)
+            keep_c = torch.empty(T * (H // 8), dtype=torch.uint8, device=dev)
+        db, dc = _site(drop, layer_index, 2, keep_bits=keep_b), _site(drop, layer_index, 3, keep_bits=keep_c)
         qkv = _f16(T, 3 * H, dev=dev)
         K.gemm(x, sh.wqkv, qkv, M=T, N=3 * H, K=H, bias=sh.bqkv)
         att = _f16(T, H, dev=dev)

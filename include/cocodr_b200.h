@@ -54,6 +54,10 @@ typedef struct cdr_dropout {
   uint32_t threshold;    /* 0 .. 65535 */
   float scale;
   int32_t row_mul;       /* >= 1 (0 is read as 1) */
+  void* keep_bits;       /* optional device [rows, cols / 8] bytes (cols % 32 == 0), bit j of byte (m, n / 8) = element
+                            (m, 8 (n / 8) + j) is kept: written by the CDR_EPI_BIAS_DROP_RESIDUAL GEMM epilogue next to
+                            its output and read by cdr_ln_bwd_drop instead of regenerating the masks (3 Philox calls per
+                            row and lane in a latency-bound kernel); NULL = regenerate.  Other entry points ignore it */
 } cdr_dropout;
 /* out[m, :] = dropout(x[m, :]) on a contiguous fp16 [rows, cols] tensor (cols % 8 == 0); out may alias x. */
 int cdr_dropout_f16(const void* x, void* out, int64_t rows, int32_t cols, const cdr_dropout* drop, void* stream);
