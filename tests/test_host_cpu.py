@@ -150,3 +150,30 @@ def test_plan_buckets_covers_all_sequences_within_the_token_budget():
             assert b > a and L % 16 == 0 or L == hi
             assert L >= lens[b - 1] and (L - lens[b - 1] < 16 or L == hi)
             assert (b - a) * L <= budget or b - a == 1
+
+
+def test_forward_counts_do_not_outlive_their_parameters():
+    """GradSync decides per layer whether its flat gradient buffer may be all-reduced in place from the number of
+    forwards since the last exit (ops.FWD_CALLS).  The counts are keyed WEAKLY by the parameter object: keyed by id(), a
+    deleted model's stale entry was inherited by a new parameter that happened to reuse the id -- on one rank of eight
+    only, which changed the order of that rank's collectives (round-2 N = 8 hang)."""
+    import gc
+    import torch
+    from cocodr_b200 import ops
+
+    class Ctx:
+        needs_input_grad = (True,)
+
+    ops.FWD_CALLS.clear()
+    p = torch.nn.Parameter(torch.zeros(4))
+    ops._note_forward(Ctx(), (p,))
+    ops._note_forward(Ctx(), (p,))
+    assert ops.FWD_CALLS.get(p, 1) == 2 and len(ops.FWD_CALLS) == 1
+    del p
+    gc.collect()
+    assert len(ops.FWD_CALLS) == 0  # the entry died with the parameter: nothing for a recycled id to inherit
+    q = torch.nn.Parameter(torch.zeros(4))
+    assert ops.FWD_CALLS.get(q, 1) == 1
+    Ctx.needs_input_grad = (False,)
+    ops._note_forward(Ctx(), (q,))  # forwards autograd does not record (no_grad) are not counted
+    assert len(ops.FWD_CALLS) == 0
